@@ -1,0 +1,188 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):   python -m oracle.gen_golden [--only NAME]
+
+Inputs are regenerated from seeds by `pytracking_b200.synth` in the tests, so the fixtures only hold
+the reference's OUTPUTS (plus tiny inputs where convenient).  The reference code paths exercised:
+  corr      ltr/models/layers/filter.py: apply_filter, apply_feat_transpose (eval -> _v2), pytracking/libs/dcf.py: max2d
+  labels    ltr/models/layers/distance.py DistanceMap + the three 1x1 predictors (optimizer.py:111-119)
+  dimp_sd   ltr/models/target_classifier/optimizer.py DiMPSteepestDescentGN.forward
+  prdimp_sd ltr/models/target_classifier/optimizer.py PrDiMPSteepestDescentNewton.forward
+  backbone  ltr/models/backbone/resnet.py ResNet.forward + classifier.feature_extractor (dimpnet50 / dimpnet18)
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shims  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def gen_corr():
+    import ltr.models.layers.filter as filter_layer
+    from pytracking import dcf
+    from pytracking_b200 import synth
+    out = {}
+    for tag, (n, c, h, k) in {"a": (3, 32, 18, 4), "b": (2, 64, 22, 4), "c": (2, 32, 18, 1), "d": (2, 32, 13, 3)}.items():
+        feat = synth.make_clf_features(100 + ord(tag), n, c, h, h, filter_size=max(k, 1))
+        g = torch.Generator().manual_seed(200 + ord(tag))
+        w = torch.randn(1, c, k, k, generator=g) * 0.5
+        s = filter_layer.apply_filter(feat.unsqueeze(1), w)            # (images, sequences=1, Ho, Wo)
+        r = torch.randn(s.shape, generator=g)
+        gt = filter_layer.apply_feat_transpose(feat.unsqueeze(1), r, (k, k), training=False)
+        gt3 = filter_layer.apply_feat_transpose(feat.unsqueeze(1), r, (k, k), training=True)
+        assert torch.allclose(gt, gt3, rtol=1e-4, atol=1e-5), "v2 vs v3 adjoint differ"
+        mv, mi = dcf.max2d(s.squeeze(1))
+        out.update({tag + "_w": _np(w), tag + "_scores": _np(s), tag + "_r": _np(r), tag + "_grad": _np(gt),
+                    tag + "_maxval": _np(mv), tag + "_maxidx": _np(mi)})
+    np.savez_compressed(os.path.join(GOLDEN, "corr.npz"), **out)
+
+
+def _ref_dimp_optimizer(lut_seed):
+    from ltr.models.target_classifier.optimizer import DiMPSteepestDescentGN
+    from pytracking_b200 import synth
+    opt = DiMPSteepestDescentGN(num_iter=5, feat_stride=16, init_step_length=0.9, init_filter_reg=0.1,
+                                init_gauss_sigma=0.9, num_dist_bins=100, bin_displacement=0.1,
+                                mask_init_factor=3.0, score_act='relu', mask_act='sigmoid')
+    p = synth.make_dimp_optimizer_params(seed=lut_seed)
+    missing = opt.load_state_dict(p, strict=True)
+    opt.eval()
+    return opt, p
+
+
+def gen_labels():
+    from pytracking_b200 import synth
+    opt, p = _ref_dimp_optimizer(lut_seed=5)
+    bb = synth.make_boxes(11, 6)
+    bb[4] = torch.tensor([-40.0, 300.0, 30.0, 20.0])   # centre far outside the map -> last-bin clamp
+    bb[5] = torch.tensor([136.0, 136.0, 16.0, 16.0])   # centre exactly on a cell
+    with torch.no_grad():
+        center = ((bb[..., :2] + bb[..., 2:] / 2) / 16).reshape(-1, 2).flip((1,))
+        dm = opt.distance_map(center, (19, 19))
+        y = opt.label_map_predictor(dm)[:, 0]
+        m = opt.target_mask_predictor(dm)[:, 0]
+        v = opt.spatial_weight_predictor(dm)[:, 0]
+    np.savez_compressed(os.path.join(GOLDEN, "labels.npz"), bb=_np(bb), y=_np(y), m=_np(m), v=_np(v))
+
+
+def gen_dimp_sd():
+    from pytracking_b200 import synth
+    out = {}
+    cases = {"n15_it10": (15, 512, 18, 10, True, 21), "n50_it2": (50, 512, 18, 2, True, 22),
+             "n4_c64": (4, 64, 18, 3, False, 23), "n7_22": (7, 128, 22, 4, True, 24)}
+    for tag, (n, c, h, it, use_sw, seed) in cases.items():
+        opt, p = _ref_dimp_optimizer(lut_seed=seed)
+        feat = synth.make_clf_features(seed, n, c, h, h)
+        bb = synth.make_boxes(seed + 1, n, center=(h * 16) / 2 - 25)
+        g = torch.Generator().manual_seed(seed + 2)
+        w0 = torch.randn(1, c, 4, 4, generator=g) * 0.02 if tag != "n15_it10" else torch.zeros(1, c, 4, 4)
+        sw = None
+        if use_sw:
+            sw = torch.rand(n, generator=g) + 0.1
+            sw = sw / sw.sum()
+        with torch.no_grad():
+            wf, its, losses = opt(w0, feat=feat.unsqueeze(1), bb=bb.unsqueeze(1),
+                                  sample_weight=None if sw is None else sw.reshape(n, 1), num_iter=it,
+                                  compute_losses=True)
+        out[tag + "_w0"] = _np(w0)
+        out[tag + "_sw"] = _np(sw) if sw is not None else np.zeros(0, np.float32)
+        out[tag + "_wfinal"] = _np(wf)
+        out[tag + "_w1"] = _np(its[1])
+        out[tag + "_losses"] = np.array([float(l) for l in losses], dtype=np.float64)
+        print(tag, "losses", [round(float(l), 5) for l in losses])
+    np.savez_compressed(os.path.join(GOLDEN, "dimp_sd.npz"), **out)
+
+
+def gen_prdimp_sd():
+    from ltr.models.target_classifier.optimizer import PrDiMPSteepestDescentNewton
+    from pytracking_b200 import synth
+    out = {}
+    # hyper-parameters: ltr/train_settings/dimp/prdimp50.py:95-98 (optim_init_reg=0.05, gauss_sigma=output_sigma*feature_sz,
+    # alpha_eps=0.05, normalize_label=True) + pytracking/parameter/dimp/prdimp50.py (softmax_reg etc. overwritten at run time)
+    cases = {"n15_22": (15, 512, 22, 10, 31, None, 0.0), "n6_18": (6, 64, 18, 3, 32, -2.0, 0.05)}
+    for tag, (n, c, h, it, seed, sreg, lthr) in cases.items():
+        sigma = (1 / 4 / 6.0) * h   # output_sigma_factor/search_area_factor * feature_sz (train_settings/dimp/prdimp50.py:20-25)
+        opt = PrDiMPSteepestDescentNewton(num_iter=5, feat_stride=16, init_step_length=1.0, init_filter_reg=0.05,
+                                          gauss_sigma=sigma, min_filter_reg=0.05, alpha_eps=0.05,
+                                          normalize_label=True, softmax_reg=sreg, label_threshold=lthr,
+                                          label_shrink=0.0 if sreg is None else 0.1)
+        opt.eval()
+        feat = synth.make_clf_features(seed, n, c, h, h)
+        bb = synth.make_boxes(seed + 1, n, center=(h * 16) / 2 - 25)
+        g = torch.Generator().manual_seed(seed + 2)
+        w0 = torch.randn(1, c, 4, 4, generator=g) * 0.02
+        sw = torch.rand(n, generator=g) + 0.1
+        sw = sw / sw.sum()
+        with torch.no_grad():
+            wf, its, losses = opt(w0, feat=feat.unsqueeze(1), bb=bb.unsqueeze(1), sample_weight=sw.reshape(n, 1),
+                                  num_iter=it, compute_losses=True)
+        out[tag + "_w0"] = _np(w0)
+        out[tag + "_sw"] = _np(sw)
+        out[tag + "_wfinal"] = _np(wf)
+        out[tag + "_w1"] = _np(its[1])
+        out[tag + "_losses"] = np.array([float(l) for l in losses], dtype=np.float64)
+        out[tag + "_sigma"] = np.array(sigma)
+        print(tag, "losses", [round(float(l), 5) for l in losses])
+    np.savez_compressed(os.path.join(GOLDEN, "prdimp_sd.npz"), **out)
+
+
+def gen_backbone():
+    from ltr.models.tracking import dimpnet
+    from oracle import dimp_oracle
+    from pytracking_b200 import synth
+    out = {}
+    common = dict(filter_size=4, backbone_pretrained=False, optim_iter=5, clf_feat_norm=True, final_conv=True,
+                  optim_init_step=0.9, optim_init_reg=0.1, init_gauss_sigma=0.9, num_dist_bins=100,
+                  bin_displacement=0.1, mask_init_factor=3.0, target_mask_act='sigmoid', score_act='relu')
+    for arch, ctor, kw in (("resnet50", dimpnet.dimpnet50, dict(clf_feat_blocks=0, out_feature_dim=512)),
+                           ("resnet18", dimpnet.dimpnet18, dict(clf_feat_blocks=1, out_feature_dim=256))):
+        net = ctor(**common, **kw)
+        sd = synth.make_dimp_state_dict(arch, seed=0, lut_seed=3)
+        res = net.load_state_dict(sd, strict=False)
+        bad = [k for k in res.missing_keys if not (k.startswith("bb_regressor") or "layer4" in k or ".fc." in k)]
+        assert not bad and not res.unexpected_keys, (bad, res.unexpected_keys)
+        net.eval()
+        for size, seed in ((288, 41), (96, 42)):
+            im = dimp_oracle.preprocess_image(synth.make_crop(seed, 1, size))
+            with torch.no_grad():
+                bf = net.extract_backbone_features(im)           # OrderedDict layer2, layer3
+                clf = net.extract_classification_feat(bf)
+            tag = "%s_%d_" % (arch, size)
+            l2 = bf["layer2"]
+            out[tag + "layer2"] = _np(l2 if size == 96 else l2[:, ::8])   # full map is 2.6 MB; keep every 8th channel
+            out[tag + "layer3"] = _np(bf["layer3"])
+            out[tag + "clf"] = _np(clf)
+            print(tag, "layer3 absmax %.3f mean %.4f  clf absmax %.5f" % (bf["layer3"].abs().max(), bf["layer3"].mean(), clf.abs().max()))
+    np.savez_compressed(os.path.join(GOLDEN, "backbone.npz"), **out)
+
+
+GENS = {"corr": gen_corr, "labels": gen_labels, "dimp_sd": gen_dimp_sd, "prdimp_sd": gen_prdimp_sd,
+        "backbone": gen_backbone}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    ref_shims.install()
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.set_num_threads(8)
+    for name, fn in GENS.items():
+        if args.only and name != args.only:
+            continue
+        print("== golden:", name)
+        fn()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,97 @@
+"""CPU: the oracle restatement (oracle/dimp_oracle.py) against golden vectors produced by the
+unmodified reference (oracle/gen_golden.py).  This is what pins the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dimp_oracle as O
+from pytracking_b200 import synth
+
+
+def _rel(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64)
+    b = torch.as_tensor(b, dtype=torch.float64)
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def G(golden_dir):
+    return {n: np.load(os.path.join(golden_dir, n + ".npz")) for n in ("corr", "labels", "dimp_sd", "prdimp_sd", "backbone")}
+
+
+@pytest.mark.parametrize("tag,n,c,h,k", [("a", 3, 32, 18, 4), ("b", 2, 64, 22, 4), ("c", 2, 32, 18, 1), ("d", 2, 32, 13, 3)])
+def test_corr_and_adjoint(G, tag, n, c, h, k):
+    g = G["corr"]
+    feat = synth.make_clf_features(100 + ord(tag), n, c, h, h, filter_size=max(k, 1))
+    w = torch.from_numpy(g[tag + "_w"])
+    s = O.apply_filter(feat, w)
+    assert s.shape[-1] == h + (k + 1) % 2
+    assert _rel(s[:, 0], g[tag + "_scores"][:, 0]) < 2e-6
+    r = torch.from_numpy(g[tag + "_r"])[:, 0:1]
+    gt = O.apply_feat_transpose(feat, r, k)
+    assert _rel(gt, g[tag + "_grad"]) < 2e-6
+    mv, mi = O.max2d(torch.from_numpy(g[tag + "_scores"])[:, 0])
+    assert np.array_equal(mi.numpy(), g[tag + "_maxidx"])
+    assert np.array_equal(mv.numpy(), g[tag + "_maxval"])
+
+
+def test_max2d_ties():
+    a = torch.zeros(2, 5, 5)
+    a[0, 3, 1] = 1.0
+    a[0, 1, 3] = 1.0     # tie: reference picks the smaller column (dcf.py:159-160)
+    a[1, 4, 2] = 2.0
+    a[1, 2, 2] = 2.0     # tie inside a column: smaller row
+    _, idx = O.max2d(a)
+    assert idx.tolist() == [[3, 1], [2, 2]]
+
+
+def test_label_maps(G):
+    g = G["labels"]
+    p = synth.make_dimp_optimizer_params(seed=5)
+    y, m, v = O.dimp_label_maps(torch.from_numpy(g["bb"]), p, (19, 19))
+    assert _rel(y, g["y"]) < 1e-5 and _rel(m, g["m"]) < 1e-5 and _rel(v, g["v"]) < 1e-5
+
+
+@pytest.mark.parametrize("tag,n,c,h,it,use_sw,seed", [("n15_it10", 15, 512, 18, 10, True, 21), ("n50_it2", 50, 512, 18, 2, True, 22),
+                                                      ("n4_c64", 4, 64, 18, 3, False, 23), ("n7_22", 7, 128, 22, 4, True, 24)])
+def test_dimp_sd(G, tag, n, c, h, it, use_sw, seed):
+    g = G["dimp_sd"]
+    p = synth.make_dimp_optimizer_params(seed=seed)
+    feat = synth.make_clf_features(seed, n, c, h, h)
+    bb = synth.make_boxes(seed + 1, n, center=(h * 16) / 2 - 25)
+    sw = torch.from_numpy(g[tag + "_sw"]) if use_sw else None
+    w, its, losses = O.dimp_sd_gn(torch.from_numpy(g[tag + "_w0"]), feat, bb, sw, p, it)
+    assert _rel(its[1], g[tag + "_w1"]) < 1e-5
+    assert _rel(w, g[tag + "_wfinal"]) < 1e-4
+    assert np.allclose([float(l) for l in losses], g[tag + "_losses"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("tag,n,c,h,it,seed,sreg,lthr", [("n15_22", 15, 512, 22, 10, 31, None, 0.0), ("n6_18", 6, 64, 18, 3, 32, -2.0, 0.05)])
+def test_prdimp_sd(G, tag, n, c, h, it, seed, sreg, lthr):
+    g = G["prdimp_sd"]
+    feat = synth.make_clf_features(seed, n, c, h, h)
+    bb = synth.make_boxes(seed + 1, n, center=(h * 16) / 2 - 25)
+    w, its, losses = O.prdimp_sd_newton(torch.from_numpy(g[tag + "_w0"]), feat, bb, torch.from_numpy(g[tag + "_sw"]),
+                                        0.0, 0.05, it, float(g[tag + "_sigma"]), min_filter_reg=0.05, alpha_eps=0.05,
+                                        softmax_reg_val=sreg, label_threshold=lthr, normalize_label=True,
+                                        label_shrink=0.0 if sreg is None else 0.1)
+    assert _rel(its[1], g[tag + "_w1"]) < 1e-5
+    assert _rel(w, g[tag + "_wfinal"]) < 1e-4
+    assert np.allclose([float(l) for l in losses], g[tag + "_losses"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("arch,size,seed", [("resnet50", 96, 42), ("resnet18", 96, 42), ("resnet50", 288, 41)])
+def test_backbone_and_head(G, arch, size, seed):
+    g = G["backbone"]
+    sd = synth.make_dimp_state_dict(arch, seed=0, lut_seed=3)
+    im = O.preprocess_image(synth.make_crop(seed, 1, size))
+    with torch.no_grad():
+        bf = O.resnet_forward(sd, im, arch)
+        clf = O.clf_head_dimp50(sd, bf["layer3"]) if arch == "resnet50" else O.clf_head_dimp18(sd, bf["layer3"])
+    tag = "%s_%d_" % (arch, size)
+    l2 = bf["layer2"] if size == 96 else bf["layer2"][:, ::8]
+    assert _rel(l2, g[tag + "layer2"]) < 1e-5
+    assert _rel(bf["layer3"], g[tag + "layer3"]) < 1e-5
+    assert _rel(clf, g[tag + "clf"]) < 1e-5
