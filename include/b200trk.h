@@ -1,0 +1,199 @@
+/*
+ * b200trk -- C ABI of the Blackwell (sm_100a) per-frame tracking engine.
+ *
+ * One shared library (pytracking_b200/libb200trk.so), plain C signatures: raw pointers, ints, floats.
+ * No torch / ATen types cross this boundary.
+ *
+ * The reference (visionml/pytracking @ 7eb9e74) has no C/FFI boundary on this path except the
+ * `_prroi_pooling` pybind module; its plug-in surface is Python duck typing.
+ * Each entry point below therefore names the reference *Python seam* (file:line, relative to the
+ * reference root) whose tensor computation it replaces; `INTEGRATION.md` shows the ctypes stub a
+ * maintainer adds at that seam.
+ *
+ * Conventions (all entry points):
+ *   - return 0 on success, non-zero on error; `b200trk_last_error()` gives the message (thread local).
+ *     The library never calls exit() (the reference's CUDA_POST_KERNEL_CHECK does,
+ *     ltr/external/PreciseRoIPooling/src/prroi_pooling_gpu_impl.cu:20-27).
+ *   - `*_dev` / unnamed pointers are DEVICE pointers on the current CUDA device, fp32, contiguous,
+ *     NCHW unless stated. The caller (torch) owns every buffer; outputs are pre-allocated by the caller.
+ *   - `stream` is a cudaStream_t passed as void* (the caller's current stream, as
+ *     prroi_pooling_gpu.c:35 does); no entry point synchronises the device unless it says so.
+ *   - the library keeps one lazily grown scratch workspace per device; calls on one device must be
+ *     issued from one host thread / one stream at a time (the reference runs one tracker per process,
+ *     pytracking/evaluation/running.py:216-218).
+ *   - `*_host` entry points take HOST pointers (pinned for full speed) and perform the H2D / D2H copies
+ *     themselves on `stream`, then synchronise that stream before returning.
+ */
+#ifndef B200TRK_H_
+#define B200TRK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200TRK_VERSION 100
+
+typedef void* b200trk_stream_t;              /* cudaStream_t */
+typedef struct b200trk_net b200trk_net_t;    /* opaque: folded + repacked network weights and activation workspaces */
+
+int         b200trk_version(void);
+const char* b200trk_last_error(void);
+/* Number of kernels this library has launched so far in this process (for bench.py's gpu_launches). */
+uint64_t    b200trk_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 2 -- target-model application
+ * ---------------------------------------------------------------------------------------------- */
+
+/* apply_filter: ltr/models/layers/filter.py:5-57 (single sequence, one filter; LinearFilter.classify
+ * ltr/models/target_classifier/linear_filter.py:75-80 <- DiMP.classify_target pytracking/tracker/dimp/dimp.py:190-194).
+ *   feat [n,C,H,W], filt [1,C,k,k] -> scores [n,1,H+(k+1)%2,W+(k+1)%2], zero padding k/2.
+ * Optionally fuses dcf.max2d (pytracking/libs/dcf.py:156-164): max_val [n], max_idx [n,2] (row,col) int64,
+ * ties resolved as the reference does (smallest column, then smallest row). Pass NULL to skip. */
+int b200trk_apply_filter(const float* feat, const float* filt, float* scores,
+                         int n, int C, int H, int W, int k,
+                         float* max_val, int64_t* max_idx, b200trk_stream_t stream);
+
+/* apply_feat_transpose: ltr/models/layers/filter.py:91-182 (the exact adjoint of apply_filter w.r.t. the filter;
+ * _v2 and _v3 agree). feat [n,C,H,W], resid [n,1,Ho,Wo] -> grad [1,C,k,k] (sum over the n samples). */
+int b200trk_apply_feat_transpose(const float* feat, const float* resid, float* grad,
+                                 int n, int C, int H, int W, int k, b200trk_stream_t stream);
+
+/* dcf.max2d: pytracking/libs/dcf.py:156-164. a [n,H,W] -> max_val [n], max_idx [n,2] int64. */
+int b200trk_max2d(const float* a, int n, int H, int W, float* max_val, int64_t* max_idx, b200trk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 3 -- online filter optimisers (one persistent cooperative kernel per call)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* DiMPSteepestDescentGN.forward: ltr/models/target_classifier/optimizer.py:85-170 (score_act='relu',
+ * mask_act='sigmoid', one sequence), incl. DistanceMap (ltr/models/layers/distance.py:17-39) and the three
+ * 1x1 predictors, which together are radial piece-wise linear LUTs.
+ *   weights      [1,C,k,k] initial filter (k must be 4); final filter is written to weights_out [1,C,k,k]
+ *   feat         [n,C,H,W] sample memory (H,W in {18,22})
+ *   bb           [n,4] (x,y,w,h) in crop pixels
+ *   sample_weight[n] or NULL (-> 1/n each)
+ *   label_lut, mask_lut, spatial_lut: [num_bins] weights of label_map_predictor, target_mask_predictor[0],
+ *                spatial_weight_predictor
+ *   step_length = exp(log_step_length); reg_weight = max(filter_reg^2, min_filter_reg^2)
+ *   iterates_out [num_iter+1,C,k,k] or NULL; losses_out [num_iter+1] or NULL (compute_losses)           */
+int b200trk_dimp_sd_gn(const float* weights, float* weights_out, const float* feat, const float* bb,
+                       const float* sample_weight, int n, int C, int H, int W, int k, int num_iter,
+                       const float* label_lut, const float* mask_lut, const float* spatial_lut,
+                       int num_bins, float bin_displacement, float feat_stride,
+                       float step_length, float reg_weight, float alpha_eps,
+                       float* iterates_out, float* losses_out, b200trk_stream_t stream);
+
+/* PrDiMPSteepestDescentNewton.forward: ltr/models/target_classifier/optimizer.py:355-439 (gauss_sigma > 0).
+ * has_softmax_reg==0 means softmax_reg=None. */
+int b200trk_prdimp_sd_newton(const float* weights, float* weights_out, const float* feat, const float* bb,
+                             const float* sample_weight, int n, int C, int H, int W, int k, int num_iter,
+                             float gauss_sigma, float feat_stride, float step_length, float reg_weight,
+                             float alpha_eps, int has_softmax_reg, float softmax_reg, float label_threshold,
+                             int normalize_label, float label_shrink, float uni_weight,
+                             float* iterates_out, float* losses_out, b200trk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 1 -- backbone + classification head
+ * ---------------------------------------------------------------------------------------------- */
+
+/* One convolution of the network as the reference state_dict holds it (HOST pointers, fp32):
+ * conv weight [cout,cin,kh,kw] (+ optional conv bias) followed by an optional eval-mode BatchNorm
+ * (gamma,beta,running_mean,running_var; eps 1e-5) which is folded into the conv at create time. */
+typedef struct {
+    const float* weight;      /* [cout,cin,k,k] */
+    const float* bias;        /* [cout] or NULL */
+    const float* bn_gamma;    /* [cout] or NULL (no BN) */
+    const float* bn_beta;
+    const float* bn_mean;
+    const float* bn_var;
+    int cout, cin, k, stride, pad;
+} b200trk_conv_desc_t;
+
+#define B200TRK_ARCH_RESNET18 18
+#define B200TRK_ARCH_RESNET50 50
+#define B200TRK_ARCH_RESNET101 101
+
+/* Build the network handle for ResNet.forward to layer3 (ltr/models/backbone/resnet.py:175-206) plus the clf
+ * head (ltr/models/target_classifier/features.py:9-28,50-73 + InstanceL2Norm ltr/models/layers/normalization.py:15-20).
+ *   convs: the backbone convs in execution order (stem conv1; per Bottleneck conv1,conv2,[downsample],conv3; per BasicBlock
+ *   conv1,[downsample],conv2) followed by
+ *   the head convs (resnet50: 1 conv; resnet18: BasicBlock conv1, conv2, final conv). n_convs is checked.
+ *   norm_scale: InstanceL2Norm scale (sqrt(1/(out_dim*filter_size^2)), ltr/models/tracking/dimpnet.py:159).
+ *   max_batch: largest S the handle will be run with (13 at DiMP.initialize, 1 per frame).
+ *   precision: 0 = fp32-faithful (error-compensated 3xTF32 tensor-core MMA + fp32 CUDA-core stem), 1 = fp32 CUDA cores only. */
+int b200trk_net_create(b200trk_net_t** out, int arch, const b200trk_conv_desc_t* convs, int n_convs,
+                       float norm_scale, int max_batch, int crop_h, int crop_w, int precision);
+int b200trk_net_destroy(b200trk_net_t* net);
+
+/* NetWithBackbone.extract_backbone (pytracking/features/net_wrappers.py:55-75) + DiMPnet.extract_classification_feat
+ * (ltr/models/tracking/dimpnet.py:80-86) in one call.
+ *   crop   [S,3,crop_h,crop_w] pixel range 0..255 (device); normalisation (/255, mean, std) is fused.
+ *   layer2 [S,C2,h/8,w/8], layer3 [S,C3,h/16,w/16], clf [S,Cc,h/16,w/16]; any may be NULL. */
+int b200trk_net_forward(b200trk_net_t* net, const float* crop, int S,
+                        float* layer2, float* layer3, float* clf, b200trk_stream_t stream);
+/* Query output geometry: dims = {C2,H2,W2, C3,H3,W3, Cc,Hc,Wc}. */
+int b200trk_net_dims(const b200trk_net_t* net, int dims[9]);
+/* FLOPs (2*MAC) of one forward pass at batch 1, for roofline accounting. */
+double b200trk_net_flops(const b200trk_net_t* net);
+
+/* ------------------------------------------------------------------------------------------------
+ * Native op -- Precise RoI Pooling (the reference's only CUDA component)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* prroi_pooling_forward_cuda: ltr/external/PreciseRoIPooling/pytorch/prroi_pool/src/prroi_pooling_gpu.c:22-44
+ * (kernel src/prroi_pooling_gpu_impl.cu:149-212). features [B,C,H,W], rois [R,5] (batch idx,x1,y1,x2,y2) ->
+ * output [R,C,ph,pw]. */
+int b200trk_prroi_pool_forward(const float* features, const float* rois, float* output,
+                               int B, int C, int H, int W, int R, int ph, int pw, float spatial_scale,
+                               b200trk_stream_t stream);
+/* prroi_pooling_backward_cuda: prroi_pooling_gpu.c:46-75 (kernel .cu:214-272). features_grad [B,C,H,W] is zeroed first. */
+int b200trk_prroi_pool_backward(const float* features, const float* rois, const float* output,
+                                const float* output_grad, float* features_grad,
+                                int B, int C, int H, int W, int R, int ph, int pw, float spatial_scale,
+                                b200trk_stream_t stream);
+/* prroi_pooling_coor_backward_cuda: prroi_pooling_gpu.c:77-107 (kernel .cu:274-379). rois_grad [R,5] is zeroed first. */
+int b200trk_prroi_pool_coor_backward(const float* features, const float* rois, const float* output,
+                                     const float* output_grad, float* rois_grad,
+                                     int B, int C, int H, int W, int R, int ph, int pw, float spatial_scale,
+                                     b200trk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer frame call (what bench.py's `e2e` times): one tracked frame of the DiMP hot path.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Per-sequence device state of the online model: sample memory, boxes, weights, filter. */
+typedef struct b200trk_dimp_state b200trk_dimp_state_t;
+
+int b200trk_dimp_state_create(b200trk_dimp_state_t** out, b200trk_net_t* net, int memory_size, int filter_size,
+                              const float* label_lut, const float* mask_lut, const float* spatial_lut /* HOST [num_bins] */,
+                              int num_bins, float bin_displacement, float feat_stride,
+                              float step_length, float reg_weight, float alpha_eps);
+int b200trk_dimp_state_destroy(b200trk_dimp_state_t* st);
+/* Device views for the Python host (torch wraps them without copying): */
+float* b200trk_dimp_state_filter(b200trk_dimp_state_t* st);        /* [1,Cc,k,k]  */
+float* b200trk_dimp_state_memory(b200trk_dimp_state_t* st);        /* [memory_size,Cc,Hc,Wc] */
+float* b200trk_dimp_state_boxes(b200trk_dimp_state_t* st);         /* [memory_size,4] */
+float* b200trk_dimp_state_sample_weights(b200trk_dimp_state_t* st);/* [memory_size] */
+float* b200trk_dimp_state_clf(b200trk_dimp_state_t* st);           /* [max_batch,Cc,Hc,Wc] features of the last crop */
+float* b200trk_dimp_state_scores(b200trk_dimp_state_t* st);        /* [max_batch,Ho,Wo] */
+
+/* DiMP.track localisation half (pytracking/tracker/dimp/dimp.py:103-117): H2D of the crop(s), backbone, clf head,
+ * classify, max2d; D2H of the score map(s) + arg-max. crop_host [S,3,h,w] 0..255; scores_host [S,Ho,Wo];
+ * max_val_host [S]; max_idx_host [S,2]. Synchronises `stream`. */
+int b200trk_dimp_localize_host(b200trk_dimp_state_t* st, const float* crop_host, int S,
+                               float* scores_host, float* max_val_host, int64_t* max_idx_host,
+                               b200trk_stream_t stream);
+/* DiMP.update_classifier (dimp.py:605-648) device half: store clf feature `scale_ind` of the last crop into memory
+ * slot `replace_ind` with box `target_box` (HOST [4]), upload the host-maintained sample weights (HOST [n_stored]),
+ * then run num_iter steepest-descent iterations over the first n_stored samples. Asynchronous on `stream`. */
+int b200trk_dimp_update_host(b200trk_dimp_state_t* st, int scale_ind, int replace_ind, const float* target_box_host,
+                             const float* sample_weights_host, int n_stored, int num_iter, b200trk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200TRK_H_ */

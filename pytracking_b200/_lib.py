@@ -1,0 +1,78 @@
+"""ctypes binding of libb200trk.so (the C ABI declared in include/b200trk.h).
+
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200trk.so")
+
+c_float_p = C.POINTER(C.c_float)
+c_int64_p = C.POINTER(C.c_int64)
+
+
+class ConvDesc(C.Structure):
+    """b200trk_conv_desc_t"""
+    _fields_ = [("weight", C.c_void_p), ("bias", C.c_void_p), ("bn_gamma", C.c_void_p), ("bn_beta", C.c_void_p),
+                ("bn_mean", C.c_void_p), ("bn_var", C.c_void_p),
+                ("cout", C.c_int), ("cin", C.c_int), ("k", C.c_int), ("stride", C.c_int), ("pad", C.c_int)]
+
+
+# name -> (restype, argtypes); every symbol of include/b200trk.h is listed (tests check the export table against it)
+_VP, _I, _F = C.c_void_p, C.c_int, C.c_float
+SIGNATURES = {
+    "b200trk_version": (_I, []),
+    "b200trk_last_error": (C.c_char_p, []),
+    "b200trk_launch_count": (C.c_uint64, []),
+    "b200trk_apply_filter": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _VP]),
+    "b200trk_apply_feat_transpose": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
+    "b200trk_max2d": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP]),
+    "b200trk_dimp_sd_gn": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _I, _F, _F, _F, _F, _F,
+                                _VP, _VP, _VP]),
+    "b200trk_prdimp_sd_newton": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _F, _F, _F, _F, _F, _I, _F, _F,
+                                      _I, _F, _F, _VP, _VP, _VP]),
+    "b200trk_net_create": (_I, [C.POINTER(_VP), _I, C.POINTER(ConvDesc), _I, _F, _I, _I, _I, _I]),
+    "b200trk_net_destroy": (_I, [_VP]),
+    "b200trk_net_forward": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _VP]),
+    "b200trk_net_dims": (_I, [_VP, C.POINTER(C.c_int * 9)]),
+    "b200trk_net_flops": (C.c_double, [_VP]),
+    "b200trk_prroi_pool_forward": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _F, _VP]),
+    "b200trk_prroi_pool_backward": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _F, _VP]),
+    "b200trk_prroi_pool_coor_backward": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _F, _VP]),
+    "b200trk_dimp_state_create": (_I, [C.POINTER(_VP), _VP, _I, _I, _VP, _VP, _VP, _I, _F, _F, _F, _F, _F]),
+    "b200trk_dimp_state_destroy": (_I, [_VP]),
+    "b200trk_dimp_state_filter": (_VP, [_VP]),
+    "b200trk_dimp_state_memory": (_VP, [_VP]),
+    "b200trk_dimp_state_boxes": (_VP, [_VP]),
+    "b200trk_dimp_state_sample_weights": (_VP, [_VP]),
+    "b200trk_dimp_state_clf": (_VP, [_VP]),
+    "b200trk_dimp_state_scores": (_VP, [_VP]),
+    "b200trk_dimp_localize_host": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _VP]),
+    "b200trk_dimp_update_host": (_I, [_VP, _I, _I, _VP, _VP, _I, _I, _VP]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the ctypes handle. Raises if the CUDA library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "pytracking_b200: %s is missing -- the CUDA extension must be built (python -c 'import "
+                "__graft_entry__ as g; g.build()'); there is no CPU / PyTorch fallback." % LIB_PATH)
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name)          # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = lib().b200trk_last_error()
+        raise RuntimeError("b200trk %s failed (status %d): %s" % (what, status, msg.decode() if msg else "?"))

@@ -1,0 +1,86 @@
+// Shared host/device helpers for libb200trk (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <atomic>
+
+#include "../../include/b200trk.h"
+
+namespace b200trk {
+
+// ---- error reporting (never exit(); see include/b200trk.h) ----------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launch_count;
+
+#define B200_CHECK_CUDA(expr)                                                                       \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            ::b200trk::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return 1;                                                                               \
+        }                                                                                           \
+    } while (0)
+
+#define B200_REQUIRE(cond, ...)                                                                     \
+    do {                                                                                            \
+        if (!(cond)) {                                                                              \
+            ::b200trk::set_error(__VA_ARGS__);                                                      \
+            return 2;                                                                               \
+        }                                                                                           \
+    } while (0)
+
+#define B200_LAUNCH_CHECK()                                                                         \
+    do {                                                                                            \
+        ::b200trk::g_launch_count.fetch_add(1, std::memory_order_relaxed);                          \
+        B200_CHECK_CUDA(cudaGetLastError());                                                        \
+    } while (0)
+
+// ---- per-device scratch workspace (grown lazily; single caller thread per device) -----------------
+// Returns a device pointer with at least `bytes` bytes, 256-byte aligned; nullptr on failure (error set).
+void* workspace(size_t bytes, int slot = 0);
+int device_sm_count();
+
+// ---- device helpers --------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block-wide sum; `red` must hold >= 32 floats. All threads get the result.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    float t = (lane < nw) ? red[lane] : 0.f;
+    t = warp_sum(t);
+    return t;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Grid-wide barrier for COOPERATIVELY launched kernels (all CTAs co-resident). `counter` is zeroed by the
+// host before launch; `epoch` counts barriers executed so far by this CTA (same on all CTAs).
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
+    __syncthreads();
+    epoch += 1;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const unsigned target = epoch * gridDim.x;
+        while (ld_acquire_u32(counter) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+}  // namespace b200trk

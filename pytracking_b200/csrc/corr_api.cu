@@ -1,0 +1,240 @@
+// Stage 2 entry points: apply_filter (+ fused max2d), apply_feat_transpose, max2d.
+// HBM roofline: algorithmic bytes per sample = 4*(C*H*W + C*k*k + Ho*Wo); each feature plane
+// is read exactly once with 128-bit coalesced loads.
+#include "corr.cuh"
+
+namespace b200trk {
+
+// --------------------------------------------------------------------------------------------------
+// max2d over [n,H,W] maps: one CTA per map. Also used as the tail of apply_filter.
+// --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ ArgMax argmax_block(const float* a, int H, int W, ArgMax* sred) {
+    ArgMax best{-INFINITY, 0x7fffffff, 0x7fffffff};
+    for (int pos = threadIdx.x; pos < H * W; pos += blockDim.x) {
+        ArgMax c{a[pos], pos / W, pos % W};
+        if (c.better_than(best)) best = c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ArgMax c;
+        c.v = __shfl_xor_sync(0xffffffffu, best.v, o);
+        c.row = __shfl_xor_sync(0xffffffffu, best.row, o);
+        c.col = __shfl_xor_sync(0xffffffffu, best.col, o);
+        if (c.better_than(best)) best = c;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) sred[wid] = best;
+    __syncthreads();
+    if (wid == 0) {
+        best = (lane < nw) ? sred[lane] : ArgMax{-INFINITY, 0x7fffffff, 0x7fffffff};
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ArgMax c;
+            c.v = __shfl_xor_sync(0xffffffffu, best.v, o);
+            c.row = __shfl_xor_sync(0xffffffffu, best.row, o);
+            c.col = __shfl_xor_sync(0xffffffffu, best.col, o);
+            if (c.better_than(best)) best = c;
+        }
+    }
+    return best;  // valid in warp 0
+}
+
+__global__ void max2d_kernel(const float* __restrict__ a, int H, int W, float* max_val, int64_t* max_idx) {
+    __shared__ ArgMax sred[32];
+    const float* m = a + (size_t)blockIdx.x * H * W;
+    ArgMax b = argmax_block(m, H, W, sred);
+    if (threadIdx.x == 0) {
+        max_val[blockIdx.x] = b.v;
+        max_idx[2 * blockIdx.x] = b.row;
+        max_idx[2 * blockIdx.x + 1] = b.col;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// apply_filter: grid (NCH, n). CTA = (channel chunk, sample). Partials -> workspace; the last CTA of a
+// sample to finish sums the NCH partials in a fixed order (deterministic) and does the arg-max.
+// --------------------------------------------------------------------------------------------------
+template <int FS, int SLOTS>
+__global__ void __launch_bounds__(CorrCta<FS, SLOTS>::NTHREADS)
+apply_filter_kernel(const float* __restrict__ feat, const float* __restrict__ filt, float* __restrict__ scores,
+                    float* part, unsigned* counters, int C, int n, int passes,
+                    float* max_val, int64_t* max_idx) {
+    using K = CorrCta<FS, SLOTS>;
+    using G = CorrGeom<FS>;
+    extern __shared__ float smem[];
+    float* planes = smem;
+    float* red = planes + K::PLANES_FLOATS;
+    float* vec = red + K::RED_FLOATS;                 // [passes*SLOTS*16]
+    __shared__ ArgMax sred[32];
+    __shared__ int s_last;
+
+    const int NCH = gridDim.x, chunk = blockIdx.x, i = blockIdx.y;
+    const int cchunk = passes * SLOTS;
+    K::zero_planes(planes);
+    for (int o = threadIdx.x; o < cchunk * 16; o += K::NTHREADS) vec[o] = filt[(size_t)chunk * cchunk * 16 + o];
+    __syncthreads();
+
+    typename K::Ctx cx{feat, C, n, chunk * cchunk, passes, i, n};   // group = i, NG = n  -> exactly one sample
+    K::sweep_apply(cx, planes, red, vec, part + (size_t)chunk * G::NPOS, (size_t)NCH * G::NPOS);
+
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&counters[i], 1u) == (unsigned)(NCH - 1));
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float* sc = red;   // reuse as staging for the arg-max
+    for (int pos = threadIdx.x; pos < G::NPOS; pos += K::NTHREADS) {
+        float s = 0.f;
+        for (int ch = 0; ch < NCH; ++ch) s += __ldcg(part + ((size_t)i * NCH + ch) * G::NPOS + pos);
+        scores[(size_t)i * G::NPOS + pos] = s;
+        sc[pos] = s;
+    }
+    __syncthreads();
+    if (max_val != nullptr) {
+        ArgMax b = argmax_block(sc, G::OS, G::OS, sred);
+        if (threadIdx.x == 0) {
+            max_val[i] = b.v;
+            max_idx[2 * i] = b.row;
+            max_idx[2 * i + 1] = b.col;
+        }
+    }
+    if (threadIdx.x == 0) counters[i] = 0;   // self-reset for the next call
+}
+
+// --------------------------------------------------------------------------------------------------
+// apply_feat_transpose: grid (NCH, NG). CTA = (channel chunk, sample group). Partials [NG][C*16] -> last CTA of a
+// chunk sums over groups in a fixed order.
+// --------------------------------------------------------------------------------------------------
+template <int FS, int SLOTS>
+__global__ void __launch_bounds__(CorrCta<FS, SLOTS>::NTHREADS)
+feat_transpose_kernel(const float* __restrict__ feat, const float* __restrict__ resid, float* __restrict__ grad,
+                      float* gpart, unsigned* counters, int C, int n, int passes, int spc_max) {
+    using K = CorrCta<FS, SLOTS>;
+    using G = CorrGeom<FS>;
+    extern __shared__ float smem[];
+    float* planes = smem;
+    float* red = planes + K::PLANES_FLOATS;
+    float* rt = red + K::RED_FLOATS;                  // [spc_max][NPOS]
+    __shared__ int s_last;
+
+    const int NCH = gridDim.x, NG = gridDim.y, chunk = blockIdx.x, group = blockIdx.y;
+    const int cchunk = passes * SLOTS;
+    K::zero_planes(planes);
+    typename K::Ctx cx{feat, C, n, chunk * cchunk, passes, group, NG};
+    const int spc = cx.spc();
+    for (int o = threadIdx.x; o < spc * G::NPOS; o += K::NTHREADS) {
+        const int j = o / G::NPOS, pos = o - j * G::NPOS;
+        rt[o] = resid[(size_t)cx.sample(j) * G::NPOS + pos];
+    }
+    __syncthreads();
+    K::sweep_transpose(cx, planes, red, rt, gpart + ((size_t)group * C + chunk * cchunk) * 16);
+
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&counters[chunk], 1u) == (unsigned)(NG - 1));
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int o = threadIdx.x; o < cchunk * 16; o += K::NTHREADS) {
+        float s = 0.f;
+        for (int g = 0; g < NG; ++g) s += __ldcg(gpart + ((size_t)g * C + chunk * cchunk) * 16 + o);
+        grad[(size_t)chunk * cchunk * 16 + o] = s;
+    }
+    if (threadIdx.x == 0) counters[chunk] = 0;
+}
+
+static int pick_passes(int C, int slots, int max_passes) {
+    for (int p = max_passes; p >= 1; p >>= 1)
+        if (C % (slots * p) == 0) return p;
+    return 0;
+}
+
+template <int FS>
+static int launch_apply_filter(const float* feat, const float* filt, float* scores, int n, int C,
+                               float* max_val, int64_t* max_idx, cudaStream_t st) {
+    constexpr int SLOTS = CorrSlots<FS>::value;
+    using K = CorrCta<FS, SLOTS>;
+    using G = CorrGeom<FS>;
+    // few samples at classification time (S scales): spread channels over many CTAs
+    int passes = pick_passes(C, SLOTS, n >= 16 ? 4 : 1);
+    B200_REQUIRE(passes > 0, "apply_filter: C=%d must be a multiple of %d for feature size %d", C, SLOTS, FS);
+    const int NCH = C / (SLOTS * passes);
+    B200_REQUIRE(n <= 1024, "apply_filter: n=%d > 1024 maps per call", n);
+    // workspace layout: [0,4096) per-sample arrival counters (zero at allocation, self-resetting), then partial maps
+    const size_t part_bytes = (size_t)n * NCH * G::NPOS * sizeof(float);
+    char* ws = (char*)workspace(4096 + part_bytes, 0);
+    if (!ws) return 3;
+    unsigned* counters = (unsigned*)ws;
+    float* part = (float*)(ws + 4096);
+    const size_t smem = (size_t)(K::PLANES_FLOATS + K::RED_FLOATS + passes * SLOTS * 16) * sizeof(float);
+    auto kern = apply_filter_kernel<FS, SLOTS>;
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(NCH, n), K::NTHREADS, smem, st>>>(feat, filt, scores, part, counters, C, n, passes, max_val, max_idx);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int FS>
+static int launch_feat_transpose(const float* feat, const float* resid, float* grad, int n, int C, cudaStream_t st) {
+    constexpr int SLOTS = CorrSlots<FS>::value;
+    using K = CorrCta<FS, SLOTS>;
+    using G = CorrGeom<FS>;
+    int passes = pick_passes(C, SLOTS, 4);
+    B200_REQUIRE(passes > 0, "apply_feat_transpose: C=%d must be a multiple of %d for feature size %d", C, SLOTS, FS);
+    const int NCH = C / (SLOTS * passes);
+    const int sms = device_sm_count();
+    int NG = sms / NCH; if (NG < 1) NG = 1; if (NG > n) NG = n;
+    const int SPC_CAP = 8;
+    if ((n + NG - 1) / NG > SPC_CAP) NG = (n + SPC_CAP - 1) / SPC_CAP;
+    const int spc_max = (n + NG - 1) / NG;
+    B200_REQUIRE(NCH <= 1024, "apply_feat_transpose: too many channel chunks (%d)", NCH);
+    const size_t gp_bytes = (size_t)NG * C * 16 * sizeof(float);
+    char* ws = (char*)workspace(4096 + gp_bytes, 1);
+    if (!ws) return 3;
+    unsigned* counters = (unsigned*)ws;
+    float* gpart = (float*)(ws + 4096);
+    const size_t smem = (size_t)(K::PLANES_FLOATS + K::RED_FLOATS + spc_max * G::NPOS) * sizeof(float);
+    auto kern = feat_transpose_kernel<FS, SLOTS>;
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(NCH, NG), K::NTHREADS, smem, st>>>(feat, resid, grad, gpart, counters, C, n, passes, spc_max);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace b200trk
+
+using namespace b200trk;
+
+extern "C" int b200trk_apply_filter(const float* feat, const float* filt, float* scores, int n, int C, int H, int W,
+                                    int k, float* max_val, int64_t* max_idx, b200trk_stream_t stream) {
+    B200_REQUIRE(feat && filt && scores, "apply_filter: null pointer");
+    B200_REQUIRE(n > 0 && C > 0, "apply_filter: empty input (n=%d, C=%d)", n, C);
+    B200_REQUIRE(k == 4, "apply_filter: filter size %d not supported by the CUDA path (only 4)", k);
+    B200_REQUIRE(H == W && (H == 18 || H == 22), "apply_filter: feature size %dx%d not supported (18x18, 22x22)", H, W);
+    B200_REQUIRE((max_val == nullptr) == (max_idx == nullptr), "apply_filter: max_val and max_idx must both be given or both NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (H == 18) return launch_apply_filter<18>(feat, filt, scores, n, C, max_val, max_idx, st);
+    return launch_apply_filter<22>(feat, filt, scores, n, C, max_val, max_idx, st);
+}
+
+extern "C" int b200trk_apply_feat_transpose(const float* feat, const float* resid, float* grad, int n, int C, int H,
+                                            int W, int k, b200trk_stream_t stream) {
+    B200_REQUIRE(feat && resid && grad, "apply_feat_transpose: null pointer");
+    B200_REQUIRE(n > 0 && C > 0, "apply_feat_transpose: empty input (n=%d, C=%d)", n, C);
+    B200_REQUIRE(k == 4, "apply_feat_transpose: filter size %d not supported by the CUDA path (only 4)", k);
+    B200_REQUIRE(H == W && (H == 18 || H == 22), "apply_feat_transpose: feature size %dx%d not supported", H, W);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (H == 18) return launch_feat_transpose<18>(feat, resid, grad, n, C, st);
+    return launch_feat_transpose<22>(feat, resid, grad, n, C, st);
+}
+
+extern "C" int b200trk_max2d(const float* a, int n, int H, int W, float* max_val, int64_t* max_idx,
+                             b200trk_stream_t stream) {
+    B200_REQUIRE(a && max_val && max_idx, "max2d: null pointer");
+    B200_REQUIRE(n > 0 && H > 0 && W > 0, "max2d: empty input");
+    max2d_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(a, H, W, max_val, max_idx);
+    B200_LAUNCH_CHECK();
+    return 0;
+}

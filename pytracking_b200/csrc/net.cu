@@ -1,0 +1,269 @@
+// b200trk_net_*: builds the stage-1 execution plan from the reference state_dict tensors (BN folded, weights
+// repacked to [cout][kh][kw][cin]) and runs it:  ResNet.forward to layer3 (ltr/models/backbone/resnet.py:175-206)
+// + clf head (ltr/models/target_classifier/features.py:9-28,50-73) + InstanceL2Norm (normalization.py:15-20).
+#include "net.cuh"
+#include <cmath>
+#include <cstring>
+
+namespace b200trk {
+
+int tc_conv_prepare(b200trk_net* net, Op& op, const std::vector<float>& w_khwc);   // conv_tc.cu
+int tc_conv_launch(b200trk_net* net, const Op& op, int S, cudaStream_t st);         // conv_tc.cu
+void tc_conv_free(TcConv* tc);
+bool tc_conv_supported(const Op& op);
+
+static int dev_alloc(b200trk_net* net, float** p, size_t floats) {
+    void* q = nullptr;
+    B200_CHECK_CUDA(cudaMalloc(&q, floats * sizeof(float)));
+    net->owned.push_back(q);
+    *p = (float*)q;
+    return 0;
+}
+
+static int new_buf(b200trk_net* net, size_t floats_per_sample, int* id) {
+    float* p = nullptr;
+    if (int e = dev_alloc(net, &p, floats_per_sample * (size_t)net->max_batch)) return e;
+    net->bufs.push_back(p);
+    net->buf_floats.push_back(floats_per_sample);
+    *id = (int)net->bufs.size() - 1;
+    return 0;
+}
+
+// fold eval-mode BN into (w, b) in double precision; repack [cout][cin][k][k] -> [cout][k][k][cin]
+static void fold_and_repack(const b200trk_conv_desc_t& d, std::vector<float>& w_out, std::vector<float>& b_out, bool& has_bias) {
+    const int kk = d.k * d.k;
+    w_out.assign((size_t)d.cout * kk * d.cin, 0.f);
+    b_out.assign(d.cout, 0.f);
+    has_bias = (d.bias != nullptr) || (d.bn_gamma != nullptr);
+    for (int co = 0; co < d.cout; ++co) {
+        double sc = 1.0, sh = 0.0;
+        if (d.bn_gamma) {
+            sc = (double)d.bn_gamma[co] / std::sqrt((double)d.bn_var[co] + 1e-5);
+            sh = (double)d.bn_beta[co] - (double)d.bn_mean[co] * sc;
+        }
+        const double cb = d.bias ? (double)d.bias[co] : 0.0;
+        b_out[co] = (float)(cb * sc + sh);
+        for (int ci = 0; ci < d.cin; ++ci)
+            for (int t = 0; t < kk; ++t)
+                w_out[((size_t)co * kk + t) * d.cin + ci] = (float)((double)d.weight[((size_t)co * d.cin + ci) * kk + t] * sc);
+    }
+}
+
+struct Builder {
+    b200trk_net* net;
+    const b200trk_conv_desc_t* convs;
+    int n_convs, next = 0;
+
+    int add_conv(int in, int res, int Hin, int Win, int cin, int cout, int k, int stride, int pad, int relu, int* out_id,
+                 int* Hout_, int* Wout_) {
+        B200_REQUIRE(next < n_convs, "net_create: ran out of conv descriptors at #%d", next);
+        const b200trk_conv_desc_t& d = convs[next];
+        B200_REQUIRE(d.cin == cin && d.cout == cout && d.k == k && d.stride == stride && d.pad == pad && d.weight,
+                     "net_create: conv #%d is (cin=%d,cout=%d,k=%d,s=%d,p=%d) but the architecture expects (%d,%d,%d,%d,%d)",
+                     next, d.cin, d.cout, d.k, d.stride, d.pad, cin, cout, k, stride, pad);
+        ++next;
+        Op op;
+        op.kind = OP_CONV;
+        op.in = in; op.res = res;
+        op.Hin = Hin; op.Win = Win; op.Cin = cin; op.Cout = cout; op.k = k; op.stride = stride; op.pad = pad; op.relu = relu;
+        op.Hout = (Hin + 2 * pad - k) / stride + 1;
+        op.Wout = (Win + 2 * pad - k) / stride + 1;
+        std::vector<float> w, b; bool hb;
+        fold_and_repack(d, w, b, hb);
+        if (int e = dev_alloc(net, &op.w, w.size())) return e;
+        B200_CHECK_CUDA(cudaMemcpy(op.w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+        if (hb) {
+            if (int e = dev_alloc(net, &op.bias, b.size())) return e;
+            B200_CHECK_CUDA(cudaMemcpy(op.bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
+        if (int e = new_buf(net, (size_t)op.Hout * op.Wout * cout, &op.out)) return e;
+        if (net->precision == 0 && tc_conv_supported(op)) {
+            if (int e = tc_conv_prepare(net, op, w)) return e;
+        }
+        net->flops += 2.0 * (double)op.Hout * op.Wout * cout * (double)k * k * cin;
+        net->ops.push_back(op);
+        *out_id = op.out; *Hout_ = op.Hout; *Wout_ = op.Wout;
+        return 0;
+    }
+};
+
+static int build(b200trk_net* net, const b200trk_conv_desc_t* convs, int n_convs) {
+    Builder B{net, convs, n_convs};
+    const bool bottleneck = net->arch != B200TRK_ARCH_RESNET18;
+    int nblocks[3];
+    if (net->arch == B200TRK_ARCH_RESNET18) { nblocks[0] = 2; nblocks[1] = 2; nblocks[2] = 2; }
+    else if (net->arch == B200TRK_ARCH_RESNET50) { nblocks[0] = 3; nblocks[1] = 4; nblocks[2] = 6; }
+    else if (net->arch == B200TRK_ARCH_RESNET101) { nblocks[0] = 3; nblocks[1] = 4; nblocks[2] = 23; }
+    else { B200_REQUIRE(false, "net_create: unknown arch %d", net->arch); }
+
+    int H = net->crop_h, W = net->crop_w;
+    // preprocess -> NHWC4
+    int b_in;
+    if (int e = new_buf(net, (size_t)H * W * 4, &b_in)) return e;
+    { Op op; op.kind = OP_PREPROCESS; op.out = b_in; op.Hin = H; op.Win = W; net->ops.push_back(op); }
+    // stem
+    {
+        B200_REQUIRE(n_convs > 0, "net_create: no conv descriptors");
+        const b200trk_conv_desc_t& d = convs[B.next++];
+        B200_REQUIRE(d.cin == 3 && d.cout == 64 && d.k == 7 && d.stride == 2 && d.pad == 3 && d.weight,
+                     "net_create: first conv must be the 7x7/2 stem (3->64)");
+        std::vector<float> w, b; bool hb;
+        fold_and_repack(d, w, b, hb);                 // [64][49][3]
+        std::vector<float> w4((size_t)64 * 49 * 4, 0.f);
+        for (int co = 0; co < 64; ++co)
+            for (int t = 0; t < 49; ++t)
+                for (int ci = 0; ci < 3; ++ci) w4[((size_t)co * 49 + t) * 4 + ci] = w[((size_t)co * 49 + t) * 3 + ci];
+        Op op; op.kind = OP_STEM; op.in = b_in; op.Hin = H; op.Win = W; op.Cin = 3; op.Cout = 64; op.k = 7; op.stride = 2; op.pad = 3;
+        op.Hout = (H + 6 - 7) / 2 + 1; op.Wout = (W + 6 - 7) / 2 + 1; op.relu = 1;
+        if (int e = dev_alloc(net, &op.w, w4.size())) return e;
+        B200_CHECK_CUDA(cudaMemcpy(op.w, w4.data(), w4.size() * sizeof(float), cudaMemcpyHostToDevice));
+        if (int e = dev_alloc(net, &op.bias, 64)) return e;
+        B200_CHECK_CUDA(cudaMemcpy(op.bias, b.data(), 64 * sizeof(float), cudaMemcpyHostToDevice));
+        if (int e = new_buf(net, (size_t)op.Hout * op.Wout * 64, &op.out)) return e;
+        net->flops += 2.0 * (double)op.Hout * op.Wout * 64 * 49 * 3;
+        net->ops.push_back(op);
+        H = op.Hout; W = op.Wout;
+    }
+    int x = net->ops.back().out;
+    // maxpool
+    {
+        Op op; op.kind = OP_MAXPOOL; op.in = x; op.Hin = H; op.Win = W; op.Cin = op.Cout = 64;
+        op.Hout = (H + 2 - 3) / 2 + 1; op.Wout = (W + 2 - 3) / 2 + 1;
+        if (int e = new_buf(net, (size_t)op.Hout * op.Wout * 64, &op.out)) return e;
+        net->ops.push_back(op);
+        H = op.Hout; W = op.Wout; x = op.out;
+    }
+    int inplanes = 64;
+    for (int li = 0; li < 3; ++li) {
+        const int planes = 64 << li;
+        for (int bi = 0; bi < nblocks[li]; ++bi) {
+            const int stride = (li > 0 && bi == 0) ? 2 : 1;
+            const int outp = bottleneck ? planes * 4 : planes;
+            const bool has_ds = (bi == 0) && (stride != 1 || inplanes != outp);
+            int c1, c2, c3, ds = -1, h1, w1, h2, w2, h3, w3;
+            if (bottleneck) {
+                if (int e = B.add_conv(x, -1, H, W, inplanes, planes, 1, 1, 0, 1, &c1, &h1, &w1)) return e;
+                if (int e = B.add_conv(c1, -1, h1, w1, planes, planes, 3, stride, 1, 1, &c2, &h2, &w2)) return e;
+                // descriptor order = execution order: conv1, conv2, [downsample], conv3
+                if (has_ds)
+                    if (int e = B.add_conv(x, -1, H, W, inplanes, outp, 1, stride, 0, 0, &ds, &h3, &w3)) return e;
+                if (int e = B.add_conv(c2, has_ds ? ds : x, h2, w2, planes, outp, 1, 1, 0, 1, &c3, &h3, &w3)) return e;
+            } else {
+                if (int e = B.add_conv(x, -1, H, W, inplanes, planes, 3, stride, 1, 1, &c1, &h1, &w1)) return e;
+                if (has_ds)
+                    if (int e = B.add_conv(x, -1, H, W, inplanes, outp, 1, stride, 0, 0, &ds, &h3, &w3)) return e;
+                if (int e = B.add_conv(c1, has_ds ? ds : x, h1, w1, planes, planes, 3, 1, 1, 1, &c3, &h3, &w3)) return e;
+            }
+            x = c3; H = h3; W = w3; inplanes = outp;
+        }
+        if (li >= 1) {
+            Op op; op.kind = OP_EXPORT_NCHW; op.in = x; op.Hin = H; op.Win = W; op.Cin = inplanes; op.export_slot = li - 1;
+            net->ops.push_back(op);
+            net->dims[(li - 1) * 3 + 0] = inplanes; net->dims[(li - 1) * 3 + 1] = H; net->dims[(li - 1) * 3 + 2] = W;
+        }
+    }
+    // classification head
+    int hx = x, hh = H, hw = W, cdim;
+    if (bottleneck) {
+        cdim = 512;
+        if (int e = B.add_conv(x, -1, H, W, inplanes, cdim, 3, 1, 1, 0, &hx, &hh, &hw)) return e;
+    } else {
+        cdim = 256;
+        int c1, c2;
+        if (int e = B.add_conv(x, -1, H, W, inplanes, 256, 3, 1, 1, 1, &c1, &hh, &hw)) return e;
+        if (int e = B.add_conv(c1, x, hh, hw, 256, 256, 3, 1, 1, 1, &c2, &hh, &hw)) return e;
+        if (int e = B.add_conv(c2, -1, hh, hw, 256, cdim, 3, 1, 1, 0, &hx, &hh, &hw)) return e;
+    }
+    {
+        Op op; op.kind = OP_L2NORM_EXPORT; op.in = hx; op.Hin = hh; op.Win = hw; op.Cin = cdim;
+        net->ops.push_back(op);
+        net->dims[6] = cdim; net->dims[7] = hh; net->dims[8] = hw;
+    }
+    B200_REQUIRE(B.next == n_convs, "net_create: %d conv descriptors given, architecture consumes %d", n_convs, B.next);
+    return 0;
+}
+
+}  // namespace b200trk
+
+using namespace b200trk;
+
+extern "C" int b200trk_net_create(b200trk_net_t** out, int arch, const b200trk_conv_desc_t* convs, int n_convs,
+                                  float norm_scale, int max_batch, int crop_h, int crop_w, int precision) {
+    B200_REQUIRE(out && convs, "net_create: null pointer");
+    B200_REQUIRE(max_batch >= 1 && max_batch <= 64, "net_create: max_batch=%d out of range", max_batch);
+    B200_REQUIRE(crop_h >= 32 && crop_w >= 32 && crop_h % 16 == 0 && crop_w % 16 == 0,
+                 "net_create: crop %dx%d must be a multiple of 16", crop_h, crop_w);
+    B200_REQUIRE(precision == 0 || precision == 1, "net_create: precision must be 0 (3xTF32 tensor cores) or 1 (fp32 CUDA cores)");
+    b200trk_net* net = new b200trk_net();
+    net->arch = arch; net->crop_h = crop_h; net->crop_w = crop_w; net->max_batch = max_batch; net->precision = precision;
+    net->norm_scale = norm_scale;
+    net->sms = device_sm_count();
+    int e = build(net, convs, n_convs);
+    if (!e) {
+        net->splitk_ws_floats = (size_t)8 << 20;   // 32 MB of split-K partials
+        e = dev_alloc(net, &net->splitk_ws, net->splitk_ws_floats);
+    }
+    if (!e) e = dev_alloc(net, &net->l2_partials, 64 * 64);
+    if (e) { b200trk_net_destroy(net); return e; }
+    *out = net;
+    return 0;
+}
+
+extern "C" int b200trk_net_destroy(b200trk_net_t* net) {
+    if (!net) return 0;
+    for (auto& op : net->ops) if (op.tc) tc_conv_free(op.tc);
+    for (void* p : net->owned) cudaFree(p);
+    delete net;
+    return 0;
+}
+
+extern "C" int b200trk_net_dims(const b200trk_net_t* net, int dims[9]) {
+    B200_REQUIRE(net && dims, "net_dims: null pointer");
+    memcpy(dims, net->dims, sizeof(int) * 9);
+    return 0;
+}
+
+extern "C" double b200trk_net_flops(const b200trk_net_t* net) { return net ? net->flops : 0.0; }
+
+extern "C" int b200trk_net_forward(b200trk_net_t* net, const float* crop, int S, float* layer2, float* layer3, float* clf,
+                                   b200trk_stream_t stream) {
+    B200_REQUIRE(net && crop, "net_forward: null pointer");
+    B200_REQUIRE(S >= 1 && S <= net->max_batch, "net_forward: batch %d outside [1,%d]", S, net->max_batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (const Op& op : net->ops) {
+        switch (op.kind) {
+        case OP_PREPROCESS:
+            if (int e = launch_preprocess(crop, net->bufs[op.out], S, op.Hin, op.Win, st)) return e;
+            break;
+        case OP_STEM:
+            if (int e = launch_stem_fp32(net->bufs[op.in], op.w, op.bias, net->bufs[op.out], S, op.Hin, op.Win, st)) return e;
+            break;
+        case OP_MAXPOOL:
+            if (int e = launch_maxpool3x3s2(net->bufs[op.in], net->bufs[op.out], S, op.Hin, op.Win, op.Cin, st)) return e;
+            break;
+        case OP_CONV: {
+            if (op.tc) {
+                if (int e = tc_conv_launch(net, op, S, st)) return e;
+                break;
+            }
+            ConvShape sh{S, op.Hin, op.Win, op.Cin, op.Hout, op.Wout, op.Cout, op.k, op.stride, op.pad};
+            ConvEpilogue ep{op.bias, op.res >= 0 ? net->bufs[op.res] : nullptr, op.relu};
+            if (int e = launch_conv_fp32(net->bufs[op.in], op.w, net->bufs[op.out], sh, ep, net->splitk_ws,
+                                         net->splitk_ws_floats, net->sms, st)) return e;
+            break;
+        }
+        case OP_EXPORT_NCHW: {
+            float* dst = op.export_slot == 0 ? layer2 : layer3;
+            if (dst)
+                if (int e = launch_nhwc_to_nchw(net->bufs[op.in], dst, S, op.Hin * op.Win, op.Cin, st)) return e;
+            break;
+        }
+        case OP_L2NORM_EXPORT:
+            if (clf)
+                if (int e = launch_l2norm_nhwc_to_nchw(net->bufs[op.in], clf, net->l2_partials, S, op.Hin * op.Win, op.Cin,
+                                                       net->norm_scale, 1e-5f, st)) return e;
+            break;
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,385 @@
+// Stage 3: the online filter optimisers as ONE persistent cooperative kernel per call.
+//   MODE 0: DiMPSteepestDescentGN      (ltr/models/target_classifier/optimizer.py:85-170)
+//   MODE 1: PrDiMPSteepestDescentNewton (ltr/models/target_classifier/optimizer.py:355-439)
+//
+// Algorithm with one algebraic restructuring: the score maps are carried across
+// iterations by linearity, s_{k+1} = A w_{k+1} = s_k - step*alpha_k * (A g_k), so an iteration costs two
+// sweeps over the sample memory (A^T r and A g) instead of the reference's three.
+//
+// Decomposition: CTA = (channel chunk, sample group); grid = NCH x NG <= #SMs, launched cooperatively.
+// Residual maps, labels, the chunk's filter taps and gradient stay in shared memory for the whole call;
+// the sample memory is streamed from L2 (it is re-read 2x per iteration; 33 MB at n=50 is L2 resident).
+// Cross-CTA exchange per iteration (all via L2, fixed summation order => bitwise deterministic):
+//   gpart [NG][C*16]   partial gradients     -> barrier 1 -> each CTA sums its own chunk over the groups
+//   qpart [n][NCH][NPOS] partial A g maps    -> barrier 2 -> each CTA sums its own samples over the chunks
+//   hpart [NG], gnorm [NCH] scalars          -> barrier 3 -> step length alpha
+#include "corr.cuh"
+
+namespace b200trk {
+
+constexpr int SD_SPC_MAX = 8;    // samples per CTA held in shared memory
+
+struct SdParams {
+    const float* w_in; float* w_out; const float* feat; const float* bb; const float* sample_weight;
+    int n, C, passes, NCH, NG, num_iter;
+    // DiMP
+    const float* label_lut; const float* mask_lut; const float* spatial_lut; int num_bins; float inv_bin_disp;
+    // PrDiMP
+    float gauss_sigma; int has_softmax_reg; float softmax_reg; float label_threshold; int normalize_label;
+    float label_shrink; float uni_weight;
+    // common
+    float inv_feat_stride, step_length, reg_weight, alpha_eps;
+    float* iterates_out; float* losses_out;
+    // workspace
+    float* gpart; float* qpart; float* hpart; float* gnorm; float* lossr; float* lossw; unsigned* barrier;
+};
+
+__device__ __forceinline__ float lut_lerp(const float* lut, int nb, float rho) {
+    // DistanceMap + 1x1 conv == piece-wise linear LUT with last-bin clamp (distance.py:33-37)
+    if (rho >= (float)(nb - 1)) return lut[nb - 1];
+    const int b = (int)rho;                 // rho >= 0
+    const float f = rho - (float)b;
+    return lut[b] * (1.f - f) + lut[b + 1] * f;
+}
+
+template <int FS, int SLOTS, int MODE>
+__global__ void __launch_bounds__(CorrCta<FS, SLOTS>::NTHREADS, 1)
+sd_kernel(SdParams P) {
+    using K = CorrCta<FS, SLOTS>;
+    using G = CorrGeom<FS>;
+    constexpr int NPOS = G::NPOS, OS = G::OS, NTH = K::NTHREADS;
+    extern __shared__ float smem[];
+    float* planes = smem;
+    float* red = planes + K::PLANES_FLOATS;
+    const int cchunk = P.passes * SLOTS;
+    float* wv = red + K::RED_FLOATS;          // [cchunk*16] current filter taps of the chunk
+    float* gv = wv + cchunk * 16;             // [cchunk*16] gradient taps of the chunk
+    float* sS = gv + cchunk * 16;             // [spc][NPOS] scores
+    float* sY = sS + SD_SPC_MAX * NPOS;       // DiMP: label y        | PrDiMP: label density p
+    float* sM = sY + SD_SPC_MAX * NPOS;       // DiMP: target mask m  | PrDiMP: softmax(s)
+    float* sV = sM + SD_SPC_MAX * NPOS;       // DiMP: sqrt(sw)*v     | PrDiMP: unused
+    float* sT = sV + SD_SPC_MAX * NPOS;       // mapped residual, then q = A g
+    __shared__ float s_red[32];
+    __shared__ float s_sw[SD_SPC_MAX];
+    __shared__ float s_scal[4];
+
+    const int tid = threadIdx.x;
+    const int chunk = blockIdx.x % P.NCH, group = blockIdx.x / P.NCH;
+    typename K::Ctx cx{P.feat, P.C, P.n, chunk * cchunk, P.passes, group, P.NG};
+    const int spc = cx.spc();
+    unsigned epoch = 0;
+    const size_t qstride = (size_t)P.NCH * NPOS;
+    const float reg = P.reg_weight;
+
+    // ---- prologue: zero staging planes, load filter chunk, build per-sample label maps ------------------
+    K::zero_planes(planes);
+    for (int o = tid; o < cchunk * 16; o += NTH) wv[o] = P.w_in[(size_t)chunk * cchunk * 16 + o];
+    if (tid < spc) {
+        const int i = cx.sample(tid);
+        s_sw[tid] = P.sample_weight ? P.sample_weight[i] : 1.0f / (float)P.n;
+    }
+    __syncthreads();
+    for (int j = 0; j < spc; ++j) {
+        const int i = cx.sample(j);
+        const float bx = P.bb[4 * i], by = P.bb[4 * i + 1], bw = P.bb[4 * i + 2], bh = P.bb[4 * i + 3];
+        // centre (row, col) in score cells; even filter -> no half-cell offset (optimizer.py:112-113)
+        const float crow = (by + bh / 2.f) * P.inv_feat_stride;
+        const float ccol = (bx + bw / 2.f) * P.inv_feat_stride;
+        if (MODE == 0) {
+            const float sqsw = sqrtf(s_sw[j]);
+            for (int pos = tid; pos < NPOS; pos += NTH) {
+                const float d0 = (float)(pos / OS) - crow, d1 = (float)(pos % OS) - ccol;
+                const float rho = sqrtf(d0 * d0 + d1 * d1) * P.inv_bin_disp;
+                sY[j * NPOS + pos] = lut_lerp(P.label_lut, P.num_bins, rho);
+                sM[j * NPOS + pos] = 1.f / (1.f + expf(-lut_lerp(P.mask_lut, P.num_bins, rho)));
+                sV[j * NPOS + pos] = sqsw * lut_lerp(P.spatial_lut, P.num_bins, rho);
+            }
+        } else {
+            const float c = -1.0f / (2.f * P.gauss_sigma * P.gauss_sigma);
+            const float nrm = 1.f / (2.f * 3.14159265358979323846f * P.gauss_sigma * P.gauss_sigma);
+            float loc = 0.f;
+            for (int pos = tid; pos < NPOS; pos += NTH) {
+                const float d0 = (float)(pos / OS) - crow, d1 = (float)(pos % OS) - ccol;
+                float gss = (expf(c * d0 * d0) * nrm) * expf(c * d1 * d1);
+                gss = (gss > P.label_threshold) ? gss : 0.f;
+                sY[j * NPOS + pos] = gss;
+                loc += gss;
+            }
+            const float tot = block_sum(loc, s_red);
+            const float inv = P.normalize_label ? 1.f / (tot + 1e-8f) : 1.f;
+            for (int pos = tid; pos < NPOS; pos += NTH)
+                sY[j * NPOS + pos] = (1.f - P.label_shrink) *
+                                     ((1.f - P.uni_weight) * (sY[j * NPOS + pos] * inv) + P.uni_weight / (float)NPOS);
+        }
+    }
+    __syncthreads();
+
+    // ---- s0 = A w0 -----------------------------------------------------------------------------------------
+    K::sweep_apply(cx, planes, red, wv, P.qpart + (size_t)chunk * NPOS, qstride);
+    grid_barrier(P.barrier, epoch);
+    for (int o = tid; o < spc * NPOS; o += NTH) {
+        const int j = o / NPOS, pos = o - j * NPOS;
+        const float* qp = P.qpart + (size_t)cx.sample(j) * qstride + pos;
+        float s = 0.f;
+        for (int ch = 0; ch < P.NCH; ++ch) s += __ldcg(qp + (size_t)ch * NPOS);
+        sS[o] = s;
+    }
+    __syncthreads();
+
+    for (int it = 0; it <= P.num_iter; ++it) {
+        // ---- residuals from the current scores (also the loss terms of iterate `it`) -----------------------
+        float lloc = 0.f;
+        if (MODE == 0) {
+            for (int o = tid; o < spc * NPOS; o += NTH) {
+                const float s = sS[o], m = sM[o], vh = sV[o];
+                const float act = 0.5f * (1.f - m) * fabsf(s) + 0.5f * (1.f + m) * s;
+                const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
+                const float dact = 0.5f * (1.f - m) * sg + 0.5f * (1.f + m);
+                const float r = vh * (act - sY[o]);
+                lloc += r * r;
+                sT[o] = dact * (vh * r);
+            }
+        } else {
+            for (int j = 0; j < spc; ++j) {
+                // softmax over the map with one extra constant logit (activation.py:7-16)
+                float mx = P.has_softmax_reg ? P.softmax_reg : -INFINITY;
+                for (int pos = tid; pos < NPOS; pos += NTH) mx = fmaxf(mx, sS[j * NPOS + pos]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                __syncthreads();
+                if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+                __syncthreads();
+                mx = s_red[0];
+                for (int wq = 1; wq < (NTH + 31) / 32; ++wq) mx = fmaxf(mx, s_red[wq]);
+                float se = 0.f, ps = 0.f;
+                for (int pos = tid; pos < NPOS; pos += NTH) {
+                    const float e = expf(sS[j * NPOS + pos] - mx);
+                    sM[j * NPOS + pos] = e;
+                    se += e;
+                    ps += sY[j * NPOS + pos] * sS[j * NPOS + pos];
+                }
+                se = block_sum(se, s_red);
+                ps = block_sum(ps, s_red);
+                const float den = se + (P.has_softmax_reg ? expf(P.softmax_reg - mx) : 0.f);
+                const float inv = 1.f / den;
+                const float sw = s_sw[j];
+                for (int pos = tid; pos < NPOS; pos += NTH) {
+                    const float sm = sM[j * NPOS + pos] * inv;
+                    sM[j * NPOS + pos] = sm;
+                    sT[j * NPOS + pos] = sw * (sm - sY[j * NPOS + pos]);
+                }
+                // loss_i = sw * (log(sum exp(s) + exp(reg)) - sum p*s)  (optimizer.py:393-396)
+                if (tid == 0) lloc += sw * ((logf(den) + mx) - ps);
+            }
+        }
+        if (P.losses_out) {
+            const float lr = block_sum(lloc, s_red);
+            float lw = 0.f;
+            for (int o = tid; o < cchunk * 16; o += NTH) lw += wv[o] * wv[o];
+            lw = block_sum(lw, s_red);
+            if (tid == 0) {
+                if (chunk == 0) P.lossr[it * P.NG + group] = lr;
+                if (group == 0) P.lossw[it * P.NCH + chunk] = lw;
+            }
+        }
+        if (it == P.num_iter) break;
+        __syncthreads();
+
+        // ---- phase 1: partial gradient of the chunk over the CTA's samples -----------------------------------
+        K::sweep_transpose(cx, planes, red, sT, P.gpart + ((size_t)group * P.C + chunk * cchunk) * 16);
+        grid_barrier(P.barrier, epoch);
+
+        // ---- phase 2: g = sum_groups gpart + reg*w ; ||g_chunk||^2 ; partial q = A g ---------------------------
+        float gl = 0.f;
+        for (int o = tid; o < cchunk * 16; o += NTH) {
+            const float* gp = P.gpart + (size_t)chunk * cchunk * 16 + o;
+            float s = 0.f;
+            for (int g = 0; g < P.NG; ++g) s += __ldcg(gp + (size_t)g * P.C * 16);
+            s += reg * wv[o];
+            gv[o] = s;
+            gl += s * s;
+        }
+        gl = block_sum(gl, s_red);
+        if (group == 0 && tid == 0) P.gnorm[chunk] = gl;
+        __syncthreads();
+        K::sweep_apply(cx, planes, red, gv, P.qpart + (size_t)chunk * NPOS, qstride);
+        grid_barrier(P.barrier, epoch);
+
+        // ---- phase 3: q_i over all chunks, curvature term --------------------------------------------------------
+        float hl = 0.f;
+        if (MODE == 0) {
+            for (int o = tid; o < spc * NPOS; o += NTH) {
+                const int j = o / NPOS, pos = o - j * NPOS;
+                const float* qp = P.qpart + (size_t)cx.sample(j) * qstride + pos;
+                float q = 0.f;
+                for (int ch = 0; ch < P.NCH; ++ch) q += __ldcg(qp + (size_t)ch * NPOS);
+                sT[o] = q;
+                const float s = sS[o], m = sM[o];
+                const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
+                const float dact = 0.5f * (1.f - m) * sg + 0.5f * (1.f + m);
+                const float h = sV[o] * (dact * q);
+                hl += h * h;
+            }
+            hl = block_sum(hl, s_red);
+        } else {
+            for (int j = 0; j < spc; ++j) {
+                float dotl = 0.f;
+                for (int pos = tid; pos < NPOS; pos += NTH) {
+                    const float* qp = P.qpart + (size_t)cx.sample(j) * qstride + pos;
+                    float q = 0.f;
+                    for (int ch = 0; ch < P.NCH; ++ch) q += __ldcg(qp + (size_t)ch * NPOS);
+                    sT[j * NPOS + pos] = q;
+                    dotl += sM[j * NPOS + pos] * q;
+                }
+                const float dot = block_sum(dotl, s_red);
+                float gh = 0.f;
+                for (int pos = tid; pos < NPOS; pos += NTH) {
+                    const float q = sT[j * NPOS + pos], sm = sM[j * NPOS + pos];
+                    gh += q * (sm * q - sm * dot);
+                }
+                gh = block_sum(gh, s_red);
+                hl += s_sw[j] * fmaxf(gh, 0.f);   // identical on all threads
+            }
+        }
+        if (chunk == 0 && tid == 0) P.hpart[group] = hl;
+        grid_barrier(P.barrier, epoch);
+
+        // ---- step length and update --------------------------------------------------------------------------------
+        if (tid == 0) {
+            float gn = 0.f, hn = 0.f;
+            for (int ch = 0; ch < P.NCH; ++ch) gn += __ldcg(P.gnorm + ch);
+            for (int g = 0; g < P.NG; ++g) hn += __ldcg(P.hpart + g);
+            const float den = fmaxf(hn + (reg + P.alpha_eps) * gn, 1e-8f);
+            s_scal[0] = P.step_length * (gn / den);
+        }
+        __syncthreads();
+        const float sa = s_scal[0];
+        for (int o = tid; o < spc * NPOS; o += NTH) sS[o] -= sa * sT[o];
+        for (int o = tid; o < cchunk * 16; o += NTH) {
+            const float w = wv[o] - sa * gv[o];
+            wv[o] = w;
+            if (group == 0 && P.iterates_out)
+                P.iterates_out[((size_t)(it + 1) * P.C + chunk * cchunk) * 16 + o] = w;
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue -------------------------------------------------------------------------------------------------------
+    if (group == 0)
+        for (int o = tid; o < cchunk * 16; o += NTH) P.w_out[(size_t)chunk * cchunk * 16 + o] = wv[o];
+    if (P.losses_out) {
+        grid_barrier(P.barrier, epoch);
+        if (blockIdx.x == 0 && tid <= P.num_iter) {
+            float l = 0.f;
+            for (int g = 0; g < P.NG; ++g) l += __ldcg(P.lossr + tid * P.NG + g);
+            float lw = 0.f;
+            for (int ch = 0; ch < P.NCH; ++ch) lw += __ldcg(P.lossw + tid * P.NCH + ch);
+            P.losses_out[tid] = l + reg * lw;
+        }
+    }
+}
+
+template <int FS, int MODE>
+static int launch_sd(SdParams P, cudaStream_t st) {
+    constexpr int SLOTS = CorrSlots<FS>::value;
+    using K = CorrCta<FS, SLOTS>;
+    using G = CorrGeom<FS>;
+    int passes = 0;
+    for (int p = 4; p >= 1; p >>= 1) if (P.C % (SLOTS * p) == 0) { passes = p; break; }
+    B200_REQUIRE(passes > 0, "sd optimizer: C=%d must be a multiple of %d for feature size %d", P.C, SLOTS, FS);
+    const int sms = device_sm_count();
+    int NCH = P.C / (SLOTS * passes);
+    // keep the grid within one wave (cooperative launch) but use as many SMs as possible
+    while (NCH > sms && passes < 64 && P.C % (SLOTS * passes * 2) == 0) { passes *= 2; NCH /= 2; }
+    B200_REQUIRE(NCH <= sms, "sd optimizer: C=%d needs %d channel chunks > %d SMs", P.C, NCH, sms);
+    int NG = sms / NCH; if (NG > P.n) NG = P.n; if (NG < 1) NG = 1;
+    const int spc = (P.n + NG - 1) / NG;
+    B200_REQUIRE(spc <= SD_SPC_MAX, "sd optimizer: n=%d samples need %d samples per CTA (max %d)", P.n, spc, SD_SPC_MAX);
+    B200_REQUIRE(P.num_iter + 1 <= K::NTHREADS, "sd optimizer: num_iter=%d too large", P.num_iter);
+    P.passes = passes; P.NCH = NCH; P.NG = NG;
+
+    const size_t n_gpart = (size_t)NG * P.C * 16, n_qpart = (size_t)P.n * NCH * G::NPOS;
+    const size_t n_loss = (size_t)(P.num_iter + 1) * (NG + NCH);
+    const size_t total = (n_gpart + n_qpart + NG + NCH + n_loss + 64) * sizeof(float) + 256;
+    char* ws = (char*)workspace(total, 2);
+    if (!ws) return 3;
+    P.barrier = (unsigned*)ws;
+    float* f = (float*)(ws + 256);
+    P.gpart = f; f += n_gpart;
+    P.qpart = f; f += n_qpart;
+    P.hpart = f; f += NG;
+    P.gnorm = f; f += NCH;
+    P.lossr = f; f += (size_t)(P.num_iter + 1) * NG;
+    P.lossw = f;
+    B200_CHECK_CUDA(cudaMemsetAsync(P.barrier, 0, 256, st));
+
+    const int cchunk = passes * SLOTS;
+    const size_t smem = (size_t)(K::PLANES_FLOATS + K::RED_FLOATS + 2 * cchunk * 16 + 5 * SD_SPC_MAX * G::NPOS) * sizeof(float);
+    auto kern = sd_kernel<FS, SLOTS, MODE>;
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* args[] = {(void*)&P};
+    B200_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(NCH * NG), dim3(K::NTHREADS), args, smem, st));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+static int check_common(const char* who, const float* w, float* wo, const float* feat, const float* bb, int n, int C,
+                        int H, int W, int k, int num_iter) {
+    B200_REQUIRE(w && wo && feat && bb, "%s: null pointer", who);
+    B200_REQUIRE(n > 0 && C > 0, "%s: empty sample memory (n=%d, C=%d)", who, n, C);
+    B200_REQUIRE(k == 4, "%s: filter size %d not supported by the CUDA path (only 4)", who, k);
+    B200_REQUIRE(H == W && (H == 18 || H == 22), "%s: feature size %dx%d not supported (18x18, 22x22)", who, H, W);
+    B200_REQUIRE(num_iter >= 0, "%s: num_iter=%d", who, num_iter);
+    return 0;
+}
+
+}  // namespace b200trk
+
+using namespace b200trk;
+
+extern "C" int b200trk_dimp_sd_gn(const float* weights, float* weights_out, const float* feat, const float* bb,
+                                  const float* sample_weight, int n, int C, int H, int W, int k, int num_iter,
+                                  const float* label_lut, const float* mask_lut, const float* spatial_lut,
+                                  int num_bins, float bin_displacement, float feat_stride, float step_length,
+                                  float reg_weight, float alpha_eps, float* iterates_out, float* losses_out,
+                                  b200trk_stream_t stream) {
+    if (int e = check_common("dimp_sd_gn", weights, weights_out, feat, bb, n, C, H, W, k, num_iter)) return e;
+    B200_REQUIRE(label_lut && mask_lut && spatial_lut && num_bins >= 2, "dimp_sd_gn: LUTs missing");
+    B200_REQUIRE(bin_displacement > 0.f && feat_stride > 0.f, "dimp_sd_gn: bad bin_displacement / feat_stride");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (iterates_out)
+        B200_CHECK_CUDA(cudaMemcpyAsync(iterates_out, weights, (size_t)C * 16 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SdParams P{};
+    P.w_in = weights; P.w_out = weights_out; P.feat = feat; P.bb = bb; P.sample_weight = sample_weight;
+    P.n = n; P.C = C; P.num_iter = num_iter;
+    P.label_lut = label_lut; P.mask_lut = mask_lut; P.spatial_lut = spatial_lut; P.num_bins = num_bins;
+    P.inv_bin_disp = 1.0f / bin_displacement; P.inv_feat_stride = 1.0f / feat_stride;
+    P.step_length = step_length; P.reg_weight = reg_weight; P.alpha_eps = alpha_eps;
+    P.iterates_out = iterates_out; P.losses_out = losses_out;
+    if (H == 18) return launch_sd<18, 0>(P, st);
+    return launch_sd<22, 0>(P, st);
+}
+
+extern "C" int b200trk_prdimp_sd_newton(const float* weights, float* weights_out, const float* feat, const float* bb,
+                                        const float* sample_weight, int n, int C, int H, int W, int k, int num_iter,
+                                        float gauss_sigma, float feat_stride, float step_length, float reg_weight,
+                                        float alpha_eps, int has_softmax_reg, float softmax_reg, float label_threshold,
+                                        int normalize_label, float label_shrink, float uni_weight,
+                                        float* iterates_out, float* losses_out, b200trk_stream_t stream) {
+    if (int e = check_common("prdimp_sd_newton", weights, weights_out, feat, bb, n, C, H, W, k, num_iter)) return e;
+    B200_REQUIRE(gauss_sigma > 0.f, "prdimp_sd_newton: gauss_sigma must be > 0 (one-hot labels not implemented)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (iterates_out)
+        B200_CHECK_CUDA(cudaMemcpyAsync(iterates_out, weights, (size_t)C * 16 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SdParams P{};
+    P.w_in = weights; P.w_out = weights_out; P.feat = feat; P.bb = bb; P.sample_weight = sample_weight;
+    P.n = n; P.C = C; P.num_iter = num_iter;
+    P.gauss_sigma = gauss_sigma; P.has_softmax_reg = has_softmax_reg; P.softmax_reg = softmax_reg;
+    P.label_threshold = label_threshold; P.normalize_label = normalize_label; P.label_shrink = label_shrink;
+    P.uni_weight = uni_weight;
+    P.inv_feat_stride = 1.0f / feat_stride;
+    P.step_length = step_length; P.reg_weight = reg_weight; P.alpha_eps = alpha_eps;
+    P.iterates_out = iterates_out; P.losses_out = losses_out;
+    if (H == 18) return launch_sd<18, 1>(P, st);
+    return launch_sd<22, 1>(P, st);
+}

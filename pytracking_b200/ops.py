@@ -1,0 +1,143 @@
+"""Torch-tensor wrappers over the C ABI (device pointers + current stream; torch is plumbing only).
+
+Every function requires CUDA tensors and raises if they are not (no CPU / eager fallback).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("b200trk: '%s' must be a CUDA tensor (the engine has no CPU path)" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("b200trk: '%s' must be float32, got %s" % (name, t.dtype))
+    return t.contiguous()
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def apply_filter(feat, filt, return_max=False):
+    """feat [n,C,H,W], filt [1,C,k,k] -> scores [n,1,Ho,Wo] (and max2d values / indices)."""
+    feat, filt = _dev(feat, "feat"), _dev(filt, "filter")
+    n, c, h, w = feat.shape
+    k = filt.shape[-1]
+    if filt.shape != (1, c, k, k):
+        raise RuntimeError("b200trk.apply_filter: filter shape %s does not match features %s" % (tuple(filt.shape), tuple(feat.shape)))
+    ho, wo = h + (k + 1) % 2, w + (k + 1) % 2
+    scores = torch.empty(n, 1, ho, wo, device=feat.device, dtype=torch.float32)
+    mv = mi = None
+    if return_max:
+        mv = torch.empty(n, device=feat.device, dtype=torch.float32)
+        mi = torch.empty(n, 2, device=feat.device, dtype=torch.int64)
+    _lib.check(_lib.lib().b200trk_apply_filter(_p(feat), _p(filt), _p(scores), n, c, h, w, k, _p(mv), _p(mi), _stream()),
+               "apply_filter")
+    return (scores, mv, mi) if return_max else scores
+
+
+def apply_feat_transpose(feat, resid, k):
+    """feat [n,C,H,W], resid [n,1,Ho,Wo] -> [1,C,k,k]."""
+    feat, resid = _dev(feat, "feat"), _dev(resid, "input")
+    n, c, h, w = feat.shape
+    ho, wo = h + (k + 1) % 2, w + (k + 1) % 2
+    if resid.numel() != n * ho * wo:
+        raise RuntimeError("b200trk.apply_feat_transpose: input has %d elements, expected %d" % (resid.numel(), n * ho * wo))
+    grad = torch.empty(1, c, k, k, device=feat.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200trk_apply_feat_transpose(_p(feat), _p(resid), _p(grad), n, c, h, w, k, _stream()),
+               "apply_feat_transpose")
+    return grad
+
+
+def max2d(a):
+    """a [..., H, W] -> (max values [...], indices [..., 2]) with the reference's tie order."""
+    a = _dev(a, "a")
+    lead = a.shape[:-2]
+    h, w = a.shape[-2:]
+    n = 1
+    for d in lead:
+        n *= d
+    mv = torch.empty(n, device=a.device, dtype=torch.float32)
+    mi = torch.empty(n, 2, device=a.device, dtype=torch.int64)
+    _lib.check(_lib.lib().b200trk_max2d(_p(a), n, h, w, _p(mv), _p(mi), _stream()), "max2d")
+    return mv.reshape(lead), mi.reshape(*lead, 2)
+
+
+def dimp_sd_gn(weights, feat, bb, sample_weight, label_lut, mask_lut, spatial_lut, num_iter, step_length, reg_weight,
+               alpha_eps=0.0, bin_displacement=0.1, feat_stride=16.0, return_iterates=False, compute_losses=False,
+               out=None):
+    weights, feat, bb = _dev(weights, "weights"), _dev(feat, "feat"), _dev(bb, "bb")
+    n, c, h, w = feat.shape
+    k = weights.shape[-1]
+    if sample_weight is not None:
+        sample_weight = _dev(sample_weight, "sample_weight")
+    luts = [_dev(t, "lut").reshape(-1) for t in (label_lut, mask_lut, spatial_lut)]
+    nb = luts[0].numel()
+    wout = out if out is not None else torch.empty_like(weights)
+    its = torch.empty(num_iter + 1, c, k, k, device=feat.device, dtype=torch.float32) if return_iterates else None
+    losses = torch.empty(num_iter + 1, device=feat.device, dtype=torch.float32) if compute_losses else None
+    _lib.check(_lib.lib().b200trk_dimp_sd_gn(
+        _p(weights), _p(wout), _p(feat), _p(bb), _p(sample_weight), n, c, h, w, k, int(num_iter),
+        _p(luts[0]), _p(luts[1]), _p(luts[2]), nb, float(bin_displacement), float(feat_stride),
+        float(step_length), float(reg_weight), float(alpha_eps), _p(its), _p(losses), _stream()), "dimp_sd_gn")
+    return wout, its, losses
+
+
+def prdimp_sd_newton(weights, feat, bb, sample_weight, num_iter, gauss_sigma, step_length, reg_weight, alpha_eps=0.0,
+                     softmax_reg=None, label_threshold=0.0, normalize_label=False, label_shrink=0.0, uni_weight=0.0,
+                     feat_stride=16.0, return_iterates=False, compute_losses=False, out=None):
+    weights, feat, bb = _dev(weights, "weights"), _dev(feat, "feat"), _dev(bb, "bb")
+    n, c, h, w = feat.shape
+    k = weights.shape[-1]
+    if sample_weight is not None:
+        sample_weight = _dev(sample_weight, "sample_weight")
+    wout = out if out is not None else torch.empty_like(weights)
+    its = torch.empty(num_iter + 1, c, k, k, device=feat.device, dtype=torch.float32) if return_iterates else None
+    losses = torch.empty(num_iter + 1, device=feat.device, dtype=torch.float32) if compute_losses else None
+    _lib.check(_lib.lib().b200trk_prdimp_sd_newton(
+        _p(weights), _p(wout), _p(feat), _p(bb), _p(sample_weight), n, c, h, w, k, int(num_iter),
+        float(gauss_sigma), float(feat_stride), float(step_length), float(reg_weight), float(alpha_eps),
+        0 if softmax_reg is None else 1, 0.0 if softmax_reg is None else float(softmax_reg), float(label_threshold),
+        1 if normalize_label else 0, float(label_shrink), float(uni_weight), _p(its), _p(losses), _stream()),
+        "prdimp_sd_newton")
+    return wout, its, losses
+
+
+def prroi_pool_forward(features, rois, ph, pw, scale):
+    features, rois = _dev(features, "features"), _dev(rois, "rois")
+    b, c, h, w = features.shape
+    r = rois.shape[0]
+    out = torch.zeros(r, c, ph, pw, device=features.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200trk_prroi_pool_forward(_p(features), _p(rois), _p(out), b, c, h, w, r, int(ph), int(pw),
+                                                     float(scale), _stream()), "prroi_pool_forward")
+    return out
+
+
+def prroi_pool_backward(features, rois, output, output_grad, ph, pw, scale):
+    features, rois, output, output_grad = (_dev(features, "features"), _dev(rois, "rois"), _dev(output, "output"),
+                                           _dev(output_grad, "output_diff"))
+    b, c, h, w = features.shape
+    r = rois.shape[0]
+    fg = torch.empty_like(features)
+    _lib.check(_lib.lib().b200trk_prroi_pool_backward(_p(features), _p(rois), _p(output), _p(output_grad), _p(fg), b, c, h, w,
+                                                      r, int(ph), int(pw), float(scale), _stream()), "prroi_pool_backward")
+    return fg
+
+
+def prroi_pool_coor_backward(features, rois, output, output_grad, ph, pw, scale):
+    features, rois, output, output_grad = (_dev(features, "features"), _dev(rois, "rois"), _dev(output, "output"),
+                                           _dev(output_grad, "output_diff"))
+    b, c, h, w = features.shape
+    r = rois.shape[0]
+    rg = torch.zeros(r, 5, device=features.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200trk_prroi_pool_coor_backward(_p(features), _p(rois), _p(output), _p(output_grad), _p(rg), b, c,
+                                                           h, w, r, int(ph), int(pw), float(scale), _stream()),
+               "prroi_pool_coor_backward")
+    return rg

@@ -1,0 +1,164 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the committed golden vectors.
+Tolerances: score maps / filter weights <= 1e-4 relative (fp32), indices bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from pytracking_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64).cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def G(golden_dir):
+    return {n: np.load(os.path.join(golden_dir, n + ".npz")) for n in ("corr", "labels", "dimp_sd", "prdimp_sd", "backbone")}
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from pytracking_b200 import ops as o
+    return o
+
+
+@pytest.mark.parametrize("tag,n,c,h", [("a", 3, 32, 18), ("b", 2, 64, 22)])
+def test_apply_filter_golden(G, ops, tag, n, c, h):
+    g = G["corr"]
+    feat = synth.make_clf_features(100 + ord(tag), n, c, h, h).cuda()
+    w = torch.from_numpy(g[tag + "_w"]).cuda()
+    s, mv, mi = ops.apply_filter(feat, w, return_max=True)
+    assert _rel(s, g[tag + "_scores"].reshape(s.shape)) < 1e-5
+    assert np.array_equal(mi.cpu().numpy(), g[tag + "_maxidx"])
+    assert _rel(mv, g[tag + "_maxval"]) < 1e-5
+    r = torch.from_numpy(g[tag + "_r"])[:, 0:1].cuda()
+    gt = ops.apply_feat_transpose(feat, r, 4)
+    assert _rel(gt, g[tag + "_grad"]) < 1e-5
+
+
+@pytest.mark.parametrize("n,c,h", [(1, 512, 18), (5, 512, 18), (50, 512, 18), (17, 256, 18), (3, 512, 22), (33, 64, 22)])
+def test_apply_filter_oracle(ops, n, c, h):
+    from oracle import dimp_oracle as O
+    feat = synth.make_clf_features(7 * n + c, n, c, h, h)
+    w = torch.randn(1, c, 4, 4, generator=torch.Generator().manual_seed(n)) * 0.3
+    s_ref = O.apply_filter(feat, w)
+    s, mv, mi = ops.apply_filter(feat.cuda(), w.cuda(), return_max=True)
+    assert _rel(s, s_ref) < 1e-5
+    mv_ref, mi_ref = O.max2d(s.cpu()[:, 0])          # arg-max of the engine's own map must follow the reference rule
+    assert torch.equal(mi.cpu(), mi_ref) and torch.equal(mv.cpu(), mv_ref)
+    r = torch.randn(n, 1, h + 1, h + 1, generator=torch.Generator().manual_seed(n + 1))
+    g_ref = O.apply_feat_transpose(feat, r, 4)
+    g = ops.apply_feat_transpose(feat.cuda(), r.cuda(), 4)
+    assert _rel(g, g_ref) < 1e-5
+    # adjointness: <A w, r> == <w, A^T r>
+    lhs = float((s.cpu().double() * r.double()).sum())
+    rhs = float((w.double() * g.cpu().double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+
+
+def test_max2d_ties(ops):
+    a = torch.zeros(3, 19, 19)
+    a[0, 3, 1] = 1.0; a[0, 1, 3] = 1.0
+    a[1, 4, 2] = 2.0; a[1, 2, 2] = 2.0
+    a[2] = -1.0; a[2, 18, 18] = -0.5
+    mv, mi = ops.max2d(a.cuda())
+    assert mi.cpu().tolist() == [[3, 1], [2, 2], [18, 18]]
+    assert mv.cpu().tolist() == [1.0, 2.0, -0.5]
+
+
+@pytest.mark.parametrize("tag,n,c,h,it,use_sw,seed", [("n15_it10", 15, 512, 18, 10, True, 21), ("n50_it2", 50, 512, 18, 2, True, 22),
+                                                      ("n4_c64", 4, 64, 18, 3, False, 23), ("n7_22", 7, 128, 22, 4, True, 24)])
+def test_dimp_sd_golden(G, ops, tag, n, c, h, it, use_sw, seed):
+    g = G["dimp_sd"]
+    p = synth.make_dimp_optimizer_params(seed=seed)
+    feat = synth.make_clf_features(seed, n, c, h, h).cuda()
+    bb = synth.make_boxes(seed + 1, n, center=(h * 16) / 2 - 25).cuda()
+    sw = torch.from_numpy(g[tag + "_sw"]).cuda() if use_sw else None
+    step = float(torch.exp(p["log_step_length"]))
+    reg = max(float(p["filter_reg"]) ** 2, 1e-3 ** 2)
+    w, its, losses = ops.dimp_sd_gn(torch.from_numpy(g[tag + "_w0"]).cuda(), feat, bb, sw,
+                                    p["label_map_predictor.weight"].cuda(), p["target_mask_predictor.0.weight"].cuda(),
+                                    p["spatial_weight_predictor.weight"].cuda(), it, step, reg,
+                                    return_iterates=True, compute_losses=True)
+    assert _rel(its[1], g[tag + "_w1"][0]) < 1e-4
+    assert _rel(w, g[tag + "_wfinal"]) < 1e-4
+    assert _rel(its[-1], g[tag + "_wfinal"][0]) < 1e-4
+    assert np.allclose(losses.cpu().numpy(), g[tag + "_losses"], rtol=1e-4)
+    # run-to-run bitwise determinism (fixed summation order)
+    w2, _, _ = ops.dimp_sd_gn(torch.from_numpy(g[tag + "_w0"]).cuda(), feat, bb, sw,
+                              p["label_map_predictor.weight"].cuda(), p["target_mask_predictor.0.weight"].cuda(),
+                              p["spatial_weight_predictor.weight"].cuda(), it, step, reg)
+    assert torch.equal(w, w2)
+
+
+def test_dimp_sd_full_size_properties(ops):
+    """BASELINE size (n=50, C=512, 10 iterations): loss decreases monotonically; zero iterations is the identity."""
+    p = synth.make_dimp_optimizer_params(seed=3)
+    feat = synth.make_clf_features(77, 50, 512, 18, 18).cuda()
+    bb = synth.make_boxes(78, 50).cuda()
+    sw = torch.full((50,), 1.0 / 50).cuda()
+    luts = [p[k].cuda() for k in ("label_map_predictor.weight", "target_mask_predictor.0.weight", "spatial_weight_predictor.weight")]
+    w0 = torch.zeros(1, 512, 4, 4).cuda()
+    w, its, losses = ops.dimp_sd_gn(w0, feat, bb, sw, *luts, 10, 0.9, 0.01, return_iterates=True, compute_losses=True)
+    l = losses.cpu().numpy()
+    assert np.all(np.diff(l) < 0), l
+    w_id, _, _ = ops.dimp_sd_gn(w, feat, bb, sw, *luts, 0, 0.9, 0.01)
+    assert torch.equal(w_id, w)
+    # the carried score maps (linear recurrence) must agree with a fresh correlation of the final filter
+    from oracle import dimp_oracle as O
+    w_ref, _, l_ref = O.dimp_sd_gn(w0.cpu(), feat.cpu(), bb.cpu(), sw.cpu(), p, 10, min_filter_reg=0.1)
+    assert _rel(w, w_ref) < 1e-4
+    assert np.allclose(l, [float(x) for x in l_ref], rtol=1e-4)
+
+
+@pytest.mark.parametrize("tag,n,c,h,it,seed,sreg,lthr", [("n15_22", 15, 512, 22, 10, 31, None, 0.0), ("n6_18", 6, 64, 18, 3, 32, -2.0, 0.05)])
+def test_prdimp_sd_golden(G, ops, tag, n, c, h, it, seed, sreg, lthr):
+    g = G["prdimp_sd"]
+    feat = synth.make_clf_features(seed, n, c, h, h).cuda()
+    bb = synth.make_boxes(seed + 1, n, center=(h * 16) / 2 - 25).cuda()
+    w, its, losses = ops.prdimp_sd_newton(torch.from_numpy(g[tag + "_w0"]).cuda(), feat, bb, torch.from_numpy(g[tag + "_sw"]).cuda(),
+                                          it, float(g[tag + "_sigma"]), 1.0, 0.05 ** 2, alpha_eps=0.05, softmax_reg=sreg,
+                                          label_threshold=lthr, normalize_label=True,
+                                          label_shrink=0.0 if sreg is None else 0.1, return_iterates=True, compute_losses=True)
+    assert _rel(its[1], g[tag + "_w1"][0]) < 1e-4
+    assert _rel(w, g[tag + "_wfinal"]) < 1e-4
+    assert np.allclose(losses.cpu().numpy(), g[tag + "_losses"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("arch,size,seed,precision", [("resnet50", 96, 42, 1), ("resnet18", 96, 42, 1), ("resnet50", 288, 41, 1),
+                                                      ("resnet50", 96, 42, 0), ("resnet18", 96, 42, 0), ("resnet50", 288, 41, 0)])
+def test_backbone_golden(G, arch, size, seed, precision):
+    from pytracking_b200.engine import BackboneEngine
+    g = G["backbone"]
+    sd = synth.make_dimp_state_dict(arch, seed=0, lut_seed=3)
+    eng = BackboneEngine(sd, arch=arch, max_batch=2, crop_size=size, precision=precision)
+    im = synth.make_crop(seed, 1, size).cuda()
+    out = eng.forward(im)
+    tag = "%s_%d_" % (arch, size)
+    l2 = out["layer2"] if size == 96 else out["layer2"][:, ::8]
+    assert _rel(l2, g[tag + "layer2"]) < 1e-4
+    assert _rel(out["layer3"], g[tag + "layer3"]) < 1e-4
+    assert _rel(out["classification"], g[tag + "clf"]) < 1e-4
+    # batch of 2 identical crops gives identical rows
+    out2 = eng.forward(torch.cat([im, im]))
+    assert torch.equal(out2["classification"][0], out2["classification"][1])
+    assert _rel(out2["classification"][0], g[tag + "clf"][0]) < 1e-4
+    eng.close()
+
+
+def test_prroi_known_answer(ops):
+    """The reference's only known-answer test (PreciseRoIPooling/pytorch/tests/test_prroi_pooling2d.py:21-35):
+    on integer-aligned RoIs with spatial_scale 0.5, PrRoIPool 7x7 equals avg_pool2d(k=2, s=1) slices."""
+    import torch.nn.functional as F
+    feat = torch.rand(4, 16, 24, 32, generator=torch.Generator().manual_seed(0)).cuda()
+    rois = torch.tensor([[0, 0, 0, 14, 14], [1, 14, 14, 28, 28]], dtype=torch.float32).cuda()
+    out = ops.prroi_pool_forward(feat, rois, 7, 7, 0.5)
+    ref = F.avg_pool2d(feat, kernel_size=2, stride=1)
+    assert torch.allclose(out[0], ref[0, :, :7, :7], atol=1e-6)
+    assert torch.allclose(out[1], ref[1, :, 7:14, 7:14], atol=1e-6)
