@@ -273,3 +273,44 @@ def prdimp_sd_newton(w, feat, bb, sample_weight, log_step_length, filter_reg, nu
     if compute_losses:
         losses.append(loss_fn(apply_filter(feat, w)[:, 0], w))
     return w, iterates, losses
+
+
+# ----------------------------------------------------------------------------------------------
+# Library-call formulation (what the reference actually executes on CPU: grouped F.conv2d), used as the
+# timed CPU baseline in bench.py; tests check it against the explicit formulas above.
+# ----------------------------------------------------------------------------------------------
+def apply_filter_conv(feat, w):
+    """filter.py:54-57 -- one sequence: a plain conv with the filter as the single output channel."""
+    k = w.shape[-1]
+    return F.conv2d(feat, w, padding=k // 2)
+
+
+def apply_feat_transpose_conv(feat, r, k):
+    """filter.py:129-155 (_v2, the eval-mode path): features as kernels, groups = samples, sum, flip."""
+    n, c = feat.shape[:2]
+    g = F.conv2d(r.reshape(1, n, r.shape[-2], r.shape[-1]), feat.reshape(n * c, 1, feat.shape[-2], feat.shape[-1]),
+                 padding=(k - 1) // 2, groups=n)
+    return g.reshape(n, c, g.shape[-2], g.shape[-1]).sum(dim=0, keepdim=True).flip((2, 3))
+
+
+def dimp_sd_gn_conv(w, feat, bb, sample_weight, params, num_iter, min_filter_reg=1e-3, alpha_eps=0.0,
+                    feat_stride=16, bin_displacement=0.1):
+    """Same iteration as dimp_sd_gn but with the reference's three library sweeps per iteration (no losses)."""
+    n = feat.shape[0]
+    k = w.shape[-1]
+    out_sz = (feat.shape[-2] + (k + 1) % 2, feat.shape[-1] + (k + 1) % 2)
+    step = torch.exp(params["log_step_length"]).item()
+    reg = max(params["filter_reg"].item() ** 2, min_filter_reg ** 2)
+    y, m, v = dimp_label_maps(bb, params, out_sz, k, feat_stride, bin_displacement)
+    vh = (math.sqrt(1.0 / n) * v) if sample_weight is None else sample_weight.sqrt().reshape(n, 1, 1) * v
+    for _ in range(num_iter):
+        s = apply_filter_conv(feat, w)[:, 0]
+        act = (1.0 - m) / 2.0 * s.abs() + (1.0 + m) / 2.0 * s
+        dact = (1.0 - m) / 2.0 * torch.sign(s) + (1.0 + m) / 2.0
+        r = vh * (act - y)
+        g = apply_feat_transpose_conv(feat, (dact * (vh * r)).unsqueeze(1), k) + reg * w
+        h = vh * (dact * apply_filter_conv(feat, g)[:, 0])
+        a_num = (g * g).sum()
+        a_den = ((h * h).sum() + (reg + alpha_eps) * a_num).clamp(min=1e-8)
+        w = w - (step * (a_num / a_den)) * g
+    return w

@@ -95,3 +95,17 @@ def test_backbone_and_head(G, arch, size, seed):
     assert _rel(l2, g[tag + "layer2"]) < 1e-5
     assert _rel(bf["layer3"], g[tag + "layer3"]) < 1e-5
     assert _rel(clf, g[tag + "clf"]) < 1e-5
+
+
+def test_conv_formulation_matches_explicit():
+    feat = synth.make_clf_features(9, 6, 64, 18, 18)
+    g = torch.Generator().manual_seed(4)
+    w = torch.randn(1, 64, 4, 4, generator=g) * 0.1
+    r = torch.randn(6, 1, 19, 19, generator=g)
+    assert _rel(O.apply_filter_conv(feat, w), O.apply_filter(feat, w)) < 1e-5
+    assert _rel(O.apply_feat_transpose_conv(feat, r, 4), O.apply_feat_transpose(feat, r, 4)) < 1e-5
+    p = synth.make_dimp_optimizer_params(seed=2)
+    bb = synth.make_boxes(3, 6)
+    w1 = O.dimp_sd_gn_conv(w, feat, bb, None, p, 3)
+    w2, _, _ = O.dimp_sd_gn(w, feat, bb, None, p, 3, compute_losses=False)
+    assert _rel(w1, w2) < 1e-4
