@@ -139,6 +139,12 @@ int b200trk_net_forward(b200trk_net_t* net, const float* crop, int S,
 int b200trk_net_dims(const b200trk_net_t* net, int dims[9]);
 /* FLOPs (2*MAC) of one forward pass at batch 1, for roofline accounting. */
 double b200trk_net_flops(const b200trk_net_t* net);
+/* Introspection of the execution plan (tests / profiling): number of plan steps; per step
+ * info = {kind (0 preprocess,1 stem,2 maxpool,3 conv,4 export,5 l2norm), Cin, Cout, k, stride, Hout, Wout, runs_on_tensor_cores};
+ * and a device-to-device copy of a step's NHWC output activation [S,Hout,Wout,Cout] after a forward pass. */
+int b200trk_net_num_ops(const b200trk_net_t* net);
+int b200trk_net_op_info(const b200trk_net_t* net, int index, int info[8]);
+int b200trk_net_op_output(const b200trk_net_t* net, int index, int S, float* dst, b200trk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Native op -- Precise RoI Pooling (the reference's only CUDA component)

@@ -1,11 +1,520 @@
-// Tensor-core (tcgen05, error-compensated 3xTF32) implicit-GEMM convolution -- see DESIGN.md.
-// PLACEHOLDER until the tcgen05 kernel lands: reports "unsupported" so that every conv runs on the fp32 CUDA-core kernel.
+// Stage 1 on the 5th-generation tensor cores: implicit-GEMM convolution (+ folded BN bias, residual add, ReLU) with
+// TMA-staged im2col tiles feeding tcgen05.mma, accumulators in TMEM.
+//
+//   D[m][n] = sum_k A[m][k] * W[n][k]     m = output pixel, n = output channel, k = (kh, kw, cin)
+//
+// fp32 fidelity on a TF32 datapath: every operand is stored as a (hi, lo) pair of TF32-representable fp32 numbers,
+// x = hi + lo (+ <= 2^-22 |x|), and each K-step issues three MMAs  A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  into the same
+// fp32 TMEM accumulator ("3xTF32"); the dropped A_lo*B_lo term is O(2^-22) relative. Weights are split once at
+// net_create; activations are split by the producing kernel's epilogue (raw, hi, lo are all written).
+//
+// Tiling: CTA = 128 output pixels (a BW x BH rectangle of one sample, rows ordered (y, x)) x BN output channels.
+// K is walked in 128-byte blocks (32 input channels of one filter tap): one 4-D TMA box {32 ch, BW*stride, BH*stride, 1}
+// (element strides {1, stride, stride, 1}; halo / padding = TMA out-of-bounds zero fill) lands the A tile directly in
+// the canonical K-major SWIZZLE_128B layout that the UMMA shared-memory descriptor expects; a 2-D box {32, BN}
+// does the same for the weights. Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2-5 = epilogue (tcgen05.ld -> registers -> bias/residual/ReLU -> global). Small layers use split-K over
+// gridDim.z; partial tiles go to an L2-resident workspace and the last CTA of a tile reduces them in split order
+// (fixed order => bitwise deterministic).
 #include "net.cuh"
+#include <cuda.h>
+#include <cstdlib>
+#include <cstring>
 
 namespace b200trk {
-struct TcConv { int unused; };
-bool tc_conv_supported(const Op&) { return false; }
-int tc_conv_prepare(b200trk_net*, Op&, const std::vector<float>&) { return 0; }
-int tc_conv_launch(b200trk_net*, const Op&, int, cudaStream_t) { set_error("tc conv not built"); return 9; }
+
+constexpr int TC_BM = 128;          // UMMA M
+constexpr int TC_KB = 32;           // fp32 elements per 128-byte K block
+constexpr int TC_THREADS = 192;     // 6 warps
+constexpr int TC_MAX_STAGES = 6;
+constexpr long long TC_WAIT_LIMIT_CLOCKS = 4000000000ll;    // ~2 s: a broken pipeline traps instead of hanging the GPU
+
+struct TcParams {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    float* out_raw; float* out_hi; float* out_lo;
+    const float* bias; const float* residual;
+    float* ws; unsigned* counters;
+    int BW, BH, tiles_w, tiles_h;
+    int Hout, Wout, Cout, Cin;
+    int ksz, stride, pad;
+    int BN, stages;
+    int total_kb, kb_per_split, splits, cblks;
+    int relu;
+    uint32_t a_bytes, b_bytes;
+};
+
+struct TcConv {
+    TcParams P;
+    float *w_hi = nullptr, *w_lo = nullptr;
+    int S_built = 0;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    long long t0 = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        if ((++spins & 1023u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > TC_WAIT_LIMIT_CLOCKS) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, single CTA
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, SWIZZLE_128B canonical layout: rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO), descriptor version 1
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
+    d |= (uint64_t)1 << 46;                 // version
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = tf32_rna(x);
+    lo = tf32_rna(x - hi);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_store_row(const TcParams& P, size_t off, int n, float (&f)[32]) {
+    // bias + residual + ReLU, then raw / hi / lo
+    if (P.bias) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + n) + q);
+            f[4 * q] += b.x; f[4 * q + 1] += b.y; f[4 * q + 2] += b.z; f[4 * q + 3] += b.w;
+        }
+    }
+    if (P.residual) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(P.residual + off) + q);
+            f[4 * q] += r.x; f[4 * q + 1] += r.y; f[4 * q + 2] += r.z; f[4 * q + 3] += r.w;
+        }
+    }
+    if (P.relu) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) f[q] = fmaxf(f[q], 0.f);
+    }
+    float4* o_raw = reinterpret_cast<float4*>(P.out_raw + off);
+    float4* o_hi = reinterpret_cast<float4*>(P.out_hi + off);
+    float4* o_lo = reinterpret_cast<float4*>(P.out_lo + off);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        float4 h, l;
+        split_tf32(f[4 * q], h.x, l.x); split_tf32(f[4 * q + 1], h.y, l.y);
+        split_tf32(f[4 * q + 2], h.z, l.z); split_tf32(f[4 * q + 3], h.w, l.w);
+        o_raw[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        o_hi[q] = h;
+        o_lo[q] = l;
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
+    extern __shared__ uint8_t tc_smem_raw[];
+    __shared__ __align__(8) uint64_t s_full[TC_MAX_STAGES];
+    __shared__ __align__(8) uint64_t s_empty[TC_MAX_STAGES];
+    __shared__ __align__(8) uint64_t s_tmem_full;
+    __shared__ uint32_t s_tmem_base;
+    __shared__ int s_is_last;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_tile = (uint32_t)TC_BM * 128u;                     // 16 KB slot regardless of the box size
+    const uint32_t b_tile = (uint32_t)P.BN * 128u;
+    const uint32_t stage_bytes = 2u * a_tile + 2u * b_tile;
+
+    // tile coordinates
+    const int tiles_per_sample = P.tiles_w * P.tiles_h;
+    const int s = blockIdx.x / tiles_per_sample;
+    const int trem = blockIdx.x - s * tiles_per_sample;
+    const int th = trem / P.tiles_w, tw = trem - th * P.tiles_w;
+    const int n0 = blockIdx.y * P.BN;
+    const int kb0 = blockIdx.z * P.kb_per_split;
+    const int kb1 = min(P.total_kb, kb0 + P.kb_per_split);
+    const int nkb = kb1 - kb0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P.stages; ++i) { mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_empty[i]), 1); }
+        mbar_init(smem_u32(&s_tmem_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"((uint32_t)P.BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const int x0 = tw * P.BW * P.stride - P.pad, y0 = th * P.BH * P.stride - P.pad;
+            for (int it = 0; it < nkb; ++it) {
+                const int kb = kb0 + it;
+                const int st = it % P.stages;
+                const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
+                mbar_wait(smem_u32(&s_empty[st]), ph ^ 1u);
+                const uint32_t full = smem_u32(&s_full[st]);
+                mbar_expect_tx(full, 2u * P.a_bytes + 2u * P.b_bytes);
+                const int tap = kb / P.cblks, cb = kb - tap * P.cblks;
+                const int kh = tap / P.ksz, kw = tap - kh * P.ksz;
+                const uint32_t sa = smem_base + (uint32_t)st * stage_bytes;
+                tma_load_4d(sa, &P.a_hi, full, cb * TC_KB, x0 + kw, y0 + kh, s);
+                tma_load_4d(sa + a_tile, &P.a_lo, full, cb * TC_KB, x0 + kw, y0 + kh, s);
+                tma_load_2d(sa + 2u * a_tile, &P.b_hi, full, tap * P.Cin + cb * TC_KB, n0);
+                tma_load_2d(sa + 2u * a_tile + b_tile, &P.b_lo, full, tap * P.Cin + cb * TC_KB, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = TF32, both K-major, N = BN, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            for (int it = 0; it < nkb; ++it) {
+                const int st = it % P.stages;
+                const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
+                mbar_wait(smem_u32(&s_full[st]), ph);
+                tc_fence_after();
+                const uint32_t sa = smem_base + (uint32_t)st * stage_bytes;
+                const uint64_t d_ah = make_smem_desc(sa), d_al = make_smem_desc(sa + a_tile);
+                const uint64_t d_bh = make_smem_desc(sa + 2u * a_tile), d_bl = make_smem_desc(sa + 2u * a_tile + b_tile);
+#pragma unroll
+                for (int k = 0; k < TC_KB / 8; ++k) {
+                    const uint64_t adv = (uint64_t)(k * 32 >> 4);      // 8 tf32 = 32 bytes per UMMA K step
+                    tc_mma_tf32(tmem_base, d_al + adv, d_bh + adv, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    tc_mma_tf32(tmem_base, d_ah + adv, d_bl + adv, idesc, 1u);
+                    tc_mma_tf32(tmem_base, d_ah + adv, d_bh + adv, idesc, 1u);
+                }
+                tc_commit(smem_u32(&s_empty[st]));
+            }
+            tc_commit(smem_u32(&s_tmem_full));
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                          // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;                   // accumulator row = pixel inside the tile
+        const int ly = row / P.BW, lx = row - ly * P.BW;
+        const int oy = th * P.BH + ly, ox = tw * P.BW + lx;
+        const bool valid = (row < P.BW * P.BH) && (oy < P.Hout) && (ox < P.Wout);
+        const size_t m = ((size_t)s * P.Hout + oy) * P.Wout + ox;
+        const int tile_lin = blockIdx.y * gridDim.x + blockIdx.x;
+        const int num_tiles = gridDim.x * gridDim.y;
+        mbar_wait(smem_u32(&s_tmem_full), 0);
+        tc_fence_after();
+        const int nchunks = P.BN / 32;
+        if (P.splits == 1) {
+            for (int c = 0; c < nchunks; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                if (valid) {
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                    tc_store_row(P, m * P.Cout + n0 + c * 32, n0 + c * 32, f);
+                }
+            }
+        } else {
+            float* wsp = P.ws + (((size_t)blockIdx.z * num_tiles + tile_lin) * TC_BM + row) * P.BN;
+            for (int c = 0; c < nchunks; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                if (valid) {
+                    float4* dst = reinterpret_cast<float4*>(wsp + c * 32);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        __stcg(dst + i, make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                    __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+                }
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 64) s_is_last = (atomicAdd(&P.counters[tile_lin], 1u) == (unsigned)(P.splits - 1));
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (s_is_last) {
+                __threadfence();
+                if (valid) {
+                    for (int c = 0; c < nchunks; ++c) {
+                        float f[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = 0.f;
+                        for (int z = 0; z < P.splits; ++z) {
+                            const float4* src = reinterpret_cast<const float4*>(
+                                P.ws + (((size_t)z * num_tiles + tile_lin) * TC_BM + row) * P.BN + c * 32);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 p = __ldcg(src + i);
+                                f[4 * i] += p.x; f[4 * i + 1] += p.y; f[4 * i + 2] += p.z; f[4 * i + 3] += p.w;
+                            }
+                        }
+                        tc_store_row(P, m * P.Cout + n0 + c * 32, n0 + c * 32, f);
+                    }
+                }
+                if (threadIdx.x == 64) P.counters[tile_lin] = 0;    // self-reset for the next launch
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.BN) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// elementwise helpers for the (raw, hi, lo) activation format
+// ------------------------------------------------------------------------------------------------------------
+__global__ void split_kernel(const float4* __restrict__ in, float4* __restrict__ hi, float4* __restrict__ lo, size_t n4) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = in[i];
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+    hi[i] = h; lo[i] = l;
+}
+
+int launch_split_tf32(const float* in, float* hi, float* lo, size_t n, cudaStream_t st) {
+    const size_t n4 = n / 4;
+    split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const float4*)in, (float4*)hi, (float4*)lo, n4);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || !p) return nullptr;
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+bool tc_conv_supported(const Op& op) {
+    if (op.kind != OP_CONV) return false;
+    if (!(op.k == 1 || op.k == 3)) return false;
+    if (op.Cin % TC_KB != 0 || op.Cout % 64 != 0) return false;
+    if (op.stride == 2 && !env_int("B200TRK_TC_STRIDE2", 1)) return false;
+    if (op.stride != 1 && op.stride != 2) return false;
+    return env_int("B200TRK_TC", 1) != 0;
+}
+
+static void split_host(const std::vector<float>& w, std::vector<float>& hi, std::vector<float>& lo) {
+    auto rna = [](float x) {
+        uint32_t u; memcpy(&u, &x, 4);
+        if ((u & 0x7f800000u) != 0x7f800000u) u += 0x1000u;   // round to nearest, ties away (cvt.rna)
+        u &= 0xffffe000u;
+        float r; memcpy(&r, &u, 4);
+        return r;
+    };
+    hi.resize(w.size()); lo.resize(w.size());
+    for (size_t i = 0; i < w.size(); ++i) { hi[i] = rna(w[i]); lo[i] = rna(w[i] - hi[i]); }
+}
+
+static int make_map_2d(CUtensorMap* m, float* base, uint64_t K, uint64_t N, uint32_t boxN) {
+    EncodeTiledFn enc = get_encode_fn();
+    B200_REQUIRE(enc, "tc_conv: cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {K, N};
+    cuuint64_t strides[1] = {K * sizeof(float)};
+    cuuint32_t box[2] = {TC_KB, boxN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, "tc_conv: cuTensorMapEncodeTiled(weights K=%llu N=%llu) failed: %d", (unsigned long long)K, (unsigned long long)N, (int)r);
+    return 0;
+}
+
+static int make_map_4d(CUtensorMap* m, float* base, int C, int W, int H, int S, int boxW, int boxH, int stride) {
+    EncodeTiledFn enc = get_encode_fn();
+    B200_REQUIRE(enc, "tc_conv: cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)S};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {TC_KB, (cuuint32_t)(boxW * stride), (cuuint32_t)(boxH * stride), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, "tc_conv: cuTensorMapEncodeTiled(act C=%d W=%d H=%d S=%d box %dx%d stride %d) failed: %d",
+                 C, W, H, S, boxW, boxH, stride, (int)r);
+    return 0;
+}
+
+// choose the BW x BH pixel rectangle (BW*BH <= 128) that wastes the fewest accumulator rows
+static void pick_tile(int Wout, int Hout, int stride, int* BW, int* BH) {
+    double best = -1.0;
+    for (int bw = 1; bw <= Wout && bw <= 128; ++bw) {
+        if (bw * stride > 256) break;
+        int bh = 128 / bw;
+        if (bh > Hout) bh = Hout;
+        if (bh * stride > 256) bh = 256 / stride;
+        if (bh < 1) continue;
+        const int tw = (Wout + bw - 1) / bw, th = (Hout + bh - 1) / bh;
+        const double eff = (double)Wout * Hout / ((double)tw * th * 128.0);
+        if (eff > best + 1e-9) { best = eff; *BW = bw; *BH = bh; }
+    }
+}
+
+int tc_conv_prepare(b200trk_net* net, Op& op, const std::vector<float>& w_khwc) {
+    TcConv* tc = new TcConv();
+    op.tc = tc;
+    std::vector<float> hi, lo;
+    split_host(w_khwc, hi, lo);
+    void *ph = nullptr, *pl = nullptr;
+    B200_CHECK_CUDA(cudaMalloc(&ph, hi.size() * sizeof(float)));
+    net->owned.push_back(ph);
+    B200_CHECK_CUDA(cudaMalloc(&pl, lo.size() * sizeof(float)));
+    net->owned.push_back(pl);
+    B200_CHECK_CUDA(cudaMemcpy(ph, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
+    B200_CHECK_CUDA(cudaMemcpy(pl, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
+    tc->w_hi = (float*)ph; tc->w_lo = (float*)pl;
+
+    TcParams& P = tc->P;
+    memset(&P, 0, sizeof(P));
+    P.Hout = op.Hout; P.Wout = op.Wout; P.Cout = op.Cout; P.Cin = op.Cin;
+    P.ksz = op.k; P.stride = op.stride; P.pad = op.pad; P.relu = op.relu;
+    pick_tile(op.Wout, op.Hout, op.stride, &P.BW, &P.BH);
+    P.tiles_w = (op.Wout + P.BW - 1) / P.BW;
+    P.tiles_h = (op.Hout + P.BH - 1) / P.BH;
+    P.cblks = op.Cin / TC_KB;
+    P.total_kb = op.k * op.k * P.cblks;
+    P.a_bytes = (uint32_t)(P.BW * P.BH) * 128u;
+    P.bias = op.bias;
+    P.out_raw = net->bufs[op.out]; P.out_hi = net->bufs_hi[op.out]; P.out_lo = net->bufs_lo[op.out];
+    P.residual = op.res >= 0 ? net->bufs[op.res] : nullptr;
+    P.ws = net->splitk_ws;           // filled in at launch (allocated after the plan is built)
+    if (int e = make_map_4d(&P.a_hi, net->bufs_hi[op.in], op.Cin, op.Win, op.Hin, net->max_batch, P.BW, P.BH, op.stride)) return e;
+    if (int e = make_map_4d(&P.a_lo, net->bufs_lo[op.in], op.Cin, op.Win, op.Hin, net->max_batch, P.BW, P.BH, op.stride)) return e;
+    void* cnt = nullptr;
+    B200_CHECK_CUDA(cudaMalloc(&cnt, 1024 * sizeof(unsigned)));
+    B200_CHECK_CUDA(cudaMemset(cnt, 0, 1024 * sizeof(unsigned)));
+    net->owned.push_back(cnt);
+    P.counters = (unsigned*)cnt;
+    tc->S_built = -1;
+    return 0;
+}
+
+// per-batch-size launch geometry (BN, split-K); the weight tensor maps depend on BN
+static int tc_configure(b200trk_net* net, const Op& op, TcConv* tc, int S) {
+    TcParams& P = tc->P;
+    const int m_tiles = P.tiles_w * P.tiles_h * S;
+    int BN = env_int("B200TRK_TC_BN", 0);
+    if (BN == 0) {
+        BN = 64;
+        if (op.Cout % 128 == 0 && m_tiles * (op.Cout / 128) >= net->sms) BN = 128;
+    }
+    if (op.Cout % BN != 0) BN = 64;
+    P.BN = BN;
+    P.b_bytes = (uint32_t)BN * 128u;
+    const uint32_t stage_bytes = 2u * TC_BM * 128u + 2u * P.b_bytes;
+    int stages = (int)((200u * 1024u) / stage_bytes);
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (stages > P.total_kb) stages = P.total_kb < 2 ? 2 : P.total_kb;
+    P.stages = stages;
+    const int ctas = m_tiles * (op.Cout / BN);
+    int splits = 1;
+    const int max_splits = env_int("B200TRK_TC_SPLITK", 1) ? 64 : 1;
+    if (ctas < net->sms) {
+        splits = net->sms / ctas;
+        const int min_kb = 4;
+        if (splits > P.total_kb / min_kb) splits = P.total_kb / min_kb;
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+        while (splits > 1 && (size_t)splits * ctas * TC_BM * BN > net->splitk_ws_floats) --splits;
+    }
+    P.kb_per_split = (P.total_kb + splits - 1) / splits;
+    P.splits = (P.total_kb + P.kb_per_split - 1) / P.kb_per_split;
+    B200_REQUIRE(ctas <= 1024 || P.splits == 1, "tc_conv: counter array too small for %d tiles", ctas);
+    P.ws = net->splitk_ws;
+    const size_t Kt = (size_t)op.k * op.k * op.Cin;
+    if (int e = make_map_2d(&P.b_hi, tc->w_hi, Kt, op.Cout, BN)) return e;
+    if (int e = make_map_2d(&P.b_lo, tc->w_lo, Kt, op.Cout, BN)) return e;
+    tc->S_built = S;
+    return 0;
+}
+
+int tc_conv_launch(b200trk_net* net, const Op& op, int S, cudaStream_t st) {
+    TcConv* tc = op.tc;
+    if (tc->S_built != S)
+        if (int e = tc_configure(net, op, tc, S)) return e;
+    const TcParams& P = tc->P;
+    const uint32_t stage_bytes = 2u * TC_BM * 128u + 2u * P.b_bytes;
+    const size_t smem = (size_t)P.stages * stage_bytes + 1024;
+    static bool attr = false;
+    if (!attr) {
+        B200_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr = true;
+    }
+    dim3 grid(P.tiles_w * P.tiles_h * S, op.Cout / P.BN, P.splits);
+    conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(P);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
 void tc_conv_free(TcConv* tc) { delete tc; }
+
 }  // namespace b200trk

@@ -11,6 +11,7 @@ int tc_conv_prepare(b200trk_net* net, Op& op, const std::vector<float>& w_khwc);
 int tc_conv_launch(b200trk_net* net, const Op& op, int S, cudaStream_t st);         // conv_tc.cu
 void tc_conv_free(TcConv* tc);
 bool tc_conv_supported(const Op& op);
+int launch_split_tf32(const float* in, float* hi, float* lo, size_t n, cudaStream_t st);   // conv_tc.cu
 
 static int dev_alloc(b200trk_net* net, float** p, size_t floats) {
     void* q = nullptr;
@@ -25,6 +26,13 @@ static int new_buf(b200trk_net* net, size_t floats_per_sample, int* id) {
     if (int e = dev_alloc(net, &p, floats_per_sample * (size_t)net->max_batch)) return e;
     net->bufs.push_back(p);
     net->buf_floats.push_back(floats_per_sample);
+    float *hi = nullptr, *lo = nullptr;
+    if (net->precision == 0) {
+        if (int e = dev_alloc(net, &hi, floats_per_sample * (size_t)net->max_batch)) return e;
+        if (int e = dev_alloc(net, &lo, floats_per_sample * (size_t)net->max_batch)) return e;
+    }
+    net->bufs_hi.push_back(hi);
+    net->bufs_lo.push_back(lo);
     *id = (int)net->bufs.size() - 1;
     return 0;
 }
@@ -198,11 +206,9 @@ extern "C" int b200trk_net_create(b200trk_net_t** out, int arch, const b200trk_c
     net->arch = arch; net->crop_h = crop_h; net->crop_w = crop_w; net->max_batch = max_batch; net->precision = precision;
     net->norm_scale = norm_scale;
     net->sms = device_sm_count();
-    int e = build(net, convs, n_convs);
-    if (!e) {
-        net->splitk_ws_floats = (size_t)8 << 20;   // 32 MB of split-K partials
-        e = dev_alloc(net, &net->splitk_ws, net->splitk_ws_floats);
-    }
+    net->splitk_ws_floats = (size_t)8 << 20;   // 32 MB of split-K partials
+    int e = dev_alloc(net, &net->splitk_ws, net->splitk_ws_floats);
+    if (!e) e = build(net, convs, n_convs);
     if (!e) e = dev_alloc(net, &net->l2_partials, 64 * 64);
     if (e) { b200trk_net_destroy(net); return e; }
     *out = net;
@@ -223,6 +229,25 @@ extern "C" int b200trk_net_dims(const b200trk_net_t* net, int dims[9]) {
     return 0;
 }
 
+extern "C" int b200trk_net_num_ops(const b200trk_net_t* net) { return net ? (int)net->ops.size() : 0; }
+
+extern "C" int b200trk_net_op_info(const b200trk_net_t* net, int index, int info[8]) {
+    B200_REQUIRE(net && info && index >= 0 && index < (int)net->ops.size(), "net_op_info: bad argument");
+    const Op& op = net->ops[index];
+    info[0] = (int)op.kind; info[1] = op.Cin; info[2] = op.Cout; info[3] = op.k; info[4] = op.stride;
+    info[5] = op.Hout; info[6] = op.Wout; info[7] = op.tc ? 1 : 0;
+    return 0;
+}
+
+extern "C" int b200trk_net_op_output(const b200trk_net_t* net, int index, int S, float* dst, b200trk_stream_t stream) {
+    B200_REQUIRE(net && dst && index >= 0 && index < (int)net->ops.size(), "net_op_output: bad argument");
+    const Op& op = net->ops[index];
+    B200_REQUIRE(op.out >= 0 && S >= 1 && S <= net->max_batch, "net_op_output: step %d has no activation output", index);
+    const size_t floats = op.kind == OP_PREPROCESS ? (size_t)op.Hin * op.Win * 4 : (size_t)op.Hout * op.Wout * op.Cout;
+    B200_CHECK_CUDA(cudaMemcpyAsync(dst, net->bufs[op.out], floats * S * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
 extern "C" double b200trk_net_flops(const b200trk_net_t* net) { return net ? net->flops : 0.0; }
 
 extern "C" int b200trk_net_forward(b200trk_net_t* net, const float* crop, int S, float* layer2, float* layer3, float* clf,
@@ -240,6 +265,9 @@ extern "C" int b200trk_net_forward(b200trk_net_t* net, const float* crop, int S,
             break;
         case OP_MAXPOOL:
             if (int e = launch_maxpool3x3s2(net->bufs[op.in], net->bufs[op.out], S, op.Hin, op.Win, op.Cin, st)) return e;
+            if (net->precision == 0)
+                if (int e = launch_split_tf32(net->bufs[op.out], net->bufs_hi[op.out], net->bufs_lo[op.out],
+                                              (size_t)S * op.Hout * op.Wout * op.Cout, st)) return e;
             break;
         case OP_CONV: {
             if (op.tc) {
@@ -250,6 +278,9 @@ extern "C" int b200trk_net_forward(b200trk_net_t* net, const float* crop, int S,
             ConvEpilogue ep{op.bias, op.res >= 0 ? net->bufs[op.res] : nullptr, op.relu};
             if (int e = launch_conv_fp32(net->bufs[op.in], op.w, net->bufs[op.out], sh, ep, net->splitk_ws,
                                          net->splitk_ws_floats, net->sms, st)) return e;
+            if (net->precision == 0)
+                if (int e = launch_split_tf32(net->bufs[op.out], net->bufs_hi[op.out], net->bufs_lo[op.out],
+                                              (size_t)S * op.Hout * op.Wout * op.Cout, st)) return e;
             break;
         }
         case OP_EXPORT_NCHW: {

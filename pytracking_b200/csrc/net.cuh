@@ -27,7 +27,8 @@ struct b200trk_net {
     int arch = 0, crop_h = 0, crop_w = 0, max_batch = 0, precision = 0;
     float norm_scale = 1.f;
     std::vector<b200trk::Op> ops;
-    std::vector<float*> bufs;            // activation buffers (device), sized for max_batch
+    std::vector<float*> bufs;            // activation buffers (device, NHWC fp32), sized for max_batch
+    std::vector<float*> bufs_hi, bufs_lo; // precision 0: TF32 (hi, lo) split copies of each buffer (operands of the 3xTF32 MMAs)
     std::vector<size_t> buf_floats;      // per-sample floats of each buffer
     std::vector<void*> owned;            // every device allocation (freed in destroy)
     float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;
