@@ -145,6 +145,11 @@ double b200trk_net_flops(const b200trk_net_t* net);
 int b200trk_net_num_ops(const b200trk_net_t* net);
 int b200trk_net_op_info(const b200trk_net_t* net, int index, int info[8]);
 int b200trk_net_op_output(const b200trk_net_t* net, int index, int S, float* dst, b200trk_stream_t stream);
+/* Profiling aid for tensor-core steps: attach a DEVICE buffer of [ctas][8] uint64 per-CTA phase time stamps
+ * (globaltimer ns: start, prologue done, previous grid complete, first operands landed, accumulator complete,
+ * split-K arrivals complete, epilogue done), NULL detaches; and query the launch geometry {grid.x, grid.y, grid.z, BN}. */
+int b200trk_net_op_set_timing_buffer(b200trk_net_t* net, int index, unsigned long long* buf);
+int b200trk_net_op_grid(const b200trk_net_t* net, int index, int dims[4]);
 
 /* ------------------------------------------------------------------------------------------------
  * Native op -- Precise RoI Pooling (the reference's only CUDA component)

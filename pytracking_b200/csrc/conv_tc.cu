@@ -27,6 +27,7 @@ constexpr int TC_BM = 128;          // UMMA M
 constexpr int TC_KB = 32;           // fp32 elements per 128-byte K block
 constexpr int TC_THREADS = 192;     // 6 warps
 constexpr int TC_MAX_STAGES = 6;
+constexpr int TC_EPI_PITCH = 36;    // floats per staged accumulator row (32 + 4: conflict-free 128-bit smem accesses)
 constexpr long long TC_WAIT_LIMIT_CLOCKS = 4000000000ll;    // ~2 s: a broken pipeline traps instead of hanging the GPU
 
 struct TcParams {
@@ -34,6 +35,7 @@ struct TcParams {
     float* out_raw; float* out_hi; float* out_lo;
     const float* bias; const float* residual;
     float* ws; unsigned* counters;
+    unsigned long long* dbg;       // optional [ctas][8] phase time stamps (globaltimer ns); nullptr in production
     int BW, BH, tiles_w, tiles_h;
     int Hout, Wout, Cout, Cin;
     int ksz, stride, pad;
@@ -113,6 +115,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                  : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -126,38 +133,16 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 // ------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tc_store_row(const TcParams& P, size_t off, int n, float (&f)[32]) {
-    // bias + residual + ReLU, then raw / hi / lo
-    if (P.bias) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + n) + q);
-            f[4 * q] += b.x; f[4 * q + 1] += b.y; f[4 * q + 2] += b.z; f[4 * q + 3] += b.w;
-        }
-    }
-    if (P.residual) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 r = __ldg(reinterpret_cast<const float4*>(P.residual + off) + q);
-            f[4 * q] += r.x; f[4 * q + 1] += r.y; f[4 * q + 2] += r.z; f[4 * q + 3] += r.w;
-        }
-    }
-    if (P.relu) {
-#pragma unroll
-        for (int q = 0; q < 32; ++q) f[q] = fmaxf(f[q], 0.f);
-    }
-    float4* o_raw = reinterpret_cast<float4*>(P.out_raw + off);
-    float4* o_hi = reinterpret_cast<float4*>(P.out_hi + off);
-    float4* o_lo = reinterpret_cast<float4*>(P.out_lo + off);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        float4 h, l;
-        split_tf32(f[4 * q], h.x, l.x); split_tf32(f[4 * q + 1], h.y, l.y);
-        split_tf32(f[4 * q + 2], h.z, l.z); split_tf32(f[4 * q + 3], h.w, l.w);
-        o_raw[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-        o_hi[q] = h;
-        o_lo[q] = l;
-    }
+// bias + residual + ReLU on 4 consecutive channels of one pixel, then the (raw, hi, lo) stores
+__device__ __forceinline__ void tc_finish4(const TcParams& P, size_t off, const float4& bias, const float4& r, float4 f) {
+    f.x += bias.x; f.y += bias.y; f.z += bias.z; f.w += bias.w;
+    f.x += r.x; f.y += r.y; f.z += r.z; f.w += r.w;
+    if (P.relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+    float4 h, l;
+    split_tf32(f.x, h.x, l.x); split_tf32(f.y, h.y, l.y); split_tf32(f.z, h.z, l.z); split_tf32(f.w, h.w, l.w);
+    *reinterpret_cast<float4*>(P.out_raw + off) = f;
+    *reinterpret_cast<float4*>(P.out_hi + off) = h;
+    *reinterpret_cast<float4*>(P.out_lo + off) = l;
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
@@ -166,7 +151,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     __shared__ __align__(8) uint64_t s_empty[TC_MAX_STAGES];
     __shared__ __align__(8) uint64_t s_tmem_full;
     __shared__ uint32_t s_tmem_base;
-    __shared__ int s_is_last;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
@@ -183,6 +167,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int kb0 = blockIdx.z * P.kb_per_split;
     const int kb1 = min(P.total_kb, kb0 + P.kb_per_split);
     const int nkb = kb1 - kb0;
+    unsigned long long* dbg = P.dbg ? P.dbg + 8 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+    if (dbg && threadIdx.x == 0) dbg[0] = gtimer();                   // CTA start
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < P.stages; ++i) { mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_empty[i]), 1); }
@@ -193,10 +179,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"((uint32_t)P.BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.a_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.a_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.b_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.b_lo) : "memory");
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the
+    // tail of the previous layer's kernel; nothing below may touch global memory before the previous grid has completed.
+    if (dbg && threadIdx.x == 0) dbg[1] = gtimer();                   // prologue done
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (dbg && threadIdx.x == 0) dbg[2] = gtimer();                   // previous grid complete
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -228,6 +226,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
                 mbar_wait(smem_u32(&s_full[st]), ph);
                 tc_fence_after();
+                if (dbg && it == 0) dbg[3] = gtimer();                // first operands landed
                 const uint32_t sa = smem_base + (uint32_t)st * stage_bytes;
                 const uint64_t d_ah = make_smem_desc(sa), d_al = make_smem_desc(sa + a_tile);
                 const uint64_t d_bh = make_smem_desc(sa + 2u * a_tile), d_bl = make_smem_desc(sa + 2u * a_tile + b_tile);
@@ -244,68 +243,130 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
+        // TMEM -> registers (thread = accumulator row) -> per-warp smem transpose -> lanes own (row, 4 channels), so
+        // that every warp-level global access covers 4 rows x 128 contiguous bytes.
         const int q = warp & 3;                          // TMEM lane quadrant this warp may access
-        const int row = q * 32 + lane;                   // accumulator row = pixel inside the tile
-        const int ly = row / P.BW, lx = row - ly * P.BW;
-        const int oy = th * P.BH + ly, ox = tw * P.BW + lx;
-        const bool valid = (row < P.BW * P.BH) && (oy < P.Hout) && (ox < P.Wout);
-        const size_t m = ((size_t)s * P.Hout + oy) * P.Wout + ox;
+        const int ew = warp - 2;                         // 0..3
         const int tile_lin = blockIdx.y * gridDim.x + blockIdx.x;
         const int num_tiles = gridDim.x * gridDim.y;
+        const int nchunks = P.BN / 32;
+        const int lrow = lane >> 3, lcol = (lane & 7) * 4;
+        float* stg = reinterpret_cast<float*>(tc_smem_raw + (smem_base - smem_u32(tc_smem_raw))) + ew * (32 * TC_EPI_PITCH);
         mbar_wait(smem_u32(&s_tmem_full), 0);
         tc_fence_after();
-        const int nchunks = P.BN / 32;
+        if (dbg && threadIdx.x == 64) dbg[4] = gtimer();              // accumulator complete
         if (P.splits == 1) {
+            // rows of this warp's quadrant handled by this lane: q*32 + i*4 + lrow
+            bool rvalid[8];
+            size_t roff[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = q * 32 + i * 4 + lrow;
+                const int ly = row / P.BW, lx = row - ly * P.BW;
+                const int oy = th * P.BH + ly, ox = tw * P.BW + lx;
+                rvalid[i] = row < P.BW * P.BH && oy < P.Hout && ox < P.Wout;
+                roff[i] = (((size_t)s * P.Hout + oy) * P.Wout + ox) * P.Cout;
+            }
             for (int c = 0; c < nchunks; ++c) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-                if (valid) {
-                    float f[32];
+                __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                    tc_store_row(P, m * P.Cout + n0 + c * 32, n0 + c * 32, f);
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<float4*>(stg + lane * TC_EPI_PITCH + 4 * i) =
+                        make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                    __uint_as_float(v[4 * i + 3]));
+                __syncwarp();
+                const int n = n0 + c * 32 + lcol;
+                const float4 bias = P.bias ? __ldg(reinterpret_cast<const float4*>(P.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                // all residual loads of the chunk are issued before the first dependent use (memory-level parallelism)
+                float4 res[8];
+                if (P.residual) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        res[i] = rvalid[i] ? __ldg(reinterpret_cast<const float4*>(P.residual + roff[i] + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (rvalid[i]) {
+                        float4 f = *reinterpret_cast<const float4*>(stg + (i * 4 + lrow) * TC_EPI_PITCH + lcol);
+                        tc_finish4(P, roff[i] + n, bias, res[i], f);
+                    }
                 }
             }
         } else {
-            float* wsp = P.ws + (((size_t)blockIdx.z * num_tiles + tile_lin) * TC_BM + row) * P.BN;
+            // ---- split-K: partial tile -> L2 workspace (coalesced), tile-wide arrival counter, then EVERY split CTA
+            //      reduces its share of the tile rows in split order (fixed order => deterministic) ----
+            float* wsp = P.ws + ((size_t)blockIdx.z * num_tiles + tile_lin) * TC_BM * P.BN;
             for (int c = 0; c < nchunks; ++c) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-                if (valid) {
-                    float4* dst = reinterpret_cast<float4*>(wsp + c * 32);
+                __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        __stcg(dst + i, make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                                    __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<float4*>(stg + lane * TC_EPI_PITCH + 4 * i) =
+                        make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                    __uint_as_float(v[4 * i + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = q * 32 + i * 4 + lrow;
+                    __stcg(reinterpret_cast<float4*>(wsp + (size_t)row * P.BN + c * 32 + lcol),
+                           *reinterpret_cast<const float4*>(stg + (i * 4 + lrow) * TC_EPI_PITCH + lcol));
                 }
             }
             __threadfence();
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (threadIdx.x == 64) s_is_last = (atomicAdd(&P.counters[tile_lin], 1u) == (unsigned)(P.splits - 1));
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (s_is_last) {
+            if (threadIdx.x == 64) {
+                atomicAdd(&P.counters[2 * tile_lin], 1u);
+                long long t0 = clock64();
+                while (ld_acquire_u32(&P.counters[2 * tile_lin]) < (unsigned)P.splits)
+                    if (clock64() - t0 > TC_WAIT_LIMIT_CLOCKS) __trap();
                 __threadfence();
-                if (valid) {
-                    for (int c = 0; c < nchunks; ++c) {
-                        float f[32];
+                if (dbg) dbg[5] = gtimer();                           // all splits of the tile arrived
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // row groups (4 rows each, 32 per tile) are dealt round-robin to (split, warp)
+            for (int g = blockIdx.z + P.splits * ew; g < 32; g += P.splits * 4) {
+                const int row = g * 4 + lrow;
+                const int ly = row / P.BW, lx = row - ly * P.BW;
+                const int oy = th * P.BH + ly, ox = tw * P.BW + lx;
+                if (!(row < P.BW * P.BH && oy < P.Hout && ox < P.Wout)) continue;
+                const size_t obase = (((size_t)s * P.Hout + oy) * P.Wout + ox) * P.Cout;
+                for (int c = 0; c < nchunks; ++c) {
+                    const int n = n0 + c * 32 + lcol;
+                    const float* src = P.ws + ((size_t)tile_lin * TC_BM + row) * P.BN + c * 32 + lcol;
+                    const size_t zstride = (size_t)num_tiles * TC_BM * P.BN;
+                    const float4 bias = P.bias ? __ldg(reinterpret_cast<const float4*>(P.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 res = P.residual ? __ldg(reinterpret_cast<const float4*>(P.residual + obase + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int z0 = 0; z0 < P.splits; z0 += 8) {     // 8 partial loads in flight, summed in split order
+                        float4 p[8];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) f[i] = 0.f;
-                        for (int z = 0; z < P.splits; ++z) {
-                            const float4* src = reinterpret_cast<const float4*>(
-                                P.ws + (((size_t)z * num_tiles + tile_lin) * TC_BM + row) * P.BN + c * 32);
+                        for (int u = 0; u < 8; ++u)
+                            p[u] = (z0 + u < P.splits) ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)(z0 + u) * zstride))
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float4 p = __ldcg(src + i);
-                                f[4 * i] += p.x; f[4 * i + 1] += p.y; f[4 * i + 2] += p.z; f[4 * i + 3] += p.w;
-                            }
-                        }
-                        tc_store_row(P, m * P.Cout + n0 + c * 32, n0 + c * 32, f);
+                        for (int u = 0; u < 8; ++u) { f.x += p[u].x; f.y += p[u].y; f.z += p[u].z; f.w += p[u].w; }
                     }
+                    tc_finish4(P, obase + n, bias, res, f);
                 }
-                if (threadIdx.x == 64) P.counters[tile_lin] = 0;    // self-reset for the next launch
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 64) {
+                // the last split CTA to finish its share re-arms both counters for the next launch
+                if (atomicAdd(&P.counters[2 * tile_lin + 1], 1u) == (unsigned)(P.splits - 1)) {
+                    P.counters[2 * tile_lin] = 0;
+                    P.counters[2 * tile_lin + 1] = 0;
+                    __threadfence();
+                }
             }
         }
         tc_fence_before();
+        if (dbg && threadIdx.x == 64) dbg[6] = gtimer();              // epilogue done
     }
     __syncthreads();
     if (warp == 1) {
@@ -465,7 +526,8 @@ static int tc_configure(b200trk_net* net, const Op& op, TcConv* tc, int S) {
     int BN = env_int("B200TRK_TC_BN", 0);
     if (BN == 0) {
         BN = 64;
-        if (op.Cout % 128 == 0 && m_tiles * (op.Cout / 128) >= net->sms) BN = 128;
+        // a second wave of 1-CTA-per-SM tiles doubles the layer time: widen the tile as soon as BN = 64 overflows the SMs
+        if (op.Cout % 128 == 0 && m_tiles * (op.Cout / 64) > net->sms) BN = 128;
     }
     if (op.Cout % BN != 0) BN = 64;
     P.BN = BN;
@@ -488,7 +550,7 @@ static int tc_configure(b200trk_net* net, const Op& op, TcConv* tc, int S) {
     }
     P.kb_per_split = (P.total_kb + splits - 1) / splits;
     P.splits = (P.total_kb + P.kb_per_split - 1) / P.kb_per_split;
-    B200_REQUIRE(ctas <= 1024 || P.splits == 1, "tc_conv: counter array too small for %d tiles", ctas);
+    B200_REQUIRE(ctas <= 512 || P.splits == 1, "tc_conv: counter array too small for %d tiles", ctas);
     P.ws = net->splitk_ws;
     const size_t Kt = (size_t)op.k * op.k * op.Cin;
     if (int e = make_map_2d(&P.b_hi, tc->w_hi, Kt, op.Cout, BN)) return e;
@@ -503,18 +565,35 @@ int tc_conv_launch(b200trk_net* net, const Op& op, int S, cudaStream_t st) {
         if (int e = tc_configure(net, op, tc, S)) return e;
     const TcParams& P = tc->P;
     const uint32_t stage_bytes = 2u * TC_BM * 128u + 2u * P.b_bytes;
-    const size_t smem = (size_t)P.stages * stage_bytes + 1024;
+    size_t smem = (size_t)P.stages * stage_bytes + 1024;
+    if (smem < 64 * 1024) smem = 64 * 1024;       // the epilogue stages 4 x 32 x 36 floats in the (idle) pipeline buffers
     static bool attr = false;
     if (!attr) {
         B200_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr = true;
     }
     dim3 grid(P.tiles_w * P.tiles_h * S, op.Cout / P.BN, P.splits);
-    conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(P);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    static const int use_pdl = env_int("B200TRK_TC_PDL", 1);
+    cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
+    B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, P));
     B200_LAUNCH_CHECK();
     return 0;
 }
 
 void tc_conv_free(TcConv* tc) { delete tc; }
+
+int tc_conv_set_debug(Op& op, unsigned long long* buf) { op.tc->P.dbg = buf; return 0; }
+int tc_conv_grid(const Op& op, int dims[4]) {
+    const TcParams& P = op.tc->P;
+    const int S = op.tc->S_built > 0 ? op.tc->S_built : 1;
+    dims[0] = P.tiles_w * P.tiles_h * S; dims[1] = P.BN ? op.Cout / P.BN : 0; dims[2] = P.splits; dims[3] = P.BN;
+    return 0;
+}
 
 }  // namespace b200trk

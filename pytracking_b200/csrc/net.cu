@@ -229,6 +229,21 @@ extern "C" int b200trk_net_dims(const b200trk_net_t* net, int dims[9]) {
     return 0;
 }
 
+namespace b200trk { int tc_conv_set_debug(Op& op, unsigned long long* buf); int tc_conv_grid(const Op& op, int dims[4]); }
+
+// Debug: attach (or detach, buf = NULL) a device buffer of [ctas][8] u64 phase time stamps to plan step `index`.
+extern "C" int b200trk_net_op_set_timing_buffer(b200trk_net_t* net, int index, unsigned long long* buf) {
+    B200_REQUIRE(net && index >= 0 && index < (int)net->ops.size(), "net_op_set_timing_buffer: bad argument");
+    Op& op = net->ops[index];
+    B200_REQUIRE(op.tc, "net_op_set_timing_buffer: step %d does not run on the tensor cores", index);
+    return tc_conv_set_debug(op, buf);
+}
+// Debug: launch geometry of a tensor-core step as last configured: dims = {gridDim.x, gridDim.y, gridDim.z, BN}.
+extern "C" int b200trk_net_op_grid(const b200trk_net_t* net, int index, int dims[4]) {
+    B200_REQUIRE(net && dims && index >= 0 && index < (int)net->ops.size() && net->ops[index].tc, "net_op_grid: bad argument");
+    return tc_conv_grid(net->ops[index], dims);
+}
+
 extern "C" int b200trk_net_num_ops(const b200trk_net_t* net) { return net ? (int)net->ops.size() : 0; }
 
 extern "C" int b200trk_net_op_info(const b200trk_net_t* net, int index, int info[8]) {
