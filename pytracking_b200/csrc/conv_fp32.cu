@@ -27,17 +27,24 @@ int launch_preprocess(const float* crop_nchw, float* out_nhwc4, int S, int H, in
 }
 
 // --------------------------------------------------------------------------------------------------
-// stem: conv 7x7 stride 2 pad 3, Cin = 3 (padded to 4), Cout = 64, + folded BN bias + ReLU
-// (ltr/models/backbone/resnet.py:182-184). CTA = 8x8 output pixels x 64 channels.
+// stem: conv 7x7 stride 2 pad 3, Cin = 3, Cout = 64, + folded BN bias + ReLU (ltr/models/backbone/resnet.py:182-184).
+// CTA = 8x8 output pixels x 64 channels, 8 warps: warp = (16-channel group, 32-pixel half), lane = pixel, so every
+// weight fetch is a warp-wide broadcast (one shared-memory wavefront) and every input fetch is conflict free: the
+// 21x21 input patch is stored as [channel][column parity][row][12] so that the stride-2 column walk of a warp touches
+// consecutive words (row pitch 12: the four pixel rows of a warp land in disjoint bank octets).
 // --------------------------------------------------------------------------------------------------
 constexpr int STEM_T = 8, STEM_P = (STEM_T - 1) * 2 + 7;   // 21x21 input patch
+constexpr int STEM_RP = 12;                                // row pitch of a parity plane (11 used)
+constexpr int STEM_PLANE = STEM_P * STEM_RP;               // floats per (channel, parity) plane
+constexpr int STEM_PATCH_FLOATS = 3 * 2 * STEM_PLANE;
+constexpr int STEM_W_FLOATS = 49 * 3 * 64;                 // [tap][cin][cout]
 
 __global__ void __launch_bounds__(256)
-stem_kernel(const float4* __restrict__ in, const float4* __restrict__ w4, const float* __restrict__ bias,
+stem_kernel(const float4* __restrict__ in, const float* __restrict__ wt, const float* __restrict__ bias,
             float* __restrict__ out, int Hin, int Win, int Hout, int Wout) {
     extern __shared__ float4 sm4[];
-    float4* patch = sm4;                       // [21][21]
-    float4* ws = sm4 + STEM_P * STEM_P;        // [49][64]
+    float* patch = reinterpret_cast<float*>(sm4);          // [3][2][21][12]
+    float* ws = patch + STEM_PATCH_FLOATS;                 // [49][3][64]
     const int s = blockIdx.z, oy0 = blockIdx.y * STEM_T, ox0 = blockIdx.x * STEM_T;
     const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
     for (int i = threadIdx.x; i < STEM_P * STEM_P; i += 256) {
@@ -45,52 +52,47 @@ stem_kernel(const float4* __restrict__ in, const float4* __restrict__ w4, const 
         const int iy = iy0 + py, ix = ix0 + px;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (iy >= 0 && iy < Hin && ix >= 0 && ix < Win) v = in[((size_t)s * Hin + iy) * Win + ix];
-        patch[i] = v;
+        const int o = (px & 1) * STEM_PLANE + py * STEM_RP + (px >> 1);
+        patch[o] = v.x; patch[2 * STEM_PLANE + o] = v.y; patch[4 * STEM_PLANE + o] = v.z;
     }
-    for (int i = threadIdx.x; i < 49 * 64; i += 256) {
-        const int tap = i >> 6, co = i & 63;
-        ws[i] = w4[co * 49 + tap];
-    }
+    for (int i = threadIdx.x; i < STEM_W_FLOATS / 4; i += 256)
+        reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(wt) + i);
     __syncthreads();
-    const int cq = threadIdx.x & 15, pq = threadIdx.x >> 4;     // 4 couts x 4 pixels per thread
-    const int py = pq >> 1, pxb = (pq & 1) * 4;
-    float acc[4][4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cg = (warp & 3) * 16;                        // first output channel of this warp
+    const int py = (warp >> 2) * 4 + (lane >> 3), px = lane & 7;
+    float acc[16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
     for (int kh = 0; kh < 7; ++kh) {
+        const float* prow = patch + (py * 2 + kh) * STEM_RP + px;
 #pragma unroll
         for (int kw = 0; kw < 7; ++kw) {
-            float4 x[4], w[4];
+            const float* xp = prow + (kw & 1) * STEM_PLANE + (kw >> 1);
+            const float x0 = xp[0], x1 = xp[2 * STEM_PLANE], x2 = xp[4 * STEM_PLANE];
+            const float4* wp = reinterpret_cast<const float4*>(ws + (kh * 7 + kw) * 192 + cg);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] = patch[(py * 2 + kh) * STEM_P + (pxb + i) * 2 + kw];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) w[j] = ws[(kh * 7 + kw) * 64 + cq * 4 + j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    acc[i][j] = fmaf(x[i].x, w[j].x, acc[i][j]);
-                    acc[i][j] = fmaf(x[i].y, w[j].y, acc[i][j]);
-                    acc[i][j] = fmaf(x[i].z, w[j].z, acc[i][j]);
-                }
+            for (int j = 0; j < 4; ++j) {
+                const float4 w0 = wp[j], w1 = wp[16 + j], w2 = wp[32 + j];
+                acc[4 * j + 0] = fmaf(x0, w0.x, acc[4 * j + 0]); acc[4 * j + 1] = fmaf(x0, w0.y, acc[4 * j + 1]);
+                acc[4 * j + 2] = fmaf(x0, w0.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(x0, w0.w, acc[4 * j + 3]);
+                acc[4 * j + 0] = fmaf(x1, w1.x, acc[4 * j + 0]); acc[4 * j + 1] = fmaf(x1, w1.y, acc[4 * j + 1]);
+                acc[4 * j + 2] = fmaf(x1, w1.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(x1, w1.w, acc[4 * j + 3]);
+                acc[4 * j + 0] = fmaf(x2, w2.x, acc[4 * j + 0]); acc[4 * j + 1] = fmaf(x2, w2.y, acc[4 * j + 1]);
+                acc[4 * j + 2] = fmaf(x2, w2.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(x2, w2.w, acc[4 * j + 3]);
+            }
         }
     }
-    const float4 b = *reinterpret_cast<const float4*>(bias + cq * 4);
-    const int oy = oy0 + py;
-    if (oy < Hout) {
+    const int oy = oy0 + py, ox = ox0 + px;
+    if (oy < Hout && ox < Wout) {
+        float* o = out + (((size_t)s * Hout + oy) * Wout + ox) * 64 + cg;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int ox = ox0 + pxb + i;
-            if (ox < Wout) {
-                float4 o;
-                o.x = fmaxf(acc[i][0] + b.x, 0.f);
-                o.y = fmaxf(acc[i][1] + b.y, 0.f);
-                o.z = fmaxf(acc[i][2] + b.z, 0.f);
-                o.w = fmaxf(acc[i][3] + b.w, 0.f);
-                *reinterpret_cast<float4*>(out + (((size_t)s * Hout + oy) * Wout + ox) * 64 + cq * 4) = o;
-            }
+        for (int j = 0; j < 4; ++j) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + cg) + j);
+            float4 v;
+            v.x = fmaxf(acc[4 * j + 0] + b.x, 0.f); v.y = fmaxf(acc[4 * j + 1] + b.y, 0.f);
+            v.z = fmaxf(acc[4 * j + 2] + b.z, 0.f); v.w = fmaxf(acc[4 * j + 3] + b.w, 0.f);
+            reinterpret_cast<float4*>(o)[j] = v;
         }
     }
 }
@@ -98,14 +100,14 @@ stem_kernel(const float4* __restrict__ in, const float4* __restrict__ w4, const 
 int launch_stem_fp32(const float* in_nhwc4, const float* w4, const float* bias, float* out, int S, int Hin, int Win,
                      cudaStream_t st) {
     const int Hout = (Hin + 6 - 7) / 2 + 1, Wout = (Win + 6 - 7) / 2 + 1;
-    const size_t smem = (size_t)(STEM_P * STEM_P + 49 * 64) * sizeof(float4);
+    const size_t smem = (size_t)(STEM_PATCH_FLOATS + STEM_W_FLOATS) * sizeof(float);
     static bool attr = false;
     if (!attr) {
         B200_CHECK_CUDA(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     dim3 grid((Wout + STEM_T - 1) / STEM_T, (Hout + STEM_T - 1) / STEM_T, S);
-    stem_kernel<<<grid, 256, smem, st>>>((const float4*)in_nhwc4, (const float4*)w4, bias, out, Hin, Win, Hout, Wout);
+    stem_kernel<<<grid, 256, smem, st>>>((const float4*)in_nhwc4, w4, bias, out, Hin, Win, Hout, Wout);
     B200_LAUNCH_CHECK();
     return 0;
 }

@@ -3,17 +3,18 @@
 //
 //   D[m][n] = sum_k A[m][k] * W[n][k]     m = output pixel, n = output channel, k = (kh, kw, cin)
 //
-// fp32 fidelity on a TF32 datapath: every operand is stored as a (hi, lo) pair of TF32-representable fp32 numbers,
-// x = hi + lo (+ <= 2^-22 |x|), and each K-step issues three MMAs  A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  into the same
-// fp32 TMEM accumulator ("3xTF32"); the dropped A_lo*B_lo term is O(2^-22) relative. Weights are split once at
-// net_create; activations are split by the producing kernel's epilogue (raw, hi, lo are all written).
+// fp32 fidelity on a TF32 datapath: every operand tile is split IN SHARED MEMORY into a (hi, lo) pair of
+// TF32-representable fp32 numbers, x = hi + lo (+ <= 2^-22 |x|), and each K-step issues three MMAs
+// A_lo*B_hi + A_hi*B_lo + A_hi*B_hi into the same fp32 TMEM accumulator ("3xTF32"); the dropped A_lo*B_lo term is
+// O(2^-22) relative. HBM/L2 only ever hold (and move) plain fp32 activations and weights.
 //
 // Tiling: CTA = 128 output pixels (a BW x BH rectangle of one sample, rows ordered (y, x)) x BN output channels.
 // K is walked in 128-byte blocks (32 input channels of one filter tap): one 4-D TMA box {32 ch, BW*stride, BH*stride, 1}
 // (element strides {1, stride, stride, 1}; halo / padding = TMA out-of-bounds zero fill) lands the A tile directly in
 // the canonical K-major SWIZZLE_128B layout that the UMMA shared-memory descriptor expects; a 2-D box {32, BN}
 // does the same for the weights. Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2-5 = epilogue (tcgen05.ld -> registers -> bias/residual/ReLU -> global). Small layers use split-K over
+// warps 2-5 = operand converter during the main loop (raw -> hi in place, lo next to it, fence.proxy.async), then
+// epilogue (tcgen05.ld -> registers -> smem transpose -> bias/residual/ReLU -> coalesced global stores). Small layers use split-K over
 // gridDim.z; partial tiles go to an L2-resident workspace and the last CTA of a tile reduces them in split order
 // (fixed order => bitwise deterministic).
 #include "net.cuh"
@@ -31,23 +32,23 @@ constexpr int TC_EPI_PITCH = 36;    // floats per staged accumulator row (32 + 4
 constexpr long long TC_WAIT_LIMIT_CLOCKS = 4000000000ll;    // ~2 s: a broken pipeline traps instead of hanging the GPU
 
 struct TcParams {
-    CUtensorMap a_hi, a_lo, b_hi, b_lo;
-    float* out_raw; float* out_hi; float* out_lo;
+    CUtensorMap a_map, b_map;       // raw fp32 activations (4-D) and weights (2-D)
+    float* out_raw;
     const float* bias; const float* residual;
     float* ws; unsigned* counters;
+    unsigned long long* trace;     // optional [16 k-blocks][8] pipeline event stamps of CTA (0,0,0)
     unsigned long long* dbg;       // optional [ctas][8] phase time stamps (globaltimer ns); nullptr in production
     int BW, BH, tiles_w, tiles_h;
     int Hout, Wout, Cout, Cin;
     int ksz, stride, pad;
     int BN, stages;
     int total_kb, kb_per_split, splits, cblks;
-    int relu;
+    int relu, split_mode;
     uint32_t a_bytes, b_bytes;
 };
 
 struct TcConv {
     TcParams P;
-    float *w_hi = nullptr, *w_lo = nullptr;
     int S_built = 0;
 };
 
@@ -125,6 +126,12 @@ __device__ __forceinline__ float tf32_rna(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+__device__ __forceinline__ float4 tc_lo_trunc(const float4& x) {
+    return make_float4(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u),
+                       x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u),
+                       x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u),
+                       x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u));
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     hi = tf32_rna(x);
     lo = tf32_rna(x - hi);
@@ -133,22 +140,19 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 // ------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------
-// bias + residual + ReLU on 4 consecutive channels of one pixel, then the (raw, hi, lo) stores
+// bias + residual + ReLU on 4 consecutive channels of one pixel
 __device__ __forceinline__ void tc_finish4(const TcParams& P, size_t off, const float4& bias, const float4& r, float4 f) {
     f.x += bias.x; f.y += bias.y; f.z += bias.z; f.w += bias.w;
     f.x += r.x; f.y += r.y; f.z += r.z; f.w += r.w;
     if (P.relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
-    float4 h, l;
-    split_tf32(f.x, h.x, l.x); split_tf32(f.y, h.y, l.y); split_tf32(f.z, h.z, l.z); split_tf32(f.w, h.w, l.w);
     *reinterpret_cast<float4*>(P.out_raw + off) = f;
-    *reinterpret_cast<float4*>(P.out_hi + off) = h;
-    *reinterpret_cast<float4*>(P.out_lo + off) = l;
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
     extern __shared__ uint8_t tc_smem_raw[];
     __shared__ __align__(8) uint64_t s_full[TC_MAX_STAGES];
     __shared__ __align__(8) uint64_t s_empty[TC_MAX_STAGES];
+    __shared__ __align__(8) uint64_t s_ready[TC_MAX_STAGES];   // (hi, lo) split of the stage finished by the 4 converter warps
     __shared__ __align__(8) uint64_t s_tmem_full;
     __shared__ uint32_t s_tmem_base;
 
@@ -169,9 +173,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int nkb = kb1 - kb0;
     unsigned long long* dbg = P.dbg ? P.dbg + 8 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = gtimer();                   // CTA start
+    unsigned long long* trace = (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? P.trace : nullptr;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < P.stages; ++i) { mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_empty[i]), 1); }
+        for (int i = 0; i < P.stages; ++i) {
+            mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_empty[i]), 1); mbar_init(smem_u32(&s_ready[i]), 4);
+        }
         mbar_init(smem_u32(&s_tmem_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -180,10 +187,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.a_hi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.a_lo) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.b_hi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.b_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.a_map) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&P.b_map) : "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -205,15 +210,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const int st = it % P.stages;
                 const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
                 mbar_wait(smem_u32(&s_empty[st]), ph ^ 1u);
+                if (trace && it < 16) trace[it * 8 + 0] = gtimer();          // slot free
                 const uint32_t full = smem_u32(&s_full[st]);
-                mbar_expect_tx(full, 2u * P.a_bytes + 2u * P.b_bytes);
+                mbar_expect_tx(full, P.a_bytes + P.b_bytes);
                 const int tap = kb / P.cblks, cb = kb - tap * P.cblks;
                 const int kh = tap / P.ksz, kw = tap - kh * P.ksz;
                 const uint32_t sa = smem_base + (uint32_t)st * stage_bytes;
-                tma_load_4d(sa, &P.a_hi, full, cb * TC_KB, x0 + kw, y0 + kh, s);
-                tma_load_4d(sa + a_tile, &P.a_lo, full, cb * TC_KB, x0 + kw, y0 + kh, s);
-                tma_load_2d(sa + 2u * a_tile, &P.b_hi, full, tap * P.Cin + cb * TC_KB, n0);
-                tma_load_2d(sa + 2u * a_tile + b_tile, &P.b_lo, full, tap * P.Cin + cb * TC_KB, n0);
+                tma_load_4d(sa, &P.a_map, full, cb * TC_KB, x0 + kw, y0 + kh, s);                 // raw -> A_hi slot
+                tma_load_2d(sa + 2u * a_tile, &P.b_map, full, tap * P.Cin + cb * TC_KB, n0);       // raw -> B_hi slot
+                if (trace && it < 16) trace[it * 8 + 1] = gtimer();          // loads issued
             }
         }
     } else if (warp == 1) {
@@ -224,9 +229,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int it = 0; it < nkb; ++it) {
                 const int st = it % P.stages;
                 const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
-                mbar_wait(smem_u32(&s_full[st]), ph);
+                mbar_wait(smem_u32(&s_ready[st]), ph);
                 tc_fence_after();
-                if (dbg && it == 0) dbg[3] = gtimer();                // first operands landed
+                if (dbg && it == 0) dbg[3] = gtimer();                // first operands landed and split
+                if (trace && it < 16) trace[it * 8 + 4] = gtimer();          // MMA warp sees the stage
                 const uint32_t sa = smem_base + (uint32_t)st * stage_bytes;
                 const uint64_t d_ah = make_smem_desc(sa), d_al = make_smem_desc(sa + a_tile);
                 const uint64_t d_bh = make_smem_desc(sa + 2u * a_tile), d_bl = make_smem_desc(sa + 2u * a_tile + b_tile);
@@ -238,6 +244,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     tc_mma_tf32(tmem_base, d_ah + adv, d_bh + adv, idesc, 1u);
                 }
                 tc_commit(smem_u32(&s_empty[st]));
+                if (trace && it < 16) trace[it * 8 + 5] = gtimer();          // MMAs + commit issued
             }
             tc_commit(smem_u32(&s_tmem_full));
         }
@@ -252,6 +259,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int nchunks = P.BN / 32;
         const int lrow = lane >> 3, lcol = (lane & 7) * 4;
         float* stg = reinterpret_cast<float*>(tc_smem_raw + (smem_base - smem_u32(tc_smem_raw))) + ew * (32 * TC_EPI_PITCH);
+        // ---- operand converter: raw fp32 tile (as landed by TMA) -> TF32 hi in place + TF32 lo in the neighbouring slot.
+        //      Element-wise and position-preserving, so the 128-byte swizzle is irrelevant here.
+        {
+            uint8_t* sbase = tc_smem_raw + (smem_base - smem_u32(tc_smem_raw));
+            const int et = threadIdx.x - 64;                       // 0..127
+            const int a_v4 = (int)(a_tile / 16), b_v4 = (int)(b_tile / 16);
+            for (int it = 0; it < nkb; ++it) {
+                const int st = it % P.stages;
+                const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
+                mbar_wait(smem_u32(&s_full[st]), ph);
+                if (trace && it < 16 && et == 0) trace[it * 8 + 2] = gtimer();   // tile landed
+                float4* a_hi = reinterpret_cast<float4*>(sbase + (size_t)st * stage_bytes);
+                float4* a_lo = a_hi + a_v4;
+                float4* b_hi = a_lo + a_v4;
+                float4* b_lo = b_hi + b_v4;
+                // all loads of the stage are issued before the first store (the compiler must not serialise them
+                // behind the shared-memory stores): 8 float4 of A and up to 8 of B per thread
+                const int nb = b_v4 >> 7;                          // 4 (BN = 64) or 8 (BN = 128)
+                float4 xa[8], xb[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) xa[j] = a_hi[et + 128 * j];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) xb[j] = (j < nb) ? b_hi[et + 128 * j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (P.split_mode == 2) {
+                    // the TF32 datapath ignores the 13 low mantissa bits of an fp32 operand, so the raw tile already IS the
+                    // hi operand (truncation split); only lo = x - trunc(x) (exact in fp32) has to be produced
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a_lo[et + 128 * j] = tc_lo_trunc(xa[j]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) if (j < nb) b_lo[et + 128 * j] = tc_lo_trunc(xb[j]);
+                } else {
+                    // explicit round-to-nearest split (cvt.rna.tf32.f32 on both parts): the checker for mode 2
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 h, l;
+                        split_tf32(xa[j].x, h.x, l.x); split_tf32(xa[j].y, h.y, l.y); split_tf32(xa[j].z, h.z, l.z); split_tf32(xa[j].w, h.w, l.w);
+                        a_hi[et + 128 * j] = h; a_lo[et + 128 * j] = l;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j < nb) {
+                            float4 h, l;
+                            split_tf32(xb[j].x, h.x, l.x); split_tf32(xb[j].y, h.y, l.y); split_tf32(xb[j].z, h.z, l.z); split_tf32(xb[j].w, h.w, l.w);
+                            b_hi[et + 128 * j] = h; b_lo[et + 128 * j] = l;
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to tcgen05.mma
+                __syncwarp();
+                if (trace && it < 16 && et == 0) trace[it * 8 + 3] = gtimer();   // split done
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_ready[st])) : "memory");
+            }
+        }
         mbar_wait(smem_u32(&s_tmem_full), 0);
         tc_fence_after();
         if (dbg && threadIdx.x == 64) dbg[4] = gtimer();              // accumulator complete
@@ -376,25 +436,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// elementwise helpers for the (raw, hi, lo) activation format
-// ------------------------------------------------------------------------------------------------------------
-__global__ void split_kernel(const float4* __restrict__ in, float4* __restrict__ hi, float4* __restrict__ lo, size_t n4) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    const float4 v = in[i];
-    float4 h, l;
-    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-    hi[i] = h; lo[i] = l;
-}
-
-int launch_split_tf32(const float* in, float* hi, float* lo, size_t n, cudaStream_t st) {
-    const size_t n4 = n / 4;
-    split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const float4*)in, (float4*)hi, (float4*)lo, n4);
-    B200_LAUNCH_CHECK();
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -424,18 +465,6 @@ bool tc_conv_supported(const Op& op) {
     if (op.stride == 2 && !env_int("B200TRK_TC_STRIDE2", 1)) return false;
     if (op.stride != 1 && op.stride != 2) return false;
     return env_int("B200TRK_TC", 1) != 0;
-}
-
-static void split_host(const std::vector<float>& w, std::vector<float>& hi, std::vector<float>& lo) {
-    auto rna = [](float x) {
-        uint32_t u; memcpy(&u, &x, 4);
-        if ((u & 0x7f800000u) != 0x7f800000u) u += 0x1000u;   // round to nearest, ties away (cvt.rna)
-        u &= 0xffffe000u;
-        float r; memcpy(&r, &u, 4);
-        return r;
-    };
-    hi.resize(w.size()); lo.resize(w.size());
-    for (size_t i = 0; i < w.size(); ++i) { hi[i] = rna(w[i]); lo[i] = rna(w[i] - hi[i]); }
 }
 
 static int make_map_2d(CUtensorMap* m, float* base, uint64_t K, uint64_t N, uint32_t boxN) {
@@ -481,19 +510,9 @@ static void pick_tile(int Wout, int Hout, int stride, int* BW, int* BH) {
 }
 
 int tc_conv_prepare(b200trk_net* net, Op& op, const std::vector<float>& w_khwc) {
+    (void)w_khwc;                    // the raw repacked weights (op.w) are the B operand; the TF32 split happens in the kernel
     TcConv* tc = new TcConv();
     op.tc = tc;
-    std::vector<float> hi, lo;
-    split_host(w_khwc, hi, lo);
-    void *ph = nullptr, *pl = nullptr;
-    B200_CHECK_CUDA(cudaMalloc(&ph, hi.size() * sizeof(float)));
-    net->owned.push_back(ph);
-    B200_CHECK_CUDA(cudaMalloc(&pl, lo.size() * sizeof(float)));
-    net->owned.push_back(pl);
-    B200_CHECK_CUDA(cudaMemcpy(ph, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
-    B200_CHECK_CUDA(cudaMemcpy(pl, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
-    tc->w_hi = (float*)ph; tc->w_lo = (float*)pl;
-
     TcParams& P = tc->P;
     memset(&P, 0, sizeof(P));
     P.Hout = op.Hout; P.Wout = op.Wout; P.Cout = op.Cout; P.Cin = op.Cin;
@@ -505,11 +524,10 @@ int tc_conv_prepare(b200trk_net* net, Op& op, const std::vector<float>& w_khwc) 
     P.total_kb = op.k * op.k * P.cblks;
     P.a_bytes = (uint32_t)(P.BW * P.BH) * 128u;
     P.bias = op.bias;
-    P.out_raw = net->bufs[op.out]; P.out_hi = net->bufs_hi[op.out]; P.out_lo = net->bufs_lo[op.out];
+    P.out_raw = net->bufs[op.out];
     P.residual = op.res >= 0 ? net->bufs[op.res] : nullptr;
-    P.ws = net->splitk_ws;           // filled in at launch (allocated after the plan is built)
-    if (int e = make_map_4d(&P.a_hi, net->bufs_hi[op.in], op.Cin, op.Win, op.Hin, net->max_batch, P.BW, P.BH, op.stride)) return e;
-    if (int e = make_map_4d(&P.a_lo, net->bufs_lo[op.in], op.Cin, op.Win, op.Hin, net->max_batch, P.BW, P.BH, op.stride)) return e;
+    P.ws = net->splitk_ws;
+    if (int e = make_map_4d(&P.a_map, net->bufs[op.in], op.Cin, op.Win, op.Hin, net->max_batch, P.BW, P.BH, op.stride)) return e;
     void* cnt = nullptr;
     B200_CHECK_CUDA(cudaMalloc(&cnt, 1024 * sizeof(unsigned)));
     B200_CHECK_CUDA(cudaMemset(cnt, 0, 1024 * sizeof(unsigned)));
@@ -529,7 +547,7 @@ static int tc_configure(b200trk_net* net, const Op& op, TcConv* tc, int S) {
         // a second wave of 1-CTA-per-SM tiles doubles the layer time: widen the tile as soon as BN = 64 overflows the SMs
         if (op.Cout % 128 == 0 && m_tiles * (op.Cout / 64) > net->sms) BN = 128;
     }
-    if (op.Cout % BN != 0) BN = 64;
+    if (op.Cout % BN != 0 || (BN != 64 && BN != 128)) BN = 64;
     P.BN = BN;
     P.b_bytes = (uint32_t)BN * 128u;
     const uint32_t stage_bytes = 2u * TC_BM * 128u + 2u * P.b_bytes;
@@ -552,9 +570,9 @@ static int tc_configure(b200trk_net* net, const Op& op, TcConv* tc, int S) {
     P.splits = (P.total_kb + P.kb_per_split - 1) / P.kb_per_split;
     B200_REQUIRE(ctas <= 512 || P.splits == 1, "tc_conv: counter array too small for %d tiles", ctas);
     P.ws = net->splitk_ws;
+    P.split_mode = env_int("B200TRK_TC_SPLIT_MODE", 2);
     const size_t Kt = (size_t)op.k * op.k * op.Cin;
-    if (int e = make_map_2d(&P.b_hi, tc->w_hi, Kt, op.Cout, BN)) return e;
-    if (int e = make_map_2d(&P.b_lo, tc->w_lo, Kt, op.Cout, BN)) return e;
+    if (int e = make_map_2d(&P.b_map, op.w, Kt, op.Cout, BN)) return e;
     tc->S_built = S;
     return 0;
 }
@@ -588,7 +606,11 @@ int tc_conv_launch(b200trk_net* net, const Op& op, int S, cudaStream_t st) {
 
 void tc_conv_free(TcConv* tc) { delete tc; }
 
-int tc_conv_set_debug(Op& op, unsigned long long* buf) { op.tc->P.dbg = buf; return 0; }
+int tc_conv_set_debug(Op& op, unsigned long long* buf) {
+    op.tc->P.dbg = buf;
+    op.tc->P.trace = buf ? buf + 8 * 2048 : nullptr;     // second half of the [4096][8] debug buffer
+    return 0;
+}
 int tc_conv_grid(const Op& op, int dims[4]) {
     const TcParams& P = op.tc->P;
     const int S = op.tc->S_built > 0 ? op.tc->S_built : 1;

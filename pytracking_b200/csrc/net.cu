@@ -4,6 +4,7 @@
 #include "net.cuh"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace b200trk {
 
@@ -11,7 +12,6 @@ int tc_conv_prepare(b200trk_net* net, Op& op, const std::vector<float>& w_khwc);
 int tc_conv_launch(b200trk_net* net, const Op& op, int S, cudaStream_t st);         // conv_tc.cu
 void tc_conv_free(TcConv* tc);
 bool tc_conv_supported(const Op& op);
-int launch_split_tf32(const float* in, float* hi, float* lo, size_t n, cudaStream_t st);   // conv_tc.cu
 
 static int dev_alloc(b200trk_net* net, float** p, size_t floats) {
     void* q = nullptr;
@@ -26,13 +26,6 @@ static int new_buf(b200trk_net* net, size_t floats_per_sample, int* id) {
     if (int e = dev_alloc(net, &p, floats_per_sample * (size_t)net->max_batch)) return e;
     net->bufs.push_back(p);
     net->buf_floats.push_back(floats_per_sample);
-    float *hi = nullptr, *lo = nullptr;
-    if (net->precision == 0) {
-        if (int e = dev_alloc(net, &hi, floats_per_sample * (size_t)net->max_batch)) return e;
-        if (int e = dev_alloc(net, &lo, floats_per_sample * (size_t)net->max_batch)) return e;
-    }
-    net->bufs_hi.push_back(hi);
-    net->bufs_lo.push_back(lo);
     *id = (int)net->bufs.size() - 1;
     return 0;
 }
@@ -117,10 +110,10 @@ static int build(b200trk_net* net, const b200trk_conv_desc_t* convs, int n_convs
                      "net_create: first conv must be the 7x7/2 stem (3->64)");
         std::vector<float> w, b; bool hb;
         fold_and_repack(d, w, b, hb);                 // [64][49][3]
-        std::vector<float> w4((size_t)64 * 49 * 4, 0.f);
+        std::vector<float> w4((size_t)49 * 3 * 64, 0.f);   // [tap][cin][cout] (warp-broadcast friendly)
         for (int co = 0; co < 64; ++co)
             for (int t = 0; t < 49; ++t)
-                for (int ci = 0; ci < 3; ++ci) w4[((size_t)co * 49 + t) * 4 + ci] = w[((size_t)co * 49 + t) * 3 + ci];
+                for (int ci = 0; ci < 3; ++ci) w4[((size_t)t * 3 + ci) * 64 + co] = w[((size_t)co * 49 + t) * 3 + ci];
         Op op; op.kind = OP_STEM; op.in = b_in; op.Hin = H; op.Win = W; op.Cin = 3; op.Cout = 64; op.k = 7; op.stride = 2; op.pad = 3;
         op.Hout = (H + 6 - 7) / 2 + 1; op.Wout = (W + 6 - 7) / 2 + 1; op.relu = 1;
         if (int e = dev_alloc(net, &op.w, w4.size())) return e;
@@ -195,6 +188,8 @@ static int build(b200trk_net* net, const b200trk_conv_desc_t* convs, int n_convs
 
 using namespace b200trk;
 
+static void drop_graph(b200trk_net_t* net);
+
 extern "C" int b200trk_net_create(b200trk_net_t** out, int arch, const b200trk_conv_desc_t* convs, int n_convs,
                                   float norm_scale, int max_batch, int crop_h, int crop_w, int precision) {
     B200_REQUIRE(out && convs, "net_create: null pointer");
@@ -217,6 +212,7 @@ extern "C" int b200trk_net_create(b200trk_net_t** out, int arch, const b200trk_c
 
 extern "C" int b200trk_net_destroy(b200trk_net_t* net) {
     if (!net) return 0;
+    drop_graph(net);
     for (auto& op : net->ops) if (op.tc) tc_conv_free(op.tc);
     for (void* p : net->owned) cudaFree(p);
     delete net;
@@ -236,6 +232,8 @@ extern "C" int b200trk_net_op_set_timing_buffer(b200trk_net_t* net, int index, u
     B200_REQUIRE(net && index >= 0 && index < (int)net->ops.size(), "net_op_set_timing_buffer: bad argument");
     Op& op = net->ops[index];
     B200_REQUIRE(op.tc, "net_op_set_timing_buffer: step %d does not run on the tensor cores", index);
+    drop_graph(net);
+    net->gkey.hits = -1000000;         // instrumented runs stay eager
     return tc_conv_set_debug(op, buf);
 }
 // Debug: launch geometry of a tensor-core step as last configured: dims = {gridDim.x, gridDim.y, gridDim.z, BN}.
@@ -265,11 +263,55 @@ extern "C" int b200trk_net_op_output(const b200trk_net_t* net, int index, int S,
 
 extern "C" double b200trk_net_flops(const b200trk_net_t* net) { return net ? net->flops : 0.0; }
 
+static int net_forward_eager(b200trk_net_t* net, const float* crop, int S, float* layer2, float* layer3, float* clf, cudaStream_t st);
+
+static void drop_graph(b200trk_net_t* net) {
+    if (net->gexec) { cudaGraphExecDestroy(net->gexec); net->gexec = nullptr; }
+    net->gkey.hits = 0;
+}
+
 extern "C" int b200trk_net_forward(b200trk_net_t* net, const float* crop, int S, float* layer2, float* layer3, float* clf,
                                    b200trk_stream_t stream) {
     B200_REQUIRE(net && crop, "net_forward: null pointer");
     B200_REQUIRE(S >= 1 && S <= net->max_batch, "net_forward: batch %d outside [1,%d]", S, net->max_batch);
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool use_graph = []() { const char* v = getenv("B200TRK_GRAPH"); return !v || atoi(v) != 0; }();
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (use_graph) cudaStreamIsCapturing(st, &cs);
+    if (!use_graph || cs != cudaStreamCaptureStatusNone) return net_forward_eager(net, crop, S, layer2, layer3, clf, st);
+    auto& k = net->gkey;
+    const bool same = k.crop == crop && k.l2 == layer2 && k.l3 == layer3 && k.clf == clf && k.S == S;
+    if (!same) {
+        drop_graph(net);
+        k.crop = crop; k.l2 = layer2; k.l3 = layer3; k.clf = clf; k.S = S;
+    }
+    if (net->gexec) {
+        B200_CHECK_CUDA(cudaGraphLaunch(net->gexec, st));
+        g_launch_count.fetch_add(net->graph_kernels, std::memory_order_relaxed);   // kernels inside the replayed graph
+        return 0;
+    }
+    if (++k.hits < 3) return net_forward_eager(net, crop, S, layer2, layer3, clf, st);   // lazy per-S setup happens eagerly
+    // third identical call: record the launch sequence (programmatic-dependent-launch edges included) and replay it from now on
+    cudaGraph_t g = nullptr;
+    B200_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const uint64_t before = g_launch_count.load();
+    const int e = net_forward_eager(net, crop, S, layer2, layer3, clf, st);
+    net->graph_kernels = g_launch_count.load() - before;
+    cudaError_t ce = cudaStreamEndCapture(st, &g);
+    if (e || ce != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        k.hits = -1000000;                 // capture not possible here: stay eager
+        return e ? e : net_forward_eager(net, crop, S, layer2, layer3, clf, st);
+    }
+    ce = cudaGraphInstantiate(&net->gexec, g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) { net->gexec = nullptr; cudaGetLastError(); k.hits = -1000000; return net_forward_eager(net, crop, S, layer2, layer3, clf, st); }
+    B200_CHECK_CUDA(cudaGraphLaunch(net->gexec, st));
+    return 0;
+}
+
+static int net_forward_eager(b200trk_net_t* net, const float* crop, int S, float* layer2, float* layer3, float* clf, cudaStream_t st) {
     for (const Op& op : net->ops) {
         switch (op.kind) {
         case OP_PREPROCESS:
@@ -280,9 +322,6 @@ extern "C" int b200trk_net_forward(b200trk_net_t* net, const float* crop, int S,
             break;
         case OP_MAXPOOL:
             if (int e = launch_maxpool3x3s2(net->bufs[op.in], net->bufs[op.out], S, op.Hin, op.Win, op.Cin, st)) return e;
-            if (net->precision == 0)
-                if (int e = launch_split_tf32(net->bufs[op.out], net->bufs_hi[op.out], net->bufs_lo[op.out],
-                                              (size_t)S * op.Hout * op.Wout * op.Cout, st)) return e;
             break;
         case OP_CONV: {
             if (op.tc) {
@@ -293,9 +332,6 @@ extern "C" int b200trk_net_forward(b200trk_net_t* net, const float* crop, int S,
             ConvEpilogue ep{op.bias, op.res >= 0 ? net->bufs[op.res] : nullptr, op.relu};
             if (int e = launch_conv_fp32(net->bufs[op.in], op.w, net->bufs[op.out], sh, ep, net->splitk_ws,
                                          net->splitk_ws_floats, net->sms, st)) return e;
-            if (net->precision == 0)
-                if (int e = launch_split_tf32(net->bufs[op.out], net->bufs_hi[op.out], net->bufs_lo[op.out],
-                                              (size_t)S * op.Hout * op.Wout * op.Cout, st)) return e;
             break;
         }
         case OP_EXPORT_NCHW: {

@@ -28,7 +28,6 @@ struct b200trk_net {
     float norm_scale = 1.f;
     std::vector<b200trk::Op> ops;
     std::vector<float*> bufs;            // activation buffers (device, NHWC fp32), sized for max_batch
-    std::vector<float*> bufs_hi, bufs_lo; // precision 0: TF32 (hi, lo) split copies of each buffer (operands of the 3xTF32 MMAs)
     std::vector<size_t> buf_floats;      // per-sample floats of each buffer
     std::vector<void*> owned;            // every device allocation (freed in destroy)
     float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;
@@ -36,4 +35,8 @@ struct b200trk_net {
     int dims[9] = {0};
     double flops = 0.0;
     int sms = 1;
+    // CUDA-graph cache of one forward pass (the per-frame call repeats with identical pointers): key + executable graph
+    struct { const float* crop = nullptr; float *l2 = nullptr, *l3 = nullptr, *clf = nullptr; int S = 0; int hits = 0; } gkey;
+    cudaGraphExec_t gexec = nullptr;
+    uint64_t graph_kernels = 0;
 };
