@@ -41,6 +41,9 @@ typedef struct b200trk_net b200trk_net_t;    /* opaque: folded + repacked networ
 
 int         b200trk_version(void);
 const char* b200trk_last_error(void);
+/* Debug aid: when B200TRK_SD_TRACE is set in the environment the SD optimiser kernels record 64 phase time stamps
+ * (globaltimer ns) of CTA 0; this copies them to out_host[64]. */
+int b200trk_debug_sd_trace(unsigned long long* out_host);
 /* Number of kernels this library has launched so far in this process (for bench.py's gpu_launches). */
 uint64_t    b200trk_launch_count(void);
 

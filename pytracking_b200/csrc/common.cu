@@ -64,6 +64,13 @@ int device_sm_count() {
 
 }  // namespace b200trk
 
+// debug: copy the SD optimiser phase trace (64 x u64) to the host
+extern "C" int b200trk_debug_sd_trace(unsigned long long* out_host) {
+    void* p = b200trk::workspace(1024, 3);
+    if (!p || !out_host) return 1;
+    return cudaMemcpy(out_host, p, 512, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
+}
+
 extern "C" int b200trk_version(void) { return B200TRK_VERSION; }
 extern "C" const char* b200trk_last_error(void) { return b200trk::g_err; }
 extern "C" uint64_t b200trk_launch_count(void) { return b200trk::g_launch_count.load(); }

@@ -213,6 +213,7 @@ extern "C" int b200trk_net_create(b200trk_net_t** out, int arch, const b200trk_c
 extern "C" int b200trk_net_destroy(b200trk_net_t* net) {
     if (!net) return 0;
     drop_graph(net);
+    if (net->cap_stream) cudaStreamDestroy(net->cap_stream);
     for (auto& op : net->ops) if (op.tc) tc_conv_free(op.tc);
     for (void* p : net->owned) cudaFree(p);
     delete net;
@@ -277,7 +278,7 @@ extern "C" int b200trk_net_forward(b200trk_net_t* net, const float* crop, int S,
     cudaStream_t st = (cudaStream_t)stream;
     static const bool use_graph = []() { const char* v = getenv("B200TRK_GRAPH"); return !v || atoi(v) != 0; }();
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (use_graph) cudaStreamIsCapturing(st, &cs);
+    if (use_graph && cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusActive; }
     if (!use_graph || cs != cudaStreamCaptureStatusNone) return net_forward_eager(net, crop, S, layer2, layer3, clf, st);
     auto& k = net->gkey;
     const bool same = k.crop == crop && k.l2 == layer2 && k.l3 == layer3 && k.clf == clf && k.S == S;
@@ -292,12 +293,14 @@ extern "C" int b200trk_net_forward(b200trk_net_t* net, const float* crop, int S,
     }
     if (++k.hits < 3) return net_forward_eager(net, crop, S, layer2, layer3, clf, st);   // lazy per-S setup happens eagerly
     // third identical call: record the launch sequence (programmatic-dependent-launch edges included) and replay it from now on
+    // (recorded on a private stream: the caller's stream may be the legacy default stream, which cannot capture)
     cudaGraph_t g = nullptr;
-    B200_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    if (!net->cap_stream) B200_CHECK_CUDA(cudaStreamCreateWithFlags(&net->cap_stream, cudaStreamNonBlocking));
+    B200_CHECK_CUDA(cudaStreamBeginCapture(net->cap_stream, cudaStreamCaptureModeThreadLocal));
     const uint64_t before = g_launch_count.load();
-    const int e = net_forward_eager(net, crop, S, layer2, layer3, clf, st);
+    const int e = net_forward_eager(net, crop, S, layer2, layer3, clf, net->cap_stream);
     net->graph_kernels = g_launch_count.load() - before;
-    cudaError_t ce = cudaStreamEndCapture(st, &g);
+    cudaError_t ce = cudaStreamEndCapture(net->cap_stream, &g);
     if (e || ce != cudaSuccess || !g) {
         if (g) cudaGraphDestroy(g);
         cudaGetLastError();

@@ -39,4 +39,5 @@ struct b200trk_net {
     struct { const float* crop = nullptr; float *l2 = nullptr, *l3 = nullptr, *clf = nullptr; int S = 0; int hits = 0; } gkey;
     cudaGraphExec_t gexec = nullptr;
     uint64_t graph_kernels = 0;
+    cudaStream_t cap_stream = nullptr;
 };

@@ -6,14 +6,17 @@
 // iterations by linearity, s_{k+1} = A w_{k+1} = s_k - step*alpha_k * (A g_k), so an iteration costs two
 // sweeps over the sample memory (A^T r and A g) instead of the reference's three.
 //
-// Decomposition: CTA = (channel chunk, sample group); grid = NCH x NG <= #SMs, launched cooperatively.
+// Decomposition: CTA = (channel chunk, sample group); grid = NCH x NG <= #SMs, launched cooperatively. The sample
+// planes are streamed by the cp.async multistage sweeps of corr2.cuh (next sweep's first planes are prefetched
+// across each grid barrier).
 // Residual maps, labels, the chunk's filter taps and gradient stay in shared memory for the whole call;
 // the sample memory is streamed from L2 (it is re-read 2x per iteration; 33 MB at n=50 is L2 resident).
 // Cross-CTA exchange per iteration (all via L2, fixed summation order => bitwise deterministic):
 //   gpart [NG][C*16]   partial gradients     -> barrier 1 -> each CTA sums its own chunk over the groups
 //   qpart [n][NCH][NPOS] partial A g maps    -> barrier 2 -> each CTA sums its own samples over the chunks
 //   hpart [NG], gnorm [NCH] scalars          -> barrier 3 -> step length alpha
-#include "corr.cuh"
+#include "corr2.cuh"
+#include <cstdlib>
 
 namespace b200trk {
 
@@ -21,7 +24,7 @@ constexpr int SD_SPC_MAX = 8;    // samples per CTA held in shared memory
 
 struct SdParams {
     const float* w_in; float* w_out; const float* feat; const float* bb; const float* sample_weight;
-    int n, C, passes, NCH, NG, num_iter;
+    int n, C, passes, NCH, NG, num_iter, spc_max, dbg_mode;
     // DiMP
     const float* label_lut; const float* mask_lut; const float* spatial_lut; int num_bins; float inv_bin_disp;
     // PrDiMP
@@ -32,7 +35,15 @@ struct SdParams {
     float* iterates_out; float* losses_out;
     // workspace
     float* gpart; float* qpart; float* hpart; float* gnorm; float* lossr; float* lossw; unsigned* barrier;
+    unsigned long long* trace;     // optional [64] phase stamps of CTA 0 (globaltimer ns)
 };
+
+__device__ __forceinline__ unsigned long long sd_gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define SD_STAMP(k) do { if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && (k) < 64) P.trace[(k)] = sd_gtimer(); } while (0)
 
 __device__ __forceinline__ float lut_lerp(const float* lut, int nb, float rho) {
     // DistanceMap + 1x1 conv == piece-wise linear LUT with last-bin clamp (distance.py:33-37)
@@ -42,43 +53,59 @@ __device__ __forceinline__ float lut_lerp(const float* lut, int nb, float rho) {
     return lut[b] * (1.f - f) + lut[b + 1] * f;
 }
 
-template <int FS, int SLOTS, int MODE>
-__global__ void __launch_bounds__(CorrCta<FS, SLOTS>::NTHREADS, 1)
+// sum_{k<count} p[k*stride] in index order with 8 loads in flight (L2 latency is paid once per batch, not per term)
+__device__ __forceinline__ float ordered_sum_ldcg(const float* p, size_t stride, int count) {
+    float s = 0.f;
+    for (int k0 = 0; k0 < count; k0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (k0 + u < count) ? __ldcg(p + (size_t)(k0 + u) * stride) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    return s;
+}
+
+template <int FS, int NST, int MODE>
+__global__ void __launch_bounds__(Corr2<FS>::NCONS, 1)
 sd_kernel(SdParams P) {
-    using K = CorrCta<FS, SLOTS>;
-    using G = CorrGeom<FS>;
-    constexpr int NPOS = G::NPOS, OS = G::OS, NTH = K::NTHREADS;
-    extern __shared__ float smem[];
-    float* planes = smem;
-    float* red = planes + K::PLANES_FLOATS;
+    using K = Corr2<FS>;
+    constexpr int NPOS = K::NPOS, OS = K::OS, NTH = K::NCONS, SLOTS = K::SLOTS, VS = K::VEC_STRIDE, PMAP = K::PMAP, PW = K::PW;
+    extern __shared__ __align__(16) float smem[];
+    float* stages = smem;                                     // [NST][ITEM_FLOATS]  zero-bordered sample planes
+    float* red = stages + NST * K::ITEM_FLOATS;               // [NT*16*17]          tile -> channel gradient reduction
     const int cchunk = P.passes * SLOTS;
-    float* wv = red + K::RED_FLOATS;          // [cchunk*16] current filter taps of the chunk
-    float* gv = wv + cchunk * 16;             // [cchunk*16] gradient taps of the chunk
-    float* sS = gv + cchunk * 16;             // [spc][NPOS] scores
-    float* sY = sS + SD_SPC_MAX * NPOS;       // DiMP: label y        | PrDiMP: label density p
-    float* sM = sY + SD_SPC_MAX * NPOS;       // DiMP: target mask m  | PrDiMP: softmax(s)
-    float* sV = sM + SD_SPC_MAX * NPOS;       // DiMP: sqrt(sw)*v     | PrDiMP: unused
-    float* sT = sV + SD_SPC_MAX * NPOS;       // mapped residual, then q = A g
+    float* wv = red + K::NT * SLOTS * K::RED_STRIDE;          // [cchunk][VS] current filter taps of the chunk
+    float* gv = wv + cchunk * VS;                             // [cchunk][VS] gradient taps of the chunk
+    float* sT = gv + cchunk * VS;                             // [spc][PMAP] mapped residual, tile-padded (zero outside the map); 16-byte aligned
+    float* sS = sT + P.spc_max * PMAP;                        // [spc][NPOS] scores
+    float* sY = sS + P.spc_max * NPOS;                        // DiMP: label y        | PrDiMP: label density p
+    float* sM = sY + P.spc_max * NPOS;                        // DiMP: target mask m  | PrDiMP: softmax(s)
+    float* sV = sM + P.spc_max * NPOS;                        // DiMP: sqrt(sw)*v     | PrDiMP: unused
+    float* sQ = sV + P.spc_max * NPOS;                        // q = A g
     __shared__ float s_red[32];
     __shared__ float s_sw[SD_SPC_MAX];
     __shared__ float s_scal[4];
 
     const int tid = threadIdx.x;
     const int chunk = blockIdx.x % P.NCH, group = blockIdx.x / P.NCH;
-    typename K::Ctx cx{P.feat, P.C, P.n, chunk * cchunk, P.passes, group, P.NG};
+    typename K::Ctx cx{P.feat, P.C, P.n, chunk * cchunk, P.passes, group, P.NG, P.dbg_mode};
     const int spc = cx.spc();
     unsigned epoch = 0;
     const size_t qstride = (size_t)P.NCH * NPOS;
     const float reg = P.reg_weight;
 
-    // ---- prologue: zero staging planes, load filter chunk, build per-sample label maps ------------------
-    K::zero_planes(planes);
-    for (int o = tid; o < cchunk * 16; o += NTH) wv[o] = P.w_in[(size_t)chunk * cchunk * 16 + o];
+    SD_STAMP(0);
+    // ---- prologue: zero staging planes + padded residual maps, load filter chunk, build per-sample label maps ----
+    K::zero_stages(stages, NST);
+    for (int o = tid; o < P.spc_max * PMAP; o += NTH) sT[o] = 0.f;
+    for (int o = tid; o < cchunk * 16; o += NTH) wv[(o >> 4) * VS + (o & 15)] = P.w_in[(size_t)chunk * cchunk * 16 + o];
     if (tid < spc) {
         const int i = cx.sample(tid);
         s_sw[tid] = P.sample_weight ? P.sample_weight[i] : 1.0f / (float)P.n;
     }
     __syncthreads();
+    K::template sweep_prologue<true, NST>(cx, stages);         // first planes are in flight while the label maps are built
     for (int j = 0; j < spc; ++j) {
         const int i = cx.sample(j);
         const float bx = P.bb[4 * i], by = P.bb[4 * i + 1], bw = P.bb[4 * i + 2], bh = P.bb[4 * i + 3];
@@ -114,30 +141,35 @@ sd_kernel(SdParams P) {
     }
     __syncthreads();
 
+    SD_STAMP(1);
     // ---- s0 = A w0 -----------------------------------------------------------------------------------------
-    K::sweep_apply(cx, planes, red, wv, P.qpart + (size_t)chunk * NPOS, qstride);
+    K::template sweep_apply<NST>(cx, stages, wv, P.qpart + (size_t)chunk * NPOS, qstride);
+    SD_STAMP(2);
+    if (P.num_iter > 0) K::template sweep_prologue<false, NST>(cx, stages);   // planes of the first gradient sweep fly across the barrier
     grid_barrier(P.barrier, epoch);
+    SD_STAMP(3);
     for (int o = tid; o < spc * NPOS; o += NTH) {
         const int j = o / NPOS, pos = o - j * NPOS;
-        const float* qp = P.qpart + (size_t)cx.sample(j) * qstride + pos;
-        float s = 0.f;
-        for (int ch = 0; ch < P.NCH; ++ch) s += __ldcg(qp + (size_t)ch * NPOS);
-        sS[o] = s;
+        sS[o] = ordered_sum_ldcg(P.qpart + (size_t)cx.sample(j) * qstride + pos, NPOS, P.NCH);
     }
     __syncthreads();
 
+    SD_STAMP(4);
     for (int it = 0; it <= P.num_iter; ++it) {
+        const int tb = 8 + it * 10;
+        SD_STAMP(tb + 0);
         // ---- residuals from the current scores (also the loss terms of iterate `it`) -----------------------
         float lloc = 0.f;
         if (MODE == 0) {
             for (int o = tid; o < spc * NPOS; o += NTH) {
+                const int j = o / NPOS, pos = o - j * NPOS;
                 const float s = sS[o], m = sM[o], vh = sV[o];
                 const float act = 0.5f * (1.f - m) * fabsf(s) + 0.5f * (1.f + m) * s;
                 const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
                 const float dact = 0.5f * (1.f - m) * sg + 0.5f * (1.f + m);
                 const float r = vh * (act - sY[o]);
                 lloc += r * r;
-                sT[o] = dact * (vh * r);
+                sT[j * PMAP + (pos / OS) * PW + (pos % OS)] = dact * (vh * r);
             }
         } else {
             for (int j = 0; j < spc; ++j) {
@@ -166,7 +198,7 @@ sd_kernel(SdParams P) {
                 for (int pos = tid; pos < NPOS; pos += NTH) {
                     const float sm = sM[j * NPOS + pos] * inv;
                     sM[j * NPOS + pos] = sm;
-                    sT[j * NPOS + pos] = sw * (sm - sY[j * NPOS + pos]);
+                    sT[j * PMAP + (pos / OS) * PW + (pos % OS)] = sw * (sm - sY[j * NPOS + pos]);
                 }
                 // loss_i = sw * (log(sum exp(s) + exp(reg)) - sum p*s)  (optimizer.py:393-396)
                 if (tid == 0) lloc += sw * ((logf(den) + mx) - ps);
@@ -175,7 +207,7 @@ sd_kernel(SdParams P) {
         if (P.losses_out) {
             const float lr = block_sum(lloc, s_red);
             float lw = 0.f;
-            for (int o = tid; o < cchunk * 16; o += NTH) lw += wv[o] * wv[o];
+            for (int o = tid; o < cchunk * 16; o += NTH) { const float w = wv[(o >> 4) * VS + (o & 15)]; lw += w * w; }
             lw = block_sum(lw, s_red);
             if (tid == 0) {
                 if (chunk == 0) P.lossr[it * P.NG + group] = lr;
@@ -185,35 +217,51 @@ sd_kernel(SdParams P) {
         if (it == P.num_iter) break;
         __syncthreads();
 
+        SD_STAMP(tb + 1);
         // ---- phase 1: partial gradient of the chunk over the CTA's samples -----------------------------------
-        K::sweep_transpose(cx, planes, red, sT, P.gpart + ((size_t)group * P.C + chunk * cchunk) * 16);
+        K::template sweep_transpose<NST>(cx, stages, red, sT, P.gpart + ((size_t)group * P.C + chunk * cchunk) * 16);
+        SD_STAMP(tb + 2);
+        K::template sweep_prologue<true, NST>(cx, stages);
         grid_barrier(P.barrier, epoch);
+        SD_STAMP(tb + 3);
 
         // ---- phase 2: g = sum_groups gpart + reg*w ; ||g_chunk||^2 ; partial q = A g ---------------------------
         float gl = 0.f;
-        for (int o = tid; o < cchunk * 16; o += NTH) {
-            const float* gp = P.gpart + (size_t)chunk * cchunk * 16 + o;
-            float s = 0.f;
-            for (int g = 0; g < P.NG; ++g) s += __ldcg(gp + (size_t)g * P.C * 16);
-            s += reg * wv[o];
-            gv[o] = s;
-            gl += s * s;
+        for (int o4 = tid; o4 < cchunk * 4; o4 += NTH) {       // 4 consecutive taps per thread, all group loads in flight at once
+            const float4* gp = reinterpret_cast<const float4*>(P.gpart + (size_t)chunk * cchunk * 16) + o4;
+            const size_t gstride4 = (size_t)P.C * 4;
+            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int g0 = 0; g0 < P.NG; g0 += 10) {
+                float4 v[10];
+#pragma unroll
+                for (int u = 0; u < 10; ++u)
+                    v[u] = (g0 + u < P.NG) ? __ldcg(gp + (size_t)(g0 + u) * gstride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 10; ++u) { s4.x += v[u].x; s4.y += v[u].y; s4.z += v[u].z; s4.w += v[u].w; }
+            }
+            const int vi = (o4 >> 2) * VS + (o4 & 3) * 4;
+            const float4 w4 = *reinterpret_cast<const float4*>(wv + vi);
+            s4.x += reg * w4.x; s4.y += reg * w4.y; s4.z += reg * w4.z; s4.w += reg * w4.w;
+            *reinterpret_cast<float4*>(gv + vi) = s4;
+            gl += s4.x * s4.x + s4.y * s4.y + s4.z * s4.z + s4.w * s4.w;
         }
         gl = block_sum(gl, s_red);
         if (group == 0 && tid == 0) P.gnorm[chunk] = gl;
         __syncthreads();
-        K::sweep_apply(cx, planes, red, gv, P.qpart + (size_t)chunk * NPOS, qstride);
+        SD_STAMP(tb + 4);
+        K::template sweep_apply<NST>(cx, stages, gv, P.qpart + (size_t)chunk * NPOS, qstride);
+        SD_STAMP(tb + 5);
+        if (it + 1 < P.num_iter) K::template sweep_prologue<false, NST>(cx, stages);
         grid_barrier(P.barrier, epoch);
+        SD_STAMP(tb + 6);
 
         // ---- phase 3: q_i over all chunks, curvature term --------------------------------------------------------
         float hl = 0.f;
         if (MODE == 0) {
             for (int o = tid; o < spc * NPOS; o += NTH) {
                 const int j = o / NPOS, pos = o - j * NPOS;
-                const float* qp = P.qpart + (size_t)cx.sample(j) * qstride + pos;
-                float q = 0.f;
-                for (int ch = 0; ch < P.NCH; ++ch) q += __ldcg(qp + (size_t)ch * NPOS);
-                sT[o] = q;
+                const float q = ordered_sum_ldcg(P.qpart + (size_t)cx.sample(j) * qstride + pos, NPOS, P.NCH);
+                sQ[o] = q;
                 const float s = sS[o], m = sM[o];
                 const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
                 const float dact = 0.5f * (1.f - m) * sg + 0.5f * (1.f + m);
@@ -225,16 +273,14 @@ sd_kernel(SdParams P) {
             for (int j = 0; j < spc; ++j) {
                 float dotl = 0.f;
                 for (int pos = tid; pos < NPOS; pos += NTH) {
-                    const float* qp = P.qpart + (size_t)cx.sample(j) * qstride + pos;
-                    float q = 0.f;
-                    for (int ch = 0; ch < P.NCH; ++ch) q += __ldcg(qp + (size_t)ch * NPOS);
-                    sT[j * NPOS + pos] = q;
+                    const float q = ordered_sum_ldcg(P.qpart + (size_t)cx.sample(j) * qstride + pos, NPOS, P.NCH);
+                    sQ[j * NPOS + pos] = q;
                     dotl += sM[j * NPOS + pos] * q;
                 }
                 const float dot = block_sum(dotl, s_red);
                 float gh = 0.f;
                 for (int pos = tid; pos < NPOS; pos += NTH) {
-                    const float q = sT[j * NPOS + pos], sm = sM[j * NPOS + pos];
+                    const float q = sQ[j * NPOS + pos], sm = sM[j * NPOS + pos];
                     gh += q * (sm * q - sm * dot);
                 }
                 gh = block_sum(gh, s_red);
@@ -242,22 +288,24 @@ sd_kernel(SdParams P) {
             }
         }
         if (chunk == 0 && tid == 0) P.hpart[group] = hl;
+        SD_STAMP(tb + 7);
         grid_barrier(P.barrier, epoch);
+        SD_STAMP(tb + 8);
 
         // ---- step length and update --------------------------------------------------------------------------------
         if (tid == 0) {
-            float gn = 0.f, hn = 0.f;
-            for (int ch = 0; ch < P.NCH; ++ch) gn += __ldcg(P.gnorm + ch);
-            for (int g = 0; g < P.NG; ++g) hn += __ldcg(P.hpart + g);
+            const float gn = ordered_sum_ldcg(P.gnorm, 1, P.NCH);
+            const float hn = ordered_sum_ldcg(P.hpart, 1, P.NG);
             const float den = fmaxf(hn + (reg + P.alpha_eps) * gn, 1e-8f);
             s_scal[0] = P.step_length * (gn / den);
         }
         __syncthreads();
         const float sa = s_scal[0];
-        for (int o = tid; o < spc * NPOS; o += NTH) sS[o] -= sa * sT[o];
+        for (int o = tid; o < spc * NPOS; o += NTH) sS[o] -= sa * sQ[o];
         for (int o = tid; o < cchunk * 16; o += NTH) {
-            const float w = wv[o] - sa * gv[o];
-            wv[o] = w;
+            const int vi = (o >> 4) * VS + (o & 15);
+            const float w = wv[vi] - sa * gv[vi];
+            wv[vi] = w;
             if (group == 0 && P.iterates_out)
                 P.iterates_out[((size_t)(it + 1) * P.C + chunk * cchunk) * 16 + o] = w;
         }
@@ -265,28 +313,37 @@ sd_kernel(SdParams P) {
     }
 
     // ---- epilogue -------------------------------------------------------------------------------------------------------
+    K::template wait_group<0>();
     if (group == 0)
-        for (int o = tid; o < cchunk * 16; o += NTH) P.w_out[(size_t)chunk * cchunk * 16 + o] = wv[o];
+        for (int o = tid; o < cchunk * 16; o += NTH) P.w_out[(size_t)chunk * cchunk * 16 + o] = wv[(o >> 4) * VS + (o & 15)];
     if (P.losses_out) {
         grid_barrier(P.barrier, epoch);
         if (blockIdx.x == 0 && tid <= P.num_iter) {
-            float l = 0.f;
-            for (int g = 0; g < P.NG; ++g) l += __ldcg(P.lossr + tid * P.NG + g);
-            float lw = 0.f;
-            for (int ch = 0; ch < P.NCH; ++ch) lw += __ldcg(P.lossw + tid * P.NCH + ch);
+            const float l = ordered_sum_ldcg(P.lossr + tid * P.NG, 1, P.NG);
+            const float lw = ordered_sum_ldcg(P.lossw + tid * P.NCH, 1, P.NCH);
             P.losses_out[tid] = l + reg * lw;
         }
     }
 }
 
+template <int FS, int NST, int MODE>
+static int launch_sd_nst(const SdParams& P, size_t smem, cudaStream_t st) {
+    using K = Corr2<FS>;
+    auto kern = sd_kernel<FS, NST, MODE>;
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* args[] = {(void*)&P};
+    B200_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(P.NCH * P.NG), dim3(K::NCONS), args, smem, st));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
 template <int FS, int MODE>
 static int launch_sd(SdParams P, cudaStream_t st) {
-    constexpr int SLOTS = CorrSlots<FS>::value;
-    using K = CorrCta<FS, SLOTS>;
-    using G = CorrGeom<FS>;
+    using K = Corr2<FS>;
+    constexpr int SLOTS = K::SLOTS;
     int passes = 0;
     for (int p = 4; p >= 1; p >>= 1) if (P.C % (SLOTS * p) == 0) { passes = p; break; }
-    B200_REQUIRE(passes > 0, "sd optimizer: C=%d must be a multiple of %d for feature size %d", P.C, SLOTS, FS);
+    B200_REQUIRE(passes > 0, "sd optimizer: C=%d must be a multiple of %d", P.C, SLOTS);
     const int sms = device_sm_count();
     int NCH = P.C / (SLOTS * passes);
     // keep the grid within one wave (cooperative launch) but use as many SMs as possible
@@ -295,32 +352,34 @@ static int launch_sd(SdParams P, cudaStream_t st) {
     int NG = sms / NCH; if (NG > P.n) NG = P.n; if (NG < 1) NG = 1;
     const int spc = (P.n + NG - 1) / NG;
     B200_REQUIRE(spc <= SD_SPC_MAX, "sd optimizer: n=%d samples need %d samples per CTA (max %d)", P.n, spc, SD_SPC_MAX);
-    B200_REQUIRE(P.num_iter + 1 <= K::NTHREADS, "sd optimizer: num_iter=%d too large", P.num_iter);
-    P.passes = passes; P.NCH = NCH; P.NG = NG;
+    B200_REQUIRE(P.num_iter + 1 <= K::NCONS, "sd optimizer: num_iter=%d too large", P.num_iter);
+    P.passes = passes; P.NCH = NCH; P.NG = NG; P.spc_max = spc;
+    { const char* v = getenv("B200TRK_SD_DBG"); P.dbg_mode = v ? atoi(v) : 0; }
+    P.trace = getenv("B200TRK_SD_TRACE") ? (unsigned long long*)workspace(1024, 3) : nullptr;
 
-    const size_t n_gpart = (size_t)NG * P.C * 16, n_qpart = (size_t)P.n * NCH * G::NPOS;
+    const size_t n_gpart = (size_t)NG * P.C * 16, n_qpart = (size_t)P.n * NCH * K::NPOS;
     const size_t n_loss = (size_t)(P.num_iter + 1) * (NG + NCH);
-    const size_t total = (n_gpart + n_qpart + NG + NCH + n_loss + 64) * sizeof(float) + 256;
+    const size_t total = (n_gpart + n_qpart + NG + NCH + n_loss + 64) * sizeof(float) + 1024;
     char* ws = (char*)workspace(total, 2);
     if (!ws) return 3;
     P.barrier = (unsigned*)ws;
-    float* f = (float*)(ws + 256);
+    float* f = (float*)(ws + 1024);
     P.gpart = f; f += n_gpart;
     P.qpart = f; f += n_qpart;
     P.hpart = f; f += NG;
     P.gnorm = f; f += NCH;
     P.lossr = f; f += (size_t)(P.num_iter + 1) * NG;
     P.lossw = f;
-    B200_CHECK_CUDA(cudaMemsetAsync(P.barrier, 0, 256, st));
+    B200_CHECK_CUDA(cudaMemsetAsync(P.barrier, 0, 1024, st));
 
     const int cchunk = passes * SLOTS;
-    const size_t smem = (size_t)(K::PLANES_FLOATS + K::RED_FLOATS + 2 * cchunk * 16 + 5 * SD_SPC_MAX * G::NPOS) * sizeof(float);
-    auto kern = sd_kernel<FS, SLOTS, MODE>;
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    void* args[] = {(void*)&P};
-    B200_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(NCH * NG), dim3(K::NTHREADS), args, smem, st));
-    g_launch_count.fetch_add(1, std::memory_order_relaxed);
-    return 0;
+    const size_t fixed = (size_t)(K::NT * SLOTS * K::RED_STRIDE + 2 * cchunk * K::VEC_STRIDE + spc * (5 * K::NPOS + K::PMAP)) * sizeof(float);
+    const size_t limit = 227 * 1024 - 512;
+    const size_t item = (size_t)K::ITEM_FLOATS * sizeof(float);
+    if (fixed + 4 * item <= limit) return launch_sd_nst<FS, 4, MODE>(P, fixed + 4 * item, st);
+    if (fixed + 3 * item <= limit) return launch_sd_nst<FS, 3, MODE>(P, fixed + 3 * item, st);
+    B200_REQUIRE(fixed + 2 * item <= limit, "sd optimizer: %d samples per CTA do not fit in shared memory", spc);
+    return launch_sd_nst<FS, 2, MODE>(P, fixed + 2 * item, st);
 }
 
 static int check_common(const char* who, const float* w, float* wo, const float* feat, const float* bb, int n, int C,
