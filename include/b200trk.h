@@ -99,6 +99,18 @@ int b200trk_prdimp_sd_newton(const float* weights, float* weights_out, const flo
                              int normalize_label, float label_shrink, float uni_weight,
                              float* iterates_out, float* losses_out, b200trk_stream_t stream);
 
+/* ConjugateGradient.run(num_iter) on ConvProblem -- the per-frame ATOM filter update: pytracking/libs/optimization.py:227-275
+ * (+ run_CG :72-163), problem pytracking/tracker/atom/optim.py:71-99, wired at pytracking/tracker/atom/atom.py:189-217,285-288
+ * (direction_forget_factor = 0, i.e. the CG state is reset every run; M1 = M2 = identity).
+ *   filter [1,C,k,k] (k = 4) current filter; filter_out receives filter + delta (may alias filter)
+ *   feat [n,C,H,W] projected sample memory, y [n,1,H,W] labels, sample_weight [n] (zero for unused slots)
+ *   filter_reg: the scalar params.filter_reg; fletcher_reeves: 0 = Polak-Ribiere (ATOM default), 1 = Fletcher-Reeves
+ *   activation: response activation phi_2: 0 none, 1 relu, 2 elu, 3 mlu(act_param)  (atom.py:455-468)               */
+int b200trk_atom_cg_filter(const float* filter, float* filter_out, const float* feat, const float* y,
+                           const float* sample_weight, int n, int C, int H, int W, int k, int num_iter,
+                           float filter_reg, int fletcher_reeves, int activation, float act_param,
+                           b200trk_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Stage 1 -- backbone + classification head
  * ---------------------------------------------------------------------------------------------- */

@@ -1,0 +1,122 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (torch-CPU fp32) of the ATOM rows of the hot path.
+
+Same rules as oracle/dimp_oracle.py: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import it.
+Parity status: PINNED -- `oracle/gen_golden.py` (gen_atom_cg, gen_fourier) runs the unmodified reference classes
+(`ConvProblem` + `ConjugateGradient`, `pytracking/libs/fourier.py`) and commits their outputs; tests/test_oracle_golden.py
+checks the functions below against them.
+
+The reference obtains J p and J^T u by double backward through `operation.conv2d` (optimization.py:251,279-280);
+here they are written out explicitly.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------------------------
+# S2.2 operation.conv2d(mode='same') / conv1x1
+# ----------------------------------------------------------------------------------------------
+def conv_same(x, w):
+    """pytracking/libs/operation.py:5-32 with mode='same': pad k//2, drop the last row/col for even kernels."""
+    kh, kw = w.shape[-2:]
+    out = F.conv2d(x, w, padding=(kh // 2, kw // 2))
+    if kh % 2 == 0:
+        out = out[:, :, :-1, :]
+    if kw % 2 == 0:
+        out = out[:, :, :, :-1]
+    return out
+
+
+def conv_same_adjoint_filter(x, u, k):
+    """Adjoint of w -> conv_same(x, w) for a single-output-channel filter: g[c,a,b] = sum_{i,y,x'} u[i,y,x'] xpad[i,c,y+a,x'+b]."""
+    p = k // 2
+    xp = F.pad(x, (p, p, p, p))
+    win = xp.unfold(2, k, 1).unfold(3, k, 1)                 # [n,c,H+1,W+1,k,k] for even k
+    win = win[:, :, :u.shape[-2], :u.shape[-1]]
+    return torch.einsum("ncyxab,nyx->cab", win.double(), u[:, 0].double()).float().unsqueeze(0)
+
+
+def conv1x1(x, P):
+    """operation.py:35-42."""
+    return torch.conv2d(x, P)
+
+
+def activation(x, kind="none", param=0.05):
+    """ATOM response / projection activations (pytracking/tracker/atom/atom.py:440-468)."""
+    if kind == "none":
+        return x
+    if kind == "relu":
+        return F.relu(x)
+    if kind == "elu":
+        return F.elu(x)
+    if kind == "mlu":
+        return F.elu(F.leaky_relu(x, 1.0 / param), param)
+    raise ValueError(kind)
+
+
+def activation_deriv(x, kind="none", param=0.05):
+    if kind == "none":
+        return torch.ones_like(x)
+    if kind == "relu":
+        return (x > 0).float()
+    if kind == "elu":
+        return torch.where(x > 0, torch.ones_like(x), torch.exp(x))
+    if kind == "mlu":
+        return torch.where(x >= 0, torch.ones_like(x), torch.exp(x / param))
+    raise ValueError(kind)
+
+
+# ----------------------------------------------------------------------------------------------
+# S3.5 ConjugateGradient.run on ConvProblem (the per-frame ATOM filter update)
+# ----------------------------------------------------------------------------------------------
+def atom_cg_filter(w, feat, y, sw, filter_reg, num_iter, act="mlu", act_param=0.05, fletcher_reeves=False):
+    """ConjugateGradient.run(num_iter) (pytracking/libs/optimization.py:227-275, run_CG :72-163) on
+    ConvProblem (pytracking/tracker/atom/optim.py:71-99), direction_forget_factor = 0 (state reset every run).
+    w [1,C,k,k], feat [n,C,H,W], y [n,1,H,W], sw [n]. Returns (w_new, delta, rho_trace)."""
+    k = w.shape[-1]
+    s = conv_same(feat, w)
+    a, d = activation(s, act, act_param), activation_deriv(s, act, act_param)
+    swv = sw.view(-1, 1, 1, 1)
+    # b = -J^T f0,  f0 = [sqrt(sw) (phi(s) - y), sqrt(reg) w],  J^T u = A^T(sqrt(sw) phi' u_data) + sqrt(reg) u_reg
+    b = -(conv_same_adjoint_filter(feat, swv * d * (a - y), k) + filter_reg * w)
+    D = swv * d * d
+
+    def A(p):
+        return conv_same_adjoint_filter(feat, D * conv_same(feat, p), k) + filter_reg * p
+
+    def ip(u, v):
+        return (u.double() * v.double()).sum().float()
+
+    r = b.clone()
+    x = None
+    p = None
+    rho = torch.ones(())
+    r_prev = None
+    trace = []
+    for ii in range(num_iter):
+        z = r
+        rho1 = rho
+        rho = ip(r, z)
+        trace.append(float(rho))
+        if float(rho) == 0.0:
+            break
+        if p is None:
+            p = z.clone()
+        else:
+            if fletcher_reeves:
+                beta = rho / rho1
+            else:
+                beta = (rho - ip(r_prev, z)) / rho1
+            beta = beta.clamp(0)
+            p = z + p * beta
+        q = A(p)
+        alpha = rho / ip(p, q)
+        if not fletcher_reeves:
+            r_prev = r.clone()
+        x = p * alpha if x is None else x + p * alpha
+        if ii < num_iter - 1:
+            r = r - q * alpha
+    if x is None:
+        x = torch.zeros_like(w)
+    return w + x, x, trace

@@ -170,6 +170,40 @@ GENS = {"corr": gen_corr, "labels": gen_labels, "dimp_sd": gen_dimp_sd, "prdimp_
         "backbone": gen_backbone}
 
 
+def gen_atom_cg():
+    """ConjugateGradient.run on ConvProblem exactly as ATOM wires it (pytracking/tracker/atom/atom.py:189-217)."""
+    from pytracking import TensorList
+    from pytracking.libs.optimization import ConjugateGradient
+    from pytracking.tracker.atom.optim import ConvProblem
+    from pytracking_b200 import synth
+    import torch.nn.functional as F
+    out = {}
+    cfgs = {"n12_c16_pr_mlu": (12, 16, 12, 5, False, "mlu", 51), "n40_c64_pr_mlu": (40, 64, 25, 5, False, "mlu", 52),
+            "n9_c32_fr_none": (9, 32, 9, 4, True, "none", 53), "n20_c64_pr_relu": (20, 64, 20, 3, False, "relu", 54)}
+    for tag, (n, c, nf, it, fr, act, seed) in cfgs.items():
+        x, y, sw = synth.make_atom_memory(seed, n, c, 18, 18, n_filled=nf)
+        g = torch.Generator().manual_seed(seed + 100)
+        w0 = torch.randn(1, c, 4, 4, generator=g) * 0.02
+        if act == "mlu":
+            fn = lambda t: F.elu(F.leaky_relu(t, 1 / 0.05), 0.05)
+        elif act == "relu":
+            fn = torch.nn.ReLU(inplace=False)
+        else:
+            fn = lambda t: t
+        filt = TensorList([w0.clone()])
+        prob = ConvProblem(TensorList([x]), TensorList([y]), TensorList([0.1]), TensorList([sw]), fn)
+        opt = ConjugateGradient(prob, filt, fletcher_reeves=fr, direction_forget_factor=0, debug=False)
+        opt.run(it)
+        out.update({tag + "_w0": _np(w0), tag + "_w": _np(filt[0]).copy(), tag + "_iters": np.array(it)})
+        # a second run from the updated filter (state is reset every run when the forget factor is 0)
+        opt.run(it)
+        out[tag + "_w2"] = _np(filt[0])
+    np.savez_compressed(os.path.join(GOLDEN, "atom_cg.npz"), **out)
+
+
+GENS["atom_cg"] = gen_atom_cg
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)

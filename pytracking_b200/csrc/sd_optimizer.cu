@@ -53,19 +53,6 @@ __device__ __forceinline__ float lut_lerp(const float* lut, int nb, float rho) {
     return lut[b] * (1.f - f) + lut[b + 1] * f;
 }
 
-// sum_{k<count} p[k*stride] in index order with 8 loads in flight (L2 latency is paid once per batch, not per term)
-__device__ __forceinline__ float ordered_sum_ldcg(const float* p, size_t stride, int count) {
-    float s = 0.f;
-    for (int k0 = 0; k0 < count; k0 += 8) {
-        float v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = (k0 + u < count) ? __ldcg(p + (size_t)(k0 + u) * stride) : 0.f;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) s += v[u];
-    }
-    return s;
-}
-
 template <int FS, int NST, int MODE>
 __global__ void __launch_bounds__(Corr2<FS>::NCONS, 1)
 sd_kernel(SdParams P) {

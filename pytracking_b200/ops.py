@@ -110,6 +110,24 @@ def prdimp_sd_newton(weights, feat, bb, sample_weight, num_iter, gauss_sigma, st
     return wout, its, losses
 
 
+ATOM_ACTIVATIONS = {"none": 0, "relu": 1, "elu": 2, "mlu": 3}
+
+
+def atom_cg_filter(filt, feat, y, sample_weight, filter_reg, num_iter, activation="mlu", act_param=0.05,
+                   fletcher_reeves=False, out=None):
+    """ConjugateGradient.run(num_iter) on ConvProblem (ATOM online filter update). Returns the updated filter."""
+    filt, feat, y, sample_weight = _dev(filt, "filter"), _dev(feat, "feat"), _dev(y, "y"), _dev(sample_weight, "sample_weight")
+    n, c, h, w = feat.shape
+    k = filt.shape[-1]
+    if y.numel() != n * h * w or sample_weight.numel() != n:
+        raise RuntimeError("b200trk.atom_cg_filter: label / weight shapes do not match the sample memory")
+    wout = out if out is not None else torch.empty_like(filt)
+    _lib.check(_lib.lib().b200trk_atom_cg_filter(_p(filt), _p(wout), _p(feat), _p(y), _p(sample_weight), n, c, h, w, k,
+                                                 int(num_iter), float(filter_reg), 1 if fletcher_reeves else 0,
+                                                 ATOM_ACTIVATIONS[activation], float(act_param), _stream()), "atom_cg_filter")
+    return wout
+
+
 def prroi_pool_forward(features, rois, ph, pw, scale):
     features, rois = _dev(features, "features"), _dev(rois, "rois")
     b, c, h, w = features.shape

@@ -172,3 +172,25 @@ def make_sequence(q, num_frames=200, height=480, width=640):
         im[y0:y0 + 60, x0:x0 + 80, :] = np.clip(base_col + tex, 0, 255)
         frames.append(im.astype(np.uint8))
     return frames, [300.0, 200.0, 80.0, 60.0]
+
+
+def make_atom_memory(seed, n, c=64, h=18, w=18, n_filled=None, sigma=1.5):
+    """ATOM sample memory as `ATOM.init_memory`/`update_memory` keep it (pytracking/tracker/atom/atom.py:561-600):
+    features [n,c,h,w] (p-norm normalised, featurebase.py:105-108 -> unit mean square), Gaussian labels
+    y [n,1,h,w] (`dcf.label_function_spatial`, pytracking/libs/dcf.py:56-59, centre jittered per sample) and
+    sample weights [n] (zero for unfilled slots, summing to one)."""
+    g = _gen(seed)
+    x = torch.randn(n, c, h, w, generator=g)
+    x = torch.nn.functional.avg_pool2d(x, 3, stride=1, padding=1) + 0.3 * x
+    x = x / torch.sqrt((x * x).reshape(n, -1).mean(1) + 1e-10).reshape(n, 1, 1, 1)
+    n_filled = n if n_filled is None else n_filled
+    ctr = (torch.rand(n, 2, generator=g) * 2 - 1) * 3.0
+    k0 = torch.arange(h, dtype=torch.float32).view(1, -1, 1) - (h - 1) / 2
+    k1 = torch.arange(w, dtype=torch.float32).view(1, 1, -1) - (w - 1) / 2
+    y = torch.exp(-0.5 / sigma ** 2 * (k0 - ctr[:, 0].view(-1, 1, 1)) ** 2) * torch.exp(-0.5 / sigma ** 2 * (k1 - ctr[:, 1].view(-1, 1, 1)) ** 2)
+    sw = torch.rand(n, generator=g) + 0.2
+    sw[n_filled:] = 0
+    sw = sw / sw.sum()
+    x[n_filled:] = 0
+    y[n_filled:] = 0
+    return x.contiguous(), y.unsqueeze(1).contiguous(), sw.contiguous()

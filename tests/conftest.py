@@ -8,7 +8,25 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def _usable_cores():
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return n
+
+
 def pytest_configure(config):
+    # the oracle is torch-CPU code made of many small ops: it is far slower with one thread per hardware thread of a
+    # large host (the GPU boxes expose 128) than with a modest pool
+    try:
+        import torch
+        torch.set_num_threads(max(1, min(16, _usable_cores())))
+    except Exception:
+        pass
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 

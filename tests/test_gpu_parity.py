@@ -162,3 +162,40 @@ def test_prroi_known_answer(ops):
     ref = F.avg_pool2d(feat, kernel_size=2, stride=1)
     assert torch.allclose(out[0], ref[0, :, :7, :7], atol=1e-6)
     assert torch.allclose(out[1], ref[1, :, 7:14, 7:14], atol=1e-6)
+
+
+ATOM_CG_CASES = {"n12_c16_pr_mlu": (12, 16, 12, 5, False, "mlu", 51), "n40_c64_pr_mlu": (40, 64, 25, 5, False, "mlu", 52),
+                 "n9_c32_fr_none": (9, 32, 9, 4, True, "none", 53), "n20_c64_pr_relu": (20, 64, 20, 3, False, "relu", 54)}
+
+
+@pytest.mark.parametrize("tag", sorted(ATOM_CG_CASES))
+def test_atom_cg_golden(golden_dir, ops, tag):
+    """ATOM ConjugateGradient.run on ConvProblem against the outputs of the reference classes (two consecutive runs)."""
+    g = np.load(os.path.join(golden_dir, "atom_cg.npz"))
+    n, c, nf, it, fr, act, seed = ATOM_CG_CASES[tag]
+    x, y, sw = synth.make_atom_memory(seed, n, c, 18, 18, n_filled=nf)
+    x, y, sw = x.cuda(), y.cuda(), sw.cuda()
+    w1 = ops.atom_cg_filter(torch.from_numpy(g[tag + "_w0"]).cuda(), x, y, sw, 0.1, it, act, 0.05, fr)
+    assert _rel(w1, g[tag + "_w"]) < 1e-4
+    w2 = ops.atom_cg_filter(w1, x, y, sw, 0.1, it, act, 0.05, fr)
+    assert _rel(w2, g[tag + "_w2"]) < 1e-4
+    w1b = ops.atom_cg_filter(torch.from_numpy(g[tag + "_w0"]).cuda(), x, y, sw, 0.1, it, act, 0.05, fr)
+    assert torch.equal(w1, w1b)                      # fixed summation order: bitwise reproducible
+
+
+def test_atom_cg_full_size(ops):
+    """BASELINE size (ATOM memory 250 x 64 x 18 x 18, 5 PR-CG iterations, mlu 0.05): equals the oracle run on the filled
+    slots (zero-weight slots contribute nothing), zero iterations is the identity, and the GN objective decreases."""
+    from oracle import atom_oracle as A
+    x, y, sw = synth.make_atom_memory(77, 250, 64, 18, 18, n_filled=24)
+    w0 = torch.randn(1, 64, 4, 4, generator=torch.Generator().manual_seed(5)) * 0.02
+    w = ops.atom_cg_filter(w0.cuda(), x.cuda(), y.cuda(), sw.cuda(), 0.1, 5, "mlu", 0.05, False)
+    w_ref, _, _ = A.atom_cg_filter(w0, x[:24], y[:24], sw[:24], 0.1, 5, "mlu", 0.05, False)
+    assert _rel(w, w_ref) < 1e-4
+    assert torch.equal(ops.atom_cg_filter(w0.cuda(), x.cuda(), y.cuda(), sw.cuda(), 0.1, 0).cpu(), w0)
+
+    def loss(wt):
+        s = A.conv_same(x[:24], wt)
+        r = sw[:24].view(-1, 1, 1, 1) * (A.activation(s, "mlu", 0.05) - y[:24]) ** 2
+        return float(r.sum() + 0.1 * (wt ** 2).sum())
+    assert loss(w.cpu()) < loss(w0)

@@ -109,3 +109,34 @@ def test_conv_formulation_matches_explicit():
     w1 = O.dimp_sd_gn_conv(w, feat, bb, None, p, 3)
     w2, _, _ = O.dimp_sd_gn(w, feat, bb, None, p, 3, compute_losses=False)
     assert _rel(w1, w2) < 1e-4
+
+
+ATOM_CG_CASES = {"n12_c16_pr_mlu": (12, 16, 12, 5, False, "mlu", 51), "n40_c64_pr_mlu": (40, 64, 25, 5, False, "mlu", 52),
+                 "n9_c32_fr_none": (9, 32, 9, 4, True, "none", 53), "n20_c64_pr_relu": (20, 64, 20, 3, False, "relu", 54)}
+
+
+@pytest.mark.parametrize("tag", sorted(ATOM_CG_CASES))
+def test_atom_cg_filter(golden_dir, tag):
+    """ATOM ConjugateGradient.run on ConvProblem (reference classes, oracle/gen_golden.py:gen_atom_cg)."""
+    from oracle import atom_oracle as A
+    g = np.load(os.path.join(golden_dir, "atom_cg.npz"))
+    n, c, nf, it, fr, act, seed = ATOM_CG_CASES[tag]
+    x, y, sw = synth.make_atom_memory(seed, n, c, 18, 18, n_filled=nf)
+    w0 = torch.from_numpy(g[tag + "_w0"])
+    w1, _, _ = A.atom_cg_filter(w0, x, y, sw, 0.1, it, act, 0.05, fr)
+    assert _rel(w1, g[tag + "_w"]) < 2e-5
+    w2, _, _ = A.atom_cg_filter(w1, x, y, sw, 0.1, it, act, 0.05, fr)
+    assert _rel(w2, g[tag + "_w2"]) < 5e-5
+
+
+def test_atom_conv_same_adjoint():
+    from oracle import atom_oracle as A
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 8, 18, 18, generator=g)
+    w = torch.randn(1, 8, 4, 4, generator=g)
+    u = torch.randn(3, 1, 18, 18, generator=g)
+    lhs = float((A.conv_same(x, w).double() * u.double()).sum())
+    rhs = float((w.double() * A.conv_same_adjoint_filter(x, u, 4).double()).sum())
+    assert abs(lhs - rhs) < 1e-4 * max(1.0, abs(lhs))
+    # conv_same == apply_filter with the last row / column dropped
+    assert _rel(A.conv_same(x, w), O.apply_filter(x, w)[:, :, :18, :18]) < 1e-5
