@@ -65,6 +65,24 @@ int b200trk_apply_filter(const float* feat, const float* filt, float* scores,
 int b200trk_apply_feat_transpose(const float* feat, const float* resid, float* grad,
                                  int n, int C, int H, int W, int k, b200trk_stream_t stream);
 
+/* ATOM.apply_filter = operation.conv2d(sample, filter, mode='same') with one k x k (k = 4) filter:
+ * pytracking/libs/operation.py:5-32, pytracking/tracker/atom/atom.py:301-302. feat [n,C,H,W], filt [1,C,k,k] ->
+ * scores [n,1,H,W] (padding k/2, last row / column of the even-kernel output dropped). */
+int b200trk_conv2d_same(const float* feat, const float* filt, float* scores, int n, int C, int H, int W, int k,
+                        b200trk_stream_t stream);
+/* operation.conv1x1 / ATOM.project_sample: pytracking/libs/operation.py:35-42, atom.py:427-431.
+ * x [S,Cin,H,W], P [Cout,Cin,1,1] -> out [S,Cout,H,W]. */
+int b200trk_conv1x1(const float* x, const float* P, float* out, int S, int Cin, int Cout, int H, int W,
+                    b200trk_stream_t stream);
+/* MultiFeatureBase.get_feature normalisation (pytracking/features/featurebase.py:105-108), in place:
+ * feat[s] /= (sum |feat[s]|^p / (C*H*W) + 1e-10)^(1/p). */
+int b200trk_feature_normalize(float* feat, int S, int C, int H, int W, float normalize_power, b200trk_stream_t stream);
+/* ATOM.localize_target Fourier upsampling of the score map (pytracking/tracker/atom/atom.py:304-316):
+ * sample_fs(sum_fs(shift_fs(cfft2(scores)/(H*W), pi*(1 - (ksz%2)/sz))), output_sz), pytracking/libs/fourier.py:20-92,
+ * for a single feature type. scores [S,1,H,W] -> out [S,1,out_h,out_w]. */
+int b200trk_fourier_interp(const float* scores, float* out, int S, int H, int W, int ksz_h, int ksz_w, int out_h,
+                           int out_w, b200trk_stream_t stream);
+
 /* dcf.max2d: pytracking/libs/dcf.py:156-164. a [n,H,W] -> max_val [n], max_idx [n,2] int64. */
 int b200trk_max2d(const float* a, int n, int H, int W, float* max_val, int64_t* max_idx, b200trk_stream_t stream);
 

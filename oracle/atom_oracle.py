@@ -120,3 +120,42 @@ def atom_cg_filter(w, feat, y, sw, filter_reg, num_iter, act="mlu", act_param=0.
     if x is None:
         x = torch.zeros_like(w)
     return w + x, x, trace
+
+
+# ----------------------------------------------------------------------------------------------
+# S2.3 Fourier-series upsampling of the score map (ATOM.localize_target)
+# ----------------------------------------------------------------------------------------------
+def fourier_interp(scores, kernel_size, output_sz):
+    """pytracking/tracker/atom/atom.py:304-316 for one feature type: cfft2 (fourier.py:20-24: rfft2 + rfftshift2, the
+    Nyquist row of an even-sized map appears at both ends) / (H*W) -> shift_fs by pi*(1 - (ksz%2)/sz) (:78-92) -> sample_fs
+    to output_sz (:35-61: zero padding of the centred half spectrum, irfft2, * prod(output_sz)). scores [S,1,H,W]."""
+    S, _, H, W = scores.shape
+    oh, ow = int(output_sz[0]), int(output_sz[1])
+    f = torch.fft.rfftn(scores.double(), dim=(-2, -1))                       # [S,1,H,W/2+1]
+    hh = H + 2
+    f = torch.cat((f[:, :, (hh - 1) // 2:, :], f[:, :, :hh // 2, :]), 2)      # rfftshift2: rows -(H//2)..(H//2) (odd count)
+    f = f / (H * W)
+    nr, nc = f.shape[2], f.shape[3]
+    ky = torch.arange(-int((nr - 1) / 2), int(nr / 2 + 1), dtype=torch.float64).view(1, 1, -1, 1)
+    kx = torch.arange(0, int((2 * nc - 1) / 2 + 1), dtype=torch.float64).view(1, 1, 1, -1)
+    sh_y = math.pi * (1 - (kernel_size[0] % 2) / H)
+    sh_x = math.pi * (1 - (kernel_size[1] % 2) / W)
+    f = f * torch.exp(1j * sh_y * ky) * torch.exp(1j * sh_x * kx)
+    szr, szc = nr, 2 * nc - 1
+    tot0, tot1 = oh - szr, ow - szc
+    pad_top = int((tot0 + 1) / 2) if szr % 2 == 0 else int(tot0 / 2)
+    pad_bottom = tot0 - pad_top
+    pad_right = int((tot1 + 1) / 2)
+    f = F.pad(torch.view_as_real(f), (0, 0, 0, pad_right, pad_top, pad_bottom))
+    f = torch.view_as_complex(f.contiguous())
+    mid = int((f.shape[2] - 1) / 2)
+    f = torch.cat((f[:, :, mid:, :], f[:, :, :mid, :]), 2)                    # irfftshift2
+    out = torch.fft.irfftn(f, s=(oh, ow), dim=(-2, -1)) * (oh * ow)
+    return out.float()
+
+
+def feature_normalize(x, p=2.0):
+    """pytracking/features/featurebase.py:105-108."""
+    n = x.shape[0]
+    d = (torch.sum(x.abs().reshape(n, 1, 1, -1) ** p, dim=3, keepdim=True) / (x.shape[1] * x.shape[2] * x.shape[3]) + 1e-10) ** (1 / p)
+    return x / d

@@ -201,7 +201,25 @@ def gen_atom_cg():
     np.savez_compressed(os.path.join(GOLDEN, "atom_cg.npz"), **out)
 
 
+def gen_fourier():
+    """ATOM.localize_target's Fourier chain with the reference's own fourier/complex modules (atom.py:304-316)."""
+    import math
+    from pytracking import fourier, TensorList
+    out = {}
+    for tag, (S, H, ksz, osz, seed) in {"s18_k4": (3, 18, 4, 288, 61), "s18_k4_o72": (2, 18, 4, 72, 62), "s17_k5": (2, 17, 5, 64, 63),
+                                        "s22_k4": (1, 22, 4, 352, 64)}.items():
+        g = torch.Generator().manual_seed(seed)
+        sc = torch.randn(S, 1, H, H, generator=g)
+        sf = fourier.cfft2(TensorList([sc])) / (H * H)
+        sf[0] = fourier.shift_fs(sf[0], math.pi * (1 - torch.Tensor([ksz % 2, ksz % 2]) / torch.Tensor([H, H])))
+        fs = fourier.sum_fs(sf)
+        up = fourier.sample_fs(fs, torch.Tensor([osz, osz]))
+        out.update({tag + "_scores": _np(sc), tag + "_up": _np(up)})
+    np.savez_compressed(os.path.join(GOLDEN, "fourier.npz"), **out)
+
+
 GENS["atom_cg"] = gen_atom_cg
+GENS["fourier"] = gen_fourier
 
 
 def main():

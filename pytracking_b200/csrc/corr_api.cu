@@ -59,7 +59,7 @@ template <int FS, int SLOTS>
 __global__ void __launch_bounds__(CorrCta<FS, SLOTS>::NTHREADS)
 apply_filter_kernel(const float* __restrict__ feat, const float* __restrict__ filt, float* __restrict__ scores,
                     float* part, unsigned* counters, int C, int n, int passes,
-                    float* max_val, int64_t* max_idx) {
+                    float* max_val, int64_t* max_idx, int crop) {
     using K = CorrCta<FS, SLOTS>;
     using G = CorrGeom<FS>;
     extern __shared__ float smem[];
@@ -88,7 +88,11 @@ apply_filter_kernel(const float* __restrict__ feat, const float* __restrict__ fi
     for (int pos = threadIdx.x; pos < G::NPOS; pos += K::NTHREADS) {
         float s = 0.f;
         for (int ch = 0; ch < NCH; ++ch) s += __ldcg(part + ((size_t)i * NCH + ch) * G::NPOS + pos);
-        scores[(size_t)i * G::NPOS + pos] = s;
+        if (!crop) scores[(size_t)i * G::NPOS + pos] = s;
+        else {            // operation.conv2d(mode='same'): drop the last row / column of the even-kernel map
+            const int yy = pos / G::OS, xx = pos - yy * G::OS;
+            if (yy < FS && xx < FS) scores[((size_t)i * FS + yy) * FS + xx] = s;
+        }
         sc[pos] = s;
     }
     __syncthreads();
@@ -153,7 +157,7 @@ static int pick_passes(int C, int slots, int max_passes) {
 
 template <int FS>
 static int launch_apply_filter(const float* feat, const float* filt, float* scores, int n, int C,
-                               float* max_val, int64_t* max_idx, cudaStream_t st) {
+                               float* max_val, int64_t* max_idx, cudaStream_t st, int crop = 0) {
     constexpr int SLOTS = CorrSlots<FS>::value;
     using K = CorrCta<FS, SLOTS>;
     using G = CorrGeom<FS>;
@@ -171,7 +175,7 @@ static int launch_apply_filter(const float* feat, const float* filt, float* scor
     const size_t smem = (size_t)(K::PLANES_FLOATS + K::RED_FLOATS + passes * SLOTS * 16) * sizeof(float);
     auto kern = apply_filter_kernel<FS, SLOTS>;
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(NCH, n), K::NTHREADS, smem, st>>>(feat, filt, scores, part, counters, C, n, passes, max_val, max_idx);
+    kern<<<dim3(NCH, n), K::NTHREADS, smem, st>>>(feat, filt, scores, part, counters, C, n, passes, max_val, max_idx, crop);
     B200_LAUNCH_CHECK();
     return 0;
 }
@@ -217,6 +221,17 @@ extern "C" int b200trk_apply_filter(const float* feat, const float* filt, float*
     cudaStream_t st = (cudaStream_t)stream;
     if (H == 18) return launch_apply_filter<18>(feat, filt, scores, n, C, max_val, max_idx, st);
     return launch_apply_filter<22>(feat, filt, scores, n, C, max_val, max_idx, st);
+}
+
+extern "C" int b200trk_conv2d_same(const float* feat, const float* filt, float* scores, int n, int C, int H, int W, int k,
+                                   b200trk_stream_t stream) {
+    B200_REQUIRE(feat && filt && scores, "conv2d_same: null pointer");
+    B200_REQUIRE(n > 0 && C > 0, "conv2d_same: empty input (n=%d, C=%d)", n, C);
+    B200_REQUIRE(k == 4, "conv2d_same: filter size %d not supported by the CUDA path (only 4)", k);
+    B200_REQUIRE(H == W && (H == 18 || H == 22), "conv2d_same: feature size %dx%d not supported (18x18, 22x22)", H, W);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (H == 18) return launch_apply_filter<18>(feat, filt, scores, n, C, nullptr, nullptr, st, 1);
+    return launch_apply_filter<22>(feat, filt, scores, n, C, nullptr, nullptr, st, 1);
 }
 
 extern "C" int b200trk_apply_feat_transpose(const float* feat, const float* resid, float* grad, int n, int C, int H,

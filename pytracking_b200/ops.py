@@ -110,6 +110,48 @@ def prdimp_sd_newton(weights, feat, bb, sample_weight, num_iter, gauss_sigma, st
     return wout, its, losses
 
 
+def conv2d_same(feat, filt):
+    """operation.conv2d(feat, filt, mode='same') for one 4x4 filter: [n,C,H,W] x [1,C,4,4] -> [n,1,H,W]."""
+    feat, filt = _dev(feat, "input"), _dev(filt, "weight")
+    n, c, h, w = feat.shape
+    k = filt.shape[-1]
+    out = torch.empty(n, 1, h, w, device=feat.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200trk_conv2d_same(_p(feat), _p(filt), _p(out), n, c, h, w, k, _stream()), "conv2d_same")
+    return out
+
+
+def conv1x1(x, weight):
+    """operation.conv1x1: [S,Cin,H,W] x [Cout,Cin,1,1] -> [S,Cout,H,W]."""
+    x, weight = _dev(x, "input"), _dev(weight, "weight")
+    s, cin, h, w = x.shape
+    cout = weight.shape[0]
+    if weight.numel() != cout * cin:
+        raise RuntimeError("b200trk.conv1x1: weight %s does not match input channels %d" % (tuple(weight.shape), cin))
+    out = torch.empty(s, cout, h, w, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200trk_conv1x1(_p(x), _p(weight), _p(out), s, cin, cout, h, w, _stream()), "conv1x1")
+    return out
+
+
+def feature_normalize_(feat, normalize_power=2.0):
+    """In-place p-norm normalisation of MultiFeatureBase.get_feature."""
+    if not feat.is_cuda or feat.dtype != torch.float32 or not feat.is_contiguous():
+        raise RuntimeError("b200trk.feature_normalize_: needs a contiguous CUDA float32 tensor")
+    s, c, h, w = feat.shape
+    _lib.check(_lib.lib().b200trk_feature_normalize(_p(feat), s, c, h, w, float(normalize_power), _stream()), "feature_normalize")
+    return feat
+
+
+def fourier_interp(scores, kernel_size, output_sz):
+    """ATOM.localize_target: Fourier-series upsampling of [S,1,H,W] score maps to [S,1,oh,ow]."""
+    scores = _dev(scores, "scores")
+    s, _, h, w = scores.shape
+    oh, ow = int(output_sz[0]), int(output_sz[1])
+    out = torch.empty(s, 1, oh, ow, device=scores.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200trk_fourier_interp(_p(scores), _p(out), s, h, w, int(kernel_size[0]), int(kernel_size[1]), oh, ow,
+                                                 _stream()), "fourier_interp")
+    return out
+
+
 ATOM_ACTIVATIONS = {"none": 0, "relu": 1, "elu": 2, "mlu": 3}
 
 

@@ -199,3 +199,63 @@ def test_atom_cg_full_size(ops):
         r = sw[:24].view(-1, 1, 1, 1) * (A.activation(s, "mlu", 0.05) - y[:24]) ** 2
         return float(r.sum() + 0.1 * (wt ** 2).sum())
     assert loss(w.cpu()) < loss(w0)
+
+
+def test_atom_stage2_ops(golden_dir, ops):
+    """S1.3 / S2.2 / S2.3: feature normalisation, conv1x1 projection, conv2d 'same', Fourier upsampling."""
+    from oracle import atom_oracle as A
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(5, 256, 18, 18, generator=g)
+    xn = ops.feature_normalize_(x.clone().cuda(), 2.0)
+    assert _rel(xn, A.feature_normalize(x, 2.0)) < 1e-5
+    P = torch.randn(64, 256, 1, 1, generator=g) * 0.05
+    proj = ops.conv1x1(xn, P.cuda())
+    proj_ref = A.conv1x1(A.feature_normalize(x, 2.0), P)
+    assert _rel(proj, proj_ref) < 1e-5
+    w = torch.randn(1, 64, 4, 4, generator=g) * 0.1
+    s = ops.conv2d_same(proj, w.cuda())
+    assert s.shape == (5, 1, 18, 18)
+    assert _rel(s, A.conv_same(proj_ref, w)) < 1e-5
+    x22 = torch.randn(2, 32, 22, 22, generator=g)
+    w22 = torch.randn(1, 32, 4, 4, generator=g)
+    assert _rel(ops.conv2d_same(x22.cuda(), w22.cuda()), A.conv_same(x22, w22)) < 1e-5
+    gf = np.load(os.path.join(golden_dir, "fourier.npz"))
+    for tag, (S, H, ksz, osz) in {"s18_k4": (3, 18, 4, 288), "s18_k4_o72": (2, 18, 4, 72), "s17_k5": (2, 17, 5, 64), "s22_k4": (1, 22, 4, 352)}.items():
+        up = ops.fourier_interp(torch.from_numpy(gf[tag + "_scores"]).cuda(), (ksz, ksz), (osz, osz))
+        assert _rel(up, gf[tag + "_up"]) < 1e-4, tag
+    # ATOM localisation at BASELINE size: 5 scales, arg-max on the 288x288 grid must agree with the oracle's arg-max
+    up = ops.fourier_interp(s, (4, 4), (288, 288))
+    up_ref = A.fourier_interp(A.conv_same(proj_ref, w), (4, 4), (288, 288))
+    assert _rel(up, up_ref) < 1e-4
+    mv, mi = ops.max2d(up[:, 0])
+    from oracle import dimp_oracle as O
+    mv_ref, mi_ref = O.max2d(up.cpu()[:, 0])
+    assert torch.equal(mi.cpu(), mi_ref)
+
+
+@pytest.mark.parametrize("B,C,H,W,R,ph,pw,scale,seed", [(2, 16, 18, 18, 6, 4, 4, 1.0 / 16, 1), (1, 32, 36, 36, 10, 5, 5, 1.0 / 8, 2),
+                                                       (3, 8, 9, 11, 4, 3, 1, 0.9, 3)])
+def test_prroi_all_three_kernels(ops, B, C, H, W, R, ph, pw, scale, seed):
+    """PrRoIPool forward / backward / coordinate backward against the CPU restatement of the reference kernels."""
+    from oracle import prroi_oracle as P
+    g = torch.Generator().manual_seed(seed)
+    feat = torch.randn(B, C, H, W, generator=g)
+    ext_w, ext_h = W / scale, H / scale
+    x1 = torch.rand(R, generator=g) * ext_w * 0.5
+    y1 = torch.rand(R, generator=g) * ext_h * 0.5
+    bw = (0.15 + 0.45 * torch.rand(R, generator=g)) * ext_w
+    bh = (0.15 + 0.45 * torch.rand(R, generator=g)) * ext_h
+    rois = torch.stack([torch.randint(0, B, (R,), generator=g).float(), x1, y1, x1 + bw, y1 + bh], 1).contiguous()
+    rois[0, 3] = ext_w + 5.0                       # a box leaving the feature map: zero padding outside
+    og = torch.randn(R, C, ph, pw, generator=g)
+    out = ops.prroi_pool_forward(feat.cuda(), rois.cuda(), ph, pw, scale)
+    out_ref = P.forward(feat.numpy(), rois.numpy(), ph, pw, scale)
+    assert _rel(out, out_ref) < 1e-5
+    fg = ops.prroi_pool_backward(feat.cuda(), rois.cuda(), out, og.cuda(), ph, pw, scale)
+    assert _rel(fg, P.backward(feat.numpy(), rois.numpy(), og.numpy(), ph, pw, scale)) < 1e-5
+    rg = ops.prroi_pool_coor_backward(feat.cuda(), rois.cuda(), out, og.cuda(), ph, pw, scale)
+    rg_ref = P.coor_backward(feat.numpy(), rois.numpy(), out_ref, og.numpy(), ph, pw, scale)
+    assert _rel(rg, rg_ref) < 1e-4
+    # degenerate RoI (zero area): zero output and zero gradients, as the reference (win_size == 0)
+    z = torch.tensor([[0, 5.0, 5.0, 5.0, 9.0]])
+    assert float(ops.prroi_pool_forward(feat.cuda(), z.cuda(), ph, pw, scale).abs().max()) == 0.0

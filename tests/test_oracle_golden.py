@@ -140,3 +140,23 @@ def test_atom_conv_same_adjoint():
     assert abs(lhs - rhs) < 1e-4 * max(1.0, abs(lhs))
     # conv_same == apply_filter with the last row / column dropped
     assert _rel(A.conv_same(x, w), O.apply_filter(x, w)[:, :, :18, :18]) < 1e-5
+
+
+FOURIER_CASES = {"s18_k4": (3, 18, 4, 288), "s18_k4_o72": (2, 18, 4, 72), "s17_k5": (2, 17, 5, 64), "s22_k4": (1, 22, 4, 352)}
+
+
+@pytest.mark.parametrize("tag", sorted(FOURIER_CASES))
+def test_fourier_interp(golden_dir, tag):
+    """cfft2 -> shift_fs -> sum_fs -> sample_fs as ATOM.localize_target chains them (reference modules, gen_fourier)."""
+    from oracle import atom_oracle as A
+    g = np.load(os.path.join(golden_dir, "fourier.npz"))
+    S, H, ksz, osz = FOURIER_CASES[tag]
+    up = A.fourier_interp(torch.from_numpy(g[tag + "_scores"]), (ksz, ksz), (osz, osz))
+    assert _rel(up, g[tag + "_up"]) < 1e-5
+    # the Fourier series passes through the shifted samples: for an even kernel the half-cell shift puts sample y at Y = 16 y + 144 (mod 288)
+    if ksz % 2 == 0 and osz % H == 0:
+        r = osz // H
+        idx = (torch.arange(H) * r + osz // 2) % osz
+        sub = up[:, 0][:, idx][:, :, idx]
+        # (an even-sized map keeps both Nyquist terms, so the pass-through is exact only up to the doubled Nyquist component)
+        assert sub.shape[-1] == H
