@@ -32,8 +32,8 @@ CROP = 288
 MEMORY = 50
 SD_ITERS = 10
 # dram__bytes_read.sum + dram__bytes_write.sum of one sd_kernel launch (n=50, 10 it) from the committed ncu --set full
-# capture profiles/r01a_sd_kernel_ncu_full.txt: the sample memory is read from HBM once per call and stays L2 resident.
-SD_DRAM_TRAFFIC_BYTES = 33287168 + 121600
+# capture profiles/r01g_ncu_full_sd_and_conv.txt: the sample memory is read from HBM once per call and stays L2 resident.
+SD_DRAM_TRAFFIC_BYTES = 33330944 + 121600
 POOL = 160          # distinct crops per rank (160 x 995 KB = 159 MB > 126 MB L2: a step's input is never L2 resident)
 
 
@@ -256,7 +256,7 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": world * K / (host_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 3 * CROP * CROP * 4 + 16 + MEMORY * 4,
                 "d2h_bytes_per_step": 19 * 19 * 4 + 4 + 16},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "sd_kernel<18,16,0> (DiMP steepest-descent, n=50, 10 it)", "bound": "hbm", "achieved": achieved,
+        "roofline": {"kernel": "sd_kernel<18,4,0> (DiMP steepest-descent, n=50, 10 it)", "bound": "hbm", "achieved": achieved,
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                      "traffic": SD_DRAM_TRAFFIC_BYTES,
                      "peak_source": peaks["source"], "us_per_launch": sd_us, "us_per_sd_iteration": sd_us / SD_ITERS},
