@@ -117,6 +117,25 @@ int b200trk_prdimp_sd_newton(const float* weights, float* weights_out, const flo
                              int normalize_label, float label_shrink, float uni_weight,
                              float* iterates_out, float* losses_out, b200trk_stream_t stream);
 
+/* DiMPL2SteepestDescentGN.forward: ltr/models/target_classifier/optimizer.py:211-291 (Gaussian label :201-208, hard hinge
+ * mask label > hinge_threshold, sample weight sqrt(sw) or sqrt(1/n)). Same contract as b200trk_dimp_sd_gn. */
+int b200trk_dimp_l2_sd_gn(const float* weights, float* weights_out, const float* feat, const float* bb,
+                          const float* sample_weight, int n, int C, int H, int W, int k, int num_iter,
+                          float gauss_sigma, float hinge_threshold, float feat_stride, float step_length,
+                          float reg_weight, float alpha_eps, float* iterates_out, float* losses_out,
+                          b200trk_stream_t stream);
+
+/* GNSteepestDescent.forward (ltr/models/meta/steepestdescent.py:32-105) with the LinearFilterHinge residual module
+ * (ltr/models/target_classifier/residual_modules.py:89-135), one sequence -- the online optimiser of dimpnet50_simple /
+ * SuperDiMPSimple / KeepTrack (ltr/models/tracking/dimpnet.py:233-240). The reference obtains g = J^T r and h = J g by
+ * autograd; they are explicit here.
+ *   train_label [n,1,Ho,Wo] label maps (an input of the residual module), sample_weight [n] or NULL (-> 1/n)
+ *   score_act: 0 = 'relu' (LeakyReluPar), 1 = 'bentpar' (BentIdentPar(act_param)); losses_out follows _compute_loss. */
+int b200trk_gn_sd_hinge(const float* weights, float* weights_out, const float* feat, const float* train_label,
+                        const float* sample_weight, int n, int C, int H, int W, int k, int num_iter,
+                        float filter_reg, float hinge_threshold, float activation_leak, int score_act, float act_param,
+                        float steplength_reg, float* iterates_out, float* losses_out, b200trk_stream_t stream);
+
 /* ConjugateGradient.run(num_iter) on ConvProblem -- the per-frame ATOM filter update: pytracking/libs/optimization.py:227-275
  * (+ run_CG :72-163), problem pytracking/tracker/atom/optim.py:71-99, wired at pytracking/tracker/atom/atom.py:189-217,285-288
  * (direction_forget_factor = 0, i.e. the CG state is reset every run; M1 = M2 = identity).

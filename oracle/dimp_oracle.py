@@ -201,6 +201,83 @@ def dimp_sd_gn(w, feat, bb, sample_weight, params, num_iter, min_filter_reg=1e-3
     return w, iterates, losses
 
 
+def dimp_l2_sd_gn(w, feat, bb, sample_weight, log_step_length, filter_reg, num_iter, gauss_sigma, hinge_threshold=-999.0,
+                  min_filter_reg=1e-3, alpha_eps=0.0, feat_stride=16, compute_losses=True):
+    """DiMPL2SteepestDescentGN.forward (ltr/models/target_classifier/optimizer.py:211-291), one sequence."""
+    n = feat.shape[0]
+    k = w.shape[-1]
+    out_sz = (feat.shape[-2] + (k + 1) % 2, feat.shape[-1] + (k + 1) % 2)
+    step = math.exp(float(log_step_length))
+    reg = max(float(filter_reg) ** 2, min_filter_reg ** 2)
+    off = (k % 2) / 2.0
+    center = ((bb[:, :2] + bb[:, 2:] / 2) / feat_stride).flip((1,)) - off
+    k0 = torch.arange(out_sz[0], dtype=torch.float32).view(1, -1, 1)
+    k1 = torch.arange(out_sz[1], dtype=torch.float32).view(1, 1, -1)
+    g0 = torch.exp(-1.0 / (2 * gauss_sigma ** 2) * (k0 - center[:, 0].view(-1, 1, 1)) ** 2)
+    g1 = torch.exp(-1.0 / (2 * gauss_sigma ** 2) * (k1 - center[:, 1].view(-1, 1, 1)) ** 2)
+    y = g0 * g1
+    m = (y > hinge_threshold).float()
+    y = y * m
+    sw = math.sqrt(1.0 / n) if sample_weight is None else sample_weight.sqrt().reshape(n, 1, 1)
+    iterates, losses = [w], []
+    for _ in range(num_iter):
+        s = apply_filter(feat, w)[:, 0]
+        act = m * s + (1.0 - m) * F.relu(s)
+        dact = m + (1.0 - m) * (s > 0).float()
+        r = sw * (act - y)
+        if compute_losses:
+            losses.append((r ** 2).sum() + reg * (w ** 2).sum())
+        g = apply_feat_transpose(feat, (dact * (sw * r)).unsqueeze(1), k) + reg * w
+        h = sw * (dact * apply_filter(feat, g)[:, 0])
+        a_num = (g * g).sum()
+        a_den = ((h * h).sum() + (reg + alpha_eps) * a_num).clamp(min=1e-8)
+        w = w - (step * (a_num / a_den)) * g
+        iterates.append(w)
+    if compute_losses:
+        s = apply_filter(feat, w)[:, 0]
+        act = m * s + (1.0 - m) * F.relu(s)
+        losses.append(((sw * (act - y)) ** 2).sum() + reg * (w ** 2).sum())
+    return w, iterates, losses
+
+
+def gn_sd_hinge(w, feat, train_label, sample_weight, filter_reg, num_iter, hinge_threshold=-999.0, activation_leak=0.0,
+                score_act="relu", act_param=1.0, steplength_reg=0.0, compute_losses=True):
+    """GNSteepestDescent.forward (ltr/models/meta/steepestdescent.py:32-105) over LinearFilterHinge
+    (ltr/models/target_classifier/residual_modules.py:89-135), one sequence, with g = J^T r and h = J g written out.
+    train_label [n,Ho,Wo]."""
+    n = feat.shape[0]
+    k = w.shape[-1]
+    sw = math.sqrt(1.0 / n) if sample_weight is None else sample_weight.sqrt().reshape(n, 1, 1)
+    m = ((train_label > hinge_threshold).float() + activation_leak).clamp(max=1.0)
+    y = m * train_label
+
+    def act_fn(s):
+        if score_act == "bentpar":
+            rt = torch.sqrt(s * s + 4.0 * act_param * act_param)
+            return (1.0 - m) / 2.0 * (rt - 2.0 * act_param) + (1.0 + m) / 2.0 * s, (1.0 - m) / 2.0 * (s / rt) + (1.0 + m) / 2.0
+        return (1.0 - m) / 2.0 * s.abs() + (1.0 + m) / 2.0 * s, (1.0 - m) / 2.0 * torch.sign(s) + (1.0 + m) / 2.0
+
+    numel = n * train_label.shape[-2] * train_label.shape[-1] + w.numel()
+    iterates, losses = [w], []
+    for _ in range(num_iter):
+        s = apply_filter(feat, w)[:, 0]
+        a, d = act_fn(s)
+        r = sw * (a - y)
+        if compute_losses:
+            losses.append(((r ** 2).sum() + (filter_reg * w).pow(2).sum()) / numel)
+        g = apply_feat_transpose(feat, (d * (sw * r)).unsqueeze(1), k) + filter_reg * filter_reg * w
+        h = sw * (d * apply_filter(feat, g)[:, 0])
+        gg = (g * g).sum()
+        hh = (h * h).sum() + (filter_reg * g).pow(2).sum()
+        alpha = gg / (hh + steplength_reg * gg).clamp(min=1e-8)
+        w = w - alpha * g
+        iterates.append(w)
+    if compute_losses:
+        a, _ = act_fn(apply_filter(feat, w)[:, 0])
+        losses.append((((sw * (a - y)) ** 2).sum() + (filter_reg * w).pow(2).sum()) / numel)
+    return w, iterates, losses
+
+
 # ----------------------------------------------------------------------------------------------
 # Stage 3b: PrDiMP steepest-descent Newton
 # ----------------------------------------------------------------------------------------------

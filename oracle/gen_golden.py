@@ -218,6 +218,64 @@ def gen_fourier():
     np.savez_compressed(os.path.join(GOLDEN, "fourier.npz"), **out)
 
 
+def gen_dimp_l2_sd():
+    from ltr.models.target_classifier.optimizer import DiMPL2SteepestDescentGN
+    from pytracking_b200 import synth
+    out = {}
+    for tag, (n, c, h, it, use_sw, thr, seed) in {"n8_c64": (8, 64, 18, 4, True, 0.05, 71), "n5_c32_22": (5, 32, 22, 3, False, -999.0, 72)}.items():
+        opt = DiMPL2SteepestDescentGN(num_iter=it, feat_stride=16, init_step_length=0.9, gauss_sigma=1.3, hinge_threshold=thr,
+                                      init_filter_reg=0.1, min_filter_reg=1e-3, alpha_eps=0.01)
+        opt.eval()
+        feat = synth.make_clf_features(seed, n, c, h, h)
+        bb = synth.make_boxes(seed + 1, n, center=(h * 16) / 2 - 25)
+        g = torch.Generator().manual_seed(seed + 2)
+        w0 = torch.randn(1, c, 4, 4, generator=g) * 0.05 if tag == "n8_c64" else torch.zeros(1, c, 4, 4)
+        sw = (torch.rand(n, generator=g) + 0.5) if use_sw else None
+        if sw is not None:
+            sw = sw / sw.sum()
+        with torch.no_grad():
+            wf, its, losses = opt(w0, feat.unsqueeze(1), bb.unsqueeze(1), sample_weight=None if sw is None else sw.unsqueeze(1),
+                                  num_iter=it, compute_losses=True)
+        out.update({tag + "_w0": _np(w0), tag + "_wfinal": _np(wf), tag + "_w1": _np(its[1]),
+                    tag + "_losses": np.array([float(l) for l in losses], dtype=np.float32)})
+        if sw is not None:
+            out[tag + "_sw"] = _np(sw)
+    np.savez_compressed(os.path.join(GOLDEN, "dimp_l2_sd.npz"), **out)
+
+
+def gen_gn_sd_hinge():
+    from ltr.models.meta.steepestdescent import GNSteepestDescent
+    from ltr.models.target_classifier.residual_modules import LinearFilterHinge
+    from pytracking import TensorList
+    from pytracking_b200 import synth
+    out = {}
+    for tag, (n, c, h, it, use_sw, thr, leak, act, seed) in {"relu_n6_c64": (6, 64, 18, 4, True, 0.05, 0.0, "relu", 81),
+                                                            "bent_n4_c32_22": (4, 32, 22, 3, False, 0.1, 0.1, "bentpar", 82)}.items():
+        res = LinearFilterHinge(feat_stride=16, init_filter_reg=0.1, hinge_threshold=thr, activation_leak=leak, score_act=act,
+                                act_param=0.7 if act == "bentpar" else None)
+        opt = GNSteepestDescent(residual_module=res, num_iter=it, residual_batch_dim=1, compute_losses=True, steplength_reg=0.02)
+        opt.eval()
+        feat = synth.make_clf_features(seed, n, c, h, h)
+        g = torch.Generator().manual_seed(seed + 2)
+        ctr = torch.rand(n, 2, generator=g) * 4 + (h / 2 - 2)
+        k0 = torch.arange(h + 1, dtype=torch.float32).view(1, -1, 1)
+        k1 = torch.arange(h + 1, dtype=torch.float32).view(1, 1, -1)
+        label = torch.exp(-0.5 / 1.5 ** 2 * (k0 - ctr[:, 0].view(-1, 1, 1)) ** 2) * torch.exp(-0.5 / 1.5 ** 2 * (k1 - ctr[:, 1].view(-1, 1, 1)) ** 2)
+        w0 = torch.randn(1, c, 4, 4, generator=g) * 0.05
+        sw = (torch.rand(n, generator=g) + 0.5) if use_sw else None
+        if sw is not None:
+            sw = sw / sw.sum()
+        wf, its, losses = opt(TensorList([w0.clone()]), feat=feat.unsqueeze(1), train_label=label.unsqueeze(1),
+                              sample_weight=None if sw is None else sw.reshape(n, 1, 1, 1), num_iter=it)
+        out.update({tag + "_w0": _np(w0), tag + "_label": _np(label), tag + "_wfinal": _np(wf[0]), tag + "_w1": _np(its[1][0]),
+                    tag + "_losses": np.array([float(l) for l in losses], dtype=np.float32)})
+        if sw is not None:
+            out[tag + "_sw"] = _np(sw)
+    np.savez_compressed(os.path.join(GOLDEN, "gn_sd_hinge.npz"), **out)
+
+
+GENS["gn_sd_hinge"] = gen_gn_sd_hinge
+GENS["dimp_l2_sd"] = gen_dimp_l2_sd
 GENS["atom_cg"] = gen_atom_cg
 GENS["fourier"] = gen_fourier
 

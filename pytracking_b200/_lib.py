@@ -35,6 +35,8 @@ SIGNATURES = {
     "b200trk_max2d": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP]),
     "b200trk_dimp_sd_gn": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _I, _F, _F, _F, _F, _F,
                                 _VP, _VP, _VP]),
+    "b200trk_dimp_l2_sd_gn": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _F, _F, _F, _F, _F, _F, _VP, _VP, _VP]),
+    "b200trk_gn_sd_hinge": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _F, _F, _F, _I, _F, _F, _VP, _VP, _VP]),
     "b200trk_prdimp_sd_newton": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _F, _F, _F, _F, _F, _I, _F, _F,
                                       _I, _F, _F, _VP, _VP, _VP]),
     "b200trk_atom_cg_filter": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _F, _I, _I, _F, _VP]),

@@ -551,16 +551,19 @@ static int tc_configure(b200trk_net* net, const Op& op, TcConv* tc, int S) {
     P.BN = BN;
     P.b_bytes = (uint32_t)BN * 128u;
     const uint32_t stage_bytes = 2u * TC_BM * 128u + 2u * P.b_bytes;
-    int stages = (int)((200u * 1024u) / stage_bytes);
+    const int occ = env_int("B200TRK_TC_OCC", 1);                 // CTAs per SM the shared-memory footprint is sized for
+    int stages = (int)(((occ >= 2 ? 98u : 200u) * 1024u) / stage_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (stages < 2) stages = 2;
     if (stages > P.total_kb) stages = P.total_kb < 2 ? 2 : P.total_kb;
     P.stages = stages;
     const int ctas = m_tiles * (op.Cout / BN);
     int splits = 1;
     const int max_splits = env_int("B200TRK_TC_SPLITK", 1) ? 64 : 1;
-    if (ctas < net->sms) {
-        splits = net->sms / ctas;
-        const int min_kb = 4;
+    const int slots = net->sms * (occ >= 2 ? 2 : 1);
+    if (ctas < slots) {
+        splits = slots / ctas;
+        const int min_kb = env_int("B200TRK_TC_MINKB", 4);
         if (splits > P.total_kb / min_kb) splits = P.total_kb / min_kb;
         if (splits > max_splits) splits = max_splits;
         if (splits < 1) splits = 1;

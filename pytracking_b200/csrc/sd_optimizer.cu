@@ -30,6 +30,8 @@ struct SdParams {
     // PrDiMP
     float gauss_sigma; int has_softmax_reg; float softmax_reg; float label_threshold; int normalize_label;
     float label_shrink; float uni_weight;
+    // GNSteepestDescent + LinearFilterHinge (MODE 3)
+    const float* label_in; float act_leak; int act_kind; float act_b; float loss_scale;
     // common
     float inv_feat_stride, step_length, reg_weight, alpha_eps;
     float* iterates_out; float* losses_out;
@@ -108,6 +110,28 @@ sd_kernel(SdParams P) {
                 sM[j * NPOS + pos] = 1.f / (1.f + expf(-lut_lerp(P.mask_lut, P.num_bins, rho)));
                 sV[j * NPOS + pos] = sqsw * lut_lerp(P.spatial_lut, P.num_bins, rho);
             }
+        } else if (MODE == 3) {
+            // LinearFilterHinge.forward (residual_modules.py:112-135): the label maps are an input of the residual module
+            const float sqsw = sqrtf(s_sw[j]);
+            for (int pos = tid; pos < NPOS; pos += NTH) {
+                const float lab = P.label_in[(size_t)i * NPOS + pos];
+                const float m = fminf(((lab > P.label_threshold) ? 1.f : 0.f) + P.act_leak, 1.f);
+                sY[j * NPOS + pos] = m * lab;
+                sM[j * NPOS + pos] = m;
+                sV[j * NPOS + pos] = sqsw;
+            }
+        } else if (MODE == 2) {
+            // DiMPL2SteepestDescentGN (optimizer.py:201-208,236-241): Gaussian label, hard hinge mask, weight sqrt(sw)
+            const float c = -1.0f / (2.f * P.gauss_sigma * P.gauss_sigma);
+            const float sqsw = sqrtf(s_sw[j]);
+            for (int pos = tid; pos < NPOS; pos += NTH) {
+                const float d0 = (float)(pos / OS) - crow, d1 = (float)(pos % OS) - ccol;
+                const float gss = expf(c * d0 * d0) * expf(c * d1 * d1);
+                const float m = (gss > P.label_threshold) ? 1.f : 0.f;
+                sY[j * NPOS + pos] = gss * m;
+                sM[j * NPOS + pos] = m;
+                sV[j * NPOS + pos] = sqsw;
+            }
         } else {
             const float c = -1.0f / (2.f * P.gauss_sigma * P.gauss_sigma);
             const float nrm = 1.f / (2.f * 3.14159265358979323846f * P.gauss_sigma * P.gauss_sigma);
@@ -147,13 +171,23 @@ sd_kernel(SdParams P) {
         SD_STAMP(tb + 0);
         // ---- residuals from the current scores (also the loss terms of iterate `it`) -----------------------
         float lloc = 0.f;
-        if (MODE == 0) {
+        if (MODE != 1) {
             for (int o = tid; o < spc * NPOS; o += NTH) {
                 const int j = o / NPOS, pos = o - j * NPOS;
                 const float s = sS[o], m = sM[o], vh = sV[o];
-                const float act = 0.5f * (1.f - m) * fabsf(s) + 0.5f * (1.f + m) * s;
-                const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
-                const float dact = 0.5f * (1.f - m) * sg + 0.5f * (1.f + m);
+                float act, dact;
+                if (MODE == 3 && P.act_kind == 1) {      // BentIdentPar (activation.py:53-74)
+                    const float rt = sqrtf(s * s + 4.f * P.act_b * P.act_b);
+                    act = 0.5f * (1.f - m) * (rt - 2.f * P.act_b) + 0.5f * (1.f + m) * s;
+                    dact = 0.5f * (1.f - m) * (s / rt) + 0.5f * (1.f + m);
+                } else if (MODE == 0 || MODE == 3) {
+                    act = 0.5f * (1.f - m) * fabsf(s) + 0.5f * (1.f + m) * s;
+                    const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
+                    dact = 0.5f * (1.f - m) * sg + 0.5f * (1.f + m);
+                } else {            // optimizer.py:258-259: mask*s + (1-mask)*relu(s), derivative mask + (1-mask)*(s > 0)
+                    act = m * s + (1.f - m) * fmaxf(s, 0.f);
+                    dact = m + (1.f - m) * ((s > 0.f) ? 1.f : 0.f);
+                }
                 const float r = vh * (act - sY[o]);
                 lloc += r * r;
                 sT[j * PMAP + (pos / OS) * PW + (pos % OS)] = dact * (vh * r);
@@ -244,14 +278,21 @@ sd_kernel(SdParams P) {
 
         // ---- phase 3: q_i over all chunks, curvature term --------------------------------------------------------
         float hl = 0.f;
-        if (MODE == 0) {
+        if (MODE != 1) {
             for (int o = tid; o < spc * NPOS; o += NTH) {
                 const int j = o / NPOS, pos = o - j * NPOS;
                 const float q = ordered_sum_ldcg(P.qpart + (size_t)cx.sample(j) * qstride + pos, NPOS, P.NCH);
                 sQ[o] = q;
                 const float s = sS[o], m = sM[o];
-                const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
-                const float dact = 0.5f * (1.f - m) * sg + 0.5f * (1.f + m);
+                float dact;
+                if (MODE == 3 && P.act_kind == 1) {
+                    dact = 0.5f * (1.f - m) * (s / sqrtf(s * s + 4.f * P.act_b * P.act_b)) + 0.5f * (1.f + m);
+                } else if (MODE == 0 || MODE == 3) {
+                    const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
+                    dact = 0.5f * (1.f - m) * sg + 0.5f * (1.f + m);
+                } else {
+                    dact = m + (1.f - m) * ((s > 0.f) ? 1.f : 0.f);
+                }
                 const float h = sV[o] * (dact * q);
                 hl += h * h;
             }
@@ -308,7 +349,7 @@ sd_kernel(SdParams P) {
         if (blockIdx.x == 0 && tid <= P.num_iter) {
             const float l = ordered_sum_ldcg(P.lossr + tid * P.NG, 1, P.NG);
             const float lw = ordered_sum_ldcg(P.lossw + tid * P.NCH, 1, P.NCH);
-            P.losses_out[tid] = l + reg * lw;
+            P.losses_out[tid] = (MODE == 3) ? (l + reg * lw) * P.loss_scale : l + reg * lw;
         }
     }
 }
@@ -428,4 +469,47 @@ extern "C" int b200trk_prdimp_sd_newton(const float* weights, float* weights_out
     P.iterates_out = iterates_out; P.losses_out = losses_out;
     if (H == 18) return launch_sd<18, 1>(P, st);
     return launch_sd<22, 1>(P, st);
+}
+
+extern "C" int b200trk_dimp_l2_sd_gn(const float* weights, float* weights_out, const float* feat, const float* bb,
+                                     const float* sample_weight, int n, int C, int H, int W, int k, int num_iter,
+                                     float gauss_sigma, float hinge_threshold, float feat_stride, float step_length,
+                                     float reg_weight, float alpha_eps, float* iterates_out, float* losses_out,
+                                     b200trk_stream_t stream) {
+    if (int e = check_common("dimp_l2_sd_gn", weights, weights_out, feat, bb, n, C, H, W, k, num_iter)) return e;
+    B200_REQUIRE(gauss_sigma > 0.f && feat_stride > 0.f, "dimp_l2_sd_gn: gauss_sigma and feat_stride must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (iterates_out)
+        B200_CHECK_CUDA(cudaMemcpyAsync(iterates_out, weights, (size_t)C * 16 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SdParams P{};
+    P.w_in = weights; P.w_out = weights_out; P.feat = feat; P.bb = bb; P.sample_weight = sample_weight;
+    P.n = n; P.C = C; P.num_iter = num_iter;
+    P.gauss_sigma = gauss_sigma; P.label_threshold = hinge_threshold;
+    P.inv_feat_stride = 1.0f / feat_stride;
+    P.step_length = step_length; P.reg_weight = reg_weight; P.alpha_eps = alpha_eps;
+    P.iterates_out = iterates_out; P.losses_out = losses_out;
+    if (H == 18) return launch_sd<18, 2>(P, st);
+    return launch_sd<22, 2>(P, st);
+}
+
+extern "C" int b200trk_gn_sd_hinge(const float* weights, float* weights_out, const float* feat, const float* train_label,
+                                   const float* sample_weight, int n, int C, int H, int W, int k, int num_iter,
+                                   float filter_reg, float hinge_threshold, float activation_leak, int score_act, float act_param,
+                                   float steplength_reg, float* iterates_out, float* losses_out, b200trk_stream_t stream) {
+    if (int e = check_common("gn_sd_hinge", weights, weights_out, feat, train_label, n, C, H, W, k, num_iter)) return e;
+    B200_REQUIRE(score_act == 0 || score_act == 1, "gn_sd_hinge: score_act must be 0 (relu) or 1 (bentpar)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (iterates_out)
+        B200_CHECK_CUDA(cudaMemcpyAsync(iterates_out, weights, (size_t)C * 16 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SdParams P{};
+    P.w_in = weights; P.w_out = weights_out; P.feat = feat; P.bb = train_label /* unused boxes: any valid pointer */;
+    P.sample_weight = sample_weight; P.n = n; P.C = C; P.num_iter = num_iter;
+    P.label_in = train_label; P.label_threshold = hinge_threshold; P.act_leak = activation_leak; P.act_kind = score_act;
+    P.act_b = act_param;
+    P.inv_feat_stride = 1.f / 16.f;
+    P.step_length = 1.f; P.reg_weight = filter_reg * filter_reg; P.alpha_eps = steplength_reg;
+    P.loss_scale = 1.f / ((float)n * (float)((H + 1) * (W + 1)) + (float)C * 16.f);   // GNSteepestDescent._compute_loss: mean over all residual entries
+    P.iterates_out = iterates_out; P.losses_out = losses_out;
+    if (H == 18) return launch_sd<18, 3>(P, st);
+    return launch_sd<22, 3>(P, st);
 }

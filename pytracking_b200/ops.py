@@ -90,6 +90,44 @@ def dimp_sd_gn(weights, feat, bb, sample_weight, label_lut, mask_lut, spatial_lu
     return wout, its, losses
 
 
+def dimp_l2_sd_gn(weights, feat, bb, sample_weight, num_iter, gauss_sigma, hinge_threshold, step_length, reg_weight,
+                  alpha_eps=0.0, feat_stride=16.0, return_iterates=False, compute_losses=False, out=None):
+    """DiMPL2SteepestDescentGN.forward (one sequence)."""
+    weights, feat, bb = _dev(weights, "weights"), _dev(feat, "feat"), _dev(bb, "bb")
+    n, c, h, w = feat.shape
+    k = weights.shape[-1]
+    if sample_weight is not None:
+        sample_weight = _dev(sample_weight, "sample_weight")
+    wout = out if out is not None else torch.empty_like(weights)
+    its = torch.empty(num_iter + 1, c, k, k, device=feat.device, dtype=torch.float32) if return_iterates else None
+    losses = torch.empty(num_iter + 1, device=feat.device, dtype=torch.float32) if compute_losses else None
+    _lib.check(_lib.lib().b200trk_dimp_l2_sd_gn(
+        _p(weights), _p(wout), _p(feat), _p(bb), _p(sample_weight), n, c, h, w, k, int(num_iter), float(gauss_sigma),
+        float(hinge_threshold), float(feat_stride), float(step_length), float(reg_weight), float(alpha_eps), _p(its), _p(losses),
+        _stream()), "dimp_l2_sd_gn")
+    return wout, its, losses
+
+
+def gn_sd_hinge(weights, feat, train_label, sample_weight, num_iter, filter_reg, hinge_threshold=-999.0, activation_leak=0.0,
+                score_act="relu", act_param=1.0, steplength_reg=0.0, return_iterates=False, compute_losses=False, out=None):
+    """GNSteepestDescent.forward with the LinearFilterHinge residual module (one sequence)."""
+    weights, feat, train_label = _dev(weights, "weights"), _dev(feat, "feat"), _dev(train_label, "train_label")
+    n, c, h, w = feat.shape
+    k = weights.shape[-1]
+    if train_label.numel() != n * (h + 1) * (w + 1):
+        raise RuntimeError("b200trk.gn_sd_hinge: train_label must be [n,1,H+1,W+1]")
+    if sample_weight is not None:
+        sample_weight = _dev(sample_weight, "sample_weight")
+    wout = out if out is not None else torch.empty_like(weights)
+    its = torch.empty(num_iter + 1, c, k, k, device=feat.device, dtype=torch.float32) if return_iterates else None
+    losses = torch.empty(num_iter + 1, device=feat.device, dtype=torch.float32) if compute_losses else None
+    _lib.check(_lib.lib().b200trk_gn_sd_hinge(
+        _p(weights), _p(wout), _p(feat), _p(train_label), _p(sample_weight), n, c, h, w, k, int(num_iter), float(filter_reg),
+        float(hinge_threshold), float(activation_leak), {"relu": 0, "bentpar": 1}[score_act], float(act_param),
+        float(steplength_reg), _p(its), _p(losses), _stream()), "gn_sd_hinge")
+    return wout, its, losses
+
+
 def prdimp_sd_newton(weights, feat, bb, sample_weight, num_iter, gauss_sigma, step_length, reg_weight, alpha_eps=0.0,
                      softmax_reg=None, label_threshold=0.0, normalize_label=False, label_shrink=0.0, uni_weight=0.0,
                      feat_stride=16.0, return_iterates=False, compute_losses=False, out=None):

@@ -259,3 +259,30 @@ def test_prroi_all_three_kernels(ops, B, C, H, W, R, ph, pw, scale, seed):
     # degenerate RoI (zero area): zero output and zero gradients, as the reference (win_size == 0)
     z = torch.tensor([[0, 5.0, 5.0, 5.0, 9.0]])
     assert float(ops.prroi_pool_forward(feat.cuda(), z.cuda(), ph, pw, scale).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("tag,n,c,h,it,use_sw,thr,seed", [("n8_c64", 8, 64, 18, 4, True, 0.05, 71), ("n5_c32_22", 5, 32, 22, 3, False, -999.0, 72)])
+def test_dimp_l2_sd_golden(golden_dir, ops, tag, n, c, h, it, use_sw, thr, seed):
+    """DiMPL2SteepestDescentGN against the reference module's outputs (zero initial filter included: relu'(0) = 0)."""
+    g = np.load(os.path.join(golden_dir, "dimp_l2_sd.npz"))
+    feat = synth.make_clf_features(seed, n, c, h, h).cuda()
+    bb = synth.make_boxes(seed + 1, n, center=(h * 16) / 2 - 25).cuda()
+    sw = torch.from_numpy(g[tag + "_sw"]).cuda() if use_sw else None
+    w, its, losses = ops.dimp_l2_sd_gn(torch.from_numpy(g[tag + "_w0"]).cuda(), feat, bb, sw, it, 1.3, thr, 0.9, max(0.1 ** 2, 1e-6),
+                                       alpha_eps=0.01, return_iterates=True, compute_losses=True)
+    assert _rel(its[1], g[tag + "_w1"][0]) < 1e-4
+    assert _rel(w, g[tag + "_wfinal"]) < 1e-4
+    assert np.allclose(losses.cpu().numpy(), g[tag + "_losses"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("tag,n,c,h,it,use_sw,thr,leak,act,seed", [("relu_n6_c64", 6, 64, 18, 4, True, 0.05, 0.0, "relu", 81),
+                                                                  ("bent_n4_c32_22", 4, 32, 22, 3, False, 0.1, 0.1, "bentpar", 82)])
+def test_gn_sd_hinge_golden(golden_dir, ops, tag, n, c, h, it, use_sw, thr, leak, act, seed):
+    g = np.load(os.path.join(golden_dir, "gn_sd_hinge.npz"))
+    feat = synth.make_clf_features(seed, n, c, h, h).cuda()
+    sw = torch.from_numpy(g[tag + "_sw"]).cuda() if use_sw else None
+    w, its, losses = ops.gn_sd_hinge(torch.from_numpy(g[tag + "_w0"]).cuda(), feat, torch.from_numpy(g[tag + "_label"]).unsqueeze(1).cuda(),
+                                     sw, it, 0.1, thr, leak, act, 0.7, 0.02, return_iterates=True, compute_losses=True)
+    assert _rel(its[1], g[tag + "_w1"][0]) < 1e-4
+    assert _rel(w, g[tag + "_wfinal"]) < 1e-4
+    assert np.allclose(losses.cpu().numpy(), g[tag + "_losses"], rtol=1e-4)

@@ -2,6 +2,8 @@
 unmodified reference (oracle/gen_golden.py).  This is what pins the oracle."""
 import os
 
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -160,3 +162,36 @@ def test_fourier_interp(golden_dir, tag):
         sub = up[:, 0][:, idx][:, :, idx]
         # (an even-sized map keeps both Nyquist terms, so the pass-through is exact only up to the doubled Nyquist component)
         assert sub.shape[-1] == H
+
+
+DIMP_L2_CASES = {"n8_c64": (8, 64, 18, 4, True, 0.05, 71), "n5_c32_22": (5, 32, 22, 3, False, -999.0, 72)}
+
+
+@pytest.mark.parametrize("tag", sorted(DIMP_L2_CASES))
+def test_dimp_l2_sd(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "dimp_l2_sd.npz"))
+    n, c, h, it, use_sw, thr, seed = DIMP_L2_CASES[tag]
+    feat = synth.make_clf_features(seed, n, c, h, h)
+    bb = synth.make_boxes(seed + 1, n, center=(h * 16) / 2 - 25)
+    sw = torch.from_numpy(g[tag + "_sw"]) if use_sw else None
+    w, its, losses = O.dimp_l2_sd_gn(torch.from_numpy(g[tag + "_w0"]), feat, bb, sw, math.log(0.9), 0.1, it, 1.3, thr, alpha_eps=0.01)
+    assert _rel(its[1], g[tag + "_w1"]) < 1e-5
+    assert _rel(w, g[tag + "_wfinal"]) < 1e-4
+    assert np.allclose([float(l) for l in losses], g[tag + "_losses"], rtol=1e-4)
+
+
+GN_HINGE_CASES = {"relu_n6_c64": (6, 64, 18, 4, True, 0.05, 0.0, "relu", 81), "bent_n4_c32_22": (4, 32, 22, 3, False, 0.1, 0.1, "bentpar", 82)}
+
+
+@pytest.mark.parametrize("tag", sorted(GN_HINGE_CASES))
+def test_gn_sd_hinge(golden_dir, tag):
+    """GNSteepestDescent over LinearFilterHinge (autograd J^T r / J g in the reference, explicit in the oracle)."""
+    g = np.load(os.path.join(golden_dir, "gn_sd_hinge.npz"))
+    n, c, h, it, use_sw, thr, leak, act, seed = GN_HINGE_CASES[tag]
+    feat = synth.make_clf_features(seed, n, c, h, h)
+    sw = torch.from_numpy(g[tag + "_sw"]) if use_sw else None
+    w, its, losses = O.gn_sd_hinge(torch.from_numpy(g[tag + "_w0"]), feat, torch.from_numpy(g[tag + "_label"]), sw, 0.1, it, thr, leak,
+                                   act, 0.7, 0.02)
+    assert _rel(its[1], g[tag + "_w1"]) < 1e-5
+    assert _rel(w, g[tag + "_wfinal"]) < 1e-4
+    assert np.allclose([float(l) for l in losses], g[tag + "_losses"], rtol=1e-4)
