@@ -204,6 +204,42 @@ int b200trk_net_op_set_timing_buffer(b200trk_net_t* net, int index, unsigned lon
 int b200trk_net_op_grid(const b200trk_net_t* net, int index, int dims[4]);
 
 /* ------------------------------------------------------------------------------------------------
+ * ToMP model predictor core -- Transformer.forward
+ * ---------------------------------------------------------------------------------------------- */
+
+/* nn.MultiheadAttention parameters (HOST pointers, fp32): in_proj_weight [3D,D] (q,k,v rows), in_proj_bias [3D],
+ * out_proj.weight [D,D], out_proj.bias [D]. */
+typedef struct {
+    const float* in_proj_weight; const float* in_proj_bias; const float* out_proj_weight; const float* out_proj_bias;
+} b200trk_mha_weights_t;
+/* TransformerEncoderLayer / TransformerDecoderLayer parameters (ltr/models/transformer/transformer.py:147-170,196-221). */
+typedef struct {
+    b200trk_mha_weights_t self_attn;
+    const float *linear1_weight, *linear1_bias, *linear2_weight, *linear2_bias;   /* [FF,D],[FF],[D,FF],[D] */
+    const float *norm1_weight, *norm1_bias, *norm2_weight, *norm2_bias;
+} b200trk_enc_layer_t;
+typedef struct {
+    b200trk_mha_weights_t self_attn, cross_attn;
+    const float *linear1_weight, *linear1_bias, *linear2_weight, *linear2_bias;
+    const float *norm1_weight, *norm1_bias, *norm2_weight, *norm2_bias, *norm3_weight, *norm3_bias;
+} b200trk_dec_layer_t;
+typedef struct b200trk_transformer b200trk_transformer_t;
+
+/* Transformer (ltr/models/transformer/transformer.py:66-96; normalize_before=False, activation relu, eval mode) for a fixed
+ * token count L and batch B (ToMP: L = (2 train + 1 test) * 18 * 18 = 972, B = 2 = {cls, bbreg}, d_model 256, 8 heads,
+ * FF 2048; ltr/models/transformer/filter_predictor.py:92-150). head_dim must be 32. */
+int b200trk_transformer_create(b200trk_transformer_t** out, const b200trk_enc_layer_t* enc, int n_enc,
+                               const b200trk_dec_layer_t* dec, int n_dec, const float* dec_norm_weight,
+                               const float* dec_norm_bias, int d_model, int nhead, int dim_ff, int L, int B);
+int b200trk_transformer_destroy(b200trk_transformer_t* t);
+/* Transformer.forward(src, mask, query_embed, pos_embed): src [L,B,D], pos [L,Bp,D] (Bp = 1 broadcasts over the batch),
+ * key_padding_mask [B,L] bytes (non-zero = ignore key) or NULL, query_embed [D] (one decoder query)
+ * -> hs [B,D] (the reference returns it as [1,B,1,D]), memory [L,B,D]. All pointers DEVICE. */
+int b200trk_transformer_forward(b200trk_transformer_t* t, const float* src, const float* pos, int Bp,
+                                const unsigned char* key_padding_mask, const float* query_embed, float* hs, float* memory,
+                                b200trk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Native op -- Precise RoI Pooling (the reference's only CUDA component)
  * ---------------------------------------------------------------------------------------------- */
 

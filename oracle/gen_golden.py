@@ -274,6 +274,36 @@ def gen_gn_sd_hinge():
     np.savez_compressed(os.path.join(GOLDEN, "gn_sd_hinge.npz"), **out)
 
 
+TRANSFORMER_CASES = {"small": (64, 2, 128, 2, 2, 40, 2, 91, True), "tomp_l72": (256, 8, 2048, 6, 6, 72, 2, 92, True),
+                     "tomp_l48_nomask": (256, 8, 2048, 6, 6, 48, 1, 93, False)}
+
+
+def gen_transformer():
+    """The reference's Transformer module (ltr/models/transformer/transformer.py) with seeded weights."""
+    from ltr.models.transformer.transformer import Transformer
+    from pytracking_b200 import synth
+    out = {}
+    for tag, (d, nh, ff, ne, nd, L, B, seed, use_mask) in TRANSFORMER_CASES.items():
+        net = Transformer(d_model=d, nhead=nh, num_encoder_layers=ne, num_decoder_layers=nd, dim_feedforward=ff, dropout=0.1,
+                          activation="relu", normalize_before=False)
+        sd = synth.make_transformer_state_dict(seed, d, nh, ff, ne, nd)
+        missing = net.load_state_dict(sd, strict=True)
+        net.eval()
+        g = torch.Generator().manual_seed(seed + 1)
+        src = torch.randn(L, B, d, generator=g)
+        pos = torch.randn(L, 1, d, generator=g) * 0.5
+        qe = torch.randn(1, d, generator=g)
+        mask = None
+        if use_mask:
+            mask = torch.zeros(B, L, dtype=torch.bool)
+            mask[B - 1, L // 3: L // 2] = True
+        with torch.no_grad():
+            hs, mem = net(src, mask, qe, pos)
+        out.update({tag + "_hs": _np(hs), tag + "_memory": _np(mem)})
+    np.savez_compressed(os.path.join(GOLDEN, "transformer.npz"), **out)
+
+
+GENS["transformer"] = gen_transformer
 GENS["gn_sd_hinge"] = gen_gn_sd_hinge
 GENS["dimp_l2_sd"] = gen_dimp_l2_sd
 GENS["atom_cg"] = gen_atom_cg

@@ -19,6 +19,24 @@ class ConvDesc(C.Structure):
                 ("cout", C.c_int), ("cin", C.c_int), ("k", C.c_int), ("stride", C.c_int), ("pad", C.c_int)]
 
 
+class MhaWeights(C.Structure):
+    """b200trk_mha_weights_t"""
+    _fields_ = [("in_proj_weight", C.c_void_p), ("in_proj_bias", C.c_void_p), ("out_proj_weight", C.c_void_p), ("out_proj_bias", C.c_void_p)]
+
+
+class EncLayer(C.Structure):
+    """b200trk_enc_layer_t"""
+    _fields_ = [("self_attn", MhaWeights)] + [(n, C.c_void_p) for n in (
+        "linear1_weight", "linear1_bias", "linear2_weight", "linear2_bias", "norm1_weight", "norm1_bias", "norm2_weight", "norm2_bias")]
+
+
+class DecLayer(C.Structure):
+    """b200trk_dec_layer_t"""
+    _fields_ = [("self_attn", MhaWeights), ("cross_attn", MhaWeights)] + [(n, C.c_void_p) for n in (
+        "linear1_weight", "linear1_bias", "linear2_weight", "linear2_bias", "norm1_weight", "norm1_bias", "norm2_weight", "norm2_bias",
+        "norm3_weight", "norm3_bias")]
+
+
 # name -> (restype, argtypes); every symbol of include/b200trk.h is listed (tests check the export table against it)
 _VP, _I, _F = C.c_void_p, C.c_int, C.c_float
 SIGNATURES = {
@@ -50,6 +68,9 @@ SIGNATURES = {
     "b200trk_net_op_output": (_I, [_VP, _I, _I, _VP, _VP]),
     "b200trk_net_op_set_timing_buffer": (_I, [_VP, _I, _VP]),
     "b200trk_net_op_grid": (_I, [_VP, _I, C.POINTER(C.c_int * 4)]),
+    "b200trk_transformer_create": (_I, [C.POINTER(_VP), C.POINTER(EncLayer), _I, C.POINTER(DecLayer), _I, _VP, _VP, _I, _I, _I, _I, _I]),
+    "b200trk_transformer_destroy": (_I, [_VP]),
+    "b200trk_transformer_forward": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP]),
     "b200trk_prroi_pool_forward": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _F, _VP]),
     "b200trk_prroi_pool_backward": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _F, _VP]),
     "b200trk_prroi_pool_coor_backward": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _F, _VP]),

@@ -194,3 +194,35 @@ def make_atom_memory(seed, n, c=64, h=18, w=18, n_filled=None, sigma=1.5):
     x[n_filled:] = 0
     y[n_filled:] = 0
     return x.contiguous(), y.unsqueeze(1).contiguous(), sw.contiguous()
+
+
+def make_transformer_state_dict(seed, d_model=256, nhead=8, dim_ff=2048, n_enc=6, n_dec=6):
+    """Random-init parameters in the key layout of ltr/models/transformer/transformer.py `Transformer.state_dict()`
+    (nn.MultiheadAttention: in_proj_weight/in_proj_bias/out_proj.weight/out_proj.bias; linear1/2; norm1..3; decoder.norm).
+    Xavier-like scales so that activations stay O(1) through 12 layers."""
+    g = _gen(seed)
+    sd = OrderedDict()
+
+    def lin(prefix, n_out, n_in, wname=".weight", bname=".bias"):
+        sd[prefix + wname] = torch.randn(n_out, n_in, generator=g) * math.sqrt(2.0 / (n_in + n_out))
+        sd[prefix + bname] = torch.randn(n_out, generator=g) * 0.02
+
+    def mha(prefix):
+        sd[prefix + ".in_proj_weight"] = torch.randn(3 * d_model, d_model, generator=g) * math.sqrt(2.0 / (2 * d_model))
+        sd[prefix + ".in_proj_bias"] = torch.randn(3 * d_model, generator=g) * 0.02
+        lin(prefix + ".out_proj", d_model, d_model)
+
+    def norm(prefix):
+        sd[prefix + ".weight"] = 1.0 + 0.1 * torch.randn(d_model, generator=g)
+        sd[prefix + ".bias"] = 0.05 * torch.randn(d_model, generator=g)
+
+    for i in range(n_enc):
+        p = "encoder.layers.%d" % i
+        mha(p + ".self_attn"); lin(p + ".linear1", dim_ff, d_model); lin(p + ".linear2", d_model, dim_ff)
+        norm(p + ".norm1"); norm(p + ".norm2")
+    for i in range(n_dec):
+        p = "decoder.layers.%d" % i
+        mha(p + ".self_attn"); mha(p + ".multihead_attn"); lin(p + ".linear1", dim_ff, d_model); lin(p + ".linear2", d_model, dim_ff)
+        norm(p + ".norm1"); norm(p + ".norm2"); norm(p + ".norm3")
+    norm("decoder.norm")
+    return sd

@@ -286,3 +286,57 @@ def test_gn_sd_hinge_golden(golden_dir, ops, tag, n, c, h, it, use_sw, thr, leak
     assert _rel(its[1], g[tag + "_w1"][0]) < 1e-4
     assert _rel(w, g[tag + "_wfinal"]) < 1e-4
     assert np.allclose(losses.cpu().numpy(), g[tag + "_losses"], rtol=1e-4)
+
+
+TRANSFORMER_CASES = {"small": (64, 2, 128, 2, 2, 40, 2, 91, True), "tomp_l72": (256, 8, 2048, 6, 6, 72, 2, 92, True),
+                     "tomp_l48_nomask": (256, 8, 2048, 6, 6, 48, 1, 93, False)}
+
+
+def _transformer_inputs(d, L, B, seed, use_mask):
+    g = torch.Generator().manual_seed(seed + 1)
+    src = torch.randn(L, B, d, generator=g)
+    pos = torch.randn(L, 1, d, generator=g) * 0.5
+    qe = torch.randn(1, d, generator=g)
+    mask = None
+    if use_mask:
+        mask = torch.zeros(B, L, dtype=torch.bool)
+        mask[B - 1, L // 3: L // 2] = True
+    return src, pos, qe, mask
+
+
+@pytest.mark.parametrize("tag", sorted(TRANSFORMER_CASES))
+def test_transformer_golden(golden_dir, tag):
+    """ToMP Transformer.forward (6+6 post-norm layers) against the reference module's outputs."""
+    from pytracking_b200.transformer_engine import TransformerEngine
+    g = np.load(os.path.join(golden_dir, "transformer.npz"))
+    d, nh, ff, ne, nd, L, B, seed, use_mask = TRANSFORMER_CASES[tag]
+    sd = synth.make_transformer_state_dict(seed, d, nh, ff, ne, nd)
+    src, pos, qe, mask = _transformer_inputs(d, L, B, seed, use_mask)
+    eng = TransformerEngine(sd, L, B, d, nh, ff, ne, nd)
+    hs, mem = eng.forward(src.cuda(), None if mask is None else mask.cuda(), qe.cuda(), pos.cuda())
+    assert _rel(mem, g[tag + "_memory"]) < 1e-4
+    assert _rel(hs, g[tag + "_hs"]) < 1e-4
+    eng.close()
+
+
+def test_transformer_tomp_size():
+    """BASELINE ToMP size: 972 tokens x batch 2 ({cls, bbreg} stacked with the bbreg key-padding mask), d 256, 8 heads, FF 2048."""
+    from oracle import tomp_oracle as T
+    from pytracking_b200.transformer_engine import TransformerEngine
+    d, nh, ff, ne, nd, L, B = 256, 8, 2048, 6, 6, 972, 2
+    sd = synth.make_transformer_state_dict(95, d, nh, ff, ne, nd)
+    g = torch.Generator().manual_seed(96)
+    src = torch.randn(L, B, d, generator=g)
+    pos = torch.randn(L, 1, d, generator=g) * 0.5
+    qe = torch.randn(1, d, generator=g)
+    mask = torch.zeros(B, L, dtype=torch.bool)
+    mask[1, 324:648] = True                                  # filter_predictor.py:134-136 (one ground-truth frame)
+    eng = TransformerEngine(sd, L, B, d, nh, ff, ne, nd)
+    hs, mem = eng.forward(src.cuda(), mask.cuda(), qe.cuda(), pos.cuda())
+    with torch.no_grad():
+        hs_ref, mem_ref = T.transformer_forward(sd, src, mask, qe, pos, nh, ne, nd)
+    assert _rel(mem, mem_ref) < 1e-4
+    assert _rel(hs, hs_ref) < 1e-4
+    hs2, mem2 = eng.forward(src.cuda(), mask.cuda(), qe.cuda(), pos.cuda())
+    assert torch.equal(mem, mem2) and torch.equal(hs, hs2)
+    eng.close()

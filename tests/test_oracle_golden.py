@@ -195,3 +195,35 @@ def test_gn_sd_hinge(golden_dir, tag):
     assert _rel(its[1], g[tag + "_w1"]) < 1e-5
     assert _rel(w, g[tag + "_wfinal"]) < 1e-4
     assert np.allclose([float(l) for l in losses], g[tag + "_losses"], rtol=1e-4)
+
+
+TRANSFORMER_CASES = {"small": (64, 2, 128, 2, 2, 40, 2, 91, True), "tomp_l72": (256, 8, 2048, 6, 6, 72, 2, 92, True),
+                     "tomp_l48_nomask": (256, 8, 2048, 6, 6, 48, 1, 93, False)}
+
+
+def transformer_inputs(tag):
+    d, nh, ff, ne, nd, L, B, seed, use_mask = TRANSFORMER_CASES[tag]
+    sd = synth.make_transformer_state_dict(seed, d, nh, ff, ne, nd)
+    g = torch.Generator().manual_seed(seed + 1)
+    src = torch.randn(L, B, d, generator=g)
+    pos = torch.randn(L, 1, d, generator=g) * 0.5
+    qe = torch.randn(1, d, generator=g)
+    mask = None
+    if use_mask:
+        mask = torch.zeros(B, L, dtype=torch.bool)
+        mask[B - 1, L // 3: L // 2] = True
+    return sd, src, pos, qe, mask
+
+
+@pytest.mark.parametrize("tag", sorted(TRANSFORMER_CASES))
+def test_transformer_forward(golden_dir, tag):
+    """ToMP Transformer.forward: explicit-attention restatement against the reference module's outputs."""
+    from oracle import tomp_oracle as T
+    g = np.load(os.path.join(golden_dir, "transformer.npz"))
+    d, nh, ff, ne, nd, L, B, seed, use_mask = TRANSFORMER_CASES[tag]
+    sd, src, pos, qe, mask = transformer_inputs(tag)
+    with torch.no_grad():
+        hs, mem = T.transformer_forward(sd, src, mask, qe, pos, nh, ne, nd)
+    assert hs.shape == g[tag + "_hs"].shape
+    assert _rel(mem, g[tag + "_memory"]) < 2e-5
+    assert _rel(hs, g[tag + "_hs"]) < 2e-5
