@@ -148,6 +148,15 @@ int b200trk_atom_cg_filter(const float* filter, float* filter_out, const float* 
                            float filter_reg, int fletcher_reeves, int activation, float act_param,
                            b200trk_stream_t stream);
 
+/* GaussNewtonCG.run(num_cg_iter, num_gn_iter) on FactorizedConvProblem -- ATOM's first-frame joint optimisation of the filter
+ * and the projection matrix: pytracking/libs/optimization.py:328-421, pytracking/tracker/atom/optim.py:6-68, wired at
+ * pytracking/tracker/atom/atom.py:157-178 (projection_activation 'none'; M1 = 1 / [filter_reg, projection_reg]).
+ *   filter [1,Cc,4,4] and proj [Cc,Cin,1,1] are updated IN PLACE; samples [n,Cin,H,W] raw (uncompressed) init samples,
+ *   y [n,1,H,W], sample_weight [n]; activation as in b200trk_atom_cg_filter. */
+int b200trk_atom_gn_joint(float* filter, float* proj, const float* samples, const float* y, const float* sample_weight,
+                          int n, int Cin, int Cc, int H, int W, int k, int num_cg_iter, int num_gn_iter, float filter_reg,
+                          float projection_reg, int fletcher_reeves, int activation, float act_param, b200trk_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Stage 1 -- backbone + classification head
  * ---------------------------------------------------------------------------------------------- */

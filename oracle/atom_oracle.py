@@ -159,3 +159,70 @@ def feature_normalize(x, p=2.0):
     n = x.shape[0]
     d = (torch.sum(x.abs().reshape(n, 1, 1, -1) ** p, dim=3, keepdim=True) / (x.shape[1] * x.shape[2] * x.shape[3]) + 1e-10) ** (1 / p)
     return x / d
+
+
+# ----------------------------------------------------------------------------------------------
+# S3.5 (init) GaussNewtonCG.run on FactorizedConvProblem: joint filter + projection matrix optimisation
+# ----------------------------------------------------------------------------------------------
+def conv_same_adjoint_input(u, w, H, W):
+    """Adjoint of x -> conv_same(x, w) (single-output-channel filter w [1,C,k,k]) w.r.t. x: [n,1,H,W] -> [n,C,H,W]."""
+    k = w.shape[-1]
+    p = k // 2
+    up = F.pad(u, (0, 1, 0, 1)) if k % 2 == 0 else u                    # undo the crop: zeros on the dropped row / column
+    return F.conv_transpose2d(up, w, padding=p)[:, :, :H, :W]
+
+
+def atom_gn_joint(w, P, X, y, sw, filter_reg, proj_reg, num_cg_iter, num_gn_iter, act="mlu", act_param=0.05, fletcher_reeves=True):
+    """GaussNewtonCG.run(num_cg_iter, num_gn_iter) (pytracking/libs/optimization.py:328-421) on FactorizedConvProblem
+    (pytracking/tracker/atom/optim.py:6-68), projection_activation = identity. Returns (w, P)."""
+    k = w.shape[-1]
+    H, Wd = X.shape[-2:]
+    swv = sw.view(-1, 1, 1, 1)
+    w, P = w.clone(), P.clone()
+
+    def ip(a, b):
+        return (a[0].double() * b[0].double()).sum().float() + (a[1].double() * b[1].double()).sum().float()
+
+    for _ in range(num_gn_iter):
+        comp = conv1x1(X, P)
+        s = conv_same(comp, w)
+        a, d = activation(s, act, act_param), activation_deriv(s, act, act_param)
+        r0 = swv * d * (a - y)
+        D = swv * d * d
+
+        def JT(u):      # u already carries sw * phi' factors
+            gw = conv_same_adjoint_filter(comp, u, k)
+            T = conv_same_adjoint_input(u, w, H, Wd)                  # [n,Cc,H,W]
+            gP = torch.einsum("ncp,nkp->ck", T.flatten(2).double(), X.flatten(2).double()).float().reshape(P.shape)
+            return gw, gP
+
+        gw, gP = JT(r0)
+        r = [-(gw + filter_reg * w), -(gP + proj_reg * P)]
+        x = None
+        p = None
+        rho = torch.ones(())
+        r_prev = None
+        for ii in range(num_cg_iter):
+            z = [r[0] / filter_reg, r[1] / proj_reg]
+            rho1 = rho
+            rho = ip(r, z)
+            if float(rho) == 0.0:
+                break
+            if p is None:
+                p = [z[0].clone(), z[1].clone()]
+            else:
+                beta = rho / rho1 if fletcher_reeves else (rho - ip(r_prev, z)) / rho1
+                beta = beta.clamp(0)
+                p = [z[0] + p[0] * beta, z[1] + p[1] * beta]
+            Jp = D * (conv_same(comp, p[0]) + conv_same(conv1x1(X, p[1]), w))
+            qw, qP = JT(Jp)
+            q = [qw + filter_reg * p[0], qP + proj_reg * p[1]]
+            alpha = rho / ip(p, q)
+            if not fletcher_reeves:
+                r_prev = [r[0].clone(), r[1].clone()]
+            x = [p[0] * alpha, p[1] * alpha] if x is None else [x[0] + p[0] * alpha, x[1] + p[1] * alpha]
+            if ii < num_cg_iter - 1:
+                r = [r[0] - q[0] * alpha, r[1] - q[1] * alpha]
+        if x is not None:
+            w, P = w + x[0], P + x[1]
+    return w, P

@@ -303,6 +303,34 @@ def gen_transformer():
     np.savez_compressed(os.path.join(GOLDEN, "transformer.npz"), **out)
 
 
+ATOM_GN_CASES = {"n6_c32_16": (6, 32, 16, 3, 2, True, "mlu", 101), "n10_c64_32_pr": (10, 64, 32, 4, 3, False, "relu", 102)}
+
+
+def gen_atom_gn():
+    """GaussNewtonCG on FactorizedConvProblem as ATOM.init_optimization wires it (atom.py:157-178)."""
+    from pytracking import TensorList
+    from pytracking.libs.optimization import GaussNewtonCG
+    from pytracking.tracker.atom.optim import FactorizedConvProblem
+    from pytracking_b200 import synth
+    import torch.nn.functional as F
+    out = {}
+    for tag, (n, cin, cc, ncg, ngn, fr, act, seed) in ATOM_GN_CASES.items():
+        x, y, sw = synth.make_atom_memory(seed, n, cin, 18, 18)
+        g = torch.Generator().manual_seed(seed + 7)
+        w0 = torch.zeros(1, cc, 4, 4) if tag.startswith("n6") else torch.randn(1, cc, 4, 4, generator=g) * 0.02
+        P0 = torch.randn(cc, cin, 1, 1, generator=g) * (1.0 / cin ** 0.5)
+        fn = (lambda t: F.elu(F.leaky_relu(t, 1 / 0.05), 0.05)) if act == "mlu" else torch.nn.ReLU(inplace=False)
+        filt, proj = TensorList([w0.clone()]), TensorList([P0.clone()])
+        prob = FactorizedConvProblem(TensorList([x]), TensorList([y]), TensorList([0.1]), TensorList([1e-2]), None, TensorList([sw]),
+                                     lambda t: t, fn)
+        var = filt.concat(proj)
+        opt = GaussNewtonCG(prob, var, fletcher_reeves=fr, debug=False)
+        opt.run(ncg, ngn)
+        out.update({tag + "_w0": _np(w0), tag + "_P0": _np(P0), tag + "_w": _np(var[0]).copy(), tag + "_P": _np(var[1]).copy()})
+    np.savez_compressed(os.path.join(GOLDEN, "atom_gn.npz"), **out)
+
+
+GENS["atom_gn"] = gen_atom_gn
 GENS["transformer"] = gen_transformer
 GENS["gn_sd_hinge"] = gen_gn_sd_hinge
 GENS["dimp_l2_sd"] = gen_dimp_l2_sd

@@ -208,6 +208,24 @@ def atom_cg_filter(filt, feat, y, sample_weight, filter_reg, num_iter, activatio
     return wout
 
 
+def atom_gn_joint_(filt, proj, samples, y, sample_weight, filter_reg, projection_reg, num_cg_iter, num_gn_iter,
+                   activation="mlu", act_param=0.05, fletcher_reeves=True):
+    """GaussNewtonCG.run(num_cg_iter, num_gn_iter) on FactorizedConvProblem; updates `filt` and `proj` in place."""
+    for name, t in (("filter", filt), ("projection_matrix", proj)):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError("b200trk.atom_gn_joint_: '%s' must be a contiguous CUDA float32 tensor (updated in place)" % name)
+    samples, y, sample_weight = _dev(samples, "samples"), _dev(y, "y"), _dev(sample_weight, "sample_weight")
+    n, cin, h, w = samples.shape
+    cc, k = filt.shape[1], filt.shape[-1]
+    if proj.numel() != cc * cin:
+        raise RuntimeError("b200trk.atom_gn_joint_: projection matrix %s does not match (%d, %d)" % (tuple(proj.shape), cc, cin))
+    _lib.check(_lib.lib().b200trk_atom_gn_joint(_p(filt), _p(proj), _p(samples), _p(y), _p(sample_weight), n, cin, cc, h, w, k,
+                                                int(num_cg_iter), int(num_gn_iter), float(filter_reg), float(projection_reg),
+                                                1 if fletcher_reeves else 0, ATOM_ACTIVATIONS[activation], float(act_param), _stream()),
+               "atom_gn_joint")
+    return filt, proj
+
+
 def prroi_pool_forward(features, rois, ph, pw, scale):
     features, rois = _dev(features, "features"), _dev(rois, "rois")
     b, c, h, w = features.shape

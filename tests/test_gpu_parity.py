@@ -340,3 +340,39 @@ def test_transformer_tomp_size():
     hs2, mem2 = eng.forward(src.cuda(), mask.cuda(), qe.cuda(), pos.cuda())
     assert torch.equal(mem, mem2) and torch.equal(hs, hs2)
     eng.close()
+
+
+ATOM_GN_CASES = {"n6_c32_16": (6, 32, 16, 3, 2, True, "mlu", 101), "n10_c64_32_pr": (10, 64, 32, 4, 3, False, "relu", 102)}
+
+
+@pytest.mark.parametrize("tag", sorted(ATOM_GN_CASES))
+def test_atom_gn_joint_golden(golden_dir, ops, tag):
+    """ATOM first-frame joint optimisation (GaussNewtonCG on FactorizedConvProblem) against the reference classes' outputs."""
+    g = np.load(os.path.join(golden_dir, "atom_gn.npz"))
+    n, cin, cc, ncg, ngn, fr, act, seed = ATOM_GN_CASES[tag]
+    x, y, sw = synth.make_atom_memory(seed, n, cin, 18, 18)
+    w = torch.from_numpy(g[tag + "_w0"]).cuda().contiguous()
+    P = torch.from_numpy(g[tag + "_P0"]).cuda().contiguous()
+    ops.atom_gn_joint_(w, P, x.cuda(), y.cuda(), sw.cuda(), 0.1, 1e-2, ncg, ngn, act, 0.05, fr)
+    assert _rel(w, g[tag + "_w"]) < 1e-4
+    assert _rel(P, g[tag + "_P"]) < 1e-4
+
+
+def test_atom_gn_joint_baseline_size(ops):
+    """ATOM default init: 30 augmented samples x 256 channels -> 64, 6 GN x 10 CG iterations (atom/default.py:27-28)."""
+    from oracle import atom_oracle as A
+    x, y, sw = synth.make_atom_memory(111, 30, 256, 18, 18)
+    g = torch.Generator().manual_seed(112)
+    P0 = torch.randn(64, 256, 1, 1, generator=g) * (1.0 / 16)
+    w0 = torch.zeros(1, 64, 4, 4)
+    w, P = w0.clone().cuda(), P0.clone().cuda()
+    ops.atom_gn_joint_(w, P, x.cuda(), y.cuda(), sw.cuda(), 0.1, 1e-4, 10, 6, "mlu", 0.05, True)
+    w_ref, P_ref = A.atom_gn_joint(w0, P0, x, y, sw, 0.1, 1e-4, 10, 6, "mlu", 0.05, True)
+    assert _rel(w, w_ref) < 2e-3          # 60 CG iterations of an ill-conditioned system amplify fp32 summation-order noise
+    assert _rel(P, P_ref) < 2e-3
+
+    def loss(wt, Pt):
+        s = A.conv_same(A.conv1x1(x, Pt), wt)
+        return float((sw.view(-1, 1, 1, 1) * (A.activation(s, "mlu", 0.05) - y) ** 2).sum() + 0.1 * (wt ** 2).sum() + 1e-4 * (Pt ** 2).sum())
+    l_gpu, l_ref, l0 = loss(w.cpu(), P.cpu()), loss(w_ref, P_ref), loss(w0, P0)
+    assert l_gpu < 0.5 * l0 and abs(l_gpu - l_ref) < 1e-3 * l_ref

@@ -227,3 +227,18 @@ def test_transformer_forward(golden_dir, tag):
     assert hs.shape == g[tag + "_hs"].shape
     assert _rel(mem, g[tag + "_memory"]) < 2e-5
     assert _rel(hs, g[tag + "_hs"]) < 2e-5
+
+
+ATOM_GN_CASES = {"n6_c32_16": (6, 32, 16, 3, 2, True, "mlu", 101), "n10_c64_32_pr": (10, 64, 32, 4, 3, False, "relu", 102)}
+
+
+@pytest.mark.parametrize("tag", sorted(ATOM_GN_CASES))
+def test_atom_gn_joint(golden_dir, tag):
+    """ATOM first-frame joint optimisation: GaussNewtonCG on FactorizedConvProblem (reference classes) vs the explicit J / J^T oracle."""
+    from oracle import atom_oracle as A
+    g = np.load(os.path.join(golden_dir, "atom_gn.npz"))
+    n, cin, cc, ncg, ngn, fr, act, seed = ATOM_GN_CASES[tag]
+    x, y, sw = synth.make_atom_memory(seed, n, cin, 18, 18)
+    w, P = A.atom_gn_joint(torch.from_numpy(g[tag + "_w0"]), torch.from_numpy(g[tag + "_P0"]), x, y, sw, 0.1, 1e-2, ncg, ngn, act, 0.05, fr)
+    assert _rel(w, g[tag + "_w"]) < 1e-4
+    assert _rel(P, g[tag + "_P"]) < 1e-4
