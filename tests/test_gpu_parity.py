@@ -376,3 +376,36 @@ def test_atom_gn_joint_baseline_size(ops):
         return float((sw.view(-1, 1, 1, 1) * (A.activation(s, "mlu", 0.05) - y) ** 2).sum() + 0.1 * (wt ** 2).sum() + 1e-4 * (Pt ** 2).sum())
     l_gpu, l_ref, l0 = loss(w.cpu(), P.cpu()), loss(w_ref, P_ref), loss(w0, P0)
     assert l_gpu < 0.5 * l0 and abs(l_gpu - l_ref) < 1e-3 * l_ref
+
+
+def test_plugin_mirror_reads_like_the_reference(golden_dir):
+    """pytracking_b200.plugin: the reference call signatures (5-D feat, (weights, iterates, losses) returns) over the C ABI."""
+    from pytracking_b200 import plugin
+    g = np.load(os.path.join(golden_dir, "dimp_sd.npz"))
+    tag, n, c, h, it, seed = "n15_it10", 15, 512, 18, 10, 21
+    p = synth.make_dimp_optimizer_params(seed=seed)
+    feat = synth.make_clf_features(seed, n, c, h, h).cuda().unsqueeze(1)                 # (images, sequences=1, C, H, W)
+    bb = synth.make_boxes(seed + 1, n, center=(h * 16) / 2 - 25).cuda().unsqueeze(1)     # (images, sequences=1, 4)
+    sw = torch.from_numpy(g[tag + "_sw"]).cuda().reshape(n, 1)
+    opt = plugin.DiMPSteepestDescentGN(p["label_map_predictor.weight"], p["target_mask_predictor.0.weight"],
+                                       p["spatial_weight_predictor.weight"], p["log_step_length"], p["filter_reg"], num_iter=5)
+    weights, iterates, losses = opt(torch.from_numpy(g[tag + "_w0"]).cuda(), feat, bb, sample_weight=sw, num_iter=it, compute_losses=True)
+    assert len(iterates) == it + 1 and len(losses) == it + 1 and iterates[0].shape == weights.shape
+    assert _rel(weights, g[tag + "_wfinal"]) < 1e-4
+    scores = plugin.apply_filter(feat, weights)
+    assert scores.shape == (n, 1, 19, 19)
+    mv, mi = plugin.max2d(scores[:, 0])
+    assert mi.shape == (n, 2)
+    gt = plugin.apply_feat_transpose(feat, scores, (4, 4), training=False)
+    assert gt.shape == (1, c, 4, 4)
+    with pytest.raises(NotImplementedError):
+        plugin.apply_filter(torch.cat([feat, feat], 1), torch.cat([weights, weights], 0))      # two sequences: not claimed
+    # ATOM optimiser objects update their variable in place, like the reference's run()
+    x, y, swa = synth.make_atom_memory(52, 40, 64, 18, 18, n_filled=25)
+    ga = np.load(os.path.join(golden_dir, "atom_cg.npz"))
+    filt = torch.from_numpy(ga["n40_c64_pr_mlu_w0"]).cuda().contiguous()
+    cg = plugin.ConjugateGradient(x.cuda(), y.cuda(), 0.1, swa.cuda(), filt, ("mlu", 0.05), fletcher_reeves=False)
+    cg.run(5)
+    assert _rel(filt, ga["n40_c64_pr_mlu_w"]) < 1e-4
+    cg.run(5)
+    assert _rel(filt, ga["n40_c64_pr_mlu_w2"]) < 1e-4
