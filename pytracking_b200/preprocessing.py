@@ -1,0 +1,49 @@
+"""Host-side mirror of the reference crop sampling (pytracking/features/preprocessing.py:6-7, 33-148) for the
+border mode the trackers of this path use ('replicate').  It runs the same torch-CPU operations in the same order as the
+reference, so the crops are bit-identical (asserted against the reference itself in oracle/gen_track_golden.py); it exists
+so that bench / tests on a machine without the reference tree can feed the engine exactly what the tracker would.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def numpy_to_torch(a):
+    """preprocessing.py:6-7: HxWx3 uint8/float ndarray -> [1,3,H,W] float32."""
+    return torch.from_numpy(a).float().permute(2, 0, 1).unsqueeze(0)
+
+
+def sample_patch(im, pos, sample_sz, output_sz=None, mode="replicate"):
+    """preprocessing.py:55-148 (mode 'replicate'). Returns (patch [1,C,h,w], patch_coord [1,4] = (tl_y, tl_x, br_y, br_x))."""
+    if mode != "replicate":
+        raise NotImplementedError("sample_patch mirror: only border_mode 'replicate'")
+    posl = pos.long().clone()
+    if output_sz is not None:
+        resize_factor = torch.min(sample_sz.float() / output_sz.float()).item()
+        df = int(max(int(resize_factor - 0.1), 1))
+    else:
+        df = int(1)
+    sz = sample_sz.float() / df
+    if df > 1:
+        os_ = posl % df
+        posl = (posl - os_) / df
+        im2 = im[..., os_[0].item()::df, os_[1].item()::df]
+    else:
+        im2 = im
+    szl = torch.max(sz.round(), torch.Tensor([2])).long()
+    tl = posl - (szl - 1) / 2
+    br = posl + szl / 2 + 1
+    pad = (-tl[1].int().item(), br[1].int().item() - im2.shape[3], -tl[0].int().item(), br[0].int().item() - im2.shape[2])
+    im_patch = F.pad(im2, pad, "replicate")
+    patch_coord = df * torch.cat((tl, br)).view(1, 4)
+    if output_sz is None or (im_patch.shape[-2] == output_sz[0] and im_patch.shape[-1] == output_sz[1]):
+        return im_patch.clone(), patch_coord
+    im_patch = F.interpolate(im_patch, output_sz.long().tolist(), mode="bilinear")
+    return im_patch, patch_coord
+
+
+def sample_patch_multiscale(im, pos, scales, image_sz, mode="replicate", max_scale_change=None):
+    """preprocessing.py:33-52."""
+    if isinstance(scales, (int, float)):
+        scales = [scales]
+    patch_iter, coord_iter = zip(*(sample_patch(im, pos, s * image_sz, image_sz, mode=mode) for s in scales))
+    return torch.cat(list(patch_iter)), torch.cat(list(coord_iter))

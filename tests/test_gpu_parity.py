@@ -409,3 +409,52 @@ def test_plugin_mirror_reads_like_the_reference(golden_dir):
     assert _rel(filt, ga["n40_c64_pr_mlu_w"]) < 1e-4
     cg.run(5)
     assert _rel(filt, ga["n40_c64_pr_mlu_w2"]) < 1e-4
+
+
+def test_dimp_tracker_trajectory_replay(golden_dir):
+    """End to end inside a real tracker run: tests/golden/dimp_track.npz is a 12-frame trajectory of the UNMODIFIED reference
+    DiMP tracker (oracle/gen_track_golden.py: dimp50 parameters, CPU, seeded random-init DiMP-50, no IoUNet). The frames are
+    regenerated here, cropped with the bit-exact mirror of the reference's sample_patch, pushed through the host-buffer frame
+    calls of the C ABI, and compared frame by frame: score maps (1e-4), arg-max cell (exact), filter after every online update."""
+    from oracle import dimp_oracle as O
+    from pytracking_b200 import preprocessing as pre
+    from pytracking_b200.frame_engine import DiMPFrameEngine, SampleWeights
+    g = np.load(os.path.join(golden_dir, "dimp_track.npz"))
+    frames, init_bbox = synth.make_sequence(0, num_frames=12)
+    assert np.allclose(init_bbox, g["init_bbox"])
+    sd = synth.make_dimp_state_dict("resnet50", seed=0, lut_seed=3)
+    eng = DiMPFrameEngine(sd, arch="resnet50", filter_size=4, memory_size=50, max_batch=1, crop_size=288, precision=0)
+    sz = torch.from_numpy(g["img_sample_sz"])
+    # ---- DiMP.initialize: one un-augmented sample, zero filter, net_opt_iter SD iterations ----
+    im0 = pre.numpy_to_torch(frames[0])
+    crop0, _ = pre.sample_patch(im0, torch.from_numpy(g["init_pos"]), float(g["init_scale"]) * sz, sz)
+    eng.filter.zero_()
+    eng.localize(crop0.contiguous().pin_memory())
+    eng.update(0, 0, g["init_target_box"], np.array([1.0], dtype=np.float32), 1, int(g["init_num_iter"]))
+    torch.cuda.synchronize()
+    assert _rel(eng.filter, g["init_filter"]) < 1e-4
+    swm = SampleWeights(50, 1, learning_rate=0.01, init_samples_minimum_weight=0.25)
+    worst_s = worst_f = 0.0
+    for t in range(1, 13):
+        k = "f%02d_" % t
+        im = pre.numpy_to_torch(frames[t])
+        crop, _ = pre.sample_patch_multiscale(im, torch.from_numpy(g[k + "crop_pos"]), [float(s) for s in g[k + "crop_scale"]], sz)
+        scores, mv, mi = eng.localize(crop.contiguous().pin_memory())
+        ref = g[k + "scores"]
+        worst_s = max(worst_s, _rel(scores, ref.reshape(scores.shape)))
+        _, mi_ref = O.max2d(torch.from_numpy(ref).reshape(1, 19, 19))
+        assert mi.tolist() == mi_ref.tolist(), "frame %d: arg-max cell differs" % t
+        if int(g[k + "updated"]):
+            lr = float(g[k + "lr"])
+            r = swm.step(None if lr < 0 else lr)
+            n = int(g[k + "n_stored"])
+            assert r == int(g[k + "replace_ind"]) and n == swm.num_stored
+            assert np.allclose(swm.w[:n], g[k + "sample_weights"], rtol=1e-6, atol=1e-9)
+            eng.update(0, r, g[k + "target_box"].reshape(4), g[k + "sample_weights"], n, 1 if lr >= 0 else 2)
+            torch.cuda.synchronize()
+            f = eng.filter.cpu().numpy()
+            worst_f = max(worst_f, _rel(f.reshape(-1)[::128], g[k + "filter_probe"]))
+            if (k + "filter") in g:
+                worst_f = max(worst_f, _rel(f, g[k + "filter"]))
+    assert worst_s < 1e-4 and worst_f < 1e-4, (worst_s, worst_f)
+    eng.close()
