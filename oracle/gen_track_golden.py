@@ -113,6 +113,15 @@ def main():
     rec["init_target_box"] = tracker.target_boxes[0].clone().numpy()
     rec["init_filter"] = tracker.target_filter.detach().clone().numpy()
     rec["init_num_iter"] = np.array(params.net_opt_iter)
+    rec["aug_expansion_factor"] = np.array(float(params.augmentation_expansion_factor))
+    # the mirror of the first-frame sample (expanded patch + Identity centre crop) must equal the reference's
+    im0 = ref_pre.numpy_to_torch(frames[0])
+    aug_sz = (tracker.img_sample_sz * params.augmentation_expansion_factor).long()
+    aug_sz += (aug_sz - tracker.img_sample_sz.long()) % 2
+    ref_patch = ref_pre.sample_patch_transformed(im0, tracker.init_sample_pos, tracker.init_sample_scale, aug_sz.float(), tracker.transforms[:1])
+    mine = mirror_pre.sample_init_patch(im0, tracker.init_sample_pos, tracker.init_sample_scale, tracker.img_sample_sz,
+                                       params.augmentation_expansion_factor)
+    assert torch.equal(ref_patch, mine), "first-frame sample mirror differs from the reference"
     rec["img_sample_sz"] = tracker.img_sample_sz.clone().numpy()
     boxes, flags = [], []
     for t in range(1, NUM_FRAMES + 1):

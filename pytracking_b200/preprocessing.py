@@ -47,3 +47,23 @@ def sample_patch_multiscale(im, pos, scales, image_sz, mode="replicate", max_sca
         scales = [scales]
     patch_iter, coord_iter = zip(*(sample_patch(im, pos, s * image_sz, image_sz, mode=mode) for s in scales))
     return torch.cat(list(patch_iter)), torch.cat(list(coord_iter))
+
+
+def sample_init_patch(im, pos, scale, img_sample_sz, aug_expansion_factor=None):
+    """The un-augmented first-frame sample of DiMP.generate_init_samples (pytracking/tracker/dimp/dimp.py:353-389):
+    the patch is sampled at the augmentation expansion size and the Identity transform crops its centre back to the sample
+    size (pytracking/features/augmentation.py:20-40: F.pad with negative 'replicate' padding)."""
+    import math
+    aug_sz = img_sample_sz.clone()
+    out_sz = None
+    if aug_expansion_factor is not None and aug_expansion_factor != 1:
+        aug_sz = (img_sample_sz * aug_expansion_factor).long()
+        aug_sz += (aug_sz - img_sample_sz.long()) % 2
+        aug_sz = aug_sz.float()
+        out_sz = img_sample_sz.long().tolist()
+    patch, _ = sample_patch(im, pos, scale * aug_sz, aug_sz)
+    if out_sz is None:
+        return patch
+    pad_h = (out_sz[0] - patch.shape[2]) / 2
+    pad_w = (out_sz[1] - patch.shape[3]) / 2
+    return F.pad(patch, (math.floor(pad_w), math.ceil(pad_w), math.floor(pad_h), math.ceil(pad_h)), "replicate")

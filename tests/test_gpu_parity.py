@@ -427,7 +427,7 @@ def test_dimp_tracker_trajectory_replay(golden_dir):
     sz = torch.from_numpy(g["img_sample_sz"])
     # ---- DiMP.initialize: one un-augmented sample, zero filter, net_opt_iter SD iterations ----
     im0 = pre.numpy_to_torch(frames[0])
-    crop0, _ = pre.sample_patch(im0, torch.from_numpy(g["init_pos"]), float(g["init_scale"]) * sz, sz)
+    crop0 = pre.sample_init_patch(im0, torch.from_numpy(g["init_pos"]), float(g["init_scale"]), sz, float(g["aug_expansion_factor"]))
     eng.filter.zero_()
     eng.localize(crop0.contiguous().pin_memory())
     eng.update(0, 0, g["init_target_box"], np.array([1.0], dtype=np.float32), 1, int(g["init_num_iter"]))
