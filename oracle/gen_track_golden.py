@@ -135,10 +135,7 @@ def main():
         if updated:
             for k in ("replace_ind", "target_box", "n_stored", "sample_weights", "lr"):
                 rec["f%02d_%s" % (t, k)] = np.array(cur[k])
-            # full filter for a few frames, a 64-tap probe for all (keeps the fixture small)
-            if t in (1, 2, NUM_FRAMES):
-                rec["f%02d_filter" % t] = cur["filter"]
-            rec["f%02d_filter_probe" % t] = cur["filter"].reshape(-1)[::128].copy()
+            rec["f%02d_filter" % t] = cur["filter"]
         log.append((t, flags[-1], [round(v, 2) for v in boxes[-1]], float(cur["scores"].max())))
     rec["boxes"] = np.array(boxes, dtype=np.float32)
     rec["flags"] = np.array(flags)
