@@ -163,19 +163,19 @@ static int build(b200trk_net* net, const b200trk_conv_desc_t* convs, int n_convs
             net->dims[(li - 1) * 3 + 0] = inplanes; net->dims[(li - 1) * 3 + 1] = H; net->dims[(li - 1) * 3 + 2] = W;
         }
     }
-    // classification head
-    int hx = x, hh = H, hw = W, cdim;
-    if (bottleneck) {
-        cdim = 512;
-        if (int e = B.add_conv(x, -1, H, W, inplanes, cdim, 3, 1, 1, 0, &hx, &hh, &hw)) return e;
-    } else {
-        cdim = 256;
-        int c1, c2;
-        if (int e = B.add_conv(x, -1, H, W, inplanes, 256, 3, 1, 1, 1, &c1, &hh, &hw)) return e;
-        if (int e = B.add_conv(c1, x, hh, hw, 256, 256, 3, 1, 1, 1, &c2, &hh, &hw)) return e;
-        if (int e = B.add_conv(c2, -1, hh, hw, 256, cdim, 3, 1, 1, 0, &hx, &hh, &hw)) return e;
-    }
-    {
+    // classification head (absent when only the backbone descriptors are given: ATOM's ATOMResNet18 uses raw layer3 features)
+    if (B.next < n_convs) {
+        int hx = x, hh = H, hw = W, cdim;
+        if (bottleneck) {
+            cdim = 512;
+            if (int e = B.add_conv(x, -1, H, W, inplanes, cdim, 3, 1, 1, 0, &hx, &hh, &hw)) return e;
+        } else {
+            cdim = 256;
+            int c1, c2;
+            if (int e = B.add_conv(x, -1, H, W, inplanes, 256, 3, 1, 1, 1, &c1, &hh, &hw)) return e;
+            if (int e = B.add_conv(c1, x, hh, hw, 256, 256, 3, 1, 1, 1, &c2, &hh, &hw)) return e;
+            if (int e = B.add_conv(c2, -1, hh, hw, 256, cdim, 3, 1, 1, 0, &hx, &hh, &hw)) return e;
+        }
         Op op; op.kind = OP_L2NORM_EXPORT; op.in = hx; op.Hin = hh; op.Win = hw; op.Cin = cdim;
         net->ops.push_back(op);
         net->dims[6] = cdim; net->dims[7] = hh; net->dims[8] = hw;

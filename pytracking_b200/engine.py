@@ -33,7 +33,7 @@ def _conv_entry(sd, keep, wkey, bnprefix, stride, pad, bias_key=None):
     return d
 
 
-def conv_descs_from_state_dict(sd, arch, backbone_prefix="feature_extractor.", head_prefix="classifier.feature_extractor."):
+def conv_descs_from_state_dict(sd, arch, backbone_prefix="feature_extractor.", head_prefix="classifier.feature_extractor.", head=True):
     """Conv descriptors in the execution order `b200trk_net_create` expects (include/b200trk.h)."""
     block, layers = RESNET_ARCH[arch]
     keep, descs = [], []
@@ -56,6 +56,8 @@ def conv_descs_from_state_dict(sd, arch, backbone_prefix="feature_extractor.", h
                     descs.append(_conv_entry(sd, keep, q + "downsample.0.weight", q + "downsample.1", stride, 0))
                 descs.append(_conv_entry(sd, keep, q + "conv2.weight", q + "bn2", 1, 1))
     h = head_prefix
+    if not head:
+        return descs, keep
     if block == "bottleneck":
         descs.append(_conv_entry(sd, keep, h + "0.weight", None, 1, 1))
     else:
@@ -68,14 +70,15 @@ def conv_descs_from_state_dict(sd, arch, backbone_prefix="feature_extractor.", h
 class BackboneEngine:
     """Owns a `b200trk_net_t`. forward(im) mirrors NetWithBackbone.extract_backbone + extract_classification_feat."""
 
-    def __init__(self, state_dict, arch="resnet50", filter_size=4, max_batch=1, crop_size=288, precision=0, device=None):
+    def __init__(self, state_dict, arch="resnet50", filter_size=4, max_batch=1, crop_size=288, precision=0, device=None, head=True):
         if not torch.cuda.is_available():
             raise RuntimeError("BackboneEngine: CUDA device required (the engine has no CPU path)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.arch = arch
         self.max_batch = max_batch
         self.crop_size = (crop_size, crop_size) if isinstance(crop_size, int) else tuple(crop_size)
-        descs, keep = conv_descs_from_state_dict(state_dict, arch)
+        descs, keep = conv_descs_from_state_dict(state_dict, arch, head=head)
+        self.has_head = head
         arr = (_lib.ConvDesc * len(descs))(*descs)
         out_dim = descs[-1].cout
         self.norm_scale = math.sqrt(1.0 / (out_dim * filter_size * filter_size))     # dimpnet.py:159
@@ -102,7 +105,7 @@ class BackboneEngine:
         outs = OrderedDict()
         ptrs = []
         for i, name in enumerate(("layer2", "layer3", "classification")):
-            if name in want:
+            if name in want and (name != "classification" or self.has_head):
                 t = torch.empty(s, d[3 * i], d[3 * i + 1], d[3 * i + 2], device=im.device, dtype=torch.float32)
                 outs[name] = t
                 ptrs.append(C.c_void_p(t.data_ptr()))

@@ -472,3 +472,65 @@ def test_dimp_tracker_trajectory_replay(golden_dir):
     assert worst_s < 1e-4 and worst_f < 1e-4, (worst_s, worst_f)
     assert drift < 1e-2, drift
     eng.close()
+
+
+def test_atom_tracker_trajectory_replay(golden_dir, ops):
+    """BASELINE configs[0]: the UNMODIFIED reference ATOM tracker (ResNet-18, 5 scales, no IoUNet; oracle/gen_atom_track_golden.py)
+    replayed through the engine: first-frame joint GN-CG optimisation, then per frame backbone -> p-norm -> projection -> conv 'same'
+    -> Fourier upsampling -> arg-max, memory update and the CG filter update; open loop from the reference's previous filter."""
+    from oracle import dimp_oracle as O
+    from pytracking_b200 import preprocessing as pre
+    from pytracking_b200.engine import BackboneEngine
+    g = np.load(os.path.join(golden_dir, "atom_track.npz"))
+    frames, init_bbox = synth.make_sequence(1, num_frames=8)
+    assert np.allclose(init_bbox, g["init_bbox"])
+    sd = synth.make_backbone_state_dict("resnet18", seed=5)
+    sz = torch.from_numpy(g["img_sample_sz"])
+    crop = int(sz[0])
+    eng = BackboneEngine(sd, arch="resnet18", max_batch=5, crop_size=crop, precision=0, head=False)
+    freg, preg = float(g["filter_reg"]), float(g["projection_reg"])
+    osz = [int(v) for v in g["output_sz"]]
+
+    def features(crops):
+        x = eng.forward(crops.cuda().contiguous(), want=("layer3",))["layer3"]
+        return ops.feature_normalize_(x, 2.0)
+
+    # ---- ATOM.initialize: joint optimisation of filter and projection matrix on the un-augmented first-frame sample ----
+    im0 = pre.numpy_to_torch(frames[0])
+    crop0 = pre.sample_init_patch(im0, torch.from_numpy(g["init_pos"]), float(g["init_scale"]), sz, float(g["aug_expansion_factor"]))
+    x0 = features(crop0)
+    w = torch.from_numpy(g["init_w0"]).cuda().contiguous()
+    P = torch.from_numpy(g["init_P0"]).cuda().contiguous()
+    y0 = torch.from_numpy(g["init_y"]).cuda()
+    ops.atom_gn_joint_(w, P, x0, y0, torch.ones(1, device="cuda"), freg, preg, int(g["init_num_cg"]), int(g["init_num_gn"]), "mlu", 0.05, True)
+    assert _rel(w, g["init_w"]) < 2e-3 and _rel(P, g["init_P"]) < 2e-3, (_rel(w, g["init_w"]), _rel(P, g["init_P"]))
+    P_ref = torch.from_numpy(g["init_P"]).cuda()
+    mem = torch.zeros(250, 64, 18, 18, device="cuda")
+    ymem = torch.zeros(250, 1, 18, 18, device="cuda")
+    mem[0] = ops.conv1x1(x0, P_ref)[0]
+    ymem[0] = y0[0]
+    prev_filter = torch.from_numpy(g["init_w"]).cuda()
+    worst_s = worst_f = worst_m = 0.0
+    for t in range(1, 9):
+        k = "f%02d_" % t
+        im = pre.numpy_to_torch(frames[t])
+        crops, _ = pre.sample_patch_multiscale(im, torch.from_numpy(g[k + "crop_pos"]), [float(s) for s in g[k + "crop_scales"]], sz)
+        proj = ops.conv1x1(features(crops), P_ref)
+        scores = ops.conv2d_same(proj, prev_filter)
+        worst_s = max(worst_s, _rel(scores, g[k + "scores_raw"]))
+        up = ops.fourier_interp(scores, (4, 4), osz)
+        mv, mi = ops.max2d(up[:, 0])
+        assert np.array_equal(mi.cpu().numpy(), g[k + "up_maxidx"]), "frame %d: arg-max on the upsampled grid differs" % t
+        worst_m = max(worst_m, _rel(mv, g[k + "up_maxval"]))
+        scale_ind = int(np.argmax(g[k + "up_maxval"]))
+        assert int(torch.argmax(mv)) == scale_ind
+        if int(g[k + "updated"]):
+            r = int(g[k + "replace_ind"])
+            mem[r] = proj[scale_ind]
+            ymem[r] = torch.from_numpy(g[k + "train_y"]).cuda()[0]
+        sw = torch.from_numpy(g[k + "sample_weights"]).cuda() if int(g[k + "updated"]) else sw
+        f = ops.atom_cg_filter(prev_filter, mem, ymem, sw, freg, int(g[k + "cg_iters"]), "mlu", 0.05, False)
+        worst_f = max(worst_f, _rel(f, g[k + "filter"]))
+        prev_filter = torch.from_numpy(g[k + "filter"]).cuda()
+    assert worst_s < 1e-4 and worst_m < 1e-4 and worst_f < 1e-4, (worst_s, worst_m, worst_f)
+    eng.close()
