@@ -83,6 +83,10 @@ int b200trk_feature_normalize(float* feat, int S, int C, int H, int W, float nor
 int b200trk_fourier_interp(const float* scores, float* out, int S, int H, int W, int ksz_h, int ksz_w, int out_h,
                            int out_w, b200trk_stream_t stream);
 
+/* activation.softmax_reg over the last dimension (ltr/models/layers/activation.py:7-16): x [n,L] -> out [n,L], with one extra
+ * constant logit `reg` in the denominator when has_reg != 0 (PrDiMP score pre-processing, pytracking/tracker/dimp/dimp.py:206-210). */
+int b200trk_softmax_reg(const float* x, float* out, int n, int L, int has_reg, float reg, b200trk_stream_t stream);
+
 /* dcf.max2d: pytracking/libs/dcf.py:156-164. a [n,H,W] -> max_val [n], max_idx [n,2] int64. */
 int b200trk_max2d(const float* a, int n, int H, int W, float* max_val, int64_t* max_idx, b200trk_stream_t stream);
 

@@ -50,6 +50,7 @@ SIGNATURES = {
     "b200trk_conv1x1": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "b200trk_feature_normalize": (_I, [_VP, _I, _I, _I, _I, _F, _VP]),
     "b200trk_fourier_interp": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
+    "b200trk_softmax_reg": (_I, [_VP, _VP, _I, _I, _I, _F, _VP]),
     "b200trk_max2d": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP]),
     "b200trk_dimp_sd_gn": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _I, _F, _F, _F, _F, _F,
                                 _VP, _VP, _VP]),

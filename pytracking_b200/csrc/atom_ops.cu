@@ -34,6 +34,29 @@ __global__ void feature_normalize_kernel(float* __restrict__ x, int per_sample, 
 }
 
 // --------------------------------------------------------------------------------------------------
+// softmax_reg over the last dimension with one extra constant logit in the denominator
+// (ltr/models/layers/activation.py:7-16; PrDiMP score pre-processing, pytracking/tracker/dimp/dimp.py:206-210)
+// --------------------------------------------------------------------------------------------------
+__global__ void softmax_reg_kernel(const float* __restrict__ x, float* __restrict__ y, int L, int has_reg, float reg) {
+    __shared__ float red[32];
+    const float* xr = x + (size_t)blockIdx.x * L;
+    float m = has_reg ? reg : -INFINITY;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) m = fmaxf(m, xr[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = red[0];
+    for (int w = 1; w < (int)(blockDim.x + 31) / 32; ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float s = 0.f;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) s += expf(xr[i] - m);
+    s = block_sum(s, red);
+    const float den = s + (has_reg ? expf(reg - m) : 0.f);
+    for (int i = threadIdx.x; i < L; i += blockDim.x) y[(size_t)blockIdx.x * L + i] = expf(xr[i] - m) / den;
+}
+
+// --------------------------------------------------------------------------------------------------
 // conv1x1 on NCHW: out[s,co,p] = sum_ci P[co,ci] x[s,ci,p].  CTA tile: 64 output channels x 64 pixels, K step 16.
 // --------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv1x1_kernel(const float* __restrict__ x, const float* __restrict__ P,
@@ -176,6 +199,14 @@ extern "C" int b200trk_fourier_interp(const float* scores, float* out, int S, in
     const size_t smem = (size_t)(H * W + FI_ROWS * W) * sizeof(float);
     fourier_interp_kernel<<<dim3((out_h + FI_ROWS - 1) / FI_ROWS, S), 256, smem, (cudaStream_t)stream>>>(
         scores, Dy, Dx, out, H, W, out_h, out_w, 1.0f / (float)(H * W));
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200trk_softmax_reg(const float* x, float* out, int n, int L, int has_reg, float reg, b200trk_stream_t stream) {
+    B200_REQUIRE(x && out, "softmax_reg: null pointer");
+    B200_REQUIRE(n > 0 && L > 0, "softmax_reg: empty input");
+    softmax_reg_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(x, out, L, has_reg ? 1 : 0, reg);
     B200_LAUNCH_CHECK();
     return 0;
 }

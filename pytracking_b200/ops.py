@@ -56,6 +56,17 @@ def apply_feat_transpose(feat, resid, k):
     return grad
 
 
+def softmax_reg(x, reg=None):
+    """activation.softmax_reg(x, dim=-1, reg): softmax over the last dimension with an optional extra constant logit."""
+    x = _dev(x, "x")
+    L = x.shape[-1]
+    n = x.numel() // L
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().b200trk_softmax_reg(_p(x), _p(out), n, L, 0 if reg is None else 1, 0.0 if reg is None else float(reg), _stream()),
+               "softmax_reg")
+    return out
+
+
 def max2d(a):
     """a [..., H, W] -> (max values [...], indices [..., 2]) with the reference's tie order."""
     a = _dev(a, "a")

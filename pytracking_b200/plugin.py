@@ -23,9 +23,15 @@ def apply_filter(feat, filter, dilation_factors=None):
         raise NotImplementedError("b200trk apply_filter: dilation / multiple filters are not on the CUDA path")
     num_images = feat.shape[0]
     num_sequences = feat.shape[1] if feat.dim() == 5 else 1
-    if num_sequences != 1 or filter.shape[0] != 1 or filter.shape[-1] != 4 or filter.shape[-2] != 4:
-        raise NotImplementedError("b200trk apply_filter: one sequence and a 4x4 filter per call")
+    if num_sequences != 1 or filter.shape[0] != 1:
+        raise NotImplementedError("b200trk apply_filter: one sequence per call")
     f = feat.reshape(num_images, *feat.shape[-3:])
+    if filter.shape[-1] == 1 and filter.shape[-2] == 1:
+        # _apply_filter_ksz1 (filter.py:60-88, the ToMP classifier): a matmul over the channels == a 1x1 convolution
+        scores = ops.conv1x1(f, filter.reshape(1, filter.shape[-3], 1, 1))
+        return scores.reshape(num_images, num_sequences, scores.shape[-2], scores.shape[-1])
+    if filter.shape[-1] != 4 or filter.shape[-2] != 4:
+        raise NotImplementedError("b200trk apply_filter: 4x4 or 1x1 filters")
     scores = ops.apply_filter(f, filter.reshape(1, *filter.shape[-3:]))
     return scores.reshape(num_images, num_sequences, scores.shape[-2], scores.shape[-1])
 
@@ -48,6 +54,13 @@ def apply_feat_transpose(feat, input, filter_ksz, training=True, groups=1):
 # ---------------------------------------------------------------------------------------------------------------
 # pytracking/libs/dcf.py, pytracking/libs/operation.py, pytracking/libs/fourier.py (ATOM)
 # ---------------------------------------------------------------------------------------------------------------
+def softmax_reg(x, dim, reg=None):
+    """ltr/models/layers/activation.py:7-16 (last dimension only)."""
+    if dim % x.dim() != x.dim() - 1:
+        raise NotImplementedError("b200trk softmax_reg: only the last dimension")
+    return ops.softmax_reg(x, reg)
+
+
 def max2d(a):
     """dcf.py:156-164 -> (max_val, argmax [.., 2] as (row, col))."""
     return ops.max2d(a)

@@ -547,3 +547,17 @@ def test_atom_tracker_trajectory_replay(golden_dir, ops):
         prev_filter = torch.from_numpy(g[k + "filter"]).cuda()
     assert worst_s < 1e-4 and worst_m < 1e-4 and worst_l < 6e-2 and worst_f < 6e-2, (worst_s, worst_m, worst_l, worst_f)
     eng.close()
+
+
+def test_small_stage2_ops(ops):
+    """softmax_reg (PrDiMP score pre-processing) and the 1x1 apply_filter path of the ToMP classifier."""
+    from oracle import dimp_oracle as O
+    from pytracking_b200 import plugin
+    g = torch.Generator().manual_seed(3)
+    s = torch.randn(5, 23 * 23, generator=g) * 3
+    assert _rel(ops.softmax_reg(s.cuda(), None), torch.softmax(s, -1)) < 1e-5
+    assert _rel(ops.softmax_reg(s.cuda(), -1.5), O.softmax_reg(s.reshape(5, 23, 23), -1.5).reshape(5, -1)) < 1e-5
+    feat = torch.randn(3, 1, 256, 18, 18, generator=g)
+    filt = torch.randn(1, 256, 1, 1, generator=g)
+    ref = torch.matmul(filt.reshape(1, 1, 1, 256), feat.reshape(1, 3, 256, -1)).reshape(3, 1, 18, 18)     # filter.py:82-88
+    assert _rel(plugin.apply_filter(feat.cuda(), filt.cuda()), ref) < 1e-5
