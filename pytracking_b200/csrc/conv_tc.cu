@@ -18,6 +18,7 @@
 // gridDim.z; partial tiles go to an L2-resident workspace and the last CTA of a tile reduces them in split order
 // (fixed order => bitwise deterministic).
 #include "net.cuh"
+#include "tc_ptx.cuh"
 #include <cuda.h>
 #include <cstdlib>
 #include <cstring>
@@ -26,10 +27,9 @@ namespace b200trk {
 
 constexpr int TC_BM = 128;          // UMMA M
 constexpr int TC_KB = 32;           // fp32 elements per 128-byte K block
-constexpr int TC_THREADS = 192;     // 6 warps
+constexpr int TC_THREADS = 192;     // 6 warps (CW = 4 converter/epilogue warps); CW = 8 -> 320 threads
 constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_EPI_PITCH = 36;    // floats per staged accumulator row (32 + 4: conflict-free 128-bit smem accesses)
-constexpr long long TC_WAIT_LIMIT_CLOCKS = 4000000000ll;    // ~2 s: a broken pipeline traps instead of hanging the GPU
 
 struct TcParams {
     CUtensorMap a_map, b_map;       // raw fp32 activations (4-D) and weights (2-D)
@@ -53,91 +53,6 @@ struct TcConv {
 };
 
 // ------------------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0, spins = 0;
-    long long t0 = 0;
-    while (true) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) break;
-        if ((++spins & 1023u) == 0) {
-            const long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > TC_WAIT_LIMIT_CLOCKS) __trap();
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], kind::tf32, single CTA
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// K-major, SWIZZLE_128B canonical layout: rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO), descriptor version 1
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
-    d |= (uint64_t)1 << 46;                 // version
-    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
-    return d;
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                 : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ unsigned long long gtimer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-__device__ __forceinline__ float4 tc_lo_trunc(const float4& x) {
-    return make_float4(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u),
-                       x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u),
-                       x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u),
-                       x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u));
-}
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = tf32_rna(x);
-    lo = tf32_rna(x - hi);
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------
 // bias + residual + ReLU on 4 consecutive channels of one pixel
@@ -148,7 +63,11 @@ __device__ __forceinline__ void tc_finish4(const TcParams& P, size_t off, const 
     *reinterpret_cast<float4*>(P.out_raw + off) = f;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
+// CW = number of converter / epilogue warps (4 or 8). With 8, warps w and w+4 share a TMEM lane quadrant and split the
+// accumulator columns (32-column chunks) between them; the converter work per thread halves.
+template <int CW>
+__global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
+    constexpr int CT = 32 * CW;        // converter / epilogue threads
     extern __shared__ uint8_t tc_smem_raw[];
     __shared__ __align__(8) uint64_t s_full[TC_MAX_STAGES];
     __shared__ __align__(8) uint64_t s_empty[TC_MAX_STAGES];
@@ -177,7 +96,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < P.stages; ++i) {
-            mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_empty[i]), 1); mbar_init(smem_u32(&s_ready[i]), 4);
+            mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_empty[i]), 1); mbar_init(smem_u32(&s_ready[i]), CW);
         }
         mbar_init(smem_u32(&s_tmem_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -253,7 +172,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // TMEM -> registers (thread = accumulator row) -> per-warp smem transpose -> lanes own (row, 4 channels), so
         // that every warp-level global access covers 4 rows x 128 contiguous bytes.
         const int q = warp & 3;                          // TMEM lane quadrant this warp may access
-        const int ew = warp - 2;                         // 0..3
+        const int ew = warp - 2;                         // 0..CW-1
+        const int chalf = ew >> 2;                       // which of the (CW / 4) column shares this warp takes
+        constexpr int CSH = CW / 4;
         const int tile_lin = blockIdx.y * gridDim.x + blockIdx.x;
         const int num_tiles = gridDim.x * gridDim.y;
         const int nchunks = P.BN / 32;
@@ -263,7 +184,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         //      Element-wise and position-preserving, so the 128-byte swizzle is irrelevant here.
         {
             uint8_t* sbase = tc_smem_raw + (smem_base - smem_u32(tc_smem_raw));
-            const int et = threadIdx.x - 64;                       // 0..127
+            const int et = threadIdx.x - 64;                       // 0..CT-1
+            constexpr int NA = 1024 / CT;                          // float4 of A per thread (8 or 4)
             const int a_v4 = (int)(a_tile / 16), b_v4 = (int)(b_tile / 16);
             for (int it = 0; it < nkb; ++it) {
                 const int st = it % P.stages;
@@ -276,33 +198,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 float4* b_lo = b_hi + b_v4;
                 // all loads of the stage are issued before the first store (the compiler must not serialise them
                 // behind the shared-memory stores): 8 float4 of A and up to 8 of B per thread
-                const int nb = b_v4 >> 7;                          // 4 (BN = 64) or 8 (BN = 128)
-                float4 xa[8], xb[8];
+                const int nb = b_v4 / CT;                          // float4 of B per thread: BN * 8 / CT
+                float4 xa[NA], xb[NA];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) xa[j] = a_hi[et + 128 * j];
+                for (int j = 0; j < NA; ++j) xa[j] = a_hi[et + CT * j];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) xb[j] = (j < nb) ? b_hi[et + 128 * j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < NA; ++j) xb[j] = (j < nb) ? b_hi[et + CT * j] : make_float4(0.f, 0.f, 0.f, 0.f);
                 if (P.split_mode == 2) {
                     // the TF32 datapath ignores the 13 low mantissa bits of an fp32 operand, so the raw tile already IS the
                     // hi operand (truncation split); only lo = x - trunc(x) (exact in fp32) has to be produced
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) a_lo[et + 128 * j] = tc_lo_trunc(xa[j]);
+                    for (int j = 0; j < NA; ++j) a_lo[et + CT * j] = tc_lo_trunc(xa[j]);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) if (j < nb) b_lo[et + 128 * j] = tc_lo_trunc(xb[j]);
+                    for (int j = 0; j < NA; ++j) if (j < nb) b_lo[et + CT * j] = tc_lo_trunc(xb[j]);
                 } else {
                     // explicit round-to-nearest split (cvt.rna.tf32.f32 on both parts): the checker for mode 2
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < NA; ++j) {
                         float4 h, l;
                         split_tf32(xa[j].x, h.x, l.x); split_tf32(xa[j].y, h.y, l.y); split_tf32(xa[j].z, h.z, l.z); split_tf32(xa[j].w, h.w, l.w);
-                        a_hi[et + 128 * j] = h; a_lo[et + 128 * j] = l;
+                        a_hi[et + CT * j] = h; a_lo[et + CT * j] = l;
                     }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < NA; ++j) {
                         if (j < nb) {
                             float4 h, l;
                             split_tf32(xb[j].x, h.x, l.x); split_tf32(xb[j].y, h.y, l.y); split_tf32(xb[j].z, h.z, l.z); split_tf32(xb[j].w, h.w, l.w);
-                            b_hi[et + 128 * j] = h; b_lo[et + 128 * j] = l;
+                            b_hi[et + CT * j] = h; b_lo[et + CT * j] = l;
                         }
                     }
                 }
@@ -327,7 +249,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 rvalid[i] = row < P.BW * P.BH && oy < P.Hout && ox < P.Wout;
                 roff[i] = (((size_t)s * P.Hout + oy) * P.Wout + ox) * P.Cout;
             }
-            for (int c = 0; c < nchunks; ++c) {
+            for (int c = chalf; c < nchunks; c += CSH) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
                 __syncwarp();
@@ -361,7 +283,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             // ---- split-K: partial tile -> L2 workspace (coalesced), tile-wide arrival counter, then EVERY split CTA
             //      reduces its share of the tile rows in split order (fixed order => deterministic) ----
             float* wsp = P.ws + ((size_t)blockIdx.z * num_tiles + tile_lin) * TC_BM * P.BN;
-            for (int c = 0; c < nchunks; ++c) {
+            for (int c = chalf; c < nchunks; c += CSH) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
                 __syncwarp();
@@ -379,7 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 }
             }
             __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
             if (threadIdx.x == 64) {
                 atomicAdd(&P.counters[2 * tile_lin], 1u);
                 long long t0 = clock64();
@@ -388,9 +310,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 __threadfence();
                 if (dbg) dbg[5] = gtimer();                           // all splits of the tile arrived
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
             // row groups (4 rows each, 32 per tile) are dealt round-robin to (split, warp)
-            for (int g = blockIdx.z + P.splits * ew; g < 32; g += P.splits * 4) {
+            for (int g = blockIdx.z + P.splits * ew; g < 32; g += P.splits * CW) {
                 const int row = g * 4 + lrow;
                 const int ly = row / P.BW, lx = row - ly * P.BW;
                 const int oy = th * P.BH + ly, ox = tw * P.BW + lx;
@@ -415,7 +337,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     tc_finish4(P, obase + n, bias, res, f);
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
             if (threadIdx.x == 64) {
                 // the last split CTA to finish its share re-arms both counters for the next launch
                 if (atomicAdd(&P.counters[2 * tile_lin + 1], 1u) == (unsigned)(P.splits - 1)) {
@@ -465,6 +387,20 @@ bool tc_conv_supported(const Op& op) {
     if (op.stride == 2 && !env_int("B200TRK_TC_STRIDE2", 1)) return false;
     if (op.stride != 1 && op.stride != 2) return false;
     return env_int("B200TRK_TC", 1) != 0;
+}
+
+int tc_make_map(CUtensorMap* m, float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+    EncodeTiledFn enc = get_encode_fn();
+    B200_REQUIRE(enc, "tc_make_map: cuTensorMapEncodeTiled not available from the driver");
+    B200_REQUIRE(rank >= 2 && rank <= 4, "tc_make_map: rank %d", rank);
+    cuuint64_t d[4]; cuuint64_t s[3]; cuuint32_t bx[4]; cuuint32_t es[4] = {1, 1, 1, 1};
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, base, d, s, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, "tc_make_map: cuTensorMapEncodeTiled(rank %d, dims %llu x %llu) failed: %d", rank,
+                 (unsigned long long)dims[0], (unsigned long long)dims[1], (int)r);
+    return 0;
 }
 
 static int make_map_2d(CUtensorMap* m, float* base, uint64_t K, uint64_t N, uint32_t boxN) {
@@ -588,21 +524,24 @@ int tc_conv_launch(b200trk_net* net, const Op& op, int S, cudaStream_t st) {
     const uint32_t stage_bytes = 2u * TC_BM * 128u + 2u * P.b_bytes;
     size_t smem = (size_t)P.stages * stage_bytes + 1024;
     if (smem < 64 * 1024) smem = 64 * 1024;       // the epilogue stages 4 x 32 x 36 floats in the (idle) pipeline buffers
+    static const int cw = env_int("B200TRK_TC_CW", 8) == 4 ? 4 : 8;
     static bool attr = false;
     if (!attr) {
-        B200_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        B200_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        B200_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr = true;
     }
     dim3 grid(P.tiles_w * P.tiles_h * S, op.Cout / P.BN, P.splits);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = grid; cfg.blockDim = dim3(64 + 32 * cw); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     static const int use_pdl = env_int("B200TRK_TC_PDL", 1);
     cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
-    B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, P));
+    if (cw == 4) B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<4>, P));
+    else B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<8>, P));
     B200_LAUNCH_CHECK();
     return 0;
 }

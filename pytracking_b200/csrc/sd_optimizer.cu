@@ -16,44 +16,10 @@
 //   qpart [n][NCH][NPOS] partial A g maps    -> barrier 2 -> each CTA sums its own samples over the chunks
 //   hpart [NG], gnorm [NCH] scalars          -> barrier 3 -> step length alpha
 #include "corr2.cuh"
+#include "sd_common.cuh"
 #include <cstdlib>
 
 namespace b200trk {
-
-constexpr int SD_SPC_MAX = 8;    // samples per CTA held in shared memory
-
-struct SdParams {
-    const float* w_in; float* w_out; const float* feat; const float* bb; const float* sample_weight;
-    int n, C, passes, NCH, NG, num_iter, spc_max, dbg_mode;
-    // DiMP
-    const float* label_lut; const float* mask_lut; const float* spatial_lut; int num_bins; float inv_bin_disp;
-    // PrDiMP
-    float gauss_sigma; int has_softmax_reg; float softmax_reg; float label_threshold; int normalize_label;
-    float label_shrink; float uni_weight;
-    // GNSteepestDescent + LinearFilterHinge (MODE 3)
-    const float* label_in; float act_leak; int act_kind; float act_b; float loss_scale;
-    // common
-    float inv_feat_stride, step_length, reg_weight, alpha_eps;
-    float* iterates_out; float* losses_out;
-    // workspace
-    float* gpart; float* qpart; float* hpart; float* gnorm; float* lossr; float* lossw; unsigned* barrier;
-    unsigned long long* trace;     // optional [64] phase stamps of CTA 0 (globaltimer ns)
-};
-
-__device__ __forceinline__ unsigned long long sd_gtimer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-#define SD_STAMP(k) do { if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && (k) < 64) P.trace[(k)] = sd_gtimer(); } while (0)
-
-__device__ __forceinline__ float lut_lerp(const float* lut, int nb, float rho) {
-    // DistanceMap + 1x1 conv == piece-wise linear LUT with last-bin clamp (distance.py:33-37)
-    if (rho >= (float)(nb - 1)) return lut[nb - 1];
-    const int b = (int)rho;                 // rho >= 0
-    const float f = rho - (float)b;
-    return lut[b] * (1.f - f) + lut[b + 1] * f;
-}
 
 template <int FS, int NST, int MODE>
 __global__ void __launch_bounds__(Corr2<FS>::NCONS, 1)
@@ -369,17 +335,36 @@ template <int FS, int MODE>
 static int launch_sd(SdParams P, cudaStream_t st) {
     using K = Corr2<FS>;
     constexpr int SLOTS = K::SLOTS;
-    int passes = 0;
-    for (int p = 4; p >= 1; p >>= 1) if (P.C % (SLOTS * p) == 0) { passes = p; break; }
-    B200_REQUIRE(passes > 0, "sd optimizer: C=%d must be a multiple of %d", P.C, SLOTS);
+    {
+        // tensor-core sweeps first (sd_tc.cu); shapes it does not claim fall through to the CUDA-core kernel below
+        int handled = 0;
+        if (int e = launch_sd_tc<FS, MODE>(P, st, &handled)) return e;
+        if (handled) return 0;
+    }
+    // Decomposition: passes x 16 channels per CTA (NCH chunks) x NG sample groups. The sweep time is set by the busiest CTA,
+    // ceil(n / NG) * passes items, so every admissible `passes` is scored (n = 50 on 148 SMs: 4 passes -> 8 items, 2 -> 6).
     const int sms = device_sm_count();
-    int NCH = P.C / (SLOTS * passes);
-    // keep the grid within one wave (cooperative launch) but use as many SMs as possible
-    while (NCH > sms && passes < 64 && P.C % (SLOTS * passes * 2) == 0) { passes *= 2; NCH /= 2; }
-    B200_REQUIRE(NCH <= sms, "sd optimizer: C=%d needs %d channel chunks > %d SMs", P.C, NCH, sms);
-    int NG = sms / NCH; if (NG > P.n) NG = P.n; if (NG < 1) NG = 1;
-    const int spc = (P.n + NG - 1) / NG;
-    B200_REQUIRE(spc <= SD_SPC_MAX, "sd optimizer: n=%d samples need %d samples per CTA (max %d)", P.n, spc, SD_SPC_MAX);
+    const size_t limit = 227 * 1024 - 512;
+    const size_t item = (size_t)K::ITEM_FLOATS * sizeof(float);
+    const int forced = [] { const char* v = getenv("B200TRK_SD_PASSES"); return v ? atoi(v) : 0; }();
+    int passes = 0, NCH = 0, NG = 0, spc = 0, best_cost = 1 << 30;
+    for (int p = 64; p >= 1; p >>= 1) {
+        if (P.C % (SLOTS * p) != 0) continue;
+        if (forced && p != forced) continue;
+        const int nch = P.C / (SLOTS * p);
+        if (nch > sms) continue;
+        int ng = sms / nch; if (ng > P.n) ng = P.n; if (ng < 1) ng = 1;
+        const int sp = (P.n + ng - 1) / ng;
+        if (sp > SD_SPC_MAX) continue;
+        const size_t fx = (size_t)(K::NT * SLOTS * K::RED_STRIDE + 2 * p * SLOTS * K::VEC_STRIDE + sp * (5 * K::NPOS + K::PMAP)) * sizeof(float);
+        if (fx + 2 * item > limit) continue;
+        int cost = sp * p * 4;
+        if (fx + 3 * item > limit) cost += cost / 2;        // a 2-stage pipeline exposes the copy latency
+        if (p > 4) cost += 1;                               // prefer <= 4 passes at equal balance (fewer partial-gradient rows)
+        if (cost < best_cost) { best_cost = cost; passes = p; NCH = nch; NG = ng; spc = sp; }
+    }
+    B200_REQUIRE(passes > 0, "sd optimizer: no decomposition for C=%d, n=%d (C must be a multiple of %d, at most %d samples per CTA)",
+                 P.C, P.n, SLOTS, SD_SPC_MAX);
     B200_REQUIRE(P.num_iter + 1 <= K::NCONS, "sd optimizer: num_iter=%d too large", P.num_iter);
     P.passes = passes; P.NCH = NCH; P.NG = NG; P.spc_max = spc;
     { const char* v = getenv("B200TRK_SD_DBG"); P.dbg_mode = v ? atoi(v) : 0; }
@@ -402,8 +387,6 @@ static int launch_sd(SdParams P, cudaStream_t st) {
 
     const int cchunk = passes * SLOTS;
     const size_t fixed = (size_t)(K::NT * SLOTS * K::RED_STRIDE + 2 * cchunk * K::VEC_STRIDE + spc * (5 * K::NPOS + K::PMAP)) * sizeof(float);
-    const size_t limit = 227 * 1024 - 512;
-    const size_t item = (size_t)K::ITEM_FLOATS * sizeof(float);
     if (fixed + 4 * item <= limit) return launch_sd_nst<FS, 4, MODE>(P, fixed + 4 * item, st);
     if (fixed + 3 * item <= limit) return launch_sd_nst<FS, 3, MODE>(P, fixed + 3 * item, st);
     B200_REQUIRE(fixed + 2 * item <= limit, "sd optimizer: %d samples per CTA do not fit in shared memory", spc);

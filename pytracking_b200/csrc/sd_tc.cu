@@ -1,0 +1,778 @@
+// Stage 3 on the tensor cores: the steepest-descent optimisers (same four modes and the same algebra as sd_optimizer.cu)
+// with both sweeps over the sample memory issued as tcgen05 GEMMs with a 16-wide N (the 16 filter taps):
+//
+//   adjoint sweep   g[c, tap]  = sum_{i, p} X_i[c, p] * R_i[p, tap]        R_i[p, tap] = r_i[p shifted by the tap]   (A^T r)
+//       A = X_i[128 channels x 32 pixels]  (K-major straight from the [n, C, H*W] sample memory, TMA box)
+//       B = R_i^T[16 taps x 32 pixels]      (gathered from the residual map in shared memory by the converter warps)
+//   apply sweep     T_i[p, tap] = sum_c X_i[p, c] * F[c, tap] ;  s_i[y, x] = sum_tap T_i[(y, x) shifted by the tap, tap]   (A f)
+//       A = X_i[128 pixels x 32 channels]  (K-major from an [n, H*W, C] copy of the sample memory made once per call)
+//       B = F^T[16 taps x 32 channels]      (the filter / gradient, resident in shared memory for the whole sweep)
+//
+// fp32 fidelity as in conv_tc.cu: every operand is split x = hi + lo with hi = the TF32 truncation the datapath applies anyway,
+// three MMAs per K step (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi) into one fp32 TMEM accumulator.
+//
+// Work decomposition: a "unit" is one 128 x 32 operand tile (16 KB of sample memory). The units of a sweep are numbered
+// (adjoint: chunk, sample, pixel block; apply: sample, pixel tile, channel block) and CTA b of G takes the contiguous range
+// [floor(b U / G), floor((b+1) U / G)) - every SM streams the same number of bytes (+-1 tile) whatever n and C are.
+// Everything that crosses CTAs goes through L2 with a fixed summation order (bitwise deterministic):
+//   gpart  [G][chunks][128][16]  per-CTA partial gradients -> barrier -> each CTA reduces a 1/G slice of the C*16 entries,
+//   gfinal [C*16]                the full gradient          -> barrier -> every CTA rebuilds F^T from it,
+//   qslots [units][19*19]        shift-added partial A g maps of every apply segment -> barrier -> summed per sample,
+//   gnpart / hpart [G]           |g|^2 and curvature partials -> barrier -> step length.
+// Per-sample state (scores, labels, residual maps) is REPLICATED in every CTA whose adjoint range touches the sample (at most
+// `smax`); the replicas evolve identically because all of them read the same partials in the same order; loss / curvature
+// terms are contributed by the sample's owner (the CTA holding its first unit) only.
+//
+// Warp roles during a sweep: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 = operand converters (lo parts, R^T tiles)
+// and epilogue (TMEM -> registers -> partials). All 320 threads run the element-wise phases between the sweeps.
+#include "tc_ptx.cuh"
+#include "sd_common.cuh"
+#include <cstdlib>
+#include <cstring>
+
+namespace b200trk {
+
+constexpr int STC_THREADS = 320;
+constexpr int STC_CT = 256;                 // converter / epilogue threads (warps 2..9)
+constexpr int STC_NSTG = 3;
+constexpr int STC_A_BYTES = 16384;          // 128 rows x 128 B
+constexpr int STC_STAGE_BYTES = 36864;      // A_hi | A_lo | B_hi (2 KB) | B_lo (2 KB)
+constexpr int STC_MAXCH = 4;                // 128-channel chunks (C <= 512)
+constexpr int STC_TT_PITCH = 132;
+constexpr int STC_QL_MAX = 64;              // apply segments of one sample (<= pixel tiles x channel blocks)
+
+struct SdTcParams {
+    SdParams p;
+    CUtensorMap map_t;      // [n][C][H*W]  as {pixel, channel, sample}
+    CUtensorMap map_a;      // [n][H*W][C]  as {channel, pixel, sample}
+    float* gpart; float* gfinal; float* gnpart; float* qslots; float* hpart; float* lossr; float* lossw;
+    unsigned* barrier;
+    int smax, nchk, kba, slice_max;
+};
+
+__device__ __forceinline__ int part_lo(long long U, int G, int b) { return (int)((U * (long long)b) / G); }
+__device__ __forceinline__ int part_owner(long long U, int G, int u) { return (int)((((long long)u + 1) * G - 1) / U); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float lo_trunc(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// byte offset of element (row, k) inside a K-major SWIZZLE_128B tile of 128-byte rows (tile base 1024-byte aligned)
+__device__ __forceinline__ uint32_t sw128(int row, int k) {
+    return (uint32_t)(row * 128 + ((((k >> 2) ^ (row & 7)) << 4) | ((k & 3) << 2)));
+}
+__device__ __forceinline__ float warp_sum_xor(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int FS, int MODE>
+__global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_constant__ SdTcParams Q) {
+    const SdParams& P = Q.p;
+    constexpr int OS = FS + 1, NPOS = OS * OS, NPX = FS * FS;
+    constexpr int KBT = (NPX + 31) / 32;          // pixel blocks of the adjoint sweep (11 / 16)
+    constexpr int NPT = (NPX + 127) / 128;        // pixel tiles of the apply sweep (3 / 4)
+    constexpr int NTH = STC_THREADS;
+    extern __shared__ uint8_t stc_raw[];
+    __shared__ __align__(8) uint64_t s_full[STC_NSTG];
+    __shared__ __align__(8) uint64_t s_empty[STC_NSTG];
+    __shared__ __align__(8) uint64_t s_ready[STC_NSTG];
+    __shared__ __align__(8) uint64_t s_acc;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_red[32];
+    __shared__ float s_scal[4];
+    __shared__ int s_state[16];        // sample ids of the state slots
+    __shared__ int s_owned[16];
+    __shared__ float s_sw[16];
+    __shared__ int s_ns;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x, b = blockIdx.x;
+    const int n = P.n, C = P.C, kba = Q.kba, nchk = Q.nchk;
+    const long long UT = (long long)nchk * n * KBT;
+    const long long UA = (long long)n * NPT * kba;
+    const int t_lo = part_lo(UT, G, b), t_hi = part_lo(UT, G, b + 1);
+    const int a_lo = part_lo(UA, G, b), a_hi = part_lo(UA, G, b + 1);
+    const int E4 = C * 4;                                             // float4 entries of the filter
+    const int sl_lo = part_lo(E4, G, b), sl_hi = part_lo(E4, G, b + 1);
+    const float reg = P.reg_weight;
+
+    // ---- shared memory carve-up ----------------------------------------------------------------------------------------
+    uint8_t* base = stc_raw + ((1024u - (smem_u32(stc_raw) & 1023u)) & 1023u);
+    const uint32_t base_u32 = smem_u32(base);
+    uint8_t* ftb = base + STC_NSTG * STC_STAGE_BYTES;                 // F^T: [kba][hi 2 KB | lo 2 KB]
+    float* Tt = reinterpret_cast<float*>(ftb + (size_t)kba * 4096);   // [16][STC_TT_PITCH] apply-epilogue staging
+    float4* wsl = reinterpret_cast<float4*>(Tt + 16 * STC_TT_PITCH);  // filter slice owned by this CTA
+    float4* gsl = wsl + Q.slice_max;                                  // gradient slice
+    float* sS = reinterpret_cast<float*>(gsl + Q.slice_max);          // [smax][NPOS] scores
+    float* sY = sS + Q.smax * NPOS;
+    float* sM = sY + Q.smax * NPOS;
+    float* sV = sM + Q.smax * NPOS;
+    float* sQ = sV + Q.smax * NPOS;
+    float* sT = sQ + Q.smax * NPOS;                                   // mapped residual (the adjoint sweep's B operand source)
+    int* qlist = reinterpret_cast<int*>(sT + Q.smax * NPOS);          // [smax][STC_QL_MAX] valid apply-segment slots per sample
+    int* qn = qlist + Q.smax * STC_QL_MAX;                            // [smax]
+
+    SD_STAMP(0);
+    // ---- prologue ------------------------------------------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int i = 0; i < STC_NSTG; ++i) {
+            mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_empty[i]), 1); mbar_init(smem_u32(&s_ready[i]), STC_CT / 32);
+        }
+        mbar_init(smem_u32(&s_acc), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // state slots: the samples of this CTA's adjoint range (runs of KBT units per (chunk, sample))
+        int ns = 0;
+        for (int u = t_lo; u < t_hi; u = (u / KBT + 1) * KBT) {
+            const int smp = (u / KBT) % n;
+            bool have = false;
+            for (int j = 0; j < ns; ++j) have |= (s_state[j] == smp);
+            if (!have && ns < Q.smax) {
+                s_state[ns] = smp;
+                s_owned[ns] = (smp * KBT >= t_lo && smp * KBT < t_hi) ? 1 : 0;     // unit (chunk 0, smp, block 0)
+                s_sw[ns] = P.sample_weight ? P.sample_weight[smp] : 1.0f / (float)n;
+                ++ns;
+            }
+        }
+        s_ns = ns;
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(64u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&Q.map_t) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&Q.map_a) : "memory");
+    }
+    for (int e = sl_lo + tid; e < sl_hi; e += NTH) wsl[e - sl_lo] = reinterpret_cast<const float4*>(P.w_in)[e];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const int ns = s_ns;
+
+    // valid apply-segment slots of every state sample: a segment starts at channel block 0 of a (sample, pixel tile) run and at
+    // every CTA range boundary inside it (static for the whole call)
+    for (int j = warp; j < ns; j += NTH / 32) {
+        const int smp = s_state[j];
+        int cnt = 0;
+        for (int r0 = 0; r0 < NPT * kba; r0 += 32) {
+            const int r = r0 + lane;
+            bool valid = false;
+            if (r < NPT * kba) {
+                const int u = smp * NPT * kba + r;
+                valid = (r % kba == 0) || (part_lo(UA, G, part_owner(UA, G, u)) == u);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, valid);
+            if (valid) qlist[j * STC_QL_MAX + cnt + __popc(m & ((1u << lane) - 1u))] = smp * NPT * kba + r;
+            cnt += __popc(m);
+        }
+        if (lane == 0) qn[j] = cnt;
+    }
+
+    // label maps of the state samples
+    for (int j = 0; j < ns; ++j) {
+        const int i = s_state[j];
+        const float bx = P.bb[4 * i], by = P.bb[4 * i + 1], bw = P.bb[4 * i + 2], bh = P.bb[4 * i + 3];
+        const float crow = (by + bh / 2.f) * P.inv_feat_stride;        // optimizer.py:112-113 (even filter: no half-cell offset)
+        const float ccol = (bx + bw / 2.f) * P.inv_feat_stride;
+        if (MODE == 0) {
+            const float sqsw = sqrtf(s_sw[j]);
+            for (int pos = tid; pos < NPOS; pos += NTH) {
+                const float d0 = (float)(pos / OS) - crow, d1 = (float)(pos % OS) - ccol;
+                const float rho = sqrtf(d0 * d0 + d1 * d1) * P.inv_bin_disp;
+                sY[j * NPOS + pos] = lut_lerp(P.label_lut, P.num_bins, rho);
+                sM[j * NPOS + pos] = 1.f / (1.f + expf(-lut_lerp(P.mask_lut, P.num_bins, rho)));
+                sV[j * NPOS + pos] = sqsw * lut_lerp(P.spatial_lut, P.num_bins, rho);
+            }
+        } else if (MODE == 3) {
+            const float sqsw = sqrtf(s_sw[j]);
+            for (int pos = tid; pos < NPOS; pos += NTH) {
+                const float lab = P.label_in[(size_t)i * NPOS + pos];
+                const float m = fminf(((lab > P.label_threshold) ? 1.f : 0.f) + P.act_leak, 1.f);
+                sY[j * NPOS + pos] = m * lab;
+                sM[j * NPOS + pos] = m;
+                sV[j * NPOS + pos] = sqsw;
+            }
+        } else if (MODE == 2) {
+            const float c = -1.0f / (2.f * P.gauss_sigma * P.gauss_sigma);
+            const float sqsw = sqrtf(s_sw[j]);
+            for (int pos = tid; pos < NPOS; pos += NTH) {
+                const float d0 = (float)(pos / OS) - crow, d1 = (float)(pos % OS) - ccol;
+                const float gss = expf(c * d0 * d0) * expf(c * d1 * d1);
+                const float m = (gss > P.label_threshold) ? 1.f : 0.f;
+                sY[j * NPOS + pos] = gss * m;
+                sM[j * NPOS + pos] = m;
+                sV[j * NPOS + pos] = sqsw;
+            }
+        } else {
+            const float c = -1.0f / (2.f * P.gauss_sigma * P.gauss_sigma);
+            const float nrm = 1.f / (2.f * 3.14159265358979323846f * P.gauss_sigma * P.gauss_sigma);
+            float loc = 0.f;
+            for (int pos = tid; pos < NPOS; pos += NTH) {
+                const float d0 = (float)(pos / OS) - crow, d1 = (float)(pos % OS) - ccol;
+                float gss = (expf(c * d0 * d0) * nrm) * expf(c * d1 * d1);
+                gss = (gss > P.label_threshold) ? gss : 0.f;
+                sY[j * NPOS + pos] = gss;
+                loc += gss;
+            }
+            const float tot = block_sum(loc, s_red);
+            const float inv = P.normalize_label ? 1.f / (tot + 1e-8f) : 1.f;
+            for (int pos = tid; pos < NPOS; pos += NTH)
+                sY[j * NPOS + pos] = (1.f - P.label_shrink) *
+                                     ((1.f - P.uni_weight) * (sY[j * NPOS + pos] * inv) + P.uni_weight / (float)NPOS);
+        }
+    }
+
+    // ---- helpers -------------------------------------------------------------------------------------------------------------
+    uint32_t ucount = 0, acount = 0;    // units / accumulator commits so far (identical in every thread)
+    unsigned epoch = 0;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const int q = warp & 3, half = (warp - 2) >> 2;                  // converter warps: TMEM lane quadrant, column half
+    const int ct = tid - 64;
+
+    // F^T (hi | lo) of all channel blocks from a [C][16] vector in global memory
+    auto build_ft = [&](const float* src) {
+        for (int idx = tid; idx < C * 16; idx += NTH) {
+            const int c = idx >> 4, tap = idx & 15;
+            const float v = __ldcg(src + idx);
+            uint8_t* t = ftb + (size_t)(c >> 5) * 4096 + sw128(tap, c & 31);
+            *reinterpret_cast<float*>(t) = v;
+            *reinterpret_cast<float*>(t + 2048) = lo_trunc(v);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+    };
+
+    // apply sweep: qslots[segment] = shift-added partial map of every (sample, pixel tile) segment of this CTA's range
+    auto sweep_apply = [&]() {
+        const int nun = a_hi - a_lo;
+        int nseg = 0;
+        for (int i = 0; i < nun; ++i) { const int kb = (a_lo + i) % kba; nseg += (i == 0 || kb == 0) ? 1 : 0; }
+        if (nun > 0) {
+            if (warp == 0) {
+                if (lane == 0) {
+                    for (int i = 0; i < nun; ++i) {
+                        const int u = a_lo + i;
+                        const int smp = u / (NPT * kba), r = u - smp * (NPT * kba), pt = r / kba, kb = r - pt * kba;
+                        const uint32_t st = (ucount + i) % STC_NSTG, ph = ((ucount + i) / STC_NSTG) & 1u;
+                        mbar_wait(smem_u32(&s_empty[st]), ph ^ 1u);
+                        const uint32_t full = smem_u32(&s_full[st]);
+                        mbar_expect_tx(full, STC_A_BYTES);
+                        tma_load_3d(base_u32 + st * STC_STAGE_BYTES, &Q.map_a, full, kb * 32, pt * 128, smp);
+                    }
+                }
+            } else if (warp == 1) {
+                if (lane == 0) {
+                    for (int i = 0; i < nun; ++i) {
+                        const int u = a_lo + i;
+                        const int kb = u % kba;
+                        const bool seg_first = (i == 0 || kb == 0), seg_last = (i == nun - 1 || kb == kba - 1);
+                        const uint32_t st = (ucount + i) % STC_NSTG, ph = ((ucount + i) / STC_NSTG) & 1u;
+                        mbar_wait(smem_u32(&s_ready[st]), ph);
+                        tc_fence_after();
+                        const uint32_t sa = base_u32 + st * STC_STAGE_BYTES;
+                        const uint32_t fb = smem_u32(ftb) + (uint32_t)kb * 4096u;
+                        const uint64_t d_ah = make_smem_desc(sa), d_al = make_smem_desc(sa + STC_A_BYTES);
+                        const uint64_t d_bh = make_smem_desc(fb), d_bl = make_smem_desc(fb + 2048u);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                            tc_mma_tf32(tmem, d_al + adv, d_bh + adv, idesc, (seg_first && k == 0) ? 0u : 1u);
+                            tc_mma_tf32(tmem, d_ah + adv, d_bl + adv, idesc, 1u);
+                            tc_mma_tf32(tmem, d_ah + adv, d_bh + adv, idesc, 1u);
+                        }
+                        tc_commit(smem_u32(&s_empty[st]));
+                        if (seg_last) tc_commit(smem_u32(&s_acc));
+                    }
+                }
+            } else {
+                int seg = 0, kb_first = 0;
+                for (int i = 0; i < nun; ++i) {
+                    const int u = a_lo + i;
+                    const int smp = u / (NPT * kba), r = u - smp * (NPT * kba), pt = r / kba, kb = r - pt * kba;
+                    const bool seg_first = (i == 0 || kb == 0), seg_last = (i == nun - 1 || kb == kba - 1);
+                    if (seg_first) kb_first = kb;
+                    const uint32_t st = (ucount + i) % STC_NSTG, ph = ((ucount + i) / STC_NSTG) & 1u;
+                    mbar_wait(smem_u32(&s_full[st]), ph);
+                    float4* ahi = reinterpret_cast<float4*>(base + (size_t)st * STC_STAGE_BYTES);
+                    float4* alo = ahi + STC_A_BYTES / 16;
+                    float4 xa[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) xa[j] = ahi[ct + STC_CT * j];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) alo[ct + STC_CT * j] = tc_lo_trunc(xa[j]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_ready[st])) : "memory");
+                    if (seg_last) {
+                        // T[p][tap] of the finished segment: TMEM -> Tt[tap][p] -> shift-add over the taps -> qslots
+                        mbar_wait(smem_u32(&s_acc), (acount + seg) & 1u);
+                        tc_fence_after();
+                        uint32_t v[8];
+                        tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 8), v);
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) Tt[(half * 8 + t) * STC_TT_PITCH + q * 32 + lane] = __uint_as_float(v[t]);
+                        tc_fence_before();
+                        asm volatile("bar.sync 1, %0;" ::"n"(STC_CT) : "memory");
+                        float* dst = Q.qslots + ((size_t)(smp * NPT + pt) * kba + kb_first) * NPOS;
+                        for (int o = ct; o < NPOS; o += STC_CT) {
+                            const int oy = o / OS, ox = o - oy * OS;
+                            float acc = 0.f;
+#pragma unroll
+                            for (int tap = 0; tap < 16; ++tap) {
+                                const int iy = oy + (tap >> 2) - 2, ix = ox + (tap & 3) - 2;
+                                const int p = iy * FS + ix - pt * 128;
+                                if (iy >= 0 && iy < FS && ix >= 0 && ix < FS && p >= 0 && p < 128) acc += Tt[tap * STC_TT_PITCH + p];
+                            }
+                            __stcg(dst + o, acc);
+                        }
+                        asm volatile("bar.sync 1, %0;" ::"n"(STC_CT) : "memory");
+                        ++seg;
+                    }
+                }
+            }
+        }
+        ucount += (uint32_t)nun;
+        acount += (uint32_t)nseg;
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    };
+
+    // adjoint sweep: gpart[b][local chunk][128][16] = partial gradient of this CTA's range
+    auto sweep_adjoint = [&]() {
+        const int nun = t_hi - t_lo;
+        const int per_chunk = n * KBT;
+        if (nun > 0) {
+            const int chunk0 = t_lo / per_chunk;
+            if (warp == 0) {
+                if (lane == 0) {
+                    for (int i = 0; i < nun; ++i) {
+                        const int u = t_lo + i;
+                        const int chunk = u / per_chunk, r = u - chunk * per_chunk, smp = r / KBT, kb = r - smp * KBT;
+                        const uint32_t st = (ucount + i) % STC_NSTG, ph = ((ucount + i) / STC_NSTG) & 1u;
+                        mbar_wait(smem_u32(&s_empty[st]), ph ^ 1u);
+                        const uint32_t full = smem_u32(&s_full[st]);
+                        mbar_expect_tx(full, STC_A_BYTES);
+                        tma_load_3d(base_u32 + st * STC_STAGE_BYTES, &Q.map_t, full, kb * 32, chunk * 128, smp);
+                    }
+                }
+            } else if (warp == 1) {
+                if (lane == 0) {
+                    uint32_t touched = 0;
+                    for (int i = 0; i < nun; ++i) {
+                        const int u = t_lo + i;
+                        const int cl = u / per_chunk - chunk0;
+                        const uint32_t st = (ucount + i) % STC_NSTG, ph = ((ucount + i) / STC_NSTG) & 1u;
+                        mbar_wait(smem_u32(&s_ready[st]), ph);
+                        tc_fence_after();
+                        const uint32_t sa = base_u32 + st * STC_STAGE_BYTES;
+                        const uint64_t d_ah = make_smem_desc(sa), d_al = make_smem_desc(sa + STC_A_BYTES);
+                        const uint64_t d_bh = make_smem_desc(sa + 2 * STC_A_BYTES), d_bl = make_smem_desc(sa + 2 * STC_A_BYTES + 2048);
+                        const uint32_t acc = tmem + (uint32_t)(cl * 16);
+                        const bool first = ((touched >> cl) & 1u) == 0u;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                            tc_mma_tf32(acc, d_al + adv, d_bh + adv, idesc, (first && k == 0) ? 0u : 1u);
+                            tc_mma_tf32(acc, d_ah + adv, d_bl + adv, idesc, 1u);
+                            tc_mma_tf32(acc, d_ah + adv, d_bh + adv, idesc, 1u);
+                        }
+                        touched |= 1u << cl;
+                        tc_commit(smem_u32(&s_empty[st]));
+                    }
+                    tc_commit(smem_u32(&s_acc));
+                }
+            } else {
+                const int tap = ct >> 4, kk0 = (ct & 15) * 2;          // this thread's two R^T elements: (tap, kk0), (tap, kk0 + 1)
+                const int dy = tap >> 2, dx = tap & 3;
+                const uint32_t boff = sw128(tap, kk0);
+                for (int i = 0; i < nun; ++i) {
+                    const int u = t_lo + i;
+                    const int chunk = u / per_chunk, r = u - chunk * per_chunk, smp = r / KBT, kb = r - smp * KBT;
+                    int j = 0;
+                    for (int jj = 1; jj < ns; ++jj) j = (s_state[jj] == smp) ? jj : j;
+                    // R^T values first (they do not depend on the TMA data)
+                    float rv[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int px = kb * 32 + kk0 + h;
+                        const int iy = px / FS, ix = px - iy * FS;
+                        const int oy = iy - dy + 2, ox = ix - dx + 2;
+                        rv[h] = (px < NPX && oy >= 0 && oy < OS && ox >= 0 && ox < OS) ? sT[j * NPOS + oy * OS + ox] : 0.f;
+                    }
+                    const uint32_t st = (ucount + i) % STC_NSTG, ph = ((ucount + i) / STC_NSTG) & 1u;
+                    mbar_wait(smem_u32(&s_full[st]), ph);
+                    uint8_t* sb = base + (size_t)st * STC_STAGE_BYTES;
+                    float4* ahi = reinterpret_cast<float4*>(sb);
+                    float4* alo = ahi + STC_A_BYTES / 16;
+                    float4 xa[4];
+#pragma unroll
+                    for (int jx = 0; jx < 4; ++jx) xa[jx] = ahi[ct + STC_CT * jx];
+#pragma unroll
+                    for (int jx = 0; jx < 4; ++jx) alo[ct + STC_CT * jx] = tc_lo_trunc(xa[jx]);
+                    *reinterpret_cast<float2*>(sb + 2 * STC_A_BYTES + boff) = make_float2(rv[0], rv[1]);
+                    *reinterpret_cast<float2*>(sb + 2 * STC_A_BYTES + 2048 + boff) = make_float2(lo_trunc(rv[0]), lo_trunc(rv[1]));
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_ready[st])) : "memory");
+                }
+                mbar_wait(smem_u32(&s_acc), acount & 1u);
+                tc_fence_after();
+                const int ncl = (t_hi - 1) / per_chunk - chunk0 + 1;
+                for (int cl = 0; cl < ncl; ++cl) {
+                    uint32_t v[8];
+                    tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cl * 16 + half * 8), v);
+                    float* dst = Q.gpart + (((size_t)b * STC_MAXCH + cl) * 128 + q * 32 + lane) * 16 + half * 8;
+                    __stcg(reinterpret_cast<float4*>(dst), make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])));
+                    __stcg(reinterpret_cast<float4*>(dst) + 1, make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7])));
+                }
+            }
+        }
+        ucount += (uint32_t)nun;
+        acount += (nun > 0) ? 1u : 0u;
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    };
+
+    // q_j = sum of the apply-segment partial maps of state sample j, in slot order
+    auto gather_q = [&](float* dstmaps) {
+        for (int o = tid; o < ns * NPOS; o += NTH) {
+            const int j = o / NPOS, pos = o - j * NPOS;
+            const int cnt = qn[j];
+            const int* ql = qlist + j * STC_QL_MAX;
+            float s = 0.f;
+            for (int k0 = 0; k0 < cnt; k0 += 8) {
+                float v[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[t] = (k0 + t < cnt) ? __ldcg(Q.qslots + (size_t)ql[k0 + t] * NPOS + pos) : 0.f;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) s += v[t];
+            }
+            dstmaps[o] = s;
+        }
+    };
+
+    // ---- s0 = A w0 -----------------------------------------------------------------------------------------------------------
+    build_ft(P.w_in);            // (also orders the label maps before their first use)
+    SD_STAMP(1);
+    sweep_apply();
+    SD_STAMP(2);
+    grid_barrier(Q.barrier, epoch);
+    SD_STAMP(3);
+    gather_q(sS);
+    __syncthreads();
+    SD_STAMP(4);
+
+    for (int it = 0; it <= P.num_iter; ++it) {
+        const int tb = 8 + it * 10;
+        SD_STAMP(tb + 0);
+        // ---- residual maps of the state samples (and the loss terms of iterate `it`, owner only) ---------------------------------
+        float lloc = 0.f;
+        if (MODE != 1) {
+            for (int o = tid; o < ns * NPOS; o += NTH) {
+                const int j = o / NPOS;
+                const float s = sS[o], m = sM[o], vh = sV[o];
+                float act, dact;
+                if (MODE == 3 && P.act_kind == 1) {      // BentIdentPar (activation.py:53-74)
+                    const float rt = sqrtf(s * s + 4.f * P.act_b * P.act_b);
+                    act = 0.5f * (1.f - m) * (rt - 2.f * P.act_b) + 0.5f * (1.f + m) * s;
+                    dact = 0.5f * (1.f - m) * (s / rt) + 0.5f * (1.f + m);
+                } else if (MODE == 0 || MODE == 3) {
+                    act = 0.5f * (1.f - m) * fabsf(s) + 0.5f * (1.f + m) * s;
+                    const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
+                    dact = 0.5f * (1.f - m) * sg + 0.5f * (1.f + m);
+                } else {            // optimizer.py:258-259
+                    act = m * s + (1.f - m) * fmaxf(s, 0.f);
+                    dact = m + (1.f - m) * ((s > 0.f) ? 1.f : 0.f);
+                }
+                const float r = vh * (act - sY[o]);
+                if (s_owned[j]) lloc += r * r;
+                sT[o] = dact * (vh * r);
+            }
+        } else {
+            for (int j = 0; j < ns; ++j) {
+                float mx = P.has_softmax_reg ? P.softmax_reg : -INFINITY;     // activation.py:7-16
+                for (int pos = tid; pos < NPOS; pos += NTH) mx = fmaxf(mx, sS[j * NPOS + pos]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                __syncthreads();
+                if (lane == 0) s_red[warp] = mx;
+                __syncthreads();
+                mx = s_red[0];
+                for (int wq = 1; wq < NTH / 32; ++wq) mx = fmaxf(mx, s_red[wq]);
+                float se = 0.f, ps = 0.f;
+                for (int pos = tid; pos < NPOS; pos += NTH) {
+                    const float e = expf(sS[j * NPOS + pos] - mx);
+                    sM[j * NPOS + pos] = e;
+                    se += e;
+                    ps += sY[j * NPOS + pos] * sS[j * NPOS + pos];
+                }
+                se = block_sum(se, s_red);
+                ps = block_sum(ps, s_red);
+                const float den = se + (P.has_softmax_reg ? expf(P.softmax_reg - mx) : 0.f);
+                const float inv = 1.f / den;
+                const float sw = s_sw[j];
+                for (int pos = tid; pos < NPOS; pos += NTH) {
+                    const float sm = sM[j * NPOS + pos] * inv;
+                    sM[j * NPOS + pos] = sm;
+                    sT[j * NPOS + pos] = sw * (sm - sY[j * NPOS + pos]);
+                }
+                if (tid == 0 && s_owned[j]) lloc += sw * ((logf(den) + mx) - ps);     // optimizer.py:393-396
+            }
+        }
+        if (P.losses_out) {
+            const float lr = block_sum(lloc, s_red);
+            float lw = 0.f;
+            for (int e = sl_lo + tid; e < sl_hi; e += NTH) { const float4 w = wsl[e - sl_lo]; lw += w.x * w.x + w.y * w.y + w.z * w.z + w.w * w.w; }
+            lw = block_sum(lw, s_red);
+            if (tid == 0) { Q.lossr[it * G + b] = lr; Q.lossw[it * G + b] = lw; }
+        }
+        if (it == P.num_iter) break;
+        __syncthreads();
+
+        SD_STAMP(tb + 1);
+        sweep_adjoint();
+        SD_STAMP(tb + 2);
+        grid_barrier(Q.barrier, epoch);
+        SD_STAMP(tb + 3);
+
+        // ---- this CTA's slice of g = sum of the partial gradients + reg * w --------------------------------------------------------
+        float gl = 0.f;
+        {
+            const int per_chunk = n * KBT;
+            for (int e = sl_lo + warp; e < sl_hi; e += NTH / 32) {
+                const int chunk = e >> 9, within = e & 511;                   // 128 channels x 16 taps = 512 float4 per chunk
+                const int bf = part_owner(UT, G, chunk * per_chunk), bl = part_owner(UT, G, (chunk + 1) * per_chunk - 1);
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int bb = bf + lane; bb <= bl; bb += 32) {
+                    const int lo = part_lo(UT, G, bb), hi = part_lo(UT, G, bb + 1);
+                    if (hi > lo) {
+                        const int cl = chunk - lo / per_chunk;
+                        const float4 v = __ldcg(reinterpret_cast<const float4*>(Q.gpart) + ((size_t)bb * STC_MAXCH + cl) * 512 + within);
+                        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+                    }
+                }
+                a.x = warp_sum_xor(a.x); a.y = warp_sum_xor(a.y); a.z = warp_sum_xor(a.z); a.w = warp_sum_xor(a.w);
+                if (lane == 0) {
+                    const float4 w = wsl[e - sl_lo];
+                    a.x += reg * w.x; a.y += reg * w.y; a.z += reg * w.z; a.w += reg * w.w;
+                    gsl[e - sl_lo] = a;
+                    __stcg(reinterpret_cast<float4*>(Q.gfinal) + e, a);
+                    gl += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+                }
+            }
+        }
+        gl = block_sum(gl, s_red);
+        if (tid == 0) Q.gnpart[b] = gl;
+        grid_barrier(Q.barrier, epoch);
+        build_ft(Q.gfinal);
+        SD_STAMP(tb + 4);
+        sweep_apply();
+        SD_STAMP(tb + 5);
+        grid_barrier(Q.barrier, epoch);
+        SD_STAMP(tb + 6);
+
+        // ---- q of the state samples, curvature term (owner only) ----------------------------------------------------------------
+        gather_q(sQ);
+        __syncthreads();
+        float hl = 0.f;
+        if (MODE != 1) {
+            for (int o = tid; o < ns * NPOS; o += NTH) {
+                const int j = o / NPOS;
+                const float qv = sQ[o], s = sS[o], m = sM[o];
+                float dact;
+                if (MODE == 3 && P.act_kind == 1) {
+                    dact = 0.5f * (1.f - m) * (s / sqrtf(s * s + 4.f * P.act_b * P.act_b)) + 0.5f * (1.f + m);
+                } else if (MODE == 0 || MODE == 3) {
+                    const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
+                    dact = 0.5f * (1.f - m) * sg + 0.5f * (1.f + m);
+                } else {
+                    dact = m + (1.f - m) * ((s > 0.f) ? 1.f : 0.f);
+                }
+                const float h = sV[o] * (dact * qv);
+                if (s_owned[j]) hl += h * h;
+            }
+            hl = block_sum(hl, s_red);
+        } else {
+            for (int j = 0; j < ns; ++j) {
+                float dotl = 0.f;
+                for (int pos = tid; pos < NPOS; pos += NTH) dotl += sM[j * NPOS + pos] * sQ[j * NPOS + pos];
+                const float dot = block_sum(dotl, s_red);
+                float gh = 0.f;
+                for (int pos = tid; pos < NPOS; pos += NTH) {
+                    const float qv = sQ[j * NPOS + pos], sm = sM[j * NPOS + pos];
+                    gh += qv * (sm * qv - sm * dot);
+                }
+                gh = block_sum(gh, s_red);
+                if (s_owned[j]) hl += s_sw[j] * fmaxf(gh, 0.f);       // identical on all threads
+            }
+        }
+        if (tid == 0) Q.hpart[b] = hl;
+        SD_STAMP(tb + 7);
+        grid_barrier(Q.barrier, epoch);
+        SD_STAMP(tb + 8);
+
+        // ---- step length and update ------------------------------------------------------------------------------------------------
+        if (warp == 0) {
+            float gn = 0.f, hn = 0.f;
+            for (int k = lane; k < G; k += 32) { gn += __ldcg(Q.gnpart + k); hn += __ldcg(Q.hpart + k); }
+            gn = warp_sum_xor(gn); hn = warp_sum_xor(hn);
+            if (lane == 0) {
+                const float den = fmaxf(hn + (reg + P.alpha_eps) * gn, 1e-8f);
+                s_scal[0] = P.step_length * (gn / den);
+            }
+        }
+        __syncthreads();
+        const float sa = s_scal[0];
+        for (int o = tid; o < ns * NPOS; o += NTH) sS[o] -= sa * sQ[o];
+        for (int e = sl_lo + tid; e < sl_hi; e += NTH) {
+            float4 w = wsl[e - sl_lo];
+            const float4 g = gsl[e - sl_lo];
+            w.x -= sa * g.x; w.y -= sa * g.y; w.z -= sa * g.z; w.w -= sa * g.w;
+            wsl[e - sl_lo] = w;
+            if (P.iterates_out) reinterpret_cast<float4*>(P.iterates_out + (size_t)(it + 1) * C * 16)[e] = w;
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue ----------------------------------------------------------------------------------------------------------------
+    for (int e = sl_lo + tid; e < sl_hi; e += NTH) reinterpret_cast<float4*>(P.w_out)[e] = wsl[e - sl_lo];
+    if (P.losses_out) {
+        grid_barrier(Q.barrier, epoch);
+        if (b == 0) {
+            for (int t = warp; t <= P.num_iter; t += NTH / 32) {
+                float l = 0.f, lw = 0.f;
+                for (int k = lane; k < G; k += 32) { l += __ldcg(Q.lossr + t * G + k); lw += __ldcg(Q.lossw + t * G + k); }
+                l = warp_sum_xor(l); lw = warp_sum_xor(lw);
+                if (lane == 0) P.losses_out[t] = (MODE == 3) ? (l + reg * lw) * P.loss_scale : l + reg * lw;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u) : "memory");
+    }
+}
+
+// [n][C][NPX] -> [n][NPX][C] (32 x 32 tiles through shared memory)
+__global__ void nchw_to_nhwc_tile_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int NPX) {
+    __shared__ float tile[32][33];
+    const int s = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const float* sp = src + (size_t)s * C * NPX;
+    float* dp = dst + (size_t)s * C * NPX;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = c0 + r, p = p0 + threadIdx.x;
+        tile[r][threadIdx.x] = (c < C && p < NPX) ? sp[(size_t)c * NPX + p] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int p = p0 + r, c = c0 + threadIdx.x;
+        if (p < NPX && c < C) dp[(size_t)p * C + c] = tile[threadIdx.x][r];
+    }
+}
+
+template <int FS, int MODE>
+int launch_sd_tc(const SdParams& P0, cudaStream_t st, int* handled) {
+    *handled = 0;
+    { const char* v = getenv("B200TRK_SD_TC"); if (!(v ? atoi(v) : 0)) return 0; }
+    constexpr int OS = FS + 1, NPOS = OS * OS, NPX = FS * FS, KBT = (NPX + 31) / 32, NPT = (NPX + 127) / 128;
+    if (P0.C % 128 != 0 || P0.C / 128 > STC_MAXCH) return 0;
+    if ((reinterpret_cast<uintptr_t>(P0.feat) & 15u) != 0) return 0;
+    const int G = device_sm_count();
+    const int n = P0.n, C = P0.C, nchk = C / 128, kba = C / 32;
+    if (NPT * kba > STC_QL_MAX) return 0;
+    const long long UT = (long long)nchk * n * KBT;
+    // samples per CTA (state slots) = the most distinct samples any adjoint range touches
+    int smax = 1;
+    for (int b = 0; b < G; ++b) {
+        const long long lo = UT * b / G, hi = UT * (b + 1) / G;
+        if (hi <= lo) continue;
+        int cnt = 0; long long seen[16];
+        for (long long u = lo; u < hi; u = (u / KBT + 1) * KBT) {
+            const long long smp = (u / KBT) % n;
+            bool have = false;
+            for (int j = 0; j < cnt; ++j) have |= (seen[j] == smp);
+            if (!have) { if (cnt == 16) return 0; seen[cnt++] = smp; }
+        }
+        if (cnt > smax) smax = cnt;
+    }
+    if (smax > 16) return 0;
+    const int slice_max = (C * 4 + G - 1) / G + 1;
+    const size_t smem = 1024 + (size_t)STC_NSTG * STC_STAGE_BYTES + (size_t)kba * 4096 + 16 * STC_TT_PITCH * 4 + 2 * (size_t)slice_max * 16 +
+                        (size_t)smax * 6 * NPOS * 4 + (size_t)smax * (STC_QL_MAX + 1) * 4 + 64;
+    if (smem > 227 * 1024 - 1024) return 0;
+    B200_REQUIRE(P0.num_iter + 1 <= 1024, "sd optimizer: num_iter=%d too large", P0.num_iter);
+
+    SdTcParams Q;
+    memset(&Q, 0, sizeof(Q));
+    Q.p = P0;
+    Q.p.trace = getenv("B200TRK_SD_TRACE") ? (unsigned long long*)workspace(1024, 3) : nullptr;
+    Q.smax = smax; Q.nchk = nchk; Q.kba = kba; Q.slice_max = slice_max;
+
+    // [n][H*W][C] copy of the sample memory for the apply sweep
+    float* nhwc = (float*)workspace((size_t)n * C * NPX * sizeof(float), 6);
+    if (!nhwc) return 3;
+    nchw_to_nhwc_tile_kernel<<<dim3((NPX + 31) / 32, (C + 31) / 32, n), dim3(32, 8), 0, st>>>(P0.feat, nhwc, C, NPX);
+    B200_LAUNCH_CHECK();
+
+    {
+        const uint64_t dims[3] = {(uint64_t)NPX, (uint64_t)C, (uint64_t)n};
+        const uint64_t strides[2] = {(uint64_t)NPX * 4, (uint64_t)C * NPX * 4};
+        const uint32_t box[3] = {32, 128, 1};
+        if (int e = tc_make_map(&Q.map_t, const_cast<float*>(P0.feat), 3, dims, strides, box)) return e;
+    }
+    {
+        const uint64_t dims[3] = {(uint64_t)C, (uint64_t)NPX, (uint64_t)n};
+        const uint64_t strides[2] = {(uint64_t)C * 4, (uint64_t)C * NPX * 4};
+        const uint32_t box[3] = {32, 128, 1};
+        if (int e = tc_make_map(&Q.map_a, nhwc, 3, dims, strides, box)) return e;
+    }
+
+    const size_t n_gpart = (size_t)G * STC_MAXCH * 128 * 16, n_q = (size_t)n * NPT * kba * NPOS;
+    const size_t n_loss = (size_t)(P0.num_iter + 1) * G;
+    const size_t total = (n_gpart + (size_t)C * 16 + n_q + 2 * (size_t)G + 2 * n_loss + 64) * sizeof(float) + 1024;
+    char* ws = (char*)workspace(total, 2);
+    if (!ws) return 3;
+    Q.barrier = (unsigned*)ws;
+    float* f = (float*)(ws + 1024);
+    Q.gpart = f; f += n_gpart;
+    Q.gfinal = f; f += (size_t)C * 16;
+    Q.qslots = f; f += n_q;
+    Q.gnpart = f; f += G;
+    Q.hpart = f; f += G;
+    Q.lossr = f; f += n_loss;
+    Q.lossw = f;
+    B200_CHECK_CUDA(cudaMemsetAsync(Q.barrier, 0, 1024, st));
+
+    auto kern = sd_tc_kernel<FS, MODE>;
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* args[] = {(void*)&Q};
+    B200_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(G), dim3(STC_THREADS), args, smem, st));
+    g_launch_count.fetch_add(2, std::memory_order_relaxed);
+    *handled = 1;
+    return 0;
+}
+
+template int launch_sd_tc<18, 0>(const SdParams&, cudaStream_t, int*);
+template int launch_sd_tc<18, 1>(const SdParams&, cudaStream_t, int*);
+template int launch_sd_tc<18, 2>(const SdParams&, cudaStream_t, int*);
+template int launch_sd_tc<18, 3>(const SdParams&, cudaStream_t, int*);
+template int launch_sd_tc<22, 0>(const SdParams&, cudaStream_t, int*);
+template int launch_sd_tc<22, 1>(const SdParams&, cudaStream_t, int*);
+template int launch_sd_tc<22, 2>(const SdParams&, cudaStream_t, int*);
+template int launch_sd_tc<22, 3>(const SdParams&, cudaStream_t, int*);
+
+}  // namespace b200trk
