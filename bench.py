@@ -34,6 +34,8 @@ SD_ITERS = 10
 # dram__bytes_read.sum + dram__bytes_write.sum of one sd_kernel launch (n=50, 10 it) from the committed ncu --set full
 # capture profiles/r01g_ncu_full_sd_and_conv.txt: the sample memory is read from HBM once per call and stays L2 resident.
 SD_DRAM_TRAFFIC_BYTES = 33330944 + 121600
+# the same for one sd_tc_kernel launch (profiles/r01j_sd_tc_ncu.txt)
+SD_TC_DRAM_TRAFFIC_BYTES = 33360000 + 257540
 POOL = 160          # distinct crops per rank (160 x 995 KB = 159 MB > 126 MB L2: a step's input is never L2 resident)
 
 
@@ -214,6 +216,7 @@ def run_b200(args, rank, world, local_rank):
         ev[2 * j + 1].record()
     torch.cuda.synchronize()
     sd_us = float(np.median([ev[2 * j].elapsed_time(ev[2 * j + 1]) for j in range(20)])) * 1e3
+    sd_tc = int(_lib.lib().b200trk_sd_last_kernel())
 
     # ---------------- host-buffer leg (e2e) ----------------
     for i in range(W):
@@ -256,9 +259,10 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": world * K / (host_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 3 * CROP * CROP * 4 + 16 + MEMORY * 4,
                 "d2h_bytes_per_step": 19 * 19 * 4 + 4 + 16},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "sd_kernel<18,4,0> (DiMP steepest-descent, n=50, 10 it)", "bound": "hbm", "achieved": achieved,
+        "roofline": {"kernel": ("sd_tc_kernel<18,0> (tcgen05 sweeps)" if sd_tc else "sd_kernel<18,4,0>") + " (DiMP steepest-descent, n=50, 10 it)",
+                     "bound": "hbm", "achieved": achieved,
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                     "traffic": SD_DRAM_TRAFFIC_BYTES,
+                     "traffic": SD_TC_DRAM_TRAFFIC_BYTES if sd_tc else SD_DRAM_TRAFFIC_BYTES,
                      "peak_source": peaks["source"], "us_per_launch": sd_us, "us_per_sd_iteration": sd_us / SD_ITERS},
         "cpu_baseline": cpu,
         "clocks": clocks,

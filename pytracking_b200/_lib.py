@@ -43,7 +43,9 @@ SIGNATURES = {
     "b200trk_version": (_I, []),
     "b200trk_last_error": (C.c_char_p, []),
     "b200trk_launch_count": (C.c_uint64, []),
+    "b200trk_sd_last_kernel": (_I, []),
     "b200trk_debug_sd_trace": (_I, [_VP]),
+    "b200trk_debug_sd_units": (_I, [_VP]),
     "b200trk_apply_filter": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _VP]),
     "b200trk_apply_feat_transpose": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "b200trk_conv2d_same": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),

@@ -71,6 +71,13 @@ extern "C" int b200trk_debug_sd_trace(unsigned long long* out_host) {
     return cudaMemcpy(out_host, p, 512, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
 }
 
+// debug: per-unit pipeline stamps of the tcgen05 SD kernel ([32 units][8] x u64 SM clocks, CTA 0, first adjoint sweep)
+extern "C" int b200trk_debug_sd_units(unsigned long long* out_host) {
+    char* p = (char*)b200trk::workspace(4096, 3);
+    if (!p || !out_host) return 1;
+    return cudaMemcpy(out_host, p + 1024, 2048, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
+}
+
 extern "C" int b200trk_version(void) { return B200TRK_VERSION; }
 extern "C" const char* b200trk_last_error(void) { return b200trk::g_err; }
 extern "C" uint64_t b200trk_launch_count(void) { return b200trk::g_launch_count.load(); }

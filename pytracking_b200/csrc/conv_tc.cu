@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = s_tmem_base;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, s_tmem_base, 0);     // provably warp-uniform (tc_ptx.cuh)
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the
     // tail of the previous layer's kernel; nothing below may touch global memory before the previous grid has completed.
     if (dbg && threadIdx.x == 0) dbg[1] = gtimer();                   // prologue done
@@ -121,51 +121,52 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
     if (dbg && threadIdx.x == 0) dbg[2] = gtimer();                   // previous grid complete
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp converged, elect.sync inside the wrappers: tc_ptx.cuh) ==========
+        {
             const int x0 = tw * P.BW * P.stride - P.pad, y0 = th * P.BH * P.stride - P.pad;
+            int tap = kb0 / P.cblks, cb = kb0 - tap * P.cblks;
+            int kh = tap / P.ksz, kw = tap - kh * P.ksz;
+            int st = 0;
+            uint32_t ph = 0;
             for (int it = 0; it < nkb; ++it) {
-                const int kb = kb0 + it;
-                const int st = it % P.stages;
-                const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
                 mbar_wait(smem_u32(&s_empty[st]), ph ^ 1u);
-                if (trace && it < 16) trace[it * 8 + 0] = gtimer();          // slot free
+                if (trace && it < 16 && lane == 0) trace[it * 8 + 0] = gtimer();          // slot free
                 const uint32_t full = smem_u32(&s_full[st]);
-                mbar_expect_tx(full, P.a_bytes + P.b_bytes);
-                const int tap = kb / P.cblks, cb = kb - tap * P.cblks;
-                const int kh = tap / P.ksz, kw = tap - kh * P.ksz;
+                mbar_expect_tx_elect(full, P.a_bytes + P.b_bytes);
                 const uint32_t sa = smem_base + (uint32_t)st * stage_bytes;
-                tma_load_4d(sa, &P.a_map, full, cb * TC_KB, x0 + kw, y0 + kh, s);                 // raw -> A_hi slot
-                tma_load_2d(sa + 2u * a_tile, &P.b_map, full, tap * P.Cin + cb * TC_KB, n0);       // raw -> B_hi slot
-                if (trace && it < 16) trace[it * 8 + 1] = gtimer();          // loads issued
+                tma_load_4d_elect(sa, &P.a_map, full, cb * TC_KB, x0 + kw, y0 + kh, s);                 // raw -> A_hi slot
+                tma_load_2d_elect(sa + 2u * a_tile, &P.b_map, full, tap * P.Cin + cb * TC_KB, n0);       // raw -> B_hi slot
+                if (trace && it < 16 && lane == 0) trace[it * 8 + 1] = gtimer();          // loads issued
+                if (++cb == P.cblks) { cb = 0; ++tap; if (++kw == P.ksz) { kw = 0; ++kh; } }
+                if (++st == P.stages) { st = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp converged, elect.sync inside the wrappers: tc_ptx.cuh) =====================
+        {
             // instruction descriptor: D = F32, A = B = TF32, both K-major, N = BN, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            int st = 0;
+            uint32_t ph = 0;
             for (int it = 0; it < nkb; ++it) {
-                const int st = it % P.stages;
-                const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
                 mbar_wait(smem_u32(&s_ready[st]), ph);
                 tc_fence_after();
-                if (dbg && it == 0) dbg[3] = gtimer();                // first operands landed and split
-                if (trace && it < 16) trace[it * 8 + 4] = gtimer();          // MMA warp sees the stage
-                const uint32_t sa = smem_base + (uint32_t)st * stage_bytes;
-                const uint64_t d_ah = make_smem_desc(sa), d_al = make_smem_desc(sa + a_tile);
-                const uint64_t d_bh = make_smem_desc(sa + 2u * a_tile), d_bl = make_smem_desc(sa + 2u * a_tile + b_tile);
+                if (dbg && it == 0 && lane == 0) dbg[3] = gtimer();                // first operands landed and split
+                if (trace && it < 16 && lane == 0) trace[it * 8 + 4] = gtimer();          // MMA warp sees the stage
+                const uint32_t d_ah = make_smem_desc_lo(smem_base + (uint32_t)st * stage_bytes), d_al = d_ah + (a_tile >> 4);
+                const uint32_t d_bh = d_al + (a_tile >> 4), d_bl = d_bh + (b_tile >> 4);
 #pragma unroll
                 for (int k = 0; k < TC_KB / 8; ++k) {
-                    const uint64_t adv = (uint64_t)(k * 32 >> 4);      // 8 tf32 = 32 bytes per UMMA K step
-                    tc_mma_tf32(tmem_base, d_al + adv, d_bh + adv, idesc, (it > 0 || k > 0) ? 1u : 0u);
-                    tc_mma_tf32(tmem_base, d_ah + adv, d_bl + adv, idesc, 1u);
-                    tc_mma_tf32(tmem_base, d_ah + adv, d_bh + adv, idesc, 1u);
+                    const uint32_t adv = (uint32_t)(k * 32 >> 4);      // 8 tf32 = 32 bytes per UMMA K step
+                    tc_mma_tf32_lo(tmem_base, d_al + adv, d_bh + adv, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    tc_mma_tf32_lo(tmem_base, d_ah + adv, d_bl + adv, idesc, 1u);
+                    tc_mma_tf32_lo(tmem_base, d_ah + adv, d_bh + adv, idesc, 1u);
                 }
-                tc_commit(smem_u32(&s_empty[st]));
-                if (trace && it < 16) trace[it * 8 + 5] = gtimer();          // MMAs + commit issued
+                tc_commit_elect(smem_u32(&s_empty[st]));
+                if (trace && it < 16 && lane == 0) trace[it * 8 + 5] = gtimer();          // MMAs + commit issued
+                if (++st == P.stages) { st = 0; ph ^= 1u; }
             }
-            tc_commit(smem_u32(&s_tmem_full));
+            tc_commit_elect(smem_u32(&s_tmem_full));
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
@@ -389,7 +390,8 @@ bool tc_conv_supported(const Op& op) {
     return env_int("B200TRK_TC", 1) != 0;
 }
 
-int tc_make_map(CUtensorMap* m, float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+int tc_make_map(CUtensorMap* m, float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                int swizzle128) {
     EncodeTiledFn enc = get_encode_fn();
     B200_REQUIRE(enc, "tc_make_map: cuTensorMapEncodeTiled not available from the driver");
     B200_REQUIRE(rank >= 2 && rank <= 4, "tc_make_map: rank %d", rank);
@@ -397,7 +399,8 @@ int tc_make_map(CUtensorMap* m, float* base, int rank, const uint64_t* dims, con
     for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
     for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, base, d, s, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_REQUIRE(r == CUDA_SUCCESS, "tc_make_map: cuTensorMapEncodeTiled(rank %d, dims %llu x %llu) failed: %d", rank,
                  (unsigned long long)dims[0], (unsigned long long)dims[1], (int)r);
     return 0;
@@ -482,6 +485,15 @@ static int tc_configure(b200trk_net* net, const Op& op, TcConv* tc, int S) {
         BN = 64;
         // a second wave of 1-CTA-per-SM tiles doubles the layer time: widen the tile as soon as BN = 64 overflows the SMs
         if (op.Cout % 128 == 0 && m_tiles * (op.Cout / 64) > net->sms) BN = 128;
+        // long-K layers that still fill the SMs with 128-wide tiles through split-K (the DiMP head: 3x3, 1024 -> 512 at 18x18): the
+        // K loop is bound by the operand bytes each CTA pulls from L2, and a wide tile re-reads the activations half as often
+        if (op.Cout % 128 == 0 && BN == 64 && env_int("B200TRK_TC_WIDE", 1)) {
+            const int ctas128 = m_tiles * (op.Cout / 128);
+            int sp = net->sms / (ctas128 > 0 ? ctas128 : 1);
+            const int min_kb = env_int("B200TRK_TC_MINKB", 4);
+            if (sp > P.total_kb / min_kb) sp = P.total_kb / min_kb;
+            if (sp >= 1 && ctas128 * sp * 10 >= net->sms * 9 && P.total_kb >= 128) BN = 128;
+        }
     }
     if (op.Cout % BN != 0 || (BN != 64 && BN != 128)) BN = 64;
     P.BN = BN;

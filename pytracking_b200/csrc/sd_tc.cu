@@ -5,7 +5,8 @@
 //       A = X_i[128 channels x 32 pixels]  (K-major straight from the [n, C, H*W] sample memory, TMA box)
 //       B = R_i^T[16 taps x 32 pixels]      (gathered from the residual map in shared memory by the converter warps)
 //   apply sweep     T_i[p, tap] = sum_c X_i[p, c] * F[c, tap] ;  s_i[y, x] = sum_tap T_i[(y, x) shifted by the tap, tap]   (A f)
-//       A = X_i[128 pixels x 32 channels]  (K-major from an [n, H*W, C] copy of the sample memory made once per call)
+//       A = X_i[128 pixels x 32 channels]  (the SAME [n, C, H*W] memory: the TMA box is 32 channel rows x 128 pixels and the
+//                                            converter warps transpose it on the way into tensor memory)
 //       B = F^T[16 taps x 32 channels]      (the filter / gradient, resident in shared memory for the whole sweep)
 //
 // fp32 fidelity as in conv_tc.cu: every operand is split x = hi + lo with hi = the TF32 truncation the datapath applies anyway,
@@ -23,31 +24,41 @@
 // `smax`); the replicas evolve identically because all of them read the same partials in the same order; loss / curvature
 // terms are contributed by the sample's owner (the CTA holding its first unit) only.
 //
+// Operand pipeline (per unit): TMA lands the raw 128 x 32 fp32 tile in a shared-memory stage; the converter warps read it back
+// (thread = tile row, conflict-free through the 128-byte swizzle) and write hi (= raw) and lo straight into a TENSOR-MEMORY
+// stage with tcgen05.st; the MMAs take A from TMEM (tcgen05.mma with a TMEM A operand) and only the 16-row B operand from
+// shared memory. The shared-memory stage is free again as soon as it has been read (not when the MMAs retire), so 6 x 20 KB
+// stages cover the L2 latency, and the shared-memory traffic per unit is 16 KB in + 16 KB out instead of ~100 KB.
+//
 // Warp roles during a sweep: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 = operand converters (lo parts, R^T tiles)
 // and epilogue (TMEM -> registers -> partials). All 320 threads run the element-wise phases between the sweeps.
 #include "tc_ptx.cuh"
 #include "sd_common.cuh"
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
 namespace b200trk {
 
-constexpr int STC_THREADS = 320;
+constexpr int STC_THREADS = 384;              // warp 0 producer, 1 / 10 / 11 MMA issuers, 2-9 converters + epilogue
 constexpr int STC_CT = 256;                 // converter / epilogue threads (warps 2..9)
-constexpr int STC_NSTG = 3;
+constexpr int STC_NS_MAX = 8;               // shared-memory stages (runtime count Q.ns >= STC_NT)
+constexpr int STC_NT = 4;                   // tensor-memory stages: 64 columns each (32 hi + 32 lo)
+constexpr int STC_ACC_COL = STC_NT * 64;    // accumulators behind the operand stages
+constexpr int STC_TMEM_COLS = 512;
 constexpr int STC_A_BYTES = 16384;          // 128 rows x 128 B
-constexpr int STC_STAGE_BYTES = 36864;      // A_hi | A_lo | B_hi (2 KB) | B_lo (2 KB)
+constexpr int STC_STAGE_BYTES = 20480;      // A raw | B_hi (2 KB) | B_lo (2 KB)
 constexpr int STC_MAXCH = 4;                // 128-channel chunks (C <= 512)
 constexpr int STC_TT_PITCH = 132;
 constexpr int STC_QL_MAX = 64;              // apply segments of one sample (<= pixel tiles x channel blocks)
 
 struct SdTcParams {
     SdParams p;
-    CUtensorMap map_t;      // [n][C][H*W]  as {pixel, channel, sample}
-    CUtensorMap map_a;      // [n][H*W][C]  as {channel, pixel, sample}
+    CUtensorMap map_t;      // [n][C][H*W] as {pixel, channel, sample}: box 32 pixels x 128 channels, SWIZZLE_128B (adjoint sweep)
+    CUtensorMap map_a;      // the same memory: box 128 pixels x 32 channels, no swizzle (apply sweep)
     float* gpart; float* gfinal; float* gnpart; float* qslots; float* hpart; float* lossr; float* lossw;
     unsigned* barrier;
-    int smax, nchk, kba, slice_max;
+    int smax, nchk, kba, slice_max, ns;
 };
 
 __device__ __forceinline__ int part_lo(long long U, int G, int b) { return (int)((U * (long long)b) / G); }
@@ -62,6 +73,38 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem], kind::tf32: A = 128 lanes x 8 columns (one fp32 / TF32 element per column)
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Grid barrier for a cooperatively launched kernel without atomics: every CTA publishes its epoch in its own flag and warp 0
+// polls all flags (flags[G], zeroed by the host).
+__device__ __forceinline__ void grid_barrier_flags(unsigned* flags, unsigned& epoch) {
+    __syncthreads();
+    epoch += 1;
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + blockIdx.x), "r"(epoch) : "memory");
+        }
+        const int G = gridDim.x;
+        long long t0 = clock64();
+        while (true) {
+            bool done = true;
+            for (int k = threadIdx.x; k < G; k += 32) done = done && (ld_acquire_u32(flags + k) >= epoch);
+            if (__all_sync(0xffffffffu, done)) break;
+            if (clock64() - t0 > 4 * TC_WAIT_LIMIT_CLOCKS) __trap();
+        }
+        __threadfence();
+    }
+    __syncthreads();
 }
 __device__ __forceinline__ float lo_trunc(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 // byte offset of element (row, k) inside a K-major SWIZZLE_128B tile of 128-byte rows (tile base 1024-byte aligned)
@@ -82,9 +125,10 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
     constexpr int NPT = (NPX + 127) / 128;        // pixel tiles of the apply sweep (3 / 4)
     constexpr int NTH = STC_THREADS;
     extern __shared__ uint8_t stc_raw[];
-    __shared__ __align__(8) uint64_t s_full[STC_NSTG];
-    __shared__ __align__(8) uint64_t s_empty[STC_NSTG];
-    __shared__ __align__(8) uint64_t s_ready[STC_NSTG];
+    __shared__ __align__(8) uint64_t s_full[STC_NS_MAX];      // TMA landed the raw tile in shared-memory stage s
+    __shared__ __align__(8) uint64_t s_sfree[STC_NS_MAX];     // the converter warps have read stage s
+    __shared__ __align__(8) uint64_t s_tready[STC_NT];        // hi / lo of a unit are in tensor-memory stage t (+ its B tile in smem)
+    __shared__ __align__(8) uint64_t s_tfree[STC_NT];         // the MMAs reading tensor-memory stage t have retired
     __shared__ __align__(8) uint64_t s_acc;
     __shared__ uint32_t s_tmem;
     __shared__ float s_red[32];
@@ -108,7 +152,8 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
     // ---- shared memory carve-up ----------------------------------------------------------------------------------------
     uint8_t* base = stc_raw + ((1024u - (smem_u32(stc_raw) & 1023u)) & 1023u);
     const uint32_t base_u32 = smem_u32(base);
-    uint8_t* ftb = base + STC_NSTG * STC_STAGE_BYTES;                 // F^T: [kba][hi 2 KB | lo 2 KB]
+    const int NS = Q.ns;
+    uint8_t* ftb = base + NS * STC_STAGE_BYTES;                 // F^T: [kba][hi 2 KB | lo 2 KB]
     float* Tt = reinterpret_cast<float*>(ftb + (size_t)kba * 4096);   // [16][STC_TT_PITCH] apply-epilogue staging
     float4* wsl = reinterpret_cast<float4*>(Tt + 16 * STC_TT_PITCH);  // filter slice owned by this CTA
     float4* gsl = wsl + Q.slice_max;                                  // gradient slice
@@ -124,10 +169,9 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
     SD_STAMP(0);
     // ---- prologue ------------------------------------------------------------------------------------------------------------
     if (tid == 0) {
-        for (int i = 0; i < STC_NSTG; ++i) {
-            mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_empty[i]), 1); mbar_init(smem_u32(&s_ready[i]), STC_CT / 32);
-        }
-        mbar_init(smem_u32(&s_acc), 1);
+        for (int i = 0; i < NS; ++i) { mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_sfree[i]), STC_CT / 32); }
+        for (int i = 0; i < STC_NT; ++i) { mbar_init(smem_u32(&s_tready[i]), STC_CT / 32); mbar_init(smem_u32(&s_tfree[i]), 3); }
+        mbar_init(smem_u32(&s_acc), 3);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // state slots: the samples of this CTA's adjoint range (runs of KBT units per (chunk, sample))
         int ns = 0;
@@ -145,7 +189,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
         s_ns = ns;
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(64u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"((uint32_t)STC_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
@@ -156,7 +200,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = s_tmem;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, s_tmem, 0);      // provably warp-uniform (see tc_ptx.cuh)
     const int ns = s_ns;
 
     // valid apply-segment slots of every state sample: a segment starts at channel block 0 of a (sample, pixel tile) run and at
@@ -241,15 +285,123 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
 
     // F^T (hi | lo) of all channel blocks from a [C][16] vector in global memory
     auto build_ft = [&](const float* src) {
-        for (int idx = tid; idx < C * 16; idx += NTH) {
-            const int c = idx >> 4, tap = idx & 15;
-            const float v = __ldcg(src + idx);
-            uint8_t* t = ftb + (size_t)(c >> 5) * 4096 + sw128(tap, c & 31);
-            *reinterpret_cast<float*>(t) = v;
-            *reinterpret_cast<float*>(t + 2048) = lo_trunc(v);
+        const int n4 = C * 4;
+        for (int b4 = 0; b4 < n4; b4 += 4 * NTH) {            // 4 independent 16-byte loads in flight per thread
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i4 = b4 + u * NTH + tid;
+                v[u] = (i4 < n4) ? __ldcg(reinterpret_cast<const float4*>(src) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i4 = b4 + u * NTH + tid;
+                if (i4 < n4) {
+                    const int c = i4 >> 2, tap0 = (i4 & 3) * 4;
+                    const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint8_t* t = ftb + (size_t)(c >> 5) * 4096 + sw128(tap0 + k, c & 31);
+                        *reinterpret_cast<float*>(t) = e[k];
+                        *reinterpret_cast<float*>(t + 2048) = lo_trunc(e[k]);
+                    }
+                }
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
+    };
+
+    // per-unit pipeline stamps (SM clock) of CTA 0 during the first adjoint sweep: utr[unit][8]
+    long long* utr = nullptr;
+    int utr_i = 0;
+#define UTR(k) do { if (utr && utr_i < 32) utr[utr_i * 8 + (k)] = clock64(); } while (0)
+    // ---- operand pipeline pieces (unit index ug = units since kernel start; identical in all roles) -----------------------
+    // producer: raw tile of one unit -> shared-memory stage
+    auto produce = [&](uint32_t ug, const CUtensorMap* map, int c0, int c1, int c2) {
+        const uint32_t s = ug % (uint32_t)NS, sp = (ug / (uint32_t)NS) & 1u;
+        mbar_wait(smem_u32(&s_sfree[s]), sp ^ 1u);
+        if (lane == 0) UTR(0);
+        const uint32_t full = smem_u32(&s_full[s]);
+        if (P.dbg_mode == 4) {          // timing experiment: no TMA traffic (results are garbage)
+            mbar_arrive_elect(full);
+            return;
+        }
+        mbar_expect_tx_elect(full, STC_A_BYTES);
+        tma_load_3d_elect(base_u32 + s * STC_STAGE_BYTES, map, full, c0, c1, c2);
+        if (lane == 0) UTR(1);
+    };
+    // converter, first half: wait for the tile and for the tensor-memory stage, read this thread's half row (16 fp32) and store
+    // hi (raw: the datapath truncates) and lo into TMEM. Returns the shared-memory stage (for the adjoint sweep's B tile).
+    auto convert_a = [&](uint32_t ug, bool transposed) -> uint8_t* {
+        const uint32_t s = ug % (uint32_t)NS, sp = (ug / (uint32_t)NS) & 1u;
+        const uint32_t t = ug % STC_NT, tp = (ug / STC_NT) & 1u;
+        mbar_wait(smem_u32(&s_full[s]), sp);
+        if (ct == 0) UTR(2);
+        mbar_wait(smem_u32(&s_tfree[t]), tp ^ 1u);
+        tc_fence_after();
+        if (ct == 0) UTR(3);
+        uint8_t* sb = base + (size_t)s * STC_STAGE_BYTES;
+        const int row = q * 32 + lane;
+        const uint8_t* arow = sb + row * 128;
+        uint32_t hi[16], lo[16];
+        if (P.dbg_mode == 3) return sb;     // timing experiment: no operand conversion
+        if (!transposed) {
+            // tile = [128 rows][32 k] with the 128-byte swizzle: this thread's row, 16 consecutive k
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 x = *reinterpret_cast<const float4*>(arow + ((((half * 4 + j) ^ (row & 7))) << 4));
+                hi[4 * j] = __float_as_uint(x.x); hi[4 * j + 1] = __float_as_uint(x.y); hi[4 * j + 2] = __float_as_uint(x.z); hi[4 * j + 3] = __float_as_uint(x.w);
+                lo[4 * j] = __float_as_uint(lo_trunc(x.x)); lo[4 * j + 1] = __float_as_uint(lo_trunc(x.y));
+                lo[4 * j + 2] = __float_as_uint(lo_trunc(x.z)); lo[4 * j + 3] = __float_as_uint(lo_trunc(x.w));
+            }
+        } else {
+            // tile = [32 k][128 rows] linear (512-byte lines): the lanes of a warp read 32 consecutive words of one line
+            const float* col = reinterpret_cast<const float*>(sb) + (half * 16) * 128 + row;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float x = col[j * 128];
+                hi[j] = __float_as_uint(x);
+                lo[j] = __float_as_uint(lo_trunc(x));
+            }
+        }
+        const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + t * 64u + (uint32_t)(half * 16);
+        tmem_st16(ta, hi);
+        tmem_st16(ta + 32u, lo);
+        return sb;
+    };
+    // converter, second half: publish the unit
+    auto convert_done = [&](uint32_t ug) {
+        const uint32_t s = ug % (uint32_t)NS, t = ug % STC_NT;
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (ct == 0) UTR(4);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_sfree[s])) : "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_tready[t])) : "memory");
+        }
+        if (ct == 0) UTR(5);
+    };
+    // MMA issuers: three warps (1, 10, 11), one per product of the 3xTF32 expansion (A_lo*B_hi, A_hi*B_lo, A_hi*B_hi), each into
+    // its own 16-column accumulator (acc + 16 * prod); issuing a tcgen05.mma costs one warp ~100 cycles of scalar work, so a single
+    // issue warp (12 MMAs per unit) was the slowest stage of the pipeline. A = tensor-memory stage t, B from shared memory.
+    const int prod = (warp == 1) ? 0 : warp - 9;
+    auto issue = [&](uint32_t ug, uint32_t acc, uint32_t b_hi_addr, bool first) {
+        const uint32_t t = ug % STC_NT, tp = (ug / STC_NT) & 1u;
+        mbar_wait(smem_u32(&s_tready[t]), tp);
+        tc_fence_after();
+        if (lane == 0 && prod == 0) UTR(6);
+        const uint32_t a_op = tmem + t * 64u + ((prod == 0) ? 32u : 0u);                               // lo | hi | hi
+        const uint32_t d_b = make_smem_desc_lo(b_hi_addr) + ((prod == 1) ? (2048u >> 4) : 0u);       // hi | lo | hi
+        if (P.dbg_mode != 1 && !(P.dbg_mode == 2 && prod != 2)) {     // (timing experiments: 1 = no MMAs, 2 = hi*hi only)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                tc_mma_tf32_ts_lo(acc + (uint32_t)(16 * prod), a_op + (uint32_t)(k * 8), d_b + (uint32_t)(k * 32 >> 4), idesc,
+                                  (first && k == 0) ? 0u : 1u);
+        }
+        tc_commit_elect(smem_u32(&s_tfree[t]));
+        if (lane == 0 && prod == 0) UTR(7);
     };
 
     // apply sweep: qslots[segment] = shift-added partial map of every (sample, pixel tile) segment of this CTA's range
@@ -259,40 +411,20 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
         for (int i = 0; i < nun; ++i) { const int kb = (a_lo + i) % kba; nseg += (i == 0 || kb == 0) ? 1 : 0; }
         if (nun > 0) {
             if (warp == 0) {
-                if (lane == 0) {
-                    for (int i = 0; i < nun; ++i) {
-                        const int u = a_lo + i;
-                        const int smp = u / (NPT * kba), r = u - smp * (NPT * kba), pt = r / kba, kb = r - pt * kba;
-                        const uint32_t st = (ucount + i) % STC_NSTG, ph = ((ucount + i) / STC_NSTG) & 1u;
-                        mbar_wait(smem_u32(&s_empty[st]), ph ^ 1u);
-                        const uint32_t full = smem_u32(&s_full[st]);
-                        mbar_expect_tx(full, STC_A_BYTES);
-                        tma_load_3d(base_u32 + st * STC_STAGE_BYTES, &Q.map_a, full, kb * 32, pt * 128, smp);
-                    }
+                // (whole warp, converged: see tc_ptx.cuh) unit coordinates advance incrementally
+                int smp = a_lo / (NPT * kba), r0 = a_lo - smp * (NPT * kba), pt = r0 / kba, kb = r0 - pt * kba;
+                for (int i = 0; i < nun; ++i) {
+                    produce(ucount + i, &Q.map_a, pt * 128, kb * 32, smp);
+                    if (++kb == kba) { kb = 0; if (++pt == NPT) { pt = 0; ++smp; } }
                 }
-            } else if (warp == 1) {
-                if (lane == 0) {
-                    for (int i = 0; i < nun; ++i) {
-                        const int u = a_lo + i;
-                        const int kb = u % kba;
-                        const bool seg_first = (i == 0 || kb == 0), seg_last = (i == nun - 1 || kb == kba - 1);
-                        const uint32_t st = (ucount + i) % STC_NSTG, ph = ((ucount + i) / STC_NSTG) & 1u;
-                        mbar_wait(smem_u32(&s_ready[st]), ph);
-                        tc_fence_after();
-                        const uint32_t sa = base_u32 + st * STC_STAGE_BYTES;
-                        const uint32_t fb = smem_u32(ftb) + (uint32_t)kb * 4096u;
-                        const uint64_t d_ah = make_smem_desc(sa), d_al = make_smem_desc(sa + STC_A_BYTES);
-                        const uint64_t d_bh = make_smem_desc(fb), d_bl = make_smem_desc(fb + 2048u);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t adv = (uint64_t)(k * 32 >> 4);
-                            tc_mma_tf32(tmem, d_al + adv, d_bh + adv, idesc, (seg_first && k == 0) ? 0u : 1u);
-                            tc_mma_tf32(tmem, d_ah + adv, d_bl + adv, idesc, 1u);
-                            tc_mma_tf32(tmem, d_ah + adv, d_bh + adv, idesc, 1u);
-                        }
-                        tc_commit(smem_u32(&s_empty[st]));
-                        if (seg_last) tc_commit(smem_u32(&s_acc));
-                    }
+            } else if (warp == 1 || warp >= 10) {
+                int kb = a_lo % kba;
+                const uint32_t ftb_m = smem_u32(ftb);
+                for (int i = 0; i < nun; ++i) {
+                    const bool seg_first = (i == 0 || kb == 0), seg_last = (i == nun - 1 || kb == kba - 1);
+                    issue(ucount + i, tmem + STC_ACC_COL, ftb_m + (uint32_t)kb * 4096u, seg_first);
+                    if (seg_last) tc_commit_elect(smem_u32(&s_acc));
+                    if (++kb == kba) kb = 0;
                 }
             } else {
                 int seg = 0, kb_first = 0;
@@ -301,26 +433,18 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
                     const int smp = u / (NPT * kba), r = u - smp * (NPT * kba), pt = r / kba, kb = r - pt * kba;
                     const bool seg_first = (i == 0 || kb == 0), seg_last = (i == nun - 1 || kb == kba - 1);
                     if (seg_first) kb_first = kb;
-                    const uint32_t st = (ucount + i) % STC_NSTG, ph = ((ucount + i) / STC_NSTG) & 1u;
-                    mbar_wait(smem_u32(&s_full[st]), ph);
-                    float4* ahi = reinterpret_cast<float4*>(base + (size_t)st * STC_STAGE_BYTES);
-                    float4* alo = ahi + STC_A_BYTES / 16;
-                    float4 xa[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) xa[j] = ahi[ct + STC_CT * j];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) alo[ct + STC_CT * j] = tc_lo_trunc(xa[j]);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_ready[st])) : "memory");
+                    convert_a(ucount + i, true);
+                    convert_done(ucount + i);
                     if (seg_last) {
                         // T[p][tap] of the finished segment: TMEM -> Tt[tap][p] -> shift-add over the taps -> qslots
                         mbar_wait(smem_u32(&s_acc), (acount + seg) & 1u);
                         tc_fence_after();
-                        uint32_t v[8];
-                        tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 8), v);
+                        uint32_t v0[8], v1[8], v2[8];
+                        const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(STC_ACC_COL + half * 8);
+                        tmem_ld8(ta, v0); tmem_ld8(ta + 16u, v1); tmem_ld8(ta + 32u, v2);
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) Tt[(half * 8 + t) * STC_TT_PITCH + q * 32 + lane] = __uint_as_float(v[t]);
+                        for (int t = 0; t < 8; ++t)
+                            Tt[(half * 8 + t) * STC_TT_PITCH + q * 32 + lane] = (__uint_as_float(v0[t]) + __uint_as_float(v1[t])) + __uint_as_float(v2[t]);
                         tc_fence_before();
                         asm volatile("bar.sync 1, %0;" ::"n"(STC_CT) : "memory");
                         float* dst = Q.qslots + ((size_t)(smp * NPT + pt) * kba + kb_first) * NPOS;
@@ -355,43 +479,26 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
         if (nun > 0) {
             const int chunk0 = t_lo / per_chunk;
             if (warp == 0) {
-                if (lane == 0) {
-                    for (int i = 0; i < nun; ++i) {
-                        const int u = t_lo + i;
-                        const int chunk = u / per_chunk, r = u - chunk * per_chunk, smp = r / KBT, kb = r - smp * KBT;
-                        const uint32_t st = (ucount + i) % STC_NSTG, ph = ((ucount + i) / STC_NSTG) & 1u;
-                        mbar_wait(smem_u32(&s_empty[st]), ph ^ 1u);
-                        const uint32_t full = smem_u32(&s_full[st]);
-                        mbar_expect_tx(full, STC_A_BYTES);
-                        tma_load_3d(base_u32 + st * STC_STAGE_BYTES, &Q.map_t, full, kb * 32, chunk * 128, smp);
-                    }
+                int chunk = chunk0, r0 = t_lo - chunk0 * per_chunk, smp = r0 / KBT, kb = r0 - smp * KBT;
+                for (int i = 0; i < nun; ++i) {
+                    utr_i = i;
+                    produce(ucount + i, &Q.map_t, kb * 32, chunk * 128, smp);
+                    if (++kb == KBT) { kb = 0; if (++smp == n) { smp = 0; ++chunk; } }
                 }
-            } else if (warp == 1) {
-                if (lane == 0) {
-                    uint32_t touched = 0;
-                    for (int i = 0; i < nun; ++i) {
-                        const int u = t_lo + i;
-                        const int cl = u / per_chunk - chunk0;
-                        const uint32_t st = (ucount + i) % STC_NSTG, ph = ((ucount + i) / STC_NSTG) & 1u;
-                        mbar_wait(smem_u32(&s_ready[st]), ph);
-                        tc_fence_after();
-                        const uint32_t sa = base_u32 + st * STC_STAGE_BYTES;
-                        const uint64_t d_ah = make_smem_desc(sa), d_al = make_smem_desc(sa + STC_A_BYTES);
-                        const uint64_t d_bh = make_smem_desc(sa + 2 * STC_A_BYTES), d_bl = make_smem_desc(sa + 2 * STC_A_BYTES + 2048);
-                        const uint32_t acc = tmem + (uint32_t)(cl * 16);
-                        const bool first = ((touched >> cl) & 1u) == 0u;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t adv = (uint64_t)(k * 32 >> 4);
-                            tc_mma_tf32(acc, d_al + adv, d_bh + adv, idesc, (first && k == 0) ? 0u : 1u);
-                            tc_mma_tf32(acc, d_ah + adv, d_bl + adv, idesc, 1u);
-                            tc_mma_tf32(acc, d_ah + adv, d_bh + adv, idesc, 1u);
-                        }
-                        touched |= 1u << cl;
-                        tc_commit(smem_u32(&s_empty[st]));
-                    }
-                    tc_commit(smem_u32(&s_acc));
+            } else if (warp == 1 || warp >= 10) {
+                uint32_t touched = 0;
+                int cl = 0, left = (chunk0 + 1) * per_chunk - t_lo;      // units left in the current chunk
+                const uint32_t ns_m = (uint32_t)NS, base_al = base_u32;
+                uint32_t s = ucount % ns_m;
+                for (int i = 0; i < nun; ++i) {
+                    utr_i = i;
+                    issue(ucount + i, tmem + (uint32_t)(STC_ACC_COL + cl * 48), base_al + s * STC_STAGE_BYTES + STC_A_BYTES,
+                          ((touched >> cl) & 1u) == 0u);
+                    touched |= 1u << cl;
+                    if (--left == 0) { ++cl; left = per_chunk; }
+                    if (++s == ns_m) s = 0;
                 }
+                tc_commit_elect(smem_u32(&s_acc));
             } else {
                 const int tap = ct >> 4, kk0 = (ct & 15) * 2;          // this thread's two R^T elements: (tap, kk0), (tap, kk0 + 1)
                 const int dy = tap >> 2, dx = tap & 3;
@@ -401,7 +508,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
                     const int chunk = u / per_chunk, r = u - chunk * per_chunk, smp = r / KBT, kb = r - smp * KBT;
                     int j = 0;
                     for (int jj = 1; jj < ns; ++jj) j = (s_state[jj] == smp) ? jj : j;
-                    // R^T values first (they do not depend on the TMA data)
+                    utr_i = i;
                     float rv[2];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -410,31 +517,26 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
                         const int oy = iy - dy + 2, ox = ix - dx + 2;
                         rv[h] = (px < NPX && oy >= 0 && oy < OS && ox >= 0 && ox < OS) ? sT[j * NPOS + oy * OS + ox] : 0.f;
                     }
-                    const uint32_t st = (ucount + i) % STC_NSTG, ph = ((ucount + i) / STC_NSTG) & 1u;
-                    mbar_wait(smem_u32(&s_full[st]), ph);
-                    uint8_t* sb = base + (size_t)st * STC_STAGE_BYTES;
-                    float4* ahi = reinterpret_cast<float4*>(sb);
-                    float4* alo = ahi + STC_A_BYTES / 16;
-                    float4 xa[4];
-#pragma unroll
-                    for (int jx = 0; jx < 4; ++jx) xa[jx] = ahi[ct + STC_CT * jx];
-#pragma unroll
-                    for (int jx = 0; jx < 4; ++jx) alo[ct + STC_CT * jx] = tc_lo_trunc(xa[jx]);
-                    *reinterpret_cast<float2*>(sb + 2 * STC_A_BYTES + boff) = make_float2(rv[0], rv[1]);
-                    *reinterpret_cast<float2*>(sb + 2 * STC_A_BYTES + 2048 + boff) = make_float2(lo_trunc(rv[0]), lo_trunc(rv[1]));
+                    // (the B area of the stage is free: the tfree wait inside convert_a covers the MMAs of unit ug - NS, NS >= NT)
+                    uint8_t* sb = convert_a(ucount + i, false);
+                    *reinterpret_cast<float2*>(sb + STC_A_BYTES + boff) = make_float2(rv[0], rv[1]);
+                    *reinterpret_cast<float2*>(sb + STC_A_BYTES + 2048 + boff) = make_float2(lo_trunc(rv[0]), lo_trunc(rv[1]));
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_ready[st])) : "memory");
+                    convert_done(ucount + i);
                 }
                 mbar_wait(smem_u32(&s_acc), acount & 1u);
                 tc_fence_after();
                 const int ncl = (t_hi - 1) / per_chunk - chunk0 + 1;
                 for (int cl = 0; cl < ncl; ++cl) {
-                    uint32_t v[8];
-                    tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cl * 16 + half * 8), v);
+                    uint32_t v0[8], v1[8], v2[8];
+                    const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(STC_ACC_COL + cl * 48 + half * 8);
+                    tmem_ld8(ta, v0); tmem_ld8(ta + 16u, v1); tmem_ld8(ta + 32u, v2);
+                    float r[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) r[t] = (__uint_as_float(v0[t]) + __uint_as_float(v1[t])) + __uint_as_float(v2[t]);
                     float* dst = Q.gpart + (((size_t)b * STC_MAXCH + cl) * 128 + q * 32 + lane) * 16 + half * 8;
-                    __stcg(reinterpret_cast<float4*>(dst), make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])));
-                    __stcg(reinterpret_cast<float4*>(dst) + 1, make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7])));
+                    __stcg(reinterpret_cast<float4*>(dst), make_float4(r[0], r[1], r[2], r[3]));
+                    __stcg(reinterpret_cast<float4*>(dst) + 1, make_float4(r[4], r[5], r[6], r[7]));
                 }
             }
         }
@@ -542,7 +644,9 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
         __syncthreads();
 
         SD_STAMP(tb + 1);
+        utr = (P.trace && b == 0 && it == 0) ? reinterpret_cast<long long*>(P.trace) + 128 : nullptr;
         sweep_adjoint();
+        utr = nullptr;
         SD_STAMP(tb + 2);
         grid_barrier(Q.barrier, epoch);
         SD_STAMP(tb + 3);
@@ -663,31 +767,19 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)STC_TMEM_COLS) : "memory");
     }
 }
 
-// [n][C][NPX] -> [n][NPX][C] (32 x 32 tiles through shared memory)
-__global__ void nchw_to_nhwc_tile_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int NPX) {
-    __shared__ float tile[32][33];
-    const int s = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
-    const float* sp = src + (size_t)s * C * NPX;
-    float* dp = dst + (size_t)s * C * NPX;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int c = c0 + r, p = p0 + threadIdx.x;
-        tile[r][threadIdx.x] = (c < C && p < NPX) ? sp[(size_t)c * NPX + p] : 0.f;
-    }
-    __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int p = p0 + r, c = c0 + threadIdx.x;
-        if (p < NPX && c < C) dp[(size_t)p * C + c] = tile[threadIdx.x][r];
-    }
-}
+std::atomic<int> g_sd_last_tc{0};
 
 template <int FS, int MODE>
 int launch_sd_tc(const SdParams& P0, cudaStream_t st, int* handled) {
     *handled = 0;
-    { const char* v = getenv("B200TRK_SD_TC"); if (!(v ? atoi(v) : 0)) return 0; }
+    g_sd_last_tc.store(0, std::memory_order_relaxed);
+    // default: the tensor-core kernel for large sample memories (its four grid barriers per iteration cost more than the sweeps
+    // save below ~32 samples); B200TRK_SD_TC=0 / 1 forces the CUDA-core / tensor-core kernel
+    { const char* v = getenv("B200TRK_SD_TC"); const int mode = v ? atoi(v) : -1; if (mode == 0 || (mode < 0 && P0.n < 32)) return 0; }
     constexpr int OS = FS + 1, NPOS = OS * OS, NPX = FS * FS, KBT = (NPX + 31) / 32, NPT = (NPX + 127) / 128;
     if (P0.C % 128 != 0 || P0.C / 128 > STC_MAXCH) return 0;
     if ((reinterpret_cast<uintptr_t>(P0.feat) & 15u) != 0) return 0;
@@ -711,34 +803,28 @@ int launch_sd_tc(const SdParams& P0, cudaStream_t st, int* handled) {
     }
     if (smax > 16) return 0;
     const int slice_max = (C * 4 + G - 1) / G + 1;
-    const size_t smem = 1024 + (size_t)STC_NSTG * STC_STAGE_BYTES + (size_t)kba * 4096 + 16 * STC_TT_PITCH * 4 + 2 * (size_t)slice_max * 16 +
-                        (size_t)smax * 6 * NPOS * 4 + (size_t)smax * (STC_QL_MAX + 1) * 4 + 64;
-    if (smem > 227 * 1024 - 1024) return 0;
+    const size_t fixed = 1024 + (size_t)kba * 4096 + 16 * STC_TT_PITCH * 4 + 2 * (size_t)slice_max * 16 +
+                         (size_t)smax * 6 * NPOS * 4 + (size_t)smax * (STC_QL_MAX + 1) * 4 + 64;
+    const size_t limit = 227 * 1024 - 2048;                     // static shared memory of the kernel: ~1.5 KB
+    if (fixed + (size_t)STC_NT * STC_STAGE_BYTES > limit) return 0;
+    int nstg = (int)((limit - fixed) / STC_STAGE_BYTES);
+    if (nstg > STC_NS_MAX) nstg = STC_NS_MAX;
+    const size_t smem = fixed + (size_t)nstg * STC_STAGE_BYTES;
     B200_REQUIRE(P0.num_iter + 1 <= 1024, "sd optimizer: num_iter=%d too large", P0.num_iter);
 
     SdTcParams Q;
     memset(&Q, 0, sizeof(Q));
     Q.p = P0;
-    Q.p.trace = getenv("B200TRK_SD_TRACE") ? (unsigned long long*)workspace(1024, 3) : nullptr;
-    Q.smax = smax; Q.nchk = nchk; Q.kba = kba; Q.slice_max = slice_max;
-
-    // [n][H*W][C] copy of the sample memory for the apply sweep
-    float* nhwc = (float*)workspace((size_t)n * C * NPX * sizeof(float), 6);
-    if (!nhwc) return 3;
-    nchw_to_nhwc_tile_kernel<<<dim3((NPX + 31) / 32, (C + 31) / 32, n), dim3(32, 8), 0, st>>>(P0.feat, nhwc, C, NPX);
-    B200_LAUNCH_CHECK();
+    { const char* v = getenv("B200TRK_SD_DBG"); Q.p.dbg_mode = v ? atoi(v) : 0; }
+    Q.p.trace = getenv("B200TRK_SD_TRACE") ? (unsigned long long*)workspace(4096, 3) : nullptr;
+    Q.smax = smax; Q.nchk = nchk; Q.kba = kba; Q.slice_max = slice_max; Q.ns = nstg;
 
     {
         const uint64_t dims[3] = {(uint64_t)NPX, (uint64_t)C, (uint64_t)n};
         const uint64_t strides[2] = {(uint64_t)NPX * 4, (uint64_t)C * NPX * 4};
-        const uint32_t box[3] = {32, 128, 1};
-        if (int e = tc_make_map(&Q.map_t, const_cast<float*>(P0.feat), 3, dims, strides, box)) return e;
-    }
-    {
-        const uint64_t dims[3] = {(uint64_t)C, (uint64_t)NPX, (uint64_t)n};
-        const uint64_t strides[2] = {(uint64_t)C * 4, (uint64_t)C * NPX * 4};
-        const uint32_t box[3] = {32, 128, 1};
-        if (int e = tc_make_map(&Q.map_a, nhwc, 3, dims, strides, box)) return e;
+        const uint32_t box_t[3] = {32, 128, 1}, box_a[3] = {128, 32, 1};
+        if (int e = tc_make_map(&Q.map_t, const_cast<float*>(P0.feat), 3, dims, strides, box_t, 1)) return e;
+        if (int e = tc_make_map(&Q.map_a, const_cast<float*>(P0.feat), 3, dims, strides, box_a, 0)) return e;
     }
 
     const size_t n_gpart = (size_t)G * STC_MAXCH * 128 * 16, n_q = (size_t)n * NPT * kba * NPOS;
@@ -761,8 +847,9 @@ int launch_sd_tc(const SdParams& P0, cudaStream_t st, int* handled) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* args[] = {(void*)&Q};
     B200_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(G), dim3(STC_THREADS), args, smem, st));
-    g_launch_count.fetch_add(2, std::memory_order_relaxed);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     *handled = 1;
+    g_sd_last_tc.store(1, std::memory_order_relaxed);
     return 0;
 }
 
@@ -776,3 +863,6 @@ template int launch_sd_tc<22, 2>(const SdParams&, cudaStream_t, int*);
 template int launch_sd_tc<22, 3>(const SdParams&, cudaStream_t, int*);
 
 }  // namespace b200trk
+
+// 1 when the most recent steepest-descent optimiser call on this process ran the tcgen05 kernel, 0 for the CUDA-core kernel
+extern "C" int b200trk_sd_last_kernel(void) { return b200trk::g_sd_last_tc.load(); }

@@ -95,8 +95,80 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 }
 
 
-// Host: K-major fp32 tensor map (SWIZZLE_128B, element strides 1, zero OOB fill) of rank 2..4; `strides_bytes` has rank-1 entries
-// (dimension 0 is contiguous). Implemented in conv_tc.cu on cuTensorMapEncodeTiled fetched through the runtime.
-int tc_make_map(CUtensorMap* m, float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+// ---- warp-uniform single-issue forms ------------------------------------------------------------------------------------
+// The producer and MMA warps run their loops with ALL 32 lanes converged and let `elect.sync` pick the issuing lane inside
+// the instruction wrapper. The operands are then provably warp-uniform, ptxas keeps descriptors and addresses in uniform
+// registers and emits the UTCHMMA / UTMALDG instructions back to back; wrapping the whole loop in `if (lane == 0)` instead
+// costs a ~10-instruction ELECT / R2UR.BROADCAST waterfall (~100 cycles) per tcgen05.mma.
+__device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+                 ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_elect(uint32_t bar) {
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void tc_mma_tf32_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x 8 columns (one fp32 / TF32 element per column)
+__device__ __forceinline__ void tc_mma_tf32_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// Descriptor forms for the converged issue loops: the shared-memory descriptor is passed as its LOW 32-bit word only
+// (start address >> 4 | LBO field); the constant high word (SBO = 1024 B, version 1, SWIZZLE_128B = 0x40004040) is attached
+// inside the asm. All operand arithmetic then stays 32-bit in the uniform datapath (UIADD3 + UTCHMMA, no ELECT / R2UR / VOTEU).
+// Values the issue warps share with the other warp roles (the shared-memory base, tile sizes from the kernel parameters) end up
+// in VECTOR registers, and every descriptor derived from them then costs R2UR / ELECT / VOTEU instructions per MMA. The issue
+// warps therefore re-derive them through these volatile wrappers: the front end cannot merge the results with the vector
+// copies, ptxas sees uniform sources (a shared-window constant, a kernel parameter) and keeps the whole chain in uniform registers.
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
+__device__ __forceinline__ uint32_t smem_u32_fresh(const void* p) {
+    uint32_t r;
+    asm volatile("{\n\t.reg .u64 t;\n\tcvta.to.shared.u64 t, %1;\n\tcvt.u32.u64 %0, t;\n\t}" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t make_smem_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void tc_mma_tf32_lo(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, 0x40004040};\n\tmov.b64 db, {%2, 0x40004040};\n\t"
+                 "elect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p, e;\n\t.reg .b64 db;\n\tmov.b64 db, {%2, 0x40004040};\n\t"
+                 "elect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "r"(bdesc_lo), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// Host: fp32 tensor map (element strides 1, zero OOB fill) of rank 2..4, SWIZZLE_128B (box[0] = 32) or no swizzle; `strides_bytes`
+// has rank-1 entries (dimension 0 is contiguous). Implemented in conv_tc.cu on cuTensorMapEncodeTiled fetched through the runtime.
+int tc_make_map(CUtensorMap* m, float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                int swizzle128);
 
 }  // namespace b200trk
