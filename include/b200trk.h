@@ -291,7 +291,8 @@ int b200trk_dimp_state_create(b200trk_dimp_state_t** out, b200trk_net_t* net, in
 int b200trk_dimp_state_destroy(b200trk_dimp_state_t* st);
 /* Device views for the Python host (torch wraps them without copying): */
 float* b200trk_dimp_state_filter(b200trk_dimp_state_t* st);        /* [1,Cc,k,k]  */
-float* b200trk_dimp_state_memory(b200trk_dimp_state_t* st);        /* [memory_size,Cc,Hc,Wc] */
+float* b200trk_dimp_state_memory(b200trk_dimp_state_t* st);        /* [memory_size,Cc,pitch]: each Hc*Wc channel plane starts at a multiple of */
+int b200trk_dimp_state_memory_pitch(b200trk_dimp_state_t* st);     /* `pitch` floats (Hc*Wc rounded up to 32: 128-byte aligned rows for TMA)   */
 float* b200trk_dimp_state_boxes(b200trk_dimp_state_t* st);         /* [memory_size,4] */
 float* b200trk_dimp_state_sample_weights(b200trk_dimp_state_t* st);/* [memory_size] */
 float* b200trk_dimp_state_clf(b200trk_dimp_state_t* st);           /* [max_batch,Cc,Hc,Wc] features of the last crop */

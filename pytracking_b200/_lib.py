@@ -81,6 +81,7 @@ SIGNATURES = {
     "b200trk_dimp_state_create": (_I, [C.POINTER(_VP), _VP, _I, _I, _VP, _VP, _VP, _I, _F, _F, _F, _F, _F]),
     "b200trk_dimp_state_destroy": (_I, [_VP]),
     "b200trk_dimp_state_filter": (_VP, [_VP]),
+    "b200trk_dimp_state_memory_pitch": (_I, [_VP]),
     "b200trk_dimp_state_memory": (_VP, [_VP]),
     "b200trk_dimp_state_boxes": (_VP, [_VP]),
     "b200trk_dimp_state_sample_weights": (_VP, [_VP]),

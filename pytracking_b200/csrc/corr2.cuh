@@ -48,10 +48,12 @@ struct Corr2 {
         const float* feat;   // [n,C,FS,FS]
         int C, n, c0, passes, group, NG;
         int dbg_mode;        // timing experiments only: 1 = skip the FMA tiles, 2 = skip the copies
+        int pstride;         // floats between two channel planes of the sample memory; 0 = dense (FS*FS)
         __device__ __forceinline__ int spc() const { return (n - group + NG - 1) / NG; }
         __device__ __forceinline__ int sample(int j) const { return group + j * NG; }
+        __device__ __forceinline__ int ps() const { return pstride ? pstride : FPLANE; }
         __device__ __forceinline__ const float* src(int j, int p) const {
-            return feat + ((size_t)sample(j) * C + c0 + p * SLOTS) * FPLANE;
+            return feat + ((size_t)sample(j) * C + c0 + p * SLOTS) * ps();
         }
     };
 
@@ -62,7 +64,7 @@ struct Corr2 {
     }
 
     // issue the asynchronous copy of one item (16 planes, dense) into the interior of a padded stage
-    __device__ static __forceinline__ void issue_item(const float* __restrict__ src, float* __restrict__ stage) {
+    __device__ static __forceinline__ void issue_item(const float* __restrict__ src, float* __restrict__ stage, int ps) {
         const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
 #pragma unroll
         for (int m = 0; m < CPT; ++m) {
@@ -71,7 +73,7 @@ struct Corr2 {
                 const int slot = idx / (FS * CHUNK8);
                 const int rem = idx - slot * (FS * CHUNK8);
                 const int row = rem / CHUNK8, ch = rem - row * CHUNK8;
-                const float* g = src + slot * FPLANE + row * FS + ch * 2;
+                const float* g = src + slot * ps + row * FS + ch * 2;
                 const uint32_t d = sbase + (uint32_t)(slot * PLANE + (row + PAD) * PITCH + PAD + ch * 2) * 4u;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(g) : "memory");
             }
@@ -79,13 +81,13 @@ struct Corr2 {
     }
     // one of the CPT copy chunks of an item (interleaved with the FMA rows of the previous item's tile so that the
     // LSU copy traffic overlaps the FMA pipe instead of forming a separate phase)
-    __device__ static __forceinline__ void issue_chunk(const float* __restrict__ src, uint32_t sbase, int m) {
+    __device__ static __forceinline__ void issue_chunk(const float* __restrict__ src, uint32_t sbase, int m, int ps) {
         const int idx = threadIdx.x + m * NCONS;
         if (idx < NCP) {
             const int slot = idx / (FS * CHUNK8);
             const int rem = idx - slot * (FS * CHUNK8);
             const int row = rem / CHUNK8, ch = rem - row * CHUNK8;
-            const float* g = src + slot * FPLANE + row * FS + ch * 2;
+            const float* g = src + slot * ps + row * FS + ch * 2;
             const uint32_t d = sbase + (uint32_t)(slot * PLANE + (row + PAD) * PITCH + PAD + ch * 2) * 4u;
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(g) : "memory");
         }
@@ -99,7 +101,7 @@ struct Corr2 {
     // Loop order (v outer; u, oc inner): 16 consecutive FMAs hit 16 different accumulators; the next patch row is
     // fetched from shared memory before the FMAs of the current one are issued.
     __device__ static __forceinline__ void apply_tile(const float* __restrict__ patch, const float (&w)[16], float (&acc)[20],
-                                                      const float* __restrict__ nsrc, uint32_t nstage) {
+                                                      const float* __restrict__ nsrc, uint32_t nstage, int ps) {
         float4 a = *reinterpret_cast<const float4*>(patch);
         float4 b = *reinterpret_cast<const float4*>(patch + 4);
 #pragma unroll
@@ -110,10 +112,10 @@ struct Corr2 {
                 b = *reinterpret_cast<const float4*>(patch + (r + 1) * PITCH + 4);
             }
             if (nsrc) {
-                issue_chunk(nsrc, nstage, r);
+                issue_chunk(nsrc, nstage, r, ps);
                 if (r == TR + 2) {
 #pragma unroll
-                    for (int m = TR + 3; m < CPT; ++m) issue_chunk(nsrc, nstage, m);
+                    for (int m = TR + 3; m < CPT; ++m) issue_chunk(nsrc, nstage, m, ps);
                 }
             }
 #pragma unroll
@@ -132,7 +134,7 @@ struct Corr2 {
     // g[u*4+v] += sum_{orow,oc} R[orow*4+oc] * x[(5ty+orow+u), (4tx+oc+v)]
     // Loop order (oc outer; u, v inner): 16 consecutive FMAs hit the 16 different gradient taps.
     __device__ static __forceinline__ void transpose_tile(const float* __restrict__ patch, const float (&R)[20], float (&g)[16],
-                                                          const float* __restrict__ nsrc, uint32_t nstage) {
+                                                          const float* __restrict__ nsrc, uint32_t nstage, int ps) {
         float4 a = *reinterpret_cast<const float4*>(patch);
         float4 b = *reinterpret_cast<const float4*>(patch + 4);
 #pragma unroll
@@ -143,10 +145,10 @@ struct Corr2 {
                 b = *reinterpret_cast<const float4*>(patch + (r + 1) * PITCH + 4);
             }
             if (nsrc) {
-                issue_chunk(nsrc, nstage, r);
+                issue_chunk(nsrc, nstage, r, ps);
                 if (r == TR + 2) {
 #pragma unroll
-                    for (int m = TR + 3; m < CPT; ++m) issue_chunk(nsrc, nstage, m);
+                    for (int m = TR + 3; m < CPT; ++m) issue_chunk(nsrc, nstage, m, ps);
                 }
             }
 #pragma unroll
@@ -181,7 +183,7 @@ struct Corr2 {
             if (s < nitems) {
                 int j, p;
                 item_jp<APPLY>(cx, s, j, p);
-                issue_item(cx.src(j, p), stages + s * ITEM_FLOATS);
+                issue_item(cx.src(j, p), stages + s * ITEM_FLOATS, cx.ps());
             }
             commit();
         }
@@ -224,8 +226,8 @@ struct Corr2 {
                 w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
                 w[8] = w2.x; w[9] = w2.y; w[10] = w2.z; w[11] = w2.w; w[12] = w3.x; w[13] = w3.y; w[14] = w3.z; w[15] = w3.w;
             }
-            if (cx.dbg_mode != 1) apply_tile(stages + (t % NST) * ITEM_FLOATS + poff, w, acc, nsrc, nstage);
-            else if (nsrc) issue_item(nsrc, stages + ((t + NST - 1) % NST) * ITEM_FLOATS);
+            if (cx.dbg_mode != 1) apply_tile(stages + (t % NST) * ITEM_FLOATS + poff, w, acc, nsrc, nstage, cx.ps());
+            else if (nsrc) issue_item(nsrc, stages + ((t + NST - 1) % NST) * ITEM_FLOATS, cx.ps());
             commit();
             if (p == cx.passes - 1) {
                 // sum over the 16 channel slots of the half warp, fixed butterfly order (deterministic)
@@ -293,8 +295,8 @@ struct Corr2 {
                     R[o * 4] = v.x; R[o * 4 + 1] = v.y; R[o * 4 + 2] = v.z; R[o * 4 + 3] = v.w;
                 }
             }
-            if (cx.dbg_mode != 1) transpose_tile(stages + (t % NST) * ITEM_FLOATS + poff, R, g, nsrc, nstage);
-            else if (nsrc) issue_item(nsrc, stages + ((t + NST - 1) % NST) * ITEM_FLOATS);
+            if (cx.dbg_mode != 1) transpose_tile(stages + (t % NST) * ITEM_FLOATS + poff, R, g, nsrc, nstage, cx.ps());
+            else if (nsrc) issue_item(nsrc, stages + ((t + NST - 1) % NST) * ITEM_FLOATS, cx.ps());
             commit();
             if (j == spc - 1) {
                 float* rp = red + (tile * SLOTS + slot) * RED_STRIDE;

@@ -4,11 +4,14 @@
 //             get_classification_features, classify_target, max2d of localize_target)
 //   update:   DiMP.update_classifier pytracking/tracker/dimp/dimp.py:605-648 (update_memory + filter_optimizer)
 #include "net.cuh"
+#include "sd_common.cuh"
 #include <vector>
 
 struct b200trk_dimp_state {
     b200trk_net* net = nullptr;
     int memory_size = 0, ksz = 4, Cc = 0, Hc = 0, Wc = 0, Ho = 0, Wo = 0, num_bins = 0, max_batch = 1;
+    int mem_pitch = 0;      // floats between two channel planes of the sample memory: H*W rounded up to 32, so that every 32-pixel
+                            // TMA row of the optimiser is one 128-byte L2 line instead of straddling two
     float bin_displacement = 0.1f, feat_stride = 16.f, step_length = 1.f, reg_weight = 0.01f, alpha_eps = 0.f;
     float *filter = nullptr, *memory = nullptr, *boxes = nullptr, *sw = nullptr, *clf = nullptr, *scores = nullptr;
     float *crop = nullptr, *maxval = nullptr, *luts = nullptr;
@@ -42,7 +45,8 @@ extern "C" int b200trk_dimp_state_create(b200trk_dimp_state_t** out, b200trk_net
     const size_t plane = (size_t)s->Cc * s->Hc * s->Wc;
     int e = 0;
     if (!e) e = st_alloc(s, (void**)&s->filter, (size_t)s->Cc * 16 * sizeof(float));
-    if (!e) e = st_alloc(s, (void**)&s->memory, plane * memory_size * sizeof(float));
+    s->mem_pitch = (s->Hc * s->Wc + 31) / 32 * 32;
+    if (!e) e = st_alloc(s, (void**)&s->memory, (size_t)s->Cc * s->mem_pitch * memory_size * sizeof(float));
     if (!e) e = st_alloc(s, (void**)&s->boxes, (size_t)memory_size * 4 * sizeof(float));
     if (!e) e = st_alloc(s, (void**)&s->sw, (size_t)memory_size * sizeof(float));
     if (!e) e = st_alloc(s, (void**)&s->clf, plane * s->max_batch * sizeof(float));
@@ -71,6 +75,7 @@ extern "C" int b200trk_dimp_state_destroy(b200trk_dimp_state_t* s) {
 
 extern "C" float* b200trk_dimp_state_filter(b200trk_dimp_state_t* s) { return s ? s->filter : nullptr; }
 extern "C" float* b200trk_dimp_state_memory(b200trk_dimp_state_t* s) { return s ? s->memory : nullptr; }
+extern "C" int b200trk_dimp_state_memory_pitch(b200trk_dimp_state_t* s) { return s ? s->mem_pitch : 0; }
 extern "C" float* b200trk_dimp_state_boxes(b200trk_dimp_state_t* s) { return s ? s->boxes : nullptr; }
 extern "C" float* b200trk_dimp_state_sample_weights(b200trk_dimp_state_t* s) { return s ? s->sw : nullptr; }
 extern "C" float* b200trk_dimp_state_clf(b200trk_dimp_state_t* s) { return s ? s->clf : nullptr; }
@@ -100,14 +105,16 @@ extern "C" int b200trk_dimp_update_host(b200trk_dimp_state_t* s, int scale_ind, 
     B200_REQUIRE(n_stored >= 1 && n_stored <= s->memory_size, "dimp_update_host: n_stored=%d", n_stored);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t plane = (size_t)s->Cc * s->Hc * s->Wc;
-    B200_CHECK_CUDA(cudaMemcpyAsync(s->memory + plane * replace_ind, s->clf + plane * scale_ind, plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    const size_t row = (size_t)s->Hc * s->Wc * sizeof(float);
+    B200_CHECK_CUDA(cudaMemcpy2DAsync(s->memory + (size_t)s->Cc * s->mem_pitch * replace_ind, (size_t)s->mem_pitch * sizeof(float),
+                                      s->clf + plane * scale_ind, row, row, (size_t)s->Cc, cudaMemcpyDeviceToDevice, st));
     B200_CHECK_CUDA(cudaMemcpyAsync(s->boxes + 4 * replace_ind, target_box_host, 4 * sizeof(float), cudaMemcpyHostToDevice, st));
     B200_CHECK_CUDA(cudaMemcpyAsync(s->sw, sample_weights_host, (size_t)n_stored * sizeof(float), cudaMemcpyHostToDevice, st));
     if (num_iter > 0) {
-        if (int e = b200trk_dimp_sd_gn(s->filter, s->filter, s->memory, s->boxes, s->sw, n_stored, s->Cc, s->Hc, s->Wc, s->ksz,
+        if (int e = dimp_sd_gn_pitched(s->filter, s->filter, s->memory, s->mem_pitch, s->boxes, s->sw, n_stored, s->Cc, s->Hc, s->Wc, s->ksz,
                                        num_iter, s->luts, s->luts + s->num_bins, s->luts + 2 * s->num_bins, s->num_bins,
                                        s->bin_displacement, s->feat_stride, s->step_length, s->reg_weight, s->alpha_eps,
-                                       nullptr, nullptr, stream)) return e;
+                                       nullptr, nullptr, st)) return e;
     }
     return 0;
 }

@@ -10,6 +10,7 @@ constexpr int SD_SPC_MAX = 8;    // samples per CTA held in shared memory
 struct SdParams {
     const float* w_in; float* w_out; const float* feat; const float* bb; const float* sample_weight;
     int n, C, passes, NCH, NG, num_iter, spc_max, dbg_mode;
+    int feat_pitch;     // floats between two channel planes of `feat`; 0 = dense H*W (dimp_state keeps a 128-byte aligned pitch)
     // DiMP
     const float* label_lut; const float* mask_lut; const float* spatial_lut; int num_bins; float inv_bin_disp;
     // PrDiMP
@@ -44,5 +45,12 @@ __device__ __forceinline__ float lut_lerp(const float* lut, int nb, float rho) {
 // caller then uses the CUDA-core kernel); non-zero status on error.
 template <int FS, int MODE>
 int launch_sd_tc(const SdParams& P, cudaStream_t st, int* handled);
+
+// b200trk_dimp_sd_gn with an explicit channel-plane pitch of the sample memory (0 = dense); used by dimp_state.cu
+int dimp_sd_gn_pitched(const float* weights, float* weights_out, const float* feat, int feat_pitch, const float* bb,
+                       const float* sample_weight, int n, int C, int H, int W, int k, int num_iter,
+                       const float* label_lut, const float* mask_lut, const float* spatial_lut,
+                       int num_bins, float bin_displacement, float feat_stride, float step_length,
+                       float reg_weight, float alpha_eps, float* iterates_out, float* losses_out, cudaStream_t st);
 
 }  // namespace b200trk

@@ -44,7 +44,7 @@ sd_kernel(SdParams P) {
 
     const int tid = threadIdx.x;
     const int chunk = blockIdx.x % P.NCH, group = blockIdx.x / P.NCH;
-    typename K::Ctx cx{P.feat, P.C, P.n, chunk * cchunk, P.passes, group, P.NG, P.dbg_mode};
+    typename K::Ctx cx{P.feat, P.C, P.n, chunk * cchunk, P.passes, group, P.NG, P.dbg_mode, P.feat_pitch};
     const int spc = cx.spc();
     unsigned epoch = 0;
     const size_t qstride = (size_t)P.NCH * NPOS;
@@ -407,20 +407,20 @@ static int check_common(const char* who, const float* w, float* wo, const float*
 
 using namespace b200trk;
 
-extern "C" int b200trk_dimp_sd_gn(const float* weights, float* weights_out, const float* feat, const float* bb,
-                                  const float* sample_weight, int n, int C, int H, int W, int k, int num_iter,
-                                  const float* label_lut, const float* mask_lut, const float* spatial_lut,
-                                  int num_bins, float bin_displacement, float feat_stride, float step_length,
-                                  float reg_weight, float alpha_eps, float* iterates_out, float* losses_out,
-                                  b200trk_stream_t stream) {
+int b200trk::dimp_sd_gn_pitched(const float* weights, float* weights_out, const float* feat, int feat_pitch, const float* bb,
+                                const float* sample_weight, int n, int C, int H, int W, int k, int num_iter,
+                                const float* label_lut, const float* mask_lut, const float* spatial_lut,
+                                int num_bins, float bin_displacement, float feat_stride, float step_length,
+                                float reg_weight, float alpha_eps, float* iterates_out, float* losses_out, cudaStream_t st) {
     if (int e = check_common("dimp_sd_gn", weights, weights_out, feat, bb, n, C, H, W, k, num_iter)) return e;
     B200_REQUIRE(label_lut && mask_lut && spatial_lut && num_bins >= 2, "dimp_sd_gn: LUTs missing");
     B200_REQUIRE(bin_displacement > 0.f && feat_stride > 0.f, "dimp_sd_gn: bad bin_displacement / feat_stride");
-    cudaStream_t st = (cudaStream_t)stream;
+    B200_REQUIRE(feat_pitch == 0 || (feat_pitch >= H * W && feat_pitch % 2 == 0), "dimp_sd_gn: bad channel-plane pitch %d", feat_pitch);
     if (iterates_out)
         B200_CHECK_CUDA(cudaMemcpyAsync(iterates_out, weights, (size_t)C * 16 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     SdParams P{};
     P.w_in = weights; P.w_out = weights_out; P.feat = feat; P.bb = bb; P.sample_weight = sample_weight;
+    P.feat_pitch = (feat_pitch == H * W) ? 0 : feat_pitch;
     P.n = n; P.C = C; P.num_iter = num_iter;
     P.label_lut = label_lut; P.mask_lut = mask_lut; P.spatial_lut = spatial_lut; P.num_bins = num_bins;
     P.inv_bin_disp = 1.0f / bin_displacement; P.inv_feat_stride = 1.0f / feat_stride;
@@ -428,6 +428,17 @@ extern "C" int b200trk_dimp_sd_gn(const float* weights, float* weights_out, cons
     P.iterates_out = iterates_out; P.losses_out = losses_out;
     if (H == 18) return launch_sd<18, 0>(P, st);
     return launch_sd<22, 0>(P, st);
+}
+
+extern "C" int b200trk_dimp_sd_gn(const float* weights, float* weights_out, const float* feat, const float* bb,
+                                  const float* sample_weight, int n, int C, int H, int W, int k, int num_iter,
+                                  const float* label_lut, const float* mask_lut, const float* spatial_lut,
+                                  int num_bins, float bin_displacement, float feat_stride, float step_length,
+                                  float reg_weight, float alpha_eps, float* iterates_out, float* losses_out,
+                                  b200trk_stream_t stream) {
+    return dimp_sd_gn_pitched(weights, weights_out, feat, 0, bb, sample_weight, n, C, H, W, k, num_iter, label_lut, mask_lut, spatial_lut,
+                              num_bins, bin_displacement, feat_stride, step_length, reg_weight, alpha_eps, iterates_out, losses_out,
+                              (cudaStream_t)stream);
 }
 
 extern "C" int b200trk_prdimp_sd_newton(const float* weights, float* weights_out, const float* feat, const float* bb,

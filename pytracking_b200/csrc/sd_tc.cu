@@ -64,10 +64,6 @@ struct SdTcParams {
 __device__ __forceinline__ int part_lo(long long U, int G, int b) { return (int)((U * (long long)b) / G); }
 __device__ __forceinline__ int part_owner(long long U, int G, int u) { return (int)((((long long)u + 1) * G - 1) / U); }
 
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -78,33 +74,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
                    "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem], kind::tf32: A = 128 lanes x 8 columns (one fp32 / TF32 element per column)
-__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// Grid barrier for a cooperatively launched kernel without atomics: every CTA publishes its epoch in its own flag and warp 0
-// polls all flags (flags[G], zeroed by the host).
-__device__ __forceinline__ void grid_barrier_flags(unsigned* flags, unsigned& epoch) {
-    __syncthreads();
-    epoch += 1;
-    if (threadIdx.x < 32) {
-        if (threadIdx.x == 0) {
-            __threadfence();
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + blockIdx.x), "r"(epoch) : "memory");
-        }
-        const int G = gridDim.x;
-        long long t0 = clock64();
-        while (true) {
-            bool done = true;
-            for (int k = threadIdx.x; k < G; k += 32) done = done && (ld_acquire_u32(flags + k) >= epoch);
-            if (__all_sync(0xffffffffu, done)) break;
-            if (clock64() - t0 > 4 * TC_WAIT_LIMIT_CLOCKS) __trap();
-        }
-        __threadfence();
-    }
-    __syncthreads();
 }
 __device__ __forceinline__ float lo_trunc(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 // byte offset of element (row, k) inside a K-major SWIZZLE_128B tile of 128-byte rows (tile base 1024-byte aligned)
@@ -323,7 +292,8 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
         mbar_wait(smem_u32(&s_sfree[s]), sp ^ 1u);
         if (lane == 0) UTR(0);
         const uint32_t full = smem_u32(&s_full[s]);
-        if (P.dbg_mode == 4) {          // timing experiment: no TMA traffic (results are garbage)
+        if (P.dbg_mode == 4 || (P.dbg_mode == 5 && (blockIdx.x & 1))) {
+            // timing experiments (results are garbage): 4 = no TMA traffic, 5 = only every second CTA loads
             mbar_arrive_elect(full);
             return;
         }
@@ -820,8 +790,11 @@ int launch_sd_tc(const SdParams& P0, cudaStream_t st, int* handled) {
     Q.smax = smax; Q.nchk = nchk; Q.kba = kba; Q.slice_max = slice_max; Q.ns = nstg;
 
     {
+        // (the pixel dimension stays H*W whatever the pitch: reads past it are TMA zero fill, never the pitch padding)
+        const uint64_t pitch = P0.feat_pitch ? (uint64_t)P0.feat_pitch : (uint64_t)NPX;
+        if ((pitch * 4) % 16 != 0) return 0;
         const uint64_t dims[3] = {(uint64_t)NPX, (uint64_t)C, (uint64_t)n};
-        const uint64_t strides[2] = {(uint64_t)NPX * 4, (uint64_t)C * NPX * 4};
+        const uint64_t strides[2] = {pitch * 4, (uint64_t)C * pitch * 4};
         const uint32_t box_t[3] = {32, 128, 1}, box_a[3] = {128, 32, 1};
         if (int e = tc_make_map(&Q.map_t, const_cast<float*>(P0.feat), 3, dims, strides, box_t, 1)) return e;
         if (int e = tc_make_map(&Q.map_a, const_cast<float*>(P0.feat), 3, dims, strides, box_a, 0)) return e;

@@ -97,9 +97,9 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 
 // ---- warp-uniform single-issue forms ------------------------------------------------------------------------------------
 // The producer and MMA warps run their loops with ALL 32 lanes converged and let `elect.sync` pick the issuing lane inside
-// the instruction wrapper. The operands are then provably warp-uniform, ptxas keeps descriptors and addresses in uniform
-// registers and emits the UTCHMMA / UTMALDG instructions back to back; wrapping the whole loop in `if (lane == 0)` instead
-// costs a ~10-instruction ELECT / R2UR.BROADCAST waterfall (~100 cycles) per tcgen05.mma.
+// the instruction wrapper: wrapping the whole loop in `if (lane == 0)` instead makes ptxas emit an ELECT / R2UR.BROADCAST /
+// BRA.U.ANY waterfall loop around every tcgen05.mma (~100 cycles each). (In a kernel whose role branches are followed by a
+// block barrier ptxas still keeps the descriptors in vector registers and pays R2UR + VOTEU per MMA)
 __device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
     asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
                  ::"r"(bar), "r"(bytes) : "memory");
@@ -126,32 +126,10 @@ __device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
     asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
                  "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]
-__device__ __forceinline__ void tc_mma_tf32_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x 8 columns (one fp32 / TF32 element per column)
-__device__ __forceinline__ void tc_mma_tf32_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
 
 // Descriptor forms for the converged issue loops: the shared-memory descriptor is passed as its LOW 32-bit word only
 // (start address >> 4 | LBO field); the constant high word (SBO = 1024 B, version 1, SWIZZLE_128B = 0x40004040) is attached
-// inside the asm. All operand arithmetic then stays 32-bit in the uniform datapath (UIADD3 + UTCHMMA, no ELECT / R2UR / VOTEU).
-// Values the issue warps share with the other warp roles (the shared-memory base, tile sizes from the kernel parameters) end up
-// in VECTOR registers, and every descriptor derived from them then costs R2UR / ELECT / VOTEU instructions per MMA. The issue
-// warps therefore re-derive them through these volatile wrappers: the front end cannot merge the results with the vector
-// copies, ptxas sees uniform sources (a shared-window constant, a kernel parameter) and keeps the whole chain in uniform registers.
-__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
-__device__ __forceinline__ uint32_t smem_u32_fresh(const void* p) {
-    uint32_t r;
-    asm volatile("{\n\t.reg .u64 t;\n\tcvta.to.shared.u64 t, %1;\n\tcvt.u32.u64 %0, t;\n\t}" : "=r"(r) : "l"(p));
-    return r;
-}
+// inside the asm, so that the per-MMA operand arithmetic is 32-bit.
 __device__ __forceinline__ uint32_t make_smem_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ void tc_mma_tf32_lo(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, 0x40004040};\n\tmov.b64 db, {%2, 0x40004040};\n\t"

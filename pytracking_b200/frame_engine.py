@@ -23,8 +23,13 @@ class _DevView:
                                          "strides": None}
 
 
-def _view(ptr, shape, owner, device):
-    return torch.as_tensor(_DevView(ptr, shape, owner), device=device)
+def _view(ptr, shape, owner, device, plane_pitch=None):
+    """plane_pitch: floats between two [H,W] planes of a [n,C,H,W] buffer (None = dense) -> a strided view, no copy."""
+    if plane_pitch is None or plane_pitch == shape[-1] * shape[-2]:
+        return torch.as_tensor(_DevView(ptr, shape, owner), device=device)
+    n, c, h, w = shape
+    flat = torch.as_tensor(_DevView(ptr, (n * c * plane_pitch,), owner), device=device)
+    return flat.as_strided((n, c, h, w), (c * plane_pitch, plane_pitch, w, 1))
 
 
 class SampleWeights:
@@ -92,7 +97,7 @@ class DiMPFrameEngine:
         self.out_sz = (hc + (filter_size + 1) % 2, wc + (filter_size + 1) % 2)
         dev = self.device
         self.filter = _view(L.b200trk_dimp_state_filter(h), (1, cc, filter_size, filter_size), self, dev)
-        self.memory = _view(L.b200trk_dimp_state_memory(h), (memory_size, cc, hc, wc), self, dev)
+        self.memory = _view(L.b200trk_dimp_state_memory(h), (memory_size, cc, hc, wc), self, dev, L.b200trk_dimp_state_memory_pitch(h))
         self.boxes = _view(L.b200trk_dimp_state_boxes(h), (memory_size, 4), self, dev)
         self.sample_weights = _view(L.b200trk_dimp_state_sample_weights(h), (memory_size,), self, dev)
         self.clf = _view(L.b200trk_dimp_state_clf(h), (max_batch, cc, hc, wc), self, dev)

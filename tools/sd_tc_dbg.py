@@ -8,7 +8,7 @@ p = synth.make_dimp_optimizer_params(seed=3)
 luts = [p[k].cuda() for k in ("label_map_predictor.weight", "target_mask_predictor.0.weight", "spatial_weight_predictor.weight")]
 feat = synth.make_clf_features(3, 50, 512, 18, 18).cuda(); bb = synth.make_boxes(4, 50).cuda(); sw = torch.full((50,), 1.0 / 50).cuda()
 w0 = torch.zeros(1, 512, 4, 4).cuda()
-for dbg in (0, 1, 2, 3, 4):
+for dbg in (0, 1, 2, 3, 4, 5):
     os.environ["B200TRK_SD_DBG"] = str(dbg)
     for _ in range(3):
         ops.dimp_sd_gn(w0, feat, bb, sw, *luts, 3, 0.9, 0.01)
@@ -19,15 +19,16 @@ for dbg in (0, 1, 2, 3, 4):
     b = 8 + 10
     d = [(t[b+k+1]-t[b+k])/1e3 for k in range(8)]
     print("dbg %d: s0 sweepA %.2f | it1: resid %.2f | sweepT %.2f | barrier1 %.2f | gsum+b1b+FT %.2f | sweepA %.2f | barrier2 %.2f | qsum+h %.2f | barrier3 %.2f" % (dbg, (t[2]-t[1])/1e3, *d), flush=True)
-os.environ["B200TRK_SD_DBG"] = "0"
-for _ in range(3):
+for dbgu in (0, 5):
+  os.environ["B200TRK_SD_DBG"] = str(dbgu)
+  for _ in range(3):
     ops.dimp_sd_gn(w0, feat, bb, sw, *luts, 3, 0.9, 0.01)
-torch.cuda.synchronize()
-ub = (C.c_uint64 * 256)()
-_lib.check(_lib.lib().b200trk_debug_sd_units(ub))
-u = np.array(list(ub), dtype=np.float64).reshape(32, 8)
-t0 = u[0, 0]
-print("unit: sfree_ok tma_issued | full_ok tfree_ok st_done arrived | tready_ok committed   (SM clocks since first)")
-for i in range(20):
+  torch.cuda.synchronize()
+  ub = (C.c_uint64 * 256)()
+  _lib.check(_lib.lib().b200trk_debug_sd_units(ub))
+  u = np.array(list(ub), dtype=np.float64).reshape(32, 8)
+  t0 = u[0, 0]
+  print("dbg %d  unit: sfree_ok tma_issued | full_ok tfree_ok st_done arrived | tready_ok committed   (SM clocks since first)" % dbgu)
+  for i in range(14):
     if u[i, 0] == 0: break
     print("%2d: " % i + " ".join("%7d" % (x - t0) for x in u[i]))
