@@ -1,3 +1,6 @@
 cd /root/repo
-timeout 300 python -m pytest tests -m gpu -q 2>&1 | tail -4
-timeout 400 python bench.py --steps 100 --warmup 10 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['roofline'])"
+export B200TRK_SD_FILL=ldg
+B200TRK_SD_TC=1 timeout 300 python -m pytest tests -m gpu -q -k "sd or dimp or hinge or l2 or track" 2>&1 | tail -4
+cd tools
+timeout 200 python sd_tc_check.py 2>&1 | grep "tc=1\|rel" | cut -c1-150
+timeout 120 python sd_tc_dbg.py 2>&1 | grep "dbg 0" | head -2
