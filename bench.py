@@ -34,7 +34,7 @@ SD_ITERS = 10
 # dram__bytes_read.sum + dram__bytes_write.sum of one sd_kernel launch (n=50, 10 it) from the committed ncu --set full
 # capture profiles/r01g_ncu_full_sd_and_conv.txt: the sample memory is read from HBM once per call and stays L2 resident.
 SD_DRAM_TRAFFIC_BYTES = 33330944 + 121600
-# the same for one sd_tc_kernel launch (profiles/r01j_sd_tc_ncu.txt)
+# the same for one sd_tc_kernel launch (profiles/r01j_sd_tc_pipeline.txt, section 4)
 SD_TC_DRAM_TRAFFIC_BYTES = 33360000 + 257540
 POOL = 160          # distinct crops per rank (160 x 995 KB = 159 MB > 126 MB L2: a step's input is never L2 resident)
 
@@ -248,7 +248,7 @@ def run_b200(args, rank, world, local_rank):
         "metric": "DiMP-50 tracked frames/sec (288x288 synthetic search crops, 10 SD iters/frame)",
         "value": world * K / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (3xTF32 error-compensated tensor-core convs; fp32 CUDA-core correlation/optimiser)" if args.precision == 0 else "f32",
+        "dtype": "f32 (3xTF32 error-compensated tcgen05 convolutions and optimiser sweeps; fp32 CUDA-core correlation)" if args.precision == 0 else "f32",
         "data": "synthetic",
         "config": {"workload": "DiMP-50 single-GPU, synthetic 288x288 crops, 10 SD iters/frame (BASELINE configs[1]); "
                                "one independent sequence per GPU", "backbone": "resnet50->layer3", "memory": MEMORY,

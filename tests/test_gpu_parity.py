@@ -561,3 +561,48 @@ def test_small_stage2_ops(ops):
     filt = torch.randn(1, 256, 1, 1, generator=g)
     ref = torch.matmul(filt.reshape(1, 1, 1, 256), feat.reshape(1, 3, 256, -1)).reshape(3, 1, 18, 18)     # filter.py:82-88
     assert _rel(plugin.apply_filter(feat.cuda(), filt.cuda()), ref) < 1e-5
+
+
+@pytest.mark.parametrize("mode,n,c,h,it", [("dimp", 40, 128, 18, 3), ("prdimp", 9, 256, 22, 3), ("l2", 6, 128, 22, 3), ("hinge_relu", 7, 128, 18, 3),
+                                           ("hinge_bent", 35, 256, 18, 2), ("dimp", 1, 512, 18, 2)])
+def test_sd_tensor_core_kernel_matches_cuda_core_kernel(ops, monkeypatch, mode, n, c, h, it):
+    """The tcgen05 optimiser kernel (sd_tc.cu, B200TRK_SD_TC=1) and the CUDA-core kernel (sd_optimizer.cu, =0) implement the same four
+    reference optimisers; the golden cases with C % 128 != 0 only reach the latter, so every mode is also compared kernel against kernel
+    (and the TMA-free operand fetch, B200TRK_SD_FILL=ldg, against both)."""
+    from pytracking_b200 import _lib
+    g = torch.Generator().manual_seed(100 + n)
+    feat = synth.make_clf_features(90 + n, n, c, h, h).cuda()
+    bb = synth.make_boxes(91 + n, n, center=(h * 16) / 2 - 25).cuda()
+    sw = torch.rand(n, generator=g) + 0.5
+    sw = (sw / sw.sum()).cuda()
+    w0 = (torch.randn(1, c, 4, 4, generator=g) * 0.01).cuda()
+    p = synth.make_dimp_optimizer_params(seed=5)
+    luts = [p[k].cuda() for k in ("label_map_predictor.weight", "target_mask_predictor.0.weight", "spatial_weight_predictor.weight")]
+    lab = torch.rand(n, 1, h + 1, h + 1, generator=g).cuda()
+
+    def run():
+        if mode == "dimp":
+            return ops.dimp_sd_gn(w0, feat, bb, sw, *luts, it, 0.9, 0.01, return_iterates=True, compute_losses=True)
+        if mode == "prdimp":
+            return ops.prdimp_sd_newton(w0, feat, bb, sw, it, 0.25, 1.0, 0.05 ** 2, alpha_eps=0.05, softmax_reg=-1.0, label_threshold=0.05,
+                                        normalize_label=True, label_shrink=0.1, return_iterates=True, compute_losses=True)
+        if mode == "l2":
+            return ops.dimp_l2_sd_gn(w0, feat, bb, sw, it, 1.3, 0.05, 0.9, 0.01, alpha_eps=0.01, return_iterates=True, compute_losses=True)
+        return ops.gn_sd_hinge(w0, feat, lab, sw, it, 0.1, 0.1, 0.1, "relu" if mode == "hinge_relu" else "bentpar", 0.7, 0.02,
+                               return_iterates=True, compute_losses=True)
+
+    res = {}
+    for tag, tc, fill in (("cuda", "0", "tma"), ("tc", "1", "tma"), ("tc_ldg", "1", "ldg")):
+        monkeypatch.setenv("B200TRK_SD_TC", tc)
+        monkeypatch.setenv("B200TRK_SD_FILL", fill)
+        w, its, losses = run()
+        torch.cuda.synchronize()
+        assert int(_lib.lib().b200trk_sd_last_kernel()) == (0 if tc == "0" else 1)
+        res[tag] = (w.clone(), [x.clone() for x in its], losses.clone())
+        w2, _, _ = run()
+        assert torch.equal(w, w2), "%s: not deterministic" % tag
+    for tag in ("tc", "tc_ldg"):
+        assert _rel(res[tag][0], res["cuda"][0]) < 2e-5
+        for a, b in zip(res[tag][1], res["cuda"][1]):
+            assert _rel(a, b) < 2e-5
+        assert np.allclose(res[tag][2].cpu().numpy(), res["cuda"][2].cpu().numpy(), rtol=2e-5)
