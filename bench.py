@@ -34,8 +34,8 @@ SD_ITERS = 10
 # dram__bytes_read.sum + dram__bytes_write.sum of one sd_kernel launch (n=50, 10 it) from the committed ncu --set full
 # capture profiles/r01g_ncu_full_sd_and_conv.txt: the sample memory is read from HBM once per call and stays L2 resident.
 SD_DRAM_TRAFFIC_BYTES = 33330944 + 121600
-# the same for one sd_tc_kernel launch (profiles/r01j_sd_tc_pipeline.txt, section 4)
-SD_TC_DRAM_TRAFFIC_BYTES = 33360000 + 257540
+# the same for one sd_tc_kernel launch on the frame engine's pitched sample memory (profiles/r01j_ncu_full_sd_tc.txt)
+SD_TC_DRAM_TRAFFIC_BYTES = 36231936 + 275200
 POOL = 160          # distinct crops per rank (160 x 995 KB = 159 MB > 126 MB L2: a step's input is never L2 resident)
 
 

@@ -520,7 +520,7 @@ static int tc_configure(b200trk_net* net, const Op& op, TcConv* tc, int S) {
     P.kb_per_split = (P.total_kb + splits - 1) / splits;
     P.splits = (P.total_kb + P.kb_per_split - 1) / P.kb_per_split;
     B200_REQUIRE(ctas <= 512 || P.splits == 1, "tc_conv: counter array too small for %d tiles", ctas);
-    P.ws = net->splitk_ws;
+    P.ws = op.side ? net->splitk_ws2 : net->splitk_ws;
     P.split_mode = env_int("B200TRK_TC_SPLIT_MODE", 2);
     const size_t Kt = (size_t)op.k * op.k * op.Cin;
     if (int e = make_map_2d(&P.b_map, op.w, Kt, op.Cout, BN)) return e;

@@ -59,7 +59,6 @@ struct SdTcParams {
     float* gpart; float* gfinal; float* gnpart; float* qslots; float* hpart; float* lossr; float* lossw;
     unsigned* barrier;
     int smax, nchk, kba, slice_max, ns;
-    int fill_ldg;           // 1: the converter warps fetch their operand rows with plain global loads (no TMA, no shared-memory stage)
 };
 
 __device__ __forceinline__ int part_lo(long long U, int G, int b) { return (int)((U * (long long)b) / G); }
@@ -123,10 +122,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
     uint8_t* base = stc_raw + ((1024u - (smem_u32(stc_raw) & 1023u)) & 1023u);
     const uint32_t base_u32 = smem_u32(base);
     const int NS = Q.ns;
-    const bool ldg = Q.fill_ldg != 0;
-    // operand region: TMA mode = NS stages (A raw | B_hi | B_lo); load mode = STC_NT B tiles (hi | lo) of the adjoint sweep only
-    uint8_t* ftb = base + (ldg ? STC_NT * 4096 : NS * STC_STAGE_BYTES);
-    const int fpitch = P.feat_pitch ? P.feat_pitch : NPX;                 // F^T: [kba][hi 2 KB | lo 2 KB]
+    uint8_t* ftb = base + NS * STC_STAGE_BYTES;                 // F^T: [kba][hi 2 KB | lo 2 KB]
     float* Tt = reinterpret_cast<float*>(ftb + (size_t)kba * 4096);   // [16][STC_TT_PITCH] apply-epilogue staging
     float4* wsl = reinterpret_cast<float4*>(Tt + 16 * STC_TT_PITCH);  // filter slice owned by this CTA
     float4* gsl = wsl + Q.slice_max;                                  // gradient slice
@@ -352,63 +348,11 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-            if (!ldg) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_sfree[s])) : "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_sfree[s])) : "memory");
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_tready[t])) : "memory");
         }
         if (ct == 0) UTR(5);
     };
-    // ---- load mode: operand rows straight from global memory (L2) into registers -----------------------------------------------
-    // A TMA box of 128 rows is served at ~12 B/clk per SM on this access pattern whatever its shape or alignment (measured; neither
-    // half boxes nor idle neighbour SMs change it), so the converter warps fetch their own rows instead: thread = operand row, 16
-    // K elements each (64 contiguous bytes in the adjoint sweep; 16 channel planes x one pixel, 128 bytes per warp and plane, in
-    // the apply sweep), two units ahead of the one being converted, and the values go from the registers to tensor memory.
-    auto load_adjoint = [&](int i, uint32_t (&raw)[16]) {
-        const int per_chunk = n * KBT;
-        const int u = t_lo + i;
-        const int chunk = u / per_chunk, r = u - chunk * per_chunk, smp = r / KBT, kb = r - smp * KBT;
-        const int px0 = kb * 32 + half * 16;
-        const float4* p = reinterpret_cast<const float4*>(P.feat + ((size_t)smp * C + chunk * 128 + q * 32 + lane) * fpitch + px0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 x = (px0 + 4 * j < NPX) ? __ldcg(p + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            raw[4 * j] = __float_as_uint(x.x); raw[4 * j + 1] = __float_as_uint(x.y); raw[4 * j + 2] = __float_as_uint(x.z); raw[4 * j + 3] = __float_as_uint(x.w);
-        }
-    };
-    auto load_apply = [&](int i, uint32_t (&raw)[16]) {
-        const int u = a_lo + i;
-        const int smp = u / (NPT * kba), r = u - smp * (NPT * kba), pt = r / kba, kb = r - pt * kba;
-        const int px = pt * 128 + q * 32 + lane;
-        const float* p = P.feat + ((size_t)smp * C + kb * 32 + half * 16) * fpitch + px;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) raw[j] = (px < NPX) ? __float_as_uint(__ldcg(p + (size_t)j * fpitch)) : 0u;
-    };
-    // registers -> tensor-memory stage (waits for the MMAs of the stage's previous unit)
-    auto stage_regs = [&](uint32_t ug, const uint32_t (&raw)[16]) {
-        const uint32_t t = ug % STC_NT, tp = (ug / STC_NT) & 1u;
-        if (ct == 0) UTR(2);
-        mbar_wait(smem_u32(&s_tfree[t]), tp ^ 1u);
-        tc_fence_after();
-        if (ct == 0) UTR(3);
-        uint32_t lo[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) lo[j] = __float_as_uint(lo_trunc(__uint_as_float(raw[j])));
-        const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + t * 64u + (uint32_t)(half * 16);
-        tmem_st16(ta, raw);
-        tmem_st16(ta + 32u, lo);
-    };
-    // software pipeline of a converter loop: loads run two units ahead through three statically indexed register sets
-#define STC_CONVERT_LOOP(NUN, LOAD, BODY)                                                         \
-    {                                                                                             \
-        uint32_t rA[16], rB[16], rC[16];                                                          \
-        if (ldg) { if (0 < (NUN)) LOAD(0, rA); if (1 < (NUN)) LOAD(1, rB); }                      \
-        for (int i0 = 0; i0 < (NUN); i0 += 3) {                                                   \
-            if (ldg && i0 + 2 < (NUN)) LOAD(i0 + 2, rC);                                          \
-            BODY(i0, rA);                                                                         \
-            if (i0 + 1 < (NUN)) { if (ldg && i0 + 3 < (NUN)) LOAD(i0 + 3, rA); BODY(i0 + 1, rB); } \
-            if (i0 + 2 < (NUN)) { if (ldg && i0 + 4 < (NUN)) LOAD(i0 + 4, rB); BODY(i0 + 2, rC); } \
-        }                                                                                         \
-    }
-
     // MMA issuers: three warps (1, 10, 11), one per product of the 3xTF32 expansion (A_lo*B_hi, A_hi*B_lo, A_hi*B_hi), each into
     // its own 16-column accumulator (acc + 16 * prod); issuing a tcgen05.mma costs one warp ~100 cycles of scalar work, so a single
     // issue warp (12 MMAs per unit) was the slowest stage of the pipeline. A = tensor-memory stage t, B from shared memory.
@@ -439,7 +383,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
             if (warp == 0) {
                 // (whole warp, converged: see tc_ptx.cuh) unit coordinates advance incrementally
                 int smp = a_lo / (NPT * kba), r0 = a_lo - smp * (NPT * kba), pt = r0 / kba, kb = r0 - pt * kba;
-                for (int i = 0; i < (ldg ? 0 : nun); ++i) {
+                for (int i = 0; i < nun; ++i) {
                     produce(ucount + i, &Q.map_a, pt * 128, kb * 32, smp);
                     if (++kb == kba) { kb = 0; if (++pt == NPT) { pt = 0; ++smp; } }
                 }
@@ -454,12 +398,12 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
                 }
             } else {
                 int seg = 0, kb_first = 0;
-                auto body = [&](int i, const uint32_t (&raw)[16]) {
+                for (int i = 0; i < nun; ++i) {
                     const int u = a_lo + i;
                     const int smp = u / (NPT * kba), r = u - smp * (NPT * kba), pt = r / kba, kb = r - pt * kba;
                     const bool seg_first = (i == 0 || kb == 0), seg_last = (i == nun - 1 || kb == kba - 1);
                     if (seg_first) kb_first = kb;
-                    if (ldg) stage_regs(ucount + i, raw); else convert_a(ucount + i, true);
+                    convert_a(ucount + i, true);
                     convert_done(ucount + i);
                     if (seg_last) {
                         // T[p][tap] of the finished segment: TMEM -> Tt[tap][p] -> shift-add over the taps -> qslots
@@ -488,8 +432,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
                         asm volatile("bar.sync 1, %0;" ::"n"(STC_CT) : "memory");
                         ++seg;
                     }
-                };
-                STC_CONVERT_LOOP(nun, load_apply, body)
+                }
             }
         }
         ucount += (uint32_t)nun;
@@ -507,7 +450,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
             const int chunk0 = t_lo / per_chunk;
             if (warp == 0) {
                 int chunk = chunk0, r0 = t_lo - chunk0 * per_chunk, smp = r0 / KBT, kb = r0 - smp * KBT;
-                for (int i = 0; i < (ldg ? 0 : nun); ++i) {
+                for (int i = 0; i < nun; ++i) {
                     utr_i = i;
                     produce(ucount + i, &Q.map_t, kb * 32, chunk * 128, smp);
                     if (++kb == KBT) { kb = 0; if (++smp == n) { smp = 0; ++chunk; } }
@@ -519,8 +462,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
                 uint32_t s = ucount % ns_m;
                 for (int i = 0; i < nun; ++i) {
                     utr_i = i;
-                    issue(ucount + i, tmem + (uint32_t)(STC_ACC_COL + cl * 48),
-                          ldg ? base_al + ((ucount + i) % STC_NT) * 4096u : base_al + s * STC_STAGE_BYTES + STC_A_BYTES,
+                    issue(ucount + i, tmem + (uint32_t)(STC_ACC_COL + cl * 48), base_al + s * STC_STAGE_BYTES + STC_A_BYTES,
                           ((touched >> cl) & 1u) == 0u);
                     touched |= 1u << cl;
                     if (--left == 0) { ++cl; left = per_chunk; }
@@ -531,7 +473,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
                 const int tap = ct >> 4, kk0 = (ct & 15) * 2;          // this thread's two R^T elements: (tap, kk0), (tap, kk0 + 1)
                 const int dy = tap >> 2, dx = tap & 3;
                 const uint32_t boff = sw128(tap, kk0);
-                auto body = [&](int i, const uint32_t (&raw)[16]) {
+                for (int i = 0; i < nun; ++i) {
                     const int u = t_lo + i;
                     const int chunk = u / per_chunk, r = u - chunk * per_chunk, smp = r / KBT, kb = r - smp * KBT;
                     int j = 0;
@@ -545,17 +487,13 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
                         const int oy = iy - dy + 2, ox = ix - dx + 2;
                         rv[h] = (px < NPX && oy >= 0 && oy < OS && ox >= 0 && ox < OS) ? sT[j * NPOS + oy * OS + ox] : 0.f;
                     }
-                    // B tile of the unit: next to the A stage (TMA mode; free because the tfree wait inside convert_a covers the MMAs of
-                    // unit ug - NS, NS >= NT) or in the slot of the tensor-memory stage (load mode)
-                    uint8_t* bt;
-                    if (ldg) { stage_regs(ucount + i, raw); bt = base + ((ucount + i) % STC_NT) * 4096u; }
-                    else bt = convert_a(ucount + i, false) + STC_A_BYTES;
-                    *reinterpret_cast<float2*>(bt + boff) = make_float2(rv[0], rv[1]);
-                    *reinterpret_cast<float2*>(bt + 2048 + boff) = make_float2(lo_trunc(rv[0]), lo_trunc(rv[1]));
+                    // (the B area of the stage is free: the tfree wait inside convert_a covers the MMAs of unit ug - NS, NS >= NT)
+                    uint8_t* sb = convert_a(ucount + i, false);
+                    *reinterpret_cast<float2*>(sb + STC_A_BYTES + boff) = make_float2(rv[0], rv[1]);
+                    *reinterpret_cast<float2*>(sb + STC_A_BYTES + 2048 + boff) = make_float2(lo_trunc(rv[0]), lo_trunc(rv[1]));
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     convert_done(ucount + i);
-                };
-                STC_CONVERT_LOOP(nun, load_adjoint, body)
+                }
                 mbar_wait(smem_u32(&s_acc), acount & 1u);
                 tc_fence_after();
                 const int ncl = (t_hi - 1) / per_chunk - chunk0 + 1;
@@ -838,13 +776,10 @@ int launch_sd_tc(const SdParams& P0, cudaStream_t st, int* handled) {
     const size_t fixed = 1024 + (size_t)kba * 4096 + 16 * STC_TT_PITCH * 4 + 2 * (size_t)slice_max * 16 +
                          (size_t)smax * 6 * NPOS * 4 + (size_t)smax * (STC_QL_MAX + 1) * 4 + 64;
     const size_t limit = 227 * 1024 - 2048;                     // static shared memory of the kernel: ~1.5 KB
-    // operand fetch: TMA stages (default) or, with B200TRK_SD_FILL=ldg, global loads by the converter warps
-    const int fill_ldg = [] { const char* v = getenv("B200TRK_SD_FILL"); return (v && v[0] == 'l') ? 1 : 0; }();
-    if (fixed + (size_t)STC_NT * (fill_ldg ? 4096 : STC_STAGE_BYTES) > limit) return 0;
+    if (fixed + (size_t)STC_NT * STC_STAGE_BYTES > limit) return 0;
     int nstg = (int)((limit - fixed) / STC_STAGE_BYTES);
     if (nstg > STC_NS_MAX) nstg = STC_NS_MAX;
-    if (nstg < STC_NT) nstg = STC_NT;
-    const size_t smem = fixed + (fill_ldg ? (size_t)STC_NT * 4096 : (size_t)nstg * STC_STAGE_BYTES);
+    const size_t smem = fixed + (size_t)nstg * STC_STAGE_BYTES;
     B200_REQUIRE(P0.num_iter + 1 <= 1024, "sd optimizer: num_iter=%d too large", P0.num_iter);
 
     SdTcParams Q;
@@ -852,7 +787,7 @@ int launch_sd_tc(const SdParams& P0, cudaStream_t st, int* handled) {
     Q.p = P0;
     { const char* v = getenv("B200TRK_SD_DBG"); Q.p.dbg_mode = v ? atoi(v) : 0; }
     Q.p.trace = getenv("B200TRK_SD_TRACE") ? (unsigned long long*)workspace(4096, 3) : nullptr;
-    Q.smax = smax; Q.nchk = nchk; Q.kba = kba; Q.slice_max = slice_max; Q.ns = nstg; Q.fill_ldg = fill_ldg;
+    Q.smax = smax; Q.nchk = nchk; Q.kba = kba; Q.slice_max = slice_max; Q.ns = nstg;
 
     {
         // (the pixel dimension stays H*W whatever the pitch: reads past it are TMA zero fill, never the pitch padding)

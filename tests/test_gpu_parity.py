@@ -567,8 +567,7 @@ def test_small_stage2_ops(ops):
                                            ("hinge_bent", 35, 256, 18, 2), ("dimp", 1, 512, 18, 2)])
 def test_sd_tensor_core_kernel_matches_cuda_core_kernel(ops, monkeypatch, mode, n, c, h, it):
     """The tcgen05 optimiser kernel (sd_tc.cu, B200TRK_SD_TC=1) and the CUDA-core kernel (sd_optimizer.cu, =0) implement the same four
-    reference optimisers; the golden cases with C % 128 != 0 only reach the latter, so every mode is also compared kernel against kernel
-    (and the TMA-free operand fetch, B200TRK_SD_FILL=ldg, against both)."""
+    reference optimisers; the golden cases with C % 128 != 0 only reach the latter, so every mode is also compared kernel against kernel."""
     from pytracking_b200 import _lib
     g = torch.Generator().manual_seed(100 + n)
     feat = synth.make_clf_features(90 + n, n, c, h, h).cuda()
@@ -592,16 +591,15 @@ def test_sd_tensor_core_kernel_matches_cuda_core_kernel(ops, monkeypatch, mode, 
                                return_iterates=True, compute_losses=True)
 
     res = {}
-    for tag, tc, fill in (("cuda", "0", "tma"), ("tc", "1", "tma"), ("tc_ldg", "1", "ldg")):
+    for tag, tc in (("cuda", "0"), ("tc", "1")):
         monkeypatch.setenv("B200TRK_SD_TC", tc)
-        monkeypatch.setenv("B200TRK_SD_FILL", fill)
         w, its, losses = run()
         torch.cuda.synchronize()
         assert int(_lib.lib().b200trk_sd_last_kernel()) == (0 if tc == "0" else 1)
         res[tag] = (w.clone(), [x.clone() for x in its], losses.clone())
         w2, _, _ = run()
         assert torch.equal(w, w2), "%s: not deterministic" % tag
-    for tag in ("tc", "tc_ldg"):
+    for tag in ("tc",):
         assert _rel(res[tag][0], res["cuda"][0]) < 2e-5
         for a, b in zip(res[tag][1], res["cuda"][1]):
             assert _rel(a, b) < 2e-5
