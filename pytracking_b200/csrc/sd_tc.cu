@@ -10,7 +10,7 @@
 //       B = F^T[16 taps x 32 channels]      (the filter / gradient, resident in shared memory for the whole sweep)
 //
 // fp32 fidelity as in conv_tc.cu: every operand is split x = hi + lo with hi = the TF32 truncation the datapath applies anyway,
-// three MMAs per K step (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi) into one fp32 TMEM accumulator.
+// three MMAs per K step (A_lo*B_hi, A_hi*B_lo, A_hi*B_hi), each product into its own fp32 TMEM accumulator (summed in the epilogue).
 //
 // Work decomposition: a "unit" is one 128 x 32 operand tile (16 KB of sample memory). The units of a sweep are numbered
 // (adjoint: chunk, sample, pixel block; apply: sample, pixel tile, channel block) and CTA b of G takes the contiguous range
@@ -30,8 +30,9 @@
 // shared memory. The shared-memory stage is free again as soon as it has been read (not when the MMAs retire), so 6 x 20 KB
 // stages cover the L2 latency, and the shared-memory traffic per unit is 16 KB in + 16 KB out instead of ~100 KB.
 //
-// Warp roles during a sweep: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 = operand converters (lo parts, R^T tiles)
-// and epilogue (TMEM -> registers -> partials). All 320 threads run the element-wise phases between the sweeps.
+// Warp roles during a sweep: warp 0 = TMA producer, warps 1 / 10 / 11 = MMA issuers (one per product), warps 2-9 = operand
+// converters (lo parts, R^T tiles) and epilogue (TMEM -> registers -> partials). All 384 threads run the element-wise phases
+// between the sweeps. Measured stage times and what bounds the sweeps: DESIGN.md sections 4.1b and 8, profiles/r01j_sd_tc_pipeline.txt.
 #include "tc_ptx.cuh"
 #include "sd_common.cuh"
 #include <atomic>
