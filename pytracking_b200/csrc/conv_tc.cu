@@ -12,11 +12,13 @@
 // K is walked in 128-byte blocks (32 input channels of one filter tap): one 4-D TMA box {32 ch, BW*stride, BH*stride, 1}
 // (element strides {1, stride, stride, 1}; halo / padding = TMA out-of-bounds zero fill) lands the A tile directly in
 // the canonical K-major SWIZZLE_128B layout that the UMMA shared-memory descriptor expects; a 2-D box {32, BN}
-// does the same for the weights. Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2-5 = operand converter during the main loop (raw -> hi in place, lo next to it, fence.proxy.async), then
-// epilogue (tcgen05.ld -> registers -> smem transpose -> bias/residual/ReLU -> coalesced global stores). Small layers use split-K over
-// gridDim.z; partial tiles go to an L2-resident workspace and the last CTA of a tile reduces them in split order
-// (fixed order => bitwise deterministic).
+// does the same for the weights. Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (both run their loops
+// with the whole warp converged, elect.sync inside the instruction wrappers of tc_ptx.cuh), warps 2-9 = operand converters during
+// the main loop (the raw tile is the hi operand: the TF32 datapath truncates; lo = x - trunc(x) is written next to it,
+// fence.proxy.async), then epilogue (tcgen05.ld -> registers -> smem transpose -> bias/residual/ReLU -> coalesced global stores;
+// warps w and w+4 share a TMEM lane quadrant and split the accumulator columns). Small layers use split-K over gridDim.z:
+// partial tiles go to an L2-resident workspace, a per-tile arrival counter releases ALL split CTAs of the tile, and each of them
+// reduces its share of the tile rows in split order (fixed order => bitwise deterministic).
 #include "net.cuh"
 #include "tc_ptx.cuh"
 #include <cuda.h>
