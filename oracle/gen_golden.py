@@ -330,6 +330,22 @@ def gen_atom_gn():
     np.savez_compressed(os.path.join(GOLDEN, "atom_gn.npz"), **out)
 
 
+def gen_softmax_reg():
+    """ltr/models/layers/activation.py:7-16 softmax_reg over the flattened score map, with and without the extra logit
+    (PrDiMP score pre-processing, pytracking/tracker/dimp/dimp.py:206-210)."""
+    from ltr.models.layers.activation import softmax_reg
+    out = {}
+    g = torch.Generator().manual_seed(4242)
+    for tag, (n, h, reg) in {"a": (5, 23, None), "b": (3, 19, -1.5), "c": (2, 19, 4.0)}.items():
+        x = torch.randn(n, 1, h, h, generator=g) * 3.0
+        y = softmax_reg(x.view(n, 1, -1), dim=2, reg=reg).view(x.shape)
+        out[tag + "_x"] = _np(x).copy()
+        out[tag + "_y"] = _np(y).copy()
+        out[tag + "_reg"] = np.array([np.nan if reg is None else reg], dtype=np.float32)
+    np.savez_compressed(os.path.join(GOLDEN, "softmax_reg.npz"), **out)
+
+
+GENS["softmax_reg"] = gen_softmax_reg
 GENS["atom_gn"] = gen_atom_gn
 GENS["transformer"] = gen_transformer
 GENS["gn_sd_hinge"] = gen_gn_sd_hinge

@@ -604,3 +604,21 @@ def test_sd_tensor_core_kernel_matches_cuda_core_kernel(ops, monkeypatch, mode, 
         for a, b in zip(res[tag][1], res["cuda"][1]):
             assert _rel(a, b) < 2e-5
         assert np.allclose(res[tag][2].cpu().numpy(), res["cuda"][2].cpu().numpy(), rtol=2e-5)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_softmax_reg_golden(golden_dir, ops, tag):
+    g = np.load(os.path.join(golden_dir, "softmax_reg.npz"))
+    x = torch.from_numpy(g[tag + "_x"])
+    reg = None if np.isnan(g[tag + "_reg"][0]) else float(g[tag + "_reg"][0])
+    y = ops.softmax_reg(x.reshape(x.shape[0], -1).cuda(), reg)
+    assert _rel(y, g[tag + "_y"].reshape(x.shape[0], -1)) < 1e-5
+
+
+def test_apply_filter_1x1_golden(G):
+    """The reference's own 1x1 apply_filter output (ltr/models/layers/filter.py:60-88, corr.npz case c) through the plug-in mirror."""
+    from pytracking_b200 import plugin
+    g = G["corr"]
+    feat = synth.make_clf_features(100 + ord("c"), 2, 32, 18, 18, filter_size=1)
+    s = plugin.apply_filter(feat.unsqueeze(1).cuda(), torch.from_numpy(g["c_w"]).cuda())
+    assert _rel(s, g["c_scores"].reshape(s.shape)) < 1e-5

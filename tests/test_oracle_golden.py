@@ -242,3 +242,14 @@ def test_atom_gn_joint(golden_dir, tag):
     w, P = A.atom_gn_joint(torch.from_numpy(g[tag + "_w0"]), torch.from_numpy(g[tag + "_P0"]), x, y, sw, 0.1, 1e-2, ncg, ngn, act, 0.05, fr)
     assert _rel(w, g[tag + "_w"]) < 1e-4
     assert _rel(P, g[tag + "_P"]) < 1e-4
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_softmax_reg_golden(golden_dir, tag):
+    """oracle softmax_reg against the reference's ltr/models/layers/activation.py:softmax_reg outputs."""
+    from oracle import dimp_oracle as O
+    g = np.load(os.path.join(golden_dir, "softmax_reg.npz"))
+    x = torch.from_numpy(g[tag + "_x"])
+    reg = None if np.isnan(g[tag + "_reg"][0]) else float(g[tag + "_reg"][0])
+    y = O.softmax_reg(x.reshape(x.shape[0], x.shape[-2], x.shape[-1]), reg).reshape(x.shape)
+    assert np.allclose(y.numpy(), g[tag + "_y"], rtol=1e-5, atol=1e-9)
