@@ -345,6 +345,20 @@ def gen_softmax_reg():
     np.savez_compressed(os.path.join(GOLDEN, "softmax_reg.npz"), **out)
 
 
+def gen_hann():
+    """pytracking/libs/dcf.py: hann1d / hann2d / hann2d_clipped (the optional output window of localize_target, built at init)."""
+    from pytracking import dcf
+    out = {}
+    for tag, (h, w, c) in {"a": (19, 19, True), "b": (19, 19, False), "c": (18, 18, False), "d": (23, 21, True), "e": (22, 17, False)}.items():
+        out["h2_" + tag] = _np(dcf.hann2d(torch.tensor([h, w]), centered=c)).copy()
+        out["h2_" + tag + "_arg"] = np.array([h, w, int(c)])
+    for tag, (h, w, eh, ew, c) in {"a": (36, 36, 25, 26, True), "b": (36, 36, 25, 26, False), "c": (19, 19, 13, 13, False), "d": (288, 288, 200, 201, False)}.items():
+        out["hc_" + tag] = _np(dcf.hann2d_clipped(torch.tensor([h, w]), torch.tensor([eh, ew]), centered=c)).copy()
+        out["hc_" + tag + "_arg"] = np.array([h, w, eh, ew, int(c)])
+    np.savez_compressed(os.path.join(GOLDEN, "hann.npz"), **out)
+
+
+GENS["hann"] = gen_hann
 GENS["softmax_reg"] = gen_softmax_reg
 GENS["atom_gn"] = gen_atom_gn
 GENS["transformer"] = gen_transformer

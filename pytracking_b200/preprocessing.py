@@ -3,6 +3,8 @@ border mode the trackers of this path use ('replicate').  It runs the same torch
 reference, so the crops are bit-identical (asserted against the reference itself in oracle/gen_track_golden.py); it exists
 so that bench / tests on a machine without the reference tree can feed the engine exactly what the tracker would.
 """
+import math
+
 import torch
 import torch.nn.functional as F
 
@@ -67,3 +69,36 @@ def sample_init_patch(im, pos, scale, img_sample_sz, aug_expansion_factor=None):
     pad_h = (out_sz[0] - patch.shape[2]) / 2
     pad_w = (out_sz[1] - patch.shape[3]) / 2
     return F.pad(patch, (math.floor(pad_w), math.ceil(pad_w), math.floor(pad_h), math.ceil(pad_h)), "replicate")
+
+
+# ---- output windows (host side, built once per sequence; pytracking/libs/dcf.py:8-37) ------------------------------------------
+def hann1d(sz, centered=True):
+    """1-D cosine window of `sz` taps: centred (peak in the middle, zero just outside both ends) or with its peak at tap 0 and the
+    taps wrapped around (the layout of an un-shifted score map).  Bit-exact mirror of dcf.hann1d (float32 arithmetic)."""
+    sz = int(sz)
+    if centered:
+        i = torch.arange(sz, dtype=torch.float32)
+        return 0.5 * (1 - torch.cos((2 * math.pi / (sz + 1)) * (i + 1)))
+    half = 0.5 * (1 + torch.cos((2 * math.pi / (sz + 2)) * torch.arange(0, sz // 2 + 1).float()))
+    idx = torch.tensor([i if i <= sz // 2 else sz - i for i in range(sz)], dtype=torch.long)
+    return half[idx]
+
+
+def hann2d(sz, centered=True):
+    """[1,1,H,W] separable cosine window (dcf.hann2d); sz = (H, W)."""
+    return hann1d(int(sz[0]), centered).reshape(1, 1, -1, 1) * hann1d(int(sz[1]), centered).reshape(1, 1, 1, -1)
+
+
+def hann2d_clipped(sz, effective_sz, centered=True):
+    """dcf.hann2d_clipped: a centred cosine window of `effective_sz` (made to differ from `sz` by an even amount), extended to `sz`
+    by replicating its border, optionally rotated so that its peak sits at index (0, 0)."""
+    sz = [int(sz[0]), int(sz[1])]
+    eff = [int(effective_sz[0]), int(effective_sz[1])]
+    eff = [e + (e - s) % 2 for e, s in zip(eff, sz)]
+    win = hann2d(eff, True)
+    rows = (torch.arange(sz[0]) - (sz[0] - eff[0]) // 2).clamp(0, eff[0] - 1)
+    cols = (torch.arange(sz[1]) - (sz[1] - eff[1]) // 2).clamp(0, eff[1] - 1)
+    win = win[:, :, rows][:, :, :, cols]
+    if centered:
+        return win
+    return torch.roll(win, shifts=(-int(sz[0] / 2), -int(sz[1] / 2)), dims=(2, 3))

@@ -253,3 +253,18 @@ def test_softmax_reg_golden(golden_dir, tag):
     reg = None if np.isnan(g[tag + "_reg"][0]) else float(g[tag + "_reg"][0])
     y = O.softmax_reg(x.reshape(x.shape[0], x.shape[-2], x.shape[-1]), reg).reshape(x.shape)
     assert np.allclose(y.numpy(), g[tag + "_y"], rtol=1e-5, atol=1e-9)
+
+
+def test_hann_windows_golden(golden_dir):
+    """Host mirror of dcf.hann2d / hann2d_clipped (pytracking_b200/preprocessing.py) against the reference's outputs: bit-exact."""
+    from pytracking_b200 import preprocessing as pre
+    g = np.load(os.path.join(golden_dir, "hann.npz"))
+    n = 0
+    for k in g.files:
+        if k.endswith("_arg"):
+            continue
+        a = [int(v) for v in g[k + "_arg"]]
+        w = pre.hann2d(a[:2], bool(a[2])) if k.startswith("h2_") else pre.hann2d_clipped(a[:2], a[2:4], bool(a[4]))
+        assert w.shape == g[k].shape and np.array_equal(w.numpy(), g[k]), k
+        n += 1
+    assert n == 9
