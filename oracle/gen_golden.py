@@ -358,6 +358,20 @@ def gen_hann():
     np.savez_compressed(os.path.join(GOLDEN, "hann.npz"), **out)
 
 
+def gen_tomp_pos():
+    """ltr/models/transformer/position_encoding.py PositionEmbeddingSine as FilterPredictor builds and calls it."""
+    import contextlib, io
+    from ltr.models.transformer.position_encoding import PositionEmbeddingSine
+    out = {}
+    for tag, (h, w, d, res) in {"a": (18, 18, 256, 18), "b": (22, 22, 256, 22), "c": (18, 16, 128, 18)}.items():
+        with contextlib.redirect_stdout(io.StringIO()):
+            pe = PositionEmbeddingSine(num_pos_feats=d // 2, sine_type='lin_sine', avoid_aliazing=True, max_spatial_resolution=res)
+        out[tag] = _np(pe(torch.zeros((1, h, w), dtype=torch.bool))[0]).copy()
+        out[tag + "_arg"] = np.array([h, w, d, res])
+    np.savez_compressed(os.path.join(GOLDEN, "tomp_pos.npz"), **out)
+
+
+GENS["tomp_pos"] = gen_tomp_pos
 GENS["hann"] = gen_hann
 GENS["softmax_reg"] = gen_softmax_reg
 GENS["atom_gn"] = gen_atom_gn

@@ -102,3 +102,22 @@ def hann2d_clipped(sz, effective_sz, centered=True):
     if centered:
         return win
     return torch.roll(win, shifts=(-int(sz[0] / 2), -int(sz[1] / 2)), dims=(2, 3))
+
+
+# ---- ToMP position encoding (host side, constant per feature size; ltr/models/transformer/position_encoding.py:6-58) -----------
+def tomp_position_encoding(h, w, d_model=256, max_spatial_resolution=18):
+    """[d_model, h, w] float32: PositionEmbeddingSine(num_pos_feats=d_model//2, sine_type='lin_sine', avoid_aliazing=True,
+    max_spatial_resolution=...) evaluated on an all-valid mask, as FilterPredictor.get_positional_encoding does
+    (ltr/models/transformer/filter_predictor.py:34-35,41-47).  Pixel centres are normalised to (0,1) per axis, then every
+    coordinate pair (x, y) is expanded into sin / cos of `depth = d_model/4` linearly spaced frequencies k * (res/depth) * pi:
+    channel layout = [sin k=1 (x,y), ..., sin k=depth (x,y), cos k=1 (x,y), ..., cos k=depth (x,y)].  Bit-exact mirror."""
+    depth = (d_model // 2) // 2
+    factor = float(max_spatial_resolution) / depth
+    ys = torch.arange(1, h + 1, dtype=torch.float32).reshape(h, 1).expand(h, w)
+    xs = torch.arange(1, w + 1, dtype=torch.float32).reshape(1, w).expand(h, w)
+    ys = (ys - 0.5) / (ys[-1:, :] + 1e-6)
+    xs = (xs - 0.5) / (xs[:, -1:] + 1e-6)
+    pos = torch.stack([xs, ys], dim=-1)                                           # [h, w, 2]
+    waves = [torch.sin((k + 1) * factor * math.pi * pos) for k in range(depth)] + \
+            [torch.cos((k + 1) * factor * math.pi * pos) for k in range(depth)]
+    return torch.cat(waves, dim=-1).permute(2, 0, 1).contiguous()

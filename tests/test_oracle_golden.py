@@ -268,3 +268,13 @@ def test_hann_windows_golden(golden_dir):
         assert w.shape == g[k].shape and np.array_equal(w.numpy(), g[k]), k
         n += 1
     assert n == 9
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_tomp_position_encoding_golden(golden_dir, tag):
+    """Host mirror of the ToMP position encoding against the reference's PositionEmbeddingSine: bit-exact."""
+    from pytracking_b200 import preprocessing as pre
+    g = np.load(os.path.join(golden_dir, "tomp_pos.npz"))
+    h, w, d, res = [int(v) for v in g[tag + "_arg"]]
+    pos = pre.tomp_position_encoding(h, w, d, res)
+    assert pos.shape == g[tag].shape and np.array_equal(pos.numpy(), g[tag])
