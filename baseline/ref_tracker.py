@@ -1,0 +1,94 @@
+"""Builds and drives the UNMODIFIED reference trackers (baseline/_ref, through baseline/ref_env.py) on seeded random-init networks
+and the synthetic sequence of SURVEY.md 8(d).  Used by `bench.py --impl reference` (CPU arm), by bench.py's PyTorch-CUDA reference
+timing, by the plug-in tests (reference tracker above the engine) and by the golden generators.
+
+The frame loop restates `Tracker._track_sequence` (pytracking/evaluation/tracker.py:176-233): `initialize(image, info)`, then for
+every frame `time.time()` around `tracker.track(image, info)` -- the reference's own clock.  (`Tracker.run_sequence` itself reads
+frames from disk through cv2, which this image does not have, so the loop is restated around the unmodified tracker class.)
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# BASELINE configs[1] ("DiMP-50 single-GPU, synthetic 288x288 crops, 10 SD iters/frame"): parameter/dimp/dimp50.py plus the
+# SURVEY.md 8(d) overrides (random-init scores are ~0.1, so the not-found test is disabled; update every frame with 10 iterations)
+CONFIG_DIMP50 = dict(target_not_found_threshold=-1e9, train_skipping=1, net_opt_update_iter=10)
+
+
+def build_dimp_net(arch="resnet50", seed=0):
+    """Reference constructor (ltr/train_settings/dimp/dimp50.py:91-95 hyper-parameters) + the seeded synthetic weights the engine
+    tests use for the backbone / clf head / optimiser; the IoUNet keeps the constructor's (seeded) random init."""
+    from baseline import ref_env
+    ref_env.install()
+    from pytracking_b200 import synth
+    import ltr.models.tracking.dimpnet as dimpnet
+    torch.manual_seed(seed)
+    ctor = dimpnet.dimpnet50 if arch == "resnet50" else dimpnet.dimpnet18
+    net = ctor(filter_size=4, backbone_pretrained=False, optim_iter=5, clf_feat_norm=True, final_conv=True,
+               optim_init_step=0.9, optim_init_reg=0.1, init_gauss_sigma=0.9, num_dist_bins=100,
+               bin_displacement=0.1, mask_init_factor=3.0)
+    sd = synth.make_dimp_state_dict(arch, seed=seed, lut_seed=3)
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    # the IoUNet of a random-init net predicts O(1e2) IoUs with O(1e3) box gradients; scale its last layer so that the refinement
+    # steps are a few pixels, as with a trained net (the weights stay a deterministic function of `seed`)
+    with torch.no_grad():
+        net.bb_regressor.iou_predictor.weight.mul_(0.02)
+    net.eval()
+    return net
+
+
+def build_dimp(device="cpu", arch="resnet50", use_iou_net=False, overrides=None, seed=0, use_augmentation=True):
+    """-> reference `DiMP` tracker object (pytracking/tracker/dimp/dimp.py), parameters = parameter/dimp/dimp50.py + overrides."""
+    from baseline import ref_env
+    ref_env.install()
+    from pytracking.parameter.dimp import dimp50 as dimp50_params
+    from pytracking.tracker.dimp.dimp import DiMP
+    from pytracking.features.net_wrappers import NetWithBackbone
+    net = build_dimp_net(arch, seed)
+    use_gpu = (device != "cpu")
+    if use_gpu:
+        net = net.cuda()
+    params = dimp50_params.parameters()
+    params.use_gpu = use_gpu
+    params.device = "cuda" if use_gpu else "cpu"
+    wrapper = NetWithBackbone(net_path="unused", use_gpu=use_gpu)
+    wrapper.net = net                    # NetWrapper.load_network reads a checkpoint file; the net is already built
+    wrapper.load_network = lambda: None
+    params.net = wrapper
+    params.use_iou_net = use_iou_net
+    params.use_augmentation = use_augmentation
+    for k, v in dict(CONFIG_DIMP50, **(overrides or {})).items():
+        setattr(params, k, v)
+    return DiMP(params)
+
+
+def run_sequence(tracker, frames, init_bbox, sync=None, seed=0, on_frame=None):
+    """pytracking/evaluation/tracker.py:176-233 around an already constructed tracker.  `sync` (e.g. torch.cuda.synchronize) is
+    called inside the timed bracket of every frame when given.  -> dict(target_bbox [T,4], time [T], init_time)"""
+    torch.manual_seed(seed)              # DiMP.initialize draws random augmentation shifts / IoUNet proposal jitter
+    np.random.seed(seed)
+    t0 = time.time()
+    tracker.initialize(frames[0], {"init_bbox": list(init_bbox)})
+    if sync:
+        sync()
+    out = {"init_time": time.time() - t0, "target_bbox": [], "time": []}
+    for t in range(1, len(frames)):
+        start = time.time()
+        o = tracker.track(frames[t], {})
+        if sync:
+            sync()
+        out["time"].append(time.time() - start)
+        out["target_bbox"].append(o["target_bbox"])
+        if on_frame:
+            on_frame(t, tracker, o)
+    out["target_bbox"] = np.array(out["target_bbox"], dtype=np.float64)
+    out["time"] = np.array(out["time"])
+    return out

@@ -310,6 +310,128 @@ int b200trk_dimp_localize_host(b200trk_dimp_state_t* st, const float* crop_host,
 int b200trk_dimp_update_host(b200trk_dimp_state_t* st, int scale_ind, int replace_ind, const float* target_box_host,
                              const float* sample_weights_host, int n_stored, int num_iter, b200trk_stream_t stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole-frame call: uint8 camera frame in, bounding box out (DiMP.track, pytracking/tracker/dimp/dimp.py:94-175).
+ * Everything between `numpy_to_torch(image)` and `out = {'target_bbox': ...}` runs inside the library: crop sampling
+ * (pytracking/features/preprocessing.py:55-148), backbone + clf head, classify, localisation (dimp.py:196-303), state update
+ * (dimp.py:486-497), memory / sample-weight bookkeeping (dimp.py:429-484) and the online filter update (dimp.py:605-648).
+ * The tracker's scalar state (pos, target_sz, target_scale, ...) is held on the HOST in float32 and evolved with the same
+ * float32 operation sequence torch executes for the reference's tensor expressions, so boxes are bit-identical to the reference's
+ * whenever the arg-max cells and localisation flags agree.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* TrackerParams of pytracking/parameter/dimp/dimp50.py (Python floats are doubles; -1 for an int means "None"). */
+typedef struct {
+    int    image_sample_size;             /* params.image_sample_size (square crop, 288 / 352) */
+    double search_area_scale;             /* 5 */
+    int    sample_memory_size;            /* 50 (must equal the state's memory_size) */
+    double learning_rate;                 /* 0.01 */
+    double hard_negative_learning_rate;   /* 0.02; < 0 = None */
+    double init_samples_minimum_weight;   /* 0.25; 0 = None */
+    int    train_skipping;                /* 20 */
+    int    train_sample_interval;         /* 1 */
+    int    net_opt_iter, net_opt_update_iter, net_opt_hn_iter;   /* 10, 2, 1 */
+    int    update_classifier;             /* 1 */
+    int    advanced_localization;         /* 1 */
+    double target_not_found_threshold, distractor_threshold, hard_negative_threshold;   /* 0.25, 0.8, 0.5 */
+    double target_neighborhood_scale, dispalcement_scale;                                /* 2.2, 0.8 (the reference's spelling) */
+    double uncertain_threshold, hard_sample_threshold;                                   /* -inf, -inf */
+    double target_inside_ratio;           /* 0.2 */
+    double augmentation_expansion_factor; /* 2; 0 = None (only the un-augmented Identity sample is built natively) */
+    int    output_not_found_box;          /* 0 */
+} b200trk_dimp_params_t;
+
+/* Crop request of one frame (sample_patch, preprocessing.py:55-148) -- what the crop kernel executes. */
+typedef struct {
+    int   df;                 /* integer pre-decimation factor */
+    int   os_r, os_c;         /* decimation offsets posl % df */
+    int   tl_r, tl_c;         /* top-left of the patch in the decimated image (may be negative: replicate padding) */
+    int   in_h, in_w;         /* patch size before resampling */
+    int   out_h, out_w;       /* resampled size (image_sample_size, or the augmentation expansion size at initialisation) */
+    int   win_r, win_c;       /* offset of the [image_sample_size]^2 window inside the resampled patch (Identity centre crop) */
+    float coord[4];           /* patch_coord = df * (tl_r, tl_c, br_r, br_c) as float32, un-truncated (preprocessing.py:140) */
+    float sample_pos[2];      /* DiMP.get_sample_location (dimp.py:177-182) */
+    float sample_scale;
+} b200trk_crop_geom_t;
+
+/* What the localisation kernel writes (one 64-byte D2H per frame) -- DiMP.localize_target / localize_advanced, dimp.py:196-303. */
+typedef struct {
+    int   flag;               /* 0 none (plain localisation), 1 normal, 2 hard_negative, 3 uncertain, 4 not_found */
+    int   scale_ind;
+    int   r1, c1, r2, c2;     /* arg-max cell, and the second maximum outside the target neighbourhood (-1 when not computed) */
+    int   use_second;         /* 1: the translation comes from (r2,c2) (dimp.py:291-292) */
+    float score1, score2;
+    float max_score;          /* torch.max(score_map) of the selected scale */
+    int   pad_[6];
+} b200trk_loc_result_t;
+
+/* What one tracked frame did (debugging / tests / bench accounting). */
+typedef struct {
+    float bbox[4];            /* target_bbox (x, y, w, h), float32 exactly as new_state.tolist() holds it */
+    int   flag;               /* as b200trk_loc_result_t.flag */
+    int   updated;            /* 1 if the memory was written this frame */
+    int   replace_ind;
+    int   num_iter;           /* optimiser iterations run this frame */
+    int   n_stored;
+    float learning_rate;
+    float target_box[4];      /* get_iounet_box of the stored sample (x, y, w, h in crop pixels) */
+    float max_score;
+    b200trk_loc_result_t loc;
+    b200trk_crop_geom_t  crop;
+} b200trk_frame_info_t;
+
+typedef struct b200trk_dimp_tracker b200trk_dimp_tracker_t;
+
+/* `state` owns the device side (b200trk_dimp_state_create); NULL gives a host-logic-only tracker (plan / commit below work,
+ * the *_host frame calls fail) -- that is what the CPU tests drive. */
+int b200trk_dimp_tracker_create(b200trk_dimp_tracker_t** out, b200trk_dimp_state_t* state, const b200trk_dimp_params_t* params);
+int b200trk_dimp_tracker_destroy(b200trk_dimp_tracker_t* t);
+
+/* DiMP.initialize (dimp.py:25-90) for the un-augmented configuration (use_augmentation = False, filter_init_zero = True,
+ * use_iou_net = False): scalar state from init_bbox (x, y, w, h), first-frame sample through the crop kernel (expanded patch +
+ * Identity centre crop), net_opt_iter steepest-descent iterations from the zero filter. image: HOST uint8 [H,W,3] RGB. */
+int b200trk_dimp_tracker_initialize_host(b200trk_dimp_tracker_t* t, const uint8_t* image, int H, int W, const double init_bbox[4],
+                                         b200trk_stream_t stream);
+/* Scalar half of initialize only (no device work): used by initialize_host and by the CPU tests. */
+int b200trk_dimp_tracker_init_state(b200trk_dimp_tracker_t* t, int H, int W, const double init_bbox[4], b200trk_crop_geom_t* init_crop,
+                                    float init_target_box[4]);
+/* Adopt the state of a tracker initialised elsewhere (e.g. the reference's DiMP.initialize with its augmentations, run above the
+ * plug-in): the scalars, the host-side sample weights and counters. The device memory / boxes / filter are written by the caller
+ * through the b200trk_dimp_state_* views. frame_num = the reference's self.frame_num. */
+int b200trk_dimp_tracker_adopt(b200trk_dimp_tracker_t* t, int H, int W, const float pos[2], const float target_sz[2], float target_scale,
+                               const float base_target_sz[2], float min_scale_factor, float max_scale_factor,
+                               const float* sample_weights, int num_stored, int num_init, int previous_replace_ind, int frame_num);
+
+/* DiMP.track for one frame. image: HOST uint8 [H,W,3] RGB (pinned for full speed). Returns after the box is known; the online
+ * filter update of the frame (if any) is still running on `stream` (the next call orders itself behind it). */
+int b200trk_dimp_track_host(b200trk_dimp_tracker_t* t, const uint8_t* image, int H, int W, b200trk_frame_info_t* info,
+                            b200trk_stream_t stream);
+
+/* The same frame with the uint8 image already resident in HBM (DEVICE pointer): no H2D copy (bench.py's device-timed `value`). */
+int b200trk_dimp_track_device(b200trk_dimp_tracker_t* t, const uint8_t* image_dev, int H, int W, b200trk_frame_info_t* info,
+                              b200trk_stream_t stream);
+
+/* The two host halves of a frame, exported for tests and for callers that run the device work themselves:
+ * plan_crop = get_centered_sample_pos + sample_patch geometry + get_sample_location for the current state;
+ * commit    = everything after the localisation kernel: translation, update_state, get_iounet_box, update_sample_weights, the
+ *             iteration schedule and the output box. `sample_weights_out` (may be NULL) receives the [sample_memory_size] weights. */
+int b200trk_dimp_tracker_plan_crop(b200trk_dimp_tracker_t* t, b200trk_crop_geom_t* geom);
+int b200trk_dimp_tracker_commit(b200trk_dimp_tracker_t* t, const b200trk_crop_geom_t* geom, const b200trk_loc_result_t* loc,
+                                b200trk_frame_info_t* info, float* sample_weights_out);
+/* Scalar state read-back: out = {pos_r, pos_c, target_sz_r, target_sz_c, target_scale, base_r, base_c, min_scale, max_scale}. */
+int b200trk_dimp_tracker_state(const b200trk_dimp_tracker_t* t, float out[9]);
+
+/* Stand-alone pieces (tests, other trackers): sample_patch + bilinear resize on the device, bit-exact with torch 2.x CPU
+ * `F.interpolate(mode='bilinear')` (fused-multiply-add form of ATen's generic kernel); image DEVICE uint8 [H,W,3],
+ * out DEVICE float [3, win_h, win_w] in 0..255. */
+int b200trk_sample_patch(const uint8_t* image_dev, int H, int W, const b200trk_crop_geom_t* geom, int win_h, int win_w, float* out,
+                         b200trk_stream_t stream);
+/* localize_target / localize_advanced on the device: scores DEVICE [S,Ho,Wo]; neigh [S][2] = target_neigh_sz per scale,
+ * prev_vec [S][2] = prev_target_vec per scale (HOST float32 arrays); result DEVICE b200trk_loc_result_t. */
+int b200trk_dimp_localize(const float* scores, int S, int Ho, int Wo, const b200trk_dimp_params_t* params, const float* neigh,
+                          const float* prev_vec, b200trk_loc_result_t* result_dev, b200trk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

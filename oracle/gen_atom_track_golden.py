@@ -29,7 +29,8 @@ def main():
     ref_shims.install()
     torch.set_num_threads(8)
     torch.manual_seed(1234)
-    from pytracking_b200 import synth, preprocessing as mirror_pre
+    from pytracking_b200 import synth
+    from oracle import preprocessing_ref as mirror_pre
     import ltr.models.bbreg.atom as atom_models
     from pytracking.parameter.atom import multiscale_no_iounet as atom_params
     import pytracking.tracker.atom.atom as atom_mod

@@ -28,7 +28,8 @@ SEQ = 0
 def main():
     ref_shims.install()
     torch.set_num_threads(8)
-    from pytracking_b200 import synth, preprocessing as mirror_pre
+    from pytracking_b200 import synth
+    from oracle import preprocessing_ref as mirror_pre
     import ltr.models.tracking.dimpnet as dimpnet
     from pytracking.parameter.dimp import dimp50 as dimp50_params
     from pytracking.tracker.dimp.dimp import DiMP

@@ -173,9 +173,9 @@ class RefModuleCPU:
 def patch_reference_function(prf):
     """PrRoIPool2DFunction.forward asserts CUDA tensors (functional.py:62-63); lift that check for the CPU oracle run."""
     fn = prf.PrRoIPool2DFunction
-    mod = prf._prroi_pooling
 
     def forward_cpu(ctx, features, rois, pooled_height, pooled_width, spatial_scale):
+        mod = prf._import_prroi_pooling()          # resolved per call, like the reference's own forward (functional.py:44)
         pooled_height, pooled_width, spatial_scale = int(pooled_height), int(pooled_width), float(spatial_scale)
         features, rois = features.contiguous(), rois.contiguous()
         params = (pooled_height, pooled_width, spatial_scale)

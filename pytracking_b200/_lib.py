@@ -37,6 +37,37 @@ class DecLayer(C.Structure):
         "norm3_weight", "norm3_bias")]
 
 
+class DimpParams(C.Structure):
+    """b200trk_dimp_params_t"""
+    _fields_ = [("image_sample_size", C.c_int), ("search_area_scale", C.c_double), ("sample_memory_size", C.c_int),
+                ("learning_rate", C.c_double), ("hard_negative_learning_rate", C.c_double), ("init_samples_minimum_weight", C.c_double),
+                ("train_skipping", C.c_int), ("train_sample_interval", C.c_int), ("net_opt_iter", C.c_int),
+                ("net_opt_update_iter", C.c_int), ("net_opt_hn_iter", C.c_int), ("update_classifier", C.c_int),
+                ("advanced_localization", C.c_int), ("target_not_found_threshold", C.c_double), ("distractor_threshold", C.c_double),
+                ("hard_negative_threshold", C.c_double), ("target_neighborhood_scale", C.c_double), ("dispalcement_scale", C.c_double),
+                ("uncertain_threshold", C.c_double), ("hard_sample_threshold", C.c_double), ("target_inside_ratio", C.c_double),
+                ("augmentation_expansion_factor", C.c_double), ("output_not_found_box", C.c_int)]
+
+
+class CropGeom(C.Structure):
+    """b200trk_crop_geom_t"""
+    _fields_ = [(n, C.c_int) for n in ("df", "os_r", "os_c", "tl_r", "tl_c", "in_h", "in_w", "out_h", "out_w", "win_r", "win_c")] + \
+               [("coord", C.c_float * 4), ("sample_pos", C.c_float * 2), ("sample_scale", C.c_float)]
+
+
+class LocResult(C.Structure):
+    """b200trk_loc_result_t"""
+    _fields_ = [(n, C.c_int) for n in ("flag", "scale_ind", "r1", "c1", "r2", "c2", "use_second")] + \
+               [("score1", C.c_float), ("score2", C.c_float), ("max_score", C.c_float), ("pad_", C.c_int * 6)]
+
+
+class FrameInfo(C.Structure):
+    """b200trk_frame_info_t"""
+    _fields_ = [("bbox", C.c_float * 4), ("flag", C.c_int), ("updated", C.c_int), ("replace_ind", C.c_int), ("num_iter", C.c_int),
+                ("n_stored", C.c_int), ("learning_rate", C.c_float), ("target_box", C.c_float * 4), ("max_score", C.c_float),
+                ("loc", LocResult), ("crop", CropGeom)]
+
+
 # name -> (restype, argtypes); every symbol of include/b200trk.h is listed (tests check the export table against it)
 _VP, _I, _F = C.c_void_p, C.c_int, C.c_float
 SIGNATURES = {
@@ -89,6 +120,19 @@ SIGNATURES = {
     "b200trk_dimp_state_scores": (_VP, [_VP]),
     "b200trk_dimp_localize_host": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _VP]),
     "b200trk_dimp_update_host": (_I, [_VP, _I, _I, _VP, _VP, _I, _I, _VP]),
+    "b200trk_dimp_tracker_create": (_I, [C.POINTER(_VP), _VP, C.POINTER(DimpParams)]),
+    "b200trk_dimp_tracker_destroy": (_I, [_VP]),
+    "b200trk_dimp_tracker_initialize_host": (_I, [_VP, _VP, _I, _I, C.POINTER(C.c_double * 4), _VP]),
+    "b200trk_dimp_tracker_init_state": (_I, [_VP, _I, _I, C.POINTER(C.c_double * 4), C.POINTER(CropGeom), C.POINTER(C.c_float * 4)]),
+    "b200trk_dimp_tracker_adopt": (_I, [_VP, _I, _I, C.POINTER(C.c_float * 2), C.POINTER(C.c_float * 2), _F, C.POINTER(C.c_float * 2),
+                                        _F, _F, _VP, _I, _I, _I, _I]),
+    "b200trk_dimp_track_host": (_I, [_VP, _VP, _I, _I, C.POINTER(FrameInfo), _VP]),
+    "b200trk_dimp_track_device": (_I, [_VP, _VP, _I, _I, C.POINTER(FrameInfo), _VP]),
+    "b200trk_dimp_tracker_plan_crop": (_I, [_VP, C.POINTER(CropGeom)]),
+    "b200trk_dimp_tracker_commit": (_I, [_VP, C.POINTER(CropGeom), C.POINTER(LocResult), C.POINTER(FrameInfo), _VP]),
+    "b200trk_dimp_tracker_state": (_I, [_VP, C.POINTER(C.c_float * 9)]),
+    "b200trk_sample_patch": (_I, [_VP, _I, _I, C.POINTER(CropGeom), _I, _I, _VP, _VP]),
+    "b200trk_dimp_localize": (_I, [_VP, _I, _I, _I, C.POINTER(DimpParams), _VP, _VP, _VP, _VP]),
 }
 
 _lib = None

@@ -10,7 +10,8 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb200trk.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-diag-suppress", "177"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-diag-suppress", "177",
+         "-Xcompiler", "-ffp-contract=off"]      # host float32 state arithmetic must not be fused (dimp_tracker.cu)
 
 
 def _sources():

@@ -3,21 +3,8 @@
 //   localize: DiMP.track lines pytracking/tracker/dimp/dimp.py:103-117 (extract_backbone_features,
 //             get_classification_features, classify_target, max2d of localize_target)
 //   update:   DiMP.update_classifier pytracking/tracker/dimp/dimp.py:605-648 (update_memory + filter_optimizer)
-#include "net.cuh"
-#include "sd_common.cuh"
-#include <vector>
+#include "dimp_state.cuh"
 
-struct b200trk_dimp_state {
-    b200trk_net* net = nullptr;
-    int memory_size = 0, ksz = 4, Cc = 0, Hc = 0, Wc = 0, Ho = 0, Wo = 0, num_bins = 0, max_batch = 1;
-    int mem_pitch = 0;      // floats between two channel planes of the sample memory: H*W rounded up to 32, so that every 32-pixel
-                            // TMA row of the optimiser is one 128-byte L2 line instead of straddling two
-    float bin_displacement = 0.1f, feat_stride = 16.f, step_length = 1.f, reg_weight = 0.01f, alpha_eps = 0.f;
-    float *filter = nullptr, *memory = nullptr, *boxes = nullptr, *sw = nullptr, *clf = nullptr, *scores = nullptr;
-    float *crop = nullptr, *maxval = nullptr, *luts = nullptr;
-    int64_t* maxidx = nullptr;
-    std::vector<void*> owned;
-};
 
 using namespace b200trk;
 
@@ -61,6 +48,12 @@ extern "C" int b200trk_dimp_state_create(b200trk_dimp_state_t** out, b200trk_net
         if (ce == cudaSuccess) ce = cudaMemcpy(s->luts + 2 * num_bins, spatial_lut, num_bins * sizeof(float), cudaMemcpyHostToDevice);
         if (ce != cudaSuccess) { set_error("dimp_state_create: LUT upload failed: %s", cudaGetErrorString(ce)); e = 1; }
     }
+    for (int i = 0; i < b200trk_dimp_state::NSTAGE && !e; ++i) {
+        if (cudaMallocHost((void**)&s->stage[i], (size_t)(4 + memory_size) * sizeof(float)) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->stage_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            set_error("dimp_state_create: pinned staging allocation failed"); e = 1;
+        }
+    }
     if (e) { b200trk_dimp_state_destroy(s); return e; }
     *out = s;
     return 0;
@@ -69,6 +62,10 @@ extern "C" int b200trk_dimp_state_create(b200trk_dimp_state_t** out, b200trk_net
 extern "C" int b200trk_dimp_state_destroy(b200trk_dimp_state_t* s) {
     if (!s) return 0;
     for (void* p : s->owned) cudaFree(p);
+    for (int i = 0; i < b200trk_dimp_state::NSTAGE; ++i) {
+        if (s->stage[i]) cudaFreeHost(s->stage[i]);
+        if (s->stage_ev[i]) cudaEventDestroy(s->stage_ev[i]);
+    }
     delete s;
     return 0;
 }
@@ -97,19 +94,27 @@ extern "C" int b200trk_dimp_localize_host(b200trk_dimp_state_t* s, const float* 
     return 0;
 }
 
-extern "C" int b200trk_dimp_update_host(b200trk_dimp_state_t* s, int scale_ind, int replace_ind, const float* target_box_host,
-                                        const float* sample_weights_host, int n_stored, int num_iter, b200trk_stream_t stream) {
-    B200_REQUIRE(s && target_box_host && sample_weights_host, "dimp_update_host: null pointer");
-    B200_REQUIRE(scale_ind >= 0 && scale_ind < s->max_batch, "dimp_update_host: scale_ind=%d", scale_ind);
-    B200_REQUIRE(replace_ind >= 0 && replace_ind < s->memory_size, "dimp_update_host: replace_ind=%d outside memory of %d", replace_ind, s->memory_size);
-    B200_REQUIRE(n_stored >= 1 && n_stored <= s->memory_size, "dimp_update_host: n_stored=%d", n_stored);
-    cudaStream_t st = (cudaStream_t)stream;
+// Device half of DiMP.update_classifier shared by the host-buffer call below and by dimp_tracker.cu.
+int b200trk::dimp_state_update(b200trk_dimp_state* s, int scale_ind, int replace_ind, const float* target_box_host,
+                               const float* sample_weights_host, int n_stored, int num_iter, cudaStream_t st) {
+    B200_REQUIRE(s && target_box_host && sample_weights_host, "dimp_update: null pointer");
+    B200_REQUIRE(scale_ind >= 0 && scale_ind < s->max_batch, "dimp_update: scale_ind=%d", scale_ind);
+    B200_REQUIRE(replace_ind >= 0 && replace_ind < s->memory_size, "dimp_update: replace_ind=%d outside memory of %d", replace_ind, s->memory_size);
+    B200_REQUIRE(n_stored >= 1 && n_stored <= s->memory_size, "dimp_update: n_stored=%d", n_stored);
     const size_t plane = (size_t)s->Cc * s->Hc * s->Wc;
     const size_t row = (size_t)s->Hc * s->Wc * sizeof(float);
+    // the caller may rewrite its buffers as soon as this returns: stage the 4 + n floats in a pinned slot of our own
+    const int slot = s->stage_next;
+    s->stage_next = (slot + 1) % b200trk_dimp_state::NSTAGE;
+    B200_CHECK_CUDA(cudaEventSynchronize(s->stage_ev[slot]));
+    float* h = s->stage[slot];
+    for (int i = 0; i < 4; ++i) h[i] = target_box_host[i];
+    for (int i = 0; i < n_stored; ++i) h[4 + i] = sample_weights_host[i];
     B200_CHECK_CUDA(cudaMemcpy2DAsync(s->memory + (size_t)s->Cc * s->mem_pitch * replace_ind, (size_t)s->mem_pitch * sizeof(float),
                                       s->clf + plane * scale_ind, row, row, (size_t)s->Cc, cudaMemcpyDeviceToDevice, st));
-    B200_CHECK_CUDA(cudaMemcpyAsync(s->boxes + 4 * replace_ind, target_box_host, 4 * sizeof(float), cudaMemcpyHostToDevice, st));
-    B200_CHECK_CUDA(cudaMemcpyAsync(s->sw, sample_weights_host, (size_t)n_stored * sizeof(float), cudaMemcpyHostToDevice, st));
+    B200_CHECK_CUDA(cudaMemcpyAsync(s->boxes + 4 * replace_ind, h, 4 * sizeof(float), cudaMemcpyHostToDevice, st));
+    B200_CHECK_CUDA(cudaMemcpyAsync(s->sw, h + 4, (size_t)n_stored * sizeof(float), cudaMemcpyHostToDevice, st));
+    B200_CHECK_CUDA(cudaEventRecord(s->stage_ev[slot], st));
     if (num_iter > 0) {
         if (int e = dimp_sd_gn_pitched(s->filter, s->filter, s->memory, s->mem_pitch, s->boxes, s->sw, n_stored, s->Cc, s->Hc, s->Wc, s->ksz,
                                        num_iter, s->luts, s->luts + s->num_bins, s->luts + 2 * s->num_bins, s->num_bins,
@@ -117,4 +122,9 @@ extern "C" int b200trk_dimp_update_host(b200trk_dimp_state_t* s, int scale_ind, 
                                        nullptr, nullptr, st)) return e;
     }
     return 0;
+}
+
+extern "C" int b200trk_dimp_update_host(b200trk_dimp_state_t* s, int scale_ind, int replace_ind, const float* target_box_host,
+                                        const float* sample_weights_host, int n_stored, int num_iter, b200trk_stream_t stream) {
+    return dimp_state_update(s, scale_ind, replace_ind, target_box_host, sample_weights_host, n_stored, num_iter, (cudaStream_t)stream);
 }

@@ -1,74 +1,11 @@
-"""Host-side mirror of the reference crop sampling (pytracking/features/preprocessing.py:6-7, 33-148) for the
-border mode the trackers of this path use ('replicate').  It runs the same torch-CPU operations in the same order as the
-reference, so the crops are bit-identical (asserted against the reference itself in oracle/gen_track_golden.py); it exists
-so that bench / tests on a machine without the reference tree can feed the engine exactly what the tracker would.
+"""Per-sequence host constants of the hot path with bit-exact mirrors of the reference's constructors: the score-map output windows
+(pytracking/libs/dcf.py:8-37) and the ToMP sine position encoding (ltr/models/transformer/position_encoding.py:33-58).  (Crop
+sampling is not here: the engine samples crops on the GPU, csrc/dimp_tracker.cu; the torch-CPU restatement used by the tests lives
+in oracle/preprocessing_ref.py.)
 """
 import math
 
 import torch
-import torch.nn.functional as F
-
-
-def numpy_to_torch(a):
-    """preprocessing.py:6-7: HxWx3 uint8/float ndarray -> [1,3,H,W] float32."""
-    return torch.from_numpy(a).float().permute(2, 0, 1).unsqueeze(0)
-
-
-def sample_patch(im, pos, sample_sz, output_sz=None, mode="replicate"):
-    """preprocessing.py:55-148 (mode 'replicate'). Returns (patch [1,C,h,w], patch_coord [1,4] = (tl_y, tl_x, br_y, br_x))."""
-    if mode != "replicate":
-        raise NotImplementedError("sample_patch mirror: only border_mode 'replicate'")
-    posl = pos.long().clone()
-    if output_sz is not None:
-        resize_factor = torch.min(sample_sz.float() / output_sz.float()).item()
-        df = int(max(int(resize_factor - 0.1), 1))
-    else:
-        df = int(1)
-    sz = sample_sz.float() / df
-    if df > 1:
-        os_ = posl % df
-        posl = (posl - os_) / df
-        im2 = im[..., os_[0].item()::df, os_[1].item()::df]
-    else:
-        im2 = im
-    szl = torch.max(sz.round(), torch.Tensor([2])).long()
-    tl = posl - (szl - 1) / 2
-    br = posl + szl / 2 + 1
-    pad = (-tl[1].int().item(), br[1].int().item() - im2.shape[3], -tl[0].int().item(), br[0].int().item() - im2.shape[2])
-    im_patch = F.pad(im2, pad, "replicate")
-    patch_coord = df * torch.cat((tl, br)).view(1, 4)
-    if output_sz is None or (im_patch.shape[-2] == output_sz[0] and im_patch.shape[-1] == output_sz[1]):
-        return im_patch.clone(), patch_coord
-    im_patch = F.interpolate(im_patch, output_sz.long().tolist(), mode="bilinear")
-    return im_patch, patch_coord
-
-
-def sample_patch_multiscale(im, pos, scales, image_sz, mode="replicate", max_scale_change=None):
-    """preprocessing.py:33-52."""
-    if isinstance(scales, (int, float)):
-        scales = [scales]
-    patch_iter, coord_iter = zip(*(sample_patch(im, pos, s * image_sz, image_sz, mode=mode) for s in scales))
-    return torch.cat(list(patch_iter)), torch.cat(list(coord_iter))
-
-
-def sample_init_patch(im, pos, scale, img_sample_sz, aug_expansion_factor=None):
-    """The un-augmented first-frame sample of DiMP.generate_init_samples (pytracking/tracker/dimp/dimp.py:353-389):
-    the patch is sampled at the augmentation expansion size and the Identity transform crops its centre back to the sample
-    size (pytracking/features/augmentation.py:20-40: F.pad with negative 'replicate' padding)."""
-    import math
-    aug_sz = img_sample_sz.clone()
-    out_sz = None
-    if aug_expansion_factor is not None and aug_expansion_factor != 1:
-        aug_sz = (img_sample_sz * aug_expansion_factor).long()
-        aug_sz += (aug_sz - img_sample_sz.long()) % 2
-        aug_sz = aug_sz.float()
-        out_sz = img_sample_sz.long().tolist()
-    patch, _ = sample_patch(im, pos, scale * aug_sz, aug_sz)
-    if out_sz is None:
-        return patch
-    pad_h = (out_sz[0] - patch.shape[2]) / 2
-    pad_w = (out_sz[1] - patch.shape[3]) / 2
-    return F.pad(patch, (math.floor(pad_w), math.ceil(pad_w), math.floor(pad_h), math.ceil(pad_h)), "replicate")
 
 
 # ---- output windows (host side, built once per sequence; pytracking/libs/dcf.py:8-37) ------------------------------------------

@@ -417,7 +417,7 @@ def test_dimp_tracker_trajectory_replay(golden_dir):
     regenerated here, cropped with the bit-exact mirror of the reference's sample_patch, pushed through the host-buffer frame
     calls of the C ABI, and compared frame by frame: score maps (1e-4), arg-max cell (exact), filter after every online update."""
     from oracle import dimp_oracle as O
-    from pytracking_b200 import preprocessing as pre
+    from oracle import preprocessing_ref as pre
     from pytracking_b200.frame_engine import DiMPFrameEngine, SampleWeights
     g = np.load(os.path.join(golden_dir, "dimp_track.npz"))
     frames, init_bbox = synth.make_sequence(0, num_frames=12)
@@ -479,7 +479,7 @@ def test_atom_tracker_trajectory_replay(golden_dir, ops):
     replayed through the engine: first-frame joint GN-CG optimisation, then per frame backbone -> p-norm -> projection -> conv 'same'
     -> Fourier upsampling -> arg-max, memory update and the CG filter update; open loop from the reference's previous filter."""
     from oracle import dimp_oracle as O
-    from pytracking_b200 import preprocessing as pre
+    from oracle import preprocessing_ref as pre
     from pytracking_b200.engine import BackboneEngine
     g = np.load(os.path.join(golden_dir, "atom_track.npz"))
     frames, init_bbox = synth.make_sequence(1, num_frames=8)

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import dimp_oracle as O
-from pytracking_b200 import preprocessing as pre
+from oracle import preprocessing_ref as pre
 from pytracking_b200 import synth
 
 

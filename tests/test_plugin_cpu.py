@@ -1,0 +1,104 @@
+"""CPU checks of `pytracking_b200.plugin.install()`: every seam of SURVEY.md 8(b) is rebound in the unmodified reference checkout, CPU /
+autograd / unsupported-shape calls fall through to the reference implementation (reference configs with 14x14 or 16x16
+feature maps must not crash after install()), and `uninstall()` restores the checkout.  No CUDA call is made here."""
+import numpy as np
+import pytest
+import torch
+
+from baseline import ref_env
+
+pytestmark = pytest.mark.skipif(not ref_env.reference_available(), reason="reference tree not staged (baseline/_ref)")
+
+SEAMS = ["filter.apply_filter", "filter.apply_feat_transpose", "dcf.max2d", "DiMPSteepestDescentGN.forward",
+         "PrDiMPSteepestDescentNewton.forward", "DiMPL2SteepestDescentGN.forward", "NetWithBackbone.extract_backbone",
+         "DiMPnet.extract_classification_feat", "functional._prroi_pooling", "operation.conv2d", "operation.conv1x1",
+         "ConjugateGradient.run", "GaussNewtonCG.run", "Transformer.forward"]
+
+
+@pytest.fixture()
+def installed():
+    from oracle import ref_shims
+    ref_shims.install(prroi_cpu=False)
+    from pytracking_b200 import plugin
+    names = plugin.install()
+    yield plugin, names
+    plugin.uninstall()
+
+
+def test_install_rebinds_every_seam_and_uninstall_restores(installed):
+    plugin, names = installed
+    for s in SEAMS:
+        assert any(n.endswith(s) for n in names), (s, names)
+    import ltr.models.layers.filter as fl
+    import ltr.models.target_classifier.optimizer as opt
+    patched = fl.apply_filter, opt.DiMPSteepestDescentGN.forward
+    plugin.uninstall()
+    assert fl.apply_filter is not patched[0] and opt.DiMPSteepestDescentGN.forward is not patched[1]
+    assert fl.apply_filter.__module__ == "ltr.models.layers.filter"
+    plugin.install()
+
+
+def test_cpu_and_unsupported_shapes_fall_through(installed):
+    plugin, _ = installed
+    import ltr.models.layers.filter as fl
+    from oracle import dimp_oracle as O
+    g = torch.Generator().manual_seed(0)
+    for hw, k in ((14, 4), (16, 4), (18, 3), (18, 4)):           # dimp50_vot18 (14x14), dimp50_vot19 (16x16), odd filter
+        feat = torch.randn(3, 1, 32, hw, hw, generator=g)
+        filt = torch.randn(1, 32, k, k, generator=g)
+        s = fl.apply_filter(feat, filt)                           # CPU tensors: the reference path
+        assert s.shape[-1] == hw + (k + 1) % 2
+        if k == 4:
+            assert torch.allclose(s.reshape(3, 1, *s.shape[-2:]), O.apply_filter(feat[:, 0], filt), atol=1e-4)
+        r = torch.randn(3, 1, s.shape[-2], s.shape[-1], generator=g)
+        assert fl.apply_feat_transpose(feat, r, (k, k), training=False).shape == (1, 32, k, k)
+    assert not plugin.stats.get("apply_filter")
+    # the mirror functions themselves reject what the library would reject -- with NotImplementedError, not RuntimeError
+    for hw, c, k in ((14, 32, 4), (16, 32, 4), (18, 24, 4), (18, 32, 3)):
+        with pytest.raises(NotImplementedError):
+            plugin.apply_filter(torch.zeros(1, 1, c, hw, hw), torch.zeros(1, c, k, k))
+        with pytest.raises(NotImplementedError):
+            plugin.apply_feat_transpose(torch.zeros(1, 1, c, hw, hw), torch.zeros(1, 1, hw + 1, hw + 1), (k, k))
+    with pytest.raises(NotImplementedError):
+        plugin.apply_filter(torch.zeros(1, 1, 32, 18, 18, dtype=torch.float64), torch.zeros(1, 32, 4, 4, dtype=torch.float64))
+
+
+def test_unsupported_optimizer_modules_are_rejected(installed):
+    plugin, _ = installed
+    import ltr.models.target_classifier.optimizer as opt
+    m = opt.DiMPSteepestDescentGN(num_dist_bins=10, score_act="bentpar", act_param=0.1)
+    with pytest.raises(NotImplementedError):
+        plugin.DiMPSteepestDescentGN.from_module(m)
+    m = opt.DiMPSteepestDescentGN(num_dist_bins=10, mask_act="linear")
+    with pytest.raises(NotImplementedError):
+        plugin.DiMPSteepestDescentGN.from_module(m)
+    plugin.DiMPSteepestDescentGN.from_module(opt.DiMPSteepestDescentGN(num_dist_bins=10))
+
+
+def test_response_activation_probe():
+    from pytracking_b200 import plugin
+    import torch.nn.functional as F
+    assert plugin._probe_activation(lambda x: x) == ("none", 0.0)
+    assert plugin._probe_activation(torch.nn.ReLU(inplace=True)) == ("relu", 0.0)
+    assert plugin._probe_activation(torch.nn.ELU(inplace=True)) == ("elu", 1.0)
+    name, par = plugin._probe_activation(lambda x: F.elu(F.leaky_relu(x, 1 / 0.05), 0.05))       # atom.py:468
+    assert name == "mlu" and abs(par - 0.05) < 1e-6
+    assert plugin._probe_activation(torch.tanh) is None
+
+
+def test_reference_tracker_on_cpu_is_unchanged_by_install():
+    """The whole reference DiMP tracker (CPU) gives bit-identical boxes with and without the plug-in installed."""
+    from oracle import ref_shims
+    ref_shims.install()
+    from baseline import ref_tracker
+    from pytracking_b200 import plugin, synth
+    torch.set_num_threads(8)
+    frames, bb = synth.make_sequence(0, num_frames=4)
+    ov = dict(net_opt_iter=2, net_opt_update_iter=1)
+    a = ref_tracker.run_sequence(ref_tracker.build_dimp("cpu", overrides=ov, use_augmentation=False), frames, bb)
+    plugin.install()
+    try:
+        b = ref_tracker.run_sequence(ref_tracker.build_dimp("cpu", overrides=ov, use_augmentation=False), frames, bb)
+    finally:
+        plugin.uninstall()
+    assert np.array_equal(a["target_bbox"], b["target_bbox"])
