@@ -45,8 +45,10 @@ def build_dimp_net(arch="resnet50", seed=0):
     return net
 
 
-def build_dimp(device="cpu", arch="resnet50", use_iou_net=False, overrides=None, seed=0, use_augmentation=True):
-    """-> reference `DiMP` tracker object (pytracking/tracker/dimp/dimp.py), parameters = parameter/dimp/dimp50.py + overrides."""
+def build_dimp(device="cpu", arch="resnet50", use_iou_net=False, overrides=None, seed=0, use_augmentation=True, dropout=True):
+    """-> reference `DiMP` tracker object (pytracking/tracker/dimp/dimp.py), parameters = parameter/dimp/dimp50.py + overrides.
+    dropout=False removes the 'dropout' entry of params.augmentation: F.dropout2d draws from the DEVICE generator, so a CPU run and a
+    CUDA run of the stock reference see different masks (and different filters) with it."""
     from baseline import ref_env
     ref_env.install()
     from pytracking.parameter.dimp import dimp50 as dimp50_params
@@ -65,6 +67,8 @@ def build_dimp(device="cpu", arch="resnet50", use_iou_net=False, overrides=None,
     params.net = wrapper
     params.use_iou_net = use_iou_net
     params.use_augmentation = use_augmentation
+    if not dropout:
+        params.augmentation = {k: v for k, v in params.augmentation.items() if k != "dropout"}
     for k, v in dict(CONFIG_DIMP50, **(overrides or {})).items():
         setattr(params, k, v)
     return DiMP(params)

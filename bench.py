@@ -1,18 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- DiMP-50 tracked frames/sec on synthetic 288x288 search crops (BASELINE.json configs[1]).
+"""bench.py -- DiMP-50 tracked frames/sec on the synthetic sequence (BASELINE.json configs[1]: 288x288 search crops, 10 SD iters/frame).
 
-One "step" = one tracked frame of the hot path on every rank: search crop -> ResNet-50 backbone to layer3 ->
-clf head (conv3x3 + InstanceL2Norm) -> apply_filter + max2d -> localisation decision (host) -> memory update ->
-10 steepest-descent iterations over the full 50-sample memory ("10 SD iters/frame").
+One "step" = one tracked frame, uint8 camera frame in -> bounding box out, of the steady-state tracker (50-sample memory full):
+crop sampling -> ResNet-50 backbone to layer3 -> clf head -> apply_filter -> localisation -> state update -> memory insert ->
+10 steepest-descent iterations over the 50 samples.  Both arms run the SAME tracker configuration (`CONFIG`), the same frames, the
+same pre-roll (PREROLL untimed frames after initialisation so that the memory is full), W warm-up frames, then K timed frames.
 
-  value : frames/s with the crops already resident in HBM (device-timed, CUDA events, max over ranks)
-  e2e   : frames/s through the host-buffer C-ABI frame calls (pinned host crop in, score map + arg-max out;
-          H2D/D2H inside the timed region, host-side localisation + sample-weight bookkeeping included)
-  --impl reference : the same per-frame path as the CPU restatement of the reference (oracle/, torch-CPU fp32,
-          all host threads) -- the reference itself cannot travel to the GPU box (no /root/reference there).
+  --impl b200 (default)
+      value : frames/s of `b200trk_dimp_track_device` -- the uint8 frames already resident in HBM (device-timed with CUDA events,
+              max over ranks); L2 is flushed before the timed region and every step reads a frame nobody touched before.
+      e2e   : frames/s of `DiMPTracker.track(frame)` -- the public call: pinned HOST uint8 frame in, box out; the H2D copy of the
+              frame and the D2H of the localisation result are inside the timed region (wall clock around the loop, max over ranks).
+      roofline[]         : per-kernel CUDA-event timings inside this run (steepest-descent optimiser, backbone+head, apply_filter).
+      cpu_baseline       : the unmodified reference tracker (baseline/_ref) on rank 0's host cores, bounded sample.
+      torch_cuda_baseline: the unmodified reference tracker on stock PyTorch-CUDA (cuDNN, TF32 off) on the same GPU -- what a
+                           pytracking user runs today -- and the same reference tracker above the engine (`plugin.install()`).
+  --impl reference
+      The UNMODIFIED reference `DiMP` tracker (baseline/_ref, staged from /root/reference by baseline/stage_reference.py), stock
+      PyTorch CPU path, timed as the reference times itself (time.time() around `tracker.track`,
+      pytracking/evaluation/tracker.py:226-233).  One reference process per rank, host threads split evenly between the ranks,
+      whole-job value = world * K / max-over-ranks time (gloo gather).
 
-Multi-GPU: one process per GPU, one independent synthetic sequence per rank (weak scaling), no collective
-inside the frame loop; a single NCCL all_gather of per-rank timings at the end.
+Multi-GPU: one process per GPU, sequence q = rank (weak scaling), no collective in the frame loop; at the end ONE NCCL all_gather of the
+per-sequence boxes / times (pytracking_b200/shard.py) from which the aggregate FPS and mean IoU against the synthetic ground truth
+are computed (pytracking/analysis/extract_results.py:29-39).
 """
 import argparse
 import json
@@ -28,24 +39,33 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CROP = 288
-MEMORY = 50
-SD_ITERS = 10
-# dram__bytes_read.sum + dram__bytes_write.sum of one sd_kernel launch (n=50, 10 it) from the committed ncu --set full
-# capture profiles/r01g_ncu_full_sd_and_conv.txt: the sample memory is read from HBM once per call and stays L2 resident.
-SD_DRAM_TRAFFIC_BYTES = 33330944 + 121600
-# the same for one sd_tc_kernel launch on the frame engine's pitched sample memory (profiles/r01j_ncu_full_sd_tc.txt)
-SD_TC_DRAM_TRAFFIC_BYTES = 36231936 + 275200
-POOL = 160          # distinct crops per rank (160 x 995 KB = 159 MB > 126 MB L2: a step's input is never L2 resident)
+CROP, MEMORY, SD_ITERS, PREROLL = 288, 50, 10, 56
+# pytracking/parameter/dimp/dimp50.py + the BASELINE configs[1] overrides of SURVEY.md 8(d); identical in both arms
+TRACKER_PARAMS = dict(image_sample_size=CROP, search_area_scale=5, sample_memory_size=MEMORY, learning_rate=0.01,
+                      init_samples_minimum_weight=0.25, train_skipping=1, update_classifier=True, net_opt_iter=10,
+                      net_opt_update_iter=SD_ITERS, net_opt_hn_iter=1, advanced_localization=True, target_not_found_threshold=-1e9,
+                      distractor_threshold=0.8, hard_negative_threshold=0.5, target_neighborhood_scale=2.2, dispalcement_scale=0.8,
+                      hard_negative_learning_rate=0.02, augmentation_expansion_factor=2)
+REF_OVERRIDES = dict(target_not_found_threshold=-1e9, train_skipping=1, net_opt_update_iter=SD_ITERS, filter_init_zero=True)
+METRIC = "DiMP-50 tracked frames/sec (uint8 frame -> box; 288x288 search crops, 10 SD iters/frame over a 50-sample memory)"
+CONFIG = {"workload": "DiMP-50 single-GPU, synthetic 288x288 crops, 10 SD iters/frame (BASELINE configs[1]); synthetic 480x640 uint8 "
+                      "sequence of SURVEY.md 8(d), one independent sequence per GPU / rank",
+          "tracker": "pytracking/parameter/dimp/dimp50.py + target_not_found_threshold=-1e9, train_skipping=1, net_opt_update_iter=10, "
+                     "use_iou_net=False, use_augmentation=False, filter_init_zero=True",
+          "backbone": "resnet50->layer3", "memory": MEMORY, "sd_iters": SD_ITERS, "use_iou_net": False, "preroll_frames": PREROLL,
+          "network": "random init (seed 0), identical state_dict in both arms",
+          "l2": "L2 flushed (256 MB write) before the timed region; every step reads a frame not touched before; network weights and "
+                "the sample memory are the tracker's steady-state working set"}
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", type=int, default=0)
+    ap.add_argument("--no-baselines", action="store_true", help="skip cpu_baseline / torch_cuda_baseline (profiling runs)")
     return ap.parse_args()
 
 
@@ -54,8 +74,9 @@ def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "bf16_tflops": d.get("bf16_tflops", 1590.0), "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "bf16_tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0)),
+                "bf16_tflops_burst": d.get("bf16_tflops", 1590.0), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_burst": 1590.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler(threading.Thread):
@@ -71,7 +92,7 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
                     break
@@ -100,208 +121,6 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------------------
-def localisation_decision(scores, max_val, max_idx, prev_disp, target_cells=(3.1, 3.1), p=None):
-    """Host half of DiMP.localize_advanced (pytracking/tracker/dimp/dimp.py:238-303) on the 19x19 map of one scale:
-    threshold tests, neighbourhood masking, second maximum, distractor / hard-negative decision tree."""
-    p = p or {}
-    sz = scores.shape[-1]
-    s1 = float(max_val)
-    r1, c1 = int(max_idx[0]), int(max_idx[1])
-    if s1 < p.get("target_not_found_threshold", -1e9):
-        return "not_found", (r1, c1)
-    ny, nx = p.get("target_neighborhood_scale", 2.2) * target_cells[0], p.get("target_neighborhood_scale", 2.2) * target_cells[1]
-    top, bot = max(round(r1 - ny / 2), 0), min(round(r1 + ny / 2 + 1), sz)
-    lef, rig = max(round(c1 - nx / 2), 0), min(round(c1 + nx / 2 + 1), sz)
-    masked = scores.copy()
-    masked[top:bot, lef:rig] = 0
-    col_best = masked.max(axis=0)
-    c2 = int(col_best.argmax())
-    r2 = int(masked[:, c2].argmax())
-    s2 = float(masked[r2, c2])
-    ctr = (sz - 1) / 2
-    d1 = np.hypot(r1 - ctr - prev_disp[0], c1 - ctr - prev_disp[1])
-    d2 = np.hypot(r2 - ctr - prev_disp[0], c2 - ctr - prev_disp[1])
-    thr = p.get("dispalcement_scale", 0.8) * np.sqrt(sz * sz) / 2
-    if s2 > p.get("distractor_threshold", 0.8) * s1:
-        if d2 > thr and d1 < thr:
-            return "hard_negative", (r1, c1)
-        if d2 < thr and d1 > thr:
-            return "hard_negative", (r2, c2)
-        return "uncertain", (r1, c1)
-    if s2 > p.get("hard_negative_threshold", 0.5) * s1 and s2 > p.get("target_not_found_threshold", -1e9):
-        return "hard_negative", (r1, c1)
-    return "normal", (r1, c1)
-
-
-def setup_engine(rank, precision):
-    from pytracking_b200 import synth
-    from pytracking_b200.frame_engine import DiMPFrameEngine, SampleWeights
-    sd = synth.make_dimp_state_dict("resnet50", seed=0, lut_seed=3)
-    eng = DiMPFrameEngine(sd, arch="resnet50", filter_size=4, memory_size=MEMORY, max_batch=1, crop_size=CROP,
-                          precision=precision)
-    # fill the sample memory as DiMP.initialize would (15 init samples) and then to capacity (steady state)
-    q = 1000 + rank
-    init = synth.make_crop(q, MEMORY, CROP)
-    boxes = synth.make_boxes(q + 1, MEMORY)
-    for i in range(MEMORY):
-        out = eng.backbone.forward(init[i:i + 1].cuda(), want=("classification",))
-        eng.memory[i].copy_(out["classification"][0])
-    eng.boxes.copy_(boxes.cuda())
-    sw = SampleWeights(MEMORY, 15)
-    for _ in range(MEMORY - 15):
-        sw.step()
-    eng.sample_weights.copy_(torch.from_numpy(sw.w).cuda())
-    eng.filter.zero_()
-    eng.localize_device(init[MEMORY - 1:MEMORY].cuda())          # leaves the clf feature of the last init crop in the state
-    eng.update(0, MEMORY - 1, boxes[MEMORY - 1].numpy(), sw.w, MEMORY, SD_ITERS)   # initial model: 10 SD iterations from w = 0
-    torch.cuda.synchronize()
-    return eng, sw, synth
-
-
-def run_b200(args, rank, world, local_rank):
-    from pytracking_b200 import _lib
-    torch.cuda.set_device(local_rank)
-    eng, sw, synth = setup_engine(rank, args.precision)
-    dev = eng.device
-    g = torch.Generator().manual_seed(7000 + rank)
-    pool_host = torch.empty(POOL, 3, CROP, CROP, dtype=torch.float32).pin_memory()
-    base = synth.make_crop(2000 + rank, 8, CROP)
-    for i in range(POOL):   # cheap distinct crops: shifted / re-noised variants of 8 base crops
-        pool_host[i] = torch.roll(base[i % 8], shifts=(i * 3) % CROP, dims=2)
-    pool_dev = pool_host.to(dev)
-    boxes_np = synth.make_boxes(3000 + rank, POOL).numpy()
-    K, W = args.steps, args.warmup
-    barrier = (lambda: torch.distributed.barrier()) if world > 1 else (lambda: None)
-
-    def frame_device(i):
-        eng.localize_device(pool_dev[i % POOL:i % POOL + 1])
-        r = sw.step()
-        eng.update(0, r, boxes_np[i % POOL], sw.w, MEMORY, SD_ITERS)
-
-    prev = [0.0, 0.0]
-
-    def frame_host(i):
-        scores, mv, mi = eng.localize(pool_host[i % POOL:i % POOL + 1])
-        flag, (r_, c_) = localisation_decision(scores[0], mv[0], mi[0], prev)
-        prev[0], prev[1] = r_ - 9.0, c_ - 9.0
-        lr = 0.02 if flag == "hard_negative" else None
-        r = sw.step(lr)
-        eng.update(0, r, boxes_np[i % POOL], sw.w, MEMORY, SD_ITERS)
-
-    # ---------------- device-resident leg (value) ----------------
-    for i in range(W):
-        frame_device(i)
-    torch.cuda.synchronize(); barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start(); time.sleep(0.25)
-    launches0 = _lib.lib().b200trk_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(); barrier()
-    e0.record()
-    for i in range(K):
-        frame_device(W + i)
-    e1.record()
-    torch.cuda.synchronize(); barrier()
-    dev_ms = e0.elapsed_time(e1)
-    launches = _lib.lib().b200trk_launch_count() - launches0
-
-    # per-kernel event timing of the dominant kernel (SD optimiser) for the roofline entry
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * 20)]
-    for j in range(20):
-        eng.localize_device(pool_dev[j:j + 1])
-        ev[2 * j].record()
-        eng.update(0, j % MEMORY, boxes_np[j], sw.w, MEMORY, SD_ITERS)
-        ev[2 * j + 1].record()
-    torch.cuda.synchronize()
-    sd_us = float(np.median([ev[2 * j].elapsed_time(ev[2 * j + 1]) for j in range(20)])) * 1e3
-    sd_tc = int(_lib.lib().b200trk_sd_last_kernel())
-
-    # ---------------- host-buffer leg (e2e) ----------------
-    for i in range(W):
-        frame_host(i)
-    torch.cuda.synchronize(); barrier()
-    t0 = time.perf_counter()
-    for i in range(K):
-        frame_host(W + i)
-    torch.cuda.synchronize()
-    host_ms = (time.perf_counter() - t0) * 1e3
-    barrier()
-    clocks = sampler.finish() if sampler else None
-
-    # ---------------- gather: max over ranks ----------------
-    t = torch.tensor([dev_ms, host_ms, sd_us], device=dev, dtype=torch.float64)
-    if world > 1:
-        allt = [torch.zeros_like(t) for _ in range(world)]
-        torch.distributed.all_gather(allt, t)
-        t = torch.stack(allt).max(dim=0).values
-    dev_ms, host_ms, sd_us = [float(x) for x in t.cpu()]
-    if rank != 0:
-        return
-    peaks = load_peaks()
-    # SURVEY.md 8(d): SD-GN algorithmic bytes per iteration = 3*n*663552 + 8*n*1444 + 3*32768 B (n = 50)
-    sd_bytes = SD_ITERS * (3 * MEMORY * 663552 + 8 * MEMORY * 1444 + 3 * 32768)
-    achieved = sd_bytes / (sd_us * 1e-6) / 1e9
-    cpu = cpu_baseline_sample(steps=3, warmup=1)
-    out = {
-        "metric": "DiMP-50 tracked frames/sec (288x288 synthetic search crops, 10 SD iters/frame)",
-        "value": world * K / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (3xTF32 error-compensated tcgen05 convolutions and optimiser sweeps; fp32 CUDA-core correlation)" if args.precision == 0 else "f32",
-        "data": "synthetic",
-        "config": {"workload": "DiMP-50 single-GPU, synthetic 288x288 crops, 10 SD iters/frame (BASELINE configs[1]); "
-                               "one independent sequence per GPU", "backbone": "resnet50->layer3", "memory": MEMORY,
-                   "sd_iters": SD_ITERS, "use_iou_net": False,
-                   "l2": "inputs > L2: each step reads a different crop from a %d-crop pool (%.0f MB); network weights and the "
-                         "50-sample memory are the tracker's steady-state working set" % (POOL, POOL * 3 * CROP * CROP * 4 / 1e6),
-                   "precision": args.precision},
-        "e2e": {"value": world * K / (host_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 3 * CROP * CROP * 4 + 16 + MEMORY * 4,
-                "d2h_bytes_per_step": 19 * 19 * 4 + 4 + 16},
-        "gpu_launches": int(launches),
-        "roofline": {"kernel": ("sd_tc_kernel<18,0> (tcgen05 sweeps)" if sd_tc else "sd_kernel<18,4,0>") + " (DiMP steepest-descent, n=50, 10 it)",
-                     "bound": "hbm", "achieved": achieved,
-                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                     "traffic": SD_TC_DRAM_TRAFFIC_BYTES if sd_tc else SD_DRAM_TRAFFIC_BYTES,
-                     "peak_source": peaks["source"], "us_per_launch": sd_us, "us_per_sd_iteration": sd_us / SD_ITERS},
-        "cpu_baseline": cpu,
-        "clocks": clocks,
-    }
-    print(json.dumps(out))
-
-
-# ------------------------------------------------------------------------------------------------------------
-class CpuFrame:
-    """The same per-frame path on the host: torch-CPU restatement of the reference (oracle/dimp_oracle.py)."""
-
-    def __init__(self):
-        from oracle import dimp_oracle as O
-        from pytracking_b200 import synth
-        from pytracking_b200.frame_engine import SampleWeights
-        self.O, self.synth = O, synth
-        self.sd = synth.make_dimp_state_dict("resnet50", seed=0, lut_seed=3)
-        self.p = {k[len("classifier.filter_optimizer."):]: v for k, v in self.sd.items() if k.startswith("classifier.filter_optimizer.")}
-        self.memory = synth.make_clf_features(11, MEMORY, 512, 18, 18)
-        self.boxes = synth.make_boxes(12, MEMORY)
-        self.sw = SampleWeights(MEMORY, 15)
-        for _ in range(MEMORY - 15):
-            self.sw.step()
-        self.w = torch.zeros(1, 512, 4, 4)
-        self.crops = synth.make_crop(13, 4, CROP)
-
-    def step(self, i):
-        O = self.O
-        with torch.no_grad():
-            im = O.preprocess_image(self.crops[i % 4:i % 4 + 1])
-            bf = O.resnet_forward(self.sd, im, "resnet50", output_layers=("layer3",))
-            clf = O.clf_head_dimp50(self.sd, bf["layer3"])
-            s = O.apply_filter_conv(clf, self.w)
-            O.max2d(s[:, 0])
-            r = self.sw.step()
-            self.memory[r] = clf[0]
-            self.w = O.dimp_sd_gn_conv(self.w, self.memory, self.boxes, torch.from_numpy(self.sw.w), self.p, SD_ITERS)
-
-
 def host_cores():
     """Cores this process may really use: scheduler affinity, capped by the cgroup CPU quota if there is one."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -314,69 +133,282 @@ def host_cores():
     return n
 
 
-def pick_cpu_threads(frame):
-    """The torch-CPU path does not scale to every core count (tiny grouped convs); time one frame per candidate
-    thread count and keep the fastest, so that the baseline is the best the host can do, not an oversubscribed one."""
-    avail = host_cores()
-    cands = sorted({c for c in (8, 16, 32, 64, avail) if c <= avail} or {avail})
-    best, best_t = cands[0], None
-    for c in cands:
-        torch.set_num_threads(c)
-        frame.step(0)
-        t0 = time.perf_counter()
-        frame.step(1)
-        dt = time.perf_counter() - t0
-        if best_t is None or dt < best_t:
-            best, best_t = c, dt
-        if dt > 8.0:          # hopeless at this count; larger counts only get worse
-            break
-    torch.set_num_threads(best)
-    return best
+def make_frames(rank, count):
+    from pytracking_b200 import synth
+    frames, bb = synth.make_sequence(rank, num_frames=count)
+    return frames, bb, synth.sequence_ground_truth(rank, count)
 
 
-def cpu_baseline_sample(steps, warmup):
-    f = CpuFrame()
-    pick_cpu_threads(f)
-    for i in range(warmup):
-        f.step(i)
-    t0 = time.perf_counter()
-    for i in range(steps):
-        f.step(warmup + i)
-    dt = time.perf_counter() - t0
-    return {"value": steps / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "%d frames of the same DiMP-50 hot path (backbone+head+classify+10 SD it over 50 samples), torch-CPU fp32 "
-                      "restatement of the reference (oracle/dimp_oracle.py)" % steps}
+# ------------------------------------------------------------------------------------------------------------
+# reference tracker (unmodified, baseline/_ref): shared by --impl reference, cpu_baseline and torch_cuda_baseline
+# ------------------------------------------------------------------------------------------------------------
+def reference_available():
+    from baseline import ref_env
+    return ref_env.reference_available()
+
+
+def run_reference_tracker(device, frames, bb, warmup, steps, threads=None, above_engine=False):
+    """init + PREROLL + warmup untimed frames, then `steps` frames timed with the reference's own clock. -> (seconds, boxes)"""
+    from baseline import ref_env, ref_tracker
+    ref_env.install()
+    if threads:
+        torch.set_num_threads(threads)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    if above_engine:
+        from pytracking_b200 import plugin
+        plugin.install()
+    try:
+        trk = ref_tracker.build_dimp(device, use_iou_net=False, overrides=REF_OVERRIDES, use_augmentation=False)
+        sync = torch.cuda.synchronize if device != "cpu" else None
+        r = ref_tracker.run_sequence(trk, frames[:1 + PREROLL + warmup + steps], bb, sync=sync)
+    finally:
+        if above_engine:
+            from pytracking_b200 import plugin
+            plugin.uninstall()
+    t = r["time"][PREROLL + warmup:]
+    return float(t.sum()), r["target_bbox"]
+
+
+def cpu_port_sample(steps):
+    """Fallback when the reference tree is not staged: the torch-CPU restatement (oracle/) of the same per-frame tensor path."""
+    from oracle import dimp_oracle as O
+    from pytracking_b200 import synth
+    from pytracking_b200.frame_engine import SampleWeights
+    sd = synth.make_dimp_state_dict("resnet50", seed=0, lut_seed=3)
+    p = {k[len("classifier.filter_optimizer."):]: v for k, v in sd.items() if k.startswith("classifier.filter_optimizer.")}
+    memory, boxes = synth.make_clf_features(11, MEMORY, 512, 18, 18), synth.make_boxes(12, MEMORY)
+    sw = SampleWeights(MEMORY, 15)
+    for _ in range(MEMORY - 15):
+        sw.step()
+    w = torch.zeros(1, 512, 4, 4)
+    crops = synth.make_crop(13, 4, CROP)
+    t0 = None
+    for i in range(steps + 1):
+        if i == 1:
+            t0 = time.perf_counter()
+        with torch.no_grad():
+            bf = O.resnet_forward(sd, O.preprocess_image(crops[i % 4:i % 4 + 1]), "resnet50", output_layers=("layer3",))
+            clf = O.clf_head_dimp50(sd, bf["layer3"])
+            O.max2d(O.apply_filter_conv(clf, w)[:, 0])
+            memory[sw.step()] = clf[0]
+            w = O.dimp_sd_gn_conv(w, memory, boxes, torch.from_numpy(sw.w), p, SD_ITERS)
+    return time.perf_counter() - t0
 
 
 def run_reference(args, rank, world):
+    K, W = args.steps, args.warmup
+    cores = host_cores()
+    threads = max(1, cores // world)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group(backend="gloo")
+    frames, bb, gt = make_frames(rank, PREROLL + W + K)
+    if reference_available():
+        secs, boxes = run_reference_tracker("cpu", frames, bb, W, K, threads=threads)
+        kind = "reference"
+        sample = ("%d frames of the unmodified reference DiMP tracker (baseline/_ref, stock PyTorch CPU path, fp32) after init + %d "
+                  "pre-roll + %d warm-up frames; time.time() around tracker.track" % (K, PREROLL, W))
+    else:
+        torch.set_num_threads(threads)
+        secs = cpu_port_sample(K)
+        kind = "port"
+        sample = "%d frames of the torch-CPU restatement (oracle/) -- baseline/_ref is not staged on this machine" % K
+    t = torch.tensor([secs], dtype=torch.float64)
+    if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        torch.distributed.all_gather(allt, t)
+        t = torch.stack(allt).max(dim=0).values
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
+    secs = float(t[0])
+    v = world * K / secs
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": secs / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": CONFIG,
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads * world, "kind": kind, "sample": sample,
+                         "processes": world, "threads_per_process": threads},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# b200 arm
+# ------------------------------------------------------------------------------------------------------------
+def event_time_us(fn, reps, stream_sync=True):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        a.record(); fn(); b.record()
+    torch.cuda.synchronize()
+    return float(np.median([a.elapsed_time(b) for a, b in ev])) * 1e3
+
+
+def run_b200(args, rank, world, local_rank):
+    from pytracking_b200 import _lib, shard, synth
+    from pytracking_b200.tracker import DiMPTracker, make_params
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     K, W = args.steps, args.warmup
-    K = min(K, 30)        # bounded sample: ~0.2 s per frame on host cores
-    W = min(W, 3)
-    f = CpuFrame()
-    pick_cpu_threads(f)
+    n_frames = PREROLL + 2 * (W + K)
+    frames, bb, gt = make_frames(rank, n_frames)
+    H, Wd = frames[0].shape[:2]
+    sd = synth.make_dimp_state_dict("resnet50", seed=0, lut_seed=3)
+    trk = DiMPTracker(sd, make_params(**TRACKER_PARAMS), arch="resnet50", precision=args.precision, device=dev)
+    pinned = torch.empty(n_frames + 1, H, Wd, 3, dtype=torch.uint8).pin_memory()
+    for i, f in enumerate(frames):
+        pinned[i] = torch.from_numpy(f)
+    barrier = (lambda: torch.distributed.barrier()) if world > 1 else (lambda: None)
+    boxes = []
+
+    # ---- setup (untimed): initialise on frame 0, pre-roll until the 50-sample memory is full ----
+    trk.initialize(pinned[0], {"init_bbox": bb})
+    f = 1
+    for _ in range(PREROLL):
+        boxes.append(trk.track(pinned[f])["target_bbox"]); f += 1
+    assert trk.info.n_stored == MEMORY, trk.info.n_stored
+
+    # ---- device-resident leg (value) ----
+    dev_frames = pinned[f:f + W + K].to(dev)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
     for i in range(W):
-        f.step(i)
+        trk.track_device(dev_frames[i]); boxes.append(list(trk.info.bbox))
+    torch.cuda.synchronize(); barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.3)
+    launches0 = _lib.lib().b200trk_launch_count()
+    flush.fill_(1.0)                                                    # L2 flush: 256 MB written right before the timed region
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); barrier()
+    e0.record()
+    for i in range(K):
+        trk.track_device(dev_frames[W + i]); boxes.append(list(trk.info.bbox))
+    e1.record()
+    torch.cuda.synchronize(); barrier()
+    dev_ms = e0.elapsed_time(e1)
+    launches = _lib.lib().b200trk_launch_count() - launches0
+    f += W + K
+    del dev_frames
+
+    # ---- host-buffer leg (e2e): the public call, pinned uint8 frame in, box out ----
+    per_frame = []
+    for i in range(W):
+        boxes.append(trk.track(pinned[f])["target_bbox"]); f += 1
+    flush.fill_(2.0)
+    torch.cuda.synchronize(); barrier()
     t0 = time.perf_counter()
     for i in range(K):
-        f.step(W + i)
-    dt = time.perf_counter() - t0
-    v = K / dt
+        ts = time.perf_counter()
+        boxes.append(trk.track(pinned[f])["target_bbox"]); f += 1
+        per_frame.append(time.perf_counter() - ts)
+    torch.cuda.synchronize()
+    host_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    clocks = sampler.finish() if sampler else None
+
+    # ---- per-kernel timings for the roofline entries (CUDA events on the launching stream, same process, same state) ----
+    eng = trk.engine
+    sw_host = np.full(MEMORY, 1.0 / MEMORY, dtype=np.float32)
+    eng.sample_weights.copy_(torch.from_numpy(sw_host).to(dev))
+    box_host = np.array([120, 120, 50, 50], dtype=np.float32)
+    sd_us = event_time_us(lambda: eng.update(0, 7, box_host, sw_host, MEMORY, SD_ITERS), 20)
+    sd_tc = int(_lib.lib().b200trk_sd_last_kernel())
+    crop_dev = synth.make_crop(5, 1, CROP).to(dev)
+    net_us = event_time_us(lambda: eng.backbone.forward(crop_dev, want=("classification",)), 20)
+    import ctypes as C
+    L = _lib.lib()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def apply_only():
+        _lib.check(L.b200trk_apply_filter(C.c_void_p(eng.clf.data_ptr()), C.c_void_p(eng.filter.data_ptr()), C.c_void_p(eng.scores.data_ptr()),
+                                          1, 512, 18, 18, 4, None, None, st), "apply_filter")
+    af_us = event_time_us(apply_only, 50)
+
+    # ---- gather: max over ranks + the final result gather (boxes, per-frame times) ----
+    t = torch.tensor([dev_ms, host_ms, sd_us, net_us, af_us], device=dev, dtype=torch.float64)
+    if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        torch.distributed.all_gather(allt, t)
+        t = torch.stack(allt).max(dim=0).values
+    dev_ms, host_ms, sd_us, net_us, af_us = [float(x) for x in t.cpu()]
+    bx = torch.tensor(np.array(boxes, dtype=np.float32))
+    times = torch.zeros(bx.shape[0]); times[-K:] = torch.tensor(per_frame)
+    merged = shard.gather_results({rank: (bx, times)}, world, n_frames, device=dev if world > 1 else None)
+    if rank != 0:
+        return
+    ious = []
+    for q, (b, _) in merged.items():
+        g = torch.tensor(synth.sequence_ground_truth(q, n_frames)[1:1 + b.shape[0]], dtype=torch.float32)
+        ious.append(float(shard.iou_overlap(b, g).mean()))
+    peaks = load_peaks()
+    # SURVEY.md 8(d): SD-GN algorithmic bytes per iteration = 3*n*663552 + 8*n*1444 + 3*32768 B (n = 50)
+    sd_bytes = SD_ITERS * (3 * MEMORY * 663552 + 8 * MEMORY * 1444 + 3 * 32768)
+    sd_once = MEMORY * 663552 + SD_ITERS * (8 * MEMORY * 1444 + 3 * 32768)      # the fused lower bound: sample memory read once per call
+    net_flops = float(eng.backbone.flops)
+    af_bytes = 4 * (512 * 18 * 18 + 512 * 16 + 19 * 19)
+    roof = [
+        {"kernel": ("sd_tc_kernel<18,0>" if sd_tc else "sd_kernel<18,4,0>") + " (DiMP steepest descent, n=50, 10 it, one launch)",
+         "bound": "hbm", "achieved": sd_bytes / (sd_us * 1e-6) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+         "frac": sd_bytes / (sd_us * 1e-6) / 1e9 / peaks["hbm_gbs"], "traffic": None, "us_per_launch": sd_us,
+         "us_per_sd_iteration": sd_us / SD_ITERS, "algorithmic_bytes": sd_bytes,
+         "fused_lower_bound": {"bytes": sd_once, "us_at_peak": sd_once / (peaks["hbm_gbs"] * 1e3), "frac": sd_once / (peaks["hbm_gbs"] * 1e3) / sd_us}},
+        {"kernel": "conv_tc_kernel chain (ResNet-50 -> layer3 + clf head, batch 1, 3xTF32 on tcgen05; whole forward)", "bound": "tensor",
+         "achieved": net_flops / (net_us * 1e-6) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+         "frac": net_flops / (net_us * 1e-6) / 1e12 / peaks["bf16_tflops"], "traffic": None, "us_per_launch": net_us,
+         "algorithmic_flops": net_flops, "mma_issue_flops": 3 * net_flops},
+        {"kernel": "apply_filter_kernel<18,16> (classify, 1 sample)", "bound": "hbm", "achieved": af_bytes / (af_us * 1e-6) / 1e9,
+         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": af_bytes / (af_us * 1e-6) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+         "us_per_launch": af_us, "algorithmic_bytes": af_bytes},
+    ]
     out = {
-        "impl": "reference",
-        "metric": "DiMP-50 tracked frames/sec (288x288 synthetic search crops, 10 SD iters/frame)",
-        "value": v, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DiMP-50 single-GPU, synthetic 288x288 crops, 10 SD iters/frame (BASELINE configs[1])",
-                   "backbone": "resnet50->layer3", "memory": MEMORY, "sd_iters": SD_ITERS, "use_iou_net": False},
-        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": "%d frames, torch-CPU fp32 restatement of the reference path (the reference tree is not "
-                                   "available on the GPU box)" % K},
-        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "metric": METRIC, "value": world * K / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (3xTF32 error-compensated tcgen05 convolutions and optimiser sweeps; fp32 CUDA-core correlation)" if args.precision == 0 else "f32",
+        "data": "synthetic", "config": CONFIG,
+        "e2e": {"value": world * K / (host_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": H * Wd * 3 + 16 + MEMORY * 4,
+                "d2h_bytes_per_step": 64, "api": "pytracking_b200.tracker.DiMPTracker.track(uint8 frame) -> {'target_bbox'}",
+                "ms_per_frame_median": float(np.median(per_frame) * 1e3)},
+        "gpu_launches": int(launches),
+        "roofline": roof[0], "rooflines": roof, "peak_source": peaks["source"],
+        "tracking": {"mean_iou_vs_synthetic_ground_truth": float(np.mean(ious)), "sequences": len(ious), "frames_per_sequence": len(boxes),
+                     "gather": "one all_gather of [frames,6] per sequence at the end (pytracking_b200/shard.py)"},
+        "clocks": clocks,
     }
+    if not args.no_baselines:
+        out.update(baselines(frames, bb, W))
     print(json.dumps(out))
+
+
+def baselines(frames, bb, W):
+    """Rank 0 only, after the timed regions: the unmodified reference on the host cores (bounded sample) and on PyTorch-CUDA."""
+    res = {}
+    cores = host_cores()
+    if not reference_available():
+        torch.set_num_threads(min(cores, 16))
+        secs = cpu_port_sample(3)
+        res["cpu_baseline"] = {"value": 3 / secs, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": "3 frames of the torch-CPU restatement (oracle/): baseline/_ref is not staged here"}
+        return res
+    n_cpu = 8
+    secs, _ = run_reference_tracker("cpu", frames, bb, 1, n_cpu, threads=cores)
+    res["cpu_baseline"] = {"value": n_cpu / secs, "unit": "frames/s", "cores": cores, "kind": "reference",
+                           "sample": "%d frames of the unmodified reference DiMP tracker (baseline/_ref, stock PyTorch CPU path) after init + "
+                                     "%d pre-roll + 1 warm-up frames; time.time() around tracker.track" % (n_cpu, PREROLL)}
+    try:
+        n_gpu = 60
+        secs, b_cuda = run_reference_tracker("cuda", frames, bb, W, n_gpu)
+        secs_e, b_eng = run_reference_tracker("cuda", frames, bb, W, n_gpu, above_engine=True)
+        res["torch_cuda_baseline"] = {
+            "value": n_gpu / secs, "unit": "frames/s", "kind": "unmodified reference tracker on stock PyTorch-CUDA (cuDNN / cuBLAS, TF32 "
+            "off), same GPU, same frames; time.time() + cuda.synchronize() around tracker.track", "frames": n_gpu,
+            "reference_above_engine": {"value": n_gpu / secs_e, "unit": "frames/s", "kind": "the same unmodified reference tracker with "
+                                       "pytracking_b200.plugin.install() (every tensor seam served by libb200trk.so)",
+                                       "boxes_identical_to_stock_cuda": bool(np.array_equal(b_cuda, b_eng))}}
+    except Exception as e:                                                         # the product numbers above must survive a baseline failure
+        res["torch_cuda_baseline"] = {"error": repr(e)[:300]}
+    return res
 
 
 def main():

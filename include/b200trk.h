@@ -204,6 +204,17 @@ int b200trk_net_destroy(b200trk_net_t* net);
  *   layer2 [S,C2,h/8,w/8], layer3 [S,C3,h/16,w/16], clf [S,Cc,h/16,w/16]; any may be NULL. */
 int b200trk_net_forward(b200trk_net_t* net, const float* crop, int S,
                         float* layer2, float* layer3, float* clf, b200trk_stream_t stream);
+/* AtomIoUNet.get_iou_feat (ltr/models/bbreg/atom_iou_net.py:172-179; DiMP.get_iou_features pytracking/tracker/dimp/dimp.py:318-320)
+ * as part of the same plan: convs = {conv3_1t, conv3_2t, conv4_1t, conv4_2t}, each conv3x3 + bias + eval-mode BN + ReLU, applied to
+ * the layer2 / layer3 activations inside the arena. Afterwards b200trk_net_forward_iou also writes iou3 [S,C,h/8,w/8] and
+ * iou4 [S,C,h/16,w/16] (NULL skips the branch); b200trk_net_iou_dims: {C3,H3,W3, C4,H4,W4}. */
+int b200trk_net_attach_iou_head(b200trk_net_t* net, const b200trk_conv_desc_t* convs);
+int b200trk_net_iou_dims(const b200trk_net_t* net, int dims[6]);
+/* The IoU branch alone on the layer2 / layer3 activations the most recent forward pass (same S) left in the arena -- the reference
+ * calls get_iou_feat lazily, only on frames that refine the box (dimp.py:657-658). */
+int b200trk_net_iou_from_arena(b200trk_net_t* net, int S, float* iou3, float* iou4, b200trk_stream_t stream);
+int b200trk_net_forward_iou(b200trk_net_t* net, const float* crop, int S, float* layer2, float* layer3, float* clf,
+                            float* iou3, float* iou4, b200trk_stream_t stream);
 /* Query output geometry: dims = {C2,H2,W2, C3,H3,W3, Cc,Hc,Wc}. */
 int b200trk_net_dims(const b200trk_net_t* net, int dims[9]);
 /* FLOPs (2*MAC) of one forward pass at batch 1, for roofline accounting. */
@@ -310,6 +321,38 @@ int b200trk_dimp_localize_host(b200trk_dimp_state_t* st, const float* crop_host,
 int b200trk_dimp_update_host(b200trk_dimp_state_t* st, int scale_ind, int replace_ind, const float* target_box_host,
                              const float* sample_weights_host, int n_stored, int num_iter, b200trk_stream_t stream);
 
+
+
+/* ------------------------------------------------------------------------------------------------
+ * IoUNet box refinement (ATOM / DiMP / PrDiMP `refine_target_box`)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* LinearBlock (ltr/models/layers/blocks.py:24-40): nn.Linear weight [out, in] (+ bias [out]) followed by an eval-mode BatchNorm2d
+ * (gamma, beta, running_mean, running_var; eps 1e-5; NULL = no BN) and ReLU. HOST pointers; BN is folded at create time. */
+typedef struct {
+    const float* weight; const float* bias; const float* bn_gamma; const float* bn_beta; const float* bn_mean; const float* bn_var;
+} b200trk_linear_block_t;
+typedef struct b200trk_iou_predictor b200trk_iou_predictor_t;
+
+/* The prediction head of AtomIoUNet (ltr/models/bbreg/atom_iou_net.py:39-48): fc3_rt = LinearBlock(C3*P3*P3 -> D3) on the P3 x P3
+ * PrRoIPool (scale 1/8) of the layer2 IoU features, fc4_rt = LinearBlock(C4*P4*P4 -> D4) on the P4 x P4 pool (scale 1/16) of the layer3
+ * IoU features, iou_predictor = Linear(D3 + D4 -> 1). DiMP-50: C3 = C4 = D3 = D4 = 256, P3 = 5, P4 = 3. */
+int b200trk_iou_predictor_create(b200trk_iou_predictor_t** out, const b200trk_linear_block_t* fc3_rt, const b200trk_linear_block_t* fc4_rt,
+                                 const float* iou_predictor_weight, const float* iou_predictor_bias, int C3, int P3, int C4, int P4,
+                                 int D3, int D4);
+int b200trk_iou_predictor_destroy(b200trk_iou_predictor_t* p);
+/* AtomIoUNet.predict_iou (atom_iou_net.py:96-136) for the R <= 16 proposals (x, y, w, h) of ONE image, and -- when grad_out is given --
+ * d iou / d (x, y, w, h), which the reference obtains with `outputs.backward()` (dimp.py:742). All pointers DEVICE:
+ * mod3 [C3], mod4 [C4] modulation vectors (get_modulation), feat3 [C3,H3,W3] / feat4 [C4,H4,W4] = get_iou_feat of the image. */
+int b200trk_iou_predict(b200trk_iou_predictor_t* p, const float* mod3, const float* mod4, const float* feat3, int H3, int W3,
+                        const float* feat4, int H4, int W4, const float* proposals, int R, float* iou_out, float* grad_out,
+                        b200trk_stream_t stream);
+/* DiMP.optimize_boxes_default (relative = 0, dimp.py:725-751) / optimize_boxes_relative (relative = 1, dimp.py:754-793): num_iter
+ * gradient-ascent steps on the boxes, entirely on the device. boxes [R,4] DEVICE, updated in place; iou_out [R] = the IoUs predicted
+ * in the last iteration's forward pass (what the reference returns). */
+int b200trk_iou_refine(b200trk_iou_predictor_t* p, const float* mod3, const float* mod4, const float* feat3, int H3, int W3,
+                       const float* feat4, int H4, int W4, float* boxes, int R, int num_iter, float step_length, float step_decay,
+                       int relative, float* iou_out, b200trk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Whole-frame call: uint8 camera frame in, bounding box out (DiMP.track, pytracking/tracker/dimp/dimp.py:94-175).

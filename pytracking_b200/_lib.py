@@ -37,6 +37,11 @@ class DecLayer(C.Structure):
         "norm3_weight", "norm3_bias")]
 
 
+class LinearBlock(C.Structure):
+    """b200trk_linear_block_t"""
+    _fields_ = [(n, C.c_void_p) for n in ("weight", "bias", "bn_gamma", "bn_beta", "bn_mean", "bn_var")]
+
+
 class DimpParams(C.Structure):
     """b200trk_dimp_params_t"""
     _fields_ = [("image_sample_size", C.c_int), ("search_area_scale", C.c_double), ("sample_memory_size", C.c_int),
@@ -96,6 +101,10 @@ SIGNATURES = {
     "b200trk_net_create": (_I, [C.POINTER(_VP), _I, C.POINTER(ConvDesc), _I, _F, _I, _I, _I, _I]),
     "b200trk_net_destroy": (_I, [_VP]),
     "b200trk_net_forward": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _VP]),
+    "b200trk_net_attach_iou_head": (_I, [_VP, C.POINTER(ConvDesc)]),
+    "b200trk_net_iou_from_arena": (_I, [_VP, _I, _VP, _VP, _VP]),
+    "b200trk_net_iou_dims": (_I, [_VP, C.POINTER(C.c_int * 6)]),
+    "b200trk_net_forward_iou": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "b200trk_net_dims": (_I, [_VP, C.POINTER(C.c_int * 9)]),
     "b200trk_net_flops": (C.c_double, [_VP]),
     "b200trk_net_num_ops": (_I, [_VP]),
@@ -120,6 +129,10 @@ SIGNATURES = {
     "b200trk_dimp_state_scores": (_VP, [_VP]),
     "b200trk_dimp_localize_host": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _VP]),
     "b200trk_dimp_update_host": (_I, [_VP, _I, _I, _VP, _VP, _I, _I, _VP]),
+    "b200trk_iou_predictor_create": (_I, [C.POINTER(_VP), C.POINTER(LinearBlock), C.POINTER(LinearBlock), _VP, _VP, _I, _I, _I, _I, _I, _I]),
+    "b200trk_iou_predictor_destroy": (_I, [_VP]),
+    "b200trk_iou_predict": (_I, [_VP, _VP, _VP, _VP, _I, _I, _VP, _I, _I, _VP, _I, _VP, _VP, _VP]),
+    "b200trk_iou_refine": (_I, [_VP, _VP, _VP, _VP, _I, _I, _VP, _I, _I, _VP, _I, _I, _F, _F, _I, _VP, _VP]),
     "b200trk_dimp_tracker_create": (_I, [C.POINTER(_VP), _VP, C.POINTER(DimpParams)]),
     "b200trk_dimp_tracker_destroy": (_I, [_VP]),
     "b200trk_dimp_tracker_initialize_host": (_I, [_VP, _VP, _I, _I, C.POINTER(C.c_double * 4), _VP]),

@@ -170,6 +170,7 @@ static int build(b200trk_net* net, const b200trk_conv_desc_t* convs, int n_convs
             Op op; op.kind = OP_EXPORT_NCHW; op.in = x; op.Hin = H; op.Win = W; op.Cin = inplanes; op.export_slot = li - 1;
             net->ops.push_back(op);
             net->dims[(li - 1) * 3 + 0] = inplanes; net->dims[(li - 1) * 3 + 1] = H; net->dims[(li - 1) * 3 + 2] = W;
+            net->feat_buf[li - 1] = x; net->feat_hw[li - 1][0] = inplanes; net->feat_hw[li - 1][1] = H; net->feat_hw[li - 1][2] = W;
         }
     }
     // classification head (absent when only the backbone descriptors are given: ATOM's ATOMResNet18 uses raw layer3 features)
@@ -284,7 +285,8 @@ extern "C" int b200trk_net_op_output(const b200trk_net_t* net, int index, int S,
 
 extern "C" double b200trk_net_flops(const b200trk_net_t* net) { return net ? net->flops : 0.0; }
 
-static int net_forward_eager(b200trk_net_t* net, const float* crop, int S, float* layer2, float* layer3, float* clf, cudaStream_t st);
+static int net_forward_eager(b200trk_net_t* net, const float* crop, int S, float* layer2, float* layer3, float* clf, float* iou3,
+                             float* iou4, cudaStream_t st);
 
 static void drop_graph(b200trk_net_t* net) {
     if (net->gexec) { cudaGraphExecDestroy(net->gexec); net->gexec = nullptr; }
@@ -293,52 +295,110 @@ static void drop_graph(b200trk_net_t* net) {
 
 extern "C" int b200trk_net_forward(b200trk_net_t* net, const float* crop, int S, float* layer2, float* layer3, float* clf,
                                    b200trk_stream_t stream) {
+    return b200trk_net_forward_iou(net, crop, S, layer2, layer3, clf, nullptr, nullptr, stream);
+}
+
+// AtomIoUNet.get_iou_feat appended to the plan: conv3_1t -> conv3_2t on the layer2 activation, conv4_1t -> conv4_2t on layer3
+// (ltr/models/bbreg/atom_iou_net.py:172-179), read straight from the NHWC arena (no export / re-import of the backbone features).
+extern "C" int b200trk_net_attach_iou_head(b200trk_net_t* net, const b200trk_conv_desc_t* convs) {
+    B200_REQUIRE(net && convs, "net_attach_iou_head: null pointer");
+    B200_REQUIRE(net->iou_dims[0] == 0, "net_attach_iou_head: already attached");
+    B200_REQUIRE(net->feat_buf[0] >= 0 && net->feat_buf[1] >= 0, "net_attach_iou_head: the network has no layer2 / layer3 outputs");
+    drop_graph(net);
+    Builder B{net, convs, 4};
+    const size_t first = net->ops.size();
+    for (int lvl = 0; lvl < 2; ++lvl) {
+        const int C = net->feat_hw[lvl][0], H = net->feat_hw[lvl][1], W = net->feat_hw[lvl][2];
+        int a, b, h, w;
+        if (int e = B.add_conv(net->feat_buf[lvl], -1, H, W, C, convs[2 * lvl].cout, 3, 1, 1, 1, &a, &h, &w)) return e;
+        if (int e = B.add_conv(a, -1, h, w, convs[2 * lvl].cout, convs[2 * lvl + 1].cout, 3, 1, 1, 1, &b, &h, &w)) return e;
+        Op op; op.kind = OP_EXPORT_NCHW; op.in = b; op.Hin = h; op.Win = w; op.Cin = convs[2 * lvl + 1].cout; op.export_slot = 2 + lvl;
+        net->ops.push_back(op);
+        net->iou_dims[3 * lvl] = op.Cin; net->iou_dims[3 * lvl + 1] = h; net->iou_dims[3 * lvl + 2] = w;
+    }
+    for (size_t i = first; i < net->ops.size(); ++i) net->ops[i].iou = 1;
+    return 0;
+}
+
+// The IoU branch alone, on the layer2 / layer3 activations the most recent forward pass of batch S left in the arena.
+extern "C" int b200trk_net_iou_from_arena(b200trk_net_t* net, int S, float* iou3, float* iou4, b200trk_stream_t stream) {
+    B200_REQUIRE(net && (iou3 || iou4), "net_iou_from_arena: null pointer");
+    B200_REQUIRE(net->iou_dims[0] > 0, "net_iou_from_arena: no IoU head is attached");
+    B200_REQUIRE(S >= 1 && S <= net->max_batch, "net_iou_from_arena: batch %d outside [1,%d]", S, net->max_batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (const Op& op : net->ops) {
+        if (!op.iou) continue;
+        if (op.kind == OP_CONV) {
+            if (op.tc) { if (int e = tc_conv_launch(net, op, S, st)) return e; continue; }
+            ConvShape sh{S, op.Hin, op.Win, op.Cin, op.Hout, op.Wout, op.Cout, op.k, op.stride, op.pad};
+            ConvEpilogue ep{op.bias, nullptr, op.relu};
+            if (int e = launch_conv_fp32(net->bufs[op.in], op.w, net->bufs[op.out], sh, ep, net->splitk_ws, net->splitk_ws_floats, net->sms, st)) return e;
+        } else if (op.kind == OP_EXPORT_NCHW) {
+            float* dst = op.export_slot == 2 ? iou3 : iou4;
+            if (dst)
+                if (int e = launch_nhwc_to_nchw(net->bufs[op.in], dst, S, op.Hin * op.Win, op.Cin, st)) return e;
+        }
+    }
+    return 0;
+}
+
+extern "C" int b200trk_net_iou_dims(const b200trk_net_t* net, int dims[6]) {
+    B200_REQUIRE(net && dims, "net_iou_dims: null pointer");
+    memcpy(dims, net->iou_dims, sizeof(int) * 6);
+    return 0;
+}
+
+extern "C" int b200trk_net_forward_iou(b200trk_net_t* net, const float* crop, int S, float* layer2, float* layer3, float* clf,
+                                       float* iou3, float* iou4, b200trk_stream_t stream) {
     B200_REQUIRE(net && crop, "net_forward: null pointer");
+    B200_REQUIRE((!iou3 && !iou4) || net->iou_dims[0] > 0, "net_forward: IoU features requested but no IoU head is attached");
     B200_REQUIRE(S >= 1 && S <= net->max_batch, "net_forward: batch %d outside [1,%d]", S, net->max_batch);
     cudaStream_t st = (cudaStream_t)stream;
     static const bool use_graph = []() { const char* v = getenv("B200TRK_GRAPH"); return !v || atoi(v) != 0; }();
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (use_graph && cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusActive; }
-    if (!use_graph || cs != cudaStreamCaptureStatusNone) return net_forward_eager(net, crop, S, layer2, layer3, clf, st);
+    if (!use_graph || cs != cudaStreamCaptureStatusNone) return net_forward_eager(net, crop, S, layer2, layer3, clf, iou3, iou4, st);
     auto& k = net->gkey;
-    const bool same = k.crop == crop && k.l2 == layer2 && k.l3 == layer3 && k.clf == clf && k.S == S;
+    const bool same = k.crop == crop && k.l2 == layer2 && k.l3 == layer3 && k.clf == clf && k.i3 == iou3 && k.i4 == iou4 && k.S == S;
     if (!same) {
         drop_graph(net);
-        k.crop = crop; k.l2 = layer2; k.l3 = layer3; k.clf = clf; k.S = S;
+        k.crop = crop; k.l2 = layer2; k.l3 = layer3; k.clf = clf; k.i3 = iou3; k.i4 = iou4; k.S = S;
     }
     if (net->gexec) {
         B200_CHECK_CUDA(cudaGraphLaunch(net->gexec, st));
         g_launch_count.fetch_add(net->graph_kernels, std::memory_order_relaxed);   // kernels inside the replayed graph
         return 0;
     }
-    if (++k.hits < 3) return net_forward_eager(net, crop, S, layer2, layer3, clf, st);   // lazy per-S setup happens eagerly
+    if (++k.hits < 3) return net_forward_eager(net, crop, S, layer2, layer3, clf, iou3, iou4, st);   // lazy per-S setup happens eagerly
     // third identical call: record the launch sequence (programmatic-dependent-launch edges included) and replay it from now on
     // (recorded on a private stream: the caller's stream may be the legacy default stream, which cannot capture)
     cudaGraph_t g = nullptr;
     if (!net->cap_stream) B200_CHECK_CUDA(cudaStreamCreateWithFlags(&net->cap_stream, cudaStreamNonBlocking));
     B200_CHECK_CUDA(cudaStreamBeginCapture(net->cap_stream, cudaStreamCaptureModeThreadLocal));
     const uint64_t before = g_launch_count.load();
-    const int e = net_forward_eager(net, crop, S, layer2, layer3, clf, net->cap_stream);
+    const int e = net_forward_eager(net, crop, S, layer2, layer3, clf, iou3, iou4, net->cap_stream);
     net->graph_kernels = g_launch_count.load() - before;
     cudaError_t ce = cudaStreamEndCapture(net->cap_stream, &g);
     if (e || ce != cudaSuccess || !g) {
         if (g) cudaGraphDestroy(g);
         cudaGetLastError();
         k.hits = -1000000;                 // capture not possible here: stay eager
-        return e ? e : net_forward_eager(net, crop, S, layer2, layer3, clf, st);
+        return e ? e : net_forward_eager(net, crop, S, layer2, layer3, clf, iou3, iou4, st);
     }
     ce = cudaGraphInstantiate(&net->gexec, g, 0);
     cudaGraphDestroy(g);
-    if (ce != cudaSuccess) { net->gexec = nullptr; cudaGetLastError(); k.hits = -1000000; return net_forward_eager(net, crop, S, layer2, layer3, clf, st); }
+    if (ce != cudaSuccess) { net->gexec = nullptr; cudaGetLastError(); k.hits = -1000000; return net_forward_eager(net, crop, S, layer2, layer3, clf, iou3, iou4, st); }
     B200_CHECK_CUDA(cudaGraphLaunch(net->gexec, st));
     return 0;
 }
 
-static int net_forward_eager(b200trk_net_t* net, const float* crop, int S, float* layer2, float* layer3, float* clf, cudaStream_t st) {
+static int net_forward_eager(b200trk_net_t* net, const float* crop, int S, float* layer2, float* layer3, float* clf, float* iou3,
+                             float* iou4, cudaStream_t st) {
     // (off by default: measured 972 vs 974 frames/s with / without the fork on the DiMP-50 frame; B200TRK_NET_FORK=1 enables it)
     static const bool fork_enabled = [] { const char* v = getenv("B200TRK_NET_FORK"); return v ? atoi(v) != 0 : false; }();
     const bool fork = fork_enabled && net->side_stream != nullptr;
     for (const Op& op : net->ops) {
+        if (op.iou && !iou3 && !iou4) continue;
         if (fork && op.kind == OP_CONV) {
             if (op.fork_op >= 0) {
                 // block input is complete at this point of `st`: start the shortcut convolution on the side stream
@@ -373,7 +433,7 @@ static int net_forward_eager(b200trk_net_t* net, const float* crop, int S, float
             break;
         }
         case OP_EXPORT_NCHW: {
-            float* dst = op.export_slot == 0 ? layer2 : layer3;
+            float* dst = op.export_slot == 0 ? layer2 : op.export_slot == 1 ? layer3 : op.export_slot == 2 ? iou3 : iou4;
             if (dst)
                 if (int e = launch_nhwc_to_nchw(net->bufs[op.in], dst, S, op.Hin * op.Win, op.Cin, st)) return e;
             break;

@@ -17,7 +17,8 @@ struct Op {
     int Hin = 0, Win = 0, Cin = 0, Hout = 0, Wout = 0, Cout = 0, k = 0, stride = 1, pad = 0, relu = 0;
     float* w = nullptr;      // device: [cout][kh][kw][cin] (stem: [64][49] float4)
     float* bias = nullptr;   // device: [cout] or nullptr
-    int export_slot = -1;    // OP_EXPORT_NCHW: 0 = layer2, 1 = layer3
+    int export_slot = -1;    // OP_EXPORT_NCHW: 0 = layer2, 1 = layer3, 2 / 3 = the IoUNet features of layer2 / layer3
+    int iou = 0;             // belongs to the IoUNet feature branch (skipped when no IoU output is requested)
     TcConv* tc = nullptr;
     // fork / join of a residual block's downsample conv (it only depends on the block input, so it runs on a side stream next to
     // conv1 / conv2): `fork_op` (on conv1) = plan index of the downsample conv, `side` marks that conv, `join` (on the conv that
@@ -41,10 +42,12 @@ struct b200trk_net {
     int n_forks = 0;
     float* l2_partials = nullptr;
     int dims[9] = {0};
+    int feat_buf[2] = {-1, -1}, feat_hw[2][3] = {{0, 0, 0}, {0, 0, 0}};   // NHWC buffers / (C,H,W) of layer2 and layer3
+    int iou_dims[6] = {0};               // IoUNet feature geometry {C,H,W} x 2 once b200trk_net_attach_iou_head ran
     double flops = 0.0;
     int sms = 1;
     // CUDA-graph cache of one forward pass (the per-frame call repeats with identical pointers): key + executable graph
-    struct { const float* crop = nullptr; float *l2 = nullptr, *l3 = nullptr, *clf = nullptr; int S = 0; int hits = 0; } gkey;
+    struct { const float* crop = nullptr; float *l2 = nullptr, *l3 = nullptr, *clf = nullptr, *i3 = nullptr, *i4 = nullptr; int S = 0; int hits = 0; } gkey;
     cudaGraphExec_t gexec = nullptr;
     uint64_t graph_kernels = 0;
     cudaStream_t cap_stream = nullptr;

@@ -93,6 +93,31 @@ class BackboneEngine:
         self.dims = list(dims)
         self.flops = _lib.lib().b200trk_net_flops(self.handle)
 
+    def attach_iou_head(self, state_dict, prefix="bb_regressor."):
+        """Append AtomIoUNet.get_iou_feat (atom_iou_net.py:172-179) to the plan; forward(want=(..., 'iou3', 'iou4')) then also
+        returns the two IoU feature maps."""
+        keep, descs = [], []
+        for name in ("conv3_1t", "conv3_2t", "conv4_1t", "conv4_2t"):
+            q = prefix + name
+            descs.append(_conv_entry(state_dict, keep, q + ".0.weight", q + ".1", 1, 1, bias_key=q + ".0.bias"))
+        arr = (_lib.ConvDesc * 4)(*descs)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().b200trk_net_attach_iou_head(self.handle, arr), "net_attach_iou_head")
+        d = (C.c_int * 6)()
+        _lib.check(_lib.lib().b200trk_net_iou_dims(self.handle, C.byref(d)), "net_iou_dims")
+        self.iou_dims = list(d)
+        self.flops = _lib.lib().b200trk_net_flops(self.handle)
+        del keep
+
+    def iou_features(self, s):
+        """get_iou_feat on the activations of the last forward pass (batch s) still in the arena -> (iou3, iou4)."""
+        dev = self.device
+        i3 = torch.empty(s, *self.iou_dims[0:3], device=dev, dtype=torch.float32)
+        i4 = torch.empty(s, *self.iou_dims[3:6], device=dev, dtype=torch.float32)
+        _lib.check(_lib.lib().b200trk_net_iou_from_arena(self.handle, s, C.c_void_p(i3.data_ptr()), C.c_void_p(i4.data_ptr()),
+                                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)), "net_iou_from_arena")
+        return i3, i4
+
     def forward(self, im, want=("layer2", "layer3", "classification")):
         """im: [S,3,H,W] CUDA float32 in pixel range 0..255. Returns OrderedDict of NCHW CUDA tensors."""
         if not im.is_cuda or im.dtype != torch.float32:
@@ -111,8 +136,17 @@ class BackboneEngine:
                 ptrs.append(C.c_void_p(t.data_ptr()))
             else:
                 ptrs.append(C.c_void_p(0))
-        _lib.check(_lib.lib().b200trk_net_forward(self.handle, C.c_void_p(im.data_ptr()), s, ptrs[0], ptrs[1], ptrs[2],
-                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)), "net_forward")
+        for i, name in enumerate(("iou3", "iou4")):
+            if name in want:
+                if not getattr(self, "iou_dims", None):
+                    raise RuntimeError("BackboneEngine.forward: '%s' requested but no IoU head is attached" % name)
+                t = torch.empty(s, *self.iou_dims[3 * i:3 * i + 3], device=im.device, dtype=torch.float32)
+                outs[name] = t
+                ptrs.append(C.c_void_p(t.data_ptr()))
+            else:
+                ptrs.append(C.c_void_p(0))
+        _lib.check(_lib.lib().b200trk_net_forward_iou(self.handle, C.c_void_p(im.data_ptr()), s, ptrs[0], ptrs[1], ptrs[2], ptrs[3],
+                                                      ptrs[4], C.c_void_p(torch.cuda.current_stream().cuda_stream)), "net_forward")
         return outs
 
     def close(self):

@@ -430,6 +430,7 @@ def install(max_batch=16, precision=0):
     ref_extract_backbone = nw.NetWithBackbone.extract_backbone
     ref_extract_clf = dn.DiMPnet.extract_classification_feat
     engines = weakref.WeakKeyDictionary()         # net module -> {(H, W): BackboneEngine}
+    last_pass = weakref.WeakKeyDictionary()       # net module -> (engine, [layer2, layer3] tensors it returned, batch) of the last pass
 
     def _arch_of(net):
         fe = getattr(net, "feature_extractor", None)
@@ -466,6 +467,7 @@ def install(max_batch=16, precision=0):
             out = eng.forward(im.to(eng.device, dtype=torch.float32, non_blocking=True), want=("layer2", "layer3", "classification"))
         feat = _FeatDict((l, out[l]) for l in net.output_layers)
         feat.b200_clf = out["classification"]
+        last_pass[net] = (eng, [out[l] for l in getattr(net, "bb_regressor_layer", [])], int(im.shape[0]))
         _count("extract_backbone")
         return feat
 
@@ -477,6 +479,24 @@ def install(max_batch=16, precision=0):
         return ref_extract_clf(self, backbone_feat)
     _bind(nw.NetWithBackbone, "extract_backbone", extract_backbone)
     _bind(dn.DiMPnet, "extract_classification_feat", extract_classification_feat)
+
+    # AtomIoUNet.get_iou_feat (ltr/models/bbreg/atom_iou_net.py:172-179 <- DiMP.get_iou_features dimp.py:318-320): when its input is
+    # exactly what the last engine pass returned, the four convolutions run on the activations still in the engine's arena
+    iou_mod = importlib.import_module("ltr.models.bbreg.atom_iou_net")
+    ref_get_iou_feat = iou_mod.AtomIoUNet.get_iou_feat
+
+    def get_iou_feat(self, feat2):
+        if not torch.is_grad_enabled() and isinstance(feat2, (list, tuple)) and len(feat2) == 2:
+            for net, (eng, feats, batch) in list(last_pass.items()):
+                if getattr(net, "bb_regressor", None) is self and len(feats) == 2 and feats[0] is feat2[0] and feats[1] is feat2[1] and \
+                        list(net.bb_regressor_layer) == ["layer2", "layer3"]:
+                    if not getattr(eng, "iou_dims", None):
+                        eng.attach_iou_head(net.state_dict())
+                    _count("get_iou_feat")
+                    with torch.cuda.device(eng.device):
+                        return eng.iou_features(batch)
+        return ref_get_iou_feat(self, feat2)
+    _bind(iou_mod.AtomIoUNet, "get_iou_feat", get_iou_feat)
 
     # ---- 4. native op: ltr/external/PreciseRoIPooling/pytorch/prroi_pool/functional.py:18-38 ----
     prf = importlib.import_module("ltr.external.PreciseRoIPooling.pytorch.prroi_pool.functional")

@@ -73,3 +73,12 @@ def aggregate_fps(merged):
     total = sum(v[0].shape[0] for v in merged.values())
     longest = max(float(v[1].sum()) for v in merged.values())
     return total / max(longest, 1e-12)
+
+
+def iou_overlap(pred_bb, anno_bb):
+    """Per-frame IoU of (x, y, w, h) boxes with the inclusive-pixel convention of `calc_iou_overlap`
+    (pytracking/analysis/extract_results.py:29-39): a box covers the pixels x .. x + w - 1."""
+    lo = torch.maximum(pred_bb[:, :2], anno_bb[:, :2])
+    hi = torch.minimum(pred_bb[:, :2] + pred_bb[:, 2:], anno_bb[:, :2] + anno_bb[:, 2:]) - 1.0
+    inter = (hi - lo + 1.0).clamp(min=0).prod(dim=1)
+    return inter / (pred_bb[:, 2:].prod(dim=1) + anno_bb[:, 2:].prod(dim=1) - inter)

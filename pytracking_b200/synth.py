@@ -174,6 +174,14 @@ def make_sequence(q, num_frames=200, height=480, width=640):
     return frames, [300.0, 200.0, 80.0, 60.0]
 
 
+def sequence_ground_truth(q, num_frames=200, height=480, width=640):
+    """Ground-truth boxes (x, y, w, h) of `make_sequence(q, num_frames)`, one per frame including frame 0."""
+    out = []
+    for t in range(num_frames + 1):
+        out.append([float(min(300 + 3 * t, width - 81)), float(min(200 + 2 * t, height - 61)), 80.0, 60.0])
+    return out
+
+
 def make_atom_memory(seed, n, c=64, h=18, w=18, n_filled=None, sigma=1.5):
     """ATOM sample memory as `ATOM.init_memory`/`update_memory` keep it (pytracking/tracker/atom/atom.py:561-600):
     features [n,c,h,w] (p-norm normalised, featurebase.py:105-108 -> unit mean square), Gaussian labels

@@ -24,7 +24,7 @@ def run(kind, frames, bb, use_iou, overrides, aug):
         plugin.install()
         plugin.stats.clear()
     try:
-        trk = ref_tracker.build_dimp(dev, use_iou_net=use_iou, overrides=overrides, use_augmentation=aug)
+        trk = ref_tracker.build_dimp(dev, use_iou_net=use_iou, overrides=overrides, use_augmentation=aug, dropout=False)
         scores, flags = [], []
         orig = trk.classify_target
 
@@ -50,7 +50,9 @@ def compare(a, b):
     same = np.all(a["target_bbox"][:nb] == b["target_bbox"][:nb], axis=1)
     first_diff = int(np.argmin(same)) if not same.all() else -1
     sd = [float(np.abs(a["scores"][i] - b["scores"][i]).max() / (np.abs(a["scores"][i]).max() + 1e-30)) for i in range(nb)]
-    return {"frames": nb, "boxes_identical": bool(same.all()), "first_box_diff_frame": first_diff,
+    fl = [i for i in range(nb) if a["flags"][i] != b["flags"][i]]
+    return {"frames": nb, "boxes_identical": bool(same.all()), "first_box_diff_frame": first_diff, "first_flag_diff_frame": fl[0] if fl else -1,
+            "score_rel_diff_by_frame": [round(v, 7) for v in sd[:12]] + ["..."] + [round(v, 7) for v in sd[-3:]],
             "max_box_abs_diff": float(np.abs(a["target_bbox"][:nb] - b["target_bbox"][:nb]).max()),
             "score_rel_diff_first": sd[0], "score_rel_diff_max": float(max(sd)),
             "score_rel_diff_until_first_box_diff": float(max(sd[:first_diff]) if first_diff > 0 else max(sd)),
@@ -66,6 +68,7 @@ def main():
     ap.add_argument("--no-aug", action="store_true")
     ap.add_argument("--tag", default="r02")
     ap.add_argument("--threads", type=int, default=16)
+    ap.add_argument("--default-schedule", action="store_true", help="stock dimp50 update schedule (train_skipping 20, 2 iterations)")
     args = ap.parse_args()
     from oracle import ref_shims
     ref_shims.install()
@@ -79,7 +82,11 @@ def main():
     kinds = ["engine", "cpu"] if args.iou else ["cuda", "engine", "cpu"]       # stock CUDA has no PrRoIPool build
     for kind in kinds:
         n = args.cpu_frames if kind == "cpu" else args.frames
-        res[kind] = run(kind, frames[:n + 1], bb, args.iou, None, not args.no_aug)
+        # stock CUDA has no PrRoIPool: the learned filter initialiser cannot run there -> zero initialiser in every arm of that comparison
+        ov = {} if args.iou else dict(filter_init_zero=True)
+        if args.default_schedule:
+            ov.update(train_skipping=20, net_opt_update_iter=2)
+        res[kind] = run(kind, frames[:n + 1], bb, args.iou, ov, not args.no_aug)
         t = res[kind]["time"]
         out[kind] = {"ms_per_frame_median": float(np.median(t) * 1e3), "ms_per_frame_mean": float(t.mean() * 1e3),
                      "fps_reference_clock": float(len(t) / t.sum()), "init_s": res[kind]["init_time"], "stats": res[kind]["stats"],
@@ -91,7 +98,7 @@ def main():
             out["%s_vs_%s" % (ks[i], ks[j])] = compare(res[ks[i]], res[ks[j]])
             print(ks[i], "vs", ks[j], json.dumps(out["%s_vs_%s" % (ks[i], ks[j])]), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "ref_above_engine_%s%s.json" % (args.tag, "_iou" if args.iou else "")), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", "ref_above_engine_%s%s%s.json" % (args.tag, "_iou" if args.iou else "", "_sched" if args.default_schedule else "")), "w") as f:
         json.dump(out, f, indent=1)
 
 
