@@ -45,7 +45,7 @@ TRACKER_PARAMS = dict(image_sample_size=CROP, search_area_scale=5, sample_memory
                       init_samples_minimum_weight=0.25, train_skipping=1, update_classifier=True, net_opt_iter=10,
                       net_opt_update_iter=SD_ITERS, net_opt_hn_iter=1, advanced_localization=True, target_not_found_threshold=-1e9,
                       distractor_threshold=0.8, hard_negative_threshold=0.5, target_neighborhood_scale=2.2, dispalcement_scale=0.8,
-                      hard_negative_learning_rate=0.02, augmentation_expansion_factor=2)
+                      hard_negative_learning_rate=0.02, augmentation_expansion_factor=2, use_iou_net=False)
 REF_OVERRIDES = dict(target_not_found_threshold=-1e9, train_skipping=1, net_opt_update_iter=SD_ITERS, filter_init_zero=True)
 METRIC = "DiMP-50 tracked frames/sec (uint8 frame -> box; 288x288 search crops, 10 SD iters/frame over a 50-sample memory)"
 CONFIG = {"workload": "DiMP-50 single-GPU, synthetic 288x288 crops, 10 SD iters/frame (BASELINE configs[1]); synthetic 480x640 uint8 "

@@ -383,6 +383,18 @@ typedef struct {
     double target_inside_ratio;           /* 0.2 */
     double augmentation_expansion_factor; /* 2; 0 = None (only the un-augmented Identity sample is built natively) */
     int    output_not_found_box;          /* 0 */
+    /* IoUNet refinement (dimp.py:650-723); only read when an IoU predictor is attached (b200trk_dimp_tracker_attach_iounet) */
+    int    use_iou_net;                   /* 1 in the stock parameter file */
+    int    iounet_k;                      /* 3 */
+    int    num_init_random_boxes;         /* 9 */
+    double box_jitter_pos, box_jitter_sz; /* 0.1, 0.5 */
+    double maximal_aspect_ratio;          /* 6 */
+    int    box_refinement_iter;           /* 5 (PrDiMP: 10) */
+    double box_refinement_step_length;    /* 1 (PrDiMP: 2.5e-3) */
+    double box_refinement_step_decay;     /* 1 */
+    int    box_refinement_relative;       /* box_refinement_space == 'relative' (PrDiMP) */
+    int    update_scale_when_uncertain;   /* 1 */
+    int    use_iounet_pos_for_learning;   /* 1 */
 } b200trk_dimp_params_t;
 
 /* Crop request of one frame (sample_patch, preprocessing.py:55-148) -- what the crop kernel executes. */
@@ -422,6 +434,8 @@ typedef struct {
     float max_score;
     b200trk_loc_result_t loc;
     b200trk_crop_geom_t  crop;
+    int   refined;            /* 1 if the IoUNet refinement produced the box of this frame */
+    float predicted_iou;      /* mean predicted IoU of the top-k refined proposals */
 } b200trk_frame_info_t;
 
 typedef struct b200trk_dimp_tracker b200trk_dimp_tracker_t;
@@ -446,6 +460,16 @@ int b200trk_dimp_tracker_adopt(b200trk_dimp_tracker_t* t, int H, int W, const fl
                                const float base_target_sz[2], float min_scale_factor, float max_scale_factor,
                                const float* sample_weights, int num_stored, int num_init, int previous_replace_ind, int frame_num);
 
+/* IoUNet refinement (DiMP.refine_target_box, dimp.py:650-723) for this tracker: `pred` = the prediction head, modulation3 / modulation4 =
+ * HOST [C3] / [C4] modulation vectors (DiMP.init_iou_net, dimp.py:509-540: get_modulation of the first-frame target, computed by the
+ * caller -- e.g. the reference's own initialisation above the plug-in). The network of the tracker's state must have the IoU feature
+ * branch attached (b200trk_net_attach_iou_head). */
+int b200trk_dimp_tracker_attach_iounet(b200trk_dimp_tracker_t* t, b200trk_iou_predictor_t* pred, const float* modulation3,
+                                       const float* modulation4);
+/* The uniform [0,1) numbers of the next frame's random proposals (`torch.rand(num_init_random_boxes, 4)`, dimp.py:667), HOST
+ * [num_init_random_boxes * 4]; consumed by the next track call. Without it the tracker draws from its own generator. */
+int b200trk_dimp_tracker_set_proposal_noise(b200trk_dimp_tracker_t* t, const float* u01, int count);
+
 /* DiMP.track for one frame. image: HOST uint8 [H,W,3] RGB (pinned for full speed). Returns after the box is known; the online
  * filter update of the frame (if any) is still running on `stream` (the next call orders itself behind it). */
 int b200trk_dimp_track_host(b200trk_dimp_tracker_t* t, const uint8_t* image, int H, int W, b200trk_frame_info_t* info,
@@ -462,6 +486,18 @@ int b200trk_dimp_track_device(b200trk_dimp_tracker_t* t, const uint8_t* image_de
 int b200trk_dimp_tracker_plan_crop(b200trk_dimp_tracker_t* t, b200trk_crop_geom_t* geom);
 int b200trk_dimp_tracker_commit(b200trk_dimp_tracker_t* t, const b200trk_crop_geom_t* geom, const b200trk_loc_result_t* loc,
                                 b200trk_frame_info_t* info, float* sample_weights_out);
+/* With use_iou_net the host half has three phases around the on-device box optimisation:
+ *   commit_localize  dimp.py:97-124   translation + update_state(new_pos)
+ *   proposals        dimp.py:654-674  boxes_out [1 + num_init_random_boxes][4]: the classifier's box + jittered copies (consumes the noise)
+ *   commit_refine    dimp.py:679-721  aspect-ratio filter, top-k mean, new position / size / scale from the optimised boxes and IoUs
+ *   commit_update    dimp.py:131-175  memory / sample weights / iteration schedule / output box          */
+int b200trk_dimp_tracker_commit_localize(b200trk_dimp_tracker_t* t, const b200trk_crop_geom_t* geom, const b200trk_loc_result_t* loc,
+                                         b200trk_frame_info_t* info);
+int b200trk_dimp_tracker_proposals(b200trk_dimp_tracker_t* t, const b200trk_crop_geom_t* geom, float* boxes_out, int* count);
+int b200trk_dimp_tracker_commit_refine(b200trk_dimp_tracker_t* t, const b200trk_crop_geom_t* geom, const float* boxes, const float* iou,
+                                       int count, b200trk_frame_info_t* info);
+int b200trk_dimp_tracker_commit_update(b200trk_dimp_tracker_t* t, const b200trk_crop_geom_t* geom, b200trk_frame_info_t* info,
+                                       float* sample_weights_out);
 /* Scalar state read-back: out = {pos_r, pos_c, target_sz_r, target_sz_c, target_scale, base_r, base_c, min_scale, max_scale}. */
 int b200trk_dimp_tracker_state(const b200trk_dimp_tracker_t* t, float out[9]);
 

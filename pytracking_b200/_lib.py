@@ -51,7 +51,12 @@ class DimpParams(C.Structure):
                 ("advanced_localization", C.c_int), ("target_not_found_threshold", C.c_double), ("distractor_threshold", C.c_double),
                 ("hard_negative_threshold", C.c_double), ("target_neighborhood_scale", C.c_double), ("dispalcement_scale", C.c_double),
                 ("uncertain_threshold", C.c_double), ("hard_sample_threshold", C.c_double), ("target_inside_ratio", C.c_double),
-                ("augmentation_expansion_factor", C.c_double), ("output_not_found_box", C.c_int)]
+                ("augmentation_expansion_factor", C.c_double), ("output_not_found_box", C.c_int),
+                ("use_iou_net", C.c_int), ("iounet_k", C.c_int), ("num_init_random_boxes", C.c_int), ("box_jitter_pos", C.c_double),
+                ("box_jitter_sz", C.c_double), ("maximal_aspect_ratio", C.c_double), ("box_refinement_iter", C.c_int),
+                ("box_refinement_step_length", C.c_double), ("box_refinement_step_decay", C.c_double),
+                ("box_refinement_relative", C.c_int), ("update_scale_when_uncertain", C.c_int),
+                ("use_iounet_pos_for_learning", C.c_int)]
 
 
 class CropGeom(C.Structure):
@@ -70,7 +75,7 @@ class FrameInfo(C.Structure):
     """b200trk_frame_info_t"""
     _fields_ = [("bbox", C.c_float * 4), ("flag", C.c_int), ("updated", C.c_int), ("replace_ind", C.c_int), ("num_iter", C.c_int),
                 ("n_stored", C.c_int), ("learning_rate", C.c_float), ("target_box", C.c_float * 4), ("max_score", C.c_float),
-                ("loc", LocResult), ("crop", CropGeom)]
+                ("loc", LocResult), ("crop", CropGeom), ("refined", C.c_int), ("predicted_iou", C.c_float)]
 
 
 # name -> (restype, argtypes); every symbol of include/b200trk.h is listed (tests check the export table against it)
@@ -139,10 +144,16 @@ SIGNATURES = {
     "b200trk_dimp_tracker_init_state": (_I, [_VP, _I, _I, C.POINTER(C.c_double * 4), C.POINTER(CropGeom), C.POINTER(C.c_float * 4)]),
     "b200trk_dimp_tracker_adopt": (_I, [_VP, _I, _I, C.POINTER(C.c_float * 2), C.POINTER(C.c_float * 2), _F, C.POINTER(C.c_float * 2),
                                         _F, _F, _VP, _I, _I, _I, _I]),
+    "b200trk_dimp_tracker_attach_iounet": (_I, [_VP, _VP, _VP, _VP]),
+    "b200trk_dimp_tracker_set_proposal_noise": (_I, [_VP, _VP, _I]),
     "b200trk_dimp_track_host": (_I, [_VP, _VP, _I, _I, C.POINTER(FrameInfo), _VP]),
     "b200trk_dimp_track_device": (_I, [_VP, _VP, _I, _I, C.POINTER(FrameInfo), _VP]),
     "b200trk_dimp_tracker_plan_crop": (_I, [_VP, C.POINTER(CropGeom)]),
     "b200trk_dimp_tracker_commit": (_I, [_VP, C.POINTER(CropGeom), C.POINTER(LocResult), C.POINTER(FrameInfo), _VP]),
+    "b200trk_dimp_tracker_commit_localize": (_I, [_VP, C.POINTER(CropGeom), C.POINTER(LocResult), C.POINTER(FrameInfo)]),
+    "b200trk_dimp_tracker_proposals": (_I, [_VP, C.POINTER(CropGeom), _VP, C.POINTER(C.c_int)]),
+    "b200trk_dimp_tracker_commit_refine": (_I, [_VP, C.POINTER(CropGeom), _VP, _VP, _I, C.POINTER(FrameInfo)]),
+    "b200trk_dimp_tracker_commit_update": (_I, [_VP, C.POINTER(CropGeom), C.POINTER(FrameInfo), _VP]),
     "b200trk_dimp_tracker_state": (_I, [_VP, C.POINTER(C.c_float * 9)]),
     "b200trk_sample_patch": (_I, [_VP, _I, _I, C.POINTER(CropGeom), _I, _I, _VP, _VP]),
     "b200trk_dimp_localize": (_I, [_VP, _I, _I, _I, C.POINTER(DimpParams), _VP, _VP, _VP, _VP]),

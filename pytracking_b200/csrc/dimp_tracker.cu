@@ -14,6 +14,7 @@
 // Python round are round-half-even).  The file is compiled with -fmad=false / -ffp-contract=off: no fused multiply-adds except
 // the explicit ones of the resampling kernel.
 #include "dimp_state.cuh"
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -181,6 +182,14 @@ struct b200trk_dimp_tracker {
     // memory bookkeeping (dimp.py:410-484)
     std::vector<float> sw;
     long num_stored = 0; int num_init = 0, prev_replace_ind = -1;
+    // IoUNet refinement (dimp.py:650-723)
+    b200trk_iou_predictor_t* iou_pred = nullptr;
+    float *mod3 = nullptr, *mod4 = nullptr, *iou3 = nullptr, *iou4 = nullptr, *boxes_dev = nullptr;   // device
+    float* boxes_host = nullptr;                     // pinned: [16][4] boxes + [16] IoUs
+    int iou_dims[6] = {0, 0, 0, 0, 0, 0};
+    float pos_iounet[2] = {0, 0}; int has_pos_iounet = 0;
+    std::vector<float> noise;                        // uniform numbers for the next frame's random proposals
+    uint64_t rng = 0x9E3779B97F4A7C15ull;
     // device side
     uint8_t* img_dev = nullptr; size_t img_cap = 0;
     b200trk_loc_result_t* loc_dev = nullptr;
@@ -273,6 +282,8 @@ extern "C" int b200trk_dimp_tracker_destroy(b200trk_dimp_tracker_t* t) {
     if (t->img_dev) cudaFree(t->img_dev);
     if (t->loc_dev) cudaFree(t->loc_dev);
     if (t->loc_host) cudaFreeHost(t->loc_host);
+    for (float* q : {t->mod3, t->mod4, t->iou3, t->iou4, t->boxes_dev}) if (q) cudaFree(q);
+    if (t->boxes_host) cudaFreeHost(t->boxes_host);
     delete t;
     return 0;
 }
@@ -400,8 +411,24 @@ static int update_sample_weights(b200trk_dimp_tracker* t, double lr) {
     return r_ind;
 }
 
-extern "C" int b200trk_dimp_tracker_commit(b200trk_dimp_tracker_t* t, const b200trk_crop_geom_t* g, const b200trk_loc_result_t* loc,
-                                           b200trk_frame_info_t* info, float* sample_weights_out) {
+// DiMP.update_state (dimp.py:486-497)
+static void update_state(b200trk_dimp_tracker* t, const float new_pos[2], const float* new_scale) {
+    if (new_scale) {
+        t->target_scale = std::fmin(std::fmax(*new_scale, t->min_scale_factor), t->max_scale_factor);
+        for (int i = 0; i < 2; ++i) t->target_sz[i] = t->base_target_sz[i] * t->target_scale;
+    }
+    const float ir = f32(t->p.target_inside_ratio - 0.5);
+    for (int i = 0; i < 2; ++i) {
+        const float off = ir * t->target_sz[i];
+        t->pos[i] = std::fmax(std::fmin(new_pos[i], t->image_sz[i] - off), off);
+    }
+}
+
+static bool refines(const b200trk_dimp_tracker* t) { return t->p.use_iou_net != 0; }
+
+// Phase 1 of a frame's host work: everything between localize_target and refine_target_box (dimp.py:97-128)
+extern "C" int b200trk_dimp_tracker_commit_localize(b200trk_dimp_tracker_t* t, const b200trk_crop_geom_t* g, const b200trk_loc_result_t* loc,
+                                                    b200trk_frame_info_t* info) {
     B200_REQUIRE(t && g && loc && info, "dimp_tracker_commit: null pointer");
     B200_REQUIRE(t->initialized, "dimp_tracker_commit: tracker not initialised");
     t->frame_num += 1;                                                                             // dimp.py:97
@@ -418,18 +445,95 @@ extern "C" int b200trk_dimp_tracker_commit(b200trk_dimp_tracker_t* t, const b200
         const float tv = (disp * (t->img_sample_sz[i] / output_sz)) * sample_scale;
         new_pos[i] = g->sample_pos[i] + tv;
     }
-    const bool not_found = loc->flag == 4, uncertain = loc->flag == 3, hard_negative = loc->flag == 2;
-    if (!not_found) {
-        // update_state(new_pos, sample_scales[scale_ind]) (dimp.py:486-497), use_iou_net = False
-        t->target_scale = std::fmin(std::fmax(sample_scale, t->min_scale_factor), t->max_scale_factor);
-        for (int i = 0; i < 2; ++i) t->target_sz[i] = t->base_target_sz[i] * t->target_scale;
-        const float ir = f32(t->p.target_inside_ratio - 0.5);
-        for (int i = 0; i < 2; ++i) {
-            const float off = ir * t->target_sz[i];
-            t->pos[i] = std::fmax(std::fmin(new_pos[i], t->image_sz[i] - off), off);
+    if (loc->flag != 4) {
+        if (refines(t)) update_state(t, new_pos, nullptr);          // the IoUNet sets the size (dimp.py:120-124)
+        else update_state(t, new_pos, &sample_scale);               // dimp.py:125-126
+    }
+    return 0;
+}
+
+static float next_uniform(b200trk_dimp_tracker* t, size_t i) {
+    if (i < t->noise.size()) return t->noise[i];
+    t->rng ^= t->rng << 13; t->rng ^= t->rng >> 7; t->rng ^= t->rng << 17;                        // xorshift64: the tracker's own generator
+    return (float)((t->rng >> 40) & 0xFFFFFF) * (1.0f / 16777216.0f);
+}
+
+// The proposals of refine_target_box (dimp.py:654-674): the classifier's box followed by num_init_random_boxes jittered copies
+extern "C" int b200trk_dimp_tracker_proposals(b200trk_dimp_tracker_t* t, const b200trk_crop_geom_t* g, float* boxes_out, int* count) {
+    B200_REQUIRE(t && g && boxes_out && count, "dimp_tracker_proposals: null pointer");
+    const int nr = t->p.num_init_random_boxes;
+    B200_REQUIRE(nr >= 0 && nr + 1 <= 16, "dimp_tracker_proposals: num_init_random_boxes=%d (at most 15)", nr);
+    float ib[4];
+    iounet_box(t, t->pos, t->target_sz, g->sample_pos, g->sample_scale, ib);
+    for (int i = 0; i < 4; ++i) boxes_out[i] = ib[i];
+    if (nr > 0) {
+        const float square = std::sqrt(ib[2] * ib[3]);
+        const float rf[4] = {square * f32(t->p.box_jitter_pos), square * f32(t->p.box_jitter_pos), square * f32(t->p.box_jitter_sz),
+                             square * f32(t->p.box_jitter_sz)};
+        const float min_edge = std::fmin(ib[2], ib[3]) / 3.0f;
+        for (int r = 0; r < nr; ++r) {
+            float rb[4];
+            for (int i = 0; i < 4; ++i) rb[i] = (next_uniform(t, (size_t)r * 4 + i) - 0.5f) * rf[i];
+            float* o = boxes_out + 4 * (r + 1);
+            for (int i = 0; i < 2; ++i) {
+                const float nsz = std::fmax(ib[2 + i] + rb[2 + i], min_edge);
+                const float nc = (ib[i] + ib[2 + i] / 2.0f) + rb[i];
+                o[i] = nc - nsz / 2.0f; o[2 + i] = nsz;
+            }
         }
     }
-    // update (dimp.py:131-146, 605-625)
+    t->noise.clear();
+    *count = nr + 1;
+    return 0;
+}
+
+// Phase 2: after optimize_boxes -- filter, top-k mean, new position / size / scale (dimp.py:679-721)
+extern "C" int b200trk_dimp_tracker_commit_refine(b200trk_dimp_tracker_t* t, const b200trk_crop_geom_t* g, const float* boxes, const float* iou,
+                                                  int count, b200trk_frame_info_t* info) {
+    B200_REQUIRE(t && g && boxes && iou && info && count >= 1 && count <= 16, "dimp_tracker_commit_refine: bad argument");
+    float bx[16][4]; float io[16]; int n = 0;
+    const float mar = f32(t->p.maximal_aspect_ratio), imar = f32(1.0 / t->p.maximal_aspect_ratio);
+    for (int r = 0; r < count; ++r) {
+        const float w = std::fmax(boxes[4 * r + 2], 1.0f), h = std::fmax(boxes[4 * r + 3], 1.0f);    // output_boxes[:, 2:].clamp_(1)
+        const float ar = w / h;
+        if (ar < mar && ar > imar) { bx[n][0] = boxes[4 * r]; bx[n][1] = boxes[4 * r + 1]; bx[n][2] = w; bx[n][3] = h; io[n] = iou[r]; ++n; }
+    }
+    if (n == 0) return 0;                                                                               // "If no box found"
+    const int k = std::min(t->p.iounet_k > 0 ? t->p.iounet_k : 5, n);
+    bool used[16] = {false};
+    float pb[4] = {0, 0, 0, 0}, piou = 0.f;
+    for (int j = 0; j < k; ++j) {                          // torch.topk: largest first
+        int best = -1;
+        for (int r = 0; r < n; ++r) if (!used[r] && (best < 0 || io[r] > io[best])) best = r;
+        used[best] = true;
+        for (int i = 0; i < 4; ++i) pb[i] += bx[best][i];
+        piou += io[best];
+    }
+    for (int i = 0; i < 4; ++i) pb[i] = pb[i] / (float)k;
+    info->predicted_iou = piou / (float)k; info->refined = 1;
+    // new position and size (dimp.py:703-721); predicted_box = (x, y, w, h), tracker vectors are (row, col)
+    const float cx = pb[0] + pb[2] / 2.0f, cy = pb[1] + pb[3] / 2.0f;
+    const float c[2] = {cy, cx}, sz[2] = {pb[3], pb[2]};
+    float new_pos[2], new_sz[2];
+    for (int i = 0; i < 2; ++i) {
+        new_pos[i] = (c[i] - (t->img_sample_sz[i] - 1.0f) / 2.0f) * g->sample_scale + g->sample_pos[i];
+        new_sz[i] = sz[i] * g->sample_scale;
+    }
+    const float new_scale = std::sqrt((new_sz[0] * new_sz[1]) / (t->base_target_sz[0] * t->base_target_sz[1]));
+    t->pos_iounet[0] = new_pos[0]; t->pos_iounet[1] = new_pos[1]; t->has_pos_iounet = 1;
+    if (t->p.use_iounet_pos_for_learning) { t->pos[0] = new_pos[0]; t->pos[1] = new_pos[1]; }
+    t->target_sz[0] = new_sz[0]; t->target_sz[1] = new_sz[1];
+    const bool update_scale = t->p.update_scale_when_uncertain || info->flag != 3;
+    if (update_scale) t->target_scale = new_scale;
+    return 0;
+}
+
+// Phase 3: the update half of the frame and the output box (dimp.py:131-175, 605-625)
+extern "C" int b200trk_dimp_tracker_commit_update(b200trk_dimp_tracker_t* t, const b200trk_crop_geom_t* g, b200trk_frame_info_t* info,
+                                                  float* sample_weights_out) {
+    B200_REQUIRE(t && g && info, "dimp_tracker_commit: null pointer");
+    const float sample_scale = g->sample_scale;
+    const bool not_found = info->flag == 4, uncertain = info->flag == 3, hard_negative = info->flag == 2;
     const bool update_flag = !not_found && !uncertain;
     if (update_flag && t->p.update_classifier) {
         iounet_box(t, t->pos, t->target_sz, g->sample_pos, sample_scale, info->target_box);
@@ -449,6 +553,8 @@ extern "C" int b200trk_dimp_tracker_commit(b200trk_dimp_tracker_t* t, const b200
         info->learning_rate = f32(lr);
     }
     info->n_stored = (int)std::min<long>(t->num_stored, (long)t->sw.size());
+    // "Set the pos of the tracker to iounet pos" (dimp.py:148-150)
+    if (refines(t) && !not_found && t->has_pos_iounet) { t->pos[0] = t->pos_iounet[0]; t->pos[1] = t->pos_iounet[1]; }
     // output box (dimp.py:163-171)
     if (t->p.output_not_found_box && not_found) {
         for (int i = 0; i < 4; ++i) info->bbox[i] = -1.f;
@@ -459,6 +565,40 @@ extern "C" int b200trk_dimp_tracker_commit(b200trk_dimp_tracker_t* t, const b200
         info->bbox[3] = t->target_sz[0];
     }
     if (sample_weights_out) std::memcpy(sample_weights_out, t->sw.data(), t->sw.size() * sizeof(float));
+    return 0;
+}
+
+// The whole host half of a frame without IoUNet refinement (use_iou_net = False): phases 1 + 3
+extern "C" int b200trk_dimp_tracker_commit(b200trk_dimp_tracker_t* t, const b200trk_crop_geom_t* g, const b200trk_loc_result_t* loc,
+                                           b200trk_frame_info_t* info, float* sample_weights_out) {
+    B200_REQUIRE(t && !refines(t), "dimp_tracker_commit: use_iou_net is set -- call commit_localize / proposals / commit_refine / commit_update");
+    if (int e = b200trk_dimp_tracker_commit_localize(t, g, loc, info)) return e;
+    return b200trk_dimp_tracker_commit_update(t, g, info, sample_weights_out);
+}
+
+extern "C" int b200trk_dimp_tracker_set_proposal_noise(b200trk_dimp_tracker_t* t, const float* u01, int count) {
+    B200_REQUIRE(t && u01 && count >= 0 && count <= 64, "dimp_tracker_set_proposal_noise: bad argument");
+    t->noise.assign(u01, u01 + count);
+    return 0;
+}
+
+extern "C" int b200trk_dimp_tracker_attach_iounet(b200trk_dimp_tracker_t* t, b200trk_iou_predictor_t* pred, const float* modulation3,
+                                                  const float* modulation4) {
+    B200_REQUIRE(t && pred && modulation3 && modulation4, "dimp_tracker_attach_iounet: null pointer");
+    B200_REQUIRE(t->st, "dimp_tracker_attach_iounet: host-logic-only tracker");
+    B200_REQUIRE(!t->iou_pred, "dimp_tracker_attach_iounet: already attached");
+    if (int e = b200trk_net_iou_dims(t->st->net, t->iou_dims)) return e;
+    B200_REQUIRE(t->iou_dims[0] > 0, "dimp_tracker_attach_iounet: the network has no IoU feature branch (b200trk_net_attach_iou_head)");
+    const int C3 = t->iou_dims[0], C4 = t->iou_dims[3];
+    B200_CHECK_CUDA(cudaMalloc((void**)&t->mod3, C3 * sizeof(float)));
+    B200_CHECK_CUDA(cudaMalloc((void**)&t->mod4, C4 * sizeof(float)));
+    B200_CHECK_CUDA(cudaMemcpy(t->mod3, modulation3, C3 * sizeof(float), cudaMemcpyHostToDevice));
+    B200_CHECK_CUDA(cudaMemcpy(t->mod4, modulation4, C4 * sizeof(float), cudaMemcpyHostToDevice));
+    B200_CHECK_CUDA(cudaMalloc((void**)&t->iou3, (size_t)C3 * t->iou_dims[1] * t->iou_dims[2] * sizeof(float)));
+    B200_CHECK_CUDA(cudaMalloc((void**)&t->iou4, (size_t)C4 * t->iou_dims[4] * t->iou_dims[5] * sizeof(float)));
+    B200_CHECK_CUDA(cudaMalloc((void**)&t->boxes_dev, 16 * 5 * sizeof(float)));
+    B200_CHECK_CUDA(cudaMallocHost((void**)&t->boxes_host, 16 * 5 * sizeof(float)));
+    t->iou_pred = pred;
     return 0;
 }
 
@@ -558,7 +698,22 @@ static int track_frame(b200trk_dimp_tracker* t, const uint8_t* image, bool on_de
     if (int e = b200trk_dimp_localize(s->scores, 1, s->Ho, s->Wo, &t->p, neigh, pv, t->loc_dev, stream)) return e;
     B200_CHECK_CUDA(cudaMemcpyAsync(t->loc_host, t->loc_dev, sizeof(b200trk_loc_result_t), cudaMemcpyDeviceToHost, st));
     B200_CHECK_CUDA(cudaStreamSynchronize(st));
-    if (int e = b200trk_dimp_tracker_commit(t, &g, t->loc_host, info, nullptr)) return e;
+    if (int e = b200trk_dimp_tracker_commit_localize(t, &g, t->loc_host, info)) return e;
+    if (refines(t) && info->flag != 4) {
+        // refine_target_box (dimp.py:650-723): IoU features of this crop, proposals up, box optimisation on the device, 320 bytes back
+        B200_REQUIRE(t->iou_pred, "dimp_track_host: use_iou_net is set but no IoU predictor is attached (b200trk_dimp_tracker_attach_iounet)");
+        int R = 0;
+        if (int e = b200trk_dimp_tracker_proposals(t, &g, t->boxes_host, &R)) return e;
+        B200_CHECK_CUDA(cudaMemcpyAsync(t->boxes_dev, t->boxes_host, (size_t)R * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (int e = b200trk_net_iou_from_arena(s->net, 1, t->iou3, t->iou4, stream)) return e;
+        if (int e = b200trk_iou_refine(t->iou_pred, t->mod3, t->mod4, t->iou3, t->iou_dims[1], t->iou_dims[2], t->iou4, t->iou_dims[4],
+                                       t->iou_dims[5], t->boxes_dev, R, t->p.box_refinement_iter, f32(t->p.box_refinement_step_length),
+                                       f32(t->p.box_refinement_step_decay), t->p.box_refinement_relative, t->boxes_dev + 64, stream)) return e;
+        B200_CHECK_CUDA(cudaMemcpyAsync(t->boxes_host, t->boxes_dev, 80 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        B200_CHECK_CUDA(cudaStreamSynchronize(st));
+        if (int e = b200trk_dimp_tracker_commit_refine(t, &g, t->boxes_host, t->boxes_host + 64, R, info)) return e;
+    }
+    if (int e = b200trk_dimp_tracker_commit_update(t, &g, info, nullptr)) return e;
     if (info->updated) {
         if (int e = dimp_state_update(s, 0, info->replace_ind, info->target_box, t->sw.data(), info->n_stored, info->num_iter, st)) return e;
     } else if (info->num_iter > 0) {

@@ -302,7 +302,12 @@ def _count(name):
     stats[name] = stats.get(name, 0) + 1
 
 
+_skip = set()
+
+
 def _bind(owner, name, new):
+    if name in _skip or "%s.%s" % (getattr(owner, "__name__", ""), name) in _skip:
+        return
     _installed.append((owner, name, owner.__dict__[name] if isinstance(owner, type) else getattr(owner, name)))
     setattr(owner, name, new)
 
@@ -339,14 +344,17 @@ class _FeatDict(dict):
     b200_clf = None
 
 
-def install(max_batch=16, precision=0):
-    """Rebind the seams inside an importable pytracking / ltr checkout (no reference file is edited); `uninstall()` restores them.
+def install(max_batch=16, precision=0, skip=()):
+    """`skip`: attribute names (e.g. "predict_iou" or "AtomIoUNet.predict_iou") to leave on the reference implementation.
+    Rebind the seams inside an importable pytracking / ltr checkout (no reference file is edited); `uninstall()` restores them.
     Calls the CUDA path does not claim (CPU tensors, autograd, training mode, shapes the library rejects) fall through to the
     reference implementation. Returns the list of rebound attributes."""
     import importlib
     import weakref
     if _installed:
         return [n for _, n, _ in _installed]
+    _skip.clear()
+    _skip.update(skip)
     from .engine import BackboneEngine
 
     # ---- 1. functional seams: ltr/models/layers/filter.py:5,91 ; pytracking/libs/dcf.py:156 ----
@@ -497,6 +505,44 @@ def install(max_batch=16, precision=0):
                         return eng.iou_features(batch)
         return ref_get_iou_feat(self, feat2)
     _bind(iou_mod.AtomIoUNet, "get_iou_feat", get_iou_feat)
+
+    # AtomIoUNet.predict_iou (atom_iou_net.py:96-136 <- DiMP.optimize_boxes_* dimp.py:737-742): the tracker differentiates the
+    # predicted IoUs w.r.t. the proposals with autograd; here one library call returns the IoUs and their box gradient, wrapped in an
+    # autograd.Function so that the tracker's own `outputs.backward(...)` / `bb_init.grad` code runs unchanged.
+    from .iou import IoUPredictor
+    ref_predict_iou = iou_mod.AtomIoUNet.predict_iou
+    predictors = weakref.WeakKeyDictionary()
+
+    class _PredictIoU(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, proposals, pred, modulation, feat):
+            iou, grad = pred.predict_iou(modulation, feat, proposals.detach(), return_grad=True)
+            ctx.save_for_backward(grad.reshape(proposals.shape))
+            return iou.reshape(proposals.shape[0], proposals.shape[1])
+
+        @staticmethod
+        def backward(ctx, grad_output):
+            (g,) = ctx.saved_tensors
+            return g * grad_output.unsqueeze(-1), None, None, None
+
+    def predict_iou(self, modulation, feat, proposals):
+        ok = (not self.training and isinstance(proposals, torch.Tensor) and proposals.is_cuda and proposals.dtype == torch.float32 and
+              proposals.dim() == 3 and proposals.shape[0] == 1 and 1 <= proposals.shape[1] <= 16 and len(modulation) == 2 and len(feat) == 2 and
+              all(isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and not t.requires_grad
+                  for t in list(modulation) + list(feat)) and feat[0].shape[0] == 1 and modulation[0].numel() == feat[0].shape[1] and
+              type(self.fc3_rt).__name__ == "LinearBlock" and self.fc3_rt.bn is not None and self.fc3_rt.relu is not None)
+        if not ok:
+            return ref_predict_iou(self, modulation, feat, proposals)
+        pred = predictors.get(self)
+        if pred is None:
+            with torch.cuda.device(proposals.device):
+                pred = IoUPredictor(self.state_dict(), prefix="", device=proposals.device)
+            predictors[self] = pred
+        _count("predict_iou")
+        if proposals.requires_grad and torch.is_grad_enabled():
+            return _PredictIoU.apply(proposals, pred, modulation, feat)
+        return pred.predict_iou(modulation, feat, proposals)
+    _bind(iou_mod.AtomIoUNet, "predict_iou", predict_iou)
 
     # ---- 4. native op: ltr/external/PreciseRoIPooling/pytorch/prroi_pool/functional.py:18-38 ----
     prf = importlib.import_module("ltr.external.PreciseRoIPooling.pytorch.prroi_pool.functional")

@@ -21,7 +21,9 @@ _DEFAULTS = dict(                                    # pytracking/parameter/dimp
     net_opt_hn_iter=None, update_classifier=False, advanced_localization=False, target_not_found_threshold=0.0,
     distractor_threshold=0.0, hard_negative_threshold=0.0, target_neighborhood_scale=0.0, dispalcement_scale=0.0,
     uncertain_threshold=-math.inf, hard_sample_threshold=-math.inf, target_inside_ratio=0.2, augmentation_expansion_factor=None,
-    output_not_found_box=False)
+    output_not_found_box=False, use_iou_net=True, iounet_k=5, num_init_random_boxes=0, box_jitter_pos=0.0, box_jitter_sz=0.0,
+    maximal_aspect_ratio=6.0, box_refinement_iter=0, box_refinement_step_length=1.0, box_refinement_step_decay=1.0,
+    box_refinement_space="default", update_scale_when_uncertain=True, use_iounet_pos_for_learning=True)
 
 
 def make_params(source=None, **overrides):
@@ -49,6 +51,17 @@ def make_params(source=None, **overrides):
         setattr(p, k, float(vals[k]))
     p.augmentation_expansion_factor = float(vals["augmentation_expansion_factor"] or 0.0)
     p.output_not_found_box = int(bool(vals["output_not_found_box"]))
+    p.use_iou_net, p.iounet_k = int(bool(vals["use_iou_net"])), int(vals["iounet_k"])
+    p.num_init_random_boxes = int(vals["num_init_random_boxes"])
+    p.box_jitter_pos, p.box_jitter_sz = float(vals["box_jitter_pos"]), float(vals["box_jitter_sz"])
+    p.maximal_aspect_ratio = float(vals["maximal_aspect_ratio"])
+    p.box_refinement_iter = int(vals["box_refinement_iter"])
+    if isinstance(vals["box_refinement_step_length"], (tuple, list)):
+        raise NotImplementedError("b200trk: per-coordinate box_refinement_step_length")
+    p.box_refinement_step_length, p.box_refinement_step_decay = float(vals["box_refinement_step_length"]), float(vals["box_refinement_step_decay"])
+    p.box_refinement_relative = int(vals["box_refinement_space"] == "relative")
+    p.update_scale_when_uncertain = int(bool(vals["update_scale_when_uncertain"]))
+    p.use_iounet_pos_for_learning = int(bool(vals["use_iounet_pos_for_learning"]))
     return p
 
 
@@ -120,6 +133,8 @@ class DiMPTracker(HostLogic):
         self.info = _lib.FrameInfo()
         self.debug_info = {}
         self._pinned = None
+        self.iou = None
+        self.torch_noise = False       # True: draw the random proposals' noise with torch.rand, exactly where the reference does
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -146,6 +161,19 @@ class DiMPTracker(HostLogic):
                        "dimp_tracker_initialize_host")
         return {}
 
+    def attach_iounet(self, state_dict, modulation):
+        """IoUNet refinement: `state_dict` of the whole DiMP network (bb_regressor.* keys), `modulation` = the two modulation vectors
+        of the first-frame target (AtomIoUNet.get_modulation; DiMP.init_iou_net dimp.py:509-540)."""
+        from .iou import IoUPredictor
+        if not getattr(self.engine.backbone, "iou_dims", None):
+            self.engine.backbone.attach_iou_head(state_dict)
+        self.iou = IoUPredictor(state_dict, device=self.device)
+        m3 = modulation[0].detach().float().reshape(-1).cpu().contiguous()
+        m4 = modulation[1].detach().float().reshape(-1).cpu().contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().b200trk_dimp_tracker_attach_iounet(self.handle, self.iou.handle, C.c_void_p(m3.data_ptr()),
+                                                                     C.c_void_p(m4.data_ptr())), "dimp_tracker_attach_iounet")
+
     def adopt_reference(self, ref, image_hw):
         """Take over from a reference `DiMP` object after its `initialize()` (any augmentation / initialiser): scalars, sample
         weights, sample memory, boxes and filter are copied into the engine; tracking continues natively."""
@@ -160,18 +188,29 @@ class DiMPTracker(HostLogic):
         prev = ref.previous_replace_ind[0]
         self.adopt(int(image_hw[0]), int(image_hw[1]), st, ref.sample_weights[0].detach().float().cpu().numpy(),
                    int(ref.num_stored_samples[0]), int(ref.num_init_samples[0]), -1 if prev is None else int(prev), int(ref.frame_num))
+        if self.params.use_iou_net and self.iou is None:
+            self.attach_iounet(ref.net.net.state_dict(), ref.iou_modulation)
         torch.cuda.synchronize(self.device)
 
+    def _noise(self):
+        n = self.params.num_init_random_boxes
+        if self.torch_noise and self.params.use_iou_net and n > 0:
+            u = torch.rand(n, 4).contiguous()                          # dimp.py:667
+            _lib.check(_lib.lib().b200trk_dimp_tracker_set_proposal_noise(self.handle, C.c_void_p(u.data_ptr()), 4 * n), "set_proposal_noise")
+
     def track(self, image, info=None):
+        self._noise()
         keep, ptr, H, W = self._image(image)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().b200trk_dimp_track_host(self.handle, C.c_void_p(ptr), H, W, C.byref(self.info), self._stream()),
                        "dimp_track_host")
-        self.debug_info = {"flag": FLAGS[self.info.flag], "max_score": float(self.info.max_score)}
+        self.debug_info = {"flag": FLAGS[self.info.flag], "max_score": float(self.info.max_score),
+                           "predicted_iou": float(self.info.predicted_iou) if self.info.refined else None}
         return {"target_bbox": [float(v) for v in self.info.bbox]}
 
     def track_device(self, image_dev):
         """`track` with the uint8 [H,W,3] frame already on the GPU (a CUDA tensor)."""
+        self._noise()
         if not image_dev.is_cuda or image_dev.dtype != torch.uint8 or image_dev.dim() != 3 or not image_dev.is_contiguous():
             raise RuntimeError("DiMPTracker.track_device: contiguous uint8 [H,W,3] CUDA tensor")
         with torch.cuda.device(self.device):
@@ -181,6 +220,9 @@ class DiMPTracker(HostLogic):
 
     def close(self):
         HostLogic.close(self)
+        if getattr(self, "iou", None) is not None:
+            self.iou.close()
+            self.iou = None
         if getattr(self, "engine", None) is not None:
             self.engine.close()
             self.engine = None

@@ -7,7 +7,8 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 DIMP50 = dict(image_sample_size=288, search_area_scale=5, sample_memory_size=50, learning_rate=0.01, init_samples_minimum_weight=0.25,
               train_skipping=20, update_classifier=True, net_opt_iter=10, net_opt_update_iter=2, net_opt_hn_iter=1,
               advanced_localization=True, target_not_found_threshold=0.25, distractor_threshold=0.8, hard_negative_threshold=0.5,
-              target_neighborhood_scale=2.2, dispalcement_scale=0.8, hard_negative_learning_rate=0.02, augmentation_expansion_factor=2)
+              target_neighborhood_scale=2.2, dispalcement_scale=0.8, hard_negative_learning_rate=0.02, augmentation_expansion_factor=2,
+              use_iou_net=False)
 OVERRIDES = {
     "cfg2": dict(target_not_found_threshold=-1e9, train_skipping=1, net_opt_update_iter=10),
     "stress": dict(target_not_found_threshold=0.052, uncertain_threshold=0.0555, hard_sample_threshold=0.058, distractor_threshold=0.3,

@@ -21,7 +21,7 @@ def run(kind, frames, bb, use_iou, overrides, aug):
     from pytracking_b200 import plugin
     dev = "cpu" if kind == "cpu" else "cuda"
     if kind == "engine":
-        plugin.install()
+        plugin.install(precision=int(os.environ.get("RAE_PRECISION", "0")))
         plugin.stats.clear()
     try:
         trk = ref_tracker.build_dimp(dev, use_iou_net=use_iou, overrides=overrides, use_augmentation=aug, dropout=False)
