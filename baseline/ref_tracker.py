@@ -96,3 +96,98 @@ def run_sequence(tracker, frames, init_bbox, sync=None, seed=0, on_frame=None):
     out["target_bbox"] = np.array(out["target_bbox"], dtype=np.float64)
     out["time"] = np.array(out["time"])
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the other BASELINE configurations (random-init networks from the reference constructors, seeded)
+# ---------------------------------------------------------------------------------------------------------------------------
+def _wrap(net, use_gpu):
+    from pytracking.features.net_wrappers import NetWithBackbone
+    if use_gpu:
+        net = net.cuda()
+    wrapper = NetWithBackbone(net_path="unused", use_gpu=use_gpu)
+    wrapper.net = net
+    wrapper.load_network = lambda: None
+    return wrapper
+
+
+def build_prdimp(device="cpu", use_iou_net=False, overrides=None, seed=0, use_augmentation=True, dropout=True):
+    """BASELINE configs[2]: PrDiMP-50 (parameter/dimp/prdimp50.py; klcedimpnet50 with the ltr/train_settings/dimp/prdimp50.py
+    hyper-parameters): 352^2 crops, 22x22 features, PrDiMPSteepestDescentNewton, softmax score pre-processing."""
+    from baseline import ref_env
+    ref_env.install()
+    from pytracking_b200 import synth
+    import ltr.models.tracking.dimpnet as dimpnet
+    from pytracking.parameter.dimp import prdimp50 as P
+    from pytracking.tracker.dimp.dimp import DiMP
+    torch.manual_seed(seed)
+    output_sigma = 1 / 4 / 6.0                                   # output_sigma_factor / search_area_factor (train settings)
+    net = dimpnet.klcedimpnet50(filter_size=4, backbone_pretrained=False, optim_iter=5, clf_feat_norm=True, final_conv=True,
+                                optim_init_step=1.0, optim_init_reg=0.05, optim_min_reg=0.05, gauss_sigma=output_sigma * 22,
+                                alpha_eps=0.05, normalize_label=True, init_initializer="zero")
+    sd = synth.make_dimp_state_dict("resnet50", seed=seed, lut_seed=3)
+    sd = {k: v for k, v in sd.items() if not k.startswith(("classifier.filter_optimizer.", "classifier.filter_initializer."))}
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    with torch.no_grad():
+        net.bb_regressor.iou_predictor.weight.mul_(0.02)
+    net.eval()
+    use_gpu = device != "cpu"
+    params = P.parameters()
+    params.use_gpu, params.device = use_gpu, ("cuda" if use_gpu else "cpu")
+    params.net = _wrap(net, use_gpu)
+    params.use_iou_net, params.use_augmentation = use_iou_net, use_augmentation
+    if not dropout:
+        params.augmentation = {k: v for k, v in params.augmentation.items() if k != "dropout"}
+    for k, v in dict(dict(target_not_found_threshold=-1e9, train_skipping=1, net_opt_update_iter=10), **(overrides or {})).items():
+        setattr(params, k, v)
+    return DiMP(params)
+
+
+def build_atom(device="cpu", overrides=None, seed=5):
+    """BASELINE configs[0]: ATOM ResNet-18 (parameter/atom/multiscale_no_iounet.py: 5 scales, no IoUNet), first-frame GaussNewtonCG
+    on FactorizedConvProblem, per-frame ConjugateGradient on ConvProblem."""
+    from baseline import ref_env
+    ref_env.install()
+    from pytracking_b200 import synth
+    import ltr.models.bbreg.atom as atom_models
+    from pytracking.parameter.atom import multiscale_no_iounet as P
+    import pytracking.tracker.atom.atom as atom_mod
+    import pytracking.features.deep as deep
+    torch.manual_seed(1234)
+    net = atom_models.atom_resnet18(backbone_pretrained=False)
+    missing, unexpected = net.load_state_dict(synth.make_backbone_state_dict("resnet18", seed=seed), strict=False)
+    assert not unexpected, unexpected
+    net.eval()
+    deep.load_network = lambda path: net
+    use_gpu = device != "cpu"
+    params = P.parameters()
+    params.use_gpu, params.device = use_gpu, ("cuda" if use_gpu else "cpu")
+    params.features.features[0].use_gpu = use_gpu
+    for k, v in dict(dict(train_skipping=1, target_not_found_threshold=-1e9), **(overrides or {})).items():
+        setattr(params, k, v)
+    return atom_mod.ATOM(params)
+
+
+def build_tomp(device="cpu", overrides=None, seed=0):
+    """BASELINE configs[3]: ToMP-101 (parameter/tomp/tomp101.py; tompnet101 with the ltr/train_settings/tomp/tomp101.py arguments)."""
+    from baseline import ref_env
+    ref_env.install()
+    from pytracking_b200 import synth
+    import ltr.models.tracking.tompnet as tompnet
+    from pytracking.parameter.tomp import tomp101 as P
+    from pytracking.tracker.tomp.tomp import ToMP
+    torch.manual_seed(seed)
+    net = tompnet.tompnet101(filter_size=1, backbone_pretrained=False, head_feat_blocks=0, head_feat_norm=True, final_conv=True,
+                             out_feature_dim=256, feature_sz=18, frozen_backbone_layers=(), num_encoder_layers=6,
+                             num_decoder_layers=6, use_test_frame_encoding=False)
+    missing, unexpected = net.load_state_dict(synth.make_backbone_state_dict("resnet101", seed=seed), strict=False)
+    assert not unexpected, unexpected
+    net.eval()
+    use_gpu = device != "cpu"
+    params = P.parameters()
+    params.use_gpu, params.device = use_gpu, ("cuda" if use_gpu else "cpu")
+    params.net = _wrap(net, use_gpu)
+    for k, v in dict(dict(target_not_found_threshold=-1e9), **(overrides or {})).items():
+        setattr(params, k, v)
+    return ToMP(params)

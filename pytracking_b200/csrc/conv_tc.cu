@@ -46,6 +46,7 @@ struct TcParams {
     int BN, stages;
     int total_kb, kb_per_split, splits, cblks;
     int relu, split_mode;
+    int acc2;        // 1: the two small products (A_lo*B_hi, A_hi*B_lo) accumulate in a TMEM accumulator of their own (columns BN..2BN)
     uint32_t a_bytes, b_bytes;
 };
 
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"((uint32_t)P.BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"((uint32_t)(P.acc2 ? 2 * P.BN : P.BN)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
@@ -160,9 +161,14 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
 #pragma unroll
                 for (int k = 0; k < TC_KB / 8; ++k) {
                     const uint32_t adv = (uint32_t)(k * 32 >> 4);      // 8 tf32 = 32 bytes per UMMA K step
-                    tc_mma_tf32_lo(tmem_base, d_al + adv, d_bh + adv, idesc, (it > 0 || k > 0) ? 1u : 0u);
-                    tc_mma_tf32_lo(tmem_base, d_ah + adv, d_bl + adv, idesc, 1u);
-                    tc_mma_tf32_lo(tmem_base, d_ah + adv, d_bh + adv, idesc, 1u);
+                    // The fp32 accumulate of the tensor pipe truncates; its error grows with the number of dependent additions into
+                    // one accumulator and with the accumulator's magnitude. The two correction products are ~2^-11 of the main one:
+                    // in an accumulator of their own their rounding is negligible, and the main accumulator takes a third of the adds.
+                    const uint32_t acc_lo = tmem_base + (P.acc2 ? (uint32_t)P.BN : 0u);
+                    const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+                    tc_mma_tf32_lo(acc_lo, d_al + adv, d_bh + adv, idesc, first);
+                    tc_mma_tf32_lo(acc_lo, d_ah + adv, d_bl + adv, idesc, 1u);
+                    tc_mma_tf32_lo(tmem_base, d_ah + adv, d_bh + adv, idesc, P.acc2 ? first : 1u);
                 }
                 tc_commit_elect(smem_u32(&s_empty[st]));
                 if (trace && it < 16 && lane == 0) trace[it * 8 + 5] = gtimer();          // MMAs + commit issued
@@ -255,6 +261,12 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
             for (int c = chalf; c < nchunks; c += CSH) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                if (P.acc2) {
+                    uint32_t v2[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(P.BN + c * 32), v2);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+                }
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
@@ -289,6 +301,12 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
             for (int c = chalf; c < nchunks; c += CSH) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                if (P.acc2) {
+                    uint32_t v2[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(P.BN + c * 32), v2);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+                }
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
@@ -356,7 +374,7 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(P.acc2 ? 2 * P.BN : P.BN)) : "memory");
     }
 }
 
@@ -524,6 +542,7 @@ static int tc_configure(b200trk_net* net, const Op& op, TcConv* tc, int S) {
     B200_REQUIRE(ctas <= 512 || P.splits == 1, "tc_conv: counter array too small for %d tiles", ctas);
     P.ws = op.side ? net->splitk_ws2 : net->splitk_ws;
     P.split_mode = env_int("B200TRK_TC_SPLIT_MODE", 2);
+    P.acc2 = env_int("B200TRK_TC_ACC2", 1);
     const size_t Kt = (size_t)op.k * op.k * op.Cin;
     if (int e = make_map_2d(&P.b_map, op.w, Kt, op.Cout, BN)) return e;
     tc->S_built = S;

@@ -191,6 +191,7 @@ struct b200trk_dimp_tracker {
     std::vector<float> noise;                        // uniform numbers for the next frame's random proposals
     uint64_t rng = 0x9E3779B97F4A7C15ull;
     // device side
+    cudaStream_t copy_stream = nullptr; cudaEvent_t ev_img = nullptr;   // frame upload overlaps the previous frame's filter update
     uint8_t* img_dev = nullptr; size_t img_cap = 0;
     b200trk_loc_result_t* loc_dev = nullptr;
     b200trk_loc_result_t* loc_host = nullptr;      // pinned
@@ -280,6 +281,8 @@ extern "C" int b200trk_dimp_tracker_create(b200trk_dimp_tracker_t** out, b200trk
 extern "C" int b200trk_dimp_tracker_destroy(b200trk_dimp_tracker_t* t) {
     if (!t) return 0;
     if (t->img_dev) cudaFree(t->img_dev);
+    if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
+    if (t->ev_img) cudaEventDestroy(t->ev_img);
     if (t->loc_dev) cudaFree(t->loc_dev);
     if (t->loc_host) cudaFreeHost(t->loc_host);
     for (float* q : {t->mod3, t->mod4, t->iou3, t->iou4, t->boxes_dev}) if (q) cudaFree(q);
@@ -647,7 +650,16 @@ static int upload_image(b200trk_dimp_tracker* t, const uint8_t* image, int H, in
         B200_CHECK_CUDA(cudaMalloc((void**)&t->img_dev, bytes));
         t->img_cap = bytes;
     }
-    B200_CHECK_CUDA(cudaMemcpyAsync(t->img_dev, image, bytes, cudaMemcpyHostToDevice, st));
+    // The previous frame's steepest-descent update may still be running on `st` (track returns as soon as the box is known); the
+    // frame travels on a copy stream of its own meanwhile. (The device image is free: the previous crop kernel finished before the
+    // previous call returned, which synchronised on its localisation result.)
+    if (!t->copy_stream) {
+        B200_CHECK_CUDA(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+        B200_CHECK_CUDA(cudaEventCreateWithFlags(&t->ev_img, cudaEventDisableTiming));
+    }
+    B200_CHECK_CUDA(cudaMemcpyAsync(t->img_dev, image, bytes, cudaMemcpyHostToDevice, t->copy_stream));
+    B200_CHECK_CUDA(cudaEventRecord(t->ev_img, t->copy_stream));
+    B200_CHECK_CUDA(cudaStreamWaitEvent(st, t->ev_img, 0));
     return 0;
 }
 

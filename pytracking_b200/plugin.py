@@ -441,25 +441,33 @@ def install(max_batch=16, precision=0, skip=()):
     last_pass = weakref.WeakKeyDictionary()       # net module -> (engine, [layer2, layer3] tensors it returned, batch) of the last pass
 
     def _arch_of(net):
+        """(arch, has_clf_head) when the network is one the engine's plan covers: a reference ResNet backbone to layer3, optionally
+        followed by the DiMP classification head (conv(s) + InstanceL2Norm); None otherwise."""
         fe = getattr(net, "feature_extractor", None)
-        if type(fe).__name__ != "ResNet" or type(net).__name__ != "DiMPnet":
+        kind_net = type(net).__name__
+        if type(fe).__name__ != "ResNet" or kind_net not in ("DiMPnet", "ToMPnet"):
             return None
         blocks = [len(getattr(fe, "layer%d" % i)) for i in (1, 2, 3)]
         kind = type(fe.layer1[0]).__name__
         arch = {("Bottleneck", (3, 4, 6)): "resnet50", ("Bottleneck", (3, 4, 23)): "resnet101",
                 ("BasicBlock", (2, 2, 2)): "resnet18"}.get((kind, tuple(blocks)))
-        if arch is None or list(net.classification_layer) != ["layer3"] or not set(net.output_layers) <= {"layer2", "layer3"}:
+        if arch is None or not set(net.output_layers) <= {"layer2", "layer3"}:
+            return None
+        if kind_net == "ToMPnet":                  # backbone only: the ToMP head works on stored backbone features (tomp.py:282-303)
+            return arch, False
+        if list(net.classification_layer) != ["layer3"]:
             return None
         head = net.classifier.feature_extractor
-        if head is None or type(head[-1]).__name__ != "InstanceL2Norm":
+        if head is None or type(head[-1]).__name__ != "InstanceL2Norm" or (arch == "resnet101"):
             return None
-        return arch
+        return arch, True
 
     def extract_backbone(self, im):
         net = self.net
-        arch = _arch_of(net) if (self.use_gpu and self.image_format == "rgb" and im.dim() == 4 and im.shape[1] == 3) else None
-        if arch is None or torch.is_grad_enabled() or im.shape[0] > 64 or im.shape[-1] % 32 or im.shape[-2] % 32:
+        info = _arch_of(net) if (self.use_gpu and self.image_format == "rgb" and im.dim() == 4 and im.shape[1] == 3) else None
+        if info is None or torch.is_grad_enabled() or im.shape[0] > 64 or im.shape[-1] % 32 or im.shape[-2] % 32:
             return ref_extract_backbone(self, im)
+        arch, has_head = info
         per_net = engines.setdefault(net, {})
         key = (int(im.shape[-2]), int(im.shape[-1]))
         eng = per_net.get(key)
@@ -468,13 +476,15 @@ def install(max_batch=16, precision=0, skip=()):
                 eng.close()
             dev = next(net.parameters()).device
             with torch.cuda.device(dev):
-                eng = BackboneEngine(net.state_dict(), arch=arch, filter_size=net.classifier.filter_size,
-                                     max_batch=max(max_batch, int(im.shape[0])), crop_size=key, precision=precision, device=dev)
+                eng = BackboneEngine(net.state_dict(), arch=arch, filter_size=net.classifier.filter_size if has_head else 1,
+                                     max_batch=max(max_batch, int(im.shape[0])), crop_size=key, precision=precision, device=dev,
+                                     head=has_head)
             per_net[key] = eng
+        want = ("layer2", "layer3", "classification") if has_head else ("layer2", "layer3")
         with torch.cuda.device(eng.device):
-            out = eng.forward(im.to(eng.device, dtype=torch.float32, non_blocking=True), want=("layer2", "layer3", "classification"))
+            out = eng.forward(im.to(eng.device, dtype=torch.float32, non_blocking=True), want=want)
         feat = _FeatDict((l, out[l]) for l in net.output_layers)
-        feat.b200_clf = out["classification"]
+        feat.b200_clf = out.get("classification")
         last_pass[net] = (eng, [out[l] for l in getattr(net, "bb_regressor_layer", [])], int(im.shape[0]))
         _count("extract_backbone")
         return feat

@@ -72,3 +72,27 @@ def test_two_rank_gather_gloo():
         ok, mine, fps = ret[rank]
         assert ok and mine == shard.assign_sequences(num_seq, world, rank)
     assert abs(ret[0][2] - ret[1][2]) < 1e-9
+
+
+def test_iou_overlap_matches_reference_calc_iou_overlap():
+    """shard.iou_overlap against the reference's calc_iou_overlap (pytracking/analysis/extract_results.py:29-39) on random boxes,
+    and the bench's synthetic ground truth against the sequence generator."""
+    import numpy as np
+    import torch
+    from pytracking_b200 import shard, synth
+    g = torch.Generator().manual_seed(0)
+    a = torch.cat([100 * torch.rand(64, 2, generator=g), 5 + 60 * torch.rand(64, 2, generator=g)], 1)
+    b = torch.cat([100 * torch.rand(64, 2, generator=g), 5 + 60 * torch.rand(64, 2, generator=g)], 1)
+    b[:8] = a[:8]
+    mine = shard.iou_overlap(a, b)
+    assert torch.allclose(mine[:8], torch.ones(8))
+    from baseline import ref_env
+    if ref_env.reference_available():
+        ref_env.install()
+        from pytracking.analysis.extract_results import calc_iou_overlap
+        assert torch.equal(mine, calc_iou_overlap(a, b))
+    frames, bb = synth.make_sequence(3, num_frames=5)
+    gt = synth.sequence_ground_truth(3, 5)
+    assert gt[0] == bb and len(gt) == len(frames)
+    x, y, w, h = [int(v) for v in gt[4]]
+    assert frames[4][y:y + h, x:x + w].mean() > 100 and frames[4][:y - 2].mean() < 40
