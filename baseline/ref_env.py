@@ -168,4 +168,23 @@ def install(scratch_dir=None):
         return _orig_getattr(self, name)
     tl_mod.TensorList.__getattr__ = _safe_getattr
 
+    # -- 8. ATOM indexes CPU tensors with the CUDA tensor `scale_ind` (pytracking/tracker/atom/atom.py:322-330: `disp[scale_ind, ...]`),
+    #       which current torch rejects ("indices should be either on cpu or on the same device"); its own `dcf.max2d` results are
+    #       handed to it on the CPU (the next line of the reference moves them there anyway, atom.py:323). Scoped to the ATOM module.
+    try:
+        import pytracking.tracker.atom.atom as atom_mod
+        import pytracking.libs.dcf as dcf_mod
+
+        class _DcfForAtom:
+            def __getattr__(self, name):
+                return getattr(dcf_mod, name)
+
+            @staticmethod
+            def max2d(a):
+                v, i = dcf_mod.max2d(a)          # resolved at call time: the plug-in's binding when installed
+                return v.cpu(), i.cpu()
+        atom_mod.dcf = _DcfForAtom()
+    except Exception as e:  # pragma: no cover
+        sys.stderr.write("[ref_env] ATOM index shim not installed: %r\n" % (e,))
+
     _installed = True

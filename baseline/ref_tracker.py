@@ -139,7 +139,9 @@ def build_prdimp(device="cpu", use_iou_net=False, overrides=None, seed=0, use_au
     params.use_iou_net, params.use_augmentation = use_iou_net, use_augmentation
     if not dropout:
         params.augmentation = {k: v for k, v in params.augmentation.items() if k != "dropout"}
-    for k, v in dict(dict(target_not_found_threshold=-1e9, train_skipping=1, net_opt_update_iter=10), **(overrides or {})).items():
+    # (filter_init_zero: FilterInitializerLinear pools with PrRoIPool even with init_weights='zero'; a stock checkout cannot run it)
+    for k, v in dict(dict(target_not_found_threshold=-1e9, train_skipping=1, net_opt_update_iter=10, filter_init_zero=True),
+                     **(overrides or {})).items():
         setattr(params, k, v)
     return DiMP(params)
 

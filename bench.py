@@ -498,7 +498,11 @@ def run_other(args, rank, world, local_rank):
            "gpu_launches": int(launches), "seams_served": stats,
            "torch_cuda_baseline": {"value": K / secs_c, "unit": "frames/s", "kind": "the same unmodified reference tracker on stock PyTorch-CUDA (TF32 off)"},
            "speedup_vs_torch_cuda": secs_c / secs_e,
-           "boxes_identical_to_stock_cuda_frames": int(n if same.all() else np.argmin(same)), "frames_compared": int(n)}
+           "boxes_identical_to_stock_cuda_frames": int(n if same.all() else np.argmin(same)), "frames_compared": int(n),
+           "max_box_abs_diff_first_10_frames_px": float(np.abs(b_eng[:10] - b_cuda[:10]).max())}
+    from pytracking_b200 import plugin as _pl
+    if _pl.seam_seconds:
+        out["seam_seconds_per_frame"] = {k: v / (preroll + W + K) for k, v in _pl.seam_seconds.items()}
     if not args.no_baselines:
         cores = host_cores()
         k_cpu = min(K, 6)

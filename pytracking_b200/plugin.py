@@ -298,8 +298,30 @@ _installed = []          # [(owner object, attribute name, original value)]
 stats = {}               # seam name -> number of calls served by the CUDA library (tests / bench read this)
 
 
+seam_seconds = {}        # seam name -> device-synchronised seconds spent inside the library call (only with B200TRK_PLUGIN_TIMING=1)
+_TIMING = bool(int(__import__("os").environ.get("B200TRK_PLUGIN_TIMING", "0")))
+
+
 def _count(name):
     stats[name] = stats.get(name, 0) + 1
+
+
+class _timed:
+    """with _timed(name): ... -- wall time of the block with a device synchronisation on both sides (debugging aid, off by default)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _TIMING:
+            torch.cuda.synchronize()
+            self.t0 = __import__("time").perf_counter()
+
+    def __exit__(self, *a):
+        if _TIMING:
+            torch.cuda.synchronize()
+            seam_seconds[self.name] = seam_seconds.get(self.name, 0.0) + __import__("time").perf_counter() - self.t0
+        return False
 
 
 _skip = set()
@@ -481,7 +503,7 @@ def install(max_batch=16, precision=0, skip=()):
                                      head=has_head)
             per_net[key] = eng
         want = ("layer2", "layer3", "classification") if has_head else ("layer2", "layer3")
-        with torch.cuda.device(eng.device):
+        with torch.cuda.device(eng.device), _timed("extract_backbone"):
             out = eng.forward(im.to(eng.device, dtype=torch.float32, non_blocking=True), want=want)
         feat = _FeatDict((l, out[l]) for l in net.output_layers)
         feat.b200_clf = out.get("classification")
@@ -661,7 +683,8 @@ def install(max_batch=16, precision=0, skip=()):
                                         n_dec=len(self.decoder.layers))
             per[key] = eng
         _count("Transformer.forward")
-        return eng.forward(src, mask, query_embed, pos_embed)
+        with _timed("Transformer.forward"):
+            return eng.forward(src, mask, query_embed, pos_embed)
     _bind(tr.Transformer, "forward", transformer_forward)
     return ["%s.%s" % (getattr(o, "__name__", str(o)), n) for o, n, _ in _installed]
 

@@ -224,8 +224,16 @@ def _lockstep(n_frames, seq, use_aug, overrides, sync_filter=False, use_iou_net=
                 f_ref = ref.target_filter.reshape(-1)
                 f_nat = nat.engine.filter.reshape(-1)
                 upd.append(float((f_ref - f_nat).abs().max() / f_ref.abs().max()))
+                if upd[-1] > 1e-5:            # diagnostics of the rare large events
+                    n_ = int(min(int(ref.num_stored_samples[0]), nat.params.sample_memory_size))
+                    swd = float((ref.sample_weights[0][:n_] - nat.engine.sample_weights[:n_]).abs().max() / ref.sample_weights[0][:n_].abs().max())
+                    memd = float((ref.training_samples[0][:n_] - nat.engine.memory[:n_]).abs().max())
+                    boxd = float((ref.target_boxes[:n_] - nat.engine.boxes[:n_]).abs().max())
+                    print("  frame %d: filter diff %.2e; flag %s; replace ref %s nat %d; iters nat %d; weights rel diff %.1e; memory abs diff %.1e; "
+                          "boxes abs diff %.1e" % (t, upd[-1], ref.debug_info["flag"], ref.previous_replace_ind[0], nat.info.replace_ind,
+                                                   nat.info.num_iter, swd, memd, boxd))
                 # one optimiser call from identical filters, memories and boxes; the only input that can differ is the last bit of a
-                # sample weight (torch sums them on the GPU, the tracker on the host) -- see test_sd_sensitivity_to_one_ulp below
+                # sample weight (torch sums them on the GPU, the tracker on the host) -- see test_sd_sensitivity_to_sample_weight_rounding below
                 assert upd[-1] <= 2e-3, (t, upd[-1])
         nat.close()
     finally:
@@ -235,7 +243,7 @@ def _lockstep(n_frames, seq, use_aug, overrides, sync_filter=False, use_iou_net=
            "; filter after one update: median %.2e, max %.2e" % (float(np.median(upd)), max(upd)) if upd else ""))
 
 
-def test_sd_sensitivity_to_one_ulp():
+def test_sd_sensitivity_to_sample_weight_rounding():
     """How ill-conditioned the BASELINE configs[1] update is on a REAL tracker memory (50 near-duplicate crops of one scene, unlike
     independent random samples): the steepest-descent calls of a few consecutive frames run twice from the tracker's own state, the
     second time with a single sample weight moved by one float32 ulp.  The amplification printed here is what every closed-loop
@@ -254,8 +262,9 @@ def test_sd_sensitivity_to_one_ulp():
     feat, boxes, sw, w0 = e.memory.contiguous().clone(), e.boxes.clone(), e.sample_weights.clone(), e.filter.clone()
     p = {k[len("classifier.filter_optimizer."):]: v for k, v in sd.items() if k.startswith("classifier.filter_optimizer.")}
     luts = [p[k].cuda() for k in ("label_map_predictor.weight", "target_mask_predictor.0.weight", "spatial_weight_predictor.weight")]
-    sw2 = sw.clone()
-    sw2[17] = torch.nextafter(sw2[17], torch.tensor(1.0, device=sw2.device))
+    # (a single-ulp change of one weight usually vanishes in the kernel's sqrt(sw): perturb every weight by a few ulps instead)
+    eps = 1e-6
+    sw2 = sw * (1 + eps * (2 * torch.rand(sw.shape, generator=torch.Generator().manual_seed(0)).to(sw.device) - 1))
     res = {}
     for calls in (1, 5, 20):
         out = []
@@ -265,8 +274,9 @@ def test_sd_sensitivity_to_one_ulp():
                 w, _, _ = ops.dimp_sd_gn(w, feat, boxes, weights, *luts, 10, e.step_length, e.reg_weight)
             out.append(w)
         res[calls] = float((out[0] - out[1]).abs().max() / out[0].abs().max())
-    print("1 ulp (6e-8 relative) on one of 50 sample weights of a real tracker memory -> filter moved (relative) by %s after "
-          "1 / 5 / 20 update calls of 10 iterations" % ", ".join("%.2e" % res[c] for c in (1, 5, 20)))
+    print("sample weights of a real tracker memory perturbed by %.0e relative -> filter moved (relative) by %s after 1 / 5 / 20 update "
+          "calls of 10 iterations (amplification x%s)" % (eps, ", ".join("%.2e" % res[c] for c in (1, 5, 20)),
+                                                          ", x".join("%.0f" % (res[c] / eps) for c in (1, 5, 20))))
     a = ops.dimp_sd_gn(w0, feat, boxes, sw, *luts, 10, e.step_length, e.reg_weight)[0]
     assert torch.equal(a, ops.dimp_sd_gn(w0, feat, boxes, sw, *luts, 10, e.step_length, e.reg_weight)[0])      # the kernel itself is deterministic
     trk.close()
