@@ -267,6 +267,28 @@ int b200trk_transformer_forward(b200trk_transformer_t* t, const float* src, cons
                                 const unsigned char* key_padding_mask, const float* query_embed, float* hs, float* memory,
                                 b200trk_stream_t stream);
 
+
+/* ToMP token assembly -- FilterPredictor.predict_cls_bbreg_filters_parallel up to the transformer call
+ * (ltr/models/transformer/filter_predictor.py:92-135): out [(n_train + n_test) * H * W, B, D] =
+ *   train cells:  train_feat + query_embed_fg * label + box_encoding(ltrb)      test cells: test_feat (+ query_embed_test, or NULL)
+ * All pointers DEVICE. train_feat [n_train,D,H,W], test_feat [n_test,D,H,W], label [n_train,H,W], ltrb [n_train,4,H,W], fg_token /
+ * test_token [D]; box_encoding = MLP([4, D1, D, D]) (filter_predictor.py:7-17) with its BatchNorm1d layers folded by the caller:
+ * w1 [D1,4], b1 [D1], w2t [D1,D] (= W2 transposed), b2 [D], w3t [D,D] (= W3 transposed), b3 [D]. */
+int b200trk_tomp_tokens(const float* train_feat, const float* test_feat, const float* label, const float* ltrb, const float* fg_token,
+                        const float* test_token, const float* w1, const float* b1, const float* w2t, const float* b2, const float* w3t,
+                        const float* b3, float* out, int n_train, int n_test, int H, int W, int D, int D1, int B, b200trk_stream_t stream);
+
+/* ToMP bounding-box regression tower -- DenseBoxRegressor.forward after the filter projection (ltr/models/transformer/heads.py:118-141):
+ * feats_att = attention * feat; n_convs - 1 times [conv3x3 + GroupNorm(1, C) + ReLU] (heads.py:8-15); conv3x3 -> 4; exp.
+ * convs: HOST descriptors (3x3, stride 1, pad 1, bias, no BN) in execution order; gn_gamma / gn_beta: n_convs - 1 HOST [C] vectors. */
+typedef struct b200trk_tower b200trk_tower_t;
+int b200trk_tower_create(b200trk_tower_t** out, const b200trk_conv_desc_t* convs, int n_convs, const float* const* gn_gamma,
+                         const float* const* gn_beta, int C, int H, int W, int max_batch, int precision);
+int b200trk_tower_destroy(b200trk_tower_t* t);
+double b200trk_tower_flops(const b200trk_tower_t* t);
+/* feat DEVICE [S,C,H,W], attention DEVICE [S,H,W] (NULL = ones) -> out DEVICE [S,4,H,W] = exp(bbreg_layer(tower(attention * feat))). */
+int b200trk_tower_forward(b200trk_tower_t* t, const float* feat, const float* attention, int S, float* out, b200trk_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Native op -- Precise RoI Pooling (the reference's only CUDA component)
  * ---------------------------------------------------------------------------------------------- */

@@ -120,6 +120,11 @@ SIGNATURES = {
     "b200trk_transformer_create": (_I, [C.POINTER(_VP), C.POINTER(EncLayer), _I, C.POINTER(DecLayer), _I, _VP, _VP, _I, _I, _I, _I, _I]),
     "b200trk_transformer_destroy": (_I, [_VP]),
     "b200trk_transformer_forward": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP]),
+    "b200trk_tomp_tokens": (_I, [_VP] * 13 + [_I, _I, _I, _I, _I, _I, _I, _VP]),
+    "b200trk_tower_create": (_I, [C.POINTER(_VP), C.POINTER(ConvDesc), _I, C.POINTER(_VP), C.POINTER(_VP), _I, _I, _I, _I, _I]),
+    "b200trk_tower_destroy": (_I, [_VP]),
+    "b200trk_tower_flops": (C.c_double, [_VP]),
+    "b200trk_tower_forward": (_I, [_VP, _VP, _VP, _I, _VP, _VP]),
     "b200trk_prroi_pool_forward": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _F, _VP]),
     "b200trk_prroi_pool_backward": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _F, _VP]),
     "b200trk_prroi_pool_coor_backward": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _F, _VP]),

@@ -46,6 +46,7 @@ struct TcParams {
     int BN, stages;
     int total_kb, kb_per_split, splits, cblks;
     int relu, split_mode;
+    int prefetch_b;  // 1: the weight tiles of the first pipeline stages are requested before griddepcontrol.wait (they do not depend on the previous layer)
     int acc2;        // 1: the two small products (A_lo*B_hi, A_hi*B_lo) accumulate in a TMEM accumulator of their own (columns BN..2BN)
     uint32_t a_bytes, b_bytes;
 };
@@ -120,6 +121,19 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
     // tail of the previous layer's kernel; nothing below may touch global memory before the previous grid has completed.
     if (dbg && threadIdx.x == 0) dbg[1] = gtimer();                   // prologue done
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // The weights are constants: the producer requests the B tiles of the first stages now, so that only the activation tiles
+    // remain to be fetched once the previous layer has completed.
+    int npre = 0;
+    if (warp == 0 && P.prefetch_b) {
+        npre = min(P.stages, nkb);
+        int tap = kb0 / P.cblks, cb = kb0 - tap * P.cblks;
+        for (int it = 0; it < npre; ++it) {
+            const uint32_t full = smem_u32(&s_full[it]);
+            mbar_expect_tx_elect(full, P.a_bytes + P.b_bytes);
+            tma_load_2d_elect(smem_base + (uint32_t)it * stage_bytes + 2u * a_tile, &P.b_map, full, tap * P.Cin + cb * TC_KB, n0);
+            if (++cb == P.cblks) { cb = 0; ++tap; }
+        }
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (dbg && threadIdx.x == 0) dbg[2] = gtimer();                   // previous grid complete
 
@@ -132,13 +146,15 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
             int st = 0;
             uint32_t ph = 0;
             for (int it = 0; it < nkb; ++it) {
-                mbar_wait(smem_u32(&s_empty[st]), ph ^ 1u);
-                if (trace && it < 16 && lane == 0) trace[it * 8 + 0] = gtimer();          // slot free
                 const uint32_t full = smem_u32(&s_full[st]);
-                mbar_expect_tx_elect(full, P.a_bytes + P.b_bytes);
+                if (it >= npre) {
+                    mbar_wait(smem_u32(&s_empty[st]), ph ^ 1u);
+                    mbar_expect_tx_elect(full, P.a_bytes + P.b_bytes);
+                }
+                if (trace && it < 16 && lane == 0) trace[it * 8 + 0] = gtimer();          // slot free
                 const uint32_t sa = smem_base + (uint32_t)st * stage_bytes;
                 tma_load_4d_elect(sa, &P.a_map, full, cb * TC_KB, x0 + kw, y0 + kh, s);                 // raw -> A_hi slot
-                tma_load_2d_elect(sa + 2u * a_tile, &P.b_map, full, tap * P.Cin + cb * TC_KB, n0);       // raw -> B_hi slot
+                if (it >= npre) tma_load_2d_elect(sa + 2u * a_tile, &P.b_map, full, tap * P.Cin + cb * TC_KB, n0);   // raw -> B_hi slot
                 if (trace && it < 16 && lane == 0) trace[it * 8 + 1] = gtimer();          // loads issued
                 if (++cb == P.cblks) { cb = 0; ++tap; if (++kw == P.ksz) { kw = 0; ++kh; } }
                 if (++st == P.stages) { st = 0; ph ^= 1u; }
@@ -543,6 +559,7 @@ static int tc_configure(b200trk_net* net, const Op& op, TcConv* tc, int S) {
     P.ws = op.side ? net->splitk_ws2 : net->splitk_ws;
     P.split_mode = env_int("B200TRK_TC_SPLIT_MODE", 2);
     P.acc2 = env_int("B200TRK_TC_ACC2", 1);
+    P.prefetch_b = env_int("B200TRK_TC_PREFETCH_B", 1);
     const size_t Kt = (size_t)op.k * op.k * op.Cin;
     if (int e = make_map_2d(&P.b_map, op.w, Kt, op.Cout, BN)) return e;
     tc->S_built = S;

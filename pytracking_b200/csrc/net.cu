@@ -177,7 +177,7 @@ static int build(b200trk_net* net, const b200trk_conv_desc_t* convs, int n_convs
     if (B.next < n_convs) {
         int hx = x, hh = H, hw = W, cdim;
         if (bottleneck) {
-            cdim = 512;
+            cdim = convs[B.next].cout;              // 512 (DiMP-50 / PrDiMP-50, dimpnet.py:159), 256 (ToMP, tompnet.py:141-144)
             if (int e = B.add_conv(x, -1, H, W, inplanes, cdim, 3, 1, 1, 0, &hx, &hh, &hw)) return e;
         } else {
             cdim = 256;

@@ -375,18 +375,36 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
         if (lane == 0 && prod == 0) UTR(7);
     };
 
+    // Cross-sweep prefetch: the sample memory does not change during the call and every CTA's unit ranges are fixed, so as soon as
+    // the producer warp has issued the last unit of a sweep it goes on with the first units of the NEXT sweep (as many as there are
+    // shared-memory stages); those tiles land while the CTAs sit in the grid barriers / reductions between the sweeps.
+    // pf_apply / pf_adj = units of the coming apply / adjoint sweep already issued.
+    int pf_apply = 0, pf_adj = 0;
+    const bool xpf = (P.dbg_mode != 6);
+    auto produce_apply_idx = [&](uint32_t ug, int i) {
+        const int u = a_lo + i;
+        const int smp = u / (NPT * kba), r0 = u - smp * (NPT * kba), pt = r0 / kba, kb = r0 - pt * kba;
+        produce(ug, &Q.map_a, pt * 128, kb * 32, smp);
+    };
+    auto produce_adj_idx = [&](uint32_t ug, int i) {
+        const int per_chunk = n * KBT;
+        const int u = t_lo + i;
+        const int chunk = u / per_chunk, r0 = u - chunk * per_chunk, smp = r0 / KBT, kb = r0 - smp * KBT;
+        produce(ug, &Q.map_t, kb * 32, chunk * 128, smp);
+    };
+
     // apply sweep: qslots[segment] = shift-added partial map of every (sample, pixel tile) segment of this CTA's range
-    auto sweep_apply = [&]() {
+    auto sweep_apply = [&](bool adjoint_follows) {
         const int nun = a_hi - a_lo;
         int nseg = 0;
         for (int i = 0; i < nun; ++i) { const int kb = (a_lo + i) % kba; nseg += (i == 0 || kb == 0) ? 1 : 0; }
         if (nun > 0) {
             if (warp == 0) {
-                // (whole warp, converged: see tc_ptx.cuh) unit coordinates advance incrementally
-                int smp = a_lo / (NPT * kba), r0 = a_lo - smp * (NPT * kba), pt = r0 / kba, kb = r0 - pt * kba;
-                for (int i = 0; i < nun; ++i) {
-                    produce(ucount + i, &Q.map_a, pt * 128, kb * 32, smp);
-                    if (++kb == kba) { kb = 0; if (++pt == NPT) { pt = 0; ++smp; } }
+                // (whole warp, converged: see tc_ptx.cuh)
+                for (int i = pf_apply; i < nun; ++i) produce_apply_idx(ucount + i, i);
+                if (xpf && adjoint_follows) {
+                    const int npf = min(NS, t_hi - t_lo);
+                    for (int i = 0; i < npf; ++i) produce_adj_idx(ucount + (uint32_t)nun + i, i);
                 }
             } else if (warp == 1 || warp >= 10) {
                 int kb = a_lo % kba;
@@ -438,6 +456,8 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
         }
         ucount += (uint32_t)nun;
         acount += (uint32_t)nseg;
+        pf_apply = 0;
+        pf_adj = (xpf && adjoint_follows && nun > 0) ? min(NS, t_hi - t_lo) : 0;
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
@@ -450,11 +470,13 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
         if (nun > 0) {
             const int chunk0 = t_lo / per_chunk;
             if (warp == 0) {
-                int chunk = chunk0, r0 = t_lo - chunk0 * per_chunk, smp = r0 / KBT, kb = r0 - smp * KBT;
-                for (int i = 0; i < nun; ++i) {
+                for (int i = pf_adj; i < nun; ++i) {
                     utr_i = i;
-                    produce(ucount + i, &Q.map_t, kb * 32, chunk * 128, smp);
-                    if (++kb == KBT) { kb = 0; if (++smp == n) { smp = 0; ++chunk; } }
+                    produce_adj_idx(ucount + i, i);
+                }
+                if (xpf) {          // an apply sweep always follows an adjoint sweep
+                    const int npf = min(NS, a_hi - a_lo);
+                    for (int i = 0; i < npf; ++i) produce_apply_idx(ucount + (uint32_t)nun + i, i);
                 }
             } else if (warp == 1 || warp >= 10) {
                 uint32_t touched = 0;
@@ -513,6 +535,8 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
         }
         ucount += (uint32_t)nun;
         acount += (nun > 0) ? 1u : 0u;
+        pf_adj = 0;
+        pf_apply = (xpf && nun > 0) ? min(NS, a_hi - a_lo) : 0;
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
@@ -539,7 +563,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
     // ---- s0 = A w0 -----------------------------------------------------------------------------------------------------------
     build_ft(P.w_in);            // (also orders the label maps before their first use)
     SD_STAMP(1);
-    sweep_apply();
+    sweep_apply(P.num_iter > 0);
     SD_STAMP(2);
     grid_barrier(Q.barrier, epoch);
     SD_STAMP(3);
@@ -653,7 +677,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
         grid_barrier(Q.barrier, epoch);
         build_ft(Q.gfinal);
         SD_STAMP(tb + 4);
-        sweep_apply();
+        sweep_apply(it + 1 < P.num_iter);
         SD_STAMP(tb + 5);
         grid_barrier(Q.barrier, epoch);
         SD_STAMP(tb + 6);

@@ -70,18 +70,20 @@ def conv_descs_from_state_dict(sd, arch, backbone_prefix="feature_extractor.", h
 class BackboneEngine:
     """Owns a `b200trk_net_t`. forward(im) mirrors NetWithBackbone.extract_backbone + extract_classification_feat."""
 
-    def __init__(self, state_dict, arch="resnet50", filter_size=4, max_batch=1, crop_size=288, precision=0, device=None, head=True):
+    def __init__(self, state_dict, arch="resnet50", filter_size=4, max_batch=1, crop_size=288, precision=0, device=None, head=True,
+                 head_prefix="classifier.feature_extractor.", norm_scale=None):
         if not torch.cuda.is_available():
             raise RuntimeError("BackboneEngine: CUDA device required (the engine has no CPU path)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.arch = arch
         self.max_batch = max_batch
         self.crop_size = (crop_size, crop_size) if isinstance(crop_size, int) else tuple(crop_size)
-        descs, keep = conv_descs_from_state_dict(state_dict, arch, head=head)
+        descs, keep = conv_descs_from_state_dict(state_dict, arch, head=head, head_prefix=head_prefix)
         self.has_head = head
         arr = (_lib.ConvDesc * len(descs))(*descs)
         out_dim = descs[-1].cout
-        self.norm_scale = math.sqrt(1.0 / (out_dim * filter_size * filter_size))     # dimpnet.py:159
+        # InstanceL2Norm scale: sqrt(1 / (out_dim * filter_size^2)) (dimpnet.py:159, tompnet.py:131) unless given explicitly
+        self.norm_scale = math.sqrt(1.0 / (out_dim * filter_size * filter_size)) if norm_scale is None else float(norm_scale)
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().b200trk_net_create(C.byref(handle), ARCH_ID[arch], arr, len(descs), self.norm_scale,

@@ -475,8 +475,12 @@ def install(max_batch=16, precision=0, skip=()):
                 ("BasicBlock", (2, 2, 2)): "resnet18"}.get((kind, tuple(blocks)))
         if arch is None or not set(net.output_layers) <= {"layer2", "layer3"}:
             return None
-        if kind_net == "ToMPnet":                  # backbone only: the ToMP head works on stored backbone features (tomp.py:282-303)
-            return arch, False
+        if kind_net == "ToMPnet":                  # tompnet.py:141-144: conv3x3 -> InstanceL2Norm on the head layer
+            fx = net.head.feature_extractor
+            if list(net.head_layer) != ["layer3"] or fx is None or len(fx) != 2 or type(fx[-1]).__name__ != "InstanceL2Norm" or \
+                    type(fx[0]).__name__ != "Conv2d" or fx[0].bias is not None:
+                return arch, False
+            return arch, True
         if list(net.classification_layer) != ["layer3"]:
             return None
         head = net.classifier.feature_extractor
@@ -498,15 +502,19 @@ def install(max_batch=16, precision=0, skip=()):
                 eng.close()
             dev = next(net.parameters()).device
             with torch.cuda.device(dev):
-                eng = BackboneEngine(net.state_dict(), arch=arch, filter_size=net.classifier.filter_size if has_head else 1,
+                tomp = type(net).__name__ == "ToMPnet"
+                eng = BackboneEngine(net.state_dict(), arch=arch, filter_size=1 if (tomp or not has_head) else net.classifier.filter_size,
                                      max_batch=max(max_batch, int(im.shape[0])), crop_size=key, precision=precision, device=dev,
-                                     head=has_head)
+                                     head=has_head, head_prefix="head.feature_extractor." if tomp else "classifier.feature_extractor.",
+                                     norm_scale=float(net.head.feature_extractor[-1].scale) if (tomp and has_head) else None)
             per_net[key] = eng
         want = ("layer2", "layer3", "classification") if has_head else ("layer2", "layer3")
         with torch.cuda.device(eng.device), _timed("extract_backbone"):
             out = eng.forward(im.to(eng.device, dtype=torch.float32, non_blocking=True), want=want)
         feat = _FeatDict((l, out[l]) for l in net.output_layers)
         feat.b200_clf = out.get("classification")
+        if type(net).__name__ == "ToMPnet":          # (layer3 tensor, head feature of the same pass) for Head.extract_head_feat
+            net._b200_last_feat = (out["layer3"], out.get("classification"))
         last_pass[net] = (eng, [out[l] for l in getattr(net, "bb_regressor_layer", [])], int(im.shape[0]))
         _count("extract_backbone")
         return feat
@@ -519,6 +527,107 @@ def install(max_batch=16, precision=0, skip=()):
         return ref_extract_clf(self, backbone_feat)
     _bind(nw.NetWithBackbone, "extract_backbone", extract_backbone)
     _bind(dn.DiMPnet, "extract_classification_feat", extract_classification_feat)
+
+    # ToMP head (ltr/models/transformer/heads.py): Head.extract_head_feat (:54-62) of the crop just extracted = the head feature of the
+    # same network pass; of the stored training frames (tomp.py:289-290 recomputes them every frame) = cached until the memory changes.
+    # DenseBoxRegressor.forward (:118-141) = filter projection (a 256x256 linear, torch) + 1x1 correlation + the tower on the engine.
+    hd = importlib.import_module("ltr.models.transformer.heads")
+    ref_head_feat, ref_bbreg = hd.Head.extract_head_feat, hd.DenseBoxRegressor.forward
+    head_cache = weakref.WeakKeyDictionary()          # Head module -> {(data_ptr, shape, version): feature}
+    towers = weakref.WeakKeyDictionary()
+    from .transformer_engine import BoxTower
+
+    def extract_head_feat(self, feat, num_sequences=None):
+        if isinstance(feat, torch.Tensor) and feat.is_cuda and not torch.is_grad_enabled() and not self.training:
+            for net, (eng, feats, batch) in list(last_pass.items()):
+                if getattr(net, "head", None) is self:
+                    hit = getattr(net, "_b200_last_feat", None)
+                    if hit is not None and hit[0] is feat and hit[1] is not None:
+                        _count("Head.extract_head_feat")
+                        out = hit[1]
+                        return out if num_sequences is None else out.reshape(-1, num_sequences, *out.shape[-3:])
+            cache = head_cache.setdefault(self, {})
+            key = (feat.data_ptr(), tuple(feat.shape), feat._version)
+            if key not in cache:
+                if len(cache) > 8:
+                    cache.clear()
+                cache[key] = ref_head_feat(self, feat, None)
+            else:
+                _count("Head.extract_head_feat(cached)")
+            out = cache[key]
+            return out if num_sequences is None else out.reshape(-1, num_sequences, *out.shape[-3:])
+        return ref_head_feat(self, feat, num_sequences)
+
+    def bbreg_forward(self, feat, filter):
+        ok = (not self.training and not torch.is_grad_enabled() and isinstance(feat, torch.Tensor) and feat.is_cuda and feat.dtype == torch.float32 and
+              feat.dim() == 5 and filter.dim() == 4 and filter.shape[0] == feat.shape[1] and filter.shape[-1] == 1 and filter.shape[-2] == 1 and
+              feat.shape[0] * feat.shape[1] <= 4 and feat.shape[2] == self.num_channels and len(self.tower) == 12)
+        if not ok:
+            return ref_bbreg(self, feat, filter)
+        nf, ns, c, h, w = feat.shape
+        filter_proj = self.linear(filter.reshape(-1, c)).reshape(filter.shape) if self.project_filter else filter
+        attention = fl.apply_filter(feat, filter_proj)                      # (nf, ns, h, w): the 1x1 correlation seam
+        key = (h, w)
+        per = towers.setdefault(self, {})
+        tw = per.get(key)
+        if tw is None:
+            with torch.cuda.device(feat.device):
+                tw = BoxTower(self.state_dict(), h, w, max_batch=4, precision=precision, device=feat.device)
+            per[key] = tw
+        _count("DenseBoxRegressor.forward")
+        with _timed("DenseBoxRegressor.forward"):
+            ltrb = tw.forward(feat.reshape(nf * ns, c, h, w), attention.reshape(nf * ns, h, w))
+        return ltrb.unsqueeze(0)
+    _bind(hd.Head, "extract_head_feat", extract_head_feat)
+    _bind(hd.DenseBoxRegressor, "forward", bbreg_forward)
+
+    # FilterPredictor.predict_cls_bbreg_filters_parallel (ltr/models/transformer/filter_predictor.py:92-150): one kernel assembles
+    # the token sequence (features + foreground embedding * label + box-encoding MLP); position encoding and key-padding mask are
+    # per-shape constants; the transformer call goes through the Transformer.forward seam below.
+    fpm = importlib.import_module("ltr.models.transformer.filter_predictor")
+    ref_parallel = fpm.FilterPredictor.predict_cls_bbreg_filters_parallel
+    from .transformer_engine import TokenBuilder
+    builders = weakref.WeakKeyDictionary()
+
+    def predict_parallel(self, train_feat, test_feat, train_label, num_gth_frames, train_ltrb_target, *args, **kwargs):
+        if train_feat.dim() == 4:
+            train_feat = train_feat.unsqueeze(1)
+        if test_feat.dim() == 4:
+            test_feat = test_feat.unsqueeze(1)
+        if train_ltrb_target.dim() == 4:
+            train_ltrb_target = train_ltrb_target.unsqueeze(1)
+        ok = (not self.training and not torch.is_grad_enabled() and all(isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32
+                                                                      for t in (train_feat, test_feat, train_ltrb_target)) and
+              isinstance(train_label, torch.Tensor) and train_label.is_cuda and train_feat.shape[1] == 1 and test_feat.shape[1] == 1 and
+              train_feat.shape[-2:] == test_feat.shape[-2:] and train_feat.shape[2] <= 256 and train_label.dim() == 4 and not args and not kwargs)
+        if not ok:
+            return ref_parallel(self, train_feat, test_feat, train_label, num_gth_frames, train_ltrb_target, *args, **kwargs)
+        nf_tr, _, c, h, w = train_feat.shape
+        nf_te = test_feat.shape[0]
+        st = builders.get(self)
+        if st is None:
+            with torch.cuda.device(train_feat.device):
+                st = {"builder": TokenBuilder(self.state_dict(), device=train_feat.device), "const": {}}
+            builders[self] = st
+        key = (nf_tr, nf_te, h, w, int(num_gth_frames))
+        if key not in st["const"]:
+            test_pos = self.get_positional_encoding(test_feat).permute(1, 2, 0, 3, 4).flatten(2).permute(2, 0, 1)
+            train_pos = self.get_positional_encoding(train_feat).permute(1, 2, 0, 3, 4).flatten(2).permute(2, 0, 1)
+            pos = torch.cat([train_pos, test_pos], dim=0).contiguous()
+            L = (nf_tr + nf_te) * h * w
+            mask = torch.zeros(2, L, dtype=torch.bool)
+            mask[1, num_gth_frames * h * w:-h * w] = True
+            st["const"] = {key: (pos, mask.to(train_feat.device))}
+        pos, mask = st["const"][key]
+        feat = st["builder"].build(train_feat[:, 0], test_feat[:, 0], train_label[:, 0].float(), train_ltrb_target[:, 0], B=2,
+                                   use_test_token=self.use_test_frame_encoding)
+        _count("FilterPredictor.predict_cls_bbreg_filters_parallel")
+        output_embed, enc_mem = self.transformer(feat, mask=mask, query_embed=self.query_embed_fg_decoder.weight, pos_embed=pos)
+        stack_shape = (nf_te, 2, c, h, w)
+        enc_opt = enc_mem[-h * w:].transpose(0, 1).permute(0, 2, 1).reshape(stack_shape)
+        dec_opt = output_embed.squeeze(0).transpose(1, 2).reshape(2, -1, 1, 1)
+        return dec_opt[0].unsqueeze(0), dec_opt[1].unsqueeze(0), enc_opt[:, 0].unsqueeze(1), enc_opt[:, 1].unsqueeze(1)
+    _bind(fpm.FilterPredictor, "predict_cls_bbreg_filters_parallel", predict_parallel)
 
     # AtomIoUNet.get_iou_feat (ltr/models/bbreg/atom_iou_net.py:172-179 <- DiMP.get_iou_features dimp.py:318-320): when its input is
     # exactly what the last engine pass returned, the four convolutions run on the activations still in the engine's arena

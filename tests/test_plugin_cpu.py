@@ -12,7 +12,8 @@ pytestmark = pytest.mark.skipif(not ref_env.reference_available(), reason="refer
 SEAMS = ["filter.apply_filter", "filter.apply_feat_transpose", "dcf.max2d", "DiMPSteepestDescentGN.forward",
          "PrDiMPSteepestDescentNewton.forward", "DiMPL2SteepestDescentGN.forward", "NetWithBackbone.extract_backbone",
          "DiMPnet.extract_classification_feat", "functional._prroi_pooling", "operation.conv2d", "operation.conv1x1",
-         "ConjugateGradient.run", "GaussNewtonCG.run", "Transformer.forward", "AtomIoUNet.get_iou_feat", "AtomIoUNet.predict_iou"]
+         "ConjugateGradient.run", "GaussNewtonCG.run", "Transformer.forward", "AtomIoUNet.get_iou_feat", "AtomIoUNet.predict_iou", "Head.extract_head_feat",
+         "DenseBoxRegressor.forward", "FilterPredictor.predict_cls_bbreg_filters_parallel"]
 
 
 @pytest.fixture()

@@ -244,10 +244,13 @@ def _lockstep(n_frames, seq, use_aug, overrides, sync_filter=False, use_iou_net=
 
 
 def test_sd_sensitivity_to_sample_weight_rounding():
-    """How ill-conditioned the BASELINE configs[1] update is on a REAL tracker memory (50 near-duplicate crops of one scene, unlike
-    independent random samples): the steepest-descent calls of a few consecutive frames run twice from the tracker's own state, the
-    second time with a single sample weight moved by one float32 ulp.  The amplification printed here is what every closed-loop
-    comparison of this tracker inherits -- in the reference (PyTorch-CPU vs PyTorch-CUDA) exactly as in the engine."""
+    """Sensitivity of the BASELINE configs[1] update on a REAL tracker memory: the steepest-descent calls of a few consecutive frames
+    run twice from the tracker's own state, the second time with the sample weights perturbed by 1e-6 relative (what the two
+    implementations of `update_sample_weights` accumulate over ~100 frames).  Typically the filter moves by about as much -- the update
+    is well conditioned -- but DiMP's loss is NOT smooth: the activation derivative contains sign(score) (LeakyReluParDeriv,
+    ltr/models/layers/activation.py:40-44; optimizer.py:139-141), so a perturbation that flips the sign of one near-zero score changes
+    a Gauss-Newton step discontinuously.  The filter-synchronised lock-step test shows exactly that pattern: median 2e-7 per update,
+    sporadic 1e-4 .. 1.6e-3 (same memory, same boxes, weights 1e-6 apart), and BASELINE configs[1] applies such an update every frame."""
     from tracker_cases import OVERRIDES
     from pytracking_b200 import ops, synth
     from pytracking_b200.tracker import DiMPTracker
