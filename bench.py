@@ -58,6 +58,11 @@ CONFIG = {"workload": "DiMP-50 single-GPU, synthetic 288x288 crops, 10 SD iters/
                 "the sample memory are the tracker's steady-state working set"}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the same kernels at the same
+# sizes (profiles/r02k_ncu_summary_all_kernels.txt, profiles/r02k_ncu_summary_conv_tc.txt; tools/ncu_round.sh) -- not measured in this run
+NCU_TRAFFIC = {"sd_tc": 36240000 + 201000, "conv_chain": 149690000, "apply_filter": 726000}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -355,15 +360,15 @@ def run_b200(args, rank, world, local_rank):
     roof = [
         {"kernel": ("sd_tc_kernel<18,0>" if sd_tc else "sd_kernel<18,4,0>") + " (DiMP steepest descent, n=50, 10 it, one launch)",
          "bound": "hbm", "achieved": sd_bytes / (sd_us * 1e-6) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-         "frac": sd_bytes / (sd_us * 1e-6) / 1e9 / peaks["hbm_gbs"], "traffic": None, "us_per_launch": sd_us,
+         "frac": sd_bytes / (sd_us * 1e-6) / 1e9 / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC["sd_tc"] if sd_tc else None, "us_per_launch": sd_us,
          "us_per_sd_iteration": sd_us / SD_ITERS, "algorithmic_bytes": sd_bytes,
          "fused_lower_bound": {"bytes": sd_once, "us_at_peak": sd_once / (peaks["hbm_gbs"] * 1e3), "frac": sd_once / (peaks["hbm_gbs"] * 1e3) / sd_us}},
         {"kernel": "conv_tc_kernel chain (ResNet-50 -> layer3 + clf head, batch 1, 3xTF32 on tcgen05; whole forward)", "bound": "tensor",
          "achieved": net_flops / (net_us * 1e-6) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-         "frac": net_flops / (net_us * 1e-6) / 1e12 / peaks["bf16_tflops"], "traffic": None, "us_per_launch": net_us,
+         "frac": net_flops / (net_us * 1e-6) / 1e12 / peaks["bf16_tflops"], "traffic": NCU_TRAFFIC["conv_chain"], "us_per_launch": net_us,
          "algorithmic_flops": net_flops, "mma_issue_flops": 3 * net_flops},
         {"kernel": "apply_filter_kernel<18,16> (classify, 1 sample)", "bound": "hbm", "achieved": af_bytes / (af_us * 1e-6) / 1e9,
-         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": af_bytes / (af_us * 1e-6) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": af_bytes / (af_us * 1e-6) / 1e9 / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC["apply_filter"],
          "us_per_launch": af_us, "algorithmic_bytes": af_bytes},
     ]
     out = {
@@ -376,6 +381,7 @@ def run_b200(args, rank, world, local_rank):
                 "ms_per_frame_median": float(np.median(per_frame) * 1e3)},
         "gpu_launches": int(launches),
         "roofline": roof[0], "rooflines": roof, "peak_source": peaks["source"],
+        "traffic_source": "ncu --set full captures committed under profiles/r02k_ncu_summary_*.txt (same kernels, same sizes, separate run)",
         "tracking": {"mean_iou_vs_synthetic_ground_truth": float(np.mean(ious)), "sequences": len(ious), "frames_per_sequence": len(boxes),
                      "gather": "one all_gather of [frames,6] per sequence at the end (pytracking_b200/shard.py)"},
         "clocks": clocks,

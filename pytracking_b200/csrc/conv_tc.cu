@@ -46,6 +46,8 @@ struct TcParams {
     int BN, stages;
     int total_kb, kb_per_split, splits, cblks;
     int relu, split_mode;
+    int cluster_red; // 1: the split-K CTAs of a tile form a thread-block cluster (1,1,splits) and reduce their partial tiles through
+                     //    distributed shared memory instead of an L2 workspace + arrival counter
     int prefetch_b;  // 1: the weight tiles of the first pipeline stages are requested before griddepcontrol.wait (they do not depend on the previous layer)
     int acc2;        // 1: the two small products (A_lo*B_hi, A_hi*B_lo) accumulate in a TMEM accumulator of their own (columns BN..2BN)
     uint32_t a_bytes, b_bytes;
@@ -65,6 +67,23 @@ __device__ __forceinline__ void tc_finish4(const TcParams& P, size_t off, const 
     f.x += r.x; f.y += r.y; f.z += r.z; f.w += r.w;
     if (P.relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
     *reinterpret_cast<float4*>(P.out_raw + off) = f;
+}
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+    return v;
 }
 
 // CW = number of converter / epilogue warps (4 or 8). With 8, warps w and w+4 share a TMEM lane quadrant and split the
@@ -310,6 +329,26 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
                     }
                 }
             }
+        } else if (P.cluster_red) {
+            // ---- split-K through distributed shared memory, phase A: this CTA's partial tile -> its own shared memory (the operand
+            //      pipeline buffers are idle: every MMA that read them has retired). Row pitch BN + 4 floats. ----
+            float* red = reinterpret_cast<float*>(tc_smem_raw + (smem_base - smem_u32(tc_smem_raw)));
+            const int RP = P.BN + 4;
+            for (int c = chalf; c < nchunks; c += CSH) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                if (P.acc2) {
+                    uint32_t v2[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(P.BN + c * 32), v2);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+                }
+                float* dst = red + (size_t)(q * 32 + lane) * RP + c * 32;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            }
         } else {
             // ---- split-K: partial tile -> L2 workspace (coalesced), tile-wide arrival counter, then EVERY split CTA
             //      reduces its share of the tile rows in split order (fixed order => deterministic) ----
@@ -386,6 +425,40 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
         }
         tc_fence_before();
         if (dbg && threadIdx.x == 64) dbg[6] = gtimer();              // epilogue done
+    }
+    if (P.cluster_red && P.splits > 1) {
+        // ---- phase B: every thread of the cluster meets (all partial tiles are staged), then each split CTA sums its share of the
+        //      tile rows over the peers' shared memory in split order (fixed order => bitwise deterministic) and finishes them ----
+        cluster_sync_all();
+        if (dbg && threadIdx.x == 64) dbg[5] = gtimer();              // all splits of the tile staged
+        if (warp >= 2) {
+            const int ew = warp - 2, lrow = lane >> 3, lcol = (lane & 7) * 4;
+            const int RP = P.BN + 4, nchunks = P.BN / 32;
+            const uint32_t red_u32 = smem_base;
+            const int rank = (int)cluster_rank();
+            for (int g = rank + P.splits * ew; g < 32; g += P.splits * CW) {
+                const int row = g * 4 + lrow;
+                const int ly = row / P.BW, lx = row - ly * P.BW;
+                const int oy = th * P.BH + ly, ox = tw * P.BW + lx;
+                if (!(row < P.BW * P.BH && oy < P.Hout && ox < P.Wout)) continue;
+                const size_t obase = (((size_t)s * P.Hout + oy) * P.Wout + ox) * P.Cout;
+                for (int c = 0; c < nchunks; ++c) {
+                    const int n = n0 + c * 32 + lcol;
+                    const uint32_t a = red_u32 + (uint32_t)((row * RP + c * 32 + lcol) * 4);
+                    const float4 bias = P.bias ? __ldg(reinterpret_cast<const float4*>(P.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 res = P.residual ? __ldg(reinterpret_cast<const float4*>(P.residual + obase + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 pv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) pv[u] = (u < P.splits) ? ld_dsmem_f4(a, (uint32_t)u) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { f.x += pv[u].x; f.y += pv[u].y; f.z += pv[u].z; f.w += pv[u].w; }
+                    tc_finish4(P, obase + n, bias, res, f);
+                }
+            }
+        }
+        cluster_sync_all();             // no CTA may leave (and release its shared memory) while a peer still reads it
+        if (dbg && threadIdx.x == 64) dbg[6] = gtimer();
     }
     __syncthreads();
     if (warp == 1) {
@@ -550,6 +623,7 @@ static int tc_configure(b200trk_net* net, const Op& op, TcConv* tc, int S) {
         const int min_kb = env_int("B200TRK_TC_MINKB", 4);
         if (splits > P.total_kb / min_kb) splits = P.total_kb / min_kb;
         if (splits > max_splits) splits = max_splits;
+        if (env_int("B200TRK_TC_CLUSTER", 1) && splits > 8) splits = 8;      // portable cluster size of the DSMEM split-K reduction
         if (splits < 1) splits = 1;
         while (splits > 1 && (size_t)splits * ctas * TC_BM * BN > net->splitk_ws_floats) --splits;
     }
@@ -559,6 +633,7 @@ static int tc_configure(b200trk_net* net, const Op& op, TcConv* tc, int S) {
     P.ws = op.side ? net->splitk_ws2 : net->splitk_ws;
     P.split_mode = env_int("B200TRK_TC_SPLIT_MODE", 2);
     P.acc2 = env_int("B200TRK_TC_ACC2", 1);
+    P.cluster_red = (env_int("B200TRK_TC_CLUSTER", 1) && P.splits > 1 && P.splits <= 8) ? 1 : 0;
     P.prefetch_b = env_int("B200TRK_TC_PREFETCH_B", 1);
     const size_t Kt = (size_t)op.k * op.k * op.Cin;
     if (int e = make_map_2d(&P.b_map, op.w, Kt, op.Cout, BN)) return e;
@@ -573,7 +648,7 @@ int tc_conv_launch(b200trk_net* net, const Op& op, int S, cudaStream_t st) {
     const TcParams& P = tc->P;
     const uint32_t stage_bytes = 2u * TC_BM * 128u + 2u * P.b_bytes;
     size_t smem = (size_t)P.stages * stage_bytes + 1024;
-    if (smem < 64 * 1024) smem = 64 * 1024;       // the epilogue stages 4 x 32 x 36 floats in the (idle) pipeline buffers
+    if (smem < 72 * 1024) smem = 72 * 1024;       // the epilogue stages accumulator rows in the (idle) pipeline buffers: up to 128 x 132 floats
     static const int cw = env_int("B200TRK_TC_CW", 8) == 4 ? 4 : 8;
     static bool attr = false;
     if (!attr) {
@@ -585,11 +660,20 @@ int tc_conv_launch(b200trk_net* net, const Op& op, int S, cudaStream_t st) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid; cfg.blockDim = dim3(64 + 32 * cw); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    int nat = 0;
     static const int use_pdl = env_int("B200TRK_TC_PDL", 1);
-    cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
+    if (use_pdl) {
+        at[nat].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[nat].val.programmaticStreamSerializationAllowed = 1;
+        ++nat;
+    }
+    if (P.cluster_red) {
+        at[nat].id = cudaLaunchAttributeClusterDimension;
+        at[nat].val.clusterDim.x = 1; at[nat].val.clusterDim.y = 1; at[nat].val.clusterDim.z = (unsigned)P.splits;
+        ++nat;
+    }
+    cfg.attrs = at; cfg.numAttrs = nat;
     if (cw == 4) B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<4>, P));
     else B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<8>, P));
     B200_LAUNCH_CHECK();

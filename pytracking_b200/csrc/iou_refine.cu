@@ -21,7 +21,7 @@ struct b200trk_iou_predictor {
     float bp = 0.f;
     // per-call scratch (R <= RMAX)
     float *rois = nullptr, *pool3 = nullptr, *pool4 = nullptr, *act = nullptr, *gpool3 = nullptr, *gpool4 = nullptr;
-    float *grois3 = nullptr, *grois4 = nullptr, *rel = nullptr, *sznorm = nullptr, *step = nullptr;
+    float *grois3 = nullptr, *grois4 = nullptr, *rel = nullptr, *sznorm = nullptr, *step = nullptr, *part = nullptr;
     std::vector<void*> owned;
 };
 
@@ -37,48 +37,67 @@ __global__ void make_rois_kernel(const float* __restrict__ boxes, float* __restr
     rois[5 * r] = 0.f; rois[5 * r + 1] = x; rois[5 * r + 2] = y; rois[5 * r + 3] = x + w; rois[5 * r + 4] = y + h;
 }
 
-// One warp per output neuron j of fc3_rt / fc4_rt: a[r][j] = relu(b[j] + sum_k W[j][k] * mod[k / PP] * pooled[r][k]), all R boxes at once
-// (the weight row is streamed once, coalesced; the R pooled vectors are L1/L2 resident).
+// fc3_rt / fc4_rt forward: z[r][j] = sum_k W[j][k] * mod[k / PP] * pooled[r][k].  The 8.9 MB of weights are the only real traffic:
+// CTA = (8 neurons, one K slice of FC_KS elements); the slice of the R pooled vectors is staged (already modulated) in shared memory
+// and each warp streams its neuron's weight slice once, coalesced, against all R boxes.  Partial sums per K slice go to `part`
+// [slices][RMAX][D3 + D4]; `iou_head_kernel` adds them in slice order (deterministic), applies bias + ReLU and the final linear layer.
+constexpr int FC_KS = 640;          // K slice: 6400 = 10 x 640, 2304 = 3.6 x 640
 template <int RMAX>
-__global__ void __launch_bounds__(256) fc_forward_kernel(const float* __restrict__ w3, const float* __restrict__ b3, const float* __restrict__ w4,
-                                                         const float* __restrict__ b4, const float* __restrict__ pool3,
+__global__ void __launch_bounds__(256) fc_forward_kernel(const float* __restrict__ w3, const float* __restrict__ w4, const float* __restrict__ pool3,
                                                          const float* __restrict__ pool4, const float* __restrict__ mod3,
-                                                         const float* __restrict__ mod4, float* __restrict__ act, int R, int K3, int PP3,
-                                                         int K4, int PP4, int D3, int D4) {
-    const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (j >= D3 + D4) return;
-    const bool lvl4 = j >= D3;
-    const float* w = lvl4 ? w4 + (size_t)(j - D3) * K4 : w3 + (size_t)j * K3;
+                                                         const float* __restrict__ mod4, float* __restrict__ part, int R, int K3, int PP3,
+                                                         int K4, int PP4, int D3, int D4, int nb3, int ns3, int ns4) {
+    __shared__ float xs[RMAX][FC_KS];
+    const bool lvl4 = (int)blockIdx.x >= nb3 * ns3;
+    const int bid = lvl4 ? (int)blockIdx.x - nb3 * ns3 : (int)blockIdx.x;
+    const int ns = lvl4 ? ns4 : ns3;
+    const int jb = bid / ns, ks = bid - jb * ns;
+    const int K = lvl4 ? K4 : K3, PP = lvl4 ? PP4 : PP3, D = lvl4 ? D4 : D3;
     const float* pool = lvl4 ? pool4 : pool3;
     const float* mod = lvl4 ? mod4 : mod3;
-    const int K = lvl4 ? K4 : K3, PP = lvl4 ? PP4 : PP3;
+    const int k0 = ks * FC_KS, klen = min(FC_KS, K - k0);
+    for (int i = threadIdx.x; i < RMAX * FC_KS; i += blockDim.x) {
+        const int r = i / FC_KS, k = i - r * FC_KS;
+        xs[r][k] = (r < R && k < klen) ? pool[(size_t)r * K + k0 + k] * mod[(k0 + k) / PP] : 0.f;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = jb * 8 + warp;
+    if (j >= D) return;
+    const float* w = (lvl4 ? w4 : w3) + (size_t)j * K + k0;
     float acc[RMAX];
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) acc[r] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-        const float wm = w[k] * mod[k / PP];
+    for (int k = lane; k < klen; k += 32) {
+        const float wv = w[k];
 #pragma unroll
-        for (int r = 0; r < RMAX; ++r)
-            if (r < R) acc[r] = fmaf(wm, pool[(size_t)r * K + k], acc[r]);
+        for (int r = 0; r < RMAX; ++r) acc[r] = fmaf(wv, xs[r][k], acc[r]);
     }
-    const float bias = lvl4 ? b4[j - D3] : b3[j];
+    const int Dall = D3 + D4, jg = (lvl4 ? D3 : 0) + j;
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) {
-        if (r < R) {
-            const float v = warp_sum(acc[r]) + bias;
-            if (lane == 0) act[(size_t)r * (D3 + D4) + j] = fmaxf(v, 0.f);
-        }
+        const float v = warp_sum(acc[r]);
+        if (lane == 0 && r < R) part[((size_t)ks * RMAX + r) * Dall + jg] = v;
     }
 }
 
-// iou[r] = bp + sum_j wp[j] * a[r][j]  (iou_predictor, atom_iou_net.py:134); one warp per box
-__global__ void iou_head_kernel(const float* __restrict__ act, const float* __restrict__ wp, float bp, float* __restrict__ iou, int R, int D) {
+// a[r][j] = relu(b[j] + sum over the K slices); iou[r] = bp + sum_j wp[j] * a[r][j]  (iou_predictor, atom_iou_net.py:134); one warp per box
+__global__ void iou_head_kernel(const float* __restrict__ part, const float* __restrict__ b3, const float* __restrict__ b4, float* __restrict__ act,
+                                const float* __restrict__ wp, float bp, float* __restrict__ iou, int R, int D3, int D4, int ns3, int ns4, int RMAX) {
     const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (r >= R) return;
+    const int D = D3 + D4;
     float s = 0.f;
-    for (int j = lane; j < D; j += 32) s = fmaf(wp[j], act[(size_t)r * D + j], s);
+    for (int j = lane; j < D; j += 32) {
+        const int ns = j < D3 ? ns3 : ns4;
+        float z = j < D3 ? b3[j] : b4[j - D3];
+        for (int k = 0; k < ns; ++k) z += part[((size_t)k * RMAX + r) * D + j];
+        z = fmaxf(z, 0.f);
+        act[(size_t)r * D + j] = z;
+        s = fmaf(wp[j], z, s);
+    }
     s = warp_sum(s);
-    if (lane == 0) iou[r] = s + bp;
+    if (lane == 0 && iou) iou[r] = s + bp;
 }
 
 // d iou[r] / d pooled[r][k] = mod[k / PP] * sum_j wp[j] * [a[r][j] > 0] * W[j][k]; thread = k (coalesced over the rows of W)
@@ -206,6 +225,7 @@ extern "C" int b200trk_iou_predictor_create(b200trk_iou_predictor_t** out, const
     if (!e) e = iou_alloc(p, &p->gpool3, (size_t)IOU_RMAX * K3);
     if (!e) e = iou_alloc(p, &p->gpool4, (size_t)IOU_RMAX * K4);
     if (!e) e = iou_alloc(p, &p->act, (size_t)IOU_RMAX * (D3 + D4));
+    if (!e) e = iou_alloc(p, &p->part, (size_t)((K3 > K4 ? K3 : K4) / FC_KS + 1) * IOU_RMAX * (D3 + D4));
     if (!e) e = iou_alloc(p, &p->grois3, IOU_RMAX * 5);
     if (!e) e = iou_alloc(p, &p->grois4, IOU_RMAX * 5);
     if (!e) e = iou_alloc(p, &p->rel, IOU_RMAX * 4);
@@ -233,13 +253,13 @@ static int iou_eval(b200trk_iou_predictor* p, const float* mod3, const float* mo
     B200_LAUNCH_CHECK();
     if (int e = b200trk_prroi_pool_forward(feat3, p->rois, p->pool3, 1, p->C3, H3, W3, R, p->P3, p->P3, 1.f / 8.f, stream)) return e;
     if (int e = b200trk_prroi_pool_forward(feat4, p->rois, p->pool4, 1, p->C4, H4, W4, R, p->P4, p->P4, 1.f / 16.f, stream)) return e;
-    fc_forward_kernel<IOU_RMAX><<<(D + 7) / 8, 256, 0, st>>>(p->w3, p->b3, p->w4, p->b4, p->pool3, p->pool4, mod3, mod4, p->act, R, K3,
-                                                            p->P3 * p->P3, K4, p->P4 * p->P4, p->D3, p->D4);
+    const int ns3 = (K3 + FC_KS - 1) / FC_KS, ns4 = (K4 + FC_KS - 1) / FC_KS, nb3 = (p->D3 + 7) / 8, nb4 = (p->D4 + 7) / 8;
+    fc_forward_kernel<IOU_RMAX><<<nb3 * ns3 + nb4 * ns4, 256, 0, st>>>(p->w3, p->w4, p->pool3, p->pool4, mod3, mod4, p->part, R, K3, p->P3 * p->P3, K4,
+                                                                      p->P4 * p->P4, p->D3, p->D4, nb3, ns3, ns4);
     B200_LAUNCH_CHECK();
-    if (iou_out) {
-        iou_head_kernel<<<1, 32 * IOU_RMAX, 0, st>>>(p->act, p->wp, p->bp, iou_out, R, D);
-        B200_LAUNCH_CHECK();
-    }
+    iou_head_kernel<<<1, 32 * IOU_RMAX, 0, st>>>(p->part, p->b3, p->b4, p->act, p->wp, p->bp, iou_out, R, p->D3, p->D4, ns3, ns4, IOU_RMAX);
+    B200_LAUNCH_CHECK();
+    (void)D;
     if (!need_grad) return 0;
     const int nb = (K3 + 255) / 256 + (K4 + 255) / 256;
     const size_t smem = (size_t)(p->D3 > p->D4 ? p->D3 : p->D4) * IOU_RMAX * sizeof(float);

@@ -153,6 +153,63 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
     }
 }
 
+
+// The decoder's cross attention has ONE query per (batch, head) (ToMP: a single foreground token): the general kernel above would
+// walk the 972 keys in 16 CTAs of which 124 threads idle.  Here one CTA per (b, h): thread = key for the scores (two-pass softmax in
+// shared memory), then warp w accumulates the keys w, w + 8, ... for all 32 output dims (lane = dim) and the 8 partial rows are summed
+// in warp order (fixed order => deterministic).
+__global__ void __launch_bounds__(256) attention_q1_kernel(const float* __restrict__ Q, const float* __restrict__ Kp, const float* __restrict__ V,
+                                                           const unsigned char* __restrict__ mask, float* __restrict__ O, int L, int B, int H,
+                                                           int ldq, int ldk, int ldv, int ldo, float scale) {
+    extern __shared__ float sp[];                 // [L] scores / probabilities, then [8][32] partial outputs
+    __shared__ float red[32];
+    __shared__ float s_q[AT_HD];
+    const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
+    if (threadIdx.x < AT_HD) s_q[threadIdx.x] = Q[(size_t)b * ldq + h * AT_HD + threadIdx.x] * scale;
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        float sc = -INFINITY;
+        if (!(mask && mask[(size_t)b * L + l])) {
+            const float4* kp = reinterpret_cast<const float4*>(Kp + ((size_t)l * B + b) * ldk + h * AT_HD);
+            sc = 0.f;
+#pragma unroll
+            for (int d = 0; d < AT_HD / 4; ++d) {
+                const float4 k4 = kp[d];
+                sc = fmaf(s_q[4 * d], k4.x, sc); sc = fmaf(s_q[4 * d + 1], k4.y, sc); sc = fmaf(s_q[4 * d + 2], k4.z, sc); sc = fmaf(s_q[4 * d + 3], k4.w, sc);
+            }
+        }
+        sp[l] = sc;
+        mx = fmaxf(mx, sc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        const float p = (sp[l] == -INFINITY) ? 0.f : __expf(sp[l] - mx);
+        sp[l] = p;
+        sum += p;
+    }
+    sum = block_sum(sum, red);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    float acc = 0.f;
+    for (int l = warp; l < L; l += nw) acc = fmaf(sp[l], V[((size_t)l * B + b) * ldv + h * AT_HD + lane], acc);
+    __syncthreads();
+    float* part = sp + L;
+    part[warp * AT_HD + lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        float o = 0.f;
+        for (int w = 0; w < nw; ++w) o += part[w * AT_HD + lane];
+        O[(size_t)b * ldo + h * AT_HD + lane] = o / sum;
+    }
+}
+
 }  // namespace b200trk
 
 using namespace b200trk;
@@ -358,8 +415,8 @@ extern "C" int b200trk_transformer_forward(b200trk_transformer_t* t, const float
         if (small(t->d_t1, Dl.ca_q, nullptr, t->d_q, D, D, 0)) return 1;
         if (int e = gemm(Dl.g_k)) return e;
         if (int e = gemm(Dl.g_v)) return e;
-        attention_kernel<<<dim3(1, B * H), 128, 0, st>>>(t->d_q, buf(t->b_k), buf(t->b_v), key_padding_mask, t->d_att, 1, L, B, H,
-                                                           D, D, D, D, scale);
+        attention_q1_kernel<<<B * H, 256, (size_t)(L + 8 * AT_HD) * sizeof(float), st>>>(t->d_q, buf(t->b_k), buf(t->b_v), key_padding_mask,
+                                                                                         t->d_att, L, B, H, D, D, D, D, scale);
         B200_LAUNCH_CHECK();
         if (small(t->d_att, Dl.ca_o, t->d_tgt, t->d_t2, D, D, 0)) return 1;
         if (ln(t->d_t2, Dl.n2, t->d_tgt, B)) return 1;

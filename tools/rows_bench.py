@@ -40,3 +40,21 @@ for k, v in res.items():
     print("%-86s median %9.1f  min %9.1f" % (k, v[0], v[1]))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/rows_bench.json", "w"), indent=1)
+try:
+    from baseline import ref_env, ref_tracker
+    if ref_env.reference_available():
+        from pytracking_b200.iou import IoUPredictor
+        from pytracking_b200.transformer_engine import BoxTower, TokenBuilder
+        net = ref_tracker.build_dimp_net()
+        pred = IoUPredictor(net.state_dict())
+        f3, f4 = torch.relu(torch.randn(1, 256, 36, 36)).cuda(), torch.relu(torch.randn(1, 256, 18, 18)).cuda()
+        mod = [torch.rand(256).cuda(), torch.rand(256).cuda()]
+        boxes = torch.tensor([[100.0, 110.0, 70.0, 55.0]] * 10).cuda()
+        extra = {"IoUNet refine R=10, 5 ascent steps (us)": timeit(lambda: pred.refine(mod, [f3, f4], boxes, 5, 1.0)),
+                 "IoUNet predict_iou + box gradient R=10 (us)": timeit(lambda: pred.predict_iou(mod, [f3, f4], boxes, return_grad=True))}
+        for k, v in extra.items():
+            print("%-86s median %9.1f  min %9.1f" % (k, v[0], v[1]))
+        res.update(extra)
+        json.dump(res, open("gpurun_out/rows_bench.json", "w"), indent=1)
+except Exception as e:
+    print("IoU rows skipped:", repr(e))
