@@ -71,18 +71,20 @@ __global__ void small_linear_kernel(const float* __restrict__ x, const float* __
 
 // nn.MultiheadAttention core: O[lq,b,h,:] = softmax_l(Q[lq,b,h,:] . K[l,b,h,:] / sqrt(32) + mask) V[l,b,h,:]
 // head_dim = 32. Q/K/V are token-major with leading dimensions ldq/ldk/ldv (floats per token).
-// CTA = 32 queries of one (b, h); 4 lanes per query split the keys of each 64-key tile; online softmax per lane,
-// merged with shuffles at the end.
-constexpr int AT_Q = 32, AT_KT = 64, AT_HD = 32;
+// CTA = 16 queries of one (b, h); 8 lanes per query split the keys of each 64-key tile and take them FOUR at a time: four
+// independent 32-term dot products (the single dependent FMA chain per key was the latency bound of the first version,
+// profiles/r02k_ncu_summary_all_kernels.txt), one running-maximum update per group, then the four rows of V.  Online softmax per
+// lane, the 8 partial states of a query merged with shuffles at the end (fixed order => deterministic).
+constexpr int AT_Q = 16, AT_LPQ = 8, AT_KT = 64, AT_HD = 32;
 __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ Q, const float* __restrict__ Kp,
                                                         const float* __restrict__ V, const unsigned char* __restrict__ mask,
                                                         float* __restrict__ O, int Lq, int L, int B, int H, int ldq, int ldk,
                                                         int ldv, int ldo, float scale) {
     __shared__ __align__(16) float Ks[AT_KT][AT_HD + 4];
     __shared__ __align__(16) float Vs[AT_KT][AT_HD + 4];
-    __shared__ unsigned char Ms[AT_KT];
+    __shared__ float Mb[AT_KT];                     // 0 for a live key, -inf for a masked / out-of-range one
     const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
-    const int qi = blockIdx.x * AT_Q + (threadIdx.x >> 2), part = threadIdx.x & 3;
+    const int qi = blockIdx.x * AT_Q + (threadIdx.x / AT_LPQ), part = threadIdx.x % AT_LPQ;
     const bool qv = qi < Lq;
     float q[AT_HD], acc[AT_HD];
 #pragma unroll
@@ -110,30 +112,52 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
         }
         if (threadIdx.x < AT_KT) {
             const int l = l0 + threadIdx.x;
-            Ms[threadIdx.x] = (l >= L) ? 1 : (mask ? mask[(size_t)b * L + l] : 0);
+            const bool dead = (l >= L) || (mask && mask[(size_t)b * L + l]);
+            Mb[threadIdx.x] = dead ? -INFINITY : 0.f;
         }
         __syncthreads();
-        for (int j = part; j < AT_KT; j += 4) {
-            if (Ms[j]) continue;
-            float s = 0.f;
+        // keys part, part + 8, part + 16, part + 24 and then the same + 32
+#pragma unroll 1
+        for (int g = 0; g < AT_KT / (4 * AT_LPQ); ++g) {
+            const int j0 = g * 4 * AT_LPQ + part;
+            float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int d = 0; d < AT_HD; ++d) s = fmaf(q[d], Ks[j][d], s);
-            if (s > mmax) {
-                const float c = __expf(mmax - s);       // exp(-inf) = 0 on the first key
+            for (int d4 = 0; d4 < AT_HD / 4; ++d4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 k4 = *reinterpret_cast<const float4*>(&Ks[j0 + u * AT_LPQ][4 * d4]);
+                    s[u] = fmaf(q[4 * d4], k4.x, s[u]); s[u] = fmaf(q[4 * d4 + 1], k4.y, s[u]);
+                    s[u] = fmaf(q[4 * d4 + 2], k4.z, s[u]); s[u] = fmaf(q[4 * d4 + 3], k4.w, s[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s[u] += Mb[j0 + u * AT_LPQ];          // -inf removes the key
+            const float gm = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
+            if (gm > mmax) {
+                const float c = __expf(mmax - gm);       // exp(-inf) = 0 on the first live key
                 ssum *= c;
 #pragma unroll
                 for (int d = 0; d < AT_HD; ++d) acc[d] *= c;
-                mmax = s;
+                mmax = gm;
             }
-            const float p = __expf(s - mmax);
-            ssum += p;
+            if (mmax == -INFINITY) continue;             // nothing live so far
+            float p[4];
 #pragma unroll
-            for (int d = 0; d < AT_HD; ++d) acc[d] = fmaf(p, Vs[j][d], acc[d]);
+            for (int u = 0; u < 4; ++u) { p[u] = __expf(s[u] - mmax); ssum += p[u]; }
+#pragma unroll
+            for (int d4 = 0; d4 < AT_HD / 4; ++d4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(&Vs[j0 + u * AT_LPQ][4 * d4]);
+                    acc[4 * d4] = fmaf(p[u], v4.x, acc[4 * d4]); acc[4 * d4 + 1] = fmaf(p[u], v4.y, acc[4 * d4 + 1]);
+                    acc[4 * d4 + 2] = fmaf(p[u], v4.z, acc[4 * d4 + 2]); acc[4 * d4 + 3] = fmaf(p[u], v4.w, acc[4 * d4 + 3]);
+                }
+            }
         }
     }
-    // merge the 4 partial softmax states of a query (lanes 4q .. 4q+3)
+    // merge the 8 partial softmax states of a query (lanes 8q .. 8q+7)
 #pragma unroll
-    for (int o = 1; o < 4; o <<= 1) {
+    for (int o = 1; o < AT_LPQ; o <<= 1) {
         const float m2 = __shfl_xor_sync(0xffffffffu, mmax, o), s2 = __shfl_xor_sync(0xffffffffu, ssum, o);
         const float mn = fmaxf(mmax, m2);
         const float c1 = (mmax == -INFINITY) ? 0.f : __expf(mmax - mn), c2 = (m2 == -INFINITY) ? 0.f : __expf(m2 - mn);
@@ -147,9 +171,15 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
     }
     if (qv) {
         const float inv = 1.f / ssum;
-        float* op = O + ((size_t)qi * B + b) * ldo + h * AT_HD + part * 8;
+        float* op = O + ((size_t)qi * B + b) * ldo + h * AT_HD + part * (AT_HD / AT_LPQ);
 #pragma unroll
-        for (int d = 0; d < 8; ++d) op[d] = acc[part * 8 + d] * inv;
+        for (int d = 0; d < AT_HD / AT_LPQ; ++d) {
+            // (acc is fully unrolled: select the lane's slice without dynamic register indexing)
+            float v = 0.f;
+#pragma unroll
+            for (int pp = 0; pp < AT_LPQ; ++pp) v = (part == pp) ? acc[pp * (AT_HD / AT_LPQ) + d] : v;
+            op[d] = v * inv;
+        }
     }
 }
 

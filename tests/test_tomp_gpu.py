@@ -49,7 +49,8 @@ def test_box_regression_tower_matches_reference_module():
     assert _rel(out, ref_cpu[0]) < 1e-4 and _rel(out, ref_cuda[0]) < 1e-4, (_rel(out, ref_cpu[0]), _rel(out, ref_cuda[0]))
     assert abs(tw.flops / 2 / 1e6 - (4 * 191.1 + 191.1 * 4 / 256)) < 2.0      # 9 * 256 * 256 * 324 = 191.1 MMAC per 256 -> 256 layer at 18x18
     two = tw.forward(torch.cat([feat.cuda()[0], feat.cuda()[0]]), torch.cat([att, att]))
-    assert torch.equal(two[0], two[1]) and torch.equal(two[0], out[0])
+    # the two samples of one launch are bitwise identical; a batch-1 launch may pick another split-K factor (different summation order)
+    assert torch.equal(two[0], two[1]) and _rel(two[0], out[0]) < 1e-5
     tw.close()
 
 
