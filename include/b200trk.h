@@ -46,7 +46,7 @@ const char* b200trk_last_error(void);
 /* 1 when the most recent steepest-descent optimiser call ran the tcgen05 kernel (sd_tc.cu), 0 for the CUDA-core kernel */
 int b200trk_sd_last_kernel(void);
 int b200trk_debug_sd_trace(unsigned long long* out_host);
-int b200trk_debug_sd_units(unsigned long long* out_host);   /* [32][8] per-unit pipeline stamps of the tcgen05 SD kernel */
+int b200trk_debug_sd_units(unsigned long long* out_host);   /* [16][16] per-unit pipeline stamps of the tcgen05 SD kernel */
 /* Number of kernels this library has launched so far in this process (for bench.py's gpu_launches). */
 uint64_t    b200trk_launch_count(void);
 

@@ -71,11 +71,12 @@ extern "C" int b200trk_debug_sd_trace(unsigned long long* out_host) {
     return cudaMemcpy(out_host, p, 512, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
 }
 
-// debug: per-unit pipeline stamps of the tcgen05 SD kernel ([32 units][8] x u64 SM clocks, CTA 0, first adjoint sweep)
+// debug: per-unit pipeline stamps of the tcgen05 SD kernel ([16 units][16] x u64 SM clocks, CTA 0, first adjoint sweep; cleared after the read)
 extern "C" int b200trk_debug_sd_units(unsigned long long* out_host) {
     char* p = (char*)b200trk::workspace(4096, 3);
     if (!p || !out_host) return 1;
-    return cudaMemcpy(out_host, p + 1024, 2048, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
+    if (cudaMemcpy(out_host, p + 1024, 2048, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    return cudaMemset(p + 1024, 0, 2048) == cudaSuccess ? 0 : 1;      // (stamps of the next run start from a clean table)
 }
 
 extern "C" int b200trk_version(void) { return B200TRK_VERSION; }

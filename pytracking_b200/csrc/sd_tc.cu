@@ -282,10 +282,12 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
         __syncthreads();
     };
 
-    // per-unit pipeline stamps (SM clock) of CTA 0 during the first adjoint sweep: utr[unit][8]
+    // per-unit pipeline stamps (SM clock) of CTA 0 during the first adjoint sweep: utr[unit][16]
+    // 0 slot free (producer) 1 TMA issued | 8 converter reaches the unit 2 tile landed 3 TMEM stage free 9 operands in registers 4 tcgen05.st
+    // retired 5 published | 6 MMA warp sees the unit 7 MMAs + commit issued
     long long* utr = nullptr;
     int utr_i = 0;
-#define UTR(k) do { if (utr && utr_i < 32) utr[utr_i * 8 + (k)] = clock64(); } while (0)
+#define UTR(k) do { if (utr && utr_i < 16) utr[utr_i * 16 + (k)] = clock64(); } while (0)
     // ---- operand pipeline pieces (unit index ug = units since kernel start; identical in all roles) -----------------------
     // producer: raw tile of one unit -> shared-memory stage
     auto produce = [&](uint32_t ug, const CUtensorMap* map, int c0, int c1, int c2) {
@@ -337,6 +339,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
             }
         }
         const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + t * 64u + (uint32_t)(half * 16);
+        if (ct == 0) UTR(9);
         tmem_st16(ta, hi);
         tmem_st16(ta + 32u, lo);
         return sb;
@@ -502,6 +505,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
                     int j = 0;
                     for (int jj = 1; jj < ns; ++jj) j = (s_state[jj] == smp) ? jj : j;
                     utr_i = i;
+                    if (ct == 0) UTR(8);
                     float rv[2];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {

@@ -19,16 +19,18 @@ for dbg in (0, 1, 2, 3, 4, 5):
     b = 8 + 10
     d = [(t[b+k+1]-t[b+k])/1e3 for k in range(8)]
     print("dbg %d: s0 sweepA %.2f | it1: resid %.2f | sweepT %.2f | barrier1 %.2f | gsum+b1b+FT %.2f | sweepA %.2f | barrier2 %.2f | qsum+h %.2f | barrier3 %.2f" % (dbg, (t[2]-t[1])/1e3, *d), flush=True)
-for dbgu in (0, 5):
+names = "slot_free tma_issued | conv_at_unit landed tmem_free regs st_retired published | mma_sees mma_committed"
+order = [0, 1, 8, 2, 3, 9, 4, 5, 6, 7]
+_lib.lib().b200trk_debug_sd_units((C.c_uint64 * 256)())
+for dbgu in (6, 0, 4, 1, 3):
   os.environ["B200TRK_SD_DBG"] = str(dbgu)
   for _ in range(3):
     ops.dimp_sd_gn(w0, feat, bb, sw, *luts, 3, 0.9, 0.01)
   torch.cuda.synchronize()
   ub = (C.c_uint64 * 256)()
   _lib.check(_lib.lib().b200trk_debug_sd_units(ub))
-  u = np.array(list(ub), dtype=np.float64).reshape(32, 8)
-  t0 = u[0, 0]
-  print("dbg %d  unit: sfree_ok tma_issued | full_ok tfree_ok st_done arrived | tready_ok committed   (SM clocks since first)" % dbgu)
-  for i in range(14):
-    if u[i, 0] == 0: break
-    print("%2d: " % i + " ".join("%7d" % (x - t0) for x in u[i]))
+  u = np.array(list(ub), dtype=np.float64).reshape(16, 16)
+  t0 = u[u > 0].min()
+  print("dbg %d  unit: %s   (SM clocks since first; -1 = not stamped)" % (dbgu, names))
+  for i in range(16):
+    print("%2d: " % i + " ".join("%7d" % ((u[i, k] - t0) if u[i, k] > 0 else -1) for k in order))
