@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
     SD_STAMP(0);
     // ---- prologue ------------------------------------------------------------------------------------------------------------
     if (tid == 0) {
-        for (int i = 0; i < NS; ++i) { mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_sfree[i]), STC_CT / 32); }
-        for (int i = 0; i < STC_NT; ++i) { mbar_init(smem_u32(&s_tready[i]), STC_CT / 32); mbar_init(smem_u32(&s_tfree[i]), 3); }
+        for (int i = 0; i < NS; ++i) { mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_sfree[i]), STC_CT / 64); }
+        for (int i = 0; i < STC_NT; ++i) { mbar_init(smem_u32(&s_tready[i]), STC_CT / 64); mbar_init(smem_u32(&s_tfree[i]), 3); }
         mbar_init(smem_u32(&s_acc), 3);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // state slots: the samples of this CTA's adjoint range (runs of KBT units per (chunk, sample))
@@ -250,7 +250,8 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
     uint32_t ucount = 0, acount = 0;    // units / accumulator commits so far (identical in every thread)
     unsigned epoch = 0;
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const int q = warp & 3, half = (warp - 2) >> 2;                  // converter warps: TMEM lane quadrant, column half
+    const int q = warp & 3, half = (warp - 2) >> 2;                  // converter warps: TMEM lane quadrant; conversion group / epilogue column half
+    const int grp = half;
     const int ct = tid - 64;
 
     // F^T (hi | lo) of all channel blocks from a [C][16] vector in global memory
@@ -288,72 +289,84 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
     long long* utr = nullptr;
     int utr_i = 0;
 #define UTR(k) do { if (utr && utr_i < 16) utr[utr_i * 16 + (k)] = clock64(); } while (0)
-    // ---- operand pipeline pieces (unit index ug = units since kernel start; identical in all roles) -----------------------
-    // producer: raw tile of one unit -> shared-memory stage
-    auto produce = [&](uint32_t ug, const CUtensorMap* map, int c0, int c1, int c2) {
-        const uint32_t s = ug % (uint32_t)NS, sp = (ug / (uint32_t)NS) & 1u;
-        mbar_wait(smem_u32(&s_sfree[s]), sp ^ 1u);
+    // ---- operand pipeline pieces --------------------------------------------------------------------------------------------
+    // Every role walks the units of a sweep with RUNNING stage counters and unit coordinates (no integer division per unit: the
+    // per-unit index arithmetic with run-time divisors cost the converter warps several hundred cycles per unit and, not the TMA
+    // unit, paced the sweeps: profiles/r02n_sd_tc_units.txt).  ug = units since kernel start; shared-memory stage = ug % NS with
+    // parity (ug / NS) & 1, tensor-memory stage = ug % 4 with parity (ug / 4) & 1.
+    struct Stage { uint32_t s, sp, t, tp; };
+    auto stage_of = [&](uint32_t ug) { Stage g; g.s = ug % (uint32_t)NS; g.sp = (ug / (uint32_t)NS) & 1u; g.t = ug % STC_NT; g.tp = (ug / STC_NT) & 1u; return g; };
+    auto stage_next = [&](Stage& g) {
+        if (++g.s == (uint32_t)NS) { g.s = 0; g.sp ^= 1u; }
+        if (++g.t == (uint32_t)STC_NT) { g.t = 0; g.tp ^= 1u; }
+    };
+    // producer: raw tile of one unit -> shared-memory stage g.s
+    auto produce = [&](const Stage& g, const CUtensorMap* map, int c0, int c1, int c2) {
+        mbar_wait(smem_u32(&s_sfree[g.s]), g.sp ^ 1u);
         if (lane == 0) UTR(0);
-        const uint32_t full = smem_u32(&s_full[s]);
+        const uint32_t full = smem_u32(&s_full[g.s]);
         if (P.dbg_mode == 4 || (P.dbg_mode == 5 && (blockIdx.x & 1))) {
             // timing experiments (results are garbage): 4 = no TMA traffic, 5 = only every second CTA loads
             mbar_arrive_elect(full);
             return;
         }
         mbar_expect_tx_elect(full, STC_A_BYTES);
-        tma_load_3d_elect(base_u32 + s * STC_STAGE_BYTES, map, full, c0, c1, c2);
+        tma_load_3d_elect(base_u32 + g.s * STC_STAGE_BYTES, map, full, c0, c1, c2);
         if (lane == 0) UTR(1);
     };
-    // converter, first half: wait for the tile and for the tensor-memory stage, read this thread's half row (16 fp32) and store
-    // hi (raw: the datapath truncates) and lo into TMEM. Returns the shared-memory stage (for the adjoint sweep's B tile).
-    auto convert_a = [&](uint32_t ug, bool transposed) -> uint8_t* {
-        const uint32_t s = ug % (uint32_t)NS, sp = (ug / (uint32_t)NS) & 1u;
-        const uint32_t t = ug % STC_NT, tp = (ug / STC_NT) & 1u;
-        mbar_wait(smem_u32(&s_full[s]), sp);
+    // converter: the eight converter warps form TWO groups of four (grp 0 = warps 2-5, grp 1 = warps 6-9; a group covers the four
+    // TMEM lane quadrants) and the groups take alternate units of a sweep: the per-unit chain of barrier waits, shared-memory
+    // reads, tensor-memory stores and the publish step is latency, not throughput, so two independent chains double the unit rate
+    // (profiles/r02o_sd_tc_units.txt).  Thread = operand row: wait for the tile and for the tensor-memory stage, then 2 x (16 fp32 of
+    // the row -> hi (raw: the datapath truncates) and lo -> tcgen05.st).  Returns the shared-memory stage (for the adjoint sweep's B tile).
+    auto convert_unit = [&](const Stage& g, bool transposed) -> uint8_t* {
+        mbar_wait(smem_u32(&s_full[g.s]), g.sp);
         if (ct == 0) UTR(2);
-        mbar_wait(smem_u32(&s_tfree[t]), tp ^ 1u);
+        mbar_wait(smem_u32(&s_tfree[g.t]), g.tp ^ 1u);
         tc_fence_after();
         if (ct == 0) UTR(3);
-        uint8_t* sb = base + (size_t)s * STC_STAGE_BYTES;
+        uint8_t* sb = base + (size_t)g.s * STC_STAGE_BYTES;
+        if (P.dbg_mode == 3) return sb;     // timing experiment: no operand conversion
         const int row = q * 32 + lane;
         const uint8_t* arow = sb + row * 128;
-        uint32_t hi[16], lo[16];
-        if (P.dbg_mode == 3) return sb;     // timing experiment: no operand conversion
-        if (!transposed) {
-            // tile = [128 rows][32 k] with the 128-byte swizzle: this thread's row, 16 consecutive k
+        const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + g.t * 64u;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 x = *reinterpret_cast<const float4*>(arow + ((((half * 4 + j) ^ (row & 7))) << 4));
-                hi[4 * j] = __float_as_uint(x.x); hi[4 * j + 1] = __float_as_uint(x.y); hi[4 * j + 2] = __float_as_uint(x.z); hi[4 * j + 3] = __float_as_uint(x.w);
-                lo[4 * j] = __float_as_uint(lo_trunc(x.x)); lo[4 * j + 1] = __float_as_uint(lo_trunc(x.y));
-                lo[4 * j + 2] = __float_as_uint(lo_trunc(x.z)); lo[4 * j + 3] = __float_as_uint(lo_trunc(x.w));
-            }
-        } else {
-            // tile = [32 k][128 rows] linear (512-byte lines): the lanes of a warp read 32 consecutive words of one line
-            const float* col = reinterpret_cast<const float*>(sb) + (half * 16) * 128 + row;
+        for (int hh = 0; hh < 2; ++hh) {
+            uint32_t hi[16], lo[16];
+            if (!transposed) {
+                // tile = [128 rows][32 k] with the 128-byte swizzle: this thread's row, 16 consecutive k
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float x = col[j * 128];
-                hi[j] = __float_as_uint(x);
-                lo[j] = __float_as_uint(lo_trunc(x));
+                for (int j = 0; j < 4; ++j) {
+                    const float4 x = *reinterpret_cast<const float4*>(arow + ((((hh * 4 + j) ^ (row & 7))) << 4));
+                    hi[4 * j] = __float_as_uint(x.x); hi[4 * j + 1] = __float_as_uint(x.y); hi[4 * j + 2] = __float_as_uint(x.z); hi[4 * j + 3] = __float_as_uint(x.w);
+                    lo[4 * j] = __float_as_uint(lo_trunc(x.x)); lo[4 * j + 1] = __float_as_uint(lo_trunc(x.y));
+                    lo[4 * j + 2] = __float_as_uint(lo_trunc(x.z)); lo[4 * j + 3] = __float_as_uint(lo_trunc(x.w));
+                }
+            } else {
+                // tile = [32 k][128 rows] linear (512-byte lines): the lanes of a warp read 32 consecutive words of one line
+                const float* col = reinterpret_cast<const float*>(sb) + (hh * 16) * 128 + row;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float x = col[j * 128];
+                    hi[j] = __float_as_uint(x);
+                    lo[j] = __float_as_uint(lo_trunc(x));
+                }
             }
+            tmem_st16(ta + (uint32_t)(hh * 16), hi);
+            tmem_st16(ta + 32u + (uint32_t)(hh * 16), lo);
         }
-        const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + t * 64u + (uint32_t)(half * 16);
         if (ct == 0) UTR(9);
-        tmem_st16(ta, hi);
-        tmem_st16(ta + 32u, lo);
         return sb;
     };
-    // converter, second half: publish the unit
-    auto convert_done = [&](uint32_t ug) {
-        const uint32_t s = ug % (uint32_t)NS, t = ug % STC_NT;
+    // converter, last step: publish the unit (shared-memory stage free again, tensor-memory stage ready); one arrival per warp of the group
+    auto publish = [&](const Stage& g) {
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         if (ct == 0) UTR(4);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_sfree[s])) : "memory");
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_tready[t])) : "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_sfree[g.s])) : "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_tready[g.t])) : "memory");
         }
         if (ct == 0) UTR(5);
     };
@@ -361,12 +374,11 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
     // its own 16-column accumulator (acc + 16 * prod); issuing a tcgen05.mma costs one warp ~100 cycles of scalar work, so a single
     // issue warp (12 MMAs per unit) was the slowest stage of the pipeline. A = tensor-memory stage t, B from shared memory.
     const int prod = (warp == 1) ? 0 : warp - 9;
-    auto issue = [&](uint32_t ug, uint32_t acc, uint32_t b_hi_addr, bool first) {
-        const uint32_t t = ug % STC_NT, tp = (ug / STC_NT) & 1u;
-        mbar_wait(smem_u32(&s_tready[t]), tp);
+    auto issue = [&](const Stage& g, uint32_t acc, uint32_t b_hi_addr, bool first) {
+        mbar_wait(smem_u32(&s_tready[g.t]), g.tp);
         tc_fence_after();
         if (lane == 0 && prod == 0) UTR(6);
-        const uint32_t a_op = tmem + t * 64u + ((prod == 0) ? 32u : 0u);                               // lo | hi | hi
+        const uint32_t a_op = tmem + g.t * 64u + ((prod == 0) ? 32u : 0u);                             // lo | hi | hi
         const uint32_t d_b = make_smem_desc_lo(b_hi_addr) + ((prod == 1) ? (2048u >> 4) : 0u);       // hi | lo | hi
         if (P.dbg_mode != 1 && !(P.dbg_mode == 2 && prod != 2)) {     // (timing experiments: 1 = no MMAs, 2 = hi*hi only)
 #pragma unroll
@@ -374,9 +386,17 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
                 tc_mma_tf32_ts_lo(acc + (uint32_t)(16 * prod), a_op + (uint32_t)(k * 8), d_b + (uint32_t)(k * 32 >> 4), idesc,
                                   (first && k == 0) ? 0u : 1u);
         }
-        tc_commit_elect(smem_u32(&s_tfree[t]));
+        tc_commit_elect(smem_u32(&s_tfree[g.t]));
         if (lane == 0 && prod == 0) UTR(7);
     };
+
+    // unit coordinates: adjoint sweep (chunk, sample, pixel block), apply sweep (sample, pixel tile, channel block)
+    struct AdjPos { int chunk, smp, kb; };
+    struct AppPos { int smp, pt, kb; };
+    auto adj_pos = [&](int u) { AdjPos c; const int per_chunk = n * KBT; c.chunk = u / per_chunk; const int r0 = u - c.chunk * per_chunk; c.smp = r0 / KBT; c.kb = r0 - c.smp * KBT; return c; };
+    auto adj_next = [&](AdjPos& c) { if (++c.kb == KBT) { c.kb = 0; if (++c.smp == n) { c.smp = 0; ++c.chunk; } } };
+    auto app_pos = [&](int u) { AppPos c; c.smp = u / (NPT * kba); const int r0 = u - c.smp * (NPT * kba); c.pt = r0 / kba; c.kb = r0 - c.pt * kba; return c; };
+    auto app_next = [&](AppPos& c) { if (++c.kb == kba) { c.kb = 0; if (++c.pt == NPT) { c.pt = 0; ++c.smp; } } };
 
     // Cross-sweep prefetch: the sample memory does not change during the call and every CTA's unit ranges are fixed, so as soon as
     // the producer warp has issued the last unit of a sweep it goes on with the first units of the NEXT sweep (as many as there are
@@ -384,50 +404,61 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
     // pf_apply / pf_adj = units of the coming apply / adjoint sweep already issued.
     int pf_apply = 0, pf_adj = 0;
     const bool xpf = (P.dbg_mode != 6);
-    auto produce_apply_idx = [&](uint32_t ug, int i) {
-        const int u = a_lo + i;
-        const int smp = u / (NPT * kba), r0 = u - smp * (NPT * kba), pt = r0 / kba, kb = r0 - pt * kba;
-        produce(ug, &Q.map_a, pt * 128, kb * 32, smp);
+    auto produce_apply_run = [&](uint32_t ug, int i0, int i1) {        // units i0 .. i1-1 of this CTA's apply range; ug = global index of i0
+        if (i0 >= i1) return;
+        Stage g = stage_of(ug);
+        AppPos c = app_pos(a_lo + i0);
+        for (int i = i0; i < i1; ++i) {
+            produce(g, &Q.map_a, c.pt * 128, c.kb * 32, c.smp);
+            stage_next(g); app_next(c);
+        }
     };
-    auto produce_adj_idx = [&](uint32_t ug, int i) {
-        const int per_chunk = n * KBT;
-        const int u = t_lo + i;
-        const int chunk = u / per_chunk, r0 = u - chunk * per_chunk, smp = r0 / KBT, kb = r0 - smp * KBT;
-        produce(ug, &Q.map_t, kb * 32, chunk * 128, smp);
+    auto produce_adj_run = [&](uint32_t ug, int i0, int i1, bool traced) {
+        if (i0 >= i1) return;
+        Stage g = stage_of(ug);
+        AdjPos c = adj_pos(t_lo + i0);
+        for (int i = i0; i < i1; ++i) {
+            if (traced) utr_i = i;
+            produce(g, &Q.map_t, c.kb * 32, c.chunk * 128, c.smp);
+            stage_next(g); adj_next(c);
+        }
     };
 
     // apply sweep: qslots[segment] = shift-added partial map of every (sample, pixel tile) segment of this CTA's range
     auto sweep_apply = [&](bool adjoint_follows) {
         const int nun = a_hi - a_lo;
         int nseg = 0;
-        for (int i = 0; i < nun; ++i) { const int kb = (a_lo + i) % kba; nseg += (i == 0 || kb == 0) ? 1 : 0; }
+        { int kb = (nun > 0) ? a_lo % kba : 0; for (int i = 0; i < nun; ++i) { nseg += (i == 0 || kb == 0) ? 1 : 0; if (++kb == kba) kb = 0; } }
         if (nun > 0) {
             if (warp == 0) {
                 // (whole warp, converged: see tc_ptx.cuh)
-                for (int i = pf_apply; i < nun; ++i) produce_apply_idx(ucount + i, i);
-                if (xpf && adjoint_follows) {
-                    const int npf = min(NS, t_hi - t_lo);
-                    for (int i = 0; i < npf; ++i) produce_adj_idx(ucount + (uint32_t)nun + i, i);
-                }
+                produce_apply_run(ucount + (uint32_t)pf_apply, pf_apply, nun);
+                if (xpf && adjoint_follows) produce_adj_run(ucount + (uint32_t)nun, 0, min(NS, t_hi - t_lo), false);
             } else if (warp == 1 || warp >= 10) {
                 int kb = a_lo % kba;
                 const uint32_t ftb_m = smem_u32(ftb);
+                Stage g = stage_of(ucount);
                 for (int i = 0; i < nun; ++i) {
                     const bool seg_first = (i == 0 || kb == 0), seg_last = (i == nun - 1 || kb == kba - 1);
-                    issue(ucount + i, tmem + STC_ACC_COL, ftb_m + (uint32_t)kb * 4096u, seg_first);
+                    issue(g, tmem + STC_ACC_COL, ftb_m + (uint32_t)kb * 4096u, seg_first);
                     if (seg_last) tc_commit_elect(smem_u32(&s_acc));
                     if (++kb == kba) kb = 0;
+                    stage_next(g);
                 }
             } else {
                 int seg = 0, kb_first = 0;
+                Stage g = stage_of(ucount);
+                AppPos c = app_pos(a_lo);
                 for (int i = 0; i < nun; ++i) {
-                    const int u = a_lo + i;
-                    const int smp = u / (NPT * kba), r = u - smp * (NPT * kba), pt = r / kba, kb = r - pt * kba;
-                    const bool seg_first = (i == 0 || kb == 0), seg_last = (i == nun - 1 || kb == kba - 1);
-                    if (seg_first) kb_first = kb;
-                    convert_a(ucount + i, true);
-                    convert_done(ucount + i);
+                    const bool seg_first = (i == 0 || c.kb == 0), seg_last = (i == nun - 1 || c.kb == kba - 1);
+                    if (seg_first) kb_first = c.kb;
+                    if ((i & 1) == grp) {
+                        convert_unit(g, true);
+                        publish(g);
+                    }
                     if (seg_last) {
+                        // (both groups: the accumulator barrier completes only after every unit of the segment has been converted,
+                        //  published and multiplied, whichever group owned it)
                         // T[p][tap] of the finished segment: TMEM -> Tt[tap][p] -> shift-add over the taps -> qslots
                         mbar_wait(smem_u32(&s_acc), (acount + seg) & 1u);
                         tc_fence_after();
@@ -439,14 +470,14 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
                             Tt[(half * 8 + t) * STC_TT_PITCH + q * 32 + lane] = (__uint_as_float(v0[t]) + __uint_as_float(v1[t])) + __uint_as_float(v2[t]);
                         tc_fence_before();
                         asm volatile("bar.sync 1, %0;" ::"n"(STC_CT) : "memory");
-                        float* dst = Q.qslots + ((size_t)(smp * NPT + pt) * kba + kb_first) * NPOS;
+                        float* dst = Q.qslots + ((size_t)(c.smp * NPT + c.pt) * kba + kb_first) * NPOS;
                         for (int o = ct; o < NPOS; o += STC_CT) {
                             const int oy = o / OS, ox = o - oy * OS;
                             float acc = 0.f;
 #pragma unroll
                             for (int tap = 0; tap < 16; ++tap) {
                                 const int iy = oy + (tap >> 2) - 2, ix = ox + (tap & 3) - 2;
-                                const int p = iy * FS + ix - pt * 128;
+                                const int p = iy * FS + ix - c.pt * 128;
                                 if (iy >= 0 && iy < FS && ix >= 0 && ix < FS && p >= 0 && p < 128) acc += Tt[tap * STC_TT_PITCH + p];
                             }
                             __stcg(dst + o, acc);
@@ -454,6 +485,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
                         asm volatile("bar.sync 1, %0;" ::"n"(STC_CT) : "memory");
                         ++seg;
                     }
+                    stage_next(g); app_next(c);
                 }
             }
         }
@@ -473,53 +505,54 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
         if (nun > 0) {
             const int chunk0 = t_lo / per_chunk;
             if (warp == 0) {
-                for (int i = pf_adj; i < nun; ++i) {
-                    utr_i = i;
-                    produce_adj_idx(ucount + i, i);
-                }
-                if (xpf) {          // an apply sweep always follows an adjoint sweep
-                    const int npf = min(NS, a_hi - a_lo);
-                    for (int i = 0; i < npf; ++i) produce_apply_idx(ucount + (uint32_t)nun + i, i);
-                }
+                produce_adj_run(ucount + (uint32_t)pf_adj, pf_adj, nun, true);
+                if (xpf) produce_apply_run(ucount + (uint32_t)nun, 0, min(NS, a_hi - a_lo));   // an apply sweep always follows an adjoint sweep
             } else if (warp == 1 || warp >= 10) {
                 uint32_t touched = 0;
                 int cl = 0, left = (chunk0 + 1) * per_chunk - t_lo;      // units left in the current chunk
-                const uint32_t ns_m = (uint32_t)NS, base_al = base_u32;
-                uint32_t s = ucount % ns_m;
+                Stage g = stage_of(ucount);
                 for (int i = 0; i < nun; ++i) {
                     utr_i = i;
-                    issue(ucount + i, tmem + (uint32_t)(STC_ACC_COL + cl * 48), base_al + s * STC_STAGE_BYTES + STC_A_BYTES,
+                    issue(g, tmem + (uint32_t)(STC_ACC_COL + cl * 48), base_u32 + g.s * STC_STAGE_BYTES + STC_A_BYTES,
                           ((touched >> cl) & 1u) == 0u);
                     touched |= 1u << cl;
                     if (--left == 0) { ++cl; left = per_chunk; }
-                    if (++s == ns_m) s = 0;
+                    stage_next(g);
                 }
                 tc_commit_elect(smem_u32(&s_acc));
             } else {
-                const int tap = ct >> 4, kk0 = (ct & 15) * 2;          // this thread's two R^T elements: (tap, kk0), (tap, kk0 + 1)
+                const int cg = ct & 127;                                 // thread index inside the group
+                const int tap = cg >> 3, kk0 = (cg & 7) * 4;             // this thread's four R^T elements: (tap, kk0 .. kk0 + 3)
                 const int dy = tap >> 2, dx = tap & 3;
-                const uint32_t boff = sw128(tap, kk0);
+                const uint32_t boff = sw128(tap, kk0);                   // (kk0 is a multiple of 4: one 16-byte chunk of the swizzled row)
+                Stage g = stage_of(ucount);
+                AdjPos c = adj_pos(t_lo);
+                int j = 0, jsmp = -1;
                 for (int i = 0; i < nun; ++i) {
-                    const int u = t_lo + i;
-                    const int chunk = u / per_chunk, r = u - chunk * per_chunk, smp = r / KBT, kb = r - smp * KBT;
-                    int j = 0;
-                    for (int jj = 1; jj < ns; ++jj) j = (s_state[jj] == smp) ? jj : j;
-                    utr_i = i;
-                    if (ct == 0) UTR(8);
-                    float rv[2];
+                    if ((i & 1) == grp) {
+                        utr_i = i;
+                        if (ct == 0) UTR(8);
+                        if (c.smp != jsmp) {                           // state slot of the sample
+                            j = 0;
+                            for (int jj = 1; jj < ns; ++jj) j = (s_state[jj] == c.smp) ? jj : j;
+                            jsmp = c.smp;
+                        }
+                        float rv[4];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int px = kb * 32 + kk0 + h;
-                        const int iy = px / FS, ix = px - iy * FS;
-                        const int oy = iy - dy + 2, ox = ix - dx + 2;
-                        rv[h] = (px < NPX && oy >= 0 && oy < OS && ox >= 0 && ox < OS) ? sT[j * NPOS + oy * OS + ox] : 0.f;
+                        for (int h = 0; h < 4; ++h) {
+                            const int px = c.kb * 32 + kk0 + h;
+                            const int iy = px / FS, ix = px - iy * FS;
+                            const int oy = iy - dy + 2, ox = ix - dx + 2;
+                            rv[h] = (px < NPX && oy >= 0 && oy < OS && ox >= 0 && ox < OS) ? sT[j * NPOS + oy * OS + ox] : 0.f;
+                        }
+                        // (the B area of the stage is free: the tfree wait inside convert_unit covers the MMAs of unit ug - NS, NS >= NT)
+                        uint8_t* sb = convert_unit(g, false);
+                        *reinterpret_cast<float4*>(sb + STC_A_BYTES + boff) = make_float4(rv[0], rv[1], rv[2], rv[3]);
+                        *reinterpret_cast<float4*>(sb + STC_A_BYTES + 2048 + boff) = make_float4(lo_trunc(rv[0]), lo_trunc(rv[1]), lo_trunc(rv[2]), lo_trunc(rv[3]));
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        publish(g);
                     }
-                    // (the B area of the stage is free: the tfree wait inside convert_a covers the MMAs of unit ug - NS, NS >= NT)
-                    uint8_t* sb = convert_a(ucount + i, false);
-                    *reinterpret_cast<float2*>(sb + STC_A_BYTES + boff) = make_float2(rv[0], rv[1]);
-                    *reinterpret_cast<float2*>(sb + STC_A_BYTES + 2048 + boff) = make_float2(lo_trunc(rv[0]), lo_trunc(rv[1]));
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    convert_done(ucount + i);
+                    stage_next(g); adj_next(c);
                 }
                 mbar_wait(smem_u32(&s_acc), acount & 1u);
                 tc_fence_after();
