@@ -26,6 +26,7 @@ per-sequence boxes / times (pytracking_b200/shard.py) from which the aggregate F
 are computed (pytracking/analysis/extract_results.py:29-39).
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -290,6 +291,7 @@ def run_b200(args, rank, world, local_rank):
     launches0 = _lib.lib().b200trk_launch_count()
     flush.fill_(1.0)                                                    # L2 flush: 256 MB written right before the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gc.collect(); gc.disable()                                          # no collector pauses inside the timed regions (re-enabled below)
     torch.cuda.synchronize(); barrier()
     e0.record()
     for i in range(K):
@@ -314,6 +316,7 @@ def run_b200(args, rank, world, local_rank):
         per_frame.append(time.perf_counter() - ts)
     torch.cuda.synchronize()
     host_ms = (time.perf_counter() - t0) * 1e3
+    gc.enable()
     barrier()
     clocks = sampler.finish() if sampler else None
 

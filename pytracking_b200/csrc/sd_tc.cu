@@ -76,6 +76,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
                    "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
+// non-blocking phase test (acquire): true once the phase with the given parity has completed
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ float lo_trunc(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 // byte offset of element (row, k) inside a K-major SWIZZLE_128B tile of 128-byte rows (tile base 1024-byte aligned)
 __device__ __forceinline__ uint32_t sw128(int row, int k) {
@@ -319,10 +326,12 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
     // reads, tensor-memory stores and the publish step is latency, not throughput, so two independent chains double the unit rate
     // (profiles/r02o_sd_tc_units.txt).  Thread = operand row: wait for the tile and for the tensor-memory stage, then 2 x (16 fp32 of
     // the row -> hi (raw: the datapath truncates) and lo -> tcgen05.st).  Returns the shared-memory stage (for the adjoint sweep's B tile).
-    auto convert_unit = [&](const Stage& g, bool transposed) -> uint8_t* {
-        mbar_wait(smem_u32(&s_full[g.s]), g.sp);
+    // have_full / have_tfree: the group already saw the two barriers complete (non-blocking tests issued one unit ahead, see
+    // `lookahead`), so the ~2 x 170-cycle blocking waits drop out of the chain whenever the pipeline runs ahead of the converters.
+    auto convert_unit = [&](const Stage& g, bool transposed, bool have_full, bool have_tfree) -> uint8_t* {
+        if (!have_full) mbar_wait(smem_u32(&s_full[g.s]), g.sp);
         if (ct == 0) UTR(2);
-        mbar_wait(smem_u32(&s_tfree[g.t]), g.tp ^ 1u);
+        if (!have_tfree) mbar_wait(smem_u32(&s_tfree[g.t]), g.tp ^ 1u);
         tc_fence_after();
         if (ct == 0) UTR(3);
         uint8_t* sb = base + (size_t)g.s * STC_STAGE_BYTES;
@@ -330,33 +339,41 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
         const int row = q * 32 + lane;
         const uint8_t* arow = sb + row * 128;
         const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + g.t * 64u;
+        // all 32 elements of the row first (the tensor-memory stores below are ordered asm statements: loads issued after them would
+        // wait for them), then hi / lo of each half row
+        float x[32];
+        if (!transposed) {
+            // tile = [128 rows][32 k] with the 128-byte swizzle: this thread's row
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 v = *reinterpret_cast<const float4*>(arow + ((j ^ (row & 7)) << 4));
+                x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+            }
+        } else {
+            // tile = [32 k][128 rows] linear (512-byte lines): the lanes of a warp read 32 consecutive words of one line
+            const float* col = reinterpret_cast<const float*>(sb) + row;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = col[j * 128];
+        }
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
             uint32_t hi[16], lo[16];
-            if (!transposed) {
-                // tile = [128 rows][32 k] with the 128-byte swizzle: this thread's row, 16 consecutive k
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 x = *reinterpret_cast<const float4*>(arow + ((((hh * 4 + j) ^ (row & 7))) << 4));
-                    hi[4 * j] = __float_as_uint(x.x); hi[4 * j + 1] = __float_as_uint(x.y); hi[4 * j + 2] = __float_as_uint(x.z); hi[4 * j + 3] = __float_as_uint(x.w);
-                    lo[4 * j] = __float_as_uint(lo_trunc(x.x)); lo[4 * j + 1] = __float_as_uint(lo_trunc(x.y));
-                    lo[4 * j + 2] = __float_as_uint(lo_trunc(x.z)); lo[4 * j + 3] = __float_as_uint(lo_trunc(x.w));
-                }
-            } else {
-                // tile = [32 k][128 rows] linear (512-byte lines): the lanes of a warp read 32 consecutive words of one line
-                const float* col = reinterpret_cast<const float*>(sb) + (hh * 16) * 128 + row;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float x = col[j * 128];
-                    hi[j] = __float_as_uint(x);
-                    lo[j] = __float_as_uint(lo_trunc(x));
-                }
-            }
+            for (int j = 0; j < 16; ++j) { hi[j] = __float_as_uint(x[hh * 16 + j]); lo[j] = __float_as_uint(lo_trunc(x[hh * 16 + j])); }
             tmem_st16(ta + (uint32_t)(hh * 16), hi);
             tmem_st16(ta + 32u + (uint32_t)(hh * 16), lo);
         }
         if (ct == 0) UTR(9);
         return sb;
+    };
+    // barrier tests for the group's NEXT unit, issued between the tensor-memory stores of the current unit and their retirement
+    // (A parity test is only meaningful while the barrier is at most one phase behind.  s_tfree: the previous user of the stage is
+    //  this group's own unit i - 2, and the MMAs retire in order.  s_full: the previous user of the stage is unit i + 2 - NS, this
+    //  group's own (already converted) unit when NS is even; with an odd stage count it belongs to the other group and its tile is
+    //  not known to have landed, so the test is not used.)
+    auto lookahead = [&](const Stage& g2, bool& have_full, bool& have_tfree) {
+        have_full = ((NS & 1) == 0) && mbar_test(smem_u32(&s_full[g2.s]), g2.sp);
+        have_tfree = mbar_test(smem_u32(&s_tfree[g2.t]), g2.tp ^ 1u);
     };
     // converter, last step: publish the unit (shared-memory stage free again, tensor-memory stage ready); one arrival per warp of the group
     auto publish = [&](const Stage& g) {
@@ -449,11 +466,14 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
                 int seg = 0, kb_first = 0;
                 Stage g = stage_of(ucount);
                 AppPos c = app_pos(a_lo);
+                bool have_full = false, have_tfree = false;
                 for (int i = 0; i < nun; ++i) {
                     const bool seg_first = (i == 0 || c.kb == 0), seg_last = (i == nun - 1 || c.kb == kba - 1);
                     if (seg_first) kb_first = c.kb;
                     if ((i & 1) == grp) {
-                        convert_unit(g, true);
+                        convert_unit(g, true, have_full, have_tfree);
+                        have_full = have_tfree = false;
+                        if (i + 2 < nun) { Stage g2 = g; stage_next(g2); stage_next(g2); lookahead(g2, have_full, have_tfree); }
                         publish(g);
                     }
                     if (seg_last) {
@@ -527,32 +547,41 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
                 const uint32_t boff = sw128(tap, kk0);                   // (kk0 is a multiple of 4: one 16-byte chunk of the swizzled row)
                 Stage g = stage_of(ucount);
                 AdjPos c = adj_pos(t_lo);
+                if (grp == 1) { stage_next(g); adj_next(c); }           // group 1 owns the odd units
                 int j = 0, jsmp = -1;
-                for (int i = 0; i < nun; ++i) {
-                    if ((i & 1) == grp) {
-                        utr_i = i;
-                        if (ct == 0) UTR(8);
-                        if (c.smp != jsmp) {                           // state slot of the sample
-                            j = 0;
-                            for (int jj = 1; jj < ns; ++jj) j = (s_state[jj] == c.smp) ? jj : j;
-                            jsmp = c.smp;
-                        }
-                        float rv[4];
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            const int px = c.kb * 32 + kk0 + h;
-                            const int iy = px / FS, ix = px - iy * FS;
-                            const int oy = iy - dy + 2, ox = ix - dx + 2;
-                            rv[h] = (px < NPX && oy >= 0 && oy < OS && ox >= 0 && ox < OS) ? sT[j * NPOS + oy * OS + ox] : 0.f;
-                        }
-                        // (the B area of the stage is free: the tfree wait inside convert_unit covers the MMAs of unit ug - NS, NS >= NT)
-                        uint8_t* sb = convert_unit(g, false);
-                        *reinterpret_cast<float4*>(sb + STC_A_BYTES + boff) = make_float4(rv[0], rv[1], rv[2], rv[3]);
-                        *reinterpret_cast<float4*>(sb + STC_A_BYTES + 2048 + boff) = make_float4(lo_trunc(rv[0]), lo_trunc(rv[1]), lo_trunc(rv[2]), lo_trunc(rv[3]));
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        publish(g);
+                float rv[4];
+                // this thread's four elements of R^T for the unit at `cc` (gathered from the mapped residual of the unit's sample)
+                auto gather = [&](const AdjPos& cc) {
+                    if (cc.smp != jsmp) {                               // state slot of the sample
+                        j = 0;
+                        for (int jj = 1; jj < ns; ++jj) j = (s_state[jj] == cc.smp) ? jj : j;
+                        jsmp = cc.smp;
                     }
-                    stage_next(g); adj_next(c);
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const int px = cc.kb * 32 + kk0 + h;
+                        const int iy = px / FS, ix = px - iy * FS;
+                        const int oy = iy - dy + 2, ox = ix - dx + 2;
+                        rv[h] = (px < NPX && oy >= 0 && oy < OS && ox >= 0 && ox < OS) ? sT[j * NPOS + oy * OS + ox] : 0.f;
+                    }
+                };
+                bool have_full = false, have_tfree = false;
+                if (grp < nun) gather(c);
+                for (int i = grp; i < nun; i += 2) {
+                    utr_i = i;
+                    if (ct == 0) UTR(8);
+                    // (the B area of the stage is free: the tfree wait / test covers the MMAs of unit ug - NS, NS >= NT)
+                    uint8_t* sb = convert_unit(g, false, have_full, have_tfree);
+                    *reinterpret_cast<float4*>(sb + STC_A_BYTES + boff) = make_float4(rv[0], rv[1], rv[2], rv[3]);
+                    *reinterpret_cast<float4*>(sb + STC_A_BYTES + 2048 + boff) = make_float4(lo_trunc(rv[0]), lo_trunc(rv[1]), lo_trunc(rv[2]), lo_trunc(rv[3]));
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    // while the tensor-memory stores of this unit retire: R^T elements and barrier tests of the group's next unit
+                    Stage g2 = g; stage_next(g2); stage_next(g2);
+                    AdjPos c2 = c; adj_next(c2); adj_next(c2);
+                    have_full = have_tfree = false;
+                    if (i + 2 < nun) { gather(c2); lookahead(g2, have_full, have_tfree); }
+                    publish(g);
+                    g = g2; c = c2;
                 }
                 mbar_wait(smem_u32(&s_acc), acount & 1u);
                 tc_fence_after();
