@@ -50,6 +50,11 @@ struct TcParams {
                      //    distributed shared memory instead of an L2 workspace + arrival counter
     int prefetch_b;  // 1: the weight tiles of the first pipeline stages are requested before griddepcontrol.wait (they do not depend on the previous layer)
     int acc2;        // 1: the two small products (A_lo*B_hi, A_hi*B_lo) accumulate in a TMEM accumulator of their own (columns BN..2BN)
+    int a_tmem;      // 1: the A operand goes through TENSOR memory: the converter warps (thread = tile row) write hi | lo of each k-block into a
+                     //    64-column TMEM stage behind the accumulators and the MMAs take A from there; shared memory then holds only the raw A
+                     //    tile and B_hi | B_lo (per k-block 80 KB of shared-memory traffic instead of 144 KB at BN = 64)
+    int tmem_cols;   // TMEM allocation (power of two)
+    uint32_t stage_bytes;
     uint32_t a_bytes, b_bytes;
 };
 
@@ -102,7 +107,9 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
     const uint32_t smem_base = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
     const uint32_t a_tile = (uint32_t)TC_BM * 128u;                     // 16 KB slot regardless of the box size
     const uint32_t b_tile = (uint32_t)P.BN * 128u;
-    const uint32_t stage_bytes = 2u * a_tile + 2u * b_tile;
+    const uint32_t stage_bytes = P.stage_bytes;
+    const uint32_t b_off = P.a_tmem ? a_tile : 2u * a_tile;            // B_hi | B_lo behind the A slot(s)
+    const uint32_t a_col0 = (uint32_t)(P.acc2 ? 2 * P.BN : P.BN);      // first TMEM column of the A stages (a_tmem)
 
     // tile coordinates
     const int tiles_per_sample = P.tiles_w * P.tiles_h;
@@ -125,7 +132,7 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"((uint32_t)(P.acc2 ? 2 * P.BN : P.BN)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"((uint32_t)P.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
         for (int it = 0; it < npre; ++it) {
             const uint32_t full = smem_u32(&s_full[it]);
             mbar_expect_tx_elect(full, P.a_bytes + P.b_bytes);
-            tma_load_2d_elect(smem_base + (uint32_t)it * stage_bytes + 2u * a_tile, &P.b_map, full, tap * P.Cin + cb * TC_KB, n0);
+            tma_load_2d_elect(smem_base + (uint32_t)it * stage_bytes + b_off, &P.b_map, full, tap * P.Cin + cb * TC_KB, n0);
             if (++cb == P.cblks) { cb = 0; ++tap; }
         }
     }
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
                 if (trace && it < 16 && lane == 0) trace[it * 8 + 0] = gtimer();          // slot free
                 const uint32_t sa = smem_base + (uint32_t)st * stage_bytes;
                 tma_load_4d_elect(sa, &P.a_map, full, cb * TC_KB, x0 + kw, y0 + kh, s);                 // raw -> A_hi slot
-                if (it >= npre) tma_load_2d_elect(sa + 2u * a_tile, &P.b_map, full, tap * P.Cin + cb * TC_KB, n0);   // raw -> B_hi slot
+                if (it >= npre) tma_load_2d_elect(sa + b_off, &P.b_map, full, tap * P.Cin + cb * TC_KB, n0);   // raw -> B_hi slot
                 if (trace && it < 16 && lane == 0) trace[it * 8 + 1] = gtimer();          // loads issued
                 if (++cb == P.cblks) { cb = 0; ++tap; if (++kw == P.ksz) { kw = 0; ++kh; } }
                 if (++st == P.stages) { st = 0; ph ^= 1u; }
@@ -192,18 +199,30 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
                 if (dbg && it == 0 && lane == 0) dbg[3] = gtimer();                // first operands landed and split
                 if (trace && it < 16 && lane == 0) trace[it * 8 + 4] = gtimer();          // MMA warp sees the stage
                 const uint32_t d_ah = make_smem_desc_lo(smem_base + (uint32_t)st * stage_bytes), d_al = d_ah + (a_tile >> 4);
-                const uint32_t d_bh = d_al + (a_tile >> 4), d_bl = d_bh + (b_tile >> 4);
+                const uint32_t d_bh = make_smem_desc_lo(smem_base + (uint32_t)st * stage_bytes + b_off), d_bl = d_bh + (b_tile >> 4);
+                const uint32_t a_tm = tmem_base + a_col0 + (uint32_t)st * 64u;      // hi columns 0..31, lo columns 32..63 (a_tmem)
+                // The fp32 accumulate of the tensor pipe truncates; its error grows with the number of dependent additions into
+                // one accumulator and with the accumulator's magnitude. The two correction products are ~2^-11 of the main one:
+                // in an accumulator of their own their rounding is negligible, and the main accumulator takes a third of the adds.
+                const uint32_t acc_lo = tmem_base + (P.acc2 ? (uint32_t)P.BN : 0u);
+                if (P.a_tmem) {
 #pragma unroll
-                for (int k = 0; k < TC_KB / 8; ++k) {
-                    const uint32_t adv = (uint32_t)(k * 32 >> 4);      // 8 tf32 = 32 bytes per UMMA K step
-                    // The fp32 accumulate of the tensor pipe truncates; its error grows with the number of dependent additions into
-                    // one accumulator and with the accumulator's magnitude. The two correction products are ~2^-11 of the main one:
-                    // in an accumulator of their own their rounding is negligible, and the main accumulator takes a third of the adds.
-                    const uint32_t acc_lo = tmem_base + (P.acc2 ? (uint32_t)P.BN : 0u);
-                    const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-                    tc_mma_tf32_lo(acc_lo, d_al + adv, d_bh + adv, idesc, first);
-                    tc_mma_tf32_lo(acc_lo, d_ah + adv, d_bl + adv, idesc, 1u);
-                    tc_mma_tf32_lo(tmem_base, d_ah + adv, d_bh + adv, idesc, P.acc2 ? first : 1u);
+                    for (int k = 0; k < TC_KB / 8; ++k) {
+                        const uint32_t adv = (uint32_t)(k * 32 >> 4), kc = (uint32_t)(k * 8);
+                        const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+                        tc_mma_tf32_ts_lo(acc_lo, a_tm + 32u + kc, d_bh + adv, idesc, first);
+                        tc_mma_tf32_ts_lo(acc_lo, a_tm + kc, d_bl + adv, idesc, 1u);
+                        tc_mma_tf32_ts_lo(tmem_base, a_tm + kc, d_bh + adv, idesc, P.acc2 ? first : 1u);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < TC_KB / 8; ++k) {
+                        const uint32_t adv = (uint32_t)(k * 32 >> 4);      // 8 tf32 = 32 bytes per UMMA K step
+                        const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+                        tc_mma_tf32_lo(acc_lo, d_al + adv, d_bh + adv, idesc, first);
+                        tc_mma_tf32_lo(acc_lo, d_ah + adv, d_bl + adv, idesc, 1u);
+                        tc_mma_tf32_lo(tmem_base, d_ah + adv, d_bh + adv, idesc, P.acc2 ? first : 1u);
+                    }
                 }
                 tc_commit_elect(smem_u32(&s_empty[st]));
                 if (trace && it < 16 && lane == 0) trace[it * 8 + 5] = gtimer();          // MMAs + commit issued
@@ -238,11 +257,36 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
                 if (trace && it < 16 && et == 0) trace[it * 8 + 2] = gtimer();   // tile landed
                 float4* a_hi = reinterpret_cast<float4*>(sbase + (size_t)st * stage_bytes);
                 float4* a_lo = a_hi + a_v4;
-                float4* b_hi = a_lo + a_v4;
+                float4* b_hi = reinterpret_cast<float4*>(sbase + (size_t)st * stage_bytes + b_off);
                 float4* b_lo = b_hi + b_v4;
+                const int nb = b_v4 / CT;                          // float4 of B per thread: BN * 8 / CT
+                if (P.a_tmem) {
+                    // A through tensor memory (CW = 8): thread = tile row q*32 + lane, warps w and w + 4 take the two 16-element halves of
+                    // the 32-element k-block; the 128-byte swizzle of the landed tile is undone in the address of each 16-byte chunk.
+                    const int row = q * 32 + lane;
+                    const uint8_t* arow = reinterpret_cast<const uint8_t*>(a_hi) + row * 128;
+                    float4 xr[4], xb[NA];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) xr[j] = *reinterpret_cast<const float4*>(arow + (((chalf * 4 + j) ^ (row & 7)) << 4));
+#pragma unroll
+                    for (int j = 0; j < NA; ++j) xb[j] = (j < nb) ? b_hi[et + CT * j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 l = tc_lo_trunc(xr[j]);
+                        hi[4 * j] = __float_as_uint(xr[j].x); hi[4 * j + 1] = __float_as_uint(xr[j].y); hi[4 * j + 2] = __float_as_uint(xr[j].z); hi[4 * j + 3] = __float_as_uint(xr[j].w);
+                        lo[4 * j] = __float_as_uint(l.x); lo[4 * j + 1] = __float_as_uint(l.y); lo[4 * j + 2] = __float_as_uint(l.z); lo[4 * j + 3] = __float_as_uint(l.w);
+                    }
+                    const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a_col0 + (uint32_t)st * 64u + (uint32_t)(chalf * 16);
+                    tmem_st16(ta, hi);
+                    tmem_st16(ta + 32u, lo);
+#pragma unroll
+                    for (int j = 0; j < NA; ++j) if (j < nb) b_lo[et + CT * j] = tc_lo_trunc(xb[j]);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                } else {
                 // all loads of the stage are issued before the first store (the compiler must not serialise them
                 // behind the shared-memory stores): 8 float4 of A and up to 8 of B per thread
-                const int nb = b_v4 / CT;                          // float4 of B per thread: BN * 8 / CT
                 float4 xa[NA], xb[NA];
 #pragma unroll
                 for (int j = 0; j < NA; ++j) xa[j] = a_hi[et + CT * j];
@@ -271,6 +315,7 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
                             b_hi[et + CT * j] = h; b_lo[et + CT * j] = l;
                         }
                     }
+                }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to tcgen05.mma
                 __syncwarp();
@@ -463,7 +508,7 @@ __global__ void __launch_bounds__(64 + 32 * CW, 1) conv_tc_kernel(const __grid_c
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(P.acc2 ? 2 * P.BN : P.BN)) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols) : "memory");
     }
 }
 
@@ -607,10 +652,16 @@ static int tc_configure(b200trk_net* net, const Op& op, TcConv* tc, int S) {
     if (op.Cout % BN != 0 || (BN != 64 && BN != 128)) BN = 64;
     P.BN = BN;
     P.b_bytes = (uint32_t)BN * 128u;
-    const uint32_t stage_bytes = 2u * TC_BM * 128u + 2u * P.b_bytes;
+    P.acc2 = env_int("B200TRK_TC_ACC2", 1);
+    P.split_mode = env_int("B200TRK_TC_SPLIT_MODE", 2);
+    P.a_tmem = (env_int("B200TRK_TC_ATMEM", 1) && env_int("B200TRK_TC_CW", 8) != 4 && P.split_mode == 2) ? 1 : 0;
+    const uint32_t stage_bytes = (P.a_tmem ? 1u : 2u) * TC_BM * 128u + 2u * P.b_bytes;
+    P.stage_bytes = stage_bytes;
     const int occ = env_int("B200TRK_TC_OCC", 1);                 // CTAs per SM the shared-memory footprint is sized for
     int stages = (int)(((occ >= 2 ? 98u : 200u) * 1024u) / stage_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    const int acc_cols = P.acc2 ? 2 * BN : BN;
+    if (P.a_tmem && stages > (512 - acc_cols) / 64) stages = (512 - acc_cols) / 64;      // one 64-column TMEM stage per shared-memory stage
     if (stages < 2) stages = 2;
     if (stages > P.total_kb) stages = P.total_kb < 2 ? 2 : P.total_kb;
     P.stages = stages;
@@ -631,8 +682,7 @@ static int tc_configure(b200trk_net* net, const Op& op, TcConv* tc, int S) {
     P.splits = (P.total_kb + P.kb_per_split - 1) / P.kb_per_split;
     B200_REQUIRE(ctas <= 512 || P.splits == 1, "tc_conv: counter array too small for %d tiles", ctas);
     P.ws = op.side ? net->splitk_ws2 : net->splitk_ws;
-    P.split_mode = env_int("B200TRK_TC_SPLIT_MODE", 2);
-    P.acc2 = env_int("B200TRK_TC_ACC2", 1);
+    { int need = acc_cols + (P.a_tmem ? P.stages * 64 : 0), cols = 32; while (cols < need) cols <<= 1; P.tmem_cols = cols; }
     P.cluster_red = (env_int("B200TRK_TC_CLUSTER", 1) && P.splits > 1 && P.splits <= 8) ? 1 : 0;
     P.prefetch_b = env_int("B200TRK_TC_PREFETCH_B", 1);
     const size_t Kt = (size_t)op.k * op.k * op.Cin;
@@ -646,8 +696,7 @@ int tc_conv_launch(b200trk_net* net, const Op& op, int S, cudaStream_t st) {
     if (tc->S_built != S)
         if (int e = tc_configure(net, op, tc, S)) return e;
     const TcParams& P = tc->P;
-    const uint32_t stage_bytes = 2u * TC_BM * 128u + 2u * P.b_bytes;
-    size_t smem = (size_t)P.stages * stage_bytes + 1024;
+    size_t smem = (size_t)P.stages * P.stage_bytes + 1024;
     if (smem < 72 * 1024) smem = 72 * 1024;       // the epilogue stages accumulator rows in the (idle) pipeline buffers: up to 128 x 132 floats
     static const int cw = env_int("B200TRK_TC_CW", 8) == 4 ? 4 : 8;
     static bool attr = false;
