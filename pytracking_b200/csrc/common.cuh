@@ -99,11 +99,12 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
     __syncthreads();
     epoch += 1;
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
+        // Arrival = one releasing reduction (fire and forget: no fence in front of it and no round trip of an atomic's return value
+        // before the polling starts); the bar.sync above orders the other threads' writes before it (cumulativity of the release),
+        // the acquiring poll + the bar.sync below publish the other CTAs' writes to every thread of this CTA.
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
         const unsigned target = epoch * gridDim.x;
         while (ld_acquire_u32(counter) < target) { }
-        __threadfence();
     }
     __syncthreads();
 }
