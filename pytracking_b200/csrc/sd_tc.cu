@@ -361,6 +361,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
     //  group's own (already converted) unit when NS is even; with an odd stage count it belongs to the other group and its tile is
     //  not known to have landed, so the test is not used.)
     auto lookahead = [&](const Stage& g2, bool& have_full, bool& have_tfree) {
+        if (P.dbg_mode == 7) { have_full = have_tfree = false; return; }       // timing experiment: blocking waits only
         have_full = ((NS & 1) == 0) && mbar_test(smem_u32(&s_full[g2.s]), g2.sp);
         have_tfree = mbar_test(smem_u32(&s_tfree[g2.t]), g2.tp ^ 1u);
     };
