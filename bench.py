@@ -60,8 +60,8 @@ CONFIG = {"workload": "DiMP-50 single-GPU, synthetic 288x288 crops, 10 SD iters/
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the same kernels at the same
-# sizes (profiles/r02k_ncu_summary_all_kernels.txt, profiles/r02k_ncu_summary_conv_tc.txt; tools/ncu_round.sh) -- not measured in this run
-NCU_TRAFFIC = {"sd_tc": 36240000 + 201000, "conv_chain": 149690000, "apply_filter": 726000}
+# sizes (profiles/r02x_ncu_summary_all_kernels.txt, profiles/r02x_ncu_summary_conv_tc.txt; tools/ncu_round.sh) -- not measured in this run
+NCU_TRAFFIC = {"sd_tc": 36251000 + 394000, "conv_chain": 149774000, "apply_filter": 726000}
 
 
 def parse():
@@ -384,12 +384,12 @@ def run_b200(args, rank, world, local_rank):
                 "ms_per_frame_median": float(np.median(per_frame) * 1e3)},
         "gpu_launches": int(launches),
         "roofline": roof[0], "rooflines": roof, "peak_source": peaks["source"],
-        "traffic_source": "ncu --set full captures committed under profiles/r02k_ncu_summary_*.txt (same kernels, same sizes, separate run)",
+        "traffic_source": "ncu --set full captures committed under profiles/r02x_ncu_summary_*.txt (same kernels, same sizes, separate run)",
         "tracking": {"mean_iou_vs_synthetic_ground_truth": float(np.mean(ious)), "sequences": len(ious), "frames_per_sequence": len(boxes),
                      "gather": "one all_gather of [frames,6] per sequence at the end (pytracking_b200/shard.py)"},
         "clocks": clocks,
     }
-    if not args.no_baselines:
+    if not args.no_baselines and world == 1:            # the CPU / stock-CUDA baselines are N = 1 lines
         out.update(baselines(frames, bb, W))
     print(json.dumps(out))
 

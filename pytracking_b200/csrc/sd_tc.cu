@@ -51,6 +51,7 @@ constexpr int STC_A_BYTES = 16384;          // 128 rows x 128 B
 constexpr int STC_STAGE_BYTES = 20480;      // A raw | B_hi (2 KB) | B_lo (2 KB)
 constexpr int STC_MAXCH = 4;                // 128-channel chunks (C <= 512)
 constexpr int STC_TT_PITCH = 132;
+constexpr int STC_MAXG = 160;                // CTAs (= SMs) the partition tables are sized for
 constexpr int STC_QL_MAX = 64;              // apply segments of one sample (<= pixel tiles x channel blocks)
 
 struct SdTcParams {
@@ -103,6 +104,8 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
     __shared__ int s_owned[16];
     __shared__ float s_sw[16];
     __shared__ int s_ns;
+    __shared__ int s_tlo[STC_MAXG + 1];   // adjoint-range starts of all CTAs (static for the call: the per-iteration gradient slice
+    __shared__ int s_bf[STC_MAXCH], s_bl[STC_MAXCH];   // reduce must not redo 64-bit divisions), first / last contributor CTA of every chunk
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x, b = blockIdx.x;
@@ -163,6 +166,12 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&Q.map_a) : "memory");
     }
     for (int e = sl_lo + tid; e < sl_hi; e += NTH) wsl[e - sl_lo] = reinterpret_cast<const float4*>(P.w_in)[e];
+    for (int k = tid; k <= G; k += NTH) s_tlo[k] = part_lo(UT, G, k);
+    if (tid < nchk) {
+        const int per_chunk = n * KBT;
+        s_bf[tid] = part_owner(UT, G, tid * per_chunk);
+        s_bl[tid] = part_owner(UT, G, (tid + 1) * per_chunk - 1);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -708,10 +717,10 @@ __global__ void __launch_bounds__(STC_THREADS, 1) sd_tc_kernel(const __grid_cons
             const int per_chunk = n * KBT;
             for (int e = sl_lo + warp; e < sl_hi; e += NTH / 32) {
                 const int chunk = e >> 9, within = e & 511;                   // 128 channels x 16 taps = 512 float4 per chunk
-                const int bf = part_owner(UT, G, chunk * per_chunk), bl = part_owner(UT, G, (chunk + 1) * per_chunk - 1);
+                const int bf = s_bf[chunk], bl = s_bl[chunk];
                 float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int bb = bf + lane; bb <= bl; bb += 32) {
-                    const int lo = part_lo(UT, G, bb), hi = part_lo(UT, G, bb + 1);
+                    const int lo = s_tlo[bb], hi = s_tlo[bb + 1];
                     if (hi > lo) {
                         const int cl = chunk - lo / per_chunk;
                         const float4 v = __ldcg(reinterpret_cast<const float4*>(Q.gpart) + ((size_t)bb * STC_MAXCH + cl) * 512 + within);
@@ -835,6 +844,7 @@ int launch_sd_tc(const SdParams& P0, cudaStream_t st, int* handled) {
     if (P0.C % 128 != 0 || P0.C / 128 > STC_MAXCH) return 0;
     if ((reinterpret_cast<uintptr_t>(P0.feat) & 15u) != 0) return 0;
     const int G = device_sm_count();
+    if (G > STC_MAXG) return 0;
     const int n = P0.n, C = P0.C, nchk = C / 128, kba = C / 32;
     if (NPT * kba > STC_QL_MAX) return 0;
     const long long UT = (long long)nchk * n * KBT;
@@ -856,7 +866,7 @@ int launch_sd_tc(const SdParams& P0, cudaStream_t st, int* handled) {
     const int slice_max = (C * 4 + G - 1) / G + 1;
     const size_t fixed = 1024 + (size_t)kba * 4096 + 16 * STC_TT_PITCH * 4 + 2 * (size_t)slice_max * 16 +
                          (size_t)smax * 6 * NPOS * 4 + (size_t)smax * (STC_QL_MAX + 1) * 4 + 64;
-    const size_t limit = 227 * 1024 - 2048;                     // static shared memory of the kernel: ~1.5 KB
+    const size_t limit = 227 * 1024 - 3072;                     // static shared memory of the kernel: ~2.3 KB
     if (fixed + (size_t)STC_NT * STC_STAGE_BYTES > limit) return 0;
     int nstg = (int)((limit - fixed) / STC_STAGE_BYTES);
     if (nstg > STC_NS_MAX) nstg = STC_NS_MAX;

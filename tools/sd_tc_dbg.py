@@ -18,6 +18,7 @@ for dbg in (0, 1, 2, 3, 4, 5):
     t = np.array(list(buf), dtype=np.float64)
     b = 8 + 10
     d = [(t[b+k+1]-t[b+k])/1e3 for k in range(8)]
+    print("dbg %d: prologue %.2f |" % (dbg, (t[1]-t[0])/1e3), end=" ")
     print("dbg %d: s0 sweepA %.2f | it1: resid %.2f | sweepT %.2f | barrier1 %.2f | gsum+b1b+FT %.2f | sweepA %.2f | barrier2 %.2f | qsum+h %.2f | barrier3 %.2f" % (dbg, (t[2]-t[1])/1e3, *d), flush=True)
 names = "slot_free tma_issued | conv_at_unit landed tmem_free regs st_retired published | mma_sees mma_committed"
 order = [0, 1, 8, 2, 3, 9, 4, 5, 6, 7]
