@@ -18,6 +18,10 @@ def _dev(t, name):
         raise RuntimeError("b200trk: '%s' must be a CUDA tensor (the engine has no CPU path)" % name)
     if t.dtype != torch.float32:
         raise RuntimeError("b200trk: '%s' must be float32, got %s" % (name, t.dtype))
+    if t.device.index != torch.cuda.current_device():
+        # the library's stream, scratch buffers and SM count belong to the CURRENT device (cudaGetDevice)
+        raise RuntimeError("b200trk: '%s' lives on %s but the current device is cuda:%d; wrap the call in torch.cuda.device(%r)"
+                           % (name, t.device, torch.cuda.current_device(), str(t.device)))
     return t.contiguous()
 
 
