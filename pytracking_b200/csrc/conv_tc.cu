@@ -3,22 +3,26 @@
 //
 //   D[m][n] = sum_k A[m][k] * W[n][k]     m = output pixel, n = output channel, k = (kh, kw, cin)
 //
-// fp32 fidelity on a TF32 datapath: every operand tile is split IN SHARED MEMORY into a (hi, lo) pair of
-// TF32-representable fp32 numbers, x = hi + lo (+ <= 2^-22 |x|), and each K-step issues three MMAs
-// A_lo*B_hi + A_hi*B_lo + A_hi*B_hi into the same fp32 TMEM accumulator ("3xTF32"); the dropped A_lo*B_lo term is
-// O(2^-22) relative. HBM/L2 only ever hold (and move) plain fp32 activations and weights.
+// fp32 fidelity on a TF32 datapath: every operand tile is split into a (hi, lo) pair of TF32-representable fp32 numbers,
+// x = hi + lo (+ <= 2^-22 |x|), and each K-step issues three MMAs A_lo*B_hi + A_hi*B_lo (into one fp32 TMEM accumulator) and
+// A_hi*B_hi (into another; summed in the epilogue) ("3xTF32"); the dropped A_lo*B_lo term is O(2^-22) relative. HBM/L2 only ever
+// hold (and move) plain fp32 activations and weights.
 //
 // Tiling: CTA = 128 output pixels (a BW x BH rectangle of one sample, rows ordered (y, x)) x BN output channels.
 // K is walked in 128-byte blocks (32 input channels of one filter tap): one 4-D TMA box {32 ch, BW*stride, BH*stride, 1}
-// (element strides {1, stride, stride, 1}; halo / padding = TMA out-of-bounds zero fill) lands the A tile directly in
-// the canonical K-major SWIZZLE_128B layout that the UMMA shared-memory descriptor expects; a 2-D box {32, BN}
-// does the same for the weights. Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (both run their loops
-// with the whole warp converged, elect.sync inside the instruction wrappers of tc_ptx.cuh), warps 2-9 = operand converters during
-// the main loop (the raw tile is the hi operand: the TF32 datapath truncates; lo = x - trunc(x) is written next to it,
-// fence.proxy.async), then epilogue (tcgen05.ld -> registers -> smem transpose -> bias/residual/ReLU -> coalesced global stores;
-// warps w and w+4 share a TMEM lane quadrant and split the accumulator columns). Small layers use split-K over gridDim.z:
-// partial tiles go to an L2-resident workspace, a per-tile arrival counter releases ALL split CTAs of the tile, and each of them
-// reduces its share of the tile rows in split order (fixed order => bitwise deterministic).
+// (element strides {1, stride, stride, 1}; halo / padding = TMA out-of-bounds zero fill) lands the A tile in the K-major
+// SWIZZLE_128B layout; a 2-D box {32, BN} does the same for the weights. Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator +
+// MMA issuer (both run their loops with the whole warp converged, elect.sync inside the instruction wrappers of tc_ptx.cuh),
+// warps 2-9 = operand converters during the main loop, then epilogue.
+// Operand conversion (default, a_tmem): the raw tile is the hi operand (the TF32 datapath truncates). A: converter thread = tile row,
+// hi | lo of its 16 elements straight into a 64-column TENSOR-MEMORY stage behind the accumulators (tcgen05.st), and the MMAs take A
+// from TMEM; B: lo = x - trunc(x) written next to the raw tile in shared memory (fence.proxy.async). The K loop was bound by
+// shared-memory bandwidth with both operands in shared memory (DESIGN.md sections 4.3 and 8).
+// Epilogue: tcgen05.ld -> registers -> smem transpose -> bias/residual/ReLU -> coalesced global stores; warps w and w+4 share a TMEM
+// lane quadrant and split the accumulator columns. Small layers use split-K over gridDim.z: the <= 8 split CTAs of a tile form a
+// thread-block cluster, stage their partial tiles in their own shared memory and each reduces its share of the tile through
+// distributed shared memory in split order (fixed order => bitwise deterministic); with more than 8 splits (or B200TRK_TC_CLUSTER=0)
+// the partial tiles go to an L2-resident workspace and a per-tile arrival counter releases the split CTAs.
 #include "net.cuh"
 #include "tc_ptx.cuh"
 #include <cuda.h>

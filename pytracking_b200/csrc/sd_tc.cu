@@ -24,15 +24,18 @@
 // `smax`); the replicas evolve identically because all of them read the same partials in the same order; loss / curvature
 // terms are contributed by the sample's owner (the CTA holding its first unit) only.
 //
-// Operand pipeline (per unit): TMA lands the raw 128 x 32 fp32 tile in a shared-memory stage; the converter warps read it back
-// (thread = tile row, conflict-free through the 128-byte swizzle) and write hi (= raw) and lo straight into a TENSOR-MEMORY
-// stage with tcgen05.st; the MMAs take A from TMEM (tcgen05.mma with a TMEM A operand) and only the 16-row B operand from
-// shared memory. The shared-memory stage is free again as soon as it has been read (not when the MMAs retire), so 6 x 20 KB
-// stages cover the L2 latency, and the shared-memory traffic per unit is 16 KB in + 16 KB out instead of ~100 KB.
+// Operand pipeline (per unit): TMA lands the raw 128 x 32 fp32 tile in a shared-memory stage; a converter thread reads its operand row
+// back (conflict-free through the 128-byte swizzle) and writes hi (= raw) and lo straight into a TENSOR-MEMORY stage with tcgen05.st;
+// the MMAs take A from TMEM (tcgen05.mma with a TMEM A operand) and only the 16-row B operand from shared memory. The shared-memory
+// stage is free again as soon as it has been read (not when the MMAs retire), so 6 x 20 KB stages cover the L2 latency, and the
+// shared-memory traffic per unit is 16 KB in + 16 KB out instead of ~100 KB.
 //
-// Warp roles during a sweep: warp 0 = TMA producer, warps 1 / 10 / 11 = MMA issuers (one per product), warps 2-9 = operand
-// converters (lo parts, R^T tiles) and epilogue (TMEM -> registers -> partials). All 384 threads run the element-wise phases
-// between the sweeps. Measured stage times and what bounds the sweeps: DESIGN.md sections 4.1b and 8, profiles/r01j_sd_tc_pipeline.txt.
+// Warp roles during a sweep: warp 0 = TMA producer (it also issues the first units of the NEXT sweep while the CTAs sit in the grid
+// barrier), warps 1 / 10 / 11 = MMA issuers (one per product), warps 2-5 and 6-9 = two converter groups that take ALTERNATE units (the
+// per-unit chain wait -> read -> tcgen05.st -> publish is latency, so two chains in flight double the unit rate) and share the
+// segment epilogues (TMEM -> registers -> partials). All 384 threads run the element-wise phases between the sweeps. Every role walks
+// its units with running counters (no integer division per unit). Measured stage times and what paces the sweeps: DESIGN.md sections
+// 4.1b and 8, profiles/r02{n,o,p}_sd_tc_units.txt (round 1: profiles/r01j_sd_tc_pipeline.txt).
 #include "tc_ptx.cuh"
 #include "sd_common.cuh"
 #include <atomic>
