@@ -164,6 +164,23 @@ int b200trk_atom_gn_joint(float* filter, float* proj, const float* samples, cons
                           int n, int Cin, int Cc, int H, int W, int k, int num_cg_iter, int num_gn_iter, float filter_reg,
                           float projection_reg, int fletcher_reeves, int activation, float act_param, b200trk_stream_t stream);
 
+/* FilterOptim.run(num_iter, new_xf) -- ECO's per-frame filter update in the Fourier domain, ONE feature block per call (the
+ * reference optimises the blocks of its TensorLists independently): pytracking/tracker/eco/optim.py:140-208 (run, A, ip, M1) +
+ * pytracking/libs/optimization.py:72-163 (run_CG), wired at pytracking/tracker/eco/eco.py:166-170,244-246.
+ * Complex tensors carry a trailing dimension of 2; spectra are half spectra [H, Wh] with ky centred (fourier.cfft2).
+ *   filter [1,C,H,Wh,2] updated IN PLACE; samples [H,Wh,N,C,2] (training_samples[i], 16-byte aligned); yf [1,1,H,Wh] real;
+ *   sample_weights [N] (zero for unused slots); reg_filter [1,1,reg_h,reg_w] (reg_h <= min(8,H), reg_w <= min(8,Wh));
+ *   sample_energy [1,C,H,Wh] updated IN PLACE with new_xf [1,C,H,Wh,2] (may be null; has_energy = 0: initialised from new_xf);
+ *   CG state of ConjugateGradientBase, updated IN PLACE: p [1,C,H,Wh,2], r_prev [1,C,H,Wh,2] (Polak-Ribiere only), rho [1] (device);
+ *   has_state = 0: the buffers hold nothing yet (p is None); direction_forget_factor = 0 resets the state every call.
+ *   C (compressed_dim) in {16, 32, 64, 128}.  num_iter = 0 returns without touching anything (optim.py:141-142).            */
+int b200trk_eco_filter_cg(float* filter, const float* samples, const float* yf, const float* sample_weights,
+                          const float* reg_filter, int reg_h, int reg_w, float* sample_energy, int has_energy,
+                          const float* new_xf, float* p, float* r_prev, float* rho, int has_state,
+                          int H, int Wh, int N, int C, int num_iter, int fletcher_reeves, int standard_alpha,
+                          float direction_forget_factor, float precond_learning_rate, float precond_data_param,
+                          float precond_reg_param, b200trk_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Stage 1 -- backbone + classification head
  * ---------------------------------------------------------------------------------------------- */

@@ -1,0 +1,116 @@
+"""TEST INFRASTRUCTURE ONLY -- golden vectors of ECO's online filter optimiser from the UNMODIFIED reference.
+
+    python -m oracle.gen_eco_golden          (needs the reference: baseline/_ref or /root/reference)
+
+Drives `pytracking.tracker.eco.optim.FilterOptim` (optim.py:120-208) exactly as `ECO.initialize` / `ECO.track` do
+(eco.py:166-170, 236-246): a two-block TensorList (a "shallow" and a "deep" block with different sizes, channel counts,
+regularisation filters from `dcf.get_reg_filter` and learning rates), three consecutive `run` calls with a memory
+update in between, so that the CG state (p, rho, r_prev) carried between runs with direction_forget_factor != 0 and the
+running sample energy are covered.  Two parameter sets: the ECO default (Polak-Ribiere, forgetting) and Fletcher-Reeves
+with a state reset (direction_forget_factor = 0) and the non-standard alpha.
+Writes tests/golden/eco_cg.npz: per case / run / block the inputs and outputs of the run.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+BLOCKS = [dict(H=9, Wh=5, C=16, lr=0.025, reg=dict(reg_window_min=1e-4, reg_window_edge=10e-3, reg_sparsity_threshold=0.05)),
+          dict(H=7, Wh=4, C=64, lr=0.0075, reg=dict(reg_window_min=10e-4, reg_window_edge=50e-3, reg_sparsity_threshold=0.1))]
+N = 6
+CASES = {"pr_forget": dict(fletcher_reeves=False, standard_alpha=True, direction_forget_factor=(1 - 0.025) ** 75, iters=(4, 3, 3)),
+         "fr_reset": dict(fletcher_reeves=True, standard_alpha=False, direction_forget_factor=0, iters=(3, 2, 2))}
+
+
+def main():
+    from oracle import ref_shims
+    ref_shims.install()
+    from pytracking import TensorList, dcf
+    from pytracking.tracker.eco.optim import FilterOptim
+    from pytracking.utils import TrackerParams
+
+    out = {}
+    for cname, case in CASES.items():
+        g = torch.Generator().manual_seed(11)
+        params = TrackerParams()
+        params.fletcher_reeves = case["fletcher_reeves"]
+        params.standard_alpha = case["standard_alpha"]
+        params.direction_forget_factor = case["direction_forget_factor"]
+        params.debug = 0
+        params.precond_data_param = 0.3
+        params.precond_reg_param = 0.15
+        params.precond_learning_rate = TensorList([b["lr"] for b in BLOCKS])
+        reg_filter, yf, samples, sw, filt = TensorList(), TensorList(), TensorList(), TensorList(), TensorList()
+        for b in BLOCKS:
+            fp = TrackerParams()
+            fp.use_reg_window = True
+            fp.reg_window_power = 2
+            for k, v in b["reg"].items():
+                setattr(fp, k, v)
+            reg_filter.append(dcf.get_reg_filter(torch.Tensor([240., 240.]), torch.Tensor([50., 64.]), fp))
+            yf.append(dcf.label_function(torch.Tensor([b["H"], 2 * b["Wh"] - 1]), torch.Tensor([1.0, 1.3])))
+            samples.append(torch.zeros(b["H"], b["Wh"], N, b["C"], 2))
+            sw.append(torch.zeros(N))
+            filt.append(0.05 * torch.randn(1, b["C"], b["H"], b["Wh"], 2, generator=g))
+        # three stored samples to start with (eco.py:141-158 leaves the unused slots zero with zero weight)
+        for s, w_, b in zip(samples, sw, BLOCKS):
+            s[:, :, :3] = torch.randn(b["H"], b["Wh"], 3, b["C"], 2, generator=g)
+            w_[:3] = torch.tensor([0.5, 0.3, 0.2])
+        reg_energy = reg_filter.view(-1) @ reg_filter.view(-1)
+        opt = FilterOptim(params, reg_energy)
+        opt.register(filt, samples, yf, sw, reg_filter)
+        for bi, (b, rf) in enumerate(zip(BLOCKS, reg_filter)):
+            out["%s/b%d/reg_filter" % (cname, bi)] = rf.numpy().copy()
+            out["%s/b%d/yf" % (cname, bi)] = yf[bi].numpy().copy()
+            out["%s/b%d/lr" % (cname, bi)] = np.float32(b["lr"])
+        for run, it in enumerate(case["iters"]):
+            new_xf = TensorList([torch.randn(1, b["C"], b["H"], b["Wh"], 2, generator=g) for b in BLOCKS])
+            if run > 0:                                        # memory update of ECO.update_memory (eco.py:337-341): one slot per run
+                for s, w_, xf in zip(samples, sw, new_xf):
+                    slot = 2 + run
+                    s[:, :, slot:slot + 1] = xf.permute(2, 3, 0, 1, 4)
+                    w_ *= 0.9
+                    w_[slot] = 0.1
+                    w_ /= w_.sum()
+            for bi in range(len(BLOCKS)):
+                k = "%s/run%d/b%d/" % (cname, run, bi)
+                out[k + "hf_in"] = filt[bi].numpy().copy()
+                out[k + "samples"] = samples[bi].numpy().copy()
+                out[k + "sw"] = sw[bi].numpy().copy()
+                out[k + "new_xf"] = new_xf[bi].numpy().copy()
+                out[k + "has_energy"] = np.int32(opt.sample_energy is not None)
+                if opt.sample_energy is not None:
+                    out[k + "energy_in"] = opt.sample_energy[bi].numpy().copy()
+                out[k + "has_state"] = np.int32(opt.p is not None)
+                if opt.p is not None:
+                    out[k + "p_in"] = opt.p[bi].numpy().copy()
+                    out[k + "rho_in"] = np.float32(float(opt.rho[bi]))
+                    if opt.r_prev is not None:
+                        out[k + "r_prev_in"] = opt.r_prev[bi].numpy().copy()
+            opt.run(it, new_xf)
+            for bi in range(len(BLOCKS)):
+                k = "%s/run%d/b%d/" % (cname, run, bi)
+                out[k + "num_iter"] = np.int32(it)
+                out[k + "hf_out"] = filt[bi].numpy().copy()
+                out[k + "energy_out"] = opt.sample_energy[bi].numpy().copy()
+                out[k + "p_out"] = opt.p[bi].numpy().copy()
+                out[k + "rho_out"] = np.float32(float(opt.rho[bi]))
+                if opt.r_prev is not None:
+                    out[k + "r_prev_out"] = opt.r_prev[bi].numpy().copy()
+            # ECO.symmetrize_filter (eco.py:381-383) runs after every optimiser call in the tracker
+            for hf in filt:
+                hf[:, :, :, 0, :] /= 2
+        out[cname + "/params"] = np.array([float(case["fletcher_reeves"]), float(case["standard_alpha"]),
+                                           float(case["direction_forget_factor"]), 0.3, 0.15], dtype=np.float64)
+    os.makedirs(GOLDEN, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLDEN, "eco_cg.npz"), **out)
+    print("wrote eco_cg.npz with %d arrays" % len(out))
+
+
+if __name__ == "__main__":
+    main()

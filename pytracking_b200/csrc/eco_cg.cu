@@ -1,0 +1,62 @@
+// ECO online filter optimiser -- device build and C ABI of the kernel in eco_cg_kernel.cuh (design notes there).
+//   reference: pytracking/tracker/eco/optim.py:140-208, pytracking/libs/optimization.py:72-163.
+#include "common.cuh"
+#include "eco_cg_kernel.cuh"
+
+namespace b200trk {
+
+template <int G, int CPL>
+static int launch_eco(const EcoPlan& pl, EcoParams& P, cudaStream_t st) {
+    auto kern = eco_cg_kernel<G, CPL>;
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+    void* args[] = {(void*)&P};
+    B200_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(pl.grid), dim3(pl.block), args, pl.smem_bytes, st));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+}  // namespace b200trk
+
+using namespace b200trk;
+
+extern "C" int b200trk_eco_filter_cg(float* filter, const float* samples, const float* yf, const float* sample_weights,
+                                     const float* reg_filter, int reg_h, int reg_w, float* sample_energy, int has_energy,
+                                     const float* new_xf, float* p, float* r_prev, float* rho, int has_state,
+                                     int H, int Wh, int N, int C, int num_iter, int fletcher_reeves, int standard_alpha,
+                                     float direction_forget_factor, float precond_learning_rate, float precond_data_param,
+                                     float precond_reg_param, b200trk_stream_t stream) {
+    B200_REQUIRE(filter && samples && yf && sample_weights && reg_filter && sample_energy && p && rho,
+                 "eco_filter_cg: null pointer");
+    B200_REQUIRE(fletcher_reeves || r_prev, "eco_filter_cg: the Polak-Ribiere formula needs the r_prev buffer");
+    B200_REQUIRE(has_energy || new_xf, "eco_filter_cg: no sample energy yet and no new sample to initialise it from");
+    B200_REQUIRE(H > 0 && Wh > 0 && N > 0 && N <= 4096, "eco_filter_cg: H=%d Wh=%d N=%d", H, Wh, N);
+    B200_REQUIRE(C == 16 || C == 32 || C == 64 || C == 128, "eco_filter_cg: C=%d (compressed_dim) must be 16, 32, 64 or 128", C);
+    B200_REQUIRE(reg_h >= 1 && reg_w >= 1 && reg_h <= 8 && reg_w <= 8, "eco_filter_cg: regularisation filter %dx%d (at most 8x8)", reg_h, reg_w);
+    // optim.py:178-183 rebuilds reg_w - 1 negative-kx columns from the half spectrum and pads reg_h - 1 rows: both must exist
+    B200_REQUIRE(reg_w <= Wh && reg_h <= H, "eco_filter_cg: regularisation filter %dx%d larger than the %dx%d half spectrum", reg_h, reg_w, H, Wh);
+    B200_REQUIRE(num_iter >= 0 && num_iter <= 1024, "eco_filter_cg: num_iter=%d", num_iter);
+    if (num_iter == 0) return 0;                                         // optim.py:141-142: nothing happens, not even the energy update
+    cudaStream_t st = (cudaStream_t)stream;
+    EcoPlan pl = eco_plan(H, Wh, N, C, num_iter, device_sm_count(), 256);
+    B200_REQUIRE(pl.smem_bytes <= 227 * 1024, "eco_filter_cg: %zu bytes of shared memory", pl.smem_bytes);
+    char* ws = (char*)workspace(pl.ws_bytes, 6);
+    if (!ws) return 3;
+    EcoParams P{};
+    P.hf = filter; P.samples = samples; P.yf = yf; P.sw = sample_weights; P.reg_filter = reg_filter;
+    P.sample_energy = sample_energy; P.new_xf = new_xf; P.p_state = p; P.r_prev_state = r_prev; P.rho_state = rho;
+    P.has_state = (has_state && direction_forget_factor != 0.f) ? 1 : 0;   // optimization.py:82-85: a zero factor resets the state
+    P.has_energy = has_energy ? 1 : 0;
+    P.H = H; P.Wh = Wh; P.N = N; P.C = C; P.rh = reg_h; P.rw = reg_w; P.num_iter = num_iter;
+    P.fletcher_reeves = fletcher_reeves ? 1 : 0; P.standard_alpha = standard_alpha ? 1 : 0;
+    P.dff = direction_forget_factor; P.lr = precond_learning_rate; P.pdp = precond_data_param; P.prp = precond_reg_param;
+    P.barrier = (unsigned*)ws;
+    P.xw = (float2*)(ws + pl.off_xw); P.pw = (float2*)(ws + pl.off_pw); P.resw = (float2*)(ws + pl.off_resw);
+    P.rpw = (float2*)(ws + pl.off_rpw); P.qw = (float2*)(ws + pl.off_qw); P.dM = (float*)(ws + pl.off_dM);
+    P.dots = (float*)(ws + pl.off_dots);
+    P.GPP = pl.GPP; P.res_slabs = pl.res_slabs; P.npx_max = pl.npx_max;
+    B200_CHECK_CUDA(cudaMemsetAsync(P.barrier, 0, 256, st));
+    if (pl.G == 16) return launch_eco<16, 1>(pl, P, st);
+    if (pl.CPL == 1) return launch_eco<32, 1>(pl, P, st);
+    if (pl.CPL == 2) return launch_eco<32, 2>(pl, P, st);
+    return launch_eco<32, 4>(pl, P, st);
+}

@@ -223,6 +223,55 @@ def atom_cg_filter(filt, feat, y, sample_weight, filter_reg, num_iter, activatio
     return wout
 
 
+def eco_filter_cg_(filt, samples, yf, sample_weights, reg_filter, sample_energy, num_iter, new_xf=None, state=None,
+                   fletcher_reeves=False, standard_alpha=True, direction_forget_factor=0.0, precond_learning_rate=0.0075,
+                   precond_data_param=0.3, precond_reg_param=0.15):
+    """FilterOptim.run(num_iter, new_xf) for one ECO feature block (optim.py:140-208).  Updates IN PLACE: `filt` [1,C,H,Wh,2],
+    `sample_energy` [1,C,H,Wh] (None: created from `new_xf`), and the CG state `state` = dict(p, r_prev, rho) of device tensors
+    (None / empty: no previous direction).  Returns (sample_energy, state)."""
+    for name, t in (("filter", filt), ("sample_energy", sample_energy)) + tuple((state or {}).items()):
+        if t is not None and (not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
+            raise RuntimeError("b200trk.eco_filter_cg_: '%s' must be a contiguous CUDA float32 tensor (updated in place)" % name)
+    _dev(filt, "filter")
+    samples, yf, sample_weights, reg_filter = _dev(samples, "training_samples"), _dev(yf, "yf"), _dev(sample_weights, "sample_weights"), \
+        _dev(reg_filter, "reg_filter")
+    if filt.dim() != 5 or filt.shape[0] != 1 or filt.shape[-1] != 2 or samples.dim() != 5:
+        raise RuntimeError("b200trk.eco_filter_cg_: filter [1,C,H,Wh,2] and training_samples [H,Wh,N,C,2] expected")
+    _, c, h, wh, _ = filt.shape
+    n = samples.shape[2]
+    if tuple(samples.shape) != (h, wh, n, c, 2) or yf.numel() != h * wh or sample_weights.numel() != n or samples.data_ptr() % 16:
+        raise RuntimeError("b200trk.eco_filter_cg_: training_samples %s / yf / sample_weights do not match the filter %s"
+                           % (tuple(samples.shape), tuple(filt.shape)))
+    if int(num_iter) == 0:
+        return sample_energy, state
+    if new_xf is not None:
+        new_xf = _dev(new_xf, "new_xf")
+        if new_xf.numel() != filt.numel():
+            raise RuntimeError("b200trk.eco_filter_cg_: new_xf %s does not match the filter" % (tuple(new_xf.shape),))
+    has_energy = sample_energy is not None
+    if not has_energy:
+        if new_xf is None:
+            raise RuntimeError("b200trk.eco_filter_cg_: no sample energy and no new sample")
+        sample_energy = torch.empty(1, c, h, wh, device=filt.device, dtype=torch.float32)
+    elif sample_energy.numel() != c * h * wh:
+        raise RuntimeError("b200trk.eco_filter_cg_: sample_energy %s does not match the filter" % (tuple(sample_energy.shape),))
+    has_state = bool(state) and state.get("p") is not None
+    if not has_state:
+        state = {"p": torch.empty_like(filt), "r_prev": None if fletcher_reeves else torch.empty_like(filt),
+                 "rho": torch.ones(1, device=filt.device, dtype=torch.float32)}
+    elif not fletcher_reeves and state.get("r_prev") is None:
+        raise RuntimeError("b200trk.eco_filter_cg_: the Polak-Ribiere formula needs state['r_prev']")
+    if state["p"].numel() != filt.numel() or state["rho"].numel() != 1:
+        raise RuntimeError("b200trk.eco_filter_cg_: CG state does not match the filter")
+    _lib.check(_lib.lib().b200trk_eco_filter_cg(
+        _p(filt), _p(samples), _p(yf), _p(sample_weights), _p(reg_filter), int(reg_filter.shape[-2]), int(reg_filter.shape[-1]),
+        _p(sample_energy), 1 if has_energy else 0, _p(new_xf), _p(state["p"]), _p(state.get("r_prev")), _p(state["rho"]),
+        1 if has_state else 0, h, wh, n, c, int(num_iter), 1 if fletcher_reeves else 0, 1 if standard_alpha else 0,
+        float(direction_forget_factor), float(precond_learning_rate), float(precond_data_param), float(precond_reg_param), _stream()),
+        "eco_filter_cg")
+    return sample_energy, state
+
+
 def atom_gn_joint_(filt, proj, samples, y, sample_weight, filter_reg, projection_reg, num_cg_iter, num_gn_iter,
                    activation="mlu", act_param=0.05, fletcher_reeves=True):
     """GaussNewtonCG.run(num_cg_iter, num_gn_iter) on FactorizedConvProblem; updates `filt` and `proj` in place."""

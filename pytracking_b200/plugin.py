@@ -770,6 +770,59 @@ def install(max_batch=16, precision=0, skip=()):
     _bind(oz.ConjugateGradient, "run", cg_run)
     _bind(oz.GaussNewtonCG, "run", gn_run)
 
+    # ---- 5b. ECO: pytracking/tracker/eco/optim.py:140-163 (FilterOptim.run), one launch per feature block ----
+    eo = importlib.import_module("pytracking.tracker.eco.optim")
+    ref_eco_run = eo.FilterOptim.run
+
+    def _eco_block_ok(hf, xs, yf, sw, rf):
+        return (_inference(hf, xs, yf, sw, rf) and hf.dim() == 5 and hf.shape[0] == 1 and hf.shape[-1] == 2 and
+                hf.shape[1] in (16, 32, 64, 128) and hf.is_contiguous() and xs.is_contiguous() and
+                tuple(xs.shape) == (hf.shape[2], hf.shape[3], xs.shape[2], hf.shape[1], 2) and xs.data_ptr() % 16 == 0 and
+                yf.numel() == hf.shape[2] * hf.shape[3] and sw.numel() == xs.shape[2] and rf.dim() == 4 and
+                rf.shape[-2] <= min(8, hf.shape[2]) and rf.shape[-1] <= min(8, hf.shape[3]))
+
+    def eco_run(self, num_iter, new_xf=None):
+        if num_iter == 0:
+            return
+        nb = len(self.filter)
+        dff = float(self.direction_forget_factor)
+        have = self.p is not None and dff != 0
+        ok = (not self.debug and len(self.training_samples) == nb and len(self.reg_filter) == nb and
+              (self.sample_energy is not None or new_xf is not None) and
+              all(_eco_block_ok(*b) for b in zip(self.filter, self.training_samples, self.yf, self.sample_weights, self.reg_filter)) and
+              (new_xf is None or (len(new_xf) == nb and all(_inference(x) and x.numel() == f.numel() for x, f in zip(new_xf, self.filter)))) and
+              (not have or (isinstance(self.rho, list) and len(self.rho) == nb and len(self.p) == nb and
+                            (self.fletcher_reeves or self.r_prev is not None))))
+        if not ok:
+            return ref_eco_run(self, num_iter, new_xf)
+        tlist = type(self.filter)
+        lr = self.params.precond_learning_rate
+        if self.sample_energy is not None and not getattr(self, "_b200trk_energy_owned", False):
+            # eco.py:168 hands over joint_problem.sample_energy itself; the library updates the energy in place, so take a copy once
+            self.sample_energy = tlist([e.detach().clone().contiguous() for e in self.sample_energy])
+        energies, ps, rps, rhos = [], [], [], []
+        for i in range(nb):
+            st = None
+            if have:
+                st = {"p": self.p[i].contiguous(), "r_prev": None if self.fletcher_reeves else self.r_prev[i].contiguous(),
+                      "rho": self.rho[i].detach().to(self.filter[i].device, torch.float32).reshape(1).clone()}
+            e, st = ops.eco_filter_cg_(self.filter[i], self.training_samples[i], self.yf[i], self.sample_weights[i], self.reg_filter[i],
+                                       None if self.sample_energy is None else self.sample_energy[i], num_iter,
+                                       None if new_xf is None else new_xf[i], st, self.fletcher_reeves, self.standard_alpha, dff,
+                                       float(lr[i]) if isinstance(lr, (list, tuple)) else float(lr),
+                                       float(self.params.precond_data_param), float(self.params.precond_reg_param))
+            energies.append(e)
+            ps.append(st["p"])
+            rps.append(st["r_prev"])
+            rhos.append(st["rho"].reshape(()))
+        # the state stays in the reference's own attributes and layout, so a later fall-through run continues from it
+        self.sample_energy = tlist(energies)
+        self._b200trk_energy_owned = True
+        self.p, self.rho = tlist(ps), tlist(rhos)
+        self.r_prev = None if self.fletcher_reeves else tlist(rps)
+        _count("FilterOptim.run")
+    _bind(eo.FilterOptim, "run", eco_run)
+
     # ---- 6. ToMP: ltr/models/transformer/transformer.py:90-96 ----
     tr = importlib.import_module("ltr.models.transformer.transformer")
     from .transformer_engine import TransformerEngine

@@ -1,0 +1,152 @@
+// TEST INFRASTRUCTURE ONLY.  A minimal SIMT-on-CPU shim: compiles a plain CUDA C kernel (no inline PTX) as host code and runs it
+// with ONE OS THREAD PER CUDA THREAD, so that bar.sync, warp shuffles, shared memory and the cooperative grid barrier keep their
+// semantics (a missing barrier is a real data race here as well, and ThreadSanitizer finds it).
+//   __syncthreads()        -> pthread barrier over the block's threads
+//   __shfl_xor_sync()      -> exchange through a per-warp buffer, one pthread barrier per shuffle (double buffered)
+//   extern __shared__      -> B200_DYN_SMEM(name): one allocation per block
+//   b200trk::grid_barrier  -> bar.sync + pthread barrier over the blocks' leader threads + bar.sync
+// The device helpers of csrc/common.cuh used by the emulated kernels (warp_sum, block_sum, grid_barrier) are restated below with
+// the same summation order.  Grids are kept small (a few blocks of 64-128 threads): the kernels under test take their
+// decomposition from gridDim / blockDim.
+#pragma once
+#include <pthread.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#define B200_CPU_EMUL 1
+
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct emul_dim3 { unsigned x, y, z; };
+using std::max;
+using std::min;
+
+namespace cpu_emul {
+
+struct Warp {
+    pthread_barrier_t bar;
+    float buf[2][32];
+};
+struct Block {
+    pthread_barrier_t bar;
+    std::vector<unsigned char> smem;
+    std::vector<Warp> warps;
+};
+struct Grid {
+    pthread_barrier_t leaders;
+    std::vector<Block> blocks;
+};
+struct ThreadCtx {
+    emul_dim3 tid, bid, bdim, gdim;
+    Block* blk;
+    Warp* warp;
+    Grid* grid;
+    int parity;
+};
+inline thread_local ThreadCtx* tctx = nullptr;
+
+inline unsigned char* dyn_smem() { return tctx->blk->smem.data(); }
+
+template <class Kernel, class Params>
+void launch(Kernel kernel, unsigned grid_dim, unsigned block_dim, size_t smem_bytes, Params params) {
+    Grid g;
+    g.blocks = std::vector<Block>(grid_dim);
+    pthread_barrier_init(&g.leaders, nullptr, grid_dim);
+    const unsigned nwarps = (block_dim + 31) / 32;
+    for (auto& b : g.blocks) {
+        pthread_barrier_init(&b.bar, nullptr, block_dim);
+        b.smem.assign(smem_bytes + 16, 0xCD);                 // poisoned: uninitialised shared memory shows up as garbage
+        b.warps = std::vector<Warp>(nwarps);
+        for (unsigned w = 0; w < nwarps; ++w) {
+            const unsigned lanes = std::min(32u, block_dim - w * 32);
+            pthread_barrier_init(&b.warps[w].bar, nullptr, lanes);
+        }
+    }
+    std::vector<std::thread> threads;
+    threads.reserve((size_t)grid_dim * block_dim);
+    for (unsigned b = 0; b < grid_dim; ++b)
+        for (unsigned t = 0; t < block_dim; ++t)
+            threads.emplace_back([&, b, t]() {
+                ThreadCtx c{};
+                c.tid = {t, 0, 0};
+                c.bid = {b, 0, 0};
+                c.bdim = {block_dim, 1, 1};
+                c.gdim = {grid_dim, 1, 1};
+                c.blk = &g.blocks[b];
+                c.warp = &g.blocks[b].warps[t / 32];
+                c.grid = &g;
+                c.parity = 0;
+                tctx = &c;
+                kernel(params);
+                tctx = nullptr;
+            });
+    for (auto& th : threads) th.join();
+    for (auto& b : g.blocks) {
+        pthread_barrier_destroy(&b.bar);
+        for (auto& w : b.warps) pthread_barrier_destroy(&w.bar);
+    }
+    pthread_barrier_destroy(&g.leaders);
+}
+
+}  // namespace cpu_emul
+
+#define threadIdx (::cpu_emul::tctx->tid)
+#define blockIdx (::cpu_emul::tctx->bid)
+#define blockDim (::cpu_emul::tctx->bdim)
+#define gridDim (::cpu_emul::tctx->gdim)
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+
+static inline void __syncthreads() { pthread_barrier_wait(&::cpu_emul::tctx->blk->bar); }
+
+static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+    auto* c = ::cpu_emul::tctx;
+    const int lane = c->tid.x & 31;
+    float* buf = c->warp->buf[c->parity];
+    c->parity ^= 1;
+    buf[lane] = v;
+    pthread_barrier_wait(&c->warp->bar);
+    return buf[lane ^ lane_mask];
+}
+
+template <class T>
+static inline T __ldcg(const T* p) { return *p; }
+
+namespace b200trk {
+
+static inline float warp_sum(float v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+static inline float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    float t = (lane < nw) ? red[lane] : 0.f;
+    t = warp_sum(t);
+    return t;
+}
+
+static inline void grid_barrier(unsigned*, unsigned& epoch) {
+    __syncthreads();
+    epoch += 1;
+    if (threadIdx.x == 0) pthread_barrier_wait(&::cpu_emul::tctx->grid->leaders);
+    __syncthreads();
+}
+
+}  // namespace b200trk

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.skipif(not ref_env.reference_available(), reason="refer
 SEAMS = ["filter.apply_filter", "filter.apply_feat_transpose", "dcf.max2d", "DiMPSteepestDescentGN.forward",
          "PrDiMPSteepestDescentNewton.forward", "DiMPL2SteepestDescentGN.forward", "NetWithBackbone.extract_backbone",
          "DiMPnet.extract_classification_feat", "functional._prroi_pooling", "operation.conv2d", "operation.conv1x1",
-         "ConjugateGradient.run", "GaussNewtonCG.run", "Transformer.forward", "AtomIoUNet.get_iou_feat", "AtomIoUNet.predict_iou", "Head.extract_head_feat",
+         "ConjugateGradient.run", "GaussNewtonCG.run", "FilterOptim.run", "Transformer.forward", "AtomIoUNet.get_iou_feat", "AtomIoUNet.predict_iou", "Head.extract_head_feat",
          "DenseBoxRegressor.forward", "FilterPredictor.predict_cls_bbreg_filters_parallel"]
 
 
@@ -103,3 +103,30 @@ def test_reference_tracker_on_cpu_is_unchanged_by_install():
     finally:
         plugin.uninstall()
     assert np.array_equal(a["target_bbox"], b["target_bbox"])
+
+
+def test_eco_filter_optim_falls_through_on_cpu(installed):
+    """FilterOptim.run (eco/optim.py:140) is rebound; CPU tensors keep the reference implementation and reproduce the golden run."""
+    plugin, _ = installed
+    import os
+    from pytracking import TensorList
+    from pytracking.tracker.eco.optim import FilterOptim
+    from pytracking.utils import TrackerParams
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eco_cg.npz"))
+    case = "pr_forget"
+    fr, sa, dff, pdp, prp = g[case + "/params"]
+    params = TrackerParams()
+    params.fletcher_reeves, params.standard_alpha, params.direction_forget_factor, params.debug = bool(fr), bool(sa), float(dff), 0
+    params.precond_data_param, params.precond_reg_param = float(pdp), float(prp)
+    params.precond_learning_rate = TensorList([float(g["%s/b%d/lr" % (case, b)]) for b in range(2)])
+    T = lambda k: torch.from_numpy(g[k].copy())
+    k0 = [case + "/run0/b%d/" % b for b in range(2)]
+    filt = TensorList([T(k + "hf_in") for k in k0])
+    reg = TensorList([T("%s/b%d/reg_filter" % (case, b)) for b in range(2)])
+    opt = FilterOptim(params, reg.view(-1) @ reg.view(-1))
+    opt.register(filt, TensorList([T(k + "samples") for k in k0]), TensorList([T("%s/b%d/yf" % (case, b)) for b in range(2)]),
+                 TensorList([T(k + "sw") for k in k0]), reg)
+    opt.run(int(g[k0[0] + "num_iter"]), TensorList([T(k + "new_xf") for k in k0]))
+    for b, k in enumerate(k0):
+        assert torch.allclose(filt[b], T(k + "hf_out"), rtol=0, atol=1e-6 * float(T(k + "hf_out").abs().max()))
+    assert not plugin.stats.get("FilterOptim.run")

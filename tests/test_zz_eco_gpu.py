@@ -1,0 +1,177 @@
+"""-m gpu parity tests of SURVEY 8 row f4: ECO's per-frame Fourier-domain filter optimiser (`b200trk_eco_filter_cg`, csrc/eco_cg.cu)
+through the C ABI against (1) the golden vectors of the UNMODIFIED reference FilterOptim (tests/golden/eco_cg.npz), (2) the oracle
+(oracle/eco_oracle.py, pinned to the same vectors on the CPU) at ECO's real block sizes, with the tolerance calibrated by the
+float32-vs-float64 spread of the oracle itself, and (3) the unmodified reference FilterOptim object on stock PyTorch-CUDA with the
+plug-in seam installed.  (The same kernel source also runs on the CPU under tests/cpu_emul -- tests/test_eco_cpu.py.)"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eco_cg.npz")
+CASES = [(c, r, b) for c in ("pr_forget", "fr_reset") for r in range(3) for b in range(2)]
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).detach().double().cpu(), torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def _state_from_golden(g, k, fr):
+    if not int(g[k + "has_state"]):
+        return None
+    return {"p": torch.from_numpy(g[k + "p_in"].copy()).cuda(),
+            "r_prev": None if fr else torch.from_numpy(g[k + "r_prev_in"].copy()).cuda(),
+            "rho": torch.tensor([float(g[k + "rho_in"])], dtype=torch.float32).cuda()}
+
+
+@pytest.mark.parametrize("case,run,bi", CASES)
+def test_eco_filter_cg_matches_reference_golden(case, run, bi):
+    from pytracking_b200 import ops
+    g = np.load(GOLD)
+    fr, sa, dff, pdp, prp = g[case + "/params"]
+    k = "%s/run%d/b%d/" % (case, run, bi)
+    D = lambda key: torch.from_numpy(g[key].copy()).cuda()
+    hf = D(k + "hf_in")
+    en = D(k + "energy_in") if int(g[k + "has_energy"]) else None
+    en, st = ops.eco_filter_cg_(hf, D(k + "samples"), D("%s/b%d/yf" % (case, bi)), D(k + "sw"), D("%s/b%d/reg_filter" % (case, bi)), en,
+                                int(g[k + "num_iter"]), D(k + "new_xf"), _state_from_golden(g, k, bool(fr)), bool(fr), bool(sa), float(dff),
+                                float(g["%s/b%d/lr" % (case, bi)]), float(pdp), float(prp))
+    torch.cuda.synchronize()
+    assert _rel(hf, g[k + "hf_out"]) < 5e-5
+    assert _rel(en, g[k + "energy_out"]) < 1e-6
+    assert _rel(st["p"], g[k + "p_out"]) < 5e-5
+    assert abs(float(st["rho"]) - float(g[k + "rho_out"])) < 5e-5 * abs(float(g[k + "rho_out"]))
+    if (k + "r_prev_out") in g:
+        assert _rel(st["r_prev"], g[k + "r_prev_out"]) < 5e-5
+
+
+def _problem(h, wh, n, c, stored, seed):
+    g = torch.Generator().manual_seed(seed)
+    samples = torch.zeros(h, wh, n, c, 2)
+    samples[:, :, :stored] = torch.randn(h, wh, stored, c, 2, generator=g)
+    sw = torch.zeros(n)
+    sw[:stored] = torch.rand(stored, generator=g) + 0.1
+    sw /= sw.sum()
+    ky = torch.arange(-(h - 1) // 2, h // 2 + 1, dtype=torch.float32).view(-1, 1)
+    kx = torch.arange(0, wh, dtype=torch.float32).view(1, -1)
+    yf = torch.exp(-0.05 * (ky ** 2 + kx ** 2)).view(1, 1, h, wh)                       # a label function's spectrum: real, decaying
+    reg = torch.tensor([[0.0, 0.02, 0.05, 0.02, 0.0], [0.02, 0.1, 0.2, 0.1, 0.02], [0.05, 0.2, 0.9, 0.2, 0.05],
+                        [0.02, 0.1, 0.2, 0.1, 0.02], [0.0, 0.02, 0.05, 0.02, 0.0]]).view(1, 1, 5, 5)
+    hf = 0.01 * torch.randn(1, c, h, wh, 2, generator=g)
+    new_xf = [torch.randn(1, c, h, wh, 2, generator=g) for _ in range(2)]
+    return samples, sw, yf, reg, hf, new_xf
+
+
+# ECO default blocks (parameter/eco/default.py): memory 200; deep 64 channels on 15x8 coefficients (one resident slab per CTA, eight
+# warps per slab), shallow 16 channels on 63x32 (14 coefficients per CTA, 8 slabs resident + 6 streamed); a partly filled memory
+@pytest.mark.parametrize("h,wh,n,c,stored", [(15, 8, 200, 64, 200), (63, 32, 200, 16, 200), (17, 9, 200, 32, 37), (13, 7, 50, 128, 50)])
+def test_eco_filter_cg_full_size_vs_oracle(h, wh, n, c, stored):
+    from oracle import eco_oracle as E
+    from pytracking_b200 import ops
+    samples, sw, yf, reg, hf0, new_xf = _problem(h, wh, n, c, stored, seed=h * 100 + c)
+    kw = dict(precond_learning_rate=0.0075, precond_data_param=0.3, precond_reg_param=0.15, fletcher_reeves=False, standard_alpha=True,
+              direction_forget_factor=(1 - 0.0075) ** 75)
+    res = {}
+    for dt in (torch.float32, torch.float64):                       # two consecutive runs: the second continues from the CG state
+        x, en, st = hf0.to(dt), None, {}
+        for r in range(2):
+            x, en, st = E.filter_optim_run(x, samples.to(dt), yf.to(dt), sw.to(dt), reg.to(dt), en, st, 5, new_xf[r].to(dt), **kw)
+        res[dt] = (x, en, st["p"])
+    hf, en, st = hf0.clone().cuda(), None, None
+    for r in range(2):
+        en, st = ops.eco_filter_cg_(hf, samples.cuda(), yf.cuda(), sw.cuda(), reg.cuda(), en, 5, new_xf[r].cuda(), st, **kw)
+    torch.cuda.synchronize()
+    spread = max(_rel(res[torch.float32][0], res[torch.float64][0]), _rel(res[torch.float32][2], res[torch.float64][2]))
+    tol = max(20 * spread, 2e-5)                                    # float32 CG against the float64 solution, calibrated by the oracle's own spread
+    assert _rel(hf, res[torch.float64][0]) < tol, (_rel(hf, res[torch.float64][0]), spread)
+    assert _rel(st["p"], res[torch.float64][2]) < tol, (_rel(st["p"], res[torch.float64][2]), spread)
+    assert _rel(en, res[torch.float64][1]) < 1e-5
+    # bitwise determinism (fixed summation orders)
+    hf2, en2, st2 = hf0.clone().cuda(), None, None
+    for r in range(2):
+        en2, st2 = ops.eco_filter_cg_(hf2, samples.cuda(), yf.cuda(), sw.cuda(), reg.cuda(), en2, 5, new_xf[r].cuda(), st2, **kw)
+    assert torch.equal(hf, hf2) and torch.equal(st["p"], st2["p"]) and torch.equal(st["rho"], st2["rho"])
+
+
+def test_eco_filter_cg_rejects_what_the_kernel_does_not_claim():
+    from pytracking_b200 import ops
+    samples, sw, yf, reg, hf, new_xf = _problem(9, 5, 8, 16, 8, seed=1)
+    with pytest.raises(RuntimeError):                               # compressed_dim 24
+        ops.eco_filter_cg_(torch.zeros(1, 24, 9, 5, 2).cuda(), torch.zeros(9, 5, 8, 24, 2).cuda(), yf.cuda(), sw.cuda(), reg.cuda(), None, 2,
+                           torch.zeros(1, 24, 9, 5, 2).cuda())
+    with pytest.raises(RuntimeError):                               # regularisation filter wider than the half spectrum
+        ops.eco_filter_cg_(hf.cuda(), samples.cuda(), yf.cuda(), sw.cuda(), torch.ones(1, 1, 3, 7).cuda(), None, 2, new_xf[0].cuda())
+    with pytest.raises(RuntimeError):                               # no energy and nothing to initialise it from
+        ops.eco_filter_cg_(hf.cuda(), samples.cuda(), yf.cuda(), sw.cuda(), reg.cuda(), None, 2, None)
+    h0 = hf.clone().cuda()
+    ops.eco_filter_cg_(h0, samples.cuda(), yf.cuda(), sw.cuda(), reg.cuda(), None, 0, new_xf[0].cuda())     # num_iter = 0: untouched
+    assert torch.equal(h0.cpu(), hf)
+
+
+def test_reference_filter_optim_above_the_engine():
+    """The unmodified reference FilterOptim object (two-block TensorLists, ECO default CG settings) on CUDA tensors: stock PyTorch vs
+    the plug-in seam, three consecutive runs with memory updates; the CG state stays in the reference's own attributes."""
+    from baseline import ref_env
+    if not ref_env.reference_available():
+        pytest.skip("reference tree not staged (baseline/_ref)")
+    from oracle import ref_shims
+    ref_shims.install()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    from pytracking import TensorList
+    from pytracking.tracker.eco.optim import FilterOptim
+    from pytracking.utils import TrackerParams
+    from pytracking_b200 import plugin
+
+    blocks = [(15, 8, 16, 0.025), (9, 5, 64, 0.0075)]
+    n = 30
+
+    def make():
+        g = torch.Generator().manual_seed(5)
+        params = TrackerParams()
+        params.fletcher_reeves, params.standard_alpha, params.debug = False, True, 0
+        params.direction_forget_factor = (1 - 0.025) ** 75
+        params.precond_data_param, params.precond_reg_param = 0.3, 0.15
+        params.precond_learning_rate = TensorList([b[3] for b in blocks])
+        probs = [_problem(h, wh, n, c, 12, seed=7 + i) for i, (h, wh, c, _) in enumerate(blocks)]
+        filt = TensorList([p[4].clone().cuda() for p in probs])
+        samples = TensorList([p[0].clone().cuda() for p in probs])
+        sw = TensorList([p[1].clone().cuda() for p in probs])
+        reg = TensorList([p[3].clone().cuda() for p in probs])
+        opt = FilterOptim(params, reg.view(-1) @ reg.view(-1))
+        opt.register(filt, samples, TensorList([p[2].clone().cuda() for p in probs]), sw, reg)
+        news = [TensorList([torch.randn(1, c, h, wh, 2, generator=g).cuda() for (h, wh, c, _) in blocks]) for _ in range(3)]
+        return opt, filt, samples, sw, news
+
+    def drive(opt, filt, samples, sw, news):
+        outs = []
+        for r, nx in enumerate(news):
+            if r:
+                for s, w_, xf in zip(samples, sw, nx):
+                    s[:, :, 12 + r:13 + r] = xf.permute(2, 3, 0, 1, 4)
+                    w_ *= 0.9
+                    w_[12 + r] = 0.1
+                    w_ /= w_.sum()
+            opt.run(5, nx)
+            for hf in filt:                                           # ECO.symmetrize_filter (eco.py:381-383)
+                hf[:, :, :, 0, :] /= 2
+            outs.append([hf.clone() for hf in filt])
+        return outs
+
+    ref = drive(*make())
+    plugin.install()
+    try:
+        before = plugin.stats.get("FilterOptim.run", 0)
+        opt, filt, samples, sw, news = make()
+        got = drive(opt, filt, samples, sw, news)
+        assert plugin.stats.get("FilterOptim.run", 0) == before + 3
+        assert isinstance(opt.p, TensorList) and opt.p[0].shape == filt[0].shape and opt.rho[0].dim() == 0
+    finally:
+        plugin.uninstall()
+    for r in range(3):
+        for b in range(2):
+            assert _rel(got[r][b], ref[r][b]) < 2e-4, (r, b, _rel(got[r][b], ref[r][b]))
