@@ -1,6 +1,28 @@
 // ECO online filter optimiser -- device build and C ABI of the kernel in eco_cg_kernel.cuh (design notes there).
 //   reference: pytracking/tracker/eco/optim.py:140-208, pytracking/libs/optimization.py:72-163.
 #include "common.cuh"
+
+namespace b200trk {
+
+// grid_barrier (common.cuh) with a bounded wait: if the other CTAs never arrive (which a cooperative launch rules out) the poll gives
+// up after ~2^20 round trips, raises word 16 of the counter block and every later barrier of this CTA falls through, so that a defect
+// can only ever produce a wrong result, never a kernel that does not terminate.
+__device__ __forceinline__ void eco_grid_barrier(unsigned* counter, unsigned& epoch, unsigned& dead) {
+    __syncthreads();
+    epoch += 1;
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+        const unsigned target = epoch * gridDim.x;
+        unsigned spins = 0;
+        while (!dead && ld_acquire_u32(counter) < target) {
+            if (++spins > (1u << 20)) { dead = 1u; counter[16] = 1u; }
+        }
+    }
+    __syncthreads();
+}
+
+}  // namespace b200trk
+
 #include "eco_cg_kernel.cuh"
 
 namespace b200trk {

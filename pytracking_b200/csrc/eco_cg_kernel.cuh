@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256, 1) eco_cg_kernel(EcoParams P) {
     const int nel = npx * C;                                 // own elements of a pixel-major field: [p0*C, p1*C)
     const size_t e0 = (size_t)p0 * C;
     const size_t slab_elems = (size_t)N * C;                 // float2 per slab
-    unsigned epoch = 0;
+    unsigned epoch = 0, dead = 0;                            // grid-barrier bookkeeping (eco_grid_barrier: bounded wait)
     int dot_slot = 0;
 
     // ---- prologue 0: composite regularisation filter W (*) W, reg_energy, sample weights, resident slabs --------------------
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256, 1) eco_cg_kernel(EcoParams P) {
         float* slotp = P.dots + (size_t)dot_slot * nb * 2;
         dot_slot += 1;
         if (tid == 0) { slotp[cta * 2] = d0; slotp[cta * 2 + 1] = d1; }
-        grid_barrier(P.barrier, epoch);
+        eco_grid_barrier(P.barrier, epoch, dead);
         if (tid < 32) {
             float a = 0.f, b = 0.f;
             for (int i = tid; i < nb; i += 32) { a += __ldcg(slotp + 2 * i); b += __ldcg(slotp + 2 * i + 1); }
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256, 1) eco_cg_kernel(EcoParams P) {
 
     // ---- right-hand side and the initial residual r = b - A x (optimization.py:88-91) -------------------------------------------
     apply(nullptr, P.resw, true);
-    grid_barrier(P.barrier, epoch);                          // x of every CTA in place
+    eco_grid_barrier(P.barrier, epoch, dead);                          // x of every CTA in place
     apply(P.xw, P.qw, false);
     float l0 = 0.f, l1 = 0.f;
     for (int e = tid; e < nel; e += NT) {
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(256, 1) eco_cg_kernel(EcoParams P) {
             P.pw[e0 + e] = p;
         }
         have_p = true;
-        grid_barrier(P.barrier, epoch);                      // p of every CTA in place
+        eco_grid_barrier(P.barrier, epoch, dead);                      // p of every CTA in place
         // ---- q = A p, <p,q> (and <p,r> for the non-standard alpha) ------------------------------------------------------------------
         apply(P.pw, P.qw, false);
         l0 = 0.f; l1 = 0.f;

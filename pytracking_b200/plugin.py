@@ -733,7 +733,7 @@ def install(max_batch=16, precision=0, skip=()):
 
     def cg_run(self, num_cg_iter):
         p = self.problem
-        if type(p).__name__ == "ConvProblem" and not self.debug and self.direction_forget_factor == 0 and self.standard_alpha and \
+        if type(p).__name__ == "ConvProblem" and type(p).__module__.endswith("atom.optim") and not self.debug and self.direction_forget_factor == 0 and self.standard_alpha and \
                 self.cg_eps == 0.0 and num_cg_iter > 0 and _single(self.x) and _single(p.training_samples) and \
                 tuple(self.x[0].shape[-2:]) == (4, 4) and self.x[0].shape[0] == 1:
             act = _probe_activation(p.response_activation)
@@ -750,7 +750,9 @@ def install(max_batch=16, precision=0, skip=()):
 
     def gn_run(self, num_cg_iter, num_gn_iter=None):
         p = self.problem
-        if type(p).__name__ == "FactorizedConvProblem" and not self.debug and not self.analyze_convergence and self.standard_alpha and \
+        # ATOM's problem class only: ECO's first-frame problem (eco/optim.py:8) has the same name and keeps the reference implementation
+        if type(p).__name__ == "FactorizedConvProblem" and type(p).__module__.endswith("atom.optim") and not self.debug and \
+                not self.analyze_convergence and self.standard_alpha and \
                 self.cg_eps == 0.0 and self.direction_forget_factor == 0 and len(self.x) == 2 and _single(self.x[:1]) and \
                 _single(self.x[1:]) and _single(p.training_samples) and tuple(self.x[0].shape[-2:]) == (4, 4) and self.x[0].shape[0] == 1:
             its = [num_cg_iter] * num_gn_iter if isinstance(num_cg_iter, int) and num_gn_iter is not None else num_cg_iter

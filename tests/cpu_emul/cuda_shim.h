@@ -149,4 +149,6 @@ static inline void grid_barrier(unsigned*, unsigned& epoch) {
     __syncthreads();
 }
 
+static inline void eco_grid_barrier(unsigned* c, unsigned& epoch, unsigned&) { grid_barrier(c, epoch); }
+
 }  // namespace b200trk

@@ -1,0 +1,42 @@
+"""CUDA-event timing of the ECO row: b200trk_eco_filter_cg at ECO's default block sizes (parameter/eco/default.py:
+memory 200, CG_iter 5; deep block 64 channels on 15x8 Fourier coefficients, shallow block 16 channels on 63x32), with the roofline
+figures of DESIGN 4.9: bytes of sample memory per call, the reference's traffic (2 (1 + num_iter) sweeps), achieved GB/s.
+
+    python tools/eco_bench.py            (on a GPU box; writes gpurun_out/eco_bench.json)
+"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from pytracking_b200 import ops  # noqa: E402
+from tools.stage_bench import timeit  # noqa: E402
+
+BLOCKS = {"deep 15x8 x 200 x 64": (15, 8, 200, 64), "shallow 63x32 x 200 x 16": (63, 32, 200, 16)}
+ITERS = 5
+res = {}
+for name, (h, wh, n, c) in BLOCKS.items():
+    g = torch.Generator().manual_seed(h)
+    samples = torch.randn(h, wh, n, c, 2, generator=g).cuda()
+    sw = torch.rand(n, generator=g)
+    sw = (sw / sw.sum()).cuda()
+    yf = torch.rand(1, 1, h, wh, generator=g).cuda()
+    reg = torch.tensor([[0.0, 0.23, 0.0], [0.16, 0.78, 0.16], [0.0, 0.23, 0.0]]).view(1, 1, 3, 3).cuda()
+    hf = (0.01 * torch.randn(1, c, h, wh, 2, generator=g)).cuda()
+    new_xf = torch.randn(1, c, h, wh, 2, generator=g).cuda()
+    state = {"en": None, "st": None}
+
+    def run():
+        state["en"], state["st"] = ops.eco_filter_cg_(hf, samples, yf, sw, reg, state["en"], ITERS, new_xf, state["st"], False, True,
+                                                      (1 - 0.0075) ** 75, 0.0075, 0.3, 0.15)
+    med, mn = timeit(run, iters=20, warm=3)
+    mem = samples.numel() * 4
+    res[name] = {"us_median": med, "us_min": mn, "sample_memory_bytes": mem,
+                 "reference_sweep_bytes": 2 * (1 + ITERS) * mem,                      # A = forward + adjoint product, b - A x and 5 x A p
+                 "GBps_vs_one_read": mem / med / 1e3, "GBps_vs_reference_sweeps": 2 * (1 + ITERS) * mem / med / 1e3}
+    print("%-28s median %8.1f us  min %8.1f us   %.1f MB memory: %.0f GB/s once-per-call, %.0f GB/s in the reference's traffic"
+          % (name, med, mn, mem / 1e6, res[name]["GBps_vs_one_read"], res[name]["GBps_vs_reference_sweeps"]))
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(res, open("gpurun_out/eco_bench.json", "w"), indent=1)
