@@ -181,6 +181,17 @@ int b200trk_eco_filter_cg(float* filter, const float* samples, const float* yf, 
                           float direction_forget_factor, float precond_learning_rate, float precond_data_param,
                           float precond_reg_param, b200trk_stream_t stream);
 
+/* GaussNewtonCG.run(num_cg_iter, num_gn_iter) on ECO's FactorizedConvProblem -- the first-frame joint optimisation of the filter and
+ * the projection matrix, ONE feature block per call: pytracking/tracker/eco/optim.py:8-117 (residuals, ip_input, M1),
+ * pytracking/libs/optimization.py:328-421 (Fletcher-Reeves CG, state reset every GN iteration), wired at eco.py:155-162.
+ *   filter [1,C,H,Wh,2] and proj [Cin,C] are updated IN PLACE; samples [H,Wh,N,Cin,2] (init_training_samples[i], contiguous);
+ *   yf [1,1,H,Wh] real; sample_weights_sqrt [N]; reg_filter [1,1,reg_h,reg_w]; diag_M_filter [1,C,H,Wh] and diag_M_proj: the
+ *   problem's diagonal preconditioner (optim.py:27-33); projection_reg: params.projection_reg.                                   */
+int b200trk_eco_joint_gn(float* filter, float* proj, const float* samples, const float* yf, const float* sample_weights_sqrt,
+                         const float* reg_filter, int reg_h, int reg_w, const float* diag_M_filter, float diag_M_proj,
+                         float projection_reg, int H, int Wh, int N, int Cin, int C, int num_cg_iter, int num_gn_iter,
+                         b200trk_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Stage 1 -- backbone + classification head
  * ---------------------------------------------------------------------------------------------- */

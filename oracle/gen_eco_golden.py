@@ -8,7 +8,8 @@ regularisation filters from `dcf.get_reg_filter` and learning rates), three cons
 update in between, so that the CG state (p, rho, r_prev) carried between runs with direction_forget_factor != 0 and the
 running sample energy are covered.  Two parameter sets: the ECO default (Polak-Ribiere, forgetting) and Fletcher-Reeves
 with a state reset (direction_forget_factor = 0) and the non-standard alpha.
-Writes tests/golden/eco_cg.npz: per case / run / block the inputs and outputs of the run.
+Writes tests/golden/eco_cg.npz: per case / run / block the inputs and outputs of the run; `joint()` writes tests/golden/eco_joint.npz
+(the first-frame joint optimisation of filter and projection matrix).
 """
 import os
 import sys
@@ -112,5 +113,62 @@ def main():
     print("wrote eco_cg.npz with %d arrays" % len(out))
 
 
+JOINT_BLOCKS = [dict(H=9, Wh=5, Cin=24, C=16, reg=dict(reg_window_min=1e-4, reg_window_edge=10e-3, reg_sparsity_threshold=0.05)),
+                dict(H=7, Wh=4, Cin=80, C=64, reg=dict(reg_window_min=10e-4, reg_window_edge=50e-3, reg_sparsity_threshold=0.1))]
+JOINT_N = 6
+
+
+def joint():
+    """First-frame joint optimisation: the reference's FactorizedConvProblem (eco/optim.py:8-117) under GaussNewtonCG with ECO's settings
+    (eco.py:155-162: defaults of the optimiser = Fletcher-Reeves, state reset; init_CG_iter // init_GN_iter CG iterations per GN
+    iteration), J and J^T by autograd as the reference does.  Writes tests/golden/eco_joint.npz."""
+    from oracle import ref_shims
+    ref_shims.install()
+    from pytracking import TensorList, dcf
+    from pytracking.libs.optimization import GaussNewtonCG
+    from pytracking.tracker.eco.optim import FactorizedConvProblem
+    from pytracking.utils import TrackerParams
+
+    g = torch.Generator().manual_seed(23)
+    params = TrackerParams()
+    params.precond_data_param, params.precond_reg_param, params.precond_proj_param, params.projection_reg = 0.3, 0.15, 35, 5e-8
+    X, yf, rf, P, hf, sw = TensorList(), TensorList(), TensorList(), TensorList(), TensorList(), TensorList()
+    for b in JOINT_BLOCKS:
+        fp = TrackerParams()
+        fp.use_reg_window, fp.reg_window_power = True, 2
+        for k, v in b["reg"].items():
+            setattr(fp, k, v)
+        rf.append(dcf.get_reg_filter(torch.Tensor([240., 240.]), torch.Tensor([50., 64.]), fp))
+        yf.append(dcf.label_function(torch.Tensor([b["H"], 2 * b["Wh"] - 1]), torch.Tensor([1.0, 1.3])))
+        # the tracker hands over a permuted view (eco.py:133); the values are what matters here
+        X.append(torch.randn(b["H"], b["Wh"], JOINT_N, b["Cin"], 2, generator=g))
+        P.append(torch.linalg.qr(torch.randn(b["Cin"], b["Cin"], generator=g))[0][:, :b["C"]].clone())    # eco.py:117-120: orthonormal columns
+        hf.append(torch.zeros(1, b["C"], b["H"], b["Wh"], 2))                                             # eco.py:150-151
+        sw.append(torch.ones(1) / JOINT_N)                                                                 # eco.py:132
+    out = {}
+    for bi in range(len(JOINT_BLOCKS)):
+        k = "b%d/" % bi
+        out[k + "samples"], out[k + "yf"], out[k + "reg_filter"] = X[bi].numpy().copy(), yf[bi].numpy().copy(), rf[bi].numpy().copy()
+        out[k + "P_in"], out[k + "hf_in"] = P[bi].numpy().copy(), hf[bi].numpy().copy()
+        out[k + "sample_weights"] = np.full(JOINT_N, 1.0 / JOINT_N, np.float32)
+    prob = FactorizedConvProblem(X, yf, rf, P, params, sw)
+    var = hf.concat(P)
+    opt = GaussNewtonCG(prob, var, debug=False)
+    nb = len(JOINT_BLOCKS)
+    for bi in range(nb):
+        k = "b%d/" % bi
+        out[k + "diag_M_filter"] = prob.diag_M[bi].numpy().copy()                 # [1,C,H,Wh,1]
+        out[k + "diag_M_proj"] = np.float32(float(prob.diag_M[nb + bi]))
+        out[k + "sample_energy"] = prob.sample_energy[bi].numpy().copy()
+    opt.run(4, 3)                                                                 # 3 GN iterations x 4 CG iterations
+    for bi in range(nb):
+        k = "b%d/" % bi
+        out[k + "hf_out"], out[k + "P_out"] = var[bi].detach().numpy().copy(), var[nb + bi].detach().numpy().copy()
+    out["params"] = np.array([4, 3, 5e-8, 0.3, 0.15, 35.0], dtype=np.float64)   # num_cg, num_gn, projection_reg, precond data / reg / proj
+    np.savez_compressed(os.path.join(GOLDEN, "eco_joint.npz"), **out)
+    print("wrote eco_joint.npz with %d arrays" % len(out))
+
+
 if __name__ == "__main__":
     main()
+    joint()

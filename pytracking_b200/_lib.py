@@ -105,6 +105,7 @@ SIGNATURES = {
     "b200trk_atom_gn_joint": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _I, _F, _VP]),
     "b200trk_eco_filter_cg": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I,
                                    _F, _F, _F, _F, _VP]),
+    "b200trk_eco_joint_gn": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _F, _F, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "b200trk_net_create": (_I, [C.POINTER(_VP), _I, C.POINTER(ConvDesc), _I, _F, _I, _I, _I, _I]),
     "b200trk_net_destroy": (_I, [_VP]),
     "b200trk_net_forward": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _VP]),

@@ -1,5 +1,6 @@
-// ECO online filter optimiser -- device build and C ABI of the kernel in eco_cg_kernel.cuh (design notes there).
-//   reference: pytracking/tracker/eco/optim.py:140-208, pytracking/libs/optimization.py:72-163.
+// ECO optimisers -- device build and C ABI of the kernels in eco_cg_kernel.cuh (online FilterOptim.run) and
+// eco_joint_kernel.cuh (first-frame GaussNewtonCG on FactorizedConvProblem); design notes in the headers.
+//   reference: pytracking/tracker/eco/optim.py:8-208, pytracking/libs/optimization.py:72-163, 328-421.
 #include "common.cuh"
 
 namespace b200trk {
@@ -24,6 +25,7 @@ __device__ __forceinline__ void eco_grid_barrier(unsigned* counter, unsigned& ep
 }  // namespace b200trk
 
 #include "eco_cg_kernel.cuh"
+#include "eco_joint_kernel.cuh"
 
 namespace b200trk {
 
@@ -81,4 +83,41 @@ extern "C" int b200trk_eco_filter_cg(float* filter, const float* samples, const 
     if (pl.CPL == 1) return launch_eco<32, 1>(pl, P, st);
     if (pl.CPL == 2) return launch_eco<32, 2>(pl, P, st);
     return launch_eco<32, 4>(pl, P, st);
+}
+
+extern "C" int b200trk_eco_joint_gn(float* filter, float* proj, const float* samples, const float* yf, const float* sample_weights_sqrt,
+                                    const float* reg_filter, int reg_h, int reg_w, const float* diag_M_filter, float diag_M_proj,
+                                    float projection_reg, int H, int Wh, int N, int Cin, int C, int num_cg_iter, int num_gn_iter,
+                                    b200trk_stream_t stream) {
+    B200_REQUIRE(filter && proj && samples && yf && sample_weights_sqrt && reg_filter && diag_M_filter, "eco_joint_gn: null pointer");
+    B200_REQUIRE(H > 0 && Wh > 0 && N > 0 && N <= 1024 && Cin > 0 && C > 0 && C <= 512 && Cin <= 4096, "eco_joint_gn: H=%d Wh=%d N=%d Cin=%d C=%d", H, Wh, N, Cin, C);
+    B200_REQUIRE(reg_h >= 1 && reg_w >= 1 && reg_h <= 8 && reg_w <= 8 && reg_w <= Wh && reg_h <= H,
+                 "eco_joint_gn: regularisation filter %dx%d (at most 8x8 and not larger than the %dx%d half spectrum)", reg_h, reg_w, H, Wh);
+    B200_REQUIRE(num_cg_iter >= 0 && num_gn_iter >= 0 && (long long)num_cg_iter * num_gn_iter <= 100000, "eco_joint_gn: %d x %d iterations", num_cg_iter, num_gn_iter);
+    B200_REQUIRE(diag_M_proj > 0.f, "eco_joint_gn: diag_M_proj=%g", diag_M_proj);
+    if (num_gn_iter == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const EcoJointPlan pl = eco_joint_plan(H, Wh, N, Cin, C, num_cg_iter, num_gn_iter, device_sm_count(), 256);
+    B200_REQUIRE(pl.smem_bytes <= 227 * 1024, "eco_joint_gn: %zu bytes of shared memory (N=%d, Cin=%d, C=%d)", pl.smem_bytes, N, Cin, C);
+    char* ws = (char*)workspace(pl.ws_bytes, 7);
+    if (!ws) return 3;
+    const size_t field = (size_t)H * Wh * C * 2 * sizeof(float), nelem = (size_t)Cin * C;
+    EcoJointParams P{};
+    P.hf = filter; P.proj = proj; P.samples = samples; P.yf = yf; P.sw_sqrt = sample_weights_sqrt; P.reg_filter = reg_filter;
+    P.dMh_in = diag_M_filter; P.dMP = diag_M_proj; P.lambda = projection_reg;
+    P.H = H; P.Wh = Wh; P.N = N; P.Cin = Cin; P.C = C; P.rh = reg_h; P.rw = reg_w; P.num_cg = num_cg_iter; P.num_gn = num_gn_iter;
+    P.barrier = (unsigned*)ws;
+    P.h0w = (float2*)(ws + pl.off_fields); P.phw = (float2*)(ws + pl.off_fields + field); P.xhw = (float2*)(ws + pl.off_fields + 2 * field);
+    P.rhw = (float2*)(ws + pl.off_fields + 3 * field); P.qhw = (float2*)(ws + pl.off_fields + 4 * field);
+    P.dMh = (float*)(ws + pl.off_dMh); P.c0w = (float2*)(ws + pl.off_c0); P.wv = (float2*)(ws + pl.off_wv);
+    P.pP = (float*)(ws + pl.off_P); P.xP = P.pP + nelem; P.rP = P.xP + nelem; P.qP = P.rP + nelem;
+    P.dots = (float*)(ws + pl.off_dots);
+    P.res_slabs = pl.res_slabs; P.npx_max = pl.npx_max; P.EPB = pl.EPB; P.SPL = pl.SPL;
+    B200_CHECK_CUDA(cudaMemsetAsync(P.barrier, 0, 256, st));
+    auto kern = eco_joint_kernel;
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+    void* args[] = {(void*)&P};
+    B200_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(pl.grid), dim3(pl.block), args, pl.smem_bytes, st));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
 }

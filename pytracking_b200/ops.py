@@ -272,6 +272,31 @@ def eco_filter_cg_(filt, samples, yf, sample_weights, reg_filter, sample_energy,
     return sample_energy, state
 
 
+def eco_joint_gn_(filt, proj, samples, yf, sample_weights_sqrt, reg_filter, diag_M_filter, diag_M_proj, projection_reg, num_cg_iter,
+                  num_gn_iter):
+    """GaussNewtonCG.run(num_cg_iter, num_gn_iter) on ECO's FactorizedConvProblem for one feature block (eco/optim.py:8-117); updates
+    `filt` [1,C,H,Wh,2] and `proj` [Cin,C] in place."""
+    for name, t in (("filter", filt), ("projection_matrix", proj)):
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError("b200trk.eco_joint_gn_: '%s' must be a contiguous CUDA float32 tensor (updated in place)" % name)
+    _dev(filt, "filter")
+    samples, yf, sample_weights_sqrt, reg_filter, diag_M_filter = _dev(samples, "training_samples"), _dev(yf, "yf"), \
+        _dev(sample_weights_sqrt, "sample_weights_sqrt"), _dev(reg_filter, "reg_filter"), _dev(diag_M_filter, "diag_M")
+    if filt.dim() != 5 or filt.shape[0] != 1 or filt.shape[-1] != 2 or samples.dim() != 5 or proj.dim() != 2:
+        raise RuntimeError("b200trk.eco_joint_gn_: filter [1,C,H,Wh,2], projection matrix [Cin,C], training_samples [H,Wh,N,Cin,2] expected")
+    _, c, h, wh, _ = filt.shape
+    n, cin = samples.shape[2], samples.shape[3]
+    if tuple(samples.shape) != (h, wh, n, cin, 2) or tuple(proj.shape) != (cin, c) or yf.numel() != h * wh or \
+            sample_weights_sqrt.numel() != n or diag_M_filter.numel() != c * h * wh:
+        raise RuntimeError("b200trk.eco_joint_gn_: shapes of training_samples %s / projection matrix %s / yf / weights / diag_M do not "
+                           "match the filter %s" % (tuple(samples.shape), tuple(proj.shape), tuple(filt.shape)))
+    _lib.check(_lib.lib().b200trk_eco_joint_gn(
+        _p(filt), _p(proj), _p(samples), _p(yf), _p(sample_weights_sqrt), _p(reg_filter), int(reg_filter.shape[-2]), int(reg_filter.shape[-1]),
+        _p(diag_M_filter), float(diag_M_proj), float(projection_reg), h, wh, n, cin, c, int(num_cg_iter), int(num_gn_iter), _stream()),
+        "eco_joint_gn")
+    return filt, proj
+
+
 def atom_gn_joint_(filt, proj, samples, y, sample_weight, filter_reg, projection_reg, num_cg_iter, num_gn_iter,
                    activation="mlu", act_param=0.05, fletcher_reeves=True):
     """GaussNewtonCG.run(num_cg_iter, num_gn_iter) on FactorizedConvProblem; updates `filt` and `proj` in place."""

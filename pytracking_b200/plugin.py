@@ -768,6 +768,35 @@ def install(max_batch=16, precision=0, skip=()):
                     return
                 except NotImplementedError:
                     pass
+        # ECO's first-frame joint problem (pytracking/tracker/eco/optim.py:8-117): one launch per feature block
+        if type(p).__name__ == "FactorizedConvProblem" and type(p).__module__.endswith("eco.optim") and not self.debug and \
+                not self.analyze_convergence and self.fletcher_reeves and self.standard_alpha and self.cg_eps == 0.0 and \
+                self.direction_forget_factor == 0 and len(self.x) % 2 == 0 and len(self.x) > 0:
+            its = [num_cg_iter] * num_gn_iter if isinstance(num_cg_iter, int) and num_gn_iter is not None else num_cg_iter
+            nblk = len(self.x) // 2
+            ok = isinstance(its, (list, tuple)) and len(its) > 0 and len(set(its)) == 1 and len(p.training_samples) == nblk and \
+                getattr(p, "sample_weights_sqrt", None) is not None
+            if ok:
+                for b in range(nblk):
+                    hf, pm, xs, rf = self.x[b], self.x[nblk + b], p.training_samples[b], p.reg_filter[b]
+                    ok = ok and _inference(hf.detach(), pm.detach(), xs, rf, p.diag_M[b]) and hf.dim() == 5 and hf.shape[0] == 1 and \
+                        hf.shape[-1] == 2 and hf.is_contiguous() and pm.dim() == 2 and pm.is_contiguous() and xs.dim() == 5 and \
+                        tuple(xs.shape) == (hf.shape[2], hf.shape[3], xs.shape[2], pm.shape[0], 2) and pm.shape[1] == hf.shape[1] and \
+                        rf.dim() == 4 and rf.shape[-2] <= min(8, hf.shape[2]) and rf.shape[-1] <= min(8, hf.shape[3]) and \
+                        p.sample_weights_sqrt[b].numel() in (1, xs.shape[2]) and p.diag_M[b].numel() == hf.numel() // 2 and \
+                        4 * (524 + 17 * ((xs.shape[2] + 3) & ~3) + 8 * (4 * hf.shape[1] + 2 * pm.shape[0])) <= 226 * 1024   # ecoj_fixed_smem_floats
+            if ok:
+                for b in range(nblk):
+                    hf, pm, xs = self.x[b], self.x[nblk + b], p.training_samples[b]
+                    h, wh, n = hf.shape[2], hf.shape[3], xs.shape[2]
+                    ops.eco_joint_gn_(hf.detach(), pm.detach(), xs.contiguous(), p.yf[b][..., 0].reshape(1, 1, h, wh).contiguous(),
+                                      p.sample_weights_sqrt[b].reshape(-1).expand(n).contiguous(), p.reg_filter[b],
+                                      p.diag_M[b].reshape(1, hf.shape[1], h, wh).contiguous(), float(p.diag_M[nblk + b]),
+                                      float(p.params.projection_reg), int(its[0]), len(its))
+                self.x.detach_()
+                self.clear_temp()
+                _count("GaussNewtonCG.run[eco]")
+                return self.losses, self.residuals
         return ref_gn_run(self, num_cg_iter, num_gn_iter)
     _bind(oz.ConjugateGradient, "run", cg_run)
     _bind(oz.GaussNewtonCG, "run", gn_run)

@@ -3,6 +3,7 @@
 // semantics (a missing barrier is a real data race here as well, and ThreadSanitizer finds it).
 //   __syncthreads()        -> pthread barrier over the block's threads
 //   __shfl_xor_sync()      -> exchange through a per-warp buffer, one pthread barrier per shuffle (double buffered)
+//   __syncwarp()           -> pthread barrier over the warp's threads
 //   extern __shared__      -> B200_DYN_SMEM(name): one allocation per block
 //   b200trk::grid_barrier  -> bar.sync + pthread barrier over the blocks' leader threads + bar.sync
 // The device helpers of csrc/common.cuh used by the emulated kernels (warp_sum, block_sum, grid_barrier) are restated below with
@@ -122,6 +123,8 @@ static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
 
 template <class T>
 static inline T __ldcg(const T* p) { return *p; }
+
+static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&::cpu_emul::tctx->warp->bar); }
 
 namespace b200trk {
 

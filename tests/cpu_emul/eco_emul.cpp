@@ -3,6 +3,7 @@
 #include "cuda_shim.h"
 
 #include "../../pytracking_b200/csrc/eco_cg_kernel.cuh"
+#include "../../pytracking_b200/csrc/eco_joint_kernel.cuh"
 
 #include <cstdlib>
 
@@ -49,4 +50,28 @@ extern "C" void eco_emul_plan(int H, int Wh, int N, int C, int num_iter, int max
     const EcoPlan pl = eco_plan(H, Wh, N, C, num_iter, max_ctas, block);
     out[0] = pl.grid; out[1] = pl.G; out[2] = pl.CPL; out[3] = pl.GPP; out[4] = pl.res_slabs; out[5] = pl.npx_max;
     out[6] = (long long)pl.smem_bytes; out[7] = (long long)pl.ws_bytes;
+}
+
+// ---- first-frame joint optimisation (csrc/eco_joint_kernel.cuh) ----------------------------------------------------------------
+extern "C" int eco_emul_joint_gn(float* hf, float* proj, const float* samples, const float* yf, const float* sw_sqrt, const float* reg_filter,
+                                 int rh, int rw, const float* dMh, float dMP, float projection_reg, int H, int Wh, int N, int Cin, int C,
+                                 int num_cg, int num_gn, int max_ctas, int block, int force_res_slabs, int* plan_out) {
+    EcoJointPlan pl = eco_joint_plan(H, Wh, N, Cin, C, num_cg, num_gn, max_ctas, block);
+    if (force_res_slabs >= 0 && force_res_slabs < pl.res_slabs) pl.res_slabs = force_res_slabs;
+    std::vector<unsigned char> ws(pl.ws_bytes + 64, 0xCD);
+    unsigned char* w = ws.data();
+    const size_t field = (size_t)H * Wh * C * 2 * sizeof(float), nelem = (size_t)Cin * C;
+    EcoJointParams P{};
+    P.hf = hf; P.proj = proj; P.samples = samples; P.yf = yf; P.sw_sqrt = sw_sqrt; P.reg_filter = reg_filter; P.dMh_in = dMh;
+    P.dMP = dMP; P.lambda = projection_reg;
+    P.H = H; P.Wh = Wh; P.N = N; P.Cin = Cin; P.C = C; P.rh = rh; P.rw = rw; P.num_cg = num_cg; P.num_gn = num_gn;
+    P.h0w = (float2*)(w + pl.off_fields); P.phw = (float2*)(w + pl.off_fields + field); P.xhw = (float2*)(w + pl.off_fields + 2 * field);
+    P.rhw = (float2*)(w + pl.off_fields + 3 * field); P.qhw = (float2*)(w + pl.off_fields + 4 * field);
+    P.dMh = (float*)(w + pl.off_dMh); P.c0w = (float2*)(w + pl.off_c0); P.wv = (float2*)(w + pl.off_wv);
+    P.pP = (float*)(w + pl.off_P); P.xP = P.pP + nelem; P.rP = P.xP + nelem; P.qP = P.rP + nelem;
+    P.dots = (float*)(w + pl.off_dots); P.barrier = (unsigned*)w;
+    P.res_slabs = pl.res_slabs; P.npx_max = pl.npx_max; P.EPB = pl.EPB; P.SPL = pl.SPL;
+    if (plan_out) { plan_out[0] = pl.grid; plan_out[1] = pl.res_slabs; plan_out[2] = pl.npx_max; plan_out[3] = pl.EPB; plan_out[4] = pl.SPL; plan_out[5] = (int)pl.smem_bytes; }
+    cpu_emul::launch(eco_joint_kernel, (unsigned)pl.grid, (unsigned)pl.block, pl.smem_bytes, P);
+    return 0;
 }

@@ -34,3 +34,22 @@ def run_emulated(lib, g, case, run, bi, max_ctas, block, force_res):
     return max(errs), list(plan), (hf, p, rho)
 
 
+
+
+def run_emulated_joint(lib, g, bi, max_ctas, block, force_res):
+    """First-frame joint optimisation (csrc/eco_joint_kernel.cuh) of block `bi` of tests/golden/eco_joint.npz on the emulated grid."""
+    k = "b%d/" % bi
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    num_cg, num_gn, lam = int(g["params"][0]), int(g["params"][1]), float(g["params"][2])
+    hf, proj = g[k + "hf_in"].copy(), np.ascontiguousarray(g[k + "P_in"]).copy()
+    samples, yf, rf = np.ascontiguousarray(g[k + "samples"]), g[k + "yf"], g[k + "reg_filter"]
+    sw_sqrt = np.sqrt(g[k + "sample_weights"]).astype(np.float32)
+    dmh = np.ascontiguousarray(g[k + "diag_M_filter"].reshape(g[k + "diag_M_filter"].shape[:4]))
+    _, cc, h, wh, _ = hf.shape
+    n, cin = samples.shape[2], samples.shape[3]
+    plan = (C.c_int * 6)()
+    rc = lib.eco_emul_joint_gn(P(hf), P(proj), P(samples), P(yf), P(sw_sqrt), P(rf), rf.shape[2], rf.shape[3], P(dmh),
+                               C.c_float(float(g[k + "diag_M_proj"])), C.c_float(lam), h, wh, n, cin, cc, num_cg, num_gn, max_ctas, block,
+                               force_res, plan)
+    assert rc == 0
+    return max(rel(hf, g[k + "hf_out"]), rel(proj, g[k + "P_out"])), list(plan), (hf, proj)

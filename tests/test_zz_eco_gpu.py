@@ -175,3 +175,98 @@ def test_reference_filter_optim_above_the_engine():
     for r in range(3):
         for b in range(2):
             assert _rel(got[r][b], ref[r][b]) < 2e-4, (r, b, _rel(got[r][b], ref[r][b]))
+
+
+# ---- first-frame joint optimisation (b200trk_eco_joint_gn) -----------------------------------------------------------------------------
+JOINT_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eco_joint.npz")
+
+
+@pytest.mark.parametrize("bi", [0, 1])
+def test_eco_joint_gn_matches_reference_golden(bi):
+    """Against the reference's GaussNewtonCG on FactorizedConvProblem (J, J^T by autograd): 3 GN x 4 CG iterations."""
+    from pytracking_b200 import ops
+    g, k = np.load(JOINT_GOLD), "b%d/" % bi
+    D = lambda key: torch.from_numpy(np.ascontiguousarray(g[key])).cuda()
+    num_cg, num_gn, lam = int(g["params"][0]), int(g["params"][1]), float(g["params"][2])
+    hf, P = D(k + "hf_in"), D(k + "P_in")
+    ops.eco_joint_gn_(hf, P, D(k + "samples"), D(k + "yf"), D(k + "sample_weights").sqrt(), D(k + "reg_filter"),
+                      D(k + "diag_M_filter").reshape(1, hf.shape[1], hf.shape[2], hf.shape[3]).contiguous(), float(g[k + "diag_M_proj"]), lam,
+                      num_cg, num_gn)
+    torch.cuda.synchronize()
+    assert _rel(hf, g[k + "hf_out"]) < 2e-5 and _rel(P, g[k + "P_out"]) < 2e-5, (_rel(hf, g[k + "hf_out"]), _rel(P, g[k + "P_out"]))
+
+
+# ECO's first frame (parameter/eco/default.py): 30 augmented samples; deep block 256 -> 64 channels on 15x8 coefficients (one resident
+# slab per CTA), shallow block 96 -> 16 on 63x32 (14 coefficients per CTA, 9 slabs resident); 2 GN x 5 CG iterations here
+@pytest.mark.parametrize("h,wh,n,cin,c", [(15, 8, 30, 256, 64), (63, 32, 30, 96, 16), (11, 6, 9, 40, 32)])
+def test_eco_joint_gn_full_size_vs_oracle(h, wh, n, cin, c):
+    from oracle import eco_oracle as E
+    from pytracking_b200 import ops
+    g = torch.Generator().manual_seed(h * 7 + c)
+    samples = torch.randn(h, wh, n, cin, 2, generator=g)
+    P0 = torch.linalg.qr(torch.randn(cin, cin, generator=g))[0][:, :c].contiguous()
+    _, _, yf, reg, _, _ = _problem(h, wh, 2, 16, 2, seed=3)
+    sw = torch.full((n,), 1.0 / n)
+    hf0 = torch.zeros(1, c, h, wh, 2)
+    res = {}
+    for dt in (torch.float32, torch.float64):
+        res[dt] = E.joint_gn_run(hf0.to(dt), P0.to(dt), samples.to(dt), yf.to(dt), sw.to(dt), reg.to(dt), 5, 2)
+    dMh, dMP, _ = E.joint_precond(samples, P0, yf, reg, 0.3, 0.15, 35.0, 5e-8)
+    hf, P = hf0.clone().cuda(), P0.clone().cuda()
+    ops.eco_joint_gn_(hf, P, samples.cuda(), yf.cuda(), sw.sqrt().cuda(), reg.cuda(), dMh.reshape(1, c, h, wh).contiguous().cuda(), float(dMP),
+                      5e-8, 5, 2)
+    torch.cuda.synchronize()
+    spread = max(_rel(res[torch.float32][0], res[torch.float64][0]), _rel(res[torch.float32][1], res[torch.float64][1]))
+    tol = max(20 * spread, 2e-5)
+    assert _rel(hf, res[torch.float64][0]) < tol and _rel(P, res[torch.float64][1]) < tol, \
+        (_rel(hf, res[torch.float64][0]), _rel(P, res[torch.float64][1]), spread)
+    hf2, P2 = hf0.clone().cuda(), P0.clone().cuda()
+    ops.eco_joint_gn_(hf2, P2, samples.cuda(), yf.cuda(), sw.sqrt().cuda(), reg.cuda(), dMh.reshape(1, c, h, wh).contiguous().cuda(), float(dMP),
+                      5e-8, 5, 2)
+    assert torch.equal(hf, hf2) and torch.equal(P, P2)                  # bitwise determinism
+
+
+def test_reference_joint_optimizer_above_the_engine():
+    """The unmodified reference FactorizedConvProblem + GaussNewtonCG objects on CUDA tensors (two blocks, permuted sample view):
+    stock PyTorch autograd vs the plug-in seam."""
+    from baseline import ref_env
+    if not ref_env.reference_available():
+        pytest.skip("reference tree not staged (baseline/_ref)")
+    from oracle import ref_shims
+    ref_shims.install()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    from pytracking import TensorList
+    from pytracking.libs.optimization import GaussNewtonCG
+    from pytracking.tracker.eco.optim import FactorizedConvProblem
+    from pytracking.utils import TrackerParams
+    from pytracking_b200 import plugin
+
+    blocks = [(15, 8, 48, 16), (9, 5, 96, 64)]
+    n = 12
+
+    def make():
+        g = torch.Generator().manual_seed(9)
+        params = TrackerParams()
+        params.precond_data_param, params.precond_reg_param, params.precond_proj_param, params.projection_reg = 0.3, 0.15, 35, 5e-8
+        X = TensorList([torch.randn(n, cin, h, wh, 2, generator=g).cuda().permute(2, 3, 0, 1, 4) for (h, wh, cin, c) in blocks])   # eco.py:133
+        P = TensorList([torch.linalg.qr(torch.randn(cin, cin, generator=g))[0][:, :c].contiguous().cuda() for (h, wh, cin, c) in blocks])
+        hf = TensorList([torch.zeros(1, c, h, wh, 2).cuda() for (h, wh, cin, c) in blocks])
+        probs = [_problem(h, wh, 2, 16, 2, seed=3) for (h, wh, cin, c) in blocks]
+        prob = FactorizedConvProblem(X, TensorList([p[2].cuda() for p in probs]), TensorList([p[3].cuda() for p in probs]), P, params,
+                                     TensorList([torch.ones(1).cuda() / n for _ in blocks]))
+        var = hf.concat(P)
+        return GaussNewtonCG(prob, var, debug=False), var
+
+    opt, ref = make()
+    opt.run(5, 3)
+    plugin.install()
+    try:
+        before = plugin.stats.get("GaussNewtonCG.run[eco]", 0)
+        opt, got = make()
+        opt.run(5, 3)
+        assert plugin.stats.get("GaussNewtonCG.run[eco]", 0) == before + 1
+    finally:
+        plugin.uninstall()
+    for i in range(4):
+        assert _rel(got[i], ref[i]) < 1e-4, (i, _rel(got[i], ref[i]))
