@@ -802,8 +802,11 @@ def install(max_batch=16, precision=0, skip=()):
     _bind(oz.GaussNewtonCG, "run", gn_run)
 
     # ---- 5b. ECO: pytracking/tracker/eco/optim.py:140-163 (FilterOptim.run), one launch per feature block ----
-    eo = importlib.import_module("pytracking.tracker.eco.optim")
-    ref_eco_run = eo.FilterOptim.run
+    try:
+        eo = importlib.import_module("pytracking.tracker.eco.optim")
+    except ImportError:                                    # a checkout without the ECO tracker keeps every other seam
+        eo = None
+    ref_eco_run = eo.FilterOptim.run if eo is not None else None
 
     def _eco_block_ok(hf, xs, yf, sw, rf):
         return (_inference(hf, xs, yf, sw, rf) and hf.dim() == 5 and hf.shape[0] == 1 and hf.shape[-1] == 2 and
@@ -852,7 +855,8 @@ def install(max_batch=16, precision=0, skip=()):
         self.p, self.rho = tlist(ps), tlist(rhos)
         self.r_prev = None if self.fletcher_reeves else tlist(rps)
         _count("FilterOptim.run")
-    _bind(eo.FilterOptim, "run", eco_run)
+    if eo is not None:
+        _bind(eo.FilterOptim, "run", eco_run)
 
     # ---- 6. ToMP: ltr/models/transformer/transformer.py:90-96 ----
     tr = importlib.import_module("ltr.models.transformer.transformer")
