@@ -19,7 +19,7 @@ extern "C" int eco_emul_filter_cg(float* hf, const float* samples, const float* 
                                   float* rho_state, int has_state, int H, int Wh, int N, int C, int num_iter, int fletcher_reeves,
                                   int standard_alpha, float dff, float lr, float pdp, float prp, int max_ctas, int block,
                                   int force_res_slabs, int* plan_out) {
-    if (!(C == 16 || C == 32 || C == 64 || C == 128)) return 2;
+    if (!(C == 16 || C == 32 || C == 64 || C == 128) || rh > H || rw > Wh || rh > 8 || rw > 8) return 2;   // as b200trk_eco_filter_cg rejects
     EcoPlan pl = eco_plan(H, Wh, N, C, num_iter, max_ctas, block);
     if (force_res_slabs >= 0 && force_res_slabs < pl.res_slabs) pl.res_slabs = force_res_slabs;   // exercise the streaming path
     std::vector<unsigned char> ws(pl.ws_bytes + 64, 0xCD);
@@ -56,6 +56,7 @@ extern "C" void eco_emul_plan(int H, int Wh, int N, int C, int num_iter, int max
 extern "C" int eco_emul_joint_gn(float* hf, float* proj, const float* samples, const float* yf, const float* sw_sqrt, const float* reg_filter,
                                  int rh, int rw, const float* dMh, float dMP, float projection_reg, int H, int Wh, int N, int Cin, int C,
                                  int num_cg, int num_gn, int max_ctas, int block, int force_res_slabs, int* plan_out) {
+    if (rh > H || rw > Wh || rh > 8 || rw > 8) return 2;                                      // as b200trk_eco_joint_gn rejects
     EcoJointPlan pl = eco_joint_plan(H, Wh, N, Cin, C, num_cg, num_gn, max_ctas, block);
     if (force_res_slabs >= 0 && force_res_slabs < pl.res_slabs) pl.res_slabs = force_res_slabs;
     std::vector<unsigned char> ws(pl.ws_bytes + 64, 0xCD);

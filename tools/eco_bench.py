@@ -38,5 +38,21 @@ for name, (h, wh, n, c) in BLOCKS.items():
                  "GBps_vs_one_read": mem / med / 1e3, "GBps_vs_reference_sweeps": 2 * (1 + ITERS) * mem / med / 1e3}
     print("%-28s median %8.1f us  min %8.1f us   %.1f MB memory: %.0f GB/s once-per-call, %.0f GB/s in the reference's traffic"
           % (name, med, mn, mem / 1e6, res[name]["GBps_vs_one_read"], res[name]["GBps_vs_reference_sweeps"]))
+# first-frame joint optimisation: 30 augmented samples, init_CG_iter 100 / init_GN_iter 10 (parameter/eco/default.py)
+JOINT = {"deep 15x8 x 30 x 256 -> 64": (15, 8, 30, 256, 64), "shallow 63x32 x 30 x 96 -> 16": (63, 32, 30, 96, 16)}
+for name, (h, wh, n, cin, c) in JOINT.items():
+    g = torch.Generator().manual_seed(h + 1)
+    samples = torch.randn(h, wh, n, cin, 2, generator=g).cuda()
+    P0 = torch.linalg.qr(torch.randn(cin, cin, generator=g))[0][:, :c].contiguous().cuda()
+    yf = torch.rand(1, 1, h, wh, generator=g).cuda()
+    reg = torch.tensor([[0.0, 0.23, 0.0], [0.16, 0.78, 0.16], [0.0, 0.23, 0.0]]).view(1, 1, 3, 3).cuda()
+    sw_sqrt = torch.full((n,), (1.0 / n) ** 0.5).cuda()
+    dMh = (torch.rand(1, c, h, wh, generator=g) + 0.5).cuda()
+
+    def runj():
+        ops.eco_joint_gn_(torch.zeros(1, c, h, wh, 2).cuda(), P0.clone(), samples, yf, sw_sqrt, reg, dMh, 35.0, 5e-8, 10, 10)
+    med, mn = timeit(runj, iters=5, warm=2)
+    res["joint " + name] = {"us_median": med, "us_min": mn, "gn_x_cg": "10 x 10", "sample_bytes": samples.numel() * 4}
+    print("joint %-32s median %9.1f us  min %9.1f us   (10 GN x 10 CG, %.1f MB of samples)" % (name, med, mn, samples.numel() * 4 / 1e6))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/eco_bench.json", "w"), indent=1)
