@@ -245,8 +245,9 @@ __global__ void __launch_bounds__(256, 1) eco_cg_kernel(EcoParams P) {
             // Hermitian symmetry F(ky,-kx) = conj F(-ky,kx) (optim.py:181-183), zero outside the spectrum
             if (valid && !rhs) {
                 const int y = pix / Wh, x = pix - y * Wh;
-                for (int t = split; t < NTAP; t += GPP) {
-                    const int s = t / TW, u = t - s * TW;
+                int s = split / TW, u = split - s * TW;      // running (row, column) of tap t: no division in the loop
+                for (int t = split; t < NTAP; t += GPP, u += GPP) {
+                    while (u >= TW) { u -= TW; ++s; }
                     int yy = y + s - (P.rh - 1);
                     int kx = x + u - (P.rw - 1);
                     if (yy < 0 || yy >= H || kx >= Wh) continue;

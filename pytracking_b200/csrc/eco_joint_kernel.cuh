@@ -171,19 +171,22 @@ __global__ void __launch_bounds__(256, 1) eco_joint_kernel(EcoJointParams P) {
     auto reg_at = [&](const float2* field, int pix, int c, bool ext) -> float2 {
         const int y = pix / Wh, x = pix - y * Wh;
         float2 acc = make_float2(0.f, 0.f);
-        for (int t = 0; t < NTAP; ++t) {
-            int yy = y + t / TW - (P.rh - 1);
-            int kx = x + t % TW - (P.rw - 1);
-            if (yy < 0 || yy >= H || kx >= Wh) continue;
-            const bool cj = kx < 0;
-            if (cj) {
-                if (!ext) continue;
-                yy = H - 1 - yy; kx = -kx;
+        for (int s = 0, t = 0; s < 2 * P.rh - 1; ++s) {
+            const int y2 = y + s - (P.rh - 1);
+            if (y2 < 0 || y2 >= H) { t += TW; continue; }
+            for (int u = 0; u < TW; ++u, ++t) {
+                int yy = y2, kx = x + u - (P.rw - 1);
+                if (kx >= Wh) continue;
+                const bool cj = kx < 0;
+                if (cj) {
+                    if (!ext) continue;
+                    yy = H - 1 - yy; kx = -kx;
+                }
+                const float2 v = __ldcg(field + ((size_t)yy * Wh + kx) * C + c);
+                const float w = s_ac[t];
+                acc.x += w * v.x;
+                acc.y += cj ? -w * v.y : w * v.y;
             }
-            const float2 v = __ldcg(field + ((size_t)yy * Wh + kx) * C + c);
-            const float w = s_ac[t];
-            acc.x += w * v.x;
-            acc.y += cj ? -w * v.y : w * v.y;
         }
         return acc;
     };
@@ -202,16 +205,24 @@ __global__ void __launch_bounds__(256, 1) eco_joint_kernel(EcoJointParams P) {
             }
             __syncwarp();
             if (lin) {
-                // c0[n,c] = sum_i X[n,i] P[i,c]
-                for (int n = 0; n < N; ++n)
+                // c0[n,c] = sum_i X[n,i] P[i,c], eight sample rows per pass over the projection matrix
+                for (int n0 = 0; n0 < N; n0 += 8)
                     for (int c = lane; c < C; c += 32) {
-                        float ar = 0.f, ai = 0.f;
+                        float2 acc[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
                         for (int i = 0; i < Cin; ++i) {
-                            const float2 xv = S[(size_t)n * pitch + i];
                             const float pv = __ldcg(P.proj + (size_t)i * C + c);
-                            ar += xv.x * pv; ai += xv.y * pv;
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const int n = n0 + k < N ? n0 + k : N - 1;      // the tail repeats the last row (not stored)
+                                const float2 xv = S[(size_t)n * pitch + i];
+                                acc[k].x += xv.x * pv; acc[k].y += xv.y * pv;
+                            }
                         }
-                        c0[(size_t)n * C + c] = make_float2(ar, ai);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (n0 + k < N) c0[(size_t)(n0 + k) * C + c] = acc[k];
                     }
             } else {
                 // v[i] = sum_c dP[i,c] h0[c]
