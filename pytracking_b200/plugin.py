@@ -454,6 +454,43 @@ def install(max_batch=16, precision=0, skip=()):
     _patch_forward(opt.DiMPL2SteepestDescentGN, DiMPL2SteepestDescentGN,
                    lambda m: _key_common(m) + (m.gauss_sigma, m.hinge_threshold), "DiMPL2SteepestDescentGN.forward")
 
+    # ---- 2b. GNSteepestDescent over LinearFilterHinge (SuperDiMPSimple / KeepTrack classifiers): ltr/models/meta/steepestdescent.py:32-105,
+    #          ltr/models/target_classifier/residual_modules.py:89-135; call site pytracking/tracker/dimp_simple/dimp_simple.py:685-689 ----
+    sdm = importlib.import_module("ltr.models.meta.steepestdescent")
+    ref_gnsd_forward = sdm.GNSteepestDescent.forward
+
+    def gnsd_forward(self, meta_parameter, num_iter=None, *args, **kwargs):
+        rm = self.residual_module
+        is_list = isinstance(meta_parameter, list)
+        w = meta_parameter[0] if is_list and len(meta_parameter) == 1 else meta_parameter
+        feat, label, sw = kwargs.get("feat"), kwargs.get("train_label"), kwargs.get("sample_weight")
+        act = {"LeakyReluPar": "relu", "BentIdentPar": "bentpar"}.get(type(getattr(rm, "score_activation", None)).__name__)
+        if (type(rm).__name__ == "LinearFilterHinge" and type(rm).__module__.endswith("target_classifier.residual_modules") and
+                not args and not self.training and act is not None and isinstance(w, torch.Tensor) and
+                set(kwargs) <= {"feat", "bb", "train_label", "sample_weight", "is_distractor"} and kwargs.get("is_distractor") is None and
+                _inference(w, feat, label) and w.dim() == 4 and tuple(w.shape[-2:]) == (4, 4) and w.shape[0] == 1 and
+                (sw is None or (isinstance(sw, torch.Tensor) and sw.is_cuda)) and self._parameter_batch_dim == 0):
+            try:
+                f, _, swv = _one_sequence(feat, None, sw)
+                n, _, h, wd = f.shape
+                if label.numel() != n * (h + 1) * (wd + 1):
+                    raise NotImplementedError("b200trk GNSteepestDescent: train_label does not match the score map")
+                it = self.num_iter if num_iter is None else num_iter
+                reg = float(rm.filter_reg.detach().float().item()) if isinstance(rm.filter_reg, torch.Tensor) else float(rm.filter_reg)
+                apar = float(rm.score_activation.b) if act == "bentpar" else 1.0      # activation.py:47-55
+                wout, its, losses = ops.gn_sd_hinge(w, f, label.reshape(n, 1, h + 1, wd + 1).float(), swv, it, reg, float(rm.hinge_threshold),
+                                                    float(rm.activation_leak), act, apar, float(self.steplength_reg), return_iterates=True,
+                                                    compute_losses=bool(self.compute_losses))
+                tlist = type(meta_parameter) if is_list else None
+                wrap = (lambda t: tlist([t])) if is_list else (lambda t: t)
+                iterates = [wrap(its[i:i + 1]) for i in range(it + 1)]
+                _count("GNSteepestDescent.forward")
+                return wrap(wout), iterates, ([l for l in losses] if self.compute_losses else [])
+            except NotImplementedError:
+                pass
+        return ref_gnsd_forward(self, meta_parameter, num_iter, *args, **kwargs)
+    _bind(sdm.GNSteepestDescent, "forward", gnsd_forward)
+
     # ---- 3. net wrapper: pytracking/features/net_wrappers.py:71-75 + ltr/models/tracking/dimpnet.py:80-81 ----
     nw = importlib.import_module("pytracking.features.net_wrappers")
     dn = importlib.import_module("ltr.models.tracking.dimpnet")

@@ -10,7 +10,7 @@ from baseline import ref_env
 pytestmark = pytest.mark.skipif(not ref_env.reference_available(), reason="reference tree not staged (baseline/_ref)")
 
 SEAMS = ["filter.apply_filter", "filter.apply_feat_transpose", "dcf.max2d", "DiMPSteepestDescentGN.forward",
-         "PrDiMPSteepestDescentNewton.forward", "DiMPL2SteepestDescentGN.forward", "NetWithBackbone.extract_backbone",
+         "PrDiMPSteepestDescentNewton.forward", "DiMPL2SteepestDescentGN.forward", "GNSteepestDescent.forward", "NetWithBackbone.extract_backbone",
          "DiMPnet.extract_classification_feat", "functional._prroi_pooling", "operation.conv2d", "operation.conv1x1",
          "ConjugateGradient.run", "GaussNewtonCG.run", "FilterOptim.run", "Transformer.forward", "AtomIoUNet.get_iou_feat", "AtomIoUNet.predict_iou", "Head.extract_head_feat",
          "DenseBoxRegressor.forward", "FilterPredictor.predict_cls_bbreg_filters_parallel"]
@@ -131,3 +131,51 @@ def test_eco_filter_optim_falls_through_on_cpu(installed):
     for b, k in enumerate(k0):
         assert torch.allclose(filt[b], T(k + "hf_out"), rtol=0, atol=1e-6 * float(T(k + "hf_out").abs().max()))
     assert plugin.stats.get("FilterOptim.run", 0) == served
+
+
+def test_gn_steepest_descent_seam_glue(installed, monkeypatch):
+    """GNSteepestDescent.forward over LinearFilterHinge (the SuperDiMPSimple / KeepTrack classifier, dimp_simple.py:685-689): CPU calls
+    keep the reference (autograd) implementation; the seam's argument mapping and return structure are checked by putting the oracle
+    (explicit g = J^T r, h = J g) behind `ops.gn_sd_hinge` and comparing with the reference module itself."""
+    plugin, _ = installed
+    from oracle import dimp_oracle as O
+    from pytracking import TensorList
+    import ltr.models.meta.steepestdescent as sdm
+    import ltr.models.target_classifier.residual_modules as rm
+    from pytracking_b200 import ops, synth
+    g = torch.Generator().manual_seed(4)
+    n, c, hw = 5, 32, 18
+    feat = synth.make_clf_features(21, n, c, hw, hw)
+    label = torch.rand(n, 1, hw + 1, hw + 1, generator=g) * 0.6
+    sw = (torch.rand(n, generator=g) + 0.2).view(-1, 1, 1, 1)
+    w0 = torch.randn(1, c, 4, 4, generator=g) * 0.05
+    for act, thr, leak in (("relu", 0.05, 0.0), ("bentpar", 0.1, 0.1)):
+        mod = sdm.GNSteepestDescent(rm.LinearFilterHinge(init_filter_reg=0.1, hinge_threshold=thr, activation_leak=leak, score_act=act,
+                                                         act_param=0.7), num_iter=3, residual_batch_dim=1, compute_losses=True,
+                                    steplength_reg=0.02).eval()
+        served = plugin.stats.get("GNSteepestDescent.forward", 0)
+        with torch.no_grad():
+            ref_w, ref_its, ref_losses = mod(TensorList([w0.clone()]), num_iter=3, feat=feat, bb=None, train_label=label, sample_weight=sw)
+        assert plugin.stats.get("GNSteepestDescent.forward", 0) == served            # CPU tensors: the reference ran
+
+        def fake(weights, f, train_label, sample_weight, num_iter, filter_reg, hinge_threshold, activation_leak, score_act, act_param,
+                 steplength_reg, return_iterates=False, compute_losses=False, out=None):
+            assert train_label.shape == (n, 1, hw + 1, hw + 1) and sample_weight.shape == (n,) and f.shape == (n, c, hw, hw)
+            w, its, losses = O.gn_sd_hinge(weights, f, train_label[:, 0], sample_weight, filter_reg, num_iter, hinge_threshold, activation_leak,
+                                           score_act, act_param, steplength_reg, compute_losses)
+            return w, torch.cat(its, 0), torch.stack(losses) if compute_losses else None
+
+        with monkeypatch.context() as mp:
+            mp.setattr(ops, "gn_sd_hinge", fake)
+            mp.setattr(plugin, "_inference", lambda *ts: all(isinstance(t, torch.Tensor) and t.dtype == torch.float32 for t in ts))
+            mp.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+            with torch.no_grad():
+                w, its, losses = mod(TensorList([w0.clone()]), num_iter=3, feat=feat, bb=None, train_label=label, sample_weight=sw)
+                w_t, its_t, _ = mod(w0.clone(), num_iter=2, feat=feat, train_label=label, sample_weight=sw)       # a bare tensor in, a tensor out
+        assert plugin.stats.get("GNSteepestDescent.forward", 0) == served + 2
+        assert isinstance(w, TensorList) and len(its) == 4 and isinstance(its[0], TensorList) and its[0][0].shape == w0.shape and len(losses) == 4
+        assert isinstance(w_t, torch.Tensor) and len(its_t) == 3 and isinstance(its_t[0], torch.Tensor)
+        assert torch.allclose(w[0], ref_w[0], rtol=0, atol=2e-5 * float(ref_w[0].abs().max()))
+        for a, b in zip(its, ref_its):
+            assert torch.allclose(a[0], b[0], rtol=0, atol=2e-5 * float(ref_w[0].abs().max()))
+        assert torch.allclose(torch.stack(list(losses)), torch.stack([l.detach() for l in ref_losses]), rtol=2e-4)
