@@ -193,3 +193,27 @@ def build_tomp(device="cpu", overrides=None, seed=0):
     for k, v in dict(dict(target_not_found_threshold=-1e9), **(overrides or {})).items():
         setattr(params, k, v)
     return ToMP(params)
+
+
+def build_eco(device="cpu", overrides=None, seed=7):
+    """The reference ECO tracker (pytracking/tracker/eco/eco.py with parameter/eco/default.py: ResNet18m1 features `vggconv1` + `layer3`,
+    compressed to 16 + 64 channels, memory 200, first-frame GaussNewtonCG on FactorizedConvProblem, FilterOptim.run every
+    `train_skipping` frames) on a seeded random-init `resnet18_vggmconv1` (the checkpoint file cannot be fetched here)."""
+    from baseline import ref_env
+    ref_env.install()
+    import ltr.models.backbone.resnet18_vggm as rv
+    import pytracking.features.deep as deep
+    import pytracking.tracker.eco.eco as eco_mod
+    from pytracking.parameter.eco import default as P
+
+    def random_init(output_layers=None, path=None, **kwargs):        # deep.ResNet18m1.initialize calls this with a checkpoint path
+        torch.manual_seed(seed)
+        return rv.resnet18_vggmconv1(output_layers, path=None, **kwargs)
+    deep.resnet18_vggmconv1 = random_init
+    use_gpu = device != "cpu"
+    params = P.parameters()
+    params.use_gpu, params.device = use_gpu, ("cuda" if use_gpu else "cpu")
+    params.features.features[0].use_gpu = use_gpu
+    for k, v in (overrides or {}).items():
+        setattr(params, k, v)
+    return eco_mod.ECO(params)

@@ -817,7 +817,7 @@ def install(max_batch=16, precision=0, skip=()):
                 for b in range(nblk):
                     hf, pm, xs, rf = self.x[b], self.x[nblk + b], p.training_samples[b], p.reg_filter[b]
                     ok = ok and _inference(hf.detach(), pm.detach(), xs, rf, p.diag_M[b]) and hf.dim() == 5 and hf.shape[0] == 1 and \
-                        hf.shape[-1] == 2 and hf.is_contiguous() and pm.dim() == 2 and pm.is_contiguous() and xs.dim() == 5 and \
+                        hf.shape[-1] == 2 and hf.is_contiguous() and pm.dim() == 2 and xs.dim() == 5 and \
                         tuple(xs.shape) == (hf.shape[2], hf.shape[3], xs.shape[2], pm.shape[0], 2) and pm.shape[1] == hf.shape[1] and \
                         rf.dim() == 4 and rf.shape[-2] <= min(8, hf.shape[2]) and rf.shape[-1] <= min(8, hf.shape[3]) and \
                         p.sample_weights_sqrt[b].numel() in (1, xs.shape[2]) and p.diag_M[b].numel() == hf.numel() // 2 and \
@@ -826,10 +826,14 @@ def install(max_batch=16, precision=0, skip=()):
                 for b in range(nblk):
                     hf, pm, xs = self.x[b], self.x[nblk + b], p.training_samples[b]
                     h, wh, n = hf.shape[2], hf.shape[3], xs.shape[2]
-                    ops.eco_joint_gn_(hf.detach(), pm.detach(), xs.contiguous(), p.yf[b][..., 0].reshape(1, 1, h, wh).contiguous(),
+                    # eco.py:120 slices the projection matrix out of torch.svd's column-major U: run on a row-major copy, write it back
+                    pc = pm.detach() if pm.is_contiguous() else pm.detach().contiguous()
+                    ops.eco_joint_gn_(hf.detach(), pc, xs.contiguous(), p.yf[b][..., 0].reshape(1, 1, h, wh).contiguous(),
                                       p.sample_weights_sqrt[b].reshape(-1).expand(n).contiguous(), p.reg_filter[b],
                                       p.diag_M[b].reshape(1, hf.shape[1], h, wh).contiguous(), float(p.diag_M[nblk + b]),
                                       float(p.params.projection_reg), int(its[0]), len(its))
+                    if pc.data_ptr() != pm.data_ptr():
+                        pm.detach().copy_(pc)
                 self.x.detach_()
                 self.clear_temp()
                 _count("GaussNewtonCG.run[eco]")

@@ -1,0 +1,82 @@
+"""The UNMODIFIED reference ECO tracker (pytracking/tracker/eco/eco.py, parameter/eco/default.py, seeded random-init ResNet18m1 features)
+driven on the CPU over the synthetic sequence, once as it is and once with `plugin.install()` binding its two optimiser seams
+(`GaussNewtonCG.run` on the first frame, `FilterOptim.run` every `train_skipping` frames).  There is no GPU here, so the two library entry
+points are replaced by the oracle (oracle/eco_oracle.py -- itself pinned to the reference's golden vectors, as is the CUDA kernel source
+under the CPU shim, tests/test_eco_cpu.py): what this test pins is everything ABOVE the C ABI inside a real tracker run -- the tensors the
+tracker actually hands over (permuted sample views, the column-major projection matrix out of torch.svd, one-element sample weights, the
+aliased sample energy), the CG state carried from run to run in the reference's own attributes, `symmetrize_filter` on the tensors updated
+in place -- by requiring the same boxes and filters as the stock run."""
+import unittest.mock as um
+
+import pytest
+import torch
+
+from baseline import ref_env
+
+pytestmark = pytest.mark.skipif(not ref_env.reference_available(), reason="reference tree not staged (baseline/_ref)")
+
+OTHER_SEAMS = ("apply_filter", "apply_feat_transpose", "max2d", "forward", "extract_backbone", "extract_classification_feat", "get_iou_feat",
+               "predict_iou", "_prroi_pooling", "_import_prroi_pooling", "conv2d", "conv1x1", "extract_head_feat",
+               "predict_cls_bbreg_filters_parallel", "ConjugateGradient.run", "softmax_reg")
+OVERRIDES = dict(init_CG_iter=12, init_GN_iter=2, train_skipping=2, sample_memory_size=36)
+FRAMES = 6
+
+
+def _drive(frames, bb):
+    from baseline import ref_tracker
+    trk = ref_tracker.build_eco(overrides=OVERRIDES)
+    torch.manual_seed(0)                                            # the dropout augmentation of the first frame (eco.py:322-326)
+    trk.initialize(frames[0], {"init_bbox": list(bb)})
+    return [trk.track(frames[i])["target_bbox"] for i in range(1, FRAMES + 1)], trk
+
+
+def test_reference_eco_tracker_with_both_optimiser_seams_bound():
+    from oracle import eco_oracle as E
+    from pytracking_b200 import ops, plugin, synth
+    frames, bb = synth.make_sequence(0, num_frames=FRAMES)
+    ref_boxes, ref_trk = _drive(frames, bb)
+    calls = {"cg": 0, "gn": 0}
+
+    def oracle_cg(filt, samples, yf, sw, reg, energy, num_iter, new_xf=None, state=None, fletcher_reeves=False, standard_alpha=True,
+                  direction_forget_factor=0.0, precond_learning_rate=0.0075, precond_data_param=0.3, precond_reg_param=0.15):
+        calls["cg"] += 1
+        assert filt.is_contiguous() and samples.is_contiguous() and tuple(samples.shape[:2]) == tuple(filt.shape[2:4])
+        st = {} if not state else {"p": state["p"], "rho": float(state["rho"]), "r_prev": state.get("r_prev")}
+        x, en, st2 = E.filter_optim_run(filt, samples, yf, sw, reg, energy, st, num_iter, new_xf, precond_learning_rate, precond_data_param,
+                                        precond_reg_param, fletcher_reeves, standard_alpha, direction_forget_factor)
+        filt.copy_(x)                                               # the library updates filter and energy in place
+        if energy is not None:
+            energy.copy_(en)
+            en = energy
+        return en, {"p": st2["p"].contiguous(), "r_prev": st2["r_prev"], "rho": torch.as_tensor(st2["rho"]).reshape(1).float()}
+
+    def oracle_gn(filt, proj, samples, yf, sw_sqrt, reg, dMh, dMP, lam, ncg, ngn):
+        calls["gn"] += 1
+        assert proj.is_contiguous() and samples.is_contiguous() and sw_sqrt.numel() == samples.shape[2]
+        # the library takes the problem's preconditioner as an argument: it must be the one the oracle derives from the same inputs
+        dh, dp, _ = E.joint_precond(samples, proj, yf, reg, 0.3, 0.15, 35.0, lam)
+        assert torch.allclose(dh.reshape(-1), dMh.reshape(-1), rtol=1e-4) and abs(float(dp) - dMP) < 1e-4 * dMP
+        h, P, _ = E.joint_gn_run(filt, proj, samples, yf, sw_sqrt * sw_sqrt, reg, ncg, ngn, lam)
+        filt.copy_(h)
+        proj.copy_(P)
+        return filt, proj
+
+    with um.patch.object(ops, "eco_filter_cg_", oracle_cg), um.patch.object(ops, "eco_joint_gn_", oracle_gn), \
+            um.patch.object(plugin, "_inference", lambda *ts: all(isinstance(t, torch.Tensor) and t.dtype == torch.float32 for t in ts)), \
+            um.patch.object(torch.Tensor, "is_cuda", property(lambda self: True)):
+        plugin.install(skip=OTHER_SEAMS)
+        served = dict(plugin.stats)
+        try:
+            boxes, trk = _drive(frames, bb)
+        finally:
+            plugin.uninstall()
+    runs = sum(1 for f in range(2, FRAMES + 2) if f % OVERRIDES["train_skipping"] == 1)        # eco.py:244: frame_num % train_skipping == 1
+    assert calls == {"gn": 2, "cg": 2 * runs}, calls                                          # two feature blocks per optimiser call
+    assert plugin.stats.get("GaussNewtonCG.run[eco]", 0) == served.get("GaussNewtonCG.run[eco]", 0) + 1
+    assert plugin.stats.get("FilterOptim.run", 0) == served.get("FilterOptim.run", 0) + runs
+    for a, b in zip(ref_boxes, boxes):
+        assert max(abs(x - y) for x, y in zip(a, b)) < 1e-3, (a, b)
+    for b in range(2):
+        d = float((ref_trk.filter[b] - trk.filter[b]).abs().max() / ref_trk.filter[b].abs().max())
+        assert d < 2e-5, (b, d)
+        assert float((ref_trk.projection_matrix[b] - trk.projection_matrix[b]).abs().max()) < 2e-5

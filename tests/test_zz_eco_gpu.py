@@ -270,3 +270,42 @@ def test_reference_joint_optimizer_above_the_engine():
         plugin.uninstall()
     for i in range(4):
         assert _rel(got[i], ref[i]) < 1e-4, (i, _rel(got[i], ref[i]))
+
+
+def test_reference_eco_tracker_above_the_engine():
+    """The UNMODIFIED reference ECO tracker (parameter/eco/default.py, seeded random-init ResNet18m1 features) on the synthetic sequence:
+    stock PyTorch-CUDA vs `plugin.install()` (first-frame GaussNewtonCG.run and every FilterOptim.run on the library).  The CPU
+    counterpart with the oracle behind the entry points is tests/test_eco_tracker_cpu.py."""
+    from baseline import ref_env
+    if not ref_env.reference_available():
+        pytest.skip("reference tree not staged (baseline/_ref)")
+    from baseline import ref_tracker
+    from pytracking_b200 import plugin, synth
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    n_frames, ov = 12, dict(init_CG_iter=40, init_GN_iter=4, train_skipping=3)
+    frames, bb = synth.make_sequence(0, num_frames=n_frames)
+
+    def drive():
+        trk = ref_tracker.build_eco(device="cuda", overrides=ov)
+        torch.manual_seed(0)
+        trk.initialize(frames[0], {"init_bbox": list(bb)})
+        return [trk.track(frames[i])["target_bbox"] for i in range(1, n_frames + 1)], trk
+
+    try:
+        ref_boxes, ref_trk = drive()
+    except Exception as e:                                          # not the engine's doing: the stock reference on this torch build
+        pytest.skip("the reference ECO tracker does not run on stock PyTorch-CUDA here: %r" % (e,))
+    plugin.install()
+    try:
+        before = dict(plugin.stats)
+        boxes, trk = drive()
+        runs = sum(1 for f in range(2, n_frames + 2) if f % ov["train_skipping"] == 1)
+        assert plugin.stats.get("GaussNewtonCG.run[eco]", 0) == before.get("GaussNewtonCG.run[eco]", 0) + 1
+        assert plugin.stats.get("FilterOptim.run", 0) == before.get("FilterOptim.run", 0) + runs
+    finally:
+        plugin.uninstall()
+    for b in range(2):
+        assert _rel(trk.filter[b], ref_trk.filter[b]) < 1e-3, (b, _rel(trk.filter[b], ref_trk.filter[b]))
+    for a, b in zip(ref_boxes, boxes):
+        assert max(abs(x - y) for x, y in zip(a, b)) < 1e-2, (a, b)
