@@ -217,3 +217,29 @@ def build_eco(device="cpu", overrides=None, seed=7):
     for k, v in (overrides or {}).items():
         setattr(params, k, v)
     return eco_mod.ECO(params)
+
+
+def build_dimp_simple(device="cpu", overrides=None, seed=0):
+    """The reference DiMPSimple tracker (pytracking/tracker/dimp_simple/dimp_simple.py with parameter/dimp_simple/super_dimp_simple.py) on a
+    seeded random-init `dimpnet50_simple` built with the arguments of ltr/train_settings/dimp/super_dimp_simple.py:104-107: the classifier
+    whose online optimiser is GNSteepestDescent over LinearFilterHinge (also KeepTrack's base tracker)."""
+    from baseline import ref_env
+    ref_env.install()
+    from pytracking_b200 import synth
+    import ltr.models.tracking.dimpnet as dimpnet
+    from pytracking.parameter.dimp_simple import super_dimp_simple as P
+    from pytracking.tracker.dimp_simple.dimp_simple import DiMPSimple
+    torch.manual_seed(seed)
+    net = dimpnet.dimpnet50_simple(filter_size=4, backbone_pretrained=False, optim_iter=5, clf_feat_norm=True, clf_feat_blocks=0,
+                                   final_conv=True, out_feature_dim=512, optim_init_reg=0.1, score_act='relu', hinge_threshold=0.05,
+                                   activation_leak=0.1, frozen_backbone_layers=['conv1', 'bn1', 'layer1', 'layer2'])
+    missing, unexpected = net.load_state_dict(synth.make_backbone_state_dict("resnet50", seed=seed), strict=False)
+    assert not unexpected, unexpected
+    net.eval()
+    use_gpu = device != "cpu"
+    params = P.parameters()
+    params.use_gpu, params.device = use_gpu, ("cuda" if use_gpu else "cpu")
+    params.net = _wrap(net, use_gpu)
+    for k, v in dict(dict(target_not_found_threshold=-1e9), **(overrides or {})).items():
+        setattr(params, k, v)
+    return DiMPSimple(params)

@@ -80,3 +80,53 @@ def test_reference_eco_tracker_with_both_optimiser_seams_bound():
         d = float((ref_trk.filter[b] - trk.filter[b]).abs().max() / ref_trk.filter[b].abs().max())
         assert d < 2e-5, (b, d)
         assert float((ref_trk.projection_matrix[b] - trk.projection_matrix[b]).abs().max()) < 2e-5
+
+
+# every seam except GNSteepestDescent.forward stays on the reference in the DiMPSimple run below
+NOT_GNSD = ("apply_filter", "apply_feat_transpose", "max2d", "extract_backbone", "extract_classification_feat", "get_iou_feat", "predict_iou",
+            "_prroi_pooling", "_import_prroi_pooling", "conv2d", "conv1x1", "extract_head_feat", "predict_cls_bbreg_filters_parallel", "run",
+            "softmax_reg", "DiMPSteepestDescentGN.forward", "PrDiMPSteepestDescentNewton.forward", "DiMPL2SteepestDescentGN.forward",
+            "Transformer.forward", "DenseBoxRegressor.forward")
+
+
+def test_reference_dimp_simple_tracker_with_the_gn_steepest_descent_seam_bound():
+    """The UNMODIFIED reference DiMPSimple tracker (SuperDiMPSimple parameters, random-init dimpnet50_simple): its classifier's
+    GNSteepestDescent(LinearFilterHinge) module is called by `LinearFilter.get_filter` with a bare weight tensor and 5-D features on the
+    first frame and by `update_classifier` with a TensorList every `train_skipping` frames (dimp_simple.py:619,685).  Stock run vs
+    `plugin.install()` with the oracle behind `ops.gn_sd_hinge` (the CUDA kernel is pinned to the same oracle on the GPU)."""
+    from oracle import dimp_oracle as O
+    from oracle import ref_shims
+    ref_shims.install()
+    from baseline import ref_tracker
+    from pytracking_b200 import ops, plugin, synth
+    frames, bb = synth.make_sequence(0, num_frames=4)
+    ov = dict(train_skipping=2, use_iou_net=False)
+
+    def drive():
+        trk = ref_tracker.build_dimp_simple(overrides=ov)
+        torch.manual_seed(0)
+        trk.initialize(frames[0], {"init_bbox": list(bb)})
+        return [trk.track(frames[i])["target_bbox"] for i in range(1, 5)], trk
+
+    ref_boxes, ref_trk = drive()
+    calls = []
+
+    def oracle_op(weights, f, train_label, sample_weight, num_iter, filter_reg, hinge_threshold, activation_leak, score_act, act_param,
+                  steplength_reg, return_iterates=False, compute_losses=False, out=None):
+        calls.append((tuple(weights.shape), tuple(f.shape), num_iter))
+        w, its, losses = O.gn_sd_hinge(weights, f, train_label[:, 0], sample_weight, filter_reg, num_iter, hinge_threshold, activation_leak,
+                                       score_act, act_param, steplength_reg, compute_losses)
+        return w, torch.cat(its, 0), torch.stack(losses) if compute_losses else None
+
+    with um.patch.object(ops, "gn_sd_hinge", oracle_op), \
+            um.patch.object(plugin, "_inference", lambda *ts: all(isinstance(t, torch.Tensor) and t.dtype == torch.float32 for t in ts)), \
+            um.patch.object(torch.Tensor, "is_cuda", property(lambda self: True)):
+        assert [n.split(".")[-2:] for n in plugin.install(skip=NOT_GNSD)] == [["GNSteepestDescent", "forward"]]
+        try:
+            boxes, trk = drive()
+        finally:
+            plugin.uninstall()
+    assert len(calls) >= 3 and calls[0][2] == 10 and all(c[0] == (1, 512, 4, 4) and c[1][1:] == (512, 22, 22) for c in calls), calls
+    for a, b in zip(ref_boxes, boxes):
+        assert max(abs(x - y) for x, y in zip(a, b)) < 1e-3, (a, b)
+    assert float((ref_trk.target_filter - trk.target_filter).abs().max() / ref_trk.target_filter.abs().max()) < 2e-5
