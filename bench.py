@@ -390,8 +390,46 @@ def run_b200(args, rank, world, local_rank):
         "clocks": clocks,
     }
     if not args.no_baselines and world == 1:            # the CPU / stock-CUDA baselines are N = 1 lines
+        out["rooflines"] = roof + eco_rows(peaks)
         out.update(baselines(frames, bb, W))
     print(json.dumps(out))
+
+
+def eco_rows(peaks):
+    """SURVEY 8 row f4 (ECO's Fourier-domain optimisers), N = 1 / rank 0 only, AFTER the timed regions: tools/eco_bench.py in a subprocess
+    (its own CUDA context, bounded by a timeout), CUDA-event medians at ECO's default block sizes.  `achieved` counts the sample memory
+    once per call (the kernels keep the slabs resident in shared memory); `reference_sweep_bytes` is what the reference's mtimes pairs read."""
+    import subprocess
+    import tempfile
+    name = "eco_cg_kernel / eco_joint_kernel (ECO FilterOptim.run / first-frame GaussNewtonCG.run, SURVEY 8 f4)"
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "eco_bench.json")
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "eco_bench.py"), "--json", path], capture_output=True, text=True,
+                               timeout=240, cwd=ROOT)
+            if r.returncode != 0 or not os.path.exists(path):
+                return [{"kernel": name, "unavailable": ("rc=%d " % r.returncode) + r.stderr.strip()[-300:]}]
+            data = json.load(open(path))
+    except Exception as e:      # noqa: BLE001 -- a timing row must never take the bench line down
+        return [{"kernel": name, "unavailable": repr(e)[:300]}]
+    return eco_rows_from(data, peaks)
+
+
+def eco_rows_from(data, peaks):
+    rows = []
+    for k, v in data.items():
+        if k.startswith("joint "):
+            rows.append({"kernel": "eco_joint_kernel (ECO first frame, GaussNewtonCG 10 x 10 on FactorizedConvProblem; %s)" % k[6:], "bound": "hbm",
+                         "achieved": v["sample_bytes"] / (v["us_median"] * 1e-6) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": v["sample_bytes"] / (v["us_median"] * 1e-6) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                         "us_per_launch": v["us_median"], "algorithmic_bytes": v["sample_bytes"],
+                         "note": "100 CG iterations with 4 grid barriers each: barrier / latency bound, the HBM figure is nominal"})
+        else:
+            rows.append({"kernel": "eco_cg_kernel (ECO FilterOptim.run, 5 CG iterations; %s)" % k, "bound": "hbm", "achieved": v["GBps_vs_one_read"],
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": v["GBps_vs_one_read"] / peaks["hbm_gbs"], "traffic": None,
+                         "us_per_launch": v["us_median"], "algorithmic_bytes": v["sample_memory_bytes"],
+                         "reference_sweep_bytes": v["reference_sweep_bytes"], "achieved_vs_reference_sweeps": v["GBps_vs_reference_sweeps"]})
+    return rows
 
 
 def baselines(frames, bb, W):

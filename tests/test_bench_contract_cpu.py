@@ -68,3 +68,21 @@ def test_other_configuration_lines():
     for d in lines:
         _check_common(d)
         assert d["value"] > d["torch_cuda_baseline"]["value"] > 0 and d["cpu_baseline"]["value"] > 0
+
+
+def test_eco_rows_of_the_roofline_list():
+    """bench.py appends the ECO rows (tools/eco_bench.py in a subprocess) to `rooflines[]`: without a GPU the row says so instead of
+    raising; with the tool's output it carries the roofline keys."""
+    import bench
+    peaks = {"hbm_gbs": 6572.2}
+    rows = bench.eco_rows(peaks)
+    assert len(rows) == 1 and "unavailable" in rows[0]                       # no CUDA device here
+    data = {"deep 15x8 x 200 x 64": {"us_median": 40.0, "us_min": 39.0, "sample_memory_bytes": 12288000, "reference_sweep_bytes": 147456000,
+                                     "GBps_vs_one_read": 307.2, "GBps_vs_reference_sweeps": 3686.4},
+            "joint deep 15x8 x 30 x 256 -> 64": {"us_median": 2000.0, "us_min": 1990.0, "gn_x_cg": "10 x 10", "sample_bytes": 7372800}}
+    rows = bench.eco_rows_from(data, peaks)
+    assert len(rows) == 2
+    for r in rows:
+        assert {"kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "us_per_launch", "algorithmic_bytes"} <= set(r)
+        assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert abs(rows[0]["achieved"] - 12288000 / 40e-6 / 1e9) < 1e-6
