@@ -72,10 +72,11 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", type=int, default=0)
     ap.add_argument("--no-baselines", action="store_true", help="skip cpu_baseline / torch_cuda_baseline (profiling runs)")
-    ap.add_argument("--config", default="dimp50", choices=["dimp50", "prdimp50", "atom", "tomp101"],
+    ap.add_argument("--config", default="dimp50", choices=["dimp50", "prdimp50", "atom", "tomp101", "eco", "dimp_simple"],
                     help="dimp50 = BASELINE configs[1] (the metric of record, native whole-frame tracker); the others time the UNMODIFIED "
                          "reference tracker of BASELINE configs[2] / [0] / [3] above the engine (plugin.install()) against the same tracker "
-                         "on stock PyTorch-CUDA and PyTorch-CPU")
+                         "on stock PyTorch-CUDA and PyTorch-CPU; eco / dimp_simple: the same for the reference ECO and SuperDiMPSimple trackers "
+                         "(not BASELINE configurations; their optimiser seams were bound last)")
     return ap.parse_args()
 
 
@@ -476,6 +477,11 @@ OTHER = {
              "BASELINE configs[0]: parameter/atom/multiscale_no_iounet.py + train_skipping=1, target_not_found_threshold=-1e9", 10),
     "tomp101": ("ToMP-101 tracked frames/sec (ResNet-101, 6+6 layer transformer model predictor over 972 tokens x 2)",
                 "BASELINE configs[3]: parameter/tomp/tomp101.py + target_not_found_threshold=-1e9", 5),
+    # not BASELINE configurations (SURVEY 8 f4 and its "also"): the trackers whose optimiser seams round 2 added last
+    "eco": ("ECO tracked frames/sec (ResNet18m1 vggconv1 + layer3 features, 5 scales, Fourier-domain CG every frame over the 200-sample memory)",
+            "parameter/eco/default.py + train_skipping=1 (5 CG iterations every frame), random-init resnet18_vggmconv1", 10),
+    "dimp_simple": ("SuperDiMPSimple tracked frames/sec (352x352 crops, GNSteepestDescent over LinearFilterHinge, 2 iterations/frame)",
+                    "parameter/dimp_simple/super_dimp_simple.py + target_not_found_threshold=-1e9, train_skipping=1, use_iou_net=False", 10),
 }
 
 
@@ -486,6 +492,10 @@ def build_other(config, device):
         return ref_tracker.build_prdimp(device, use_iou_net=False, dropout=False)
     if config == "atom":
         return ref_tracker.build_atom(device)
+    if config == "eco":
+        return ref_tracker.build_eco(device, overrides=dict(train_skipping=1))
+    if config == "dimp_simple":
+        return ref_tracker.build_dimp_simple(device, overrides=dict(train_skipping=1, use_iou_net=False))
     return ref_tracker.build_tomp(device)
 
 
