@@ -59,6 +59,8 @@ extern "C" int b200trk_eco_filter_cg(float* filter, const float* samples, const 
     // optim.py:178-183 rebuilds reg_w - 1 negative-kx columns from the half spectrum and pads reg_h - 1 rows: both must exist
     B200_REQUIRE(reg_w <= Wh && reg_h <= H, "eco_filter_cg: regularisation filter %dx%d larger than the %dx%d half spectrum", reg_h, reg_w, H, Wh);
     B200_REQUIRE(num_iter >= 0 && num_iter <= 1024, "eco_filter_cg: num_iter=%d", num_iter);
+    B200_REQUIRE(((uintptr_t)samples & 15) == 0 && ((uintptr_t)filter & 7) == 0 && ((uintptr_t)p & 7) == 0 && (!r_prev || ((uintptr_t)r_prev & 7) == 0) &&
+                 (!new_xf || ((uintptr_t)new_xf & 7) == 0), "eco_filter_cg: samples must be 16-byte aligned, complex tensors 8-byte aligned");
     if (num_iter == 0) return 0;                                         // optim.py:141-142: nothing happens, not even the energy update
     cudaStream_t st = (cudaStream_t)stream;
     EcoPlan pl = eco_plan(H, Wh, N, C, num_iter, device_sm_count(), 256);
@@ -95,6 +97,7 @@ extern "C" int b200trk_eco_joint_gn(float* filter, float* proj, const float* sam
                  "eco_joint_gn: regularisation filter %dx%d (at most 8x8 and not larger than the %dx%d half spectrum)", reg_h, reg_w, H, Wh);
     B200_REQUIRE(num_cg_iter >= 0 && num_gn_iter >= 0 && (long long)num_cg_iter * num_gn_iter <= 100000, "eco_joint_gn: %d x %d iterations", num_cg_iter, num_gn_iter);
     B200_REQUIRE(diag_M_proj > 0.f, "eco_joint_gn: diag_M_proj=%g", diag_M_proj);
+    B200_REQUIRE(((uintptr_t)samples & 7) == 0 && ((uintptr_t)filter & 7) == 0, "eco_joint_gn: complex tensors must be 8-byte aligned");
     if (num_gn_iter == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const EcoJointPlan pl = eco_joint_plan(H, Wh, N, Cin, C, num_cg_iter, num_gn_iter, device_sm_count(), 256);
