@@ -62,10 +62,11 @@ struct EcoPlan {
 constexpr int ECO_MAX_TAPS = 15 * 15;     // (2rh-1)(2rw-1), rh, rw <= 8
 constexpr size_t ECO_SMEM_LIMIT = 227 * 1024 - 1024;
 
-// shared memory carve-up (floats): w2[ECO_MAX_TAPS+3], scal[8], red32[32], sw[N rounded to 4], mean[npx_max rounded to 4],
+// shared memory carve-up (floats): w2[ECO_MAX_TAPS+3], tapw[ECO_MAX_TAPS+3], tapi[ECO_MAX_TAPS+3], scal[8], red32[32], sw[N rounded to 4],
+// mean[npx_max rounded to 4],
 // red[NGRP*C*2], slabs[res_slabs*N*C*2]
 inline size_t eco_fixed_smem_floats(int N, int C, int npx_max, int ngrp) {
-    return (size_t)(ECO_MAX_TAPS + 3) + 8 + 32 + (size_t)((N + 3) & ~3) + (size_t)((npx_max + 3) & ~3) + (size_t)ngrp * C * 2;
+    return 3 * (size_t)(ECO_MAX_TAPS + 3) + 8 + 32 + (size_t)((N + 3) & ~3) + (size_t)((npx_max + 3) & ~3) + (size_t)ngrp * C * 2;
 }
 
 // Launch plan shared by the CUDA launcher and the CPU emulation harness.  `max_ctas` = co-resident CTAs (SM count).
@@ -121,7 +122,9 @@ __global__ void __launch_bounds__(256, 1) eco_cg_kernel(EcoParams P) {
     const int TW = 2 * P.rw - 1, NTAP = (2 * P.rh - 1) * TW;
 
     float* s_w2 = reinterpret_cast<float*>(smem_raw);
-    float* s_scal = s_w2 + ECO_MAX_TAPS + 3;
+    float* s_tapw = s_w2 + ECO_MAX_TAPS + 3;                 // non-zero taps of the composite filter, compacted: weight ...
+    int* s_tapi = reinterpret_cast<int*>(s_tapw + ECO_MAX_TAPS + 3);   // ... and (row << 8 | column)
+    float* s_scal = reinterpret_cast<float*>(s_tapi + ECO_MAX_TAPS + 3);
     float* s_red32 = s_scal + 8;
     float* s_sw = s_red32 + 32;
     float* s_mean = s_sw + ((N + 3) & ~3);
@@ -157,6 +160,13 @@ __global__ void __launch_bounds__(256, 1) eco_cg_kernel(EcoParams P) {
         for (int t = 0; t < P.rh * P.rw; ++t) e += P.reg_filter[t] * P.reg_filter[t];
         s_scal[7] = e;                                       // reg_energy (optim.py:125, eco.py:82)
     }
+    __syncthreads();
+    if (tid == 0) {                                          // the sparsified reg filters leave many composite taps exactly zero
+        int nz = 0;
+        for (int t = 0; t < NTAP; ++t)
+            if (s_w2[t] != 0.f) { s_tapw[nz] = s_w2[t]; s_tapi[nz] = ((t / TW) << 8) | (t % TW); ++nz; }
+        s_tapi[ECO_MAX_TAPS + 2] = nz;
+    }
     for (int n = tid; n < N; n += NT) s_sw[n] = P.sw[n];
     {
         const int nres = npx < P.res_slabs ? npx : P.res_slabs;
@@ -167,6 +177,7 @@ __global__ void __launch_bounds__(256, 1) eco_cg_kernel(EcoParams P) {
     }
     __syncthreads();
     const float reg_energy = s_scal[7];
+    const int NZ = s_tapi[ECO_MAX_TAPS + 2];
 
     // ---- prologue 1: running sample energy (optim.py:144-149), state import into the pixel-major fields ---------------------
     for (int e = tid; e < nel; e += NT) {
@@ -245,22 +256,33 @@ __global__ void __launch_bounds__(256, 1) eco_cg_kernel(EcoParams P) {
             // Hermitian symmetry F(ky,-kx) = conj F(-ky,kx) (optim.py:181-183), zero outside the spectrum
             if (valid && !rhs) {
                 const int y = pix / Wh, x = pix - y * Wh;
-                int s = split / TW, u = split - s * TW;      // running (row, column) of tap t: no division in the loop
-                for (int t = split; t < NTAP; t += GPP, u += GPP) {
-                    while (u >= TW) { u -= TW; ++s; }
-                    int yy = y + s - (P.rh - 1);
-                    int kx = x + u - (P.rw - 1);
-                    if (yy < 0 || yy >= H || kx >= Wh) continue;
-                    const bool cj = kx < 0;
-                    if (cj) { yy = H - 1 - yy; kx = -kx; }
-                    const float w = s_w2[t];
-                    const float2* src = field + ((size_t)yy * Wh + kx) * C + gl;
+                for (int t0 = split; t0 < NZ; t0 += 8 * GPP) {        // eight independent L2 requests in flight per channel
+                    float2 v[CPL][8];
+                    float wk[8];
+                    bool cjk[8];
 #pragma unroll
-                    for (int k = 0; k < CPL; ++k) {
-                        const float2 v = __ldcg(src + k * G);
-                        acc[k].x += w * v.x;
-                        acc[k].y += cj ? w * v.y : -w * v.y; // accumulated conjugated: the result is conj(acc)
+                    for (int q = 0; q < 8; ++q) {
+                        const int t = t0 + q * GPP;
+                        bool ok = t < NZ;
+                        const int code = ok ? s_tapi[t] : 0;
+                        int yy = y + (code >> 8) - (P.rh - 1);
+                        int kx = x + (code & 255) - (P.rw - 1);
+                        ok = ok && yy >= 0 && yy < H && kx < Wh;
+                        cjk[q] = kx < 0;
+                        if (cjk[q]) { yy = H - 1 - yy; kx = -kx; }
+                        if (!ok) { yy = y; kx = x; }            // keep the (unused) address inside the field
+                        wk[q] = ok ? s_tapw[t] : 0.f;
+                        const float2* src = field + ((size_t)yy * Wh + kx) * C + gl;
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) v[k][q] = ok ? __ldcg(src + k * G) : make_float2(0.f, 0.f);
                     }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) {
+                            acc[k].x += wk[q] * v[k][q].x;
+                            acc[k].y += cjk[q] ? wk[q] * v[k][q].y : -wk[q] * v[k][q].y;   // accumulated conjugated: the result is conj(acc)
+                        }
                 }
             }
             if (GPP > 1) {

@@ -41,21 +41,23 @@ struct EcoJointParams {
     float* dots;
     unsigned* barrier;
     int res_slabs, npx_max, EPB, SPL;      // resident slabs per CTA; elements per tile, coefficient splits per element
+    int stage_pm;                          // the projection matrix / its CG direction staged in shared memory per phase
 };
 
 struct EcoJointPlan {
-    int grid, block, res_slabs, npx_max, EPB, SPL;
+    int grid, block, res_slabs, npx_max, EPB, SPL, stage_pm;
     size_t smem_bytes, ws_bytes, off_fields, off_dMh, off_c0, off_wv, off_P, off_dots;
 };
 
 constexpr int ECOJ_MAX_TAPS = 15 * 15;
 
-// shared memory (floats): acorr[228], scal[8], red32[32], sw[N4], per warp {h0[2C], ph[2C], v[2Cin], u[2N4]}, tile partials [block],
-// slabs [res][N][(Cin+1)*2]
+// shared memory (floats): acorr[228], tapw[228], tapi[228], scal[8], red32[32], sw[N4], per warp {h0[2C], ph[2C], v[2Cin], u[2N4]},
+// tile partials [block], staged matrix [Cin][C+1] (when it fits), slabs [res][N][(Cin+1)*2]
 inline size_t ecoj_fixed_smem_floats(int N, int Cin, int C, int block) {
     const int N4 = (N + 3) & ~3;
-    return (size_t)(ECOJ_MAX_TAPS + 3) + 8 + 32 + N4 + (size_t)(block / 32) * (4 * C + 2 * Cin + 2 * N4) + block;
+    return 3 * (size_t)(ECOJ_MAX_TAPS + 3) + 8 + 32 + N4 + (size_t)(block / 32) * (4 * C + 2 * Cin + 2 * N4) + block;
 }
+inline size_t ecoj_stage_floats(int Cin, int C) { return ((size_t)Cin * (C + 1) + 1) & ~(size_t)1; }
 
 inline EcoJointPlan eco_joint_plan(int H, int Wh, int N, int Cin, int C, int num_cg, int num_gn, int max_ctas, int block) {
     EcoJointPlan pl{};
@@ -63,9 +65,13 @@ inline EcoJointPlan eco_joint_plan(int H, int Wh, int N, int Cin, int C, int num
     pl.block = block;
     pl.grid = P < max_ctas ? P : max_ctas;
     pl.npx_max = (P + pl.grid - 1) / pl.grid;
-    const size_t fixed = ecoj_fixed_smem_floats(N, Cin, C, block) * sizeof(float);
+    size_t fixed = ecoj_fixed_smem_floats(N, Cin, C, block) * sizeof(float);
     const size_t slab = (size_t)N * (Cin + 1) * 2 * sizeof(float);
     const size_t limit = 227 * 1024 - 1024;
+    // the [Cin, C] matrix every coefficient multiplies with (P when linearising, the direction dP in the CG iterations) first ...
+    pl.stage_pm = fixed + ecoj_stage_floats(Cin, C) * sizeof(float) <= limit ? 1 : 0;
+    if (pl.stage_pm) fixed += ecoj_stage_floats(Cin, C) * sizeof(float);
+    // ... then as many sample slabs as still fit
     size_t res = fixed < limit ? (limit - fixed) / slab : 0;
     if (res > (size_t)pl.npx_max) res = (size_t)pl.npx_max;
     pl.res_slabs = (int)res;
@@ -108,7 +114,9 @@ __global__ void __launch_bounds__(256, 1) eco_joint_kernel(EcoJointParams P) {
     const int PITCH = Cin + 1;                               // float2 per slab row in shared memory
 
     float* s_ac = reinterpret_cast<float*>(smem_raw);        // autocorrelation of the regularisation filter
-    float* s_scal = s_ac + ECOJ_MAX_TAPS + 3;
+    float* s_tapw = s_ac + ECOJ_MAX_TAPS + 3;                // its non-zero taps, compacted: weight ...
+    int* s_tapi = reinterpret_cast<int*>(s_tapw + ECOJ_MAX_TAPS + 3);   // ... and (row << 8 | column)
+    float* s_scal = reinterpret_cast<float*>(s_tapi + ECOJ_MAX_TAPS + 3);
     float* s_red32 = s_scal + 8;
     float* s_sw = s_red32 + 32;
     float* s_warp = s_sw + N4;                               // per-warp scratch
@@ -118,7 +126,9 @@ __global__ void __launch_bounds__(256, 1) eco_joint_kernel(EcoJointParams P) {
     float2* s_v = s_ph + C;
     float2* s_u = s_v + Cin;
     float* s_tile = s_warp + (size_t)NW * WARP_FLOATS;       // [NT] partial sums of the projection-gradient tiles
-    float2* s_slab = reinterpret_cast<float2*>(s_tile + NT);
+    float* s_pm = s_tile + NT;                               // [Cin][C+1] staged matrix (P.stage_pm)
+    const int PMP = C + 1;
+    float2* s_slab = reinterpret_cast<float2*>(s_pm + (P.stage_pm ? (((size_t)Cin * PMP + 1) & ~(size_t)1) : 0));
 
     const int p0 = (int)(((long long)cta * NPIX) / nb), p1 = (int)(((long long)(cta + 1) * NPIX) / nb);
     const int npx = p1 - p0;
@@ -143,6 +153,13 @@ __global__ void __launch_bounds__(256, 1) eco_joint_kernel(EcoJointParams P) {
         s_ac[t] = acc;
     }
     for (int n = tid; n < N; n += NT) s_sw[n] = P.sw_sqrt[n];
+    __syncthreads();
+    if (tid == 0) {                                          // the sparsified reg filters leave many taps exactly zero
+        int nz = 0;
+        for (int t = 0; t < NTAP; ++t)
+            if (s_ac[t] != 0.f) { s_tapw[nz] = s_ac[t]; s_tapi[nz] = ((t / TW) << 8) | (t % TW); ++nz; }
+        s_tapi[ECOJ_MAX_TAPS + 2] = nz;
+    }
     {
         const int nres = npx < P.res_slabs ? npx : P.res_slabs;
         const float2* src = reinterpret_cast<const float2*>(P.samples) + (size_t)p0 * N * Cin;
@@ -170,23 +187,28 @@ __global__ void __launch_bounds__(256, 1) eco_joint_kernel(EcoJointParams P) {
     // by Hermitian symmetry when `ext` (the residual value), zero otherwise (the Jacobian)
     auto reg_at = [&](const float2* field, int pix, int c, bool ext) -> float2 {
         const int y = pix / Wh, x = pix - y * Wh;
+        const int NZ = s_tapi[ECOJ_MAX_TAPS + 2];
         float2 acc = make_float2(0.f, 0.f);
-        for (int s = 0, t = 0; s < 2 * P.rh - 1; ++s) {
-            const int y2 = y + s - (P.rh - 1);
-            if (y2 < 0 || y2 >= H) { t += TW; continue; }
-            for (int u = 0; u < TW; ++u, ++t) {
-                int yy = y2, kx = x + u - (P.rw - 1);
-                if (kx >= Wh) continue;
+        for (int t0 = 0; t0 < NZ; t0 += 8) {                 // eight independent L2 requests in flight
+            float2 v[8];
+            float wk[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int t = t0 + q;
+                bool ok = t < NZ;
+                const int code = ok ? s_tapi[t] : 0;
+                int yy = y + (code >> 8) - (P.rh - 1);
+                int kx = x + (code & 255) - (P.rw - 1);
+                ok = ok && yy >= 0 && yy < H && kx < Wh && (ext || kx >= 0);
                 const bool cj = kx < 0;
-                if (cj) {
-                    if (!ext) continue;
-                    yy = H - 1 - yy; kx = -kx;
-                }
-                const float2 v = __ldcg(field + ((size_t)yy * Wh + kx) * C + c);
-                const float w = s_ac[t];
-                acc.x += w * v.x;
-                acc.y += cj ? -w * v.y : w * v.y;
+                if (cj) { yy = H - 1 - yy; kx = -kx; }
+                if (!ok) { yy = y; kx = x; }
+                wk[q] = ok ? s_tapw[t] : 0.f;
+                v[q] = ok ? __ldcg(field + ((size_t)yy * Wh + kx) * C + c) : make_float2(0.f, 0.f);
+                if (cj) v[q].y = -v[q].y;
             }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { acc.x += wk[q] * v[q].x; acc.y += wk[q] * v[q].y; }
         }
         return acc;
     };
@@ -194,6 +216,14 @@ __global__ void __launch_bounds__(256, 1) eco_joint_kernel(EcoJointParams P) {
     // coefficient-local part of J^T J (dh, dP) (lin == false) or of J^T f (lin == true, which also recomputes c0 = X P) for the
     // coefficients of this CTA, one warp per coefficient: writes gh -> dst and the w vector -> wv
     auto pixel_phase = [&](bool lin, float2* dst) {
+        const float* pm = lin ? P.proj : P.pP;               // the matrix of this phase, L2 resident ...
+        int pmp = C;
+        if (P.stage_pm) {                                    // ... staged once per phase for all coefficients of the CTA
+            for (int e = tid; e < NE; e += NT) s_pm[(size_t)(e / C) * PMP + e % C] = __ldcg(pm + e);
+            __syncthreads();
+            pm = s_pm;
+            pmp = PMP;
+        }
         for (int j = warp; j < npx; j += NW) {
             const int pix = p0 + j;
             int pitch;
@@ -212,7 +242,7 @@ __global__ void __launch_bounds__(256, 1) eco_joint_kernel(EcoJointParams P) {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
                         for (int i = 0; i < Cin; ++i) {
-                            const float pv = __ldcg(P.proj + (size_t)i * C + c);
+                            const float pv = P.stage_pm ? pm[(size_t)i * pmp + c] : __ldcg(pm + (size_t)i * pmp + c);
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
                                 const int n = n0 + k < N ? n0 + k : N - 1;      // the tail repeats the last row (not stored)
@@ -229,7 +259,7 @@ __global__ void __launch_bounds__(256, 1) eco_joint_kernel(EcoJointParams P) {
                 for (int i = lane; i < Cin; i += 32) {
                     float ar = 0.f, ai = 0.f;
                     for (int c = 0; c < C; ++c) {
-                        const float pv = __ldcg(P.pP + (size_t)i * C + c);
+                        const float pv = P.stage_pm ? pm[(size_t)i * pmp + c] : __ldcg(pm + (size_t)i * pmp + c);
                         ar += pv * s_h0[c].x; ai += pv * s_h0[c].y;
                     }
                     s_v[i] = make_float2(ar, ai);
@@ -298,10 +328,16 @@ __global__ void __launch_bounds__(256, 1) eco_joint_kernel(EcoJointParams P) {
             if (act) {
                 const int i = e / C, c = e - i * C;
                 const int q0 = (int)(((long long)sp * NPIX) / SPL), q1 = (int)(((long long)(sp + 1) * NPIX) / SPL);
-                for (int q = q0; q < q1; ++q) {
-                    const float2 hv = __ldcg(P.h0w + (size_t)q * C + c);
-                    const float2 wv = __ldcg(P.wv + (size_t)q * Cin + i);
-                    acc += hv.x * wv.x + hv.y * wv.y;
+                for (int q = q0; q < q1; q += 8) {           // sixteen independent L2 requests in flight, summed in coefficient order
+                    float2 hv[8], wv[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const bool ok = q + k < q1;
+                        hv[k] = ok ? __ldcg(P.h0w + (size_t)(q + k) * C + c) : make_float2(0.f, 0.f);
+                        wv[k] = ok ? __ldcg(P.wv + (size_t)(q + k) * Cin + i) : make_float2(0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc += hv[k].x * wv[k].x + hv[k].y * wv[k].y;
                 }
             }
             s_tile[tid] = acc;

@@ -821,7 +821,7 @@ def install(max_batch=16, precision=0, skip=()):
                         tuple(xs.shape) == (hf.shape[2], hf.shape[3], xs.shape[2], pm.shape[0], 2) and pm.shape[1] == hf.shape[1] and \
                         rf.dim() == 4 and rf.shape[-2] <= min(8, hf.shape[2]) and rf.shape[-1] <= min(8, hf.shape[3]) and \
                         p.sample_weights_sqrt[b].numel() in (1, xs.shape[2]) and p.diag_M[b].numel() == hf.numel() // 2 and \
-                        4 * (524 + 17 * ((xs.shape[2] + 3) & ~3) + 8 * (4 * hf.shape[1] + 2 * pm.shape[0])) <= 226 * 1024   # ecoj_fixed_smem_floats
+                        4 * (980 + 17 * ((xs.shape[2] + 3) & ~3) + 8 * (4 * hf.shape[1] + 2 * pm.shape[0])) <= 226 * 1024   # ecoj_fixed_smem_floats
             if ok:
                 for b in range(nblk):
                     hf, pm, xs = self.x[b], self.x[nblk + b], p.training_samples[b]
