@@ -115,7 +115,7 @@ extern "C" int b200trk_eco_joint_gn(float* filter, float* proj, const float* sam
     P.dMh = (float*)(ws + pl.off_dMh); P.c0w = (float2*)(ws + pl.off_c0); P.wv = (float2*)(ws + pl.off_wv);
     P.pP = (float*)(ws + pl.off_P); P.xP = P.pP + nelem; P.rP = P.xP + nelem; P.qP = P.rP + nelem;
     P.dots = (float*)(ws + pl.off_dots);
-    P.res_slabs = pl.res_slabs; P.npx_max = pl.npx_max; P.EPB = pl.EPB; P.SPL = pl.SPL; P.stage_pm = pl.stage_pm;
+    P.res_slabs = pl.res_slabs; P.npx_max = pl.npx_max; P.EPB = pl.EPB; P.SPL = pl.SPL; P.stage_pm = pl.stage_pm; P.wide = pl.wide;
     B200_CHECK_CUDA(cudaMemsetAsync(P.barrier, 0, 256, st));
     auto kern = eco_joint_kernel;
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));

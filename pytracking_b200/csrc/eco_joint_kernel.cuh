@@ -42,10 +42,11 @@ struct EcoJointParams {
     unsigned* barrier;
     int res_slabs, npx_max, EPB, SPL;      // resident slabs per CTA; elements per tile, coefficient splits per element
     int stage_pm;                          // the projection matrix / its CG direction staged in shared memory per phase
+    int wide;                              // the whole CTA works on one coefficient at a time (few coefficients per CTA)
 };
 
 struct EcoJointPlan {
-    int grid, block, res_slabs, npx_max, EPB, SPL, stage_pm;
+    int grid, block, res_slabs, npx_max, EPB, SPL, stage_pm, wide;
     size_t smem_bytes, ws_bytes, off_fields, off_dMh, off_c0, off_wv, off_P, off_dots;
 };
 
@@ -65,6 +66,7 @@ inline EcoJointPlan eco_joint_plan(int H, int Wh, int N, int Cin, int C, int num
     pl.block = block;
     pl.grid = P < max_ctas ? P : max_ctas;
     pl.npx_max = (P + pl.grid - 1) / pl.grid;
+    pl.wide = pl.npx_max * 2 <= block / 32 ? 1 : 0;
     size_t fixed = ecoj_fixed_smem_floats(N, Cin, C, block) * sizeof(float);
     const size_t slab = (size_t)N * (Cin + 1) * 2 * sizeof(float);
     const size_t limit = 227 * 1024 - 1024;
@@ -121,10 +123,7 @@ __global__ void __launch_bounds__(256, 1) eco_joint_kernel(EcoJointParams P) {
     float* s_sw = s_red32 + 32;
     float* s_warp = s_sw + N4;                               // per-warp scratch
     const int WARP_FLOATS = 4 * C + 2 * Cin + 2 * N4;
-    float2* s_h0 = reinterpret_cast<float2*>(s_warp + (size_t)warp * WARP_FLOATS);
-    float2* s_ph = s_h0 + C;
-    float2* s_v = s_ph + C;
-    float2* s_u = s_v + Cin;
+    float2* s_h0 = reinterpret_cast<float2*>(s_warp + (size_t)warp * WARP_FLOATS);   // {h0[C], ph[C], v[Cin], u[N4]} of this warp
     float* s_tile = s_warp + (size_t)NW * WARP_FLOATS;       // [NT] partial sums of the projection-gradient tiles
     float* s_pm = s_tile + NT;                               // [Cin][C+1] staged matrix (P.stage_pm)
     const int PMP = C + 1;
@@ -224,93 +223,127 @@ __global__ void __launch_bounds__(256, 1) eco_joint_kernel(EcoJointParams P) {
             pm = s_pm;
             pmp = PMP;
         }
-        for (int j = warp; j < npx; j += NW) {
+        // a coefficient is worked on by a TEAM: one warp when the CTA owns many coefficients, the whole CTA when it owns few (deep block:
+        // one); the scratch vectors of a team live in shared memory, its loops are strided by the team size
+        const bool wide = P.wide != 0;
+        const int T = wide ? NT : 32, tl = wide ? tid : lane;
+        float2* t_h0 = wide ? reinterpret_cast<float2*>(s_warp) : s_h0;
+        float2* t_ph = t_h0 + C;
+        float2* t_v = t_ph + C;
+        float2* t_u = t_v + Cin;
+        auto team_sync = [&]() { if (wide) __syncthreads(); else __syncwarp(); };
+        const int NB8 = (N + 7) / 8;
+        for (int j = wide ? 0 : warp; j < npx; j += wide ? 1 : NW) {
             const int pix = p0 + j;
             int pitch;
             const float2* S = slab_of(j, pitch);
             float2* c0 = P.c0w + (size_t)pix * N * C;
-            for (int c = lane; c < C; c += 32) {
-                s_h0[c] = P.h0w[(size_t)pix * C + c];
-                s_ph[c] = lin ? make_float2(0.f, 0.f) : P.phw[(size_t)pix * C + c];
+            for (int c = tl; c < C; c += T) {
+                t_h0[c] = P.h0w[(size_t)pix * C + c];
+                t_ph[c] = lin ? make_float2(0.f, 0.f) : P.phw[(size_t)pix * C + c];
             }
-            __syncwarp();
+            team_sync();
             if (lin) {
                 // c0[n,c] = sum_i X[n,i] P[i,c], eight sample rows per pass over the projection matrix
-                for (int n0 = 0; n0 < N; n0 += 8)
-                    for (int c = lane; c < C; c += 32) {
-                        float2 acc[8];
+                for (int item = tl; item < NB8 * C; item += T) {
+                    const int n0 = (item / C) * 8, c = item % C;
+                    float2 acc[8];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
-                        for (int i = 0; i < Cin; ++i) {
-                            const float pv = P.stage_pm ? pm[(size_t)i * pmp + c] : __ldcg(pm + (size_t)i * pmp + c);
+                    for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
+                    for (int i = 0; i < Cin; ++i) {
+                        const float pv = P.stage_pm ? pm[(size_t)i * pmp + c] : __ldcg(pm + (size_t)i * pmp + c);
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const int n = n0 + k < N ? n0 + k : N - 1;      // the tail repeats the last row (not stored)
-                                const float2 xv = S[(size_t)n * pitch + i];
-                                acc[k].x += xv.x * pv; acc[k].y += xv.y * pv;
-                            }
+                        for (int k = 0; k < 8; ++k) {
+                            const int n = n0 + k < N ? n0 + k : N - 1;          // the tail repeats the last row (not stored)
+                            const float2 xv = S[(size_t)n * pitch + i];
+                            acc[k].x += xv.x * pv; acc[k].y += xv.y * pv;
                         }
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            if (n0 + k < N) c0[(size_t)(n0 + k) * C + c] = acc[k];
                     }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (n0 + k < N) c0[(size_t)(n0 + k) * C + c] = acc[k];
+                }
             } else {
                 // v[i] = sum_c dP[i,c] h0[c]
-                for (int i = lane; i < Cin; i += 32) {
+                for (int i = tl; i < Cin; i += T) {
                     float ar = 0.f, ai = 0.f;
                     for (int c = 0; c < C; ++c) {
                         const float pv = P.stage_pm ? pm[(size_t)i * pmp + c] : __ldcg(pm + (size_t)i * pmp + c);
-                        ar += pv * s_h0[c].x; ai += pv * s_h0[c].y;
+                        ar += pv * t_h0[c].x; ai += pv * t_h0[c].y;
                     }
-                    s_v[i] = make_float2(ar, ai);
+                    t_v[i] = make_float2(ar, ai);
                 }
             }
-            __syncwarp();
-            // u[n] = sw_n (sum_c c0[n,c] h[c] (+ sum_i X[n,i] v[i]) (- yf)), one row per lane
+            team_sync();
+            // u[n] = sw_n (sum_c c0[n,c] h[c] (+ sum_i X[n,i] v[i]) (- yf))
             const float yfv = P.yf[pix];
-            for (int n = lane; n < N; n += 32) {
-                const float2* hv = lin ? s_h0 : s_ph;
-                float ar = 0.f, ai = 0.f;
-                for (int c = 0; c < C; ++c) {
-                    const float2 cv = c0[(size_t)n * C + c];
-                    ar += cv.x * hv[c].x - cv.y * hv[c].y;
-                    ai += cv.x * hv[c].y + cv.y * hv[c].x;
-                }
-                if (lin) {
-                    ar -= yfv;
-                } else {
-                    for (int i = 0; i < Cin; ++i) {
-                        const float2 xv = S[(size_t)n * pitch + i];
-                        ar += xv.x * s_v[i].x - xv.y * s_v[i].y;
-                        ai += xv.x * s_v[i].y + xv.y * s_v[i].x;
+            const float2* hv = lin ? t_h0 : t_ph;
+            if (wide) {                                      // a warp per sample row, the two dot products reduced across its lanes
+                for (int n = warp; n < N; n += NW) {
+                    float ar = 0.f, ai = 0.f;
+                    for (int c = lane; c < C; c += 32) {
+                        const float2 cv = c0[(size_t)n * C + c];
+                        ar += cv.x * hv[c].x - cv.y * hv[c].y;
+                        ai += cv.x * hv[c].y + cv.y * hv[c].x;
+                    }
+                    if (!lin)
+                        for (int i = lane; i < Cin; i += 32) {
+                            const float2 xv = S[(size_t)n * pitch + i];
+                            ar += xv.x * t_v[i].x - xv.y * t_v[i].y;
+                            ai += xv.x * t_v[i].y + xv.y * t_v[i].x;
+                        }
+                    ar = warp_sum(ar);
+                    ai = warp_sum(ai);
+                    if (lane == 0) {
+                        if (lin) ar -= yfv;
+                        const float w2 = s_sw[n] * s_sw[n];
+                        t_u[n] = make_float2(w2 * ar, w2 * ai);
                     }
                 }
-                const float w2 = s_sw[n] * s_sw[n];          // sqrt(sw) from the residual / J, sqrt(sw) again in J^T
-                s_u[n] = make_float2(w2 * ar, w2 * ai);
+            } else {                                         // a sample row per lane
+                for (int n = lane; n < N; n += 32) {
+                    float ar = 0.f, ai = 0.f;
+                    for (int c = 0; c < C; ++c) {
+                        const float2 cv = c0[(size_t)n * C + c];
+                        ar += cv.x * hv[c].x - cv.y * hv[c].y;
+                        ai += cv.x * hv[c].y + cv.y * hv[c].x;
+                    }
+                    if (lin) {
+                        ar -= yfv;
+                    } else {
+                        for (int i = 0; i < Cin; ++i) {
+                            const float2 xv = S[(size_t)n * pitch + i];
+                            ar += xv.x * t_v[i].x - xv.y * t_v[i].y;
+                            ai += xv.x * t_v[i].y + xv.y * t_v[i].x;
+                        }
+                    }
+                    const float w2 = s_sw[n] * s_sw[n];      // sqrt(sw) from the residual / J, sqrt(sw) again in J^T
+                    t_u[n] = make_float2(w2 * ar, w2 * ai);
+                }
             }
-            __syncwarp();
+            team_sync();
             // gh[c] = sum_n conj(c0[n,c]) u[n] + regularisation
-            for (int c = lane; c < C; c += 32) {
+            for (int c = tl; c < C; c += T) {
                 float ar = 0.f, ai = 0.f;
                 for (int n = 0; n < N; ++n) {
                     const float2 cv = c0[(size_t)n * C + c];
-                    ar += cv.x * s_u[n].x + cv.y * s_u[n].y;
-                    ai += cv.x * s_u[n].y - cv.y * s_u[n].x;
+                    ar += cv.x * t_u[n].x + cv.y * t_u[n].y;
+                    ai += cv.x * t_u[n].y - cv.y * t_u[n].x;
                 }
                 const float2 rg = reg_at(lin ? P.h0w : P.phw, pix, c, lin);
                 dst[(size_t)pix * C + c] = make_float2(ar + rg.x, ai + rg.y);
             }
             // w[i] = sum_n conj(X[n,i]) u[n]
-            for (int i = lane; i < Cin; i += 32) {
+            for (int i = tl; i < Cin; i += T) {
                 float ar = 0.f, ai = 0.f;
                 for (int n = 0; n < N; ++n) {
                     const float2 xv = S[(size_t)n * pitch + i];
-                    ar += xv.x * s_u[n].x + xv.y * s_u[n].y;
-                    ai += xv.x * s_u[n].y - xv.y * s_u[n].x;
+                    ar += xv.x * t_u[n].x + xv.y * t_u[n].y;
+                    ai += xv.x * t_u[n].y - xv.y * t_u[n].x;
                 }
                 P.wv[(size_t)pix * Cin + i] = make_float2(ar, ai);
             }
-            __syncwarp();
+            team_sync();
         }
         __syncthreads();
     };

@@ -72,7 +72,7 @@ extern "C" int eco_emul_joint_gn(float* hf, float* proj, const float* samples, c
     P.dMh = (float*)(w + pl.off_dMh); P.c0w = (float2*)(w + pl.off_c0); P.wv = (float2*)(w + pl.off_wv);
     P.pP = (float*)(w + pl.off_P); P.xP = P.pP + nelem; P.rP = P.xP + nelem; P.qP = P.rP + nelem;
     P.dots = (float*)(w + pl.off_dots); P.barrier = (unsigned*)w;
-    P.res_slabs = pl.res_slabs; P.npx_max = pl.npx_max; P.EPB = pl.EPB; P.SPL = pl.SPL; P.stage_pm = pl.stage_pm;
+    P.res_slabs = pl.res_slabs; P.npx_max = pl.npx_max; P.EPB = pl.EPB; P.SPL = pl.SPL; P.stage_pm = pl.stage_pm; P.wide = pl.wide;
     if (plan_out) { plan_out[0] = pl.grid; plan_out[1] = pl.res_slabs; plan_out[2] = pl.npx_max; plan_out[3] = pl.EPB; plan_out[4] = pl.SPL; plan_out[5] = (int)pl.smem_bytes; }
     cpu_emul::launch(eco_joint_kernel, (unsigned)pl.grid, (unsigned)pl.block, pl.smem_bytes, P);
     return 0;
