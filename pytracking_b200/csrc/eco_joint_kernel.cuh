@@ -13,8 +13,8 @@
 // J_reg^T J_reg is the correlation with the autocorrelation of W (all partial overlaps exist because the reference pads fully).
 //
 // Decomposition as in eco_cg_kernel.cuh: Fourier coefficients dealt to the CTAs in contiguous ranges, the [N, Cin] sample slab of a
-// coefficient resident in shared memory (row pitch Cin + 1, bank-conflict free for both access directions), one WARP per coefficient
-// in the coefficient-local phases.  The projection-matrix gradient is a sum over all coefficients: every coefficient publishes its
+// coefficient resident in shared memory (row pitch Cin + 1, bank-conflict free for both access directions); in the coefficient-local
+// phases a coefficient is worked on by a team: one warp when the CTA owns many coefficients, the whole CTA when it owns few.  The projection-matrix gradient is a sum over all coefficients: every coefficient publishes its
 // Cin-vector w, then the [Cin, C] elements are dealt to the CTAs in tiles (element x coefficient-split threads, fixed summation
 // order).  Four grid barriers per CG iteration; every reduction deterministic.
 // Plain SIMT CUDA C: the same source runs on the CPU under tests/cpu_emul/cuda_shim.h (tests/test_eco_cpu.py).
