@@ -225,31 +225,42 @@ __global__ void __launch_bounds__(256, 1) eco_cg_kernel(EcoParams P) {
                     for (int k = 0; k < CPL; ++k) vin[k] = field[(size_t)pix * C + gl + k * G];
                 }
             }
-            // rows of the slab: the forward product is reduced across the group, the same registers feed the adjoint
-            for (int n0 = 0; n0 < N; n0 += GPP) {
-                const int n = n0 + split;
-                const float swn = (valid && n < N) ? s_sw[n] : 0.f;
-                float2 xv[CPL];
-                float sr = 0.f, si = 0.f;
+            // rows of the slab: the forward product is reduced across the group, the same registers feed the adjoint; four rows at a
+            // time so that four independent shuffle chains are in flight
+            constexpr int RB = 4;
+            for (int n0 = 0; n0 < N; n0 += RB * GPP) {
+                float2 xv[RB][CPL];
+                float sr[RB], si[RB], swn[RB];
 #pragma unroll
-                for (int k = 0; k < CPL; ++k) {
-                    xv[k] = (swn != 0.f) ? S[(size_t)n * C + gl + k * G] : make_float2(0.f, 0.f);
-                    sr += xv[k].x * vin[k].x - xv[k].y * vin[k].y;
-                    si += xv[k].x * vin[k].y + xv[k].y * vin[k].x;
+                for (int r = 0; r < RB; ++r) {
+                    const int n = n0 + r * GPP + split;
+                    swn[r] = (valid && n < N) ? s_sw[n] : 0.f;
+                    sr[r] = 0.f; si[r] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) {
+                        xv[r][k] = (swn[r] != 0.f) ? S[(size_t)n * C + gl + k * G] : make_float2(0.f, 0.f);
+                        sr[r] += xv[r][k].x * vin[k].x - xv[r][k].y * vin[k].y;
+                        si[r] += xv[r][k].x * vin[k].y + xv[r][k].y * vin[k].x;
+                    }
                 }
-                float ur = swn, ui = 0.f;
                 if (!rhs) {                                  // uniform across the CTA
 #pragma unroll
-                    for (int o = G / 2; o > 0; o >>= 1) {
-                        sr += __shfl_xor_sync(0xffffffffu, sr, o);
-                        si += __shfl_xor_sync(0xffffffffu, si, o);
-                    }
-                    ur = swn * sr; ui = -swn * si;           // sw_n conj(X_n . v)
+                    for (int o = G / 2; o > 0; o >>= 1)
+#pragma unroll
+                        for (int r = 0; r < RB; ++r) {
+                            sr[r] += __shfl_xor_sync(0xffffffffu, sr[r], o);
+                            si[r] += __shfl_xor_sync(0xffffffffu, si[r], o);
+                        }
                 }
 #pragma unroll
-                for (int k = 0; k < CPL; ++k) {
-                    acc[k].x += ur * xv[k].x - ui * xv[k].y;
-                    acc[k].y += ur * xv[k].y + ui * xv[k].x;
+                for (int r = 0; r < RB; ++r) {
+                    const float ur = rhs ? swn[r] : swn[r] * sr[r];          // sw_n conj(X_n . v)
+                    const float ui = rhs ? 0.f : -swn[r] * si[r];
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) {
+                        acc[k].x += ur * xv[r][k].x - ui * xv[r][k].y;
+                        acc[k].y += ur * xv[r][k].y + ui * xv[r][k].x;
+                    }
                 }
             }
             // regularisation taps of this group: out(ky,kx) += w2[s,u] F(ky + s - (rh-1), kx + u - (rw-1)), negative kx by
