@@ -456,8 +456,11 @@ def install(max_batch=16, precision=0, skip=()):
 
     # ---- 2b. GNSteepestDescent over LinearFilterHinge (SuperDiMPSimple / KeepTrack classifiers): ltr/models/meta/steepestdescent.py:32-105,
     #          ltr/models/target_classifier/residual_modules.py:89-135; call site pytracking/tracker/dimp_simple/dimp_simple.py:685-689 ----
-    sdm = importlib.import_module("ltr.models.meta.steepestdescent")
-    ref_gnsd_forward = sdm.GNSteepestDescent.forward
+    try:
+        sdm = importlib.import_module("ltr.models.meta.steepestdescent")
+    except Exception:                                      # as above: an optional seam must not take install() down
+        sdm = None
+    ref_gnsd_forward = sdm.GNSteepestDescent.forward if sdm is not None else None
 
     def gnsd_forward(self, meta_parameter, num_iter=None, *args, **kwargs):
         rm = self.residual_module
@@ -489,7 +492,8 @@ def install(max_batch=16, precision=0, skip=()):
             except NotImplementedError:
                 pass
         return ref_gnsd_forward(self, meta_parameter, num_iter, *args, **kwargs)
-    _bind(sdm.GNSteepestDescent, "forward", gnsd_forward)
+    if sdm is not None:
+        _bind(sdm.GNSteepestDescent, "forward", gnsd_forward)
 
     # ---- 3. net wrapper: pytracking/features/net_wrappers.py:71-75 + ltr/models/tracking/dimpnet.py:80-81 ----
     nw = importlib.import_module("pytracking.features.net_wrappers")
@@ -846,7 +850,7 @@ def install(max_batch=16, precision=0, skip=()):
     # ---- 5b. ECO: pytracking/tracker/eco/optim.py:140-163 (FilterOptim.run), one launch per feature block ----
     try:
         eo = importlib.import_module("pytracking.tracker.eco.optim")
-    except ImportError:                                    # a checkout without the ECO tracker keeps every other seam
+    except Exception:                                      # a checkout whose ECO tracker does not import keeps every other seam
         eo = None
     ref_eco_run = eo.FilterOptim.run if eo is not None else None
 
