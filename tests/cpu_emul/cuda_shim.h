@@ -4,7 +4,7 @@
 //   __syncthreads()        -> pthread barrier over the block's threads
 //   __shfl_xor_sync()      -> exchange through a per-warp buffer, one pthread barrier per shuffle (double buffered)
 //   __syncwarp()           -> pthread barrier over the warp's threads
-//   extern __shared__      -> B200_DYN_SMEM(name): one allocation per block
+//   extern __shared__      -> B200_DYN_SMEM(name): one allocation per block; static __shared__ -> a function-local static (one block at a time)
 //   b200trk::grid_barrier  -> bar.sync + pthread barrier over the blocks' leader threads + bar.sync
 // The device helpers of csrc/common.cuh used by the emulated kernels (warp_sum, block_sum, grid_barrier) are restated below with
 // the same summation order.  Grids are kept small (a few blocks of 64-128 threads): the kernels under test take their
@@ -56,8 +56,8 @@ inline thread_local ThreadCtx* tctx = nullptr;
 
 inline unsigned char* dyn_smem() { return tctx->blk->smem.data(); }
 
-template <class Kernel, class Params>
-void launch(Kernel kernel, unsigned grid_dim, unsigned block_dim, size_t smem_bytes, Params params) {
+template <class Kernel, class... Args>
+void launch(Kernel kernel, unsigned grid_dim, unsigned block_dim, size_t smem_bytes, Args... params) {
     Grid g;
     g.blocks = std::vector<Block>(grid_dim);
     pthread_barrier_init(&g.leaders, nullptr, grid_dim);
@@ -86,7 +86,7 @@ void launch(Kernel kernel, unsigned grid_dim, unsigned block_dim, size_t smem_by
                 c.grid = &g;
                 c.parity = 0;
                 tctx = &c;
-                kernel(params);
+                kernel(params...);
                 tctx = nullptr;
             });
     for (auto& th : threads) th.join();
@@ -95,6 +95,23 @@ void launch(Kernel kernel, unsigned grid_dim, unsigned block_dim, size_t smem_by
         for (auto& w : b.warps) pthread_barrier_destroy(&w.bar);
     }
     pthread_barrier_destroy(&g.leaders);
+}
+
+// Kernels without any barrier or shuffle (one thread = one output element): every thread of a 2-D grid in turn, on the calling thread.
+template <class Kernel, class... Args>
+void launch_serial(Kernel kernel, unsigned grid_x, unsigned grid_y, unsigned block_dim, Args... params) {
+    ThreadCtx c{};
+    c.bdim = {block_dim, 1, 1};
+    c.gdim = {grid_x, grid_y, 1};
+    tctx = &c;
+    for (unsigned by = 0; by < grid_y; ++by)
+        for (unsigned bx = 0; bx < grid_x; ++bx)
+            for (unsigned t = 0; t < block_dim; ++t) {
+                c.tid = {t, 0, 0};
+                c.bid = {bx, by, 0};
+                kernel(params...);
+            }
+    tctx = nullptr;
 }
 
 }  // namespace cpu_emul
@@ -121,8 +138,27 @@ static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
     return buf[lane ^ lane_mask];
 }
 
+static inline int __shfl_xor_sync(unsigned m, int v, int lane_mask) {
+    float f;
+    std::memcpy(&f, &v, 4);
+    f = __shfl_xor_sync(m, f, lane_mask);
+    std::memcpy(&v, &f, 4);
+    return v;
+}
+
 template <class T>
 static inline T __ldcg(const T* p) { return *p; }
+
+// explicitly rounded single operations (compile the emulation with -ffp-contract=off so that they stay single operations)
+static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+static inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+// static __shared__ arrays: only for kernels launched with ONE block at a time (the array is shared by that block's threads)
+#define __shared__ static
 
 static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&::cpu_emul::tctx->warp->bar); }
 
