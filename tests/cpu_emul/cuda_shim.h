@@ -97,6 +97,45 @@ void launch(Kernel kernel, unsigned grid_dim, unsigned block_dim, size_t smem_by
     pthread_barrier_destroy(&g.leaders);
 }
 
+// Kernels without a grid barrier: the blocks of a (3-D) grid one after the other, each with its own OS threads.  Function-local
+// `__shared__` arrays (static here) are safe in this mode because only one block is alive at a time.
+template <class Kernel, class... Args>
+void launch_blocks(Kernel kernel, unsigned gx, unsigned gy, unsigned gz, unsigned block_dim, size_t smem_bytes, Args... params) {
+    for (unsigned bz = 0; bz < gz; ++bz)
+        for (unsigned by = 0; by < gy; ++by)
+            for (unsigned bx = 0; bx < gx; ++bx) {
+                Grid g;
+                g.blocks = std::vector<Block>(1);
+                pthread_barrier_init(&g.leaders, nullptr, 1);
+                Block& b = g.blocks[0];
+                pthread_barrier_init(&b.bar, nullptr, block_dim);
+                b.smem.assign(smem_bytes + 16, 0xCD);
+                const unsigned nwarps = (block_dim + 31) / 32;
+                b.warps = std::vector<Warp>(nwarps);
+                for (unsigned w = 0; w < nwarps; ++w) pthread_barrier_init(&b.warps[w].bar, nullptr, std::min(32u, block_dim - w * 32));
+                std::vector<std::thread> threads;
+                threads.reserve(block_dim);
+                for (unsigned t = 0; t < block_dim; ++t)
+                    threads.emplace_back([&, t]() {
+                        ThreadCtx c{};
+                        c.tid = {t, 0, 0};
+                        c.bid = {bx, by, bz};
+                        c.bdim = {block_dim, 1, 1};
+                        c.gdim = {gx, gy, gz};
+                        c.blk = &b;
+                        c.warp = &b.warps[t / 32];
+                        c.grid = &g;
+                        tctx = &c;
+                        kernel(params...);
+                        tctx = nullptr;
+                    });
+                for (auto& th : threads) th.join();
+                pthread_barrier_destroy(&b.bar);
+                for (auto& w : b.warps) pthread_barrier_destroy(&w.bar);
+                pthread_barrier_destroy(&g.leaders);
+            }
+}
+
 // Kernels without any barrier or shuffle (one thread = one output element): every thread of a 2-D grid in turn, on the calling thread.
 template <class Kernel, class... Args>
 void launch_serial(Kernel kernel, unsigned grid_x, unsigned grid_y, unsigned block_dim, Args... params) {
