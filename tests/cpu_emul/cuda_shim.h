@@ -188,6 +188,18 @@ static inline int __shfl_xor_sync(unsigned m, int v, int lane_mask) {
 template <class T>
 static inline T __ldcg(const T* p) { return *p; }
 
+static inline float atomicAdd(float* addr, float v) {      // CAS loop on the bit pattern (the emulating threads are real threads)
+    unsigned* ia = reinterpret_cast<unsigned*>(addr);
+    unsigned old_bits = __atomic_load_n(ia, __ATOMIC_RELAXED), new_bits;
+    float old_val;
+    do {
+        std::memcpy(&old_val, &old_bits, 4);
+        const float nv = old_val + v;
+        std::memcpy(&new_bits, &nv, 4);
+    } while (!__atomic_compare_exchange_n(ia, &old_bits, new_bits, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+    return old_val;
+}
+
 // explicitly rounded single operations (compile the emulation with -ffp-contract=off so that they stay single operations)
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 static inline float __fadd_rn(float a, float b) { return a + b; }
