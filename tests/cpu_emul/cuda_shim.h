@@ -164,6 +164,7 @@ void launch_serial(Kernel kernel, unsigned grid_x, unsigned grid_y, unsigned blo
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
 
 static inline void __syncthreads() { pthread_barrier_wait(&::cpu_emul::tctx->blk->bar); }
 
@@ -187,6 +188,11 @@ static inline int __shfl_xor_sync(unsigned m, int v, int lane_mask) {
 
 template <class T>
 static inline T __ldcg(const T* p) { return *p; }
+
+static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
+#define __expf(x) expf(x)      // the fast-math intrinsic: tolerance tests only
+template <class T>
+static inline T __ldg(const T* p) { return *p; }
 
 static inline float atomicAdd(float* addr, float v) {      // CAS loop on the bit pattern (the emulating threads are real threads)
     unsigned* ia = reinterpret_cast<unsigned*>(addr);
