@@ -1,5 +1,6 @@
 // Shared host/device helpers for libb200trk (sm_100a only).
 #pragma once
+#ifndef B200_CPU_EMUL      // host builds of the *_kernels.cuh headers get these helpers restated by tests/cpu_emul/cuda_shim.h
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -123,3 +124,5 @@ __device__ __forceinline__ float ordered_sum_ldcg(const float* p, size_t stride,
 }
 
 }  // namespace b200trk
+
+#endif  // B200_CPU_EMUL

@@ -189,6 +189,8 @@ static inline int __shfl_xor_sync(unsigned m, int v, int lane_mask) {
 template <class T>
 static inline T __ldcg(const T* p) { return *p; }
 
+static inline unsigned atomicAdd(unsigned* addr, unsigned v) { return __atomic_fetch_add(addr, v, __ATOMIC_ACQ_REL); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
 #define __expf(x) expf(x)      // the fast-math intrinsic: tolerance tests only
 template <class T>
