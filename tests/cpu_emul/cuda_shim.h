@@ -27,6 +27,7 @@ struct alignas(16) float4 { float x, y, z, w; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 struct emul_dim3 { unsigned x, y, z; };
+typedef void* cudaStream_t;                               // only named by host declarations the kernel headers pull in
 using std::max;
 using std::min;
 
@@ -100,7 +101,8 @@ void launch(Kernel kernel, unsigned grid_dim, unsigned block_dim, size_t smem_by
 // Kernels without a grid barrier: the blocks of a (3-D) grid one after the other, each with its own OS threads.  Function-local
 // `__shared__` arrays (static here) are safe in this mode because only one block is alive at a time.
 template <class Kernel, class... Args>
-void launch_blocks(Kernel kernel, unsigned gx, unsigned gy, unsigned gz, unsigned block_dim, size_t smem_bytes, Args... params) {
+void launch_blocks2(Kernel kernel, unsigned gx, unsigned gy, unsigned gz, unsigned block_x, unsigned block_y, size_t smem_bytes, Args... params) {
+    const unsigned block_dim = block_x * block_y;            // threads are linearised x-fastest, as on the device (warps = 32 consecutive)
     for (unsigned bz = 0; bz < gz; ++bz)
         for (unsigned by = 0; by < gy; ++by)
             for (unsigned bx = 0; bx < gx; ++bx) {
@@ -118,9 +120,9 @@ void launch_blocks(Kernel kernel, unsigned gx, unsigned gy, unsigned gz, unsigne
                 for (unsigned t = 0; t < block_dim; ++t)
                     threads.emplace_back([&, t]() {
                         ThreadCtx c{};
-                        c.tid = {t, 0, 0};
+                        c.tid = {t % block_x, t / block_x, 0};
                         c.bid = {bx, by, bz};
-                        c.bdim = {block_dim, 1, 1};
+                        c.bdim = {block_x, block_y, 1};
                         c.gdim = {gx, gy, gz};
                         c.blk = &b;
                         c.warp = &b.warps[t / 32];
@@ -134,6 +136,11 @@ void launch_blocks(Kernel kernel, unsigned gx, unsigned gy, unsigned gz, unsigne
                 for (auto& w : b.warps) pthread_barrier_destroy(&w.bar);
                 pthread_barrier_destroy(&g.leaders);
             }
+}
+
+template <class Kernel, class... Args>
+void launch_blocks(Kernel kernel, unsigned gx, unsigned gy, unsigned gz, unsigned block_dim, size_t smem_bytes, Args... params) {
+    launch_blocks2(kernel, gx, gy, gz, block_dim, 1u, smem_bytes, params...);
 }
 
 // Kernels without any barrier or shuffle (one thread = one output element): every thread of a 2-D grid in turn, on the calling thread.
