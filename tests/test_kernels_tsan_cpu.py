@@ -1,0 +1,31 @@
+"""ThreadSanitizer over the GPU-validated kernels that the CPU tier executes under tests/cpu_emul/cuda_shim.h (one OS thread per CUDA
+thread): a `__syncthreads()` / `__syncwarp()` missing between a write and another thread's read would be a data race between the
+emulating threads.  (The persistent ECO kernels have their own sanitizer runs in tests/test_eco_cpu.py, incl. the grid barriers.)"""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HARNESSES = ("transformer", "corr", "prroi", "atom", "conv_fp32")
+
+
+def test_block_level_kernels_under_thread_sanitizer(tmp_path):
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    rt = subprocess.run(["g++", "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(rt) or not os.path.exists(rt):
+        pytest.skip("no ThreadSanitizer runtime")
+    for n in HARNESSES:
+        subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-fsanitize=thread", "-Wno-unknown-pragmas",
+                        "-Wno-tsan", os.path.join(ROOT, "tests", "cpu_emul", n + "_emul.cpp"), "-o", str(tmp_path / ("lib%s_tsan.so" % n))],
+                       check=True, capture_output=True)
+    env = dict(os.environ, LD_PRELOAD=rt, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "cpu_emul", "tsan_sweep.py"), str(tmp_path)], capture_output=True, text=True,
+                       env=env, timeout=900)
+    if "EMUL_DONE" not in r.stdout and "ThreadSanitizer" not in r.stderr:
+        pytest.skip("ThreadSanitizer could not run here: %s" % r.stderr[-300:])
+    assert "EMUL_DONE" in r.stdout, r.stderr[-2000:]
+    assert "data race" not in r.stderr, r.stderr[:4000]
