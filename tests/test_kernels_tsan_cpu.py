@@ -22,7 +22,8 @@ def test_block_level_kernels_under_thread_sanitizer(tmp_path):
         subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-fsanitize=thread", "-Wno-unknown-pragmas",
                         "-Wno-tsan", os.path.join(ROOT, "tests", "cpu_emul", n + "_emul.cpp"), "-o", str(tmp_path / ("lib%s_tsan.so" % n))],
                        check=True, capture_output=True)
-    env = dict(os.environ, LD_PRELOAD=rt, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0")
+    # B200_EMUL_THREADS: real OS threads per block (the default cooperative fiber mode of launch_blocks has nothing for the sanitizer to see)
+    env = dict(os.environ, LD_PRELOAD=rt, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0", B200_EMUL_THREADS="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "cpu_emul", "tsan_sweep.py"), str(tmp_path)], capture_output=True, text=True,
                        env=env, timeout=900)
     if "EMUL_DONE" not in r.stdout and "ThreadSanitizer" not in r.stderr:
