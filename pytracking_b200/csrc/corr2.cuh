@@ -15,6 +15,14 @@
 #pragma once
 #include "common.cuh"
 
+// 8-byte asynchronous global -> shared copy.  The host build of the kernels (tests/cpu_emul/cuda_shim.h) performs the copy at once -- the
+// earliest moment the hardware could land it, i.e. the schedule that exposes a stage reused too early.
+#ifdef B200_CPU_EMUL
+#define B200_CP_ASYNC_8(d, g) std::memcpy(::cpu_emul::dyn_smem() + (d), (g), 8)
+#else
+#define B200_CP_ASYNC_8(d, g) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(g) : "memory")
+#endif
+
 namespace b200trk {
 
 template <int FS>
@@ -75,7 +83,7 @@ struct Corr2 {
                 const int row = rem / CHUNK8, ch = rem - row * CHUNK8;
                 const float* g = src + slot * ps + row * FS + ch * 2;
                 const uint32_t d = sbase + (uint32_t)(slot * PLANE + (row + PAD) * PITCH + PAD + ch * 2) * 4u;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(g) : "memory");
+                B200_CP_ASYNC_8(d, g);
             }
         }
     }
@@ -89,12 +97,18 @@ struct Corr2 {
             const int row = rem / CHUNK8, ch = rem - row * CHUNK8;
             const float* g = src + slot * ps + row * FS + ch * 2;
             const uint32_t d = sbase + (uint32_t)(slot * PLANE + (row + PAD) * PITCH + PAD + ch * 2) * 4u;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(g) : "memory");
+            B200_CP_ASYNC_8(d, g);
         }
     }
+#ifdef B200_CPU_EMUL
+    __device__ static __forceinline__ void commit() {}
+    template <int N>
+    __device__ static __forceinline__ void wait_group() {}
+#else
     __device__ static __forceinline__ void commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
     template <int N>
     __device__ static __forceinline__ void wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
 
     // ---- register-tile kernels -----------------------------------------------------------------------------
     // acc[orow*4+oc] += sum_{u,v} x[(5ty+orow+u), (4tx+oc+v)] * w[u*4+v]

@@ -27,9 +27,13 @@ struct SdParams {
 };
 
 __device__ __forceinline__ unsigned long long sd_gtimer() {
+#ifdef B200_CPU_EMUL
+    return 0ull;
+#else
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
+#endif
 }
 #define SD_STAMP(k) do { if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && (k) < 64) P.trace[(k)] = sd_gtimer(); } while (0)
 

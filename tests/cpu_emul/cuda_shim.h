@@ -320,6 +320,10 @@ static inline int __shfl_xor_sync(unsigned m, int v, int lane_mask) {
 template <class T>
 static inline T __ldcg(const T* p) { return *p; }
 
+// 32-bit "shared window" address of a pointer into the block's dynamic shared memory (cp.async destinations, csrc/corr2.cuh)
+static inline size_t __cvta_generic_to_shared(const void* p) {
+    return (size_t)(reinterpret_cast<const unsigned char*>(p) - ::cpu_emul::dyn_smem());
+}
 static inline unsigned atomicAdd(unsigned* addr, unsigned v) { return __atomic_fetch_add(addr, v, __ATOMIC_ACQ_REL); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
@@ -379,6 +383,16 @@ static inline void grid_barrier(unsigned*, unsigned& epoch) {
     epoch += 1;
     if (threadIdx.x == 0) pthread_barrier_wait(&::cpu_emul::tctx->grid->leaders);
     __syncthreads();
+}
+
+static inline float ordered_sum_ldcg(const float* p, size_t stride, int count) {      // common.cuh: index order, batches of 8
+    float s = 0.f;
+    for (int k0 = 0; k0 < count; k0 += 8) {
+        float v[8];
+        for (int u = 0; u < 8; ++u) v[u] = (k0 + u < count) ? p[(size_t)(k0 + u) * stride] : 0.f;
+        for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    return s;
 }
 
 static inline void eco_grid_barrier(unsigned* c, unsigned& epoch, unsigned&) { grid_barrier(c, epoch); }

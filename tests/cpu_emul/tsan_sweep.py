@@ -1,12 +1,13 @@
 """TEST INFRASTRUCTURE ONLY -- numpy / ctypes driver that pushes one representative call through every multi-threaded kernel of the
 `*_emul.cpp` harnesses (attention, single-query attention, LayerNorm; apply_filter with the last-CTA reduction, apply_feat_transpose, max2d;
 the three PrRoIPool kernels incl. the atomics of the backward; feature normalisation, softmax_reg, conv1x1, Fourier interpolation; the stem,
-the implicit-GEMM convolution fused and split-K, InstanceL2Norm + export).  tests/test_kernels_tsan_cpu.py runs it in a subprocess under
+the implicit-GEMM convolution fused and split-K, InstanceL2Norm + export; one CTA of the persistent steepest-descent optimiser and of
+ATOM's CG kernel with the immediate form of their cp.async copies -- the schedule that exposes a pipeline stage reused too early).  tests/test_kernels_tsan_cpu.py runs it in a subprocess under
 ThreadSanitizer (no torch import): every hand-over between the threads of a block must be ordered by a barrier.
 
-    python tsan_sweep.py <dir with lib{transformer,corr,prroi,atom,conv_fp32}_tsan.so>"""
+    python tsan_sweep.py <dir with lib{transformer,corr,prroi,atom,conv_fp32,sd,cg}_tsan.so>"""
 import sys
-LIB = {n: "%s/lib%s_tsan.so" % (sys.argv[1], n) for n in ("transformer", "corr", "prroi", "atom", "conv_fp32")}
+LIB = {n: "%s/lib%s_tsan.so" % (sys.argv[1], n) for n in ("transformer", "corr", "prroi", "atom", "conv_fp32", "sd", "cg")}
 import ctypes as C, numpy as np
 rng = np.random.RandomState(0)
 P = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
@@ -56,4 +57,18 @@ L.c32_emul_conv(P(xin), P(wk), P(oo), 1, 8, 8, 32, 16, 3, 1, 1, P(f32(16)), None
 L.c32_emul_conv(P(xin), P(wk), P(oo), 1, 8, 8, 32, 16, 3, 1, 1, None, None, 0, 0, None)
 xe, oe = f32(1, 9, 40), np.zeros((1, 40, 9), np.float32); L.c32_emul_export(P(xe), P(oe), 1, 9, 40, 1, C.c_float(0.1), C.c_float(1e-5))
 print("conv_fp32 ok")
+# persistent optimiser kernels, one CTA (static __shared__ storage): DiMP steepest descent and ATOM CG on the cp.async sweeps
+L = C.CDLL(LIB["sd"])
+n, c, h, it = 4, 32, 18, 2
+feat, w0, w = f32(n, c, h, h), f32(1, c, 4, 4) * 0.1, np.zeros((1, c, 4, 4), np.float32)
+bb = np.ascontiguousarray(np.array([[100, 110, 60, 50]] * n, np.float32) + rng.rand(n, 4).astype(np.float32) * 10)
+luts = [np.ascontiguousarray(rng.rand(100).astype(np.float32)) for _ in range(3)]
+its, losses = np.zeros((it + 1, c, 4, 4), np.float32), np.zeros(it + 1, np.float32)
+assert L.sd_emul_dimp_sd_gn(P(w0), P(w), P(feat), P(bb), None, n, c, h, h, it, P(luts[0]), P(luts[1]), P(luts[2]), 100, C.c_float(0.1), C.c_float(16.0),
+                            C.c_float(0.9), C.c_float(0.01), C.c_float(0.0), P(its), P(losses)) == 0
+print("sd ok")
+L = C.CDLL(LIB["cg"])
+y, sw, out = f32(n, 1, h, h), np.ascontiguousarray(np.full(n, 1.0 / n, np.float32)), np.zeros((1, c, 4, 4), np.float32)
+assert L.cg_emul_atom_cg_filter(P(w0), P(out), P(feat), P(y), P(sw), n, c, h, h, 2, C.c_float(0.1), 0, 3, C.c_float(0.05)) == 0
+print("cg ok")
 print("EMUL_DONE")
