@@ -51,7 +51,7 @@ struct FiberSched {
     int cur = -1, alive = 0;
     std::function<void(int)> body;
 };
-inline FiberSched* fsched = nullptr;                       // non-null while a fiber launch is running (single OS thread)
+inline thread_local FiberSched* fsched = nullptr;          // non-null while this OS thread runs a block's fibers
 void fiber_yield();
 
 struct Warp {
@@ -84,7 +84,7 @@ inline thread_local ThreadCtx* tctx = nullptr;
 inline unsigned char* dyn_smem() { return tctx->blk->smem.data(); }
 
 struct FiberCtxTable { std::vector<ThreadCtx>* ctxs = nullptr; };
-inline FiberCtxTable ftable;
+inline thread_local FiberCtxTable ftable;
 
 inline void fiber_switch(int next) {
     FiberSched* S = fsched;
@@ -180,6 +180,44 @@ void launch(Kernel kernel, unsigned grid_dim, unsigned block_dim, size_t smem_by
         pthread_barrier_destroy(&b.bar);
         for (auto& w : b.warps) pthread_barrier_destroy(&w.bar);
     }
+    pthread_barrier_destroy(&g.leaders);
+}
+
+// Cooperative kernels with MANY blocks, cheaply: one OS thread per block, the block's threads as fibers inside it.  Blocks run
+// concurrently (the grid barrier is a pthread barrier over the blocks' leader fibers: the other fibers of a block wait at bar.sync anyway),
+// ThreadSanitizer sees the cross-block traffic through global memory, and -- with B200_EMUL_COOP_FIBERS defined before this header --
+// function-local `__shared__` arrays become `static thread_local`, i.e. one copy per block.
+template <class Kernel, class... Args>
+void launch_coop(Kernel kernel, unsigned grid_dim, unsigned block_dim, size_t smem_bytes, Args... params) {
+    Grid g;
+    g.blocks = std::vector<Block>(grid_dim);
+    pthread_barrier_init(&g.leaders, nullptr, grid_dim);
+    const unsigned nwarps = (block_dim + 31) / 32;
+    for (auto& b : g.blocks) {
+        b.nthreads = block_dim;
+        b.smem.assign(smem_bytes + 16, 0xCD);
+        b.warps = std::vector<Warp>(nwarps);
+        for (unsigned w = 0; w < nwarps; ++w) b.warps[w].lanes = std::min(32u, block_dim - w * 32);
+    }
+    std::vector<std::thread> threads;
+    threads.reserve(grid_dim);
+    for (unsigned bi = 0; bi < grid_dim; ++bi)
+        threads.emplace_back([&, bi]() {
+            std::vector<ThreadCtx> ctxs(block_dim);
+            for (unsigned t = 0; t < block_dim; ++t) {
+                ThreadCtx& c = ctxs[t];
+                c.tid = {t, 0, 0};
+                c.bid = {bi, 0, 0};
+                c.bdim = {block_dim, 1, 1};
+                c.gdim = {grid_dim, 1, 1};
+                c.blk = &g.blocks[bi];
+                c.warp = &g.blocks[bi].warps[t / 32];
+                c.grid = &g;
+                c.fiber = 1;
+            }
+            run_fibers(ctxs, [&](int) { kernel(params...); });
+        });
+    for (auto& th : threads) th.join();
     pthread_barrier_destroy(&g.leaders);
 }
 
@@ -351,8 +389,13 @@ static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __fsqrt_rn(float a) { return std::sqrt(a); }
 static inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
-// static __shared__ arrays: only for kernels launched with ONE block at a time (the array is shared by that block's threads)
+// static __shared__ arrays: a function-local static, i.e. only for kernels launched with ONE live block at a time (launch with one block,
+// launch_blocks) -- or, with B200_EMUL_COOP_FIBERS, one copy per OS thread = per block of launch_coop
+#ifdef B200_EMUL_COOP_FIBERS
+#define __shared__ static thread_local
+#else
 #define __shared__ static
+#endif
 
 static inline void __syncwarp(unsigned = 0xffffffffu) {
     auto* c = ::cpu_emul::tctx;
