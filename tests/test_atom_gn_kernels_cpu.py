@@ -25,7 +25,7 @@ def emul(tmp_path_factory):
     if shutil.which("g++") is None:
         pytest.skip("no g++")
     out = os.path.join(str(tmp_path_factory.mktemp("atom_gn_emul")), "libatom_gn_emul.so")
-    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas",
+    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-fno-gnu-unique", "-Wno-unknown-pragmas",
                     os.path.join(ROOT, "tests", "cpu_emul", "atom_gn_emul.cpp"), "-o", out], check=True, capture_output=True)
     return C.CDLL(out)
 

@@ -24,7 +24,7 @@ def emul(tmp_path_factory):
     if shutil.which("g++") is None:
         pytest.skip("no g++")
     out = os.path.join(str(tmp_path_factory.mktemp("corr_emul")), "libcorr_emul.so")
-    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas",
+    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-fno-gnu-unique", "-Wno-unknown-pragmas",
                     os.path.join(ROOT, "tests", "cpu_emul", "corr_emul.cpp"), "-o", out], check=True, capture_output=True)
     return C.CDLL(out)
 

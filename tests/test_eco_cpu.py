@@ -57,7 +57,7 @@ def test_oracle_matches_reference_filter_optim(gold, case, run, bi, dtype):
 # ---- the kernel source on the CPU ------------------------------------------------------------------------------------------------
 def _build(tmp, tsan=False):
     out = os.path.join(tmp, "libeco_emul%s.so" % ("_tsan" if tsan else ""))
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas"] + \
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-pthread", "-shared", "-fPIC", "-fno-gnu-unique", "-Wno-unknown-pragmas"] + \
           (["-fsanitize=thread"] if tsan else []) + [os.path.join(ROOT, "tests", "cpu_emul", "eco_emul.cpp"), "-o", out]
     subprocess.run(cmd, check=True, capture_output=True)
     return out
