@@ -9,9 +9,17 @@
 
 using namespace b200trk;
 
+// plain build: one OS thread per CUDA thread (ThreadSanitizer sees every hand-over; small grids).  -DB200_EMUL_COOP_FIBERS: a block = one OS
+// thread, its threads = fibers -- the launch plan of a real B200 (148 CTAs x 256 threads) at ECO's real block sizes becomes affordable.
+#ifdef B200_EMUL_COOP_FIBERS
+#define ECO_LAUNCH cpu_emul::launch_coop
+#else
+#define ECO_LAUNCH cpu_emul::launch
+#endif
+
 template <int G, int CPL>
 static void run(const EcoPlan& pl, const EcoParams& P) {
-    cpu_emul::launch(eco_cg_kernel<G, CPL>, (unsigned)pl.grid, (unsigned)pl.block, pl.smem_bytes, P);
+    ECO_LAUNCH(eco_cg_kernel<G, CPL>, (unsigned)pl.grid, (unsigned)pl.block, pl.smem_bytes, P);
 }
 
 extern "C" int eco_emul_filter_cg(float* hf, const float* samples, const float* yf, const float* sw, const float* reg_filter, int rh, int rw,
@@ -74,6 +82,6 @@ extern "C" int eco_emul_joint_gn(float* hf, float* proj, const float* samples, c
     P.dots = (float*)(w + pl.off_dots); P.barrier = (unsigned*)w;
     P.res_slabs = pl.res_slabs; P.npx_max = pl.npx_max; P.EPB = pl.EPB; P.SPL = pl.SPL; P.stage_pm = pl.stage_pm; P.wide = pl.wide;
     if (plan_out) { plan_out[0] = pl.grid; plan_out[1] = pl.res_slabs; plan_out[2] = pl.npx_max; plan_out[3] = pl.EPB; plan_out[4] = pl.SPL; plan_out[5] = (int)pl.smem_bytes; }
-    cpu_emul::launch(eco_joint_kernel, (unsigned)pl.grid, (unsigned)pl.block, pl.smem_bytes, P);
+    ECO_LAUNCH(eco_joint_kernel, (unsigned)pl.grid, (unsigned)pl.block, pl.smem_bytes, P);
     return 0;
 }
