@@ -26,7 +26,7 @@
 
 #define B200_CPU_EMUL 1
 
-struct float2 { float x, y; };
+struct alignas(8) float2 { float x, y; };      // as on the device: a misaligned vector access is an error there (-fsanitize=alignment finds it here)
 struct alignas(16) float4 { float x, y, z, w; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
