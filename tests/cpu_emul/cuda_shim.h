@@ -25,6 +25,11 @@
 #include <vector>
 
 #define B200_CPU_EMUL 1
+#ifdef __SANITIZE_ADDRESS__
+#define B200_EMUL_SMEM_SLACK 0       // AddressSanitizer build: the first byte past the launch's dynamic shared memory is out of bounds
+#else
+#define B200_EMUL_SMEM_SLACK 16
+#endif
 
 struct alignas(8) float2 { float x, y; };      // as on the device: a misaligned vector access is an error there (-fsanitize=alignment finds it here)
 struct alignas(16) float4 { float x, y, z, w; };
@@ -150,7 +155,7 @@ void launch(Kernel kernel, unsigned grid_dim, unsigned block_dim, size_t smem_by
     const unsigned nwarps = (block_dim + 31) / 32;
     for (auto& b : g.blocks) {
         pthread_barrier_init(&b.bar, nullptr, block_dim);
-        b.smem.assign(smem_bytes + 16, 0xCD);                 // poisoned: uninitialised shared memory shows up as garbage
+        b.smem.assign(smem_bytes + B200_EMUL_SMEM_SLACK, 0xCD);                 // poisoned: uninitialised shared memory shows up as garbage
         b.warps = std::vector<Warp>(nwarps);
         for (unsigned w = 0; w < nwarps; ++w) {
             const unsigned lanes = std::min(32u, block_dim - w * 32);
@@ -195,7 +200,7 @@ void launch_coop(Kernel kernel, unsigned grid_dim, unsigned block_dim, size_t sm
     const unsigned nwarps = (block_dim + 31) / 32;
     for (auto& b : g.blocks) {
         b.nthreads = block_dim;
-        b.smem.assign(smem_bytes + 16, 0xCD);
+        b.smem.assign(smem_bytes + B200_EMUL_SMEM_SLACK, 0xCD);
         b.warps = std::vector<Warp>(nwarps);
         for (unsigned w = 0; w < nwarps; ++w) b.warps[w].lanes = std::min(32u, block_dim - w * 32);
     }
@@ -232,7 +237,7 @@ void launch_blocks2(Kernel kernel, unsigned gx, unsigned gy, unsigned gz, unsign
         g.blocks = std::vector<Block>(1);
         Block& b = g.blocks[0];
         b.nthreads = block_dim;
-        b.smem.assign(smem_bytes + 16, 0xCD);
+        b.smem.assign(smem_bytes + B200_EMUL_SMEM_SLACK, 0xCD);
         const unsigned nwarps = (block_dim + 31) / 32;
         b.warps = std::vector<Warp>(nwarps);
         for (unsigned w = 0; w < nwarps; ++w) b.warps[w].lanes = std::min(32u, block_dim - w * 32);
@@ -266,7 +271,7 @@ void launch_blocks2(Kernel kernel, unsigned gx, unsigned gy, unsigned gz, unsign
     pthread_barrier_init(&g.leaders, nullptr, 1);
     Block& b = g.blocks[0];
     pthread_barrier_init(&b.bar, nullptr, block_dim);
-    b.smem.assign(smem_bytes + 16, 0xCD);
+    b.smem.assign(smem_bytes + B200_EMUL_SMEM_SLACK, 0xCD);
     const unsigned nwarps = (block_dim + 31) / 32;
     b.warps = std::vector<Warp>(nwarps);
     for (unsigned w = 0; w < nwarps; ++w) pthread_barrier_init(&b.warps[w].bar, nullptr, std::min(32u, block_dim - w * 32));

@@ -459,3 +459,20 @@ def test_full_b200_launch_of_the_joint_kernel_at_eco_default_sizes(emul_coop, ca
     assert rc == 0 and plan[0] == grid
     assert "runtime error" not in capfd.readouterr().err
     assert _rel(hf, ref[0].numpy()) < 1e-5 and _rel(Pn, ref[1].numpy()) < 1e-5, (list(plan), _rel(hf, ref[0].numpy()), _rel(Pn, ref[1].numpy()))
+
+
+def test_eco_kernels_under_address_sanitizer(tmp_path):
+    """No access outside the launch's dynamic shared memory or a global buffer, at real per-CTA sizes and at ragged ones."""
+    rt = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if shutil.which("g++") is None or not os.path.isabs(rt) or not os.path.exists(rt):
+        pytest.skip("no AddressSanitizer runtime")
+    lib = str(tmp_path / "libeco_emul_asan.so")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-pthread", "-shared", "-fPIC", "-fno-gnu-unique", "-Wno-unknown-pragmas", "-fsanitize=address",
+                    os.path.join(ROOT, "tests", "cpu_emul", "eco_emul.cpp"), "-o", lib], check=True, capture_output=True)
+    env = dict(os.environ, LD_PRELOAD=rt, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "cpu_emul", "eco_asan_sweep.py"), lib], capture_output=True, text=True, env=env,
+                       timeout=900)
+    if "EMUL_DONE" not in r.stdout and "AddressSanitizer" not in r.stderr:
+        pytest.skip("AddressSanitizer could not run here: %s" % r.stderr[-300:])
+    assert "AddressSanitizer" not in r.stderr, r.stderr[:4000]
+    assert "EMUL_DONE" in r.stdout, r.stderr[-2000:]

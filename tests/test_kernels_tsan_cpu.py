@@ -31,3 +31,24 @@ def test_block_level_kernels_under_thread_sanitizer(tmp_path):
     assert "EMUL_DONE" in r.stdout, r.stderr[-2000:]
     assert "data race" not in r.stderr, r.stderr[:4000]
     assert "runtime error" not in r.stderr, r.stderr[:4000]            # -fsanitize=alignment: a misaligned float2 / float4 access faults on the device
+
+
+def test_block_level_kernels_under_address_sanitizer(tmp_path):
+    """The same sweep under AddressSanitizer (the launch's dynamic shared memory is a heap block of exactly the requested size, the global
+    buffers are numpy's): no access outside either."""
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    rt = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(rt) or not os.path.exists(rt):
+        pytest.skip("no AddressSanitizer runtime")
+    for n in HARNESSES:
+        subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-fno-gnu-unique", "-fsanitize=address",
+                        "-Wno-unknown-pragmas", os.path.join(ROOT, "tests", "cpu_emul", n + "_emul.cpp"), "-o", str(tmp_path / ("lib%s_tsan.so" % n))],
+                       check=True, capture_output=True)
+    env = dict(os.environ, LD_PRELOAD=rt, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1", B200_EMUL_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "cpu_emul", "tsan_sweep.py"), str(tmp_path)], capture_output=True, text=True,
+                       env=env, timeout=900)
+    if "EMUL_DONE" not in r.stdout and "AddressSanitizer" not in r.stderr:
+        pytest.skip("AddressSanitizer could not run here: %s" % r.stderr[-300:])
+    assert "AddressSanitizer" not in r.stderr, r.stderr[:4000]
+    assert "EMUL_DONE" in r.stdout, r.stderr[-2000:]
