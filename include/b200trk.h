@@ -192,6 +192,19 @@ int b200trk_eco_joint_gn(float* filter, float* proj, const float* samples, const
                          float projection_reg, int H, int Wh, int N, int Cin, int C, int num_cg_iter, int num_gn_iter,
                          b200trk_stream_t stream);
 
+/* ECO.apply_filter for ONE feature block (pytracking/tracker/eco/eco.py:244-245): complex.mult(filter, sample_xf).sum(1, keepdim=True).
+ *   filter [1,C,H,Wh,2]; sample_xf [S,C,H,Wh,2] (the S scales of the test sample); sf [S,1,H,Wh,2] out.                            */
+int b200trk_eco_apply_filter(const float* filter, const float* sample_xf, float* sf, int S, int C, int H, int Wh,
+                             b200trk_stream_t stream);
+
+/* The score map of ECO.localize_target (eco.py:247-252): fourier.sample_fs(fourier.sum_fs(weight * sf), output_sz) with rescale = True
+ * (pytracking/libs/fourier.py:35-61, 95-114) -- the reference zero-pads the summed series to the grid and takes out_h*out_w * irfft2;
+ * here the trigonometric series is evaluated directly.  sf_blocks: HOST array of num_blocks (<= 8) DEVICE pointers [S,1,H[b],Wh[b],2]
+ * (centred half spectra, H[b] odd); H, Wh, weights (may be null = 1): HOST arrays; scores [S,1,out_h,out_w] DEVICE out.  The grid must
+ * be at least as large as the largest series (H x (2 Wh - 1)) and not equal to it (fourier.py:43-48 take other paths there).          */
+int b200trk_eco_sample_fs(const float* const* sf_blocks, const int* H, const int* Wh, const float* weights, int num_blocks, int S,
+                          int out_h, int out_w, float* scores, b200trk_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Stage 1 -- backbone + classification head
  * ---------------------------------------------------------------------------------------------- */

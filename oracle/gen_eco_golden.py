@@ -169,6 +169,47 @@ def joint():
     print("wrote eco_joint.npz with %d arrays" % len(out))
 
 
+# (block sizes [(H, Wh, C)], scales, output size): two blocks as ECO's default (a large shallow and a small deep one), an even and an odd
+# output grid, one single-block case, and a grid exactly one step larger than the series
+LOC_CASES = {"two_blocks_even": dict(blocks=[(15, 8, 8), (9, 5, 12)], S=3, out=(24, 24), weights=(1.0, 0.7)),
+             "two_blocks_odd": dict(blocks=[(7, 4, 12), (13, 7, 6)], S=5, out=(25, 23), weights=(0.4, 1.0)),
+             "one_block": dict(blocks=[(11, 6, 16)], S=2, out=(32, 20), weights=(1.0,)),
+             "tight": dict(blocks=[(9, 5, 4), (5, 3, 8)], S=1, out=(10, 10), weights=(1.0, 1.0))}
+
+
+def loc():
+    """Score computation and localisation of `ECO.track` (eco.py:194-196, 244-274): `apply_filter` = complex.mult(filter, sample_xf).sum(1)
+    per block, then score_fusion_strategy 'weightedsum': fourier.sample_fs(fourier.sum_fs(weight * sf), output_sz) and dcf.max2d -- the
+    reference's own functions (irfft of the zero-padded series).  Writes tests/golden/eco_loc.npz."""
+    from oracle import ref_shims
+    ref_shims.install()
+    from pytracking import TensorList, complex, dcf, fourier
+    out = {}
+    for name, c in LOC_CASES.items():
+        g = torch.Generator().manual_seed(len(name))
+        filt = TensorList([0.1 * torch.randn(1, C, H, Wh, 2, generator=g) for (H, Wh, C) in c["blocks"]])
+        xf = TensorList([torch.randn(c["S"], C, H, Wh, 2, generator=g) for (H, Wh, C) in c["blocks"]])
+        sf = complex.mult(filt, xf).sum(1, keepdim=True)                                     # ECO.apply_filter (eco.py:244-245)
+        weight = TensorList(list(c["weights"]))
+        scores = fourier.sample_fs(fourier.sum_fs(weight * sf), torch.Tensor(list(c["out"])))   # eco.py:250-252
+        max_score, max_disp = dcf.max2d(scores)                                              # eco.py:271
+        out[name + "/out"] = np.array(c["out"], np.int64)
+        out[name + "/weights"] = np.array(c["weights"], np.float32)
+        for b in range(len(filt)):
+            out["%s/b%d/filter" % (name, b)] = filt[b].numpy()
+            out["%s/b%d/xf" % (name, b)] = xf[b].numpy()
+            out["%s/b%d/sf" % (name, b)] = sf[b].numpy()
+        out[name + "/scores"] = scores.numpy()
+        out[name + "/max_score"] = max_score.numpy()
+        out[name + "/max_disp"] = max_disp.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "eco_loc.npz"), **out)
+    print("wrote eco_loc.npz: %d arrays, %.1f KB" % (len(out), os.path.getsize(os.path.join(GOLDEN, "eco_loc.npz")) / 1e3))
+
+
 if __name__ == "__main__":
-    main()
-    joint()
+    if "loc" in sys.argv[1:]:
+        loc()
+    else:
+        main()
+        joint()
+        loc()

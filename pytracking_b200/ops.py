@@ -297,6 +297,40 @@ def eco_joint_gn_(filt, proj, samples, yf, sample_weights_sqrt, reg_filter, diag
     return filt, proj
 
 
+def eco_apply_filter(filt, sample_xf):
+    """ECO.apply_filter for one feature block (eco.py:244-245): filter [1,C,H,Wh,2] x sample_xf [S,C,H,Wh,2] -> [S,1,H,Wh,2]."""
+    filt, sample_xf = _dev(filt, "filter"), _dev(sample_xf, "sample_xf")
+    if filt.dim() != 5 or sample_xf.dim() != 5 or filt.shape[0] != 1 or filt.shape[-1] != 2 or tuple(sample_xf.shape[1:]) != tuple(filt.shape[1:]):
+        raise RuntimeError("b200trk.eco_apply_filter: filter [1,C,H,Wh,2] and sample_xf [S,C,H,Wh,2] expected, got %s and %s"
+                           % (tuple(filt.shape), tuple(sample_xf.shape)))
+    s, c, h, wh, _ = sample_xf.shape
+    sf = torch.empty(s, 1, h, wh, 2, device=filt.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b200trk_eco_apply_filter(_p(filt), _p(sample_xf), _p(sf), s, c, h, wh, _stream()), "eco_apply_filter")
+    return sf
+
+
+def eco_sample_fs(sf_blocks, output_sz, weights=None):
+    """fourier.sample_fs(fourier.sum_fs(weight * sf), output_sz) of ECO.localize_target (eco.py:247-252; fourier.py:35-61, 95-114): the
+    centred half spectra `sf_blocks` (a tensor or a list of tensors [S,1,H_b,Wh_b,2]) summed with `weights` and evaluated on the
+    output_sz grid -> scores [S,1,oh,ow]."""
+    import ctypes as C
+    blocks = [sf_blocks] if isinstance(sf_blocks, torch.Tensor) else list(sf_blocks)
+    blocks = [_dev(b, "sf") for b in blocks]
+    nb = len(blocks)
+    if nb == 0 or any(b.dim() != 5 or b.shape[1] != 1 or b.shape[-1] != 2 or b.shape[0] != blocks[0].shape[0] for b in blocks):
+        raise RuntimeError("b200trk.eco_sample_fs: blocks [S,1,H,Wh,2] with a common S expected, got %s" % [tuple(b.shape) for b in blocks])
+    if weights is not None and len(weights) != nb:
+        raise RuntimeError("b200trk.eco_sample_fs: %d weights for %d blocks" % (len(weights), nb))
+    s = blocks[0].shape[0]
+    oh, ow = int(output_sz[0]), int(output_sz[1])
+    out = torch.empty(s, 1, oh, ow, device=blocks[0].device, dtype=torch.float32)
+    ptrs = (C.c_void_p * nb)(*[b.data_ptr() for b in blocks])
+    hs, ws = (C.c_int * nb)(*[b.shape[2] for b in blocks]), (C.c_int * nb)(*[b.shape[3] for b in blocks])
+    wts = (C.c_float * nb)(*[float(w) for w in weights]) if weights is not None else None
+    _lib.check(_lib.lib().b200trk_eco_sample_fs(ptrs, hs, ws, wts, nb, s, oh, ow, _p(out), _stream()), "eco_sample_fs")
+    return out
+
+
 def atom_gn_joint_(filt, proj, samples, y, sample_weight, filter_reg, projection_reg, num_cg_iter, num_gn_iter,
                    activation="mlu", act_param=0.05, fletcher_reeves=True):
     """GaussNewtonCG.run(num_cg_iter, num_gn_iter) on FactorizedConvProblem; updates `filt` and `proj` in place."""

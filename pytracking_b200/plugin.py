@@ -904,6 +904,43 @@ def install(max_batch=16, precision=0, skip=()):
     if eo is not None:
         _bind(eo.FilterOptim, "run", eco_run)
 
+    # ---- 5c. ECO score computation: pytracking/tracker/eco/eco.py:244-252 (apply_filter; sample_fs as localize_target calls it) ----
+    try:
+        em = importlib.import_module("pytracking.tracker.eco.eco")
+    except Exception:
+        em = None
+    if em is not None:
+        ref_eco_apply = em.ECO.apply_filter
+
+        def eco_apply_filter(self, sample_xf):
+            filt = self.filter
+            if len(filt) == len(sample_xf) and all(_inference(f, x) and f.dim() == 5 and x.dim() == 5 and f.shape[0] == 1 and f.shape[-1] == 2 and
+                                                   tuple(x.shape[1:]) == tuple(f.shape[1:]) for f, x in zip(filt, sample_xf)):
+                _count("ECO.apply_filter")
+                return type(sample_xf)([ops.eco_apply_filter(f.contiguous(), x.contiguous()) for f, x in zip(filt, sample_xf)])
+            return ref_eco_apply(self, sample_xf)
+        _bind(em.ECO, "apply_filter", eco_apply_filter)
+
+        ref_fourier = em.fourier
+
+        class _EcoFourier:
+            """`fourier` as the ECO module sees it: sample_fs of one summed series on a larger grid (eco.py:249-252) goes to the library,
+            every other name and every other call is the reference module's (other trackers keep theirs untouched)."""
+            def __getattr__(self, name):
+                return getattr(ref_fourier, name)
+
+            @staticmethod
+            def sample_fs(a, grid_sz=None, rescale=True):
+                if isinstance(a, torch.Tensor) and grid_sz is not None and rescale and _inference(a) and a.dim() == 5 and a.shape[1] == 1 and \
+                        a.shape[-1] == 2 and a.shape[2] % 2 == 1:
+                    oh, ow = int(grid_sz[0]), int(grid_sz[1])
+                    if float(grid_sz[0]) == oh and float(grid_sz[1]) == ow and oh >= a.shape[2] and ow >= 2 * a.shape[3] - 1 and \
+                            (oh, ow) != (a.shape[2], 2 * a.shape[3] - 1):
+                        _count("fourier.sample_fs[eco]")
+                        return ops.eco_sample_fs(a.contiguous(), (oh, ow))
+                return ref_fourier.sample_fs(a, grid_sz, rescale)
+        _bind(em, "fourier", _EcoFourier())
+
     # ---- 6. ToMP: ltr/models/transformer/transformer.py:90-96 ----
     tr = importlib.import_module("ltr.models.transformer.transformer")
     from .transformer_engine import TransformerEngine

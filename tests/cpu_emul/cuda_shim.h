@@ -370,6 +370,7 @@ static inline size_t __cvta_generic_to_shared(const void* p) {
 static inline unsigned atomicAdd(unsigned* addr, unsigned v) { return __atomic_fetch_add(addr, v, __ATOMIC_ACQ_REL); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
+static inline void sincospif(float a, float* s, float* c) { *s = (float)std::sin(3.14159265358979323846 * (double)a); *c = (float)std::cos(3.14159265358979323846 * (double)a); }
 #define __expf(x) expf(x)      // the fast-math intrinsic: tolerance tests only
 template <class T>
 static inline T __ldg(const T* p) { return *p; }

@@ -2,12 +2,13 @@
 `*_emul.cpp` harnesses (attention, single-query attention, LayerNorm; apply_filter with the last-CTA reduction, apply_feat_transpose, max2d;
 the three PrRoIPool kernels incl. the atomics of the backward; feature normalisation, softmax_reg, conv1x1, Fourier interpolation; the stem,
 the implicit-GEMM convolution fused and split-K, InstanceL2Norm + export; one CTA of the persistent steepest-descent optimiser and of
-ATOM's CG kernel with the immediate form of their cp.async copies -- the schedule that exposes a pipeline stage reused too early).  tests/test_kernels_tsan_cpu.py runs it in a subprocess under
+ATOM's CG kernel with the immediate form of their cp.async copies -- the schedule that exposes a pipeline stage reused too early; ECO's
+score kernels).  tests/test_kernels_tsan_cpu.py runs it in a subprocess under
 ThreadSanitizer (no torch import): every hand-over between the threads of a block must be ordered by a barrier.
 
-    python tsan_sweep.py <dir with lib{transformer,corr,prroi,atom,conv_fp32,sd,cg}_tsan.so>"""
+    python tsan_sweep.py <dir with lib{transformer,corr,prroi,atom,conv_fp32,sd,cg,eco_loc}_tsan.so>"""
 import sys
-LIB = {n: "%s/lib%s_tsan.so" % (sys.argv[1], n) for n in ("transformer", "corr", "prroi", "atom", "conv_fp32", "sd", "cg")}
+LIB = {n: "%s/lib%s_tsan.so" % (sys.argv[1], n) for n in ("transformer", "corr", "prroi", "atom", "conv_fp32", "sd", "cg", "eco_loc")}
 import ctypes as C, numpy as np
 rng = np.random.RandomState(0)
 P = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
@@ -71,4 +72,16 @@ L = C.CDLL(LIB["cg"])
 y, sw, out = f32(n, 1, h, h), np.ascontiguousarray(np.full(n, 1.0 / n, np.float32)), np.zeros((1, c, 4, 4), np.float32)
 assert L.cg_emul_atom_cg_filter(P(w0), P(out), P(feat), P(y), P(sw), n, c, h, h, 2, C.c_float(0.1), 0, 3, C.c_float(0.05)) == 0
 print("cg ok")
+# ECO score kernels: apply_filter, then sum_fs + sample_fs of two blocks on an odd grid
+L = C.CDLL(LIB["eco_loc"])
+blocks = [(9, 5, 6), (5, 3, 4)]
+sfs = []
+for (hh, wh, cc) in blocks:
+    hf, xf, sf = f32(1, cc, hh, wh, 2), f32(2, cc, hh, wh, 2), np.zeros((2, 1, hh, wh, 2), np.float32)
+    assert L.eco_loc_emul_apply_filter(P(hf), P(xf), P(sf), 2, cc, hh, wh) == 0
+    sfs.append(sf)
+sc = np.zeros((2, 1, 13, 11), np.float32)
+ptrs = (C.c_void_p * 2)(*[a.ctypes.data for a in sfs])
+assert L.eco_loc_emul_sample_fs(ptrs, (C.c_int * 2)(9, 5), (C.c_int * 2)(5, 3), (C.c_float * 2)(1.0, 0.5), 2, 2, 13, 11, P(sc)) == 0 and np.isfinite(sc).all()
+print("eco_loc ok")
 print("EMUL_DONE")

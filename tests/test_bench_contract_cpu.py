@@ -79,9 +79,10 @@ def test_eco_rows_of_the_roofline_list():
     assert len(rows) == 1 and "unavailable" in rows[0]                       # no CUDA device here
     data = {"deep 15x8 x 200 x 64": {"us_median": 40.0, "us_min": 39.0, "sample_memory_bytes": 12288000, "reference_sweep_bytes": 147456000,
                                      "GBps_vs_one_read": 307.2, "GBps_vs_reference_sweeps": 3686.4},
-            "joint deep 15x8 x 30 x 256 -> 64": {"us_median": 2000.0, "us_min": 1990.0, "gn_x_cg": "10 x 10", "sample_bytes": 7372800}}
+            "joint deep 15x8 x 30 x 256 -> 64": {"us_median": 2000.0, "us_min": 1990.0, "gn_x_cg": "10 x 10", "sample_bytes": 7372800},
+            "scores 5 scales": {"us_median": 30.0, "us_min": 29.0, "bytes": 3000000, "launches": 4}}
     rows = bench.eco_rows_from(data, peaks)
-    assert len(rows) == 2
+    assert len(rows) == 3
     for r in rows:
         assert {"kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "us_per_launch", "algorithmic_bytes"} <= set(r)
         assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12

@@ -1,0 +1,120 @@
+"""ECO's score computation (eco.py:244-252): ECO.apply_filter and fourier.sample_fs(fourier.sum_fs(weight * sf), output_sz).
+CPU tier: (1) the restatement in oracle/eco_oracle.py against outputs of the UNMODIFIED reference functions (tests/golden/eco_loc.npz,
+oracle/gen_eco_golden.py loc); (2) the kernel source of pytracking_b200/csrc/eco_loc_kernels.cuh, compiled as host code under
+tests/cpu_emul/cuda_shim.h and launched as the C ABI launches it, against the same goldens incl. the arg-max of dcf.max2d; (3) ECO's
+real sizes (63x32 + 15x8 coefficients, five scales, a 250x250 grid) against the float64 oracle; (4) what the entry point rejects."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import eco_oracle as E
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "eco_loc.npz")
+CASES = ("two_blocks_even", "two_blocks_odd", "one_block", "tight")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def _blocks(g, name):
+    nb = len({k.split("/")[1] for k in g.files if k.startswith(name + "/b")})
+    return [(g["%s/b%d/filter" % (name, b)], g["%s/b%d/xf" % (name, b)], g["%s/b%d/sf" % (name, b)]) for b in range(nb)]
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_oracle_matches_reference_functions(gold, name, dtype):
+    sfs = []
+    for filt, xf, sf_ref in _blocks(gold, name):
+        sf = E.apply_filter(torch.from_numpy(filt).to(dtype), torch.from_numpy(xf).to(dtype))
+        assert _rel(sf.numpy(), sf_ref) < 1e-6
+        sfs.append(sf)
+    scores = E.sample_fs(E.sum_fs(sfs, gold[name + "/weights"].tolist()), gold[name + "/out"])
+    assert scores.shape == gold[name + "/scores"].shape and _rel(scores.numpy(), gold[name + "/scores"]) < 2e-6
+    mv, mi = E.max2d(scores)
+    assert np.array_equal(mi.numpy().reshape(-1, 2), gold[name + "/max_disp"].reshape(-1, 2))
+    assert np.allclose(mv.numpy().reshape(-1), gold[name + "/max_score"].reshape(-1), rtol=1e-5)
+
+
+# ---- the kernel source on the CPU ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    out = os.path.join(str(tmp_path_factory.mktemp("eco_loc")), "libeco_loc_emul.so")
+    cmd = ["g++", "-std=c++17", "-O2", "-g", "-pthread", "-shared", "-fPIC", "-fno-gnu-unique", "-ffp-contract=off", "-Wno-unknown-pragmas",
+           "-fsanitize=alignment", os.path.join(ROOT, "tests", "cpu_emul", "eco_loc_emul.cpp"), "-o", out]
+    if subprocess.run(cmd, capture_output=True).returncode != 0:
+        cmd.remove("-fsanitize=alignment")
+        subprocess.run(cmd, check=True, capture_output=True)
+    return C.CDLL(out)
+
+
+P = lambda a: a.ctypes.data_as(C.c_void_p)
+
+
+def _apply(emul, filt, xf):
+    s, c, h, wh, _ = xf.shape
+    sf = np.full((s, 1, h, wh, 2), np.nan, np.float32)
+    assert emul.eco_loc_emul_apply_filter(P(filt), P(xf), P(sf), s, c, h, wh) == 0
+    return sf
+
+
+def _sample(emul, sfs, weights, out_sz):
+    nb, s = len(sfs), sfs[0].shape[0]
+    scores = np.full((s, 1, int(out_sz[0]), int(out_sz[1])), np.nan, np.float32)
+    ptrs = (C.c_void_p * nb)(*[a.ctypes.data for a in sfs])
+    hs, ws = (C.c_int * nb)(*[a.shape[2] for a in sfs]), (C.c_int * nb)(*[a.shape[3] for a in sfs])
+    wts = (C.c_float * nb)(*[float(w) for w in weights]) if weights is not None else None
+    rc = emul.eco_loc_emul_sample_fs(ptrs, hs, ws, wts, nb, s, int(out_sz[0]), int(out_sz[1]), P(scores))
+    return rc, scores
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_emulated_kernels_match_reference_functions(emul, gold, capfd, name):
+    sfs = []
+    for filt, xf, sf_ref in _blocks(gold, name):
+        sf = _apply(emul, filt, xf)
+        assert _rel(sf, sf_ref) < 2e-6
+        sfs.append(sf)
+    rc, scores = _sample(emul, sfs, gold[name + "/weights"], gold[name + "/out"])
+    assert rc == 0 and "runtime error" not in capfd.readouterr().err
+    assert _rel(scores, gold[name + "/scores"]) < 5e-6, _rel(scores, gold[name + "/scores"])
+    mv, mi = E.max2d(torch.from_numpy(scores))                       # dcf.max2d on the kernel's map: the reference's arg-max cell
+    assert np.array_equal(mi.numpy().reshape(-1, 2), gold[name + "/max_disp"].reshape(-1, 2))
+
+
+def test_emulated_kernels_at_eco_default_sizes(emul, capfd):
+    """parameter/eco/default.py: shallow block 16 channels on 63x32 coefficients, deep block 64 on 15x8, five scales, output_sz 250x250."""
+    g = torch.Generator().manual_seed(3)
+    blocks = [(63, 32, 16), (15, 8, 64)]
+    filt = [0.1 * torch.randn(1, c, h, wh, 2, generator=g) for (h, wh, c) in blocks]
+    xf = [torch.randn(5, c, h, wh, 2, generator=g) for (h, wh, c) in blocks]
+    ref = E.sample_fs(E.sum_fs([E.apply_filter(f.double(), x.double()) for f, x in zip(filt, xf)], [1.0, 0.6]), (250, 250))
+    sfs = [_apply(emul, f.numpy(), x.numpy()) for f, x in zip(filt, xf)]
+    rc, scores = _sample(emul, sfs[::-1], [0.6, 1.0], (250, 250))      # the caller's order does not matter: sum_fs sorts by rows
+    assert rc == 0 and "runtime error" not in capfd.readouterr().err
+    assert _rel(scores, ref.numpy()) < 5e-6, _rel(scores, ref.numpy())
+    assert torch.equal(E.max2d(torch.from_numpy(scores))[1], E.max2d(ref)[1])
+
+
+def test_entry_point_rejects_what_the_kernel_does_not_claim(emul):
+    sf = np.zeros((1, 1, 9, 5, 2), np.float32)
+    assert _sample(emul, [sf], None, (8, 20))[0] == 2                  # grid smaller than the series (fourier.py:47-48 raises)
+    assert _sample(emul, [sf], None, (9, 9))[0] == 2                   # equal size: the reference's other branch
+    assert _sample(emul, [np.zeros((1, 1, 8, 5, 2), np.float32)], None, (20, 20))[0] == 2       # even number of rows
+    assert _sample(emul, [sf, np.zeros((1, 1, 5, 7, 2), np.float32)], None, (20, 20))[0] == 2   # more columns than the largest block
+    assert _sample(emul, [sf], None, (10, 9))[0] == 0

@@ -9,7 +9,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HARNESSES = ("transformer", "corr", "prroi", "atom", "conv_fp32", "sd", "cg")
+HARNESSES = ("transformer", "corr", "prroi", "atom", "conv_fp32", "sd", "cg", "eco_loc")
 
 
 def test_block_level_kernels_under_thread_sanitizer(tmp_path):

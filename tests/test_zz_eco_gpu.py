@@ -272,10 +272,57 @@ def test_reference_joint_optimizer_above_the_engine():
         assert _rel(got[i], ref[i]) < 1e-4, (i, _rel(got[i], ref[i]))
 
 
-def test_reference_eco_tracker_above_the_engine():
+# ---- score computation (b200trk_eco_apply_filter, b200trk_eco_sample_fs; eco.py:244-252) ----------------------------------------------
+LOC_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eco_loc.npz")
+
+
+@pytest.mark.parametrize("name", ["two_blocks_even", "two_blocks_odd", "one_block", "tight"])
+def test_eco_score_kernels_match_reference_golden(name):
+    """Outputs of the unmodified reference functions (complex.mult(..).sum(1), fourier.sum_fs, fourier.sample_fs, dcf.max2d;
+    oracle/gen_eco_golden.py loc) against the two entry points and ops.max2d."""
+    from pytracking_b200 import ops
+    g = np.load(LOC_GOLD)
+    nb = len({k.split("/")[1] for k in g.files if k.startswith(name + "/b")})
+    sfs = []
+    for b in range(nb):
+        sf = ops.eco_apply_filter(torch.from_numpy(g["%s/b%d/filter" % (name, b)]).cuda(), torch.from_numpy(g["%s/b%d/xf" % (name, b)]).cuda())
+        assert _rel(sf, g["%s/b%d/sf" % (name, b)]) < 2e-6
+        sfs.append(sf)
+    scores = ops.eco_sample_fs(sfs, g[name + "/out"].tolist(), g[name + "/weights"].tolist())
+    assert tuple(scores.shape) == g[name + "/scores"].shape and _rel(scores, g[name + "/scores"]) < 5e-6, _rel(scores, g[name + "/scores"])
+    mv, mi = ops.max2d(scores)
+    assert np.array_equal(mi.cpu().numpy().reshape(-1, 2), g[name + "/max_disp"].reshape(-1, 2))
+    assert np.allclose(mv.cpu().numpy().reshape(-1), g[name + "/max_score"].reshape(-1), rtol=1e-5)
+
+
+def test_eco_score_kernels_at_eco_default_sizes_vs_oracle():
+    """parameter/eco/default.py: shallow block 16 channels on 63x32 coefficients, deep block 64 on 15x8, five scales, a 250x250 grid."""
+    from oracle import eco_oracle as E
+    from pytracking_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    blocks = [(63, 32, 16), (15, 8, 64)]
+    filt = [0.1 * torch.randn(1, c, h, wh, 2, generator=g) for (h, wh, c) in blocks]
+    xf = [torch.randn(5, c, h, wh, 2, generator=g) for (h, wh, c) in blocks]
+    ref = E.sample_fs(E.sum_fs([E.apply_filter(f.double(), x.double()) for f, x in zip(filt, xf)], [1.0, 0.6]), (250, 250))
+    sfs = [ops.eco_apply_filter(f.cuda(), x.cuda()) for f, x in zip(filt, xf)]
+    scores = ops.eco_sample_fs(sfs[::-1], (250, 250), [0.6, 1.0])        # the caller's order does not matter: sum_fs sorts by rows
+    assert _rel(scores, ref) < 5e-6, _rel(scores, ref)
+    assert torch.equal(ops.max2d(scores)[1].cpu().view(-1, 2), E.max2d(ref)[1].view(-1, 2))
+    assert torch.equal(scores, ops.eco_sample_fs(sfs[::-1], (250, 250), [0.6, 1.0]))
+    sf = torch.zeros(1, 1, 9, 5, 2).cuda()
+    for bad in ((8, 20), (9, 9)):                                        # smaller than the series / equal to it (fourier.py:43-48)
+        with pytest.raises(RuntimeError):
+            ops.eco_sample_fs(sf, bad)
+    with pytest.raises(RuntimeError):
+        ops.eco_sample_fs(torch.zeros(1, 1, 8, 5, 2).cuda(), (20, 20))   # a centred half spectrum has an odd number of rows
+
+
+@pytest.mark.parametrize("score_seams", [False, True])
+def test_reference_eco_tracker_above_the_engine(score_seams):
     """The UNMODIFIED reference ECO tracker (parameter/eco/default.py, seeded random-init ResNet18m1 features) on the synthetic sequence:
-    stock PyTorch-CUDA vs `plugin.install()` (first-frame GaussNewtonCG.run and every FilterOptim.run on the library).  The CPU
-    counterpart with the oracle behind the entry points is tests/test_eco_tracker_cpu.py."""
+    stock PyTorch-CUDA vs `plugin.install()` (first-frame GaussNewtonCG.run and every FilterOptim.run on the library; with `score_seams`
+    also ECO.apply_filter and the sample_fs of ECO.localize_target).  The CPU counterpart with the oracle behind the entry points is
+    tests/test_eco_tracker_cpu.py."""
     from baseline import ref_env
     if not ref_env.reference_available():
         pytest.skip("reference tree not staged (baseline/_ref)")
@@ -296,13 +343,15 @@ def test_reference_eco_tracker_above_the_engine():
         ref_boxes, ref_trk = drive()
     except Exception as e:                                          # not the engine's doing: the stock reference on this torch build
         pytest.skip("the reference ECO tracker does not run on stock PyTorch-CUDA here: %r" % (e,))
-    plugin.install()
+    plugin.install(skip=() if score_seams else ("ECO.apply_filter", "fourier"))
     try:
         before = dict(plugin.stats)
         boxes, trk = drive()
         runs = sum(1 for f in range(2, n_frames + 2) if f % ov["train_skipping"] == 1)
         assert plugin.stats.get("GaussNewtonCG.run[eco]", 0) == before.get("GaussNewtonCG.run[eco]", 0) + 1
         assert plugin.stats.get("FilterOptim.run", 0) == before.get("FilterOptim.run", 0) + runs
+        assert plugin.stats.get("ECO.apply_filter", 0) == before.get("ECO.apply_filter", 0) + (n_frames if score_seams else 0)
+        assert plugin.stats.get("fourier.sample_fs[eco]", 0) == before.get("fourier.sample_fs[eco]", 0) + (n_frames if score_seams else 0)
     finally:
         plugin.uninstall()
     for b in range(2):

@@ -1,6 +1,7 @@
 """CUDA-event timing of the ECO row: b200trk_eco_filter_cg at ECO's default block sizes (parameter/eco/default.py:
 memory 200, CG_iter 5; deep block 64 channels on 15x8 Fourier coefficients, shallow block 16 channels on 63x32), with the roofline
-figures of DESIGN 4.9: bytes of sample memory per call, the reference's traffic (2 (1 + num_iter) sweeps), achieved GB/s.
+figures of DESIGN 4.9: bytes of sample memory per call, the reference's traffic (2 (1 + num_iter) sweeps), achieved GB/s; the first-frame
+joint optimisation; and the score computation of a tracked frame (apply_filter, sample_fs, max2d).
 
     python tools/eco_bench.py [--json PATH]    (on a GPU box; writes gpurun_out/eco_bench.json or PATH)
 
@@ -57,6 +58,22 @@ for name, (h, wh, n, cin, c) in JOINT.items():
     med, mn = timeit(runj, iters=5, warm=2)
     res["joint " + name] = {"us_median": med, "us_min": mn, "gn_x_cg": "10 x 10", "sample_bytes": samples.numel() * 4}
     print("joint %-32s median %9.1f us  min %9.1f us   (10 GN x 10 CG, %.1f MB of samples)" % (name, med, mn, samples.numel() * 4 / 1e6))
+# score computation of a tracked frame (eco.py:194-196): apply_filter of both blocks for 5 scales, sum_fs + sample_fs to 250x250, max2d
+try:
+    g = torch.Generator().manual_seed(9)
+    sblocks = [(63, 32, 16), (15, 8, 64)]
+    filt = [(0.1 * torch.randn(1, c, h, wh, 2, generator=g)).cuda() for (h, wh, c) in sblocks]
+    xfs = [torch.randn(5, c, h, wh, 2, generator=g).cuda() for (h, wh, c) in sblocks]
+
+    def runs():
+        sfs = [ops.eco_apply_filter(f, x) for f, x in zip(filt, xfs)]
+        ops.max2d(ops.eco_sample_fs(sfs, (250, 250), [1.0, 0.6]))
+    med, mn = timeit(runs, iters=20, warm=3)
+    nbytes = sum(t.numel() * 4 for t in filt + xfs) + 5 * 250 * 250 * 4
+    res["scores 5 scales, 63x32x16 + 15x8x64 -> 250x250"] = {"us_median": med, "us_min": mn, "bytes": nbytes, "launches": 4}
+    print("scores (apply_filter x 2 + sample_fs + max2d) median %8.1f us  min %8.1f us   (%.2f MB in + out)" % (med, mn, nbytes / 1e6))
+except Exception as e:      # noqa: BLE001 -- the optimiser rows above must survive a defect here
+    print("scores row failed: %r" % (e,))
 out_path = sys.argv[sys.argv.index("--json") + 1] if "--json" in sys.argv else os.path.join("gpurun_out", "eco_bench.json")
 os.makedirs(os.path.dirname(os.path.abspath(out_path)), exist_ok=True)
 json.dump(res, open(out_path, "w"), indent=1)
