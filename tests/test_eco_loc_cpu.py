@@ -118,3 +118,43 @@ def test_entry_point_rejects_what_the_kernel_does_not_claim(emul):
     assert _sample(emul, [np.zeros((1, 1, 8, 5, 2), np.float32)], None, (20, 20))[0] == 2       # even number of rows
     assert _sample(emul, [sf, np.zeros((1, 1, 5, 7, 2), np.float32)], None, (20, 20))[0] == 2   # more columns than the largest block
     assert _sample(emul, [sf], None, (10, 9))[0] == 0
+
+
+def test_score_seams_claim_only_what_the_library_serves(gold):
+    """`plugin.install()` on the ECO module: `ECO.apply_filter` and the module-scoped `fourier.sample_fs` go to the library for CUDA float32
+    series on a larger grid and to the reference for everything else (CPU tensors here, TensorLists, rescale=False, a grid equal to the
+    series); every other name of `fourier` is the reference module's; ATOM's module keeps the reference `fourier`; uninstall restores."""
+    import unittest.mock as um
+    from baseline import ref_env
+    if not ref_env.reference_available():
+        pytest.skip("reference tree not staged (baseline/_ref)")
+    from oracle import ref_shims
+    ref_shims.install()
+    import pytracking.libs.fourier as ref_fourier
+    import pytracking.tracker.atom.atom as atom_mod
+    import pytracking.tracker.eco.eco as eco_mod
+    from pytracking import TensorList
+    from pytracking_b200 import ops, plugin
+    name = "two_blocks_even"
+    sf = [torch.from_numpy(b[2]) for b in _blocks(gold, name)]
+    a = ref_fourier.sum_fs(TensorList(sf))
+    out = torch.Tensor(gold[name + "/out"].tolist())
+    ref = ref_fourier.sample_fs(a, out)
+    calls = []
+    plugin.install()
+    try:
+        assert eco_mod.fourier is not ref_fourier and atom_mod.fourier is ref_fourier
+        assert eco_mod.fourier.cfft2 is ref_fourier.cfft2 and eco_mod.fourier.sum_fs is ref_fourier.sum_fs
+        assert torch.equal(eco_mod.fourier.sample_fs(a, out), ref)                                   # CPU tensor: the reference
+        with um.patch.object(ops, "eco_sample_fs", lambda s, o, weights=None: calls.append(tuple(o)) or E.sample_fs(s, o)), \
+                um.patch.object(plugin, "_inference", lambda *ts: all(isinstance(t, torch.Tensor) and t.dtype == torch.float32 for t in ts)):
+            got = eco_mod.fourier.sample_fs(a, out)
+            assert calls == [tuple(int(v) for v in gold[name + "/out"])] and _rel(got.numpy(), ref.numpy()) < 2e-6
+            eco_mod.fourier.sample_fs(a, out, False)                                                 # rescale=False
+            eco_mod.fourier.sample_fs(TensorList([a]), out)                                          # a TensorList
+            eco_mod.fourier.sample_fs(a, torch.Tensor([a.shape[2], 2 * a.shape[3] - 1]))             # the series' own size
+            eco_mod.fourier.sample_fs(a)                                                             # no grid
+            assert len(calls) == 1
+    finally:
+        plugin.uninstall()
+    assert eco_mod.fourier is ref_fourier and "apply_filter" in eco_mod.ECO.__dict__
