@@ -426,10 +426,10 @@ def eco_rows_from(data, peaks):
                          "us_per_launch": v["us_median"], "algorithmic_bytes": v["sample_bytes"],
                          "note": "100 CG iterations with 4 grid barriers each: barrier / latency bound, the HBM figure is nominal"})
         elif k.startswith("scores "):
-            rows.append({"kernel": "eco_apply_filter_kernel x 2 + eco_sample_fs_kernel + max2d_kernel (ECO.apply_filter / localize_target scores; %s)" % k[7:],
+            rows.append({"kernel": "eco_preprocess_kernel x 2 + eco_apply_filter_kernel x 2 + eco_sample_fs_kernel + max2d_kernel (ECO.preprocess_sample / apply_filter / localize_target scores; %s)" % k[7:],
                          "bound": "hbm", "achieved": v["bytes"] / (v["us_median"] * 1e-6) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": v["bytes"] / (v["us_median"] * 1e-6) / 1e9 / peaks["hbm_gbs"], "traffic": None, "us_per_launch": v["us_median"],
-                         "algorithmic_bytes": v["bytes"], "note": "four launches of a few microseconds each: launch / latency bound"})
+                         "algorithmic_bytes": v["bytes"], "note": "six launches of a few microseconds each: launch / latency bound"})
         else:
             rows.append({"kernel": "eco_cg_kernel (ECO FilterOptim.run, 5 CG iterations; %s)" % k, "bound": "hbm", "achieved": v["GBps_vs_one_read"],
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": v["GBps_vs_one_read"] / peaks["hbm_gbs"], "traffic": None,

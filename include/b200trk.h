@@ -205,6 +205,15 @@ int b200trk_eco_apply_filter(const float* filter, const float* sample_xf, float*
 int b200trk_eco_sample_fs(const float* const* sf_blocks, const int* H, const int* Wh, const float* weights, int num_blocks, int S,
                           int out_h, int out_w, float* scores, b200trk_stream_t stream);
 
+/* ECO.preprocess_sample for ONE feature block (eco.py:297-300): x *= window; fourier.cfft2 (pytracking/libs/fourier.py:20-25);
+ * dcf.interpolate_dft with the (interp_y, interp_x) pair of dcf.get_interp_fourier (pytracking/libs/dcf.py:72-102).
+ *   x [S,C,H,W] with strides (in elements; the tracker hands over a permuted view of the projection's [H,W,S,C] result, eco.py:304-309)
+ *   is windowed IN PLACE as the reference does; window [1,1,H,W]; interp_y [1,1,H',1,2], interp_x [1,1,1,Wh',2] with
+ *   H' = H + (H+1)%2 (odd), Wh' = W/2 + 1; xf [S,C,H',Wh',2] contiguous out (centred half spectrum).                               */
+int b200trk_eco_preprocess_sample(float* x, long long stride_s, long long stride_c, long long stride_y, long long stride_x,
+                                  const float* window, const float* interp_y, const float* interp_x, float* xf, int S, int C,
+                                  int H, int W, b200trk_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Stage 1 -- backbone + classification head
  * ---------------------------------------------------------------------------------------------- */

@@ -205,11 +205,49 @@ def loc():
     np.savez_compressed(os.path.join(GOLDEN, "eco_loc.npz"), **out)
     print("wrote eco_loc.npz: %d arrays, %.1f KB" % (len(out), os.path.getsize(os.path.join(GOLDEN, "eco_loc.npz")) / 1e3))
 
+# feature map sizes (H, W), channels, samples: even (ECO's shallow 62x62 -> 63x32 in small), odd (deep 15x15 -> 15x8 in small), non-square
+PREP_CASES = {"even": dict(sz=(10, 10), C=3, S=2), "odd": dict(sz=(7, 7), C=4, S=3), "rect": dict(sz=(6, 9), C=2, S=1)}
+
+
+def prep():
+    """`ECO.preprocess_sample` (eco.py:297-300) called unbound on a stand-in `self` that carries what ECO.initialize builds (eco.py:65-78):
+    the Hann window of the feature size, the interpolation kernel's Fourier coefficients of the filter size (bicubic, a = -0.75, centred:
+    parameter/eco/default.py:72-75).  x *= window (in place), fourier.cfft2, dcf.interpolate_dft.  Writes tests/golden/eco_prep.npz."""
+    from oracle import ref_shims
+    ref_shims.install()
+    import types
+    from pytracking import TensorList, dcf
+    from pytracking.tracker.eco.eco import ECO
+    out = {}
+    names = list(PREP_CASES)
+    g = torch.Generator().manual_seed(21)
+    feature_sz = TensorList([torch.Tensor(list(PREP_CASES[n]["sz"])) for n in names])
+    filter_sz = feature_sz + (feature_sz + 1) % 2
+    me = types.SimpleNamespace(window=TensorList([dcf.hann2d(sz) for sz in feature_sz]),
+                               interp_fs=TensorList([dcf.get_interp_fourier(sz, "bicubic", -0.75, True, False, "cpu") for sz in filter_sz]))
+    x = TensorList([torch.randn(PREP_CASES[n]["S"], PREP_CASES[n]["C"], *PREP_CASES[n]["sz"], generator=g) for n in names])
+    x_in = [e.clone() for e in x]
+    xf = ECO.preprocess_sample(me, x)
+    for i, n in enumerate(names):
+        out[n + "/x"] = x_in[i].numpy()
+        out[n + "/x_after"] = x[i].numpy()                         # the reference windows its argument in place
+        out[n + "/window"] = me.window[i].numpy()
+        out[n + "/interp_y"] = me.interp_fs[i][0].numpy()
+        out[n + "/interp_x"] = me.interp_fs[i][1].numpy()
+        out[n + "/xf"] = xf[i].numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "eco_prep.npz"), **out)
+    print("wrote eco_prep.npz: %d arrays, %.1f KB; shapes %s" % (len(out), os.path.getsize(os.path.join(GOLDEN, "eco_prep.npz")) / 1e3,
+                                                                   [tuple(e.shape) for e in xf]))
+
 
 if __name__ == "__main__":
-    if "loc" in sys.argv[1:]:
-        loc()
+    if "loc" in sys.argv[1:] or "prep" in sys.argv[1:]:
+        if "loc" in sys.argv[1:]:
+            loc()
+        if "prep" in sys.argv[1:]:
+            prep()
     else:
         main()
         joint()
         loc()
+        prep()

@@ -30,3 +30,19 @@ extern "C" int b200trk_eco_sample_fs(const float* const* sf_blocks, const int* H
     B200_LAUNCH_CHECK();
     return 0;
 }
+
+extern "C" int b200trk_eco_preprocess_sample(float* x, long long stride_s, long long stride_c, long long stride_y, long long stride_x,
+                                             const float* window, const float* interp_y, const float* interp_x, float* xf, int S, int C,
+                                             int H, int W, b200trk_stream_t stream) {
+    B200_REQUIRE(x && window && interp_y && interp_x && xf, "eco_preprocess_sample: null pointer");
+    B200_REQUIRE(S > 0 && C > 0 && H > 0 && W > 0 && (long long)S * C < (1ll << 31), "eco_preprocess_sample: S=%d C=%d H=%d W=%d", S, C, H, W);
+    B200_REQUIRE(stride_s >= 0 && stride_c >= 0 && stride_y >= 0 && stride_x >= 0, "eco_preprocess_sample: negative stride");
+    B200_REQUIRE((((uintptr_t)interp_y | (uintptr_t)interp_x | (uintptr_t)xf) & 7) == 0, "eco_preprocess_sample: complex tensors must be 8-byte aligned");
+    const size_t smem = eco_preprocess_smem_floats(H, W) * sizeof(float);
+    B200_REQUIRE(smem <= 200 * 1024, "eco_preprocess_sample: a %dx%d feature map needs %zu bytes of shared memory", H, W, smem);
+    B200_CHECK_CUDA(cudaFuncSetAttribute(eco_preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    eco_preprocess_kernel<<<S * C, 256, smem, (cudaStream_t)stream>>>(x, window, (const float2*)interp_y, (const float2*)interp_x, (float2*)xf, C, H, W,
+                                                                               stride_s, stride_c, stride_y, stride_x);
+    B200_LAUNCH_CHECK();
+    return 0;
+}

@@ -142,4 +142,65 @@ __global__ void __launch_bounds__(256) eco_sample_fs_kernel(EcoLocParams P) {
     }
 }
 
+// ---- ECO.preprocess_sample (eco.py:297-300) for one block: x *= window (in place, as the reference), cfft2 (fourier.py:20-25),
+// dcf.interpolate_dft (dcf.py:96-102).  One CTA per (sample, channel) map; the H x W map is tiny (62 x 62 at most in ECO), so the
+// real-to-complex transform is evaluated directly and separably in shared memory:
+//     T[y][kx] = sum_x v[y][x] e^{-2 pi i kx x / W},   xf[ky][kx] = sum_y T[y][kx] e^{-2 pi i ky y / H},   ky = -(H'-1)/2 .. H'/2
+// (H' = H + (H+1)%2 rows: for an even H the Nyquist row appears at both ends, exactly what rfftshift2 produces), then
+// (xf * interp_y[ky]) * interp_x[kx] in the reference's order.  Twiddle tables e^{2 pi i m / N} in shared memory, indices as running integers.
+// shared memory (floats): v H*W | T 2*H*Wh' | tx 2*W | ty 2*H
+inline size_t eco_preprocess_smem_floats(int H, int W) { return (size_t)H * W + (H * W) % 2 + 2 * ((size_t)H * (W / 2 + 1) + W + H); }
+
+// x is addressed through its strides (in elements): the tracker hands over a permuted view of the projection's [H,W,S,C] result (eco.py:304-309)
+__global__ void __launch_bounds__(256) eco_preprocess_kernel(float* __restrict__ x, const float* __restrict__ window, const float2* __restrict__ iy,
+                                                             const float2* __restrict__ ix, float2* __restrict__ xf, int C, int H, int W,
+                                                             long long st_s, long long st_c, long long st_y, long long st_x) {
+    B200_DYN_SMEM_F(psm);
+    const int HP = H + (H + 1) % 2, WH = W / 2 + 1;
+    float* v = psm;
+    float2* T = reinterpret_cast<float2*>(psm + H * W + (H * W) % 2);      // 8-byte aligned
+    float2* tx = T + H * WH;
+    float2* ty = tx + W;
+    float* xm = x + (long long)(blockIdx.x / C) * st_s + (long long)(blockIdx.x % C) * st_c;
+    for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+        const int y = i / W, xx = i - y * W;
+        float* e = xm + y * st_y + xx * st_x;
+        const float a = *e * window[i];
+        v[i] = a; *e = a;
+    }
+    for (int m = threadIdx.x; m < W; m += blockDim.x) { float sn, cs; sincospif(2.f * (float)m / (float)W, &sn, &cs); tx[m] = make_float2(cs, sn); }
+    for (int m = threadIdx.x; m < H; m += blockDim.x) { float sn, cs; sincospif(2.f * (float)m / (float)H, &sn, &cs); ty[m] = make_float2(cs, sn); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H * WH; i += blockDim.x) {
+        const int y = i / WH, kx = i - y * WH;
+        const float* row = v + y * W;
+        float re = 0.f, im = 0.f;
+        int m = 0;
+        for (int xx = 0; xx < W; ++xx) {
+            const float2 t = tx[m];
+            re = fmaf(row[xx], t.x, re); im = fmaf(-row[xx], t.y, im);
+            m += kx; if (m >= W) m -= W;
+        }
+        T[i] = make_float2(re, im);
+    }
+    __syncthreads();
+    float2* out = xf + (size_t)blockIdx.x * HP * WH;
+    for (int i = threadIdx.x; i < HP * WH; i += blockDim.x) {
+        const int q = i / WH, kx = i - q * WH;
+        const int ky = q - (HP - 1) / 2;
+        const int step = ((ky % H) + H) % H;
+        float re = 0.f, im = 0.f;
+        int m = 0;
+        for (int y = 0; y < H; ++y) {                                      // T * conj(t)
+            const float2 a = T[y * WH + kx], t = ty[m];
+            re = fmaf(a.x, t.x, re); re = fmaf(a.y, t.y, re);
+            im = fmaf(a.y, t.x, im); im = fmaf(-a.x, t.y, im);
+            m += step; if (m >= H) m -= H;
+        }
+        const float2 wy = iy[q], wx = ix[kx];
+        const float r1 = re * wy.x - im * wy.y, i1 = re * wy.y + im * wy.x;       // complex.mult (complex.py:14-32), twice
+        out[i] = make_float2(r1 * wx.x - i1 * wx.y, r1 * wx.y + i1 * wx.x);
+    }
+}
+
 }  // namespace b200trk

@@ -331,6 +331,27 @@ def eco_sample_fs(sf_blocks, output_sz, weights=None):
     return out
 
 
+def eco_preprocess_sample_(x, window, interp_y, interp_x):
+    """ECO.preprocess_sample for one feature block (eco.py:297-300): windows `x` [S,C,H,W] (any strides) IN PLACE (as the reference does) and returns
+    interpolate_dft(cfft2(x), (interp_y, interp_x)) [S,C,H',Wh',2]."""
+    if not isinstance(x, torch.Tensor) or not x.is_cuda or x.dtype != torch.float32 or x.dim() != 4 or min(x.stride()) < 0:
+        raise RuntimeError("b200trk.eco_preprocess_sample_: x must be a CUDA float32 [S,C,H,W] tensor or view (windowed in place)")
+    if torch.cuda.current_device() != x.device.index:
+        raise RuntimeError("b200trk.eco_preprocess_sample_: x lives on %s but the current device is cuda:%d" % (x.device, torch.cuda.current_device()))
+    window, interp_y, interp_x = _dev(window, "window"), _dev(interp_y, "interp_y"), _dev(interp_x, "interp_x")
+    s, c, h, w = x.shape
+    hp, whp = h + (h + 1) % 2, w // 2 + 1
+    if window.numel() != h * w or interp_y.numel() != 2 * hp or interp_x.numel() != 2 * whp:
+        raise RuntimeError("b200trk.eco_preprocess_sample_: window %s / interp_y %s / interp_x %s do not match the %dx%d feature map"
+                           % (tuple(window.shape), tuple(interp_y.shape), tuple(interp_x.shape), h, w))
+    xf = torch.empty(s, c, hp, whp, 2, device=x.device, dtype=torch.float32)
+    st = x.stride()
+    _lib.check(_lib.lib().b200trk_eco_preprocess_sample(_p(x), st[0], st[1], st[2], st[3], _p(window), _p(interp_y), _p(interp_x), _p(xf), s, c, h, w,
+                                                        _stream()),
+               "eco_preprocess_sample")
+    return xf
+
+
 def atom_gn_joint_(filt, proj, samples, y, sample_weight, filter_reg, projection_reg, num_cg_iter, num_gn_iter,
                    activation="mlu", act_param=0.05, fletcher_reeves=True):
     """GaussNewtonCG.run(num_cg_iter, num_gn_iter) on FactorizedConvProblem; updates `filt` and `proj` in place."""

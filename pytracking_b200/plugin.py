@@ -904,7 +904,8 @@ def install(max_batch=16, precision=0, skip=()):
     if eo is not None:
         _bind(eo.FilterOptim, "run", eco_run)
 
-    # ---- 5c. ECO score computation: pytracking/tracker/eco/eco.py:244-252 (apply_filter; sample_fs as localize_target calls it) ----
+    # ---- 5c. ECO score computation: pytracking/tracker/eco/eco.py:244-252, 297-300 (apply_filter; sample_fs as localize_target calls it;
+    #          preprocess_sample) ----
     try:
         em = importlib.import_module("pytracking.tracker.eco.eco")
     except Exception:
@@ -920,6 +921,25 @@ def install(max_batch=16, precision=0, skip=()):
                 return type(sample_xf)([ops.eco_apply_filter(f.contiguous(), x.contiguous()) for f, x in zip(filt, sample_xf)])
             return ref_eco_apply(self, sample_xf)
         _bind(em.ECO, "apply_filter", eco_apply_filter)
+
+        ref_eco_prep = em.ECO.preprocess_sample
+
+        def eco_preprocess_sample(self, x):
+            win, ifs = self.window, self.interp_fs
+
+            def ok(e, w, bf):
+                if not (_inference(e, w) and e.dim() == 4 and min(e.stride()) >= 0 and isinstance(bf, (tuple, list)) and len(bf) == 2 and
+                        _inference(bf[0], bf[1])):
+                    return False
+                h, wd = e.shape[2], e.shape[3]
+                return (w.numel() == h * wd and bf[0].numel() == 2 * (h + (h + 1) % 2) and bf[1].numel() == 2 * (wd // 2 + 1) and
+                        4 * (h * wd + 1 + 2 * (h * (wd // 2 + 1) + h + wd)) <= 200 * 1024)
+            if len(x) == len(win) == len(ifs) and all(ok(e, w, bf) for e, w, bf in zip(x, win, ifs)):
+                _count("ECO.preprocess_sample")
+                return type(x)([ops.eco_preprocess_sample_(e, w.contiguous(), bf[0].contiguous(), bf[1].contiguous())
+                                for e, w, bf in zip(x, win, ifs)])
+            return ref_eco_prep(self, x)
+        _bind(em.ECO, "preprocess_sample", eco_preprocess_sample)
 
         ref_fourier = em.fourier
 

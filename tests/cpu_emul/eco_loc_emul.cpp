@@ -22,3 +22,12 @@ extern "C" int eco_loc_emul_sample_fs(const float* const* sf_blocks, const int* 
     cpu_emul::launch_blocks(eco_sample_fs_kernel, (unsigned)((out_h + EL_ROWS - 1) / EL_ROWS), (unsigned)S, 1u, 256u, smem, P);
     return 0;
 }
+
+extern "C" int eco_loc_emul_preprocess(float* x, long long st_s, long long st_c, long long st_y, long long st_x, const float* window, const float* iy,
+                                       const float* ix, float* xf, int S, int C, int H, int W) {
+    const size_t smem = eco_preprocess_smem_floats(H, W) * sizeof(float);
+    if (smem > 200 * 1024) return 2;
+    cpu_emul::launch_blocks(eco_preprocess_kernel, (unsigned)(S * C), 1u, 1u, 256u, smem, x, window, (const float2*)iy, (const float2*)ix, (float2*)xf, C, H, W, st_s, st_c,
+                            st_y, st_x);
+    return 0;
+}

@@ -83,5 +83,11 @@ for (hh, wh, cc) in blocks:
 sc = np.zeros((2, 1, 13, 11), np.float32)
 ptrs = (C.c_void_p * 2)(*[a.ctypes.data for a in sfs])
 assert L.eco_loc_emul_sample_fs(ptrs, (C.c_int * 2)(9, 5), (C.c_int * 2)(5, 3), (C.c_float * 2)(1.0, 0.5), 2, 2, 13, 11, P(sc)) == 0 and np.isfinite(sc).all()
+xs, win = f32(2, 3, 6, 8), np.abs(f32(1, 1, 6, 8))
+xv = np.ascontiguousarray(xs.transpose(2, 3, 0, 1)).transpose(2, 3, 0, 1)                 # the tracker's permuted view
+iy, ix, xo = f32(1, 1, 7, 1, 2), f32(1, 1, 1, 5, 2), np.zeros((2, 3, 7, 5, 2), np.float32)
+st = [C.c_longlong(v // 4) for v in xv.strides]
+assert L.eco_loc_emul_preprocess(C.c_void_p(xv.transpose(2, 3, 0, 1).ctypes.data), st[0], st[1], st[2], st[3], P(win), P(iy), P(ix), P(xo), 2, 3, 6, 8) == 0
+assert np.isfinite(xo).all()
 print("eco_loc ok")
 print("EMUL_DONE")

@@ -158,3 +158,54 @@ def test_score_seams_claim_only_what_the_library_serves(gold):
     finally:
         plugin.uninstall()
     assert eco_mod.fourier is ref_fourier and "apply_filter" in eco_mod.ECO.__dict__
+
+
+# ---- ECO.preprocess_sample (eco.py:297-300) -----------------------------------------------------------------------------------------
+PREP_GOLD = os.path.join(ROOT, "tests", "golden", "eco_prep.npz")
+
+
+@pytest.mark.parametrize("name", ["even", "odd", "rect"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_preprocess_oracle_matches_reference_method(name, dtype):
+    g = np.load(PREP_GOLD)
+    xf, v = E.preprocess_sample(torch.from_numpy(g[name + "/x"]).to(dtype), torch.from_numpy(g[name + "/window"]),
+                                torch.from_numpy(g[name + "/interp_y"]), torch.from_numpy(g[name + "/interp_x"]))
+    assert xf.shape == g[name + "/xf"].shape and _rel(xf.numpy(), g[name + "/xf"]) < 1e-6
+    assert _rel(v.numpy(), g[name + "/x_after"]) < 1e-6
+
+
+def _preprocess(emul, x, window, iy, ix, permuted=False):
+    """permuted: x as the tracker hands it over -- a [S,C,H,W] view of the projection's contiguous [H,W,S,C] result (eco.py:304-309)"""
+    s, c, h, w = x.shape
+    x = np.ascontiguousarray(x.transpose(2, 3, 0, 1)).transpose(2, 3, 0, 1) if permuted else np.ascontiguousarray(x).copy()
+    st = [C.c_longlong(v // 4) for v in x.strides]
+    xf = np.full((s, c, h + (h + 1) % 2, w // 2 + 1, 2), np.nan, np.float32)
+    base = x.ctypes.data if not permuted else x.transpose(2, 3, 0, 1).ctypes.data
+    assert emul.eco_loc_emul_preprocess(C.c_void_p(base), st[0], st[1], st[2], st[3], P(np.ascontiguousarray(window)), P(np.ascontiguousarray(iy)),
+                                        P(np.ascontiguousarray(ix)), P(xf), s, c, h, w) == 0
+    return xf, x
+
+
+@pytest.mark.parametrize("permuted", [False, True])
+@pytest.mark.parametrize("name", ["even", "odd", "rect"])
+def test_emulated_preprocess_kernel_matches_reference_method(emul, capfd, name, permuted):
+    g = np.load(PREP_GOLD)
+    xf, x_after = _preprocess(emul, g[name + "/x"], g[name + "/window"], g[name + "/interp_y"], g[name + "/interp_x"], permuted)
+    assert "runtime error" not in capfd.readouterr().err
+    assert _rel(xf, g[name + "/xf"]) < 2e-6, _rel(xf, g[name + "/xf"])
+    assert np.array_equal(x_after, g[name + "/x_after"])             # the argument windowed in place, bit for bit
+
+
+@pytest.mark.parametrize("s,c,hw", [(5, 16, 62), (5, 64, 15), (2, 3, 61)])
+def test_emulated_preprocess_kernel_at_eco_default_sizes(emul, capfd, s, c, hw):
+    """parameter/eco/default.py feature maps (62x62 shallow -> 63x32 coefficients, 15x15 deep -> 15x8) against the float64 oracle."""
+    g = torch.Generator().manual_seed(hw)
+    x = torch.randn(s, c, hw, hw, generator=g)
+    hann = 0.5 * (1 - torch.cos(2 * torch.pi * torch.arange(1, hw + 1).float() / (hw + 1)))
+    window = (hann.view(-1, 1) * hann.view(1, -1)).view(1, 1, hw, hw)
+    hp, whp = hw + (hw + 1) % 2, hw // 2 + 1
+    iy, ix = torch.randn(1, 1, hp, 1, 2, generator=g) / hw, torch.randn(1, 1, 1, whp, 2, generator=g) / hw
+    ref, _ = E.preprocess_sample(x.double(), window.double(), iy.double(), ix.double())
+    xf, _ = _preprocess(emul, x.numpy(), window.numpy(), iy.numpy(), ix.numpy())
+    assert "runtime error" not in capfd.readouterr().err
+    assert _rel(xf, ref.numpy()) < 5e-6, _rel(xf, ref.numpy())

@@ -317,11 +317,47 @@ def test_eco_score_kernels_at_eco_default_sizes_vs_oracle():
         ops.eco_sample_fs(torch.zeros(1, 1, 8, 5, 2).cuda(), (20, 20))   # a centred half spectrum has an odd number of rows
 
 
+@pytest.mark.parametrize("permuted", [False, True])
+@pytest.mark.parametrize("name", ["even", "odd", "rect"])
+def test_eco_preprocess_sample_matches_reference_golden(name, permuted):
+    """Outputs of the unmodified `ECO.preprocess_sample` (oracle/gen_eco_golden.py prep); `permuted`: x as the tracker hands it over, a
+    [S,C,H,W] view of the projection's contiguous [H,W,S,C] result (eco.py:304-309)."""
+    from pytracking_b200 import ops
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eco_prep.npz"))
+    x = torch.from_numpy(g[name + "/x"]).cuda()
+    if permuted:
+        x = x.permute(2, 3, 0, 1).contiguous().permute(2, 3, 0, 1)
+    xf = ops.eco_preprocess_sample_(x, torch.from_numpy(g[name + "/window"]).cuda(), torch.from_numpy(g[name + "/interp_y"]).cuda(),
+                                    torch.from_numpy(g[name + "/interp_x"]).cuda())
+    assert tuple(xf.shape) == g[name + "/xf"].shape and _rel(xf, g[name + "/xf"]) < 2e-6, _rel(xf, g[name + "/xf"])
+    assert torch.equal(x.cpu(), torch.from_numpy(g[name + "/x_after"]))          # windowed in place, bit for bit
+
+
+@pytest.mark.parametrize("s,c,hw", [(5, 16, 62), (5, 64, 15), (30, 96, 62)])
+def test_eco_preprocess_sample_at_eco_default_sizes_vs_oracle(s, c, hw):
+    """parameter/eco/default.py feature maps: 62x62 (-> 63x32 coefficients) and 15x15 (-> 15x8); the last case is the first frame's call on
+    the 30 augmented, not yet projected samples."""
+    from oracle import eco_oracle as E
+    from pytracking_b200 import ops
+    g = torch.Generator().manual_seed(hw)
+    x = torch.randn(s, c, hw, hw, generator=g)
+    hann = 0.5 * (1 - torch.cos(2 * torch.pi * torch.arange(1, hw + 1).float() / (hw + 1)))
+    window = (hann.view(-1, 1) * hann.view(1, -1)).view(1, 1, hw, hw)
+    hp, whp = hw + (hw + 1) % 2, hw // 2 + 1
+    iy, ix = torch.randn(1, 1, hp, 1, 2, generator=g) / hw, torch.randn(1, 1, 1, whp, 2, generator=g) / hw
+    n = min(s, 3)                                                   # the float64 oracle on the first samples only
+    ref, _ = E.preprocess_sample(x[:n].double(), window.double(), iy.double(), ix.double())
+    xd = x.cuda()
+    xf = ops.eco_preprocess_sample_(xd, window.cuda(), iy.cuda(), ix.cuda())
+    assert _rel(xf[:n], ref) < 5e-6, _rel(xf[:n], ref)
+    assert torch.equal(xd.cpu(), x * window)
+
+
 @pytest.mark.parametrize("score_seams", [False, True])
 def test_reference_eco_tracker_above_the_engine(score_seams):
     """The UNMODIFIED reference ECO tracker (parameter/eco/default.py, seeded random-init ResNet18m1 features) on the synthetic sequence:
     stock PyTorch-CUDA vs `plugin.install()` (first-frame GaussNewtonCG.run and every FilterOptim.run on the library; with `score_seams`
-    also ECO.apply_filter and the sample_fs of ECO.localize_target).  The CPU counterpart with the oracle behind the entry points is
+    also ECO.preprocess_sample, ECO.apply_filter and the sample_fs of ECO.localize_target).  The CPU counterpart with the oracle behind the entry points is
     tests/test_eco_tracker_cpu.py."""
     from baseline import ref_env
     if not ref_env.reference_available():
@@ -343,7 +379,7 @@ def test_reference_eco_tracker_above_the_engine(score_seams):
         ref_boxes, ref_trk = drive()
     except Exception as e:                                          # not the engine's doing: the stock reference on this torch build
         pytest.skip("the reference ECO tracker does not run on stock PyTorch-CUDA here: %r" % (e,))
-    plugin.install(skip=() if score_seams else ("ECO.apply_filter", "fourier"))
+    plugin.install(skip=() if score_seams else ("ECO.apply_filter", "fourier", "preprocess_sample"))
     try:
         before = dict(plugin.stats)
         boxes, trk = drive()
@@ -352,6 +388,7 @@ def test_reference_eco_tracker_above_the_engine(score_seams):
         assert plugin.stats.get("FilterOptim.run", 0) == before.get("FilterOptim.run", 0) + runs
         assert plugin.stats.get("ECO.apply_filter", 0) == before.get("ECO.apply_filter", 0) + (n_frames if score_seams else 0)
         assert plugin.stats.get("fourier.sample_fs[eco]", 0) == before.get("fourier.sample_fs[eco]", 0) + (n_frames if score_seams else 0)
+        assert plugin.stats.get("ECO.preprocess_sample", 0) == before.get("ECO.preprocess_sample", 0) + (n_frames + 1 if score_seams else 0)
     finally:
         plugin.uninstall()
     for b in range(2):

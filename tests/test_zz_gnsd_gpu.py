@@ -53,7 +53,7 @@ def test_reference_gn_steepest_descent_above_the_engine(act, thr, leak, n, c, hw
 NOT_GNSD = ("apply_filter", "apply_feat_transpose", "max2d", "extract_backbone", "extract_classification_feat", "get_iou_feat", "predict_iou",
             "_prroi_pooling", "_import_prroi_pooling", "conv2d", "conv1x1", "extract_head_feat", "predict_cls_bbreg_filters_parallel", "run",
             "softmax_reg", "DiMPSteepestDescentGN.forward", "PrDiMPSteepestDescentNewton.forward", "DiMPL2SteepestDescentGN.forward",
-            "Transformer.forward", "DenseBoxRegressor.forward", "fourier")
+            "Transformer.forward", "DenseBoxRegressor.forward", "fourier", "preprocess_sample")
 
 
 def test_reference_dimp_simple_tracker_above_the_engine():
