@@ -177,6 +177,87 @@ def test_reference_filter_optim_above_the_engine():
             assert _rel(got[r][b], ref[r][b]) < 2e-4, (r, b, _rel(got[r][b], ref[r][b]))
 
 
+# ---- score computation (b200trk_eco_apply_filter, b200trk_eco_sample_fs; eco.py:244-252) ----------------------------------------------
+LOC_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eco_loc.npz")
+
+
+@pytest.mark.parametrize("name", ["two_blocks_even", "two_blocks_odd", "one_block", "tight"])
+def test_eco_score_kernels_match_reference_golden(name):
+    """Outputs of the unmodified reference functions (complex.mult(..).sum(1), fourier.sum_fs, fourier.sample_fs, dcf.max2d;
+    oracle/gen_eco_golden.py loc) against the two entry points and ops.max2d."""
+    from pytracking_b200 import ops
+    g = np.load(LOC_GOLD)
+    nb = len({k.split("/")[1] for k in g.files if k.startswith(name + "/b")})
+    sfs = []
+    for b in range(nb):
+        sf = ops.eco_apply_filter(torch.from_numpy(g["%s/b%d/filter" % (name, b)]).cuda(), torch.from_numpy(g["%s/b%d/xf" % (name, b)]).cuda())
+        assert _rel(sf, g["%s/b%d/sf" % (name, b)]) < 2e-6
+        sfs.append(sf)
+    scores = ops.eco_sample_fs(sfs, g[name + "/out"].tolist(), g[name + "/weights"].tolist())
+    assert tuple(scores.shape) == g[name + "/scores"].shape and _rel(scores, g[name + "/scores"]) < 5e-6, _rel(scores, g[name + "/scores"])
+    mv, mi = ops.max2d(scores)
+    assert np.array_equal(mi.cpu().numpy().reshape(-1, 2), g[name + "/max_disp"].reshape(-1, 2))
+    assert np.allclose(mv.cpu().numpy().reshape(-1), g[name + "/max_score"].reshape(-1), rtol=1e-5)
+
+
+def test_eco_score_kernels_at_eco_default_sizes_vs_oracle():
+    """parameter/eco/default.py: shallow block 16 channels on 63x32 coefficients, deep block 64 on 15x8, five scales, a 250x250 grid."""
+    from oracle import eco_oracle as E
+    from pytracking_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    blocks = [(63, 32, 16), (15, 8, 64)]
+    filt = [0.1 * torch.randn(1, c, h, wh, 2, generator=g) for (h, wh, c) in blocks]
+    xf = [torch.randn(5, c, h, wh, 2, generator=g) for (h, wh, c) in blocks]
+    ref = E.sample_fs(E.sum_fs([E.apply_filter(f.double(), x.double()) for f, x in zip(filt, xf)], [1.0, 0.6]), (250, 250))
+    sfs = [ops.eco_apply_filter(f.cuda(), x.cuda()) for f, x in zip(filt, xf)]
+    scores = ops.eco_sample_fs(sfs[::-1], (250, 250), [0.6, 1.0])        # the caller's order does not matter: sum_fs sorts by rows
+    assert _rel(scores, ref) < 5e-6, _rel(scores, ref)
+    assert torch.equal(ops.max2d(scores)[1].cpu().view(-1, 2), E.max2d(ref)[1].view(-1, 2))
+    assert torch.equal(scores, ops.eco_sample_fs(sfs[::-1], (250, 250), [0.6, 1.0]))
+    sf = torch.zeros(1, 1, 9, 5, 2).cuda()
+    for bad in ((8, 20), (9, 9)):                                        # smaller than the series / equal to it (fourier.py:43-48)
+        with pytest.raises(RuntimeError):
+            ops.eco_sample_fs(sf, bad)
+    with pytest.raises(RuntimeError):
+        ops.eco_sample_fs(torch.zeros(1, 1, 8, 5, 2).cuda(), (20, 20))   # a centred half spectrum has an odd number of rows
+
+
+@pytest.mark.parametrize("permuted", [False, True])
+@pytest.mark.parametrize("name", ["even", "odd", "rect"])
+def test_eco_preprocess_sample_matches_reference_golden(name, permuted):
+    """Outputs of the unmodified `ECO.preprocess_sample` (oracle/gen_eco_golden.py prep); `permuted`: x as the tracker hands it over, a
+    [S,C,H,W] view of the projection's contiguous [H,W,S,C] result (eco.py:304-309)."""
+    from pytracking_b200 import ops
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eco_prep.npz"))
+    x = torch.from_numpy(g[name + "/x"]).cuda()
+    if permuted:
+        x = x.permute(2, 3, 0, 1).contiguous().permute(2, 3, 0, 1)
+    xf = ops.eco_preprocess_sample_(x, torch.from_numpy(g[name + "/window"]).cuda(), torch.from_numpy(g[name + "/interp_y"]).cuda(),
+                                    torch.from_numpy(g[name + "/interp_x"]).cuda())
+    assert tuple(xf.shape) == g[name + "/xf"].shape and _rel(xf, g[name + "/xf"]) < 2e-6, _rel(xf, g[name + "/xf"])
+    assert torch.equal(x.cpu(), torch.from_numpy(g[name + "/x_after"]))          # windowed in place, bit for bit
+
+
+@pytest.mark.parametrize("s,c,hw", [(5, 16, 62), (5, 64, 15), (30, 96, 62)])
+def test_eco_preprocess_sample_at_eco_default_sizes_vs_oracle(s, c, hw):
+    """parameter/eco/default.py feature maps: 62x62 (-> 63x32 coefficients) and 15x15 (-> 15x8); the last case is the first frame's call on
+    the 30 augmented, not yet projected samples."""
+    from oracle import eco_oracle as E
+    from pytracking_b200 import ops
+    g = torch.Generator().manual_seed(hw)
+    x = torch.randn(s, c, hw, hw, generator=g)
+    hann = 0.5 * (1 - torch.cos(2 * torch.pi * torch.arange(1, hw + 1).float() / (hw + 1)))
+    window = (hann.view(-1, 1) * hann.view(1, -1)).view(1, 1, hw, hw)
+    hp, whp = hw + (hw + 1) % 2, hw // 2 + 1
+    iy, ix = torch.randn(1, 1, hp, 1, 2, generator=g) / hw, torch.randn(1, 1, 1, whp, 2, generator=g) / hw
+    n = min(s, 3)                                                   # the float64 oracle on the first samples only
+    ref, _ = E.preprocess_sample(x[:n].double(), window.double(), iy.double(), ix.double())
+    xd = x.cuda()
+    xf = ops.eco_preprocess_sample_(xd, window.cuda(), iy.cuda(), ix.cuda())
+    assert _rel(xf[:n], ref) < 5e-6, _rel(xf[:n], ref)
+    assert torch.equal(xd.cpu(), x * window)
+
+
 # ---- first-frame joint optimisation (b200trk_eco_joint_gn) -----------------------------------------------------------------------------
 JOINT_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eco_joint.npz")
 
@@ -270,87 +351,6 @@ def test_reference_joint_optimizer_above_the_engine():
         plugin.uninstall()
     for i in range(4):
         assert _rel(got[i], ref[i]) < 1e-4, (i, _rel(got[i], ref[i]))
-
-
-# ---- score computation (b200trk_eco_apply_filter, b200trk_eco_sample_fs; eco.py:244-252) ----------------------------------------------
-LOC_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eco_loc.npz")
-
-
-@pytest.mark.parametrize("name", ["two_blocks_even", "two_blocks_odd", "one_block", "tight"])
-def test_eco_score_kernels_match_reference_golden(name):
-    """Outputs of the unmodified reference functions (complex.mult(..).sum(1), fourier.sum_fs, fourier.sample_fs, dcf.max2d;
-    oracle/gen_eco_golden.py loc) against the two entry points and ops.max2d."""
-    from pytracking_b200 import ops
-    g = np.load(LOC_GOLD)
-    nb = len({k.split("/")[1] for k in g.files if k.startswith(name + "/b")})
-    sfs = []
-    for b in range(nb):
-        sf = ops.eco_apply_filter(torch.from_numpy(g["%s/b%d/filter" % (name, b)]).cuda(), torch.from_numpy(g["%s/b%d/xf" % (name, b)]).cuda())
-        assert _rel(sf, g["%s/b%d/sf" % (name, b)]) < 2e-6
-        sfs.append(sf)
-    scores = ops.eco_sample_fs(sfs, g[name + "/out"].tolist(), g[name + "/weights"].tolist())
-    assert tuple(scores.shape) == g[name + "/scores"].shape and _rel(scores, g[name + "/scores"]) < 5e-6, _rel(scores, g[name + "/scores"])
-    mv, mi = ops.max2d(scores)
-    assert np.array_equal(mi.cpu().numpy().reshape(-1, 2), g[name + "/max_disp"].reshape(-1, 2))
-    assert np.allclose(mv.cpu().numpy().reshape(-1), g[name + "/max_score"].reshape(-1), rtol=1e-5)
-
-
-def test_eco_score_kernels_at_eco_default_sizes_vs_oracle():
-    """parameter/eco/default.py: shallow block 16 channels on 63x32 coefficients, deep block 64 on 15x8, five scales, a 250x250 grid."""
-    from oracle import eco_oracle as E
-    from pytracking_b200 import ops
-    g = torch.Generator().manual_seed(3)
-    blocks = [(63, 32, 16), (15, 8, 64)]
-    filt = [0.1 * torch.randn(1, c, h, wh, 2, generator=g) for (h, wh, c) in blocks]
-    xf = [torch.randn(5, c, h, wh, 2, generator=g) for (h, wh, c) in blocks]
-    ref = E.sample_fs(E.sum_fs([E.apply_filter(f.double(), x.double()) for f, x in zip(filt, xf)], [1.0, 0.6]), (250, 250))
-    sfs = [ops.eco_apply_filter(f.cuda(), x.cuda()) for f, x in zip(filt, xf)]
-    scores = ops.eco_sample_fs(sfs[::-1], (250, 250), [0.6, 1.0])        # the caller's order does not matter: sum_fs sorts by rows
-    assert _rel(scores, ref) < 5e-6, _rel(scores, ref)
-    assert torch.equal(ops.max2d(scores)[1].cpu().view(-1, 2), E.max2d(ref)[1].view(-1, 2))
-    assert torch.equal(scores, ops.eco_sample_fs(sfs[::-1], (250, 250), [0.6, 1.0]))
-    sf = torch.zeros(1, 1, 9, 5, 2).cuda()
-    for bad in ((8, 20), (9, 9)):                                        # smaller than the series / equal to it (fourier.py:43-48)
-        with pytest.raises(RuntimeError):
-            ops.eco_sample_fs(sf, bad)
-    with pytest.raises(RuntimeError):
-        ops.eco_sample_fs(torch.zeros(1, 1, 8, 5, 2).cuda(), (20, 20))   # a centred half spectrum has an odd number of rows
-
-
-@pytest.mark.parametrize("permuted", [False, True])
-@pytest.mark.parametrize("name", ["even", "odd", "rect"])
-def test_eco_preprocess_sample_matches_reference_golden(name, permuted):
-    """Outputs of the unmodified `ECO.preprocess_sample` (oracle/gen_eco_golden.py prep); `permuted`: x as the tracker hands it over, a
-    [S,C,H,W] view of the projection's contiguous [H,W,S,C] result (eco.py:304-309)."""
-    from pytracking_b200 import ops
-    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eco_prep.npz"))
-    x = torch.from_numpy(g[name + "/x"]).cuda()
-    if permuted:
-        x = x.permute(2, 3, 0, 1).contiguous().permute(2, 3, 0, 1)
-    xf = ops.eco_preprocess_sample_(x, torch.from_numpy(g[name + "/window"]).cuda(), torch.from_numpy(g[name + "/interp_y"]).cuda(),
-                                    torch.from_numpy(g[name + "/interp_x"]).cuda())
-    assert tuple(xf.shape) == g[name + "/xf"].shape and _rel(xf, g[name + "/xf"]) < 2e-6, _rel(xf, g[name + "/xf"])
-    assert torch.equal(x.cpu(), torch.from_numpy(g[name + "/x_after"]))          # windowed in place, bit for bit
-
-
-@pytest.mark.parametrize("s,c,hw", [(5, 16, 62), (5, 64, 15), (30, 96, 62)])
-def test_eco_preprocess_sample_at_eco_default_sizes_vs_oracle(s, c, hw):
-    """parameter/eco/default.py feature maps: 62x62 (-> 63x32 coefficients) and 15x15 (-> 15x8); the last case is the first frame's call on
-    the 30 augmented, not yet projected samples."""
-    from oracle import eco_oracle as E
-    from pytracking_b200 import ops
-    g = torch.Generator().manual_seed(hw)
-    x = torch.randn(s, c, hw, hw, generator=g)
-    hann = 0.5 * (1 - torch.cos(2 * torch.pi * torch.arange(1, hw + 1).float() / (hw + 1)))
-    window = (hann.view(-1, 1) * hann.view(1, -1)).view(1, 1, hw, hw)
-    hp, whp = hw + (hw + 1) % 2, hw // 2 + 1
-    iy, ix = torch.randn(1, 1, hp, 1, 2, generator=g) / hw, torch.randn(1, 1, 1, whp, 2, generator=g) / hw
-    n = min(s, 3)                                                   # the float64 oracle on the first samples only
-    ref, _ = E.preprocess_sample(x[:n].double(), window.double(), iy.double(), ix.double())
-    xd = x.cuda()
-    xf = ops.eco_preprocess_sample_(xd, window.cuda(), iy.cuda(), ix.cuda())
-    assert _rel(xf[:n], ref) < 5e-6, _rel(xf[:n], ref)
-    assert torch.equal(xd.cpu(), x * window)
 
 
 @pytest.mark.parametrize("score_seams", [False, True])

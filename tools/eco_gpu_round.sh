@@ -8,7 +8,7 @@ set -u
 cd "$(dirname "$0")/.."
 TAG=${1:-r03a}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_zz_eco_gpu.py tests/test_zz_gnsd_gpu.py -q 2>&1 | tail -15 > gpurun_out/${TAG}_eco_gpu_tests.txt; cat gpurun_out/${TAG}_eco_gpu_tests.txt
+timeout 600 python -m pytest tests/test_zz_eco_gpu.py tests/test_zy_gnsd_gpu.py -q 2>&1 | tail -15 > gpurun_out/${TAG}_eco_gpu_tests.txt; cat gpurun_out/${TAG}_eco_gpu_tests.txt
 timeout 300 python tools/eco_bench.py --json gpurun_out/${TAG}_eco_bench.json 2>&1 | tail -6
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_eco_launches.csv \
     python tools/eco_bench.py --json /dev/null > gpurun_out/${TAG}_eco_ncu_launches.log 2>&1
