@@ -2,7 +2,9 @@
 // eco_joint_kernel.cuh (first-frame GaussNewtonCG on FactorizedConvProblem); design notes in the headers.
 //   reference: pytracking/tracker/eco/optim.py:8-208, pytracking/libs/optimization.py:72-163, 328-421.
 #include "common.cuh"
+#include "launch.cuh"
 
+#ifndef B200_CPU_EMUL      // the CPU test tier has its own (pthread) barrier under the same name
 namespace b200trk {
 
 // grid_barrier (common.cuh) with a bounded wait: if the other CTAs never arrive (which a cooperative launch rules out) the poll gives
@@ -23,6 +25,7 @@ __device__ __forceinline__ void eco_grid_barrier(unsigned* counter, unsigned& ep
 }
 
 }  // namespace b200trk
+#endif
 
 #include "eco_cg_kernel.cuh"
 #include "eco_joint_kernel.cuh"
@@ -31,10 +34,7 @@ namespace b200trk {
 
 template <int G, int CPL>
 static int launch_eco(const EcoPlan& pl, EcoParams& P, cudaStream_t st) {
-    auto kern = eco_cg_kernel<G, CPL>;
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-    void* args[] = {(void*)&P};
-    B200_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(pl.grid), dim3(pl.block), args, pl.smem_bytes, st));
+    if (int e = b200_launch_cooperative(eco_cg_kernel<G, CPL>, pl.grid, pl.block, pl.smem_bytes, st, P)) return e;
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
@@ -117,10 +117,7 @@ extern "C" int b200trk_eco_joint_gn(float* filter, float* proj, const float* sam
     P.dots = (float*)(ws + pl.off_dots);
     P.res_slabs = pl.res_slabs; P.npx_max = pl.npx_max; P.EPB = pl.EPB; P.SPL = pl.SPL; P.stage_pm = pl.stage_pm; P.wide = pl.wide;
     B200_CHECK_CUDA(cudaMemsetAsync(P.barrier, 0, 256, st));
-    auto kern = eco_joint_kernel;
-    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-    void* args[] = {(void*)&P};
-    B200_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(pl.grid), dim3(pl.block), args, pl.smem_bytes, st));
+    if (int e = b200_launch_cooperative(eco_joint_kernel, pl.grid, pl.block, pl.smem_bytes, st, P)) return e;
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }

@@ -1,6 +1,7 @@
 // ECO's score computation in the Fourier domain: ECO.apply_filter and the sum_fs -> sample_fs chain of ECO.localize_target
 // (pytracking/tracker/eco/eco.py:244-252; pytracking/libs/fourier.py:35-61, 95-114).  Kernels and their derivation: eco_loc_kernels.cuh.
 #include "common.cuh"
+#include "launch.cuh"
 #include "eco_loc_kernels.cuh"
 
 using namespace b200trk;
@@ -11,7 +12,8 @@ extern "C" int b200trk_eco_apply_filter(const float* filter, const float* sample
     B200_REQUIRE(S > 0 && C > 0 && H > 0 && Wh > 0 && (long long)S * H * Wh < (1ll << 30), "eco_apply_filter: S=%d C=%d H=%d Wh=%d", S, C, H, Wh);
     B200_REQUIRE((((uintptr_t)filter | (uintptr_t)sample_xf | (uintptr_t)sf) & 7) == 0, "eco_apply_filter: complex tensors must be 8-byte aligned");
     const int total = S * H * Wh;
-    eco_apply_filter_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const float2*)filter, (const float2*)sample_xf, (float2*)sf, S, C, H * Wh);
+    B200_LAUNCH_KERNEL(eco_apply_filter_kernel, (total + 127) / 128, 1, 128, 0, (cudaStream_t)stream, (const float2*)filter, (const float2*)sample_xf,
+                       (float2*)sf, S, C, H * Wh);
     B200_LAUNCH_CHECK();
     return 0;
 }
@@ -26,7 +28,7 @@ extern "C" int b200trk_eco_sample_fs(const float* const* sf_blocks, const int* H
     const size_t smem = eco_sample_fs_smem_floats(P.H[0], P.Wh[0], out_h, out_w) * sizeof(float);
     B200_REQUIRE(smem <= 200 * 1024, "eco_sample_fs: %zu bytes of shared memory", smem);
     B200_CHECK_CUDA(cudaFuncSetAttribute(eco_sample_fs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    eco_sample_fs_kernel<<<dim3((out_h + EL_ROWS - 1) / EL_ROWS, S), 256, smem, (cudaStream_t)stream>>>(P);
+    B200_LAUNCH_KERNEL(eco_sample_fs_kernel, (out_h + EL_ROWS - 1) / EL_ROWS, S, 256, smem, (cudaStream_t)stream, P);
     B200_LAUNCH_CHECK();
     return 0;
 }
@@ -41,8 +43,8 @@ extern "C" int b200trk_eco_preprocess_sample(float* x, long long stride_s, long 
     const size_t smem = eco_preprocess_smem_floats(H, W) * sizeof(float);
     B200_REQUIRE(smem <= 200 * 1024, "eco_preprocess_sample: a %dx%d feature map needs %zu bytes of shared memory", H, W, smem);
     B200_CHECK_CUDA(cudaFuncSetAttribute(eco_preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    eco_preprocess_kernel<<<S * C, 256, smem, (cudaStream_t)stream>>>(x, window, (const float2*)interp_y, (const float2*)interp_x, (float2*)xf, C, H, W,
-                                                                               stride_s, stride_c, stride_y, stride_x);
+    B200_LAUNCH_KERNEL(eco_preprocess_kernel, S * C, 1, 256, smem, (cudaStream_t)stream, x, window, (const float2*)interp_y, (const float2*)interp_x,
+                       (float2*)xf, C, H, W, stride_s, stride_c, stride_y, stride_x);
     B200_LAUNCH_CHECK();
     return 0;
 }

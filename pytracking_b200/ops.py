@@ -13,7 +13,7 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _dev(t, name):
+def _dev(t, name, contiguous=True):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise RuntimeError("b200trk: '%s' must be a CUDA tensor (the engine has no CPU path)" % name)
     if t.dtype != torch.float32:
@@ -22,7 +22,7 @@ def _dev(t, name):
         # the library's stream, scratch buffers and SM count belong to the CURRENT device (cudaGetDevice)
         raise RuntimeError("b200trk: '%s' lives on %s but the current device is cuda:%d; wrap the call in torch.cuda.device(%r)"
                            % (name, t.device, torch.cuda.current_device(), str(t.device)))
-    return t.contiguous()
+    return t.contiguous() if contiguous else t
 
 
 def _p(t):
@@ -334,10 +334,9 @@ def eco_sample_fs(sf_blocks, output_sz, weights=None):
 def eco_preprocess_sample_(x, window, interp_y, interp_x):
     """ECO.preprocess_sample for one feature block (eco.py:297-300): windows `x` [S,C,H,W] (any strides) IN PLACE (as the reference does) and returns
     interpolate_dft(cfft2(x), (interp_y, interp_x)) [S,C,H',Wh',2]."""
-    if not isinstance(x, torch.Tensor) or not x.is_cuda or x.dtype != torch.float32 or x.dim() != 4 or min(x.stride()) < 0:
-        raise RuntimeError("b200trk.eco_preprocess_sample_: x must be a CUDA float32 [S,C,H,W] tensor or view (windowed in place)")
-    if torch.cuda.current_device() != x.device.index:
-        raise RuntimeError("b200trk.eco_preprocess_sample_: x lives on %s but the current device is cuda:%d" % (x.device, torch.cuda.current_device()))
+    x = _dev(x, "x", contiguous=False)                              # windowed in place: the caller's tensor or view, through its strides
+    if x.dim() != 4 or min(x.stride()) < 0:
+        raise RuntimeError("b200trk.eco_preprocess_sample_: x must be a [S,C,H,W] tensor or view with non-negative strides")
     window, interp_y, interp_x = _dev(window, "window"), _dev(interp_y, "interp_y"), _dev(interp_x, "interp_x")
     s, c, h, w = x.shape
     hp, whp = h + (h + 1) % 2, w // 2 + 1

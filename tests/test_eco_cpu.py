@@ -398,67 +398,8 @@ def test_emulated_joint_kernel_at_real_per_cta_sizes(emul, h, wh, n, cin, c, cta
     assert _rel(hf, ref[0].numpy()) < 1e-5 and _rel(Pn, ref[1].numpy()) < 1e-5, (list(plan), _rel(hf, ref[0].numpy()), _rel(Pn, ref[1].numpy()))
 
 
-# ---- the WHOLE launch of a B200 on the CPU ------------------------------------------------------------------------------------------
-# -DB200_EMUL_COOP_FIBERS: a block = one OS thread, its 256 threads = fibers, the grid barrier as on the device.  The launch plan a B200
-# derives (148 CTAs, 256 threads, resident/streamed slabs) at the sizes of parameter/eco/default.py -- the same inputs, oracle and bounds
-# as tests/test_zz_eco_gpu.py's full-size cases, whose GPU run the round's budget did not reach.
-@pytest.fixture(scope="module")
-def emul_coop(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("no g++")
-    out = os.path.join(str(tmp_path_factory.mktemp("eco_coop")), "libeco_coop.so")
-    # -fsanitize=alignment (recovering mode: a report on stderr, checked by the tests through capfd): the float2 / float4 accesses of the
-    # kernels must be 8 / 16-byte aligned for the shared-memory carving of THESE sizes -- on the device a misaligned one is a fault
-    cmd = ["g++", "-std=c++17", "-O2", "-g", "-pthread", "-shared", "-fPIC", "-fno-gnu-unique", "-Wno-unknown-pragmas", "-DB200_EMUL_COOP_FIBERS",
-           "-fsanitize=alignment", os.path.join(ROOT, "tests", "cpu_emul", "eco_emul.cpp"), "-o", out]
-    if subprocess.run(cmd, capture_output=True).returncode != 0:                      # no UBSan runtime here: the same build without the check
-        cmd.remove("-fsanitize=alignment")
-        subprocess.run(cmd, check=True, capture_output=True)
-    return C.CDLL(out)
-
-
-@pytest.mark.parametrize("h,wh,n,c,stored,grid", [(15, 8, 200, 64, 200, 120), (63, 32, 200, 16, 200, 148), (17, 9, 200, 32, 37, 148),
-                                                   (13, 7, 50, 128, 50, 91)])
-def test_full_b200_launch_of_the_online_kernel_at_eco_default_sizes(emul_coop, capfd, h, wh, n, c, stored, grid):
-    samples, sw, yf, reg, hf0, new_xf = _synthetic_block(h, wh, n, c, stored, seed=h * 100 + c)
-    dff = (1 - 0.0075) ** 75
-    kw = dict(precond_learning_rate=0.0075, precond_data_param=0.3, precond_reg_param=0.15, fletcher_reeves=False, standard_alpha=True,
-              direction_forget_factor=dff)
-    x, en, st = hf0.double(), None, {}
-    for r in range(2):
-        x, en, st = E.filter_optim_run(x, samples.double(), yf.double(), sw.double(), reg.double(), en, st, 5, new_xf[r].double(), **kw)
-    P = lambda a: a.ctypes.data_as(C.c_void_p)
-    hf, ene = hf0.numpy().copy(), np.full((1, c, h, wh), np.nan, np.float32)
-    p, rp, rho = np.full_like(hf, np.nan), np.full_like(hf, np.nan), np.full(1, np.nan, np.float32)
-    plan = (C.c_int * 6)()
-    for r in range(2):
-        rc = emul_coop.eco_emul_filter_cg(P(hf), P(samples.numpy()), P(yf.numpy()), P(sw.numpy()), P(reg.numpy()), 5, 5, P(ene), int(r > 0),
-                                          P(new_xf[r].numpy()), P(p), P(rp), P(rho), int(r > 0), h, wh, n, c, 5, 0, 1, C.c_float(dff),
-                                          C.c_float(0.0075), C.c_float(0.3), C.c_float(0.15), 148, 256, -1, plan)
-        assert rc == 0
-    assert plan[0] == grid
-    assert "runtime error" not in capfd.readouterr().err
-    assert _rel(hf, x.numpy()) < 1e-5 and _rel(p, st["p"].numpy()) < 5e-5 and _rel(ene, en.numpy()) < 1e-5, (list(plan), _rel(hf, x.numpy()))
-
-
-@pytest.mark.parametrize("h,wh,n,cin,c,grid", [(15, 8, 30, 256, 64, 120), (63, 32, 30, 96, 16, 148), (11, 6, 9, 40, 32, 66)])
-def test_full_b200_launch_of_the_joint_kernel_at_eco_default_sizes(emul_coop, capfd, h, wh, n, cin, c, grid):
-    g = torch.Generator().manual_seed(h * 7 + c)
-    samples = torch.randn(h, wh, n, cin, 2, generator=g)
-    P0 = torch.linalg.qr(torch.randn(cin, cin, generator=g))[0][:, :c].contiguous()
-    _, _, yf, reg, _, _ = _synthetic_block(h, wh, 2, 16, 2, seed=3)
-    sw = torch.full((n,), 1.0 / n)
-    hf0 = torch.zeros(1, c, h, wh, 2)
-    ref = E.joint_gn_run(hf0.double(), P0.double(), samples.double(), yf.double(), sw.double(), reg.double(), 5, 2)
-    dMh, dMP, _ = E.joint_precond(samples, P0, yf, reg, 0.3, 0.15, 35.0, 5e-8)
-    P = lambda a: a.ctypes.data_as(C.c_void_p)
-    hf, Pn, plan = hf0.numpy().copy(), P0.numpy().copy(), (C.c_int * 6)()
-    rc = emul_coop.eco_emul_joint_gn(P(hf), P(Pn), P(samples.numpy()), P(yf.numpy()), P(sw.sqrt().numpy()), P(reg.numpy()), 5, 5,
-                                     P(np.ascontiguousarray(dMh.reshape(1, c, h, wh).numpy())), C.c_float(float(dMP)), C.c_float(5e-8), h, wh, n, cin,
-                                     c, 5, 2, 148, 256, -1, plan)
-    assert rc == 0 and plan[0] == grid
-    assert "runtime error" not in capfd.readouterr().err
-    assert _rel(hf, ref[0].numpy()) < 1e-5 and _rel(Pn, ref[1].numpy()) < 1e-5, (list(plan), _rel(hf, ref[0].numpy()), _rel(Pn, ref[1].numpy()))
+# The WHOLE launch of a B200 (148 CTAs x 256 threads) at ECO's default sizes runs in tests/test_eco_gpu_file_on_cpu.py: the `-m gpu` test file
+# itself against the launchers' host code and these kernel sources.
 
 
 def test_eco_kernels_under_address_sanitizer(tmp_path):

@@ -252,7 +252,7 @@ def test_eco_preprocess_sample_at_eco_default_sizes_vs_oracle(s, c, hw):
     iy, ix = torch.randn(1, 1, hp, 1, 2, generator=g) / hw, torch.randn(1, 1, 1, whp, 2, generator=g) / hw
     n = min(s, 3)                                                   # the float64 oracle on the first samples only
     ref, _ = E.preprocess_sample(x[:n].double(), window.double(), iy.double(), ix.double())
-    xd = x.cuda()
+    xd = x.clone().cuda()
     xf = ops.eco_preprocess_sample_(xd, window.cuda(), iy.cuda(), ix.cuda())
     assert _rel(xf[:n], ref) < 5e-6, _rel(xf[:n], ref)
     assert torch.equal(xd.cpu(), x * window)
