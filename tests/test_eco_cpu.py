@@ -334,70 +334,6 @@ def test_joint_launch_plan_at_eco_block_sizes(emul):
         assert (227 * 1024 - 1024 - fixed) // slab >= 1                # at least one coefficient's slab resident per CTA
 
 
-# ---- the per-CTA configurations of ECO's real block sizes, on small grids ---------------------------------------------------------------
-def _synthetic_block(h, wh, n, c, stored, seed, reg3=False):
-    g = torch.Generator().manual_seed(seed)
-    samples = torch.zeros(h, wh, n, c, 2)
-    samples[:, :, :stored] = torch.randn(h, wh, stored, c, 2, generator=g)
-    sw = torch.zeros(n)
-    sw[:stored] = torch.rand(stored, generator=g) + 0.1
-    sw /= sw.sum()
-    ky = torch.arange(-(h - 1) // 2, h // 2 + 1, dtype=torch.float32).view(-1, 1)
-    kx = torch.arange(0, wh, dtype=torch.float32).view(1, -1)
-    yf = torch.exp(-0.05 * (ky ** 2 + kx ** 2)).view(1, 1, h, wh)
-    reg = torch.tensor([[0.0, 0.02, 0.05, 0.02, 0.0], [0.02, 0.1, 0.2, 0.1, 0.02], [0.05, 0.2, 0.9, 0.2, 0.05],
-                        [0.02, 0.1, 0.2, 0.1, 0.02], [0.0, 0.02, 0.05, 0.02, 0.0]]).view(1, 1, 5, 5)
-    if reg3:                                                      # lets the half spectrum be as small as 3 x 3 (few emulating threads)
-        reg = torch.tensor([[0.0, 0.23, 0.0], [0.16, 0.78, 0.16], [0.0, 0.23, 0.0]]).view(1, 1, 3, 3)
-    return samples, sw, yf, reg, 0.01 * torch.randn(1, c, h, wh, 2, generator=g), [torch.randn(1, c, h, wh, 2, generator=g) for _ in range(2)]
-
-
-# (H, Wh, memory, channels, stored, CTAs): what ONE CTA does at ECO's default sizes -- deep block: one resident 200 x 64 slab, eight warps
-# per slab; shallow block: 14 coefficients per CTA, 8 slabs resident + 6 streamed, 16 half-warp groups; 128 channels: 4 per lane
-@pytest.mark.parametrize("h,wh,n,c,stored,ctas", [(3, 3, 200, 64, 200, 9), (7, 8, 200, 16, 150, 4), (3, 3, 60, 128, 60, 9)])
-def test_emulated_kernel_at_real_per_cta_sizes(emul, h, wh, n, c, stored, ctas):
-    samples, sw, yf, reg, hf0, new_xf = _synthetic_block(h, wh, n, c, stored, seed=h * 100 + c, reg3=(wh < 5))
-    rk = reg.shape[-1]
-    dff = (1 - 0.0075) ** 75
-    kw = dict(precond_learning_rate=0.0075, precond_data_param=0.3, precond_reg_param=0.15, fletcher_reeves=False, standard_alpha=True,
-              direction_forget_factor=dff)
-    x, en, st = hf0.double(), None, {}
-    for r in range(2):
-        x, en, st = E.filter_optim_run(x, samples.double(), yf.double(), sw.double(), reg.double(), en, st, 5, new_xf[r].double(), **kw)
-    P = lambda a: a.ctypes.data_as(C.c_void_p)
-    hf, ene = hf0.numpy().copy(), np.full((1, c, h, wh), np.nan, np.float32)
-    p, rp, rho = np.full_like(hf, np.nan), np.full_like(hf, np.nan), np.full(1, np.nan, np.float32)
-    plan = (C.c_int * 6)()
-    for r in range(2):
-        rc = emul.eco_emul_filter_cg(P(hf), P(samples.numpy()), P(yf.numpy()), P(sw.numpy()), P(reg.numpy()), rk, rk, P(ene), int(r > 0),
-                                     P(new_xf[r].numpy()), P(p), P(rp), P(rho), int(r > 0), h, wh, n, c, 5, 0, 1, C.c_float(dff),
-                                     C.c_float(0.0075), C.c_float(0.3), C.c_float(0.15), ctas, 256, -1, plan)
-        assert rc == 0
-    assert _rel(hf, x.numpy()) < 1e-5 and _rel(p, st["p"].numpy()) < 5e-5 and _rel(ene, en.numpy()) < 1e-5, (list(plan), _rel(hf, x.numpy()))
-
-
-# first frame: 30 augmented samples; deep 256 -> 64 (one resident slab per CTA), shallow 96 -> 16 (14 coefficients per CTA, 9 resident);
-# more than 32 samples (two rows per lane)
-@pytest.mark.parametrize("h,wh,n,cin,c,ctas", [(3, 3, 30, 256, 64, 9), (7, 8, 30, 96, 16, 4), (5, 5, 40, 64, 32, 3)])
-def test_emulated_joint_kernel_at_real_per_cta_sizes(emul, h, wh, n, cin, c, ctas):
-    g = torch.Generator().manual_seed(h * 7 + c)
-    samples = torch.randn(h, wh, n, cin, 2, generator=g)
-    P0 = torch.linalg.qr(torch.randn(cin, cin, generator=g))[0][:, :c].contiguous()
-    _, _, yf, reg, _, _ = _synthetic_block(h, wh, 2, 16, 2, seed=3, reg3=(wh < 5))
-    rk = reg.shape[-1]
-    sw = torch.full((n,), 1.0 / n)
-    hf0 = torch.zeros(1, c, h, wh, 2)
-    ref = E.joint_gn_run(hf0.double(), P0.double(), samples.double(), yf.double(), sw.double(), reg.double(), 5, 2)
-    dMh, dMP, _ = E.joint_precond(samples, P0, yf, reg, 0.3, 0.15, 35.0, 5e-8)
-    P = lambda a: a.ctypes.data_as(C.c_void_p)
-    hf, Pn, plan = hf0.numpy().copy(), P0.numpy().copy(), (C.c_int * 6)()
-    rc = emul.eco_emul_joint_gn(P(hf), P(Pn), P(samples.numpy()), P(yf.numpy()), P(sw.sqrt().numpy()), P(reg.numpy()), rk, rk,
-                                P(np.ascontiguousarray(dMh.reshape(1, c, h, wh).numpy())), C.c_float(float(dMP)), C.c_float(5e-8), h, wh, n, cin, c,
-                                5, 2, ctas, 256, -1, plan)
-    assert rc == 0
-    assert _rel(hf, ref[0].numpy()) < 1e-5 and _rel(Pn, ref[1].numpy()) < 1e-5, (list(plan), _rel(hf, ref[0].numpy()), _rel(Pn, ref[1].numpy()))
-
-
 # The WHOLE launch of a B200 (148 CTAs x 256 threads) at ECO's default sizes runs in tests/test_eco_gpu_file_on_cpu.py: the `-m gpu` test file
 # itself against the launchers' host code and these kernel sources.
 
