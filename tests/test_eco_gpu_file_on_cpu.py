@@ -4,7 +4,8 @@ tests/cpu_emul/eco_abi_emul.cpp (the launchers csrc/eco_cg.cu and csrc/eco_loc.c
 SIMT shim with the 148-CTA launch of a B200) in place of libb200trk.so.  The same test code, `ops` wrappers, ctypes signatures, plug-in
 seams, launch plans and kernels as on the device; what differs is who executes the kernels.  The two tracker-level tests (the unmodified
 reference ECO tracker over 12 frames, stock vs above the engine; the plugin builds it on the CPU) take three more minutes and run only
-with B200_ECO_TRACKER_ON_CPU=1; their recorded run is profiles/r02zc_eco_gpu_test_file_on_cpu.txt."""
+with B200_ECO_TRACKER_ON_CPU=1, as do the two slowest full-size cases of the online kernel (the 63x32x200x16 block with streamed slabs:
+a minute of emulation); the recorded run of all 40 is profiles/r02zc_eco_gpu_test_file_on_cpu.txt."""
 import os
 import shutil
 import subprocess
@@ -30,10 +31,10 @@ def test_eco_gpu_test_file_runs_on_the_cpu_against_launchers_and_kernel_sources(
     env = dict(os.environ, B200_ECO_ABI_EMUL=lib, B200_EMUL_SMS="148",
                PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests", "cpu_emul"), ROOT, os.environ.get("PYTHONPATH", "")]))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_zz_eco_gpu.py"), "-p", "gpu_file_on_cpu_plugin", "-q", "-x",
-                        "-p", "no:cacheprovider", "-s"] + ([] if FULL else ["-k", "not tracker"]), capture_output=True, text=True, env=env, cwd=ROOT, timeout=3000)
+                        "-p", "no:cacheprovider", "-s"] + ([] if FULL else ["-k", "not tracker and not 63-32-200-16-200 and not 17-9-200-32-37"]), capture_output=True, text=True, env=env, cwd=ROOT, timeout=3000)
     tail = r.stdout[-3000:] + r.stderr[-1500:]
     assert r.returncode == 0, tail
     assert "runtime error" not in r.stderr and "runtime error" not in r.stdout, tail
     assert " passed" in r.stdout and "failed" not in r.stdout, tail
     n = int(r.stdout.strip().split("\n")[-1].split(" passed")[0].split()[-1])
-    assert n >= (40 if FULL else 38), tail                                            # 13 golden runs of the online kernel + everything that had not run on a B200
+    assert n >= (40 if FULL else 36), tail                                            # 13 golden runs of the online kernel + everything that had not run on a B200
