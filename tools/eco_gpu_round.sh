@@ -12,7 +12,7 @@ timeout 600 python -m pytest tests/test_zz_eco_gpu.py tests/test_zy_gnsd_gpu.py 
 timeout 300 python tools/eco_bench.py --json gpurun_out/${TAG}_eco_bench.json 2>&1 | tail -6
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_eco_launches.csv \
     python tools/eco_bench.py --json /dev/null > gpurun_out/${TAG}_eco_ncu_launches.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k "regex:eco_cg_kernel|eco_joint_kernel" -s 8 -c 4 -o gpurun_out/${TAG}_eco -f \
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:eco_cg_kernel|eco_joint_kernel|eco_sample_fs_kernel|eco_preprocess_kernel|eco_apply_filter_kernel" -s 8 -c 12 -o gpurun_out/${TAG}_eco -f \
     python tools/eco_bench.py --json /dev/null > gpurun_out/${TAG}_eco_ncu_full.log 2>&1
 ncu -i gpurun_out/${TAG}_eco.ncu-rep --page raw --csv > gpurun_out/${TAG}_eco_raw.csv 2>/dev/null
 rm -f gpurun_out/${TAG}_eco.ncu-rep
