@@ -214,6 +214,10 @@ int b200trk_eco_preprocess_sample(float* x, long long stride_s, long long stride
                                   const float* window, const float* interp_y, const float* interp_x, float* xf, int S, int C,
                                   int H, int W, b200trk_stream_t stream);
 
+/* fourier.shift_fs (pytracking/libs/fourier.py:78-92) as ECO.track / ECO.initialize call it (eco.py:119-127, 226-227):
+ * out = (a * exp(i shift_y ky)) * exp(i shift_x kx) on a centred half spectrum a [S,C,H,Wh,2] (H odd); out may not alias a.           */
+int b200trk_eco_shift_fs(const float* a, float* out, int S, int C, int H, int Wh, float shift_y, float shift_x, b200trk_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Stage 1 -- backbone + classification head
  * ---------------------------------------------------------------------------------------------- */

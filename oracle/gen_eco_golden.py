@@ -240,8 +240,30 @@ def prep():
                                                                    [tuple(e.shape) for e in xf]))
 
 
+SHIFT_CASES = {"small": dict(shape=(2, 3, 7, 4), shift=(0.3, -1.1)), "large": dict(shape=(1, 5, 11, 6), shift=(-2.9, 3.0)),
+               "one_axis": dict(shape=(3, 2, 5, 3), shift=(0.0, 0.7))}
+
+
+def shift():
+    """fourier.shift_fs (fourier.py:78-92) as ECO.track / ECO.initialize call it (eco.py:119-127, 226-227).  Writes tests/golden/eco_shift.npz."""
+    from oracle import ref_shims
+    ref_shims.install()
+    from pytracking import fourier
+    out = {}
+    g = torch.Generator().manual_seed(5)
+    for name, c in SHIFT_CASES.items():
+        a = torch.randn(*c["shape"], 2, generator=g)
+        out[name + "/a"] = a.numpy()
+        out[name + "/shift"] = np.array(c["shift"], np.float64)
+        out[name + "/out"] = fourier.shift_fs(a, shift=torch.Tensor(list(c["shift"]))).numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "eco_shift.npz"), **out)
+    print("wrote eco_shift.npz: %d arrays" % len(out))
+
+
 if __name__ == "__main__":
-    if "loc" in sys.argv[1:] or "prep" in sys.argv[1:]:
+    if "shift" in sys.argv[1:]:
+        shift()
+    elif "loc" in sys.argv[1:] or "prep" in sys.argv[1:]:
         if "loc" in sys.argv[1:]:
             loc()
         if "prep" in sys.argv[1:]:
@@ -251,3 +273,4 @@ if __name__ == "__main__":
         joint()
         loc()
         prep()
+        shift()

@@ -109,6 +109,7 @@ SIGNATURES = {
     "b200trk_eco_apply_filter": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "b200trk_eco_sample_fs": (_I, [C.POINTER(_VP), C.POINTER(_I), C.POINTER(_I), C.POINTER(_F), _I, _I, _I, _I, _VP, _VP]),
     "b200trk_eco_preprocess_sample": (_I, [_VP, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
+    "b200trk_eco_shift_fs": (_I, [_VP, _VP, _I, _I, _I, _I, _F, _F, _VP]),
     "b200trk_net_create": (_I, [C.POINTER(_VP), _I, C.POINTER(ConvDesc), _I, _F, _I, _I, _I, _I]),
     "b200trk_net_destroy": (_I, [_VP]),
     "b200trk_net_forward": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _VP]),

@@ -48,3 +48,14 @@ extern "C" int b200trk_eco_preprocess_sample(float* x, long long stride_s, long 
     B200_LAUNCH_CHECK();
     return 0;
 }
+
+extern "C" int b200trk_eco_shift_fs(const float* a, float* out, int S, int C, int H, int Wh, float shift_y, float shift_x, b200trk_stream_t stream) {
+    B200_REQUIRE(a && out, "eco_shift_fs: null pointer");
+    B200_REQUIRE(S > 0 && C > 0 && H > 0 && H % 2 == 1 && Wh > 0, "eco_shift_fs: S=%d C=%d H=%d Wh=%d (a centred half spectrum has an odd number of rows)", S, C, H, Wh);
+    B200_REQUIRE((((uintptr_t)a | (uintptr_t)out) & 7) == 0, "eco_shift_fs: complex tensors must be 8-byte aligned");
+    const long long total = (long long)S * C * H * Wh;
+    B200_REQUIRE(total < (1ll << 38), "eco_shift_fs: %lld coefficients", total);
+    B200_LAUNCH_KERNEL(eco_shift_fs_kernel, (total + 255) / 256, 1, 256, 0, (cudaStream_t)stream, (const float2*)a, (float2*)out, total, H, Wh, shift_y, shift_x);
+    B200_LAUNCH_CHECK();
+    return 0;
+}

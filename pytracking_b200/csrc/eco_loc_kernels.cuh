@@ -203,4 +203,17 @@ __global__ void __launch_bounds__(256) eco_preprocess_kernel(float* __restrict__
     }
 }
 
+// ---- fourier.shift_fs (fourier.py:78-92): out = (a * e^{i shift_y ky}) * e^{i shift_x kx}, one thread per coefficient; the phases formed as the
+// reference forms them (the shift as a float times the float frequency), the two complex products in its order
+__global__ void eco_shift_fs_kernel(const float2* __restrict__ a, float2* __restrict__ out, long long total, int H, int Wh, float sy, float sx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int kx = (int)(i % Wh), q = (int)((i / Wh) % H);
+    const float py = sy * (float)(q - (H - 1) / 2), px = sx * (float)kx;
+    const float cy = cosf(py), sny = sinf(py), cx = cosf(px), snx = sinf(px);
+    const float2 v = a[i];
+    const float r1 = v.x * cy - v.y * sny, i1 = v.x * sny + v.y * cy;
+    out[i] = make_float2(r1 * cx - i1 * snx, r1 * snx + i1 * cx);
+}
+
 }  // namespace b200trk

@@ -351,6 +351,17 @@ def eco_preprocess_sample_(x, window, interp_y, interp_x):
     return xf
 
 
+def eco_shift_fs(a, shift_y, shift_x):
+    """fourier.shift_fs (fourier.py:78-92): the centred half spectrum a [S,C,H,Wh,2] shifted by (shift_y, shift_x) radians per frequency."""
+    a = _dev(a, "a")
+    if a.dim() != 5 or a.shape[-1] != 2:
+        raise RuntimeError("b200trk.eco_shift_fs: a must be the Fourier coefficients [S,C,H,Wh,2], got %s" % (tuple(a.shape),))
+    s, c, h, wh, _ = a.shape
+    out = torch.empty_like(a)
+    _lib.check(_lib.lib().b200trk_eco_shift_fs(_p(a), _p(out), s, c, h, wh, float(shift_y), float(shift_x), _stream()), "eco_shift_fs")
+    return out
+
+
 def atom_gn_joint_(filt, proj, samples, y, sample_weight, filter_reg, projection_reg, num_cg_iter, num_gn_iter,
                    activation="mlu", act_param=0.05, fletcher_reeves=True):
     """GaussNewtonCG.run(num_cg_iter, num_gn_iter) on FactorizedConvProblem; updates `filt` and `proj` in place."""

@@ -959,6 +959,17 @@ def install(max_batch=16, precision=0, skip=()):
                         _count("fourier.sample_fs[eco]")
                         return ops.eco_sample_fs(a.contiguous(), (oh, ow))
                 return ref_fourier.sample_fs(a, grid_sz, rescale)
+            @staticmethod
+            def shift_fs(a, shift):
+                if isinstance(a, (list, tuple)) and not isinstance(a, torch.Tensor):                 # @tensor_operation: element-wise over a TensorList
+                    return type(a)([_EcoFourier.shift_fs(e, shift) for e in a])
+                if isinstance(a, torch.Tensor) and _inference(a) and a.dim() == 5 and a.shape[-1] == 2 and a.shape[2] % 2 == 1 and a.numel() > 0:
+                    sy, sx = float(shift[0]), float(shift[1])
+                    if sy == 0 and sx == 0:
+                        return a                                                                    # fourier.py:86-87
+                    _count("fourier.shift_fs[eco]")
+                    return ops.eco_shift_fs(a.contiguous(), sy, sx)
+                return ref_fourier.shift_fs(a, shift)
         _bind(em, "fourier", _EcoFourier())
 
     # ---- 6. ToMP: ltr/models/transformer/transformer.py:90-96 ----

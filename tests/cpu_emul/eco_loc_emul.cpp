@@ -31,3 +31,9 @@ extern "C" int eco_loc_emul_preprocess(float* x, long long st_s, long long st_c,
                             st_y, st_x);
     return 0;
 }
+
+extern "C" int eco_loc_emul_shift_fs(const float* a, float* out, int S, int C, int H, int Wh, float sy, float sx) {
+    const long long total = (long long)S * C * H * Wh;
+    cpu_emul::launch_blocks(eco_shift_fs_kernel, (unsigned)((total + 255) / 256), 1u, 1u, 256u, 0, (const float2*)a, (float2*)out, total, H, Wh, sy, sx);
+    return 0;
+}

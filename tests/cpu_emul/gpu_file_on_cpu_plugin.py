@@ -9,7 +9,8 @@ import os
 
 import torch
 
-ECO = ("b200trk_eco_filter_cg", "b200trk_eco_joint_gn", "b200trk_eco_apply_filter", "b200trk_eco_sample_fs", "b200trk_eco_preprocess_sample")
+ECO = ("b200trk_eco_filter_cg", "b200trk_eco_joint_gn", "b200trk_eco_apply_filter", "b200trk_eco_sample_fs", "b200trk_eco_preprocess_sample",
+       "b200trk_eco_shift_fs")
 
 
 class _Handle:

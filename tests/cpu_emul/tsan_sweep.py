@@ -89,5 +89,7 @@ iy, ix, xo = f32(1, 1, 7, 1, 2), f32(1, 1, 1, 5, 2), np.zeros((2, 3, 7, 5, 2), n
 st = [C.c_longlong(v // 4) for v in xv.strides]
 assert L.eco_loc_emul_preprocess(C.c_void_p(xv.transpose(2, 3, 0, 1).ctypes.data), st[0], st[1], st[2], st[3], P(win), P(iy), P(ix), P(xo), 2, 3, 6, 8) == 0
 assert np.isfinite(xo).all()
+ash, osh = f32(2, 3, 7, 4, 2), np.zeros((2, 3, 7, 4, 2), np.float32)
+assert L.eco_loc_emul_shift_fs(P(ash), P(osh), 2, 3, 7, 4, C.c_float(0.3), C.c_float(-1.1)) == 0 and np.isfinite(osh).all()
 print("eco_loc ok")
 print("EMUL_DONE")

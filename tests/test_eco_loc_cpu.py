@@ -209,3 +209,16 @@ def test_emulated_preprocess_kernel_at_eco_default_sizes(emul, capfd, s, c, hw):
     xf, _ = _preprocess(emul, x.numpy(), window.numpy(), iy.numpy(), ix.numpy())
     assert "runtime error" not in capfd.readouterr().err
     assert _rel(xf, ref.numpy()) < 5e-6, _rel(xf, ref.numpy())
+
+
+# ---- fourier.shift_fs (fourier.py:78-92) ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["small", "large", "one_axis"])
+def test_shift_fs_oracle_and_emulated_kernel_match_reference_function(emul, name):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "eco_shift.npz"))
+    a, shift, ref = g[name + "/a"], g[name + "/shift"], g[name + "/out"]
+    assert np.array_equal(E.shift_fs(torch.from_numpy(a), shift).numpy(), ref)               # the float32 restatement: bit for bit
+    assert _rel(E.shift_fs(torch.from_numpy(a).double(), shift).numpy(), ref) < 2e-6
+    out = np.full_like(a, np.nan)
+    s, c, h, wh, _ = a.shape
+    assert emul.eco_loc_emul_shift_fs(P(a), P(out), s, c, h, wh, C.c_float(shift[0]), C.c_float(shift[1])) == 0
+    assert _rel(out, ref) < 1e-6, _rel(out, ref)

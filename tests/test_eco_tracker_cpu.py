@@ -1,7 +1,7 @@
 """The UNMODIFIED reference ECO tracker (pytracking/tracker/eco/eco.py, parameter/eco/default.py, seeded random-init ResNet18m1 features)
 driven on the CPU over the synthetic sequence, once as it is and once with `plugin.install()` binding its two optimiser seams
-(`GaussNewtonCG.run` on the first frame, `FilterOptim.run` every `train_skipping` frames) and its three score-path seams (`ECO.preprocess_sample`,
-`ECO.apply_filter`, `fourier.sample_fs` as `ECO.localize_target` calls it).  There is no GPU here, so the two library entry
+(`GaussNewtonCG.run` on the first frame, `FilterOptim.run` every `train_skipping` frames) and its score-path seams (`ECO.preprocess_sample`,
+`ECO.apply_filter`, `fourier.sample_fs` as `ECO.localize_target` calls it, `fourier.shift_fs`).  There is no GPU here, so the two library entry
 points are replaced by the oracle (oracle/eco_oracle.py -- itself pinned to the reference's golden vectors, as is the CUDA kernel source
 under the CPU shim, tests/test_eco_cpu.py): what this test pins is everything ABOVE the C ABI inside a real tracker run -- the tensors the
 tracker actually hands over (permuted sample views, the column-major projection matrix out of torch.svd, one-element sample weights, the
@@ -36,7 +36,7 @@ def test_reference_eco_tracker_with_both_optimiser_seams_bound():
     from pytracking_b200 import ops, plugin, synth
     frames, bb = synth.make_sequence(0, num_frames=FRAMES)
     ref_boxes, ref_trk = _drive(frames, bb)
-    calls = {"cg": 0, "gn": 0, "apply": 0, "sample": 0, "prep": 0}
+    calls = {"cg": 0, "gn": 0, "apply": 0, "sample": 0, "prep": 0, "shift": 0}
 
     def oracle_cg(filt, samples, yf, sw, reg, energy, num_iter, new_xf=None, state=None, fletcher_reeves=False, standard_alpha=True,
                   direction_forget_factor=0.0, precond_learning_rate=0.0075, precond_data_param=0.3, precond_reg_param=0.15):
@@ -73,6 +73,11 @@ def test_reference_eco_tracker_with_both_optimiser_seams_bound():
         x.copy_(v)                                                  # the library windows its argument in place, as the reference does
         return xf
 
+    def oracle_shift(a, sy, sx):
+        calls["shift"] += 1
+        assert a.is_contiguous()
+        return E.shift_fs(a, (sy, sx))
+
     def oracle_sample(sf, out_sz, weights=None):
         calls["sample"] += 1
         return E.sample_fs(sf, out_sz)
@@ -80,6 +85,7 @@ def test_reference_eco_tracker_with_both_optimiser_seams_bound():
     with um.patch.object(ops, "eco_filter_cg_", oracle_cg), um.patch.object(ops, "eco_joint_gn_", oracle_gn), \
             um.patch.object(ops, "eco_apply_filter", oracle_apply), um.patch.object(ops, "eco_sample_fs", oracle_sample), \
             um.patch.object(ops, "eco_preprocess_sample_", oracle_prep), \
+            um.patch.object(ops, "eco_shift_fs", oracle_shift), \
             um.patch.object(plugin, "_inference", lambda *ts: all(isinstance(t, torch.Tensor) and t.dtype == torch.float32 for t in ts)), \
             um.patch.object(torch.Tensor, "is_cuda", property(lambda self: True)):
         plugin.install(skip=OTHER_SEAMS)
@@ -91,6 +97,8 @@ def test_reference_eco_tracker_with_both_optimiser_seams_bound():
     runs = sum(1 for f in range(2, FRAMES + 2) if f % OVERRIDES["train_skipping"] == 1)        # eco.py:244: frame_num % train_skipping == 1
     # two feature blocks per optimiser call and per ECO.apply_filter; one summed series per frame through sample_fs
     # preprocess_sample: two blocks on the first frame (the augmented samples) and on every tracked frame
+    shifts = calls.pop("shift")                                     # eco.py:119-127 (augmentation shifts, sub-pixel position) and :226-227
+    assert shifts >= 2 * FRAMES, shifts
     assert calls == {"gn": 2, "cg": 2 * runs, "apply": 2 * FRAMES, "sample": FRAMES, "prep": 2 * (FRAMES + 1)}, calls
     assert plugin.stats.get("GaussNewtonCG.run[eco]", 0) == served.get("GaussNewtonCG.run[eco]", 0) + 1
     assert plugin.stats.get("FilterOptim.run", 0) == served.get("FilterOptim.run", 0) + runs

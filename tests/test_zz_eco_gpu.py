@@ -222,6 +222,15 @@ def test_eco_score_kernels_at_eco_default_sizes_vs_oracle():
         ops.eco_sample_fs(torch.zeros(1, 1, 8, 5, 2).cuda(), (20, 20))   # a centred half spectrum has an odd number of rows
 
 
+@pytest.mark.parametrize("name", ["small", "large", "one_axis"])
+def test_eco_shift_fs_matches_reference_golden(name):
+    """Outputs of the unmodified fourier.shift_fs (oracle/gen_eco_golden.py shift)."""
+    from pytracking_b200 import ops
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eco_shift.npz"))
+    out = ops.eco_shift_fs(torch.from_numpy(g[name + "/a"]).cuda(), float(g[name + "/shift"][0]), float(g[name + "/shift"][1]))
+    assert _rel(out, g[name + "/out"]) < 1e-6, _rel(out, g[name + "/out"])
+
+
 @pytest.mark.parametrize("permuted", [False, True])
 @pytest.mark.parametrize("name", ["even", "odd", "rect"])
 def test_eco_preprocess_sample_matches_reference_golden(name, permuted):
