@@ -5,7 +5,7 @@ SIMT shim with the 148-CTA launch of a B200) in place of libb200trk.so.  The sam
 seams, launch plans and kernels as on the device; what differs is who executes the kernels.  The two tracker-level tests (the unmodified
 reference ECO tracker over 12 frames, stock vs above the engine; the plugin builds it on the CPU) take three more minutes and run only
 with B200_ECO_TRACKER_ON_CPU=1, as do the two slowest full-size cases of the online kernel (the 63x32x200x16 block with streamed slabs:
-a minute of emulation); the recorded run of all 40 is profiles/r02zc_eco_gpu_test_file_on_cpu.txt."""
+a minute of emulation); the recorded run of all 43 is profiles/r02zc_eco_gpu_test_file_on_cpu.txt."""
 import os
 import shutil
 import subprocess
