@@ -944,8 +944,9 @@ def install(max_batch=16, precision=0, skip=()):
         ref_fourier = em.fourier
 
         class _EcoFourier:
-            """`fourier` as the ECO module sees it: sample_fs of one summed series on a larger grid (eco.py:249-252) goes to the library,
-            every other name and every other call is the reference module's (other trackers keep theirs untouched)."""
+            """`fourier` as the ECO module sees it: sample_fs of one summed series on a larger grid (eco.py:249-252) and shift_fs
+            (eco.py:119-127, 226-227) go to the library, every other name and every call they do not claim is the reference module's
+            (other trackers keep theirs untouched)."""
             def __getattr__(self, name):
                 return getattr(ref_fourier, name)
 
@@ -959,6 +960,7 @@ def install(max_batch=16, precision=0, skip=()):
                         _count("fourier.sample_fs[eco]")
                         return ops.eco_sample_fs(a.contiguous(), (oh, ow))
                 return ref_fourier.sample_fs(a, grid_sz, rescale)
+
             @staticmethod
             def shift_fs(a, shift):
                 if isinstance(a, (list, tuple)) and not isinstance(a, torch.Tensor):                 # @tensor_operation: element-wise over a TensorList
